@@ -1,0 +1,371 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the read-depth hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale F]
+
+Workload (N=1 and every N): BASELINE.json configs[1] -- `cnvetti cmd coverage` (Fragments, 500 bp
+windows, --reference for GC) + `cmd normalize --normalization MedianGcBinned` on a synthetic 30x
+whole-genome sample (chr1-22 hg38 lengths, ~900 M reads).  One "step" = one pass of that path
+over the whole sample.  Multi-GPU: one process per GPU, each rank processes its own sample (the
+reference's only data parallelism is one coverage+normalize chain per input BAM,
+cnvetti/src/quick_wis_build_model.rs:148-184), no data-path collective => weak scaling.
+
+`value`  : reads/s, inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the public API with HOST (pinned) SoA buffers: H2D of all inputs and
+           D2H of the result table inside the timed region.
+`roofline`: dominant kernel frag_bin_gw_kernel, algorithmic 7 B/read (mid i32 + mapq u8 + flags
+           u16) over its CUDA-event time inside the timed steps.
+`cpu_baseline`: the oracle (restated reference CPU path) on a bounded sample, host cores stated.
+`--impl reference`: times that CPU path alone (the reference cannot be built here: no Rust).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WINDOW = 500
+MIN_MAPQ = 20
+READS_PER_BP = 900e6 / 2_875_001_522      # ~900 M reads over chr1-22
+BYTES_PER_READ_GW = 7                     # mid i32 + mapq u8 + flags u16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
+    ap.add_argument("--cpu-sample-contigs", type=int, default=4, help="last k contigs form the CPU sample")
+    return ap.parse_args()
+
+
+def contigs(scale):
+    from cnvetti_b200.synth import HG38_AUTOSOMES
+    return [("chr%d" % (i + 1), max(100_000, int(L * scale))) for i, L in enumerate(HG38_AUTOSOMES)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("frag_bin_gw_kernel")
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_leg(sample, steps, warmup):
+    """Times the oracle (restated reference CPU path) on the sample: coverage (Fragments,
+    genome-wide) + refstats + record assembly per contig, then MedianGcBinned over the sample's
+    windows.  Single thread: `cmd coverage` / `cmd normalize` are single-threaded in the
+    reference (regions are processed sequentially, lib-coverage/src/lib.rs:768)."""
+    import oracle
+    oracle.build()
+    oopts = oracle.cov_opts(window_length=WINDOW, min_mapq=MIN_MAPQ)
+    prepared = [(oracle.ReadBatch(d["pos"], d["isize"], d["flag"], d["mapq"], d["cigar_off"], d["cigar"]), L, seq)
+                for (d, L, seq) in sample]
+    n_reads = sum(p[0].n for p in prepared)
+
+    def one():
+        lcvs, gcs = [], []
+        for reads, L, seq in prepared:
+            counts, _, _ = oracle.frag_gw(reads, oopts, L)
+            cov, start, end, frm = oracle.frag_gw_stats(counts, oopts, L)
+            lcv, _, _ = oracle.cov_records(cov, None, start, end, frm, False, oopts)
+            gc, _ = oracle.refstats(seq, WINDOW)
+            lcvs.append(lcv)
+            gcs.append(gc)
+        return oracle.norm_gc_median(np.concatenate(lcvs), np.concatenate(gcs))
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return n_reads, dt
+
+
+def main():
+    args = parse_args()
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if args.impl == "reference" and rank != 0:
+        return 0  # rank 0 alone runs the CPU arm
+
+    if not torch.cuda.is_available():
+        if args.impl == "reference":
+            dev = None
+        else:
+            print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+            return 2
+    else:
+        torch.cuda.set_device(local_rank)
+        dev = "cuda:%d" % local_rank
+    if distributed and args.impl == "b200":
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import pipeline, synth, synth_torch
+
+    regs = contigs(args.scale)
+    n_pairs = [max(1000, int(round(L * READS_PER_BP / 2))) for _, L in regs]
+    workload = ("cfg2: cmd coverage (Fragments, %d bp windows, MAPQ>=%d, GC from reference) + normalize "
+                "MedianGcBinned, synthetic 30x WGS chr1-22" % (WINDOW, MIN_MAPQ))
+
+    # ---- reference arm: CPU only --------------------------------------------------------------
+    k = max(1, min(args.cpu_sample_contigs, len(regs)))
+    sample_ids = list(range(len(regs) - k, len(regs)))
+
+    def make_cpu_sample():
+        out = []
+        for ci in sample_ids:
+            L = regs[ci][1]
+            gdev = dev or "cpu"
+            soa = synth_torch.synth_soa_contig(2 * 1000 + ci + 7919 * rank, L, n_pairs[ci], gdev)
+            d = synth_torch.soa_to_oracle_records(soa)
+            seq = synth_torch.synth_reference_torch(2 * 1000 + ci, L, gdev).cpu().numpy()
+            out.append((d, L, seq))
+            del soa
+        return out
+
+    if args.impl == "reference":
+        sample = make_cpu_sample()
+        n_reads, dt = cpu_reference_leg(sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        val = n_reads / dt
+        desc = "%s (%.0f M reads) of the workload" % ("+".join(regs[i][0] for i in sample_ids), n_reads / 1e6)
+        line = {
+            "impl": "reference", "metric": "aligned reads/s binned", "value": val, "unit": "reads/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": {"workload": workload, "sample": desc},
+            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": 1, "kind": "port", "sample": desc,
+                             "host_cores_available": os.cpu_count()},
+            "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "restated reference CPU path (oracle/, plain C -O2); the Rust reference cannot be built "
+                    "here; cmd coverage/normalize are single-threaded in the reference",
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---- B200 arm ---------------------------------------------------------------------------------
+    ctx = cb.Context(local_rank)
+    opts = cb.CoverageOptions(window_length=WINDOW, min_mapq=MIN_MAPQ)
+    t_gen = time.perf_counter()
+    dev_regions, host_cols = [], []
+    n_reads = 0
+    for ci, (name, L) in enumerate(regs):
+        soa = synth_torch.synth_soa_contig(2 * 1000 + ci + 7919 * rank, L, n_pairs[ci], dev)
+        seq = synth_torch.synth_reference_torch(2 * 1000 + ci, L, dev)
+        batch = cb.ReadBatch(mid=soa["mid"].contiguous(), mapq=soa["mapq"].contiguous(), flags=soa["flags"].contiguous())
+        dev_regions.append(pipeline.Region(name, L, batch, seq))
+        n_reads += len(batch)
+        del soa
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t_gen
+
+    def step_device():
+        t = pipeline.coverage_run(dev_regions, opts, ctx=ctx)
+        return pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # correctness guard on the full-size run: every counted fragment lands in exactly one window
+    t = step_device()
+    torch.cuda.synchronize()
+    assert int(t.rcv.double().sum().item()) == sum(t.num_processed) - sum(t.num_skipped), "checksum"
+    n_windows = int(t.rcv.numel())
+    for _ in range(max(0, args.warmup - 1)):
+        step_device()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    kern = {}
+    for kname in ("frag_bin_gw_kernel", "refstats_count_kernel", "gc_radix_hist_kernel"):
+        kms, cnt = ctx.timing_query(kname)
+        kern[kname] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps}
+    ctx.set_timing(False)
+    ctx.timing_reset()
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    value = world * n_reads / (ms_max * 1e-3)
+
+    # ---- end to end: pinned host SoA in, table out -----------------------------------------------------
+    host_regions = []
+    h2d = 0
+    for r in dev_regions:
+        cols = {}
+        for kcol in ("mid", "mapq", "flags"):
+            src = getattr(r.reads, kcol)
+            h = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            h.copy_(src)
+            cols[kcol] = h
+            h2d += h.numel() * h.element_size()
+        hseq = torch.empty(r.sequence.shape, dtype=torch.uint8, pin_memory=True)
+        hseq.copy_(r.sequence)
+        h2d += hseq.numel()
+        host_regions.append(pipeline.Region(r.name, r.length, cb.ReadBatch(**cols), hseq))
+    torch.cuda.synchronize()
+    out_host = {kcol: torch.empty(n_windows, dtype=dt, pin_memory=True)
+                for kcol, dt in (("cv", torch.float32), ("cv2", torch.float32), ("lcv", torch.float32),
+                                 ("rcv", torch.float32), ("gc", torch.float32), ("norm_flags", torch.uint8),
+                                 ("gap", torch.uint8))}
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    def step_e2e():
+        tt = pipeline.coverage_run(host_regions, opts, ctx=ctx)
+        pipeline.normalize_run(tt, "MedianGcBinned", ctx=ctx)
+        for kcol, h in out_host.items():
+            h.copy_(getattr(tt, kcol), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_reads / float(te.item())
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    gw = kern["frag_bin_gw_kernel"]
+    achieved = BYTES_PER_READ_GW * n_reads / (gw["ms_per_step"] * 1e-3) / 1e9 if gw["ms_per_step"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "frag_bin_gw_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_read": BYTES_PER_READ_GW,
+                "kernel_share_of_step": gw["ms_per_step"] / ms}
+    rs = kern["refstats_count_kernel"]
+    total_bp = sum(L for _, L in regs)
+    kern["refstats_count_kernel"]["achieved_gbs"] = total_bp / (rs["ms_per_step"] * 1e-3) / 1e9 if rs["ms_per_step"] > 0 else 0.0
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ------------------------------------------
+    cpu = None
+    if world == 1:
+        sample = make_cpu_sample()
+        cn, cdt = cpu_reference_leg(sample, 1, 1)
+        cpu = {"value": cn / cdt, "unit": "reads/s", "cores": 1, "kind": "port",
+               "sample": "%s (%.0f M reads) of the workload, oracle coverage+refstats+normalize, single thread "
+                         "(the reference's cmd coverage/normalize are single-threaded)" %
+                         ("+".join(regs[i][0] for i in sample_ids), cn / 1e6),
+               "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": "aligned reads/s binned", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload, "reads_per_gpu": n_reads, "windows_per_gpu": n_windows,
+                   "contigs": len(regs), "window_length": WINDOW, "scale": args.scale,
+                   "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" %
+                         ((BYTES_PER_READ_GW * n_reads + total_bp) / 1e9),
+                   "parallelism": "one sample per GPU, no collective" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "kernels": kern, "gen_seconds": gen_s,
+    }
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

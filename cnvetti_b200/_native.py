@@ -1,0 +1,93 @@
+"""ctypes binding of libcnvetti_b200.so (the C ABI in include/cnvetti_b200.h).
+
+There is no fallback: if the shared library is missing this module raises, and if no CUDA device
+is present every compute call fails with CNVB_ERR_CUDA.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcnvetti_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_REFERENCE_PANIC, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_CLIPFAIL, FLAG_ISIZE_NONPOS = 0x1000, 0x2000
+FRAGMENTS_GENOME_WIDE, FRAGMENTS_TARGET_REGIONS, COVERAGE = 0, 1, 2
+FT_LOWCOV, FT_PILE = 1, 2
+N2_CV, N2_CV2, N2_CVSD, N2_FEW_GCWINDOWS = 1, 2, 4, 8
+F32_MISSING_BITS = 0x7F800001
+
+
+class ReadSoa(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("end", C.c_void_p),
+                ("mid", C.c_void_p), ("frag_end", C.c_void_p), ("mapq", C.c_void_p),
+                ("flags", C.c_void_p), ("mem", C.c_int)]
+
+
+class CovOpts(C.Structure):
+    _fields_ = [("min_mapq", C.c_uint8), ("min_unclipped", C.c_float),
+                ("window_length", C.c_uint32), ("min_window_remaining", C.c_float),
+                ("min_raw_coverage", C.c_uint32), ("plp_flag_mask", C.c_uint32)]
+
+
+# every symbol include/cnvetti_b200.h declares: name -> (restype, argtypes)
+_vp, _u64, _u32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+SYMBOLS = {
+    "cnvb_ctx_create": (_int, [_int, _vp, C.POINTER(_vp)]),
+    "cnvb_ctx_destroy": (None, [_vp]),
+    "cnvb_ctx_synchronize": (_int, [_vp]),
+    "cnvb_last_error": (C.c_char_p, [_vp]),
+    "cnvb_create_error": (C.c_char_p, []),
+    "cnvb_ctx_launch_count": (_u64, [_vp]),
+    "cnvb_version": (C.c_char_p, []),
+    "cnvb_ctx_set_timing": (_int, [_vp, _int]),
+    "cnvb_ctx_timing_reset": (_int, [_vp]),
+    "cnvb_ctx_timing_query": (_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "cnvb_pack_reads": (_int, [_u64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]),
+    "cnvb_cov_create": (_int, [_vp, C.POINTER(CovOpts), _int, _u32, _vp, _vp, _u32, _vp, _vp,
+                               _u32, C.POINTER(_vp)]),
+    "cnvb_cov_put_records": (_int, [_vp, C.POINTER(ReadSoa)]),
+    "cnvb_cov_finish": (_int, [_vp]),
+    "cnvb_cov_finish_async": (_int, [_vp]),
+    "cnvb_cov_num_regions": (_u64, [_vp]),
+    "cnvb_cov_num_processed": (_u32, [_vp]),
+    "cnvb_cov_num_skipped": (_u32, [_vp]),
+    "cnvb_cov_get_stats": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
+    "cnvb_cov_get_counts": (_int, [_vp, _vp, _int]),
+    "cnvb_cov_destroy": (None, [_vp]),
+    "cnvb_refstats": (_int, [_vp, _vp, _u64, _u32, _vp, _vp, _int]),
+    "cnvb_cov_records": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _int, C.POINTER(CovOpts),
+                                _vp, _vp, _vp, _int]),
+    "cnvb_norm_total": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _int]),
+    "cnvb_norm_gc_median": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _int]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (building it is `python -m cnvetti_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "cnvetti_b200: %s is missing. Build it with `python -m cnvetti_b200.build`; "
+                "there is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class CnvbError(RuntimeError):
+    def __init__(self, code, chain):
+        self.code = code
+        self.chain = chain
+        RuntimeError.__init__(self, "error: %s" % chain)
+
+
+class ReferencePanic(CnvbError):
+    """Input on which the reference itself panics (CNVB_ERR_REFERENCE_PANIC)."""

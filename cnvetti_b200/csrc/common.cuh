@@ -1,0 +1,256 @@
+// common.cuh -- context, error chain and small device helpers shared by all kernels.
+// Target: sm_100a (B200) only.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <initializer_list>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cnvetti_b200.h"
+
+struct cnvb_span {  // one timed kernel launch (only while timing is switched on)
+    int name_id;
+    cudaEvent_t a, b;
+};
+
+struct cnvb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    std::string err;
+    // grow-only device scratch (outputs staged for CNVB_MEM_HOST callers, partial sums, ...)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // grow-only device staging for CNVB_MEM_HOST inputs
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    // caching device allocator: aggregators are created and destroyed once per region, and
+    // cudaMalloc/cudaFree would serialise the device every time
+    std::map<size_t, std::vector<void *>> pool_free;
+    std::unordered_map<void *, size_t> pool_live;
+    // pinned host slots for asynchronous read-back of per-aggregator tallies
+    uint32_t *tally_slots = nullptr;  // kTallySlots x 4 u32
+    uint32_t tally_next = 0;
+    // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
+    bool timing = false;
+    std::vector<std::string> span_names;
+    std::vector<cnvb_span> spans;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace cnvb {
+
+// error chain in the style of error-chain's "error: ... / caused by: ..." (cnvetti/src/main.rs)
+inline int fail(cnvb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+inline int fail_cuda(cnvb_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, CNVB_ERR_CUDA, "%s\ncaused by: CUDA error %d (%s): %s", what, (int)e,
+                cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+#define CNVB_CUDA(ctx, call, what)                                        \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return cnvb::fail_cuda((ctx), e__, what); \
+    } while (0)
+
+#define CNVB_TRY(expr)            \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// RAII: brackets a kernel launch with two events when ctx->timing is on
+struct KernelSpan {
+    cnvb_ctx *ctx;
+    cudaEvent_t b = nullptr;
+    static cudaEvent_t get_event(cnvb_ctx *c) {
+        if (!c->event_pool.empty()) {
+            cudaEvent_t e = c->event_pool.back();
+            c->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    KernelSpan(cnvb_ctx *c, const char *name) : ctx(c) {
+        if (!c->timing) return;
+        int id = -1;
+        for (size_t i = 0; i < c->span_names.size(); ++i)
+            if (c->span_names[i] == name) id = (int)i;
+        if (id < 0) {
+            c->span_names.push_back(name);
+            id = (int)c->span_names.size() - 1;
+        }
+        cudaEvent_t a = get_event(c);
+        b = get_event(c);
+        cudaEventRecord(a, c->stream);
+        c->spans.push_back({id, a, b});
+    }
+    ~KernelSpan() {
+        if (b) cudaEventRecord(b, ctx->stream);
+    }
+};
+
+// after a kernel launch: count it and surface launch errors
+#define CNVB_LAUNCHED(ctx, name)                                              \
+    do {                                                                      \
+        (ctx)->launches += 1;                                                 \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) return cnvb::fail_cuda((ctx), e__, "launch of " name); \
+    } while (0)
+
+inline int ensure_scratch(cnvb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return 0;
+    if (ctx->scratch) {
+        CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "sync before scratch regrow");
+        cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 2) + 4096;
+    CNVB_CUDA(ctx, cudaMalloc(&ctx->scratch, want), "allocating device scratch");
+    ctx->scratch_bytes = want;
+    return 0;
+}
+
+inline int ensure_stage(cnvb_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return 0;
+    if (ctx->stage) {
+        CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "sync before staging regrow");
+        cudaFree(ctx->stage);
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+    }
+    size_t want = bytes + 4096;
+    CNVB_CUDA(ctx, cudaMalloc(&ctx->stage, want), "allocating device staging");
+    ctx->stage_bytes = want;
+    return 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr uint32_t kTallySlots = 4096;
+
+// pooled device allocation (size classes: next power of two, >= 512 B)
+inline cudaError_t pool_alloc(cnvb_ctx *ctx, size_t bytes, void **out) {
+    size_t cls = 512;
+    while (cls < bytes) cls <<= 1;
+    auto it = ctx->pool_free.find(cls);
+    if (it != ctx->pool_free.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+    } else {
+        cudaError_t e = cudaMalloc(out, cls);
+        if (e != cudaSuccess) return e;
+    }
+    ctx->pool_live[*out] = cls;
+    return cudaSuccess;
+}
+template <typename T>
+inline cudaError_t pool_alloc_t(cnvb_ctx *ctx, size_t count, T **out) {
+    void *p = nullptr;
+    cudaError_t e = pool_alloc(ctx, (count ? count : 1) * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return e;
+}
+// Returns the block to the pool.  Stream-ordered reuse is safe: everything runs on ctx->stream.
+inline void pool_release(cnvb_ctx *ctx, void *p) {
+    if (!p) return;
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) return;
+    ctx->pool_free[it->second].push_back(p);
+    ctx->pool_live.erase(it);
+}
+inline void pool_destroy(cnvb_ctx *ctx) {
+    for (auto &kv : ctx->pool_free)
+        for (void *p : kv.second) cudaFree(p);
+    for (auto &kv : ctx->pool_live) cudaFree(kv.first);
+    ctx->pool_free.clear();
+    ctx->pool_live.clear();
+}
+
+// Carves aligned sub-buffers out of one allocation.
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base(static_cast<char *>(b)) {}
+    template <typename T>
+    T *take(size_t count) {
+        off = align_up(off, 256);
+        T *p = reinterpret_cast<T *>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+    static size_t need(std::initializer_list<size_t> sizes) {
+        size_t o = 0;
+        for (size_t s : sizes) o = align_up(o, 256) + s;
+        return o + 256;
+    }
+};
+
+// ---- device helpers ---------------------------------------------------------------------
+
+__device__ __forceinline__ float f32_missing() { return __uint_as_float(CNVB_F32_MISSING_BITS); }
+
+// streaming 128/64/32-bit loads that do not pollute L1 (data is touched exactly once)
+__device__ __forceinline__ int4 ld_stream(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// Exact u32 division by a runtime-invariant divisor: q = n / d with m = min(2^32/d, 2^32-1).
+// floor(n*m / 2^32) is q or q-1, so one correction step suffices.
+struct FastDiv {
+    uint32_t d, m;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint64_t m = (1ull << 32) / d;
+    f.m = m > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)m;
+    return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, FastDiv f) {
+    uint32_t q = __umulhi(n, f.m);
+    uint32_t r = n - q * f.d;
+    return q + (r >= f.d ? 1u : 0u);
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+}  // namespace cnvb

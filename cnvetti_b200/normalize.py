@@ -1,0 +1,38 @@
+"""Host-side mirror of lib-normalize (lib-normalize/src/lib.rs:43-66) on in-memory columns."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .context import buf, default_context
+
+
+def run_uncorrected_normalization(lcv, lcvsd=None, ctx=None):
+    """Normalization::TotalCovSum (lib-normalize/src/uncorrected.rs:51-96).
+    Returns (cv, cvsd or None, lcv_sum)."""
+    ctx = ctx or default_context()
+    p, mem, keep = buf(lcv, np.float32)
+    n = int(keep.shape[0])
+    cv = ctx.empty(n, np.float32, mem)
+    cvsd = ctx.empty(n, np.float32, mem) if lcvsd is not None else None
+    s = C.c_double(0.0)
+    ctx.check(N.lib().cnvb_norm_total(ctx.handle, p, buf(lcvsd, np.float32)[0], n, buf(cv)[0],
+                                      buf(cvsd)[0], C.addressof(s), mem))
+    return cv, cvsd, s.value
+
+
+def run_binned_correction(lcv, gc, lcvsd=None, ctx=None):
+    """Normalization::MedianGcBinned (lib-normalize/src/correct_binned.rs:77-146).
+    Returns dict(cv, cv2, cvsd, flags, medians); flags bits N2_* say which fields are written."""
+    ctx = ctx or default_context()
+    p, mem, keep = buf(lcv, np.float32)
+    n = int(keep.shape[0])
+    cv = ctx.empty(n, np.float32, mem)
+    cv2 = ctx.empty(n, np.float32, mem)
+    cvsd = ctx.empty(n, np.float32, mem) if lcvsd is not None else None
+    flags = ctx.empty(n, np.uint8, mem)
+    med = np.empty(101, np.float32)
+    ctx.check(N.lib().cnvb_norm_gc_median(ctx.handle, p, buf(lcvsd, np.float32)[0],
+                                          buf(gc, np.float32)[0], n, buf(cv)[0], buf(cv2)[0],
+                                          buf(cvsd)[0], buf(flags)[0], med.ctypes.data, mem))
+    return dict(cv=cv, cv2=cv2, cvsd=cvsd, flags=flags, medians=med)

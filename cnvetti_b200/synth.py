@@ -1,0 +1,204 @@
+"""Seeded synthetic inputs of the shapes SURVEY.md section 8(d) names (no network, no real data).
+
+All generators are deterministic in their seed.  BAM-level generators return what a BAM record
+carries (pos, insert size, FLAG, MAPQ, CIGAR); `cnvetti_b200.pack_reads` turns them into the SoA
+batch the kernels consume.
+"""
+import numpy as np
+
+HG38_AUTOSOMES = [
+    248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+    138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+    83257441, 80373285, 58617616, 64444167, 46709983, 50818468,
+]
+CHR22_LEN = HG38_AUTOSOMES[21]
+
+CIG_M, CIG_I, CIG_D, CIG_N, CIG_S, CIG_H = 0, 1, 2, 3, 4, 5
+
+
+def _cnv_density(contig_len, rng, n_cnv):
+    """Piecewise-constant relative density with planted CNVs: (starts, ends, factor)."""
+    segs = []
+    for k in range(n_cnv):
+        length = int(rng.integers(200_000, 2_000_000)) if contig_len > 8_000_000 else \
+            int(rng.integers(max(2, contig_len // 40), max(3, contig_len // 10)))
+        start = int(rng.integers(0, max(1, contig_len - length)))
+        segs.append((start, start + length, 0.5 if k % 2 == 0 else 1.5))
+    return segs
+
+
+def synth_bam_records(seed, contig_len, n_pairs, read_len=100, n_cnv=6, unpaired_frac=0.0,
+                      refskip_frac=0.0):
+    """Coordinate-sorted paired-end records on one contig.
+
+    isize ~ N(350,50) clipped to [120,800]; MAPQ 88% 60 / 7% U[1,59] / 5% 0; 1% dup, 0.5%
+    secondary, 0.5% supplementary, 0.3% qcfail, 2% improper pairs; CIGAR 94% <L>M, 4%
+    soft-clipped (1..60 bases), 2% one I or D of <= 10.  `unpaired_frac` adds single-end records
+    (only meaningful for the Targets / Coverage kinds: genome-wide fragment counting gives
+    unpaired reads the centre pos+end_pos, lib-coverage/src/agg.rs:127-132).
+    Returns dict(pos, isize, flag, mapq, cigar_off, cigar) of numpy arrays.
+    """
+    rng = np.random.default_rng(seed)
+    segs = _cnv_density(contig_len, rng, n_cnv)
+    max_isize = 800
+    # fragment starts: rejection sampling against the CNV density
+    want = n_pairs
+    starts = []
+    while want > 0:
+        cand = rng.integers(0, max(1, contig_len - max_isize), size=int(want * 1.6) + 16)
+        dens = np.ones(cand.size)
+        for (s, e, f) in segs:
+            dens[(cand >= s) & (cand < e)] = f
+        keep = cand[rng.random(cand.size) * 1.5 < dens][:want]
+        starts.append(keep)
+        want -= keep.size
+    fstart = np.concatenate(starts).astype(np.int64)
+    n_pairs = fstart.size
+    isize = np.clip(np.rint(rng.normal(350, 50, n_pairs)), max(120, read_len), max_isize).astype(np.int64)
+
+    improper = rng.random(n_pairs) < 0.02
+    single = rng.random(n_pairs) < unpaired_frac
+
+    def mate_fields(n):
+        mapq = np.full(n, 60, np.uint8)
+        u = rng.random(n)
+        low = (u >= 0.88) & (u < 0.95)
+        mapq[low] = rng.integers(1, 60, int(low.sum()))
+        mapq[u >= 0.95] = 0
+        extra = np.zeros(n, np.uint16)
+        extra[rng.random(n) < 0.01] |= 0x400
+        extra[rng.random(n) < 0.005] |= 0x100
+        extra[rng.random(n) < 0.005] |= 0x800
+        extra[rng.random(n) < 0.003] |= 0x200
+        return mapq, extra
+
+    mq1, ex1 = mate_fields(n_pairs)
+    mq2, ex2 = mate_fields(n_pairs)
+    proper = np.where(improper, 0, 0x2).astype(np.uint16)
+    flag1 = (0x1 | 0x20 | 0x40) | proper | ex1
+    flag2 = (0x1 | 0x10 | 0x80) | proper | ex2
+    flag1 = np.where(single, ex1, flag1).astype(np.uint16)  # single-end: no pairing bits
+    pos1 = fstart
+    pos2 = fstart + isize - read_len
+    is1 = np.where(single, 0, isize)
+    is2 = -isize
+    keep2 = ~single
+    pos = np.concatenate([pos1, pos2[keep2]])
+    isz = np.concatenate([is1, is2[keep2]])
+    flag = np.concatenate([flag1, flag2[keep2]])
+    mapq = np.concatenate([mq1, mq2[keep2]])
+    n = pos.size
+
+    # CIGARs: up to 3 ops per read
+    kind = rng.random(n)
+    ops = np.zeros((n, 3), np.uint32)
+    nops = np.ones(n, np.int64)
+    ops[:, 0] = (read_len << 4) | CIG_M
+    sc = (kind >= 0.94) & (kind < 0.98)
+    clip = rng.integers(1, min(61, read_len), n).astype(np.uint32)
+    left = rng.random(n) < 0.5
+    a = sc & left
+    ops[a, 0] = (clip[a] << 4) | CIG_S
+    ops[a, 1] = ((read_len - clip[a]) << 4) | CIG_M
+    b = sc & ~left
+    ops[b, 0] = ((read_len - clip[b]) << 4) | CIG_M
+    ops[b, 1] = (clip[b] << 4) | CIG_S
+    nops[sc] = 2
+    indel = kind >= 0.98
+    k = rng.integers(1, 11, n).astype(np.uint32)
+    first = rng.integers(10, read_len - 20, n).astype(np.uint32)
+    ins = indel & (rng.random(n) < 0.5)
+    dele = indel & ~ins
+    ops[ins, 0] = (first[ins] << 4) | CIG_M
+    ops[ins, 1] = (k[ins] << 4) | CIG_I
+    ops[ins, 2] = ((read_len - first[ins] - k[ins]) << 4) | CIG_M
+    ops[dele, 0] = (first[dele] << 4) | CIG_M
+    ops[dele, 1] = (k[dele] << 4) | CIG_D
+    ops[dele, 2] = ((read_len - first[dele]) << 4) | CIG_M
+    nops[indel] = 3
+    if refskip_frac > 0:
+        rs = rng.random(n) < refskip_frac
+        gap = rng.integers(50, 3000, n).astype(np.uint32)
+        ops[rs, 0] = ((read_len // 2) << 4) | CIG_M
+        ops[rs, 1] = (gap[rs] << 4) | CIG_N
+        ops[rs, 2] = ((read_len - read_len // 2) << 4) | CIG_M
+        nops[rs] = 3
+
+    order = np.argsort(pos, kind="stable")
+    pos, isz, flag, mapq, ops, nops = pos[order], isz[order], flag[order], mapq[order], ops[order], nops[order]
+    cigar_off = np.zeros(n + 1, np.uint64)
+    np.cumsum(nops, out=cigar_off[1:])
+    mask = np.arange(3)[None, :] < nops[:, None]
+    cigar = ops[mask]
+    return dict(pos=pos.astype(np.int32), isize=isz.astype(np.int32), flag=flag.astype(np.uint16),
+                mapq=mapq.astype(np.uint8), cigar_off=cigar_off, cigar=cigar.astype(np.uint32))
+
+
+def synth_reference(seed, length, block=10_000, gap_frac=0.02, lowercase_frac=0.3):
+    """Synthetic contig sequence: GC fraction per `block` drawn from Beta(8,11), a fraction of
+    blocks are N gaps, soft-masked (lower-case) stretches, a sprinkle of IUPAC codes."""
+    rng = np.random.default_rng(seed)
+    nblk = (length + block - 1) // block
+    gcf = rng.beta(8, 11, nblk)
+    u = rng.random(length)
+    gcb = np.repeat(gcf, block)[:length]
+    is_gc = u < gcb
+    pick = rng.random(length) < 0.5
+    seq = np.where(is_gc, np.where(pick, ord("G"), ord("C")), np.where(pick, ord("A"), ord("T"))).astype(np.uint8)
+    lower = np.repeat(rng.random(nblk) < lowercase_frac, block)[:length]
+    seq[lower] |= 0x20
+    gaps = np.repeat(rng.random(nblk) < gap_frac, block)[:length]
+    seq[gaps] = ord("N")
+    iupac = rng.random(length) < 1e-4
+    seq[iupac] = rng.choice(np.frombuffer(b"RYKMSWnrym", np.uint8), int(iupac.sum()))
+    return seq
+
+
+def synth_targets(seed, contig_len, n_targets, min_len=80, max_len=400, overlap_frac=0.0):
+    """Sorted target intervals (exome-like).  `overlap_frac` > 0 makes some neighbours overlap."""
+    rng = np.random.default_rng(seed)
+    starts = np.sort(rng.integers(0, max(1, contig_len - max_len), n_targets)).astype(np.int64)
+    lens = rng.integers(min_len, max_len + 1, n_targets)
+    ends = starts + lens
+    if overlap_frac <= 0:
+        # make disjoint: push starts right where needed
+        for i in range(1, n_targets):
+            if starts[i] <= ends[i - 1]:
+                starts[i] = ends[i - 1] + 1 + int(rng.integers(0, 50))
+                ends[i] = starts[i] + lens[i]
+        ok = ends <= contig_len
+        starts, ends = starts[ok], ends[ok]
+    return starts.astype(np.uint32), ends.astype(np.uint32)
+
+
+def synth_panel(seed, T, S, n_contigs=22):
+    """WIS panel X[T][S] (f32) as SURVEY 8(d) config 3: eff_t ~ LogNormal(0,0.4), noise ~ N(1,0.08),
+    column-normalised to sum 1 (mimics TotalCovSum); tids from contigs proportional to length."""
+    rng = np.random.default_rng(seed)
+    eff = rng.lognormal(0.0, 0.4, T)
+    X = eff[:, None] * rng.normal(1.0, 0.08, (T, S))
+    X = np.maximum(X, 0.0)
+    X = X / X.sum(axis=0, keepdims=True)
+    w = np.array(HG38_AUTOSOMES[:n_contigs], np.float64)
+    bounds = np.floor(np.cumsum(w) / w.sum() * T).astype(np.int64)
+    tids = np.searchsorted(bounds, np.arange(T), side="right").astype(np.uint32)
+    tids = np.minimum(tids, n_contigs - 1).astype(np.uint32)
+    return X.astype(np.float32), tids
+
+
+def synth_cv_lanes(seed, n_bins, n_cnv=20, noise=0.08, sigma0=0.02, missing_frac=0.001):
+    """One normalised coverage lane (config 4): CV ~ N(cn/2, noise*sqrt(cn/2)+sigma0) with planted
+    segments cn in {0,1,3,4} of 5..500 bins.  Returns (cv f32, true cn u8)."""
+    rng = np.random.default_rng(seed)
+    cn = np.full(n_bins, 2, np.uint8)
+    for _ in range(n_cnv):
+        ln = int(rng.integers(5, 501))
+        if n_bins <= ln + 1:
+            continue
+        s = int(rng.integers(0, n_bins - ln))
+        cn[s:s + ln] = rng.choice(np.array([0, 1, 3, 4], np.uint8))
+    mu = cn / 2.0
+    cv = rng.normal(mu, noise * np.sqrt(mu) + sigma0).astype(np.float32)
+    miss = rng.random(n_bins) < missing_frac
+    cv[miss] = np.frombuffer(np.uint32(0x7F800001).tobytes(), np.float32)[0]
+    return cv, cn

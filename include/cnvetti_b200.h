@@ -1,0 +1,178 @@
+/*
+ * cnvetti_b200.h -- C ABI of the B200-native read-depth hot path of bihealth/cnvetti.
+ *
+ * The reference has no FFI; its seams for this path are a Rust trait and four `run` functions
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the Rust `-sys` binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes; opaque handles; no exceptions cross the ABI;
+ *  - every call returns 0 on success or a negative CNVB_ERR_* code; the human-readable error
+ *    chain ("what: caused by ...", as error-chain prints in cnvetti/src/main.rs:171-185) is
+ *    read with cnvb_last_error(ctx);
+ *  - one cnvb_ctx = one CUDA device + one stream + scratch memory.  A ctx (and the handles made
+ *    from it) is used by one host thread at a time; different ctxs may be used concurrently
+ *    from different threads (the reference runs one `run` per rayon worker,
+ *    cnvetti/src/quick_wis_build_model.rs:148-184).  No process-global mutable state;
+ *  - `mem` arguments say where caller buffers live: CNVB_MEM_HOST (pageable or pinned host
+ *    memory; the library stages through pinned buffers and copies asynchronously) or
+ *    CNVB_MEM_DEVICE (device pointers on the ctx's device; zero-copy);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    CNVB_ERR_CUDA.
+ */
+#ifndef CNVETTI_B200_H
+#define CNVETTI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNVB_OK 0
+#define CNVB_ERR_INVALID (-1)         /* bad argument                                        */
+#define CNVB_ERR_CUDA (-2)            /* CUDA runtime error / no device                      */
+#define CNVB_ERR_REFERENCE_PANIC (-3) /* input on which the reference itself panics          */
+#define CNVB_ERR_STATE (-4)           /* call order violated (e.g. get_stats before finish)  */
+#define CNVB_ERR_NOMEM (-5)
+
+#define CNVB_MEM_HOST 0
+#define CNVB_MEM_DEVICE 1
+
+/* f32::missing() of rust-htslib (bcf_float_missing) */
+#define CNVB_F32_MISSING_BITS 0x7F800001u
+
+/* ---- context ---------------------------------------------------------------------------- */
+typedef struct cnvb_ctx cnvb_ctx;
+
+/* `stream`: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+int cnvb_ctx_create(int device, void *stream, cnvb_ctx **out);
+void cnvb_ctx_destroy(cnvb_ctx *ctx);
+int cnvb_ctx_synchronize(cnvb_ctx *ctx);
+/* error chain of the last failing call on this ctx ("" if none); valid until the next call */
+const char *cnvb_last_error(const cnvb_ctx *ctx);
+/* error text of a failed cnvb_ctx_create (thread-local) */
+const char *cnvb_create_error(void);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+uint64_t cnvb_ctx_launch_count(const cnvb_ctx *ctx);
+const char *cnvb_version(void);
+/* Optional instrumentation: while on, every kernel launch is bracketed by CUDA events on the
+ * ctx stream; cnvb_ctx_timing_query sums the device time of all launches of `kernel` (e.g.
+ * "frag_bin_gw_kernel") since the last reset.  Query and reset synchronise the stream. */
+int cnvb_ctx_set_timing(cnvb_ctx *ctx, int on);
+int cnvb_ctx_timing_reset(cnvb_ctx *ctx);
+int cnvb_ctx_timing_query(cnvb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *count);
+
+/* ---- read batches ------------------------------------------------------------------------ */
+/* Extra bits the host decoder ORs into the 16-bit FLAG word (BAM uses bits 0..11):          */
+#define CNVB_FLAG_CLIPFAIL 0x1000u     /* skip_clipping() is true   (agg.rs:174-193)          */
+#define CNVB_FLAG_ISIZE_NONPOS 0x2000u /* insert_size() <= 0        (agg.rs:196-198)          */
+
+/* Structure-of-arrays batch in coordinate order, as the host BAM decoder fills it
+ * (north_star: tid, pos, end, mapq, flags, fragment midpoint).  Arrays a kernel does not need
+ * may be NULL: GenomeWide reads mid/mapq/flags; TargetRegions pos/frag_end/mapq/flags;
+ * Coverage pos/end/mapq/flags. */
+typedef struct {
+    uint64_t n;
+    const int32_t *tid;      /* optional, unused by the kernels (one aggregator = one region) */
+    const int32_t *pos;      /* record.pos()                                                  */
+    const int32_t *end;      /* htslib bam_endpos(): pos + max(1, reference length)           */
+    const int32_t *mid;      /* GenomeWide fragment centre, agg.rs:124-133 (bit pattern of u32)*/
+    const int32_t *frag_end; /* TargetRegions interval end, agg.rs:312-320                    */
+    const uint8_t *mapq;
+    const uint16_t *flags;   /* FLAG | CNVB_FLAG_*                                            */
+    int mem;                 /* CNVB_MEM_HOST | CNVB_MEM_DEVICE                               */
+} cnvb_read_soa;
+
+/* Host-side packer: BAM-level fields -> SoA fields, exactly as the reference derives them from
+ * a bam::Record (agg.rs:124-133, 174-198, 311-321; htslib bam_endpos).  `cigar` is BAM-encoded
+ * (len<<4|op), `cigar_off` has n+1 entries.  Pure host code (no device needed); this is what a
+ * BGZF/BAM decoder thread calls per block of records. */
+int cnvb_pack_reads(uint64_t n, const int32_t *pos, const int32_t *isize, const uint16_t *flag,
+                    const uint64_t *cigar_off, const uint32_t *cigar, float min_unclipped,
+                    int32_t *out_end, int32_t *out_mid, int32_t *out_frag_end,
+                    uint16_t *out_flags);
+
+/* ---- lib-coverage: BamRecordAggregator (lib-coverage/src/agg.rs:49-64) -------------------- */
+typedef struct cnvb_cov cnvb_cov;
+
+typedef struct {
+    uint8_t min_mapq;           /* CoverageOptions::min_mapq            (options.rs:64)       */
+    float min_unclipped;        /* CoverageOptions::min_unclipped       (options.rs:66)       */
+    uint32_t window_length;     /* CoverageOptions::window_length       (options.rs:75)       */
+    float min_window_remaining; /* CoverageOptions::min_window_remaining (options.rs:69)      */
+    uint32_t min_raw_coverage;  /* CoverageOptions::min_raw_coverage    (options.rs:71)       */
+    uint32_t plp_flag_mask;     /* flags htslib's pileup drops before the reference's filter;
+                                   0 selects the default 0x704 (UNMAP|SECONDARY|QCFAIL|DUP)   */
+} cnvb_cov_opts;
+
+/* (count_kind, considered_regions) pairs accepted at lib-coverage/src/lib.rs:510-529 */
+#define CNVB_FRAGMENTS_GENOME_WIDE 0    /* FragmentsGenomeWideAggregator   agg.rs:68-257     */
+#define CNVB_FRAGMENTS_TARGET_REGIONS 1 /* FragmentsTargetRegionsAggregator agg.rs:261-444   */
+#define CNVB_COVERAGE 2                 /* CoverageAggregator              agg.rs:468-600    */
+
+/* = XxxAggregator::new (agg.rs:90, :278, :485).  `region_end` is the `contig_length` argument
+ * the reference passes (the region end, lib.rs:514,526).  Targets (sorted by start, as a tabix
+ * BED yields them) only for TARGET_REGIONS; piles (disjoint, sorted) only for GENOME_WIDE.
+ * Target/pile arrays are host memory and are copied. */
+int cnvb_cov_create(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, uint32_t region_end,
+                    const uint32_t *tgt_start, const uint32_t *tgt_end, uint32_t n_tgt,
+                    const uint32_t *pile_start, const uint32_t *pile_end, uint32_t n_pile,
+                    cnvb_cov **out);
+/* = put_fetched_records (agg.rs:51): batches arrive in coordinate order; may be called
+ * repeatedly.  Asynchronous with respect to the host for CNVB_MEM_DEVICE batches. */
+int cnvb_cov_put_records(cnvb_cov *agg, const cnvb_read_soa *batch);
+/* end of the fetch()ed stream: flushes, runs the Coverage window pass (incl. the reference's
+ * lagging window state machine, agg.rs:523-573) and checks for reference-panic conditions. */
+int cnvb_cov_finish(cnvb_cov *agg);
+/* Same, but only enqueues the work on the ctx stream: get_stats(CNVB_MEM_DEVICE) may follow at
+ * once; tallies and reference-panic conditions are reported by a later cnvb_cov_finish. */
+int cnvb_cov_finish_async(cnvb_cov *agg);
+uint64_t cnvb_cov_num_regions(const cnvb_cov *agg);     /* agg.rs:57  */
+uint32_t cnvb_cov_num_processed(const cnvb_cov *agg);   /* agg.rs:60  (valid after finish)   */
+uint32_t cnvb_cov_num_skipped(const cnvb_cov *agg);     /* agg.rs:63  (valid after finish)   */
+/* = get_stats for every region id (agg.rs:54, AggregationStats agg.rs:17-32), arrays of
+ * num_regions.  cov_sd / frac_removed are the Option<f32> members: pass NULL to skip; asking
+ * for one the aggregator kind does not produce is CNVB_ERR_INVALID.  mean_mapq may be NULL. */
+int cnvb_cov_get_stats(cnvb_cov *agg, float *cov, float *cov_sd, uint32_t *start, uint32_t *end,
+                       float *frac_removed, float *mean_mapq, int mem);
+/* raw integer counters (Fragments kinds), for bit-exact checks: u32[num_regions] */
+int cnvb_cov_get_counts(cnvb_cov *agg, uint32_t *counts, int mem);
+void cnvb_cov_destroy(cnvb_cov *agg);
+
+/* = ReferenceStats::look_at_chars (lib-coverage/src/reference.rs:84-130).
+ * gc[ceil(len/wl)] (missing pattern where a window has no ACGT), has_gap[ceil(len/wl)]. */
+int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, uint32_t window_length,
+                  float *gc, uint8_t *has_gap, int mem);
+
+/* = FORMAT value assembly in process_region (lib-coverage/src/lib.rs:623-668):
+ * LCV = RCV/(end-start), LCVSD, FT bits (CNVB_FT_LOWCOV, CNVB_FT_PILE).
+ * cov_sd/lcvsd and frac_removed may be NULL. */
+#define CNVB_FT_LOWCOV 1
+#define CNVB_FT_PILE 2
+int cnvb_cov_records(cnvb_ctx *ctx, uint64_t n, const float *cov, const float *cov_sd,
+                     const uint32_t *start, const uint32_t *end, const float *frac_removed,
+                     int is_targets, const cnvb_cov_opts *opts, float *lcv, float *lcvsd,
+                     uint8_t *ft, int mem);
+
+/* ---- lib-normalize ------------------------------------------------------------------------ */
+/* = run_uncorrected_normalization (lib-normalize/src/uncorrected.rs:20-96).  lcvsd/cvsd may be
+ * NULL.  *lcv_sum (host, may be NULL) receives the f64 sum. */
+int cnvb_norm_total(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, uint64_t n, float *cv,
+                    float *cvsd, double *lcv_sum, int mem);
+/* = run_binned_correction (lib-normalize/src/correct_binned.rs:25-146).  flags bits say which
+ * FORMAT/INFO fields the reference writes for the record.  medians (host, 101 floats) may be
+ * NULL.  lcvsd/cvsd may be NULL. */
+#define CNVB_N2_CV 1
+#define CNVB_N2_CV2 2
+#define CNVB_N2_CVSD 4
+#define CNVB_N2_FEW_GCWINDOWS 8
+int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, const float *gc,
+                        uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
+                        float *medians, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNVETTI_B200_H */
