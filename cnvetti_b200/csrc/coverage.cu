@@ -90,66 +90,115 @@ __device__ __forceinline__ uint32_t gw_weight(const GwArgs &a, uint32_t mid, uin
 // ---- A2: FragmentsGenomeWideAggregator::put_bam_record over a whole batch ------------------
 // Each lane owns 4 consecutive reads per step: mid as one int4 (128-bit), mapq as one u32,
 // flags as one uint2.  Algorithmic traffic 7 B/read.
+//
+// The kernel is instruction-issue bound (7 bytes per read is very little data), so the per-read
+// work is cut to the filter plus three compares.  Coordinate-sorted input means the 128 reads of
+// one warp step fall into a handful of adjacent windows: the warp takes the window A of its
+// first counting read as anchor and every lane classifies its reads into the four windows
+// A-1 .. A+2 with three unsigned compares, accumulating four 8-bit counters packed in one
+// register (32 lanes x 4 reads = 128 <= 255, no carry between bytes).  ONE warp REDUX then yields
+// all four window totals and lanes 0..3 issue at most one RED each.  Reads outside the four
+// windows (possible for any input, rare for sorted reads) take a per-read path.
+// fail bits of two packed 16-bit flag words at once (see frag_pass): non-zero half = read fails
+__device__ __forceinline__ uint32_t frag_fail2(uint32_t F) {
+    const uint32_t G = F ^ 0x00020002u;                          // bit 1: not a proper pair
+    const uint32_t T = (F & 0x00010001u) * 0x2002u + 0x1F001F00u;  // paired ? 0x3F02 : 0x1F00
+    return G & T;
+}
+
 template <bool PILES>
 __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
-    const uint64_t nq = a.n >> 2;  // full quads
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const int4 *mid4 = reinterpret_cast<const int4 *>(a.mid);
-    const uint32_t *mq4 = reinterpret_cast<const uint32_t *>(a.mapq);
-    const uint2 *fl4 = reinterpret_cast<const uint2 *>(a.flags);
+    const uint32_t nq = (uint32_t)(a.n >> 2);  // full quads (a launch covers < 2^32 reads)
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const int4 *__restrict__ mid4 = reinterpret_cast<const int4 *>(a.mid);
+    const uint32_t *__restrict__ mq4 = reinterpret_cast<const uint32_t *>(a.mapq);
+    const uint2 *__restrict__ fl4 = reinterpret_cast<const uint2 *>(a.flags);
+    const uint32_t lane = lane_id();
+    const uint32_t wl = a.div.d, wl2 = 2u * wl, wl3 = 3u * wl, wl4 = 4u * wl;
+    const uint32_t minq = a.min_mapq, minq8 = minq << 8, minq16 = minq << 16, minq24 = minq << 24;
+    constexpr uint32_t kFailFlags = 0x01000100u;  // "secondary" in both halves: never counted
     uint32_t n_proc = 0, n_skip = 0, n_oob = 0;
 
     // warp-uniform trip count so that the warp collectives below stay converged
-    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t warp_first = first - lane_id();
-    for (uint64_t qb = warp_first; qb < nq; qb += stride) {
-        const uint64_t q = qb + lane_id();
-        const bool valid = q < nq;
-        int4 m = make_int4(0, 0, 0, 0);
-        uint32_t mq = 0;
-        uint2 fl = make_uint2(0, 0);
-        if (valid) {
-            m = ld_stream(mid4 + q);
-            mq = ld_stream(mq4 + q);
-            fl = ld_stream(fl4 + q);
+    uint32_t qb = blockIdx.x * blockDim.x + threadIdx.x - lane;
+    // software pipeline: the loads of step i+1 are in flight while step i is classified
+    int4 m = make_int4(0, 0, 0, 0);
+    uint32_t mq = 0;
+    uint2 fl = make_uint2(kFailFlags, kFailFlags);
+    if (qb + lane < nq) {
+        m = ld_stream(mid4 + qb + lane);
+        mq = ld_stream(mq4 + qb + lane);
+        fl = ld_stream(fl4 + qb + lane);
+    }
+    for (; qb < nq; qb += stride) {
+        const int4 cm = m;
+        const uint32_t cmq = mq;
+        const uint2 cfl = fl;
+        const uint32_t nx = qb + stride + lane;
+        fl = make_uint2(kFailFlags, kFailFlags);
+        if (nx < nq && nx >= stride) {  // (second test: no wrap-around of the 32-bit index)
+            m = ld_stream(mid4 + nx);
+            mq = ld_stream(mq4 + nx);
+            fl = ld_stream(fl4 + nx);
         }
-        const uint32_t mids[4] = {(uint32_t)m.x, (uint32_t)m.y, (uint32_t)m.z, (uint32_t)m.w};
-        const uint32_t fs[4] = {fl.x & 0xffffu, fl.x >> 16, fl.y & 0xffffu, fl.y >> 16};
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            w[e] = valid ? gw_weight<PILES>(a, mids[e], (mq >> (8 * e)) & 0xffu, fs[e], n_proc, n_skip)
-                         : 0u;
-        // bin of the first element; the other three almost always share it (sorted input)
-        const uint32_t b0 = fastdiv(mids[0], a.div);
-        const uint32_t lo = b0 * a.div.d;
-        bool uniform = true;
-#pragma unroll
-        for (int e = 1; e < 4; ++e) uniform = uniform && ((mids[e] - lo) < a.div.d || w[e] == 0u);
-        const uint32_t wsum = w[0] + w[1] + w[2] + w[3];
-        if (__all_sync(0xffffffffu, uniform)) {
-            uint32_t cnt = wsum;
-            if (cnt && b0 >= a.num_bins) {
-                n_oob += cnt;
-                cnt = 0;
-            }
-            warp_bin_add(a.counters, b0, cnt);
-        } else {
+        const uint32_t mids[4] = {(uint32_t)cm.x, (uint32_t)cm.y, (uint32_t)cm.z, (uint32_t)cm.w};
+        const uint32_t x0 = frag_fail2(cfl.x), x1 = frag_fail2(cfl.y);
+        bool w[4];
+        // mapq bytes are compared in place (byte e >= minq  <=>  masked word >= minq << 8e)
+        w[0] = ((x0 & 0xffffu) == 0u) && ((cmq & 0xffu) >= minq);
+        w[1] = ((x0 >> 16) == 0u) && ((cmq & 0xff00u) >= minq8);
+        w[2] = ((x1 & 0xffffu) == 0u) && ((cmq & 0xff0000u) >= minq16);
+        w[3] = ((x1 >> 16) == 0u) && (cmq >= minq24);
+        if (PILES) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const uint32_t b = fastdiv(mids[e], a.div);
-                uint32_t cnt = w[e];
-                if (cnt && b >= a.num_bins) {
-                    n_oob += cnt;
-                    cnt = 0;
+                n_proc += w[e];
+                if (w[e] && pile_hit(a.pile_start, a.pile_end, a.n_pile, mids[e])) {
+                    w[e] = false;
+                    n_skip += 1;
                 }
-                warp_bin_add(a.counters, b, cnt);
+            }
+        }
+        // anchor window: the first counting read of the warp
+        const uint32_t lane_anchor = w[0] ? mids[0] : (w[1] ? mids[1] : (w[2] ? mids[2] : mids[3]));
+        const unsigned has = __ballot_sync(0xffffffffu, w[0] || w[1] || w[2] || w[3]);
+        if (has == 0u) continue;
+        const uint32_t amid = __shfl_sync(0xffffffffu, lane_anchor, __ffs(has) - 1);
+        const uint32_t A = fastdiv(amid, a.div);
+        const uint32_t base = (A - 1u) * wl;  // may wrap for A == 0; differences below stay exact
+        uint32_t acc = 0u, outl = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t r = mids[e] - base;
+            const uint32_t inc = r < wl ? 1u : (r < wl2 ? 0x100u : (r < wl3 ? 0x10000u : 0x1000000u));
+            const bool in4 = r < wl4;
+            acc += (w[e] && in4) ? inc : 0u;
+            outl |= (w[e] && !in4) ? (1u << e) : 0u;
+        }
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, acc);
+        // without piles every read passing the filter is counted: tally per warp, not per read
+        if (!PILES && lane == 0u) n_proc += (tot * 0x01010101u) >> 24;
+        if (lane < 4u) {
+            const uint32_t cnt = (tot >> (8u * lane)) & 0xffu;
+            const uint32_t bin = A - 1u + lane;
+            if (cnt) {
+                if (bin < a.num_bins) atomicAdd(&a.counters[bin], cnt); else n_oob += cnt;
+            }
+        }
+        if (__any_sync(0xffffffffu, outl != 0u)) {  // reads far from the anchor: one RED each
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (outl & (1u << e)) {
+                    if (!PILES) n_proc += 1;
+                    const uint32_t b = fastdiv(mids[e], a.div);
+                    if (b < a.num_bins) atomicAdd(&a.counters[b], 1u); else n_oob += 1;
+                }
             }
         }
     }
     // tail (n % 4 reads): one thread, direct atomics
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (uint64_t i = nq << 2; i < a.n; ++i) {
+        for (uint64_t i = (uint64_t)nq << 2; i < a.n; ++i) {
             const uint32_t mid = (uint32_t)a.mid[i];
             if (gw_weight<PILES>(a, mid, a.mapq[i], a.flags[i], n_proc, n_skip)) {
                 const uint32_t b = fastdiv(mid, a.div);
@@ -160,7 +209,7 @@ __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
     n_proc = __reduce_add_sync(0xffffffffu, n_proc);
     n_skip = __reduce_add_sync(0xffffffffu, n_skip);
     n_oob = __reduce_add_sync(0xffffffffu, n_oob);
-    if (lane_id() == 0) {
+    if (lane == 0) {
         if (n_proc) atomicAdd(&a.stats[0], n_proc);
         if (n_skip) atomicAdd(&a.stats[1], n_skip);
         if (n_oob) atomicAdd(&a.stats[2], n_oob);
@@ -405,7 +454,9 @@ int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
     cnvb_ctx *ctx = a->ctx;
     if (!b->mid || !b->mapq || !b->flags)
         return fail(ctx, CNVB_ERR_INVALID, "GenomeWide batches need mid, mapq and flags");
-    const uint64_t chunk = b->mem == CNVB_MEM_DEVICE ? b->n : (b->n < kChunkReads ? b->n : kChunkReads);
+    constexpr uint64_t kMaxLaunchReads = 1ull << 31;
+    const uint64_t chunk = b->mem == CNVB_MEM_DEVICE ? (b->n < kMaxLaunchReads ? b->n : kMaxLaunchReads)
+                                                     : (b->n < kChunkReads ? b->n : kChunkReads);
     int32_t *s_mid = nullptr;
     uint8_t *s_mq = nullptr;
     uint16_t *s_fl = nullptr;

@@ -1,144 +1,125 @@
 // refstats.cu -- ReferenceStats::look_at_chars (lib-coverage/src/reference.rs:84-130).
 //
 // Per window: gc = #[GCgc] / #[ACGTacgt] (f32, missing if no ACGT), has_gap = any [Nn].
-// HBM-streaming byte kernel, 1 B/base: every lane loads 16 sequence bytes with one 128-bit load
-// and classifies them with SWAR byte tests (no per-byte branches, no lookup table):
-//   [CGcg] <=> (b & 0xDB) == 0x43      [Aa] <=> (b & 0xDF) == 0x41
-//   [Tt]   <=> (b & 0xDF) == 0x54      [Nn] <=> (b & 0xDF) == 0x4E
-// A lane's 16 bytes belong to at most two windows (wl >= 16); per-lane counts are combined with
-// one warp REDUX per distinct window and leave the SM as one RED per (warp step, window).
+// HBM-streaming byte kernel, algorithmic traffic 1 B/base in, 5 B/window out.
+//
+// A byte-at-a-time (or SWAR) classifier is instruction-issue bound long before HBM is busy
+// (round-1 ncu: 0.8 warp instructions per byte, 12 % DRAM throughput).  This kernel classifies
+// TWO bytes per shared-memory lookup: a 65536-entry u16 table (128 KB, built in the CTA's shared
+// memory at kernel start; one persistent 1024-thread CTA per SM) maps a byte pair to its packed
+// class counts
+//   bits 0..4 #[GCgc]   bits 5..9 #[ACGTacgt]   bits 10..14 #[Nn]
+// with   [CGcg] <=> (b & 0xDB) == 0x43    [Aa] <=> (b & 0xDF) == 0x41
+//        [Tt]   <=> (b & 0xDF) == 0x54    [Nn] <=> (b & 0xDF) == 0x4E
+// so a lane turns its 16 bytes (one 128-bit load) into counts with 8 LDS.U16 + 7 adds.  A group
+// of G lanes (power of two, 16*G >= wl + 30) owns one window per pass: the lanes read the
+// aligned 16-byte chunks overlapping the window (coalesced), bytes outside the window are zeroed
+// (0x00 belongs to no class), the group reduces with REDUX / shuffles and its first lane writes
+// gc and has_gap directly -- no counters in HBM, no atomics, no memset, no finalize pass,
+// bit-reproducible.
 #include "common.cuh"
 
 using namespace cnvb;
 
 namespace {
 
-// 0x80 in every byte of y that is zero (exact, no cross-byte carries)
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) {
-    const uint32_t t = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    return ~(t | y) & 0x80808080u;
-}
-
 __device__ __forceinline__ uint32_t byte_mask_below(int k) {  // bytes with index < k (k in 0..4)
     return k >= 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1u);
 }
 
-// number of flagged bytes with chunk index in [lo, hi)
-__device__ __forceinline__ uint32_t count_flags(const uint32_t f[4], int lo, int hi) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int a = min(max(lo - 4 * j, 0), 4), b = min(max(hi - 4 * j, 0), 4);
-        const uint32_t m = byte_mask_below(b) & ~byte_mask_below(a);
-        c |= (f[j] & m) >> (7 - j);
-    }
-    return __popc(c);
-}
-__device__ __forceinline__ uint32_t count_flags_all(const uint32_t f[4]) {
-    return __popc((f[0] >> 7) | (f[1] >> 6) | (f[2] >> 5) | (f[3] >> 4));
-}
-
 struct RefArgs {
-    const uint8_t *seq;  // original pointer
+    const uint8_t *seq;
     uint64_t len;
     uint32_t wl;
-    FastDiv div;  // only valid while len < 2^32; 64-bit division otherwise
-    uint32_t *gc_cnt, *acgt_cnt, *n_cnt;
 };
 
-__device__ __forceinline__ void warp_window_add(const RefArgs &a, uint32_t win, uint32_t packed) {
-    const uint32_t lane = lane_id();
-    unsigned todo = __ballot_sync(0xffffffffu, packed != 0u);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const uint32_t w = __shfl_sync(0xffffffffu, win, leader);
-        const unsigned same = __ballot_sync(0xffffffffu, win == w) & todo;
-        const uint32_t v = ((same >> lane) & 1u) ? packed : 0u;
-        const uint32_t tot = __reduce_add_sync(0xffffffffu, v);
-        if ((int)lane == leader) {
-            const uint32_t g = tot & 0x3ffu, c = (tot >> 10) & 0x3ffu, n = tot >> 20;
-            if (g) atomicAdd(&a.gc_cnt[w], g);
-            if (c) atomicAdd(&a.acgt_cnt[w], c);
-            if (n) atomicAdd(&a.n_cnt[w], n);
-        }
-        todo &= ~same;
-    }
+__device__ __forceinline__ uint32_t ref_class(uint32_t b) {
+    const uint32_t isgc = (b & 0xDBu) == 0x43u, x = b & 0xDFu;
+    const uint32_t isacgt = isgc | (x == 0x41u) | (x == 0x54u);
+    const uint32_t isn = x == 0x4Eu;
+    return isgc | (isacgt << 5) | (isn << 10);
 }
 
-// requires wl >= 16
-__global__ void __launch_bounds__(256, 4) refstats_count_kernel(RefArgs a) {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(a.seq);
-    const uint32_t mis = (uint32_t)(addr & 15u);  // bytes before seq[0] in its 16-byte line
-    const uint4 *base = reinterpret_cast<const uint4 *>(addr - mis);
-    const uint64_t nchunks = (a.len + mis + 15) / 16;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t cb = first - lane_id(); cb < nchunks; cb += stride) {
-        const uint64_t c = cb + lane_id();
-        uint32_t winA = 0, packA = 0, winB = 0, packB = 0;
-        if (c < nchunks) {
-            const int4 raw = ld_stream(reinterpret_cast<const int4 *>(base + c));
-            const uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
-            uint32_t fgc[4], facgt[4], fn[4];
+struct RefWin {  // one window as seen by a lane group
+    uintptr_t as, ae, a0;  // absolute byte addresses: window start / end, first aligned chunk
+    uint32_t nchunks;      // aligned 16-byte chunks overlapping the window (0 = idle group)
+    uint64_t W;
+};
+
+__device__ __forceinline__ RefWin ref_window(const RefArgs &a, uint64_t W, uint64_t num_bins) {
+    RefWin r;
+    r.W = W;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(a.seq);
+    const uint64_t s = W * a.wl;
+    const uint64_t e = s + a.wl < a.len ? s + a.wl : a.len;
+    r.as = base + s;
+    r.ae = base + e;
+    r.a0 = r.as & ~(uintptr_t)15;
+    r.nchunks = W < num_bins ? (uint32_t)((r.ae - r.a0 + 15) >> 4) : 0u;
+    return r;
+}
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64_t num_bins,
+                                                               float *__restrict__ gc,
+                                                               uint8_t *__restrict__ has_gap) {
+    extern __shared__ uint16_t s_lut[];  // [65536]
+    for (uint32_t i = threadIdx.x; i < 65536u; i += blockDim.x)
+        s_lut[i] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
+    __syncthreads();
+    constexpr uint32_t kGroups = 32 / G;
+    const uint32_t lane = lane_id(), sub = lane % G, grp = lane / G;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t step = (uint64_t)gridDim.x * (blockDim.x >> 5) * kGroups;
+    uint64_t W0 = warp_global * kGroups;
+    // software pipeline: the first chunk of the next window is in flight while this one is counted
+    RefWin nxt = ref_window(a, W0 + grp, num_bins);
+    int4 nraw = make_int4(0, 0, 0, 0);
+    if (sub < nxt.nchunks) nraw = ld_stream(reinterpret_cast<const int4 *>(nxt.a0 + ((uintptr_t)sub << 4)));
+    for (; W0 < num_bins; W0 += step) {
+        const RefWin cur = nxt;
+        int4 raw = nraw;
+        nxt = ref_window(a, W0 + step + grp, num_bins);
+        if (sub < nxt.nchunks) nraw = ld_stream(reinterpret_cast<const int4 *>(nxt.a0 + ((uintptr_t)sub << 4)));
+        uint32_t g = 0, c = 0, n = 0;
+        for (uint32_t k = sub; k < cur.nchunks; k += G) {
+            const uintptr_t ca = cur.a0 + ((uintptr_t)k << 4);
+            if (k != sub) raw = ld_stream(reinterpret_cast<const int4 *>(ca));
+            uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+            if (ca < cur.as || ca + 16 > cur.ae) {  // first / last chunk: zero the foreign bytes
+                const int lo = ca < cur.as ? (int)(cur.as - ca) : 0;
+                const int hi = ca + 16 > cur.ae ? (int)(cur.ae - ca) : 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t x = w[j] & 0xDFDFDFDFu;
-                fgc[j] = zero_bytes((w[j] & 0xDBDBDBDBu) ^ 0x43434343u);
-                facgt[j] = fgc[j] | zero_bytes(x ^ 0x41414141u) | zero_bytes(x ^ 0x54545454u);
-                fn[j] = zero_bytes(x ^ 0x4E4E4E4Eu);
+                for (int j = 0; j < 4; ++j) {
+                    const int x = min(max(lo - 4 * j, 0), 4), y = min(max(hi - 4 * j, 0), 4);
+                    w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
+                }
             }
-            // sequence offsets covered by this chunk: [o, o+16) clipped to [0, len)
-            const int64_t o = (int64_t)(c * 16) - mis;
-            const int lo = o < 0 ? (int)(-o) : 0;
-            const int hi = (uint64_t)(o + 16) > a.len ? (int)((int64_t)a.len - o) : 16;
-            const uint64_t p0 = (uint64_t)(o + lo);
-            const uint64_t wA = a.len <= 0xFFFFFFFFull ? fastdiv((uint32_t)p0, a.div) : p0 / a.wl;
-            const uint64_t boundary = (wA + 1) * a.wl;  // first offset of the next window
-            winA = (uint32_t)wA;
-            winB = winA + 1;
-            if (lo == 0 && hi == 16 && boundary >= (uint64_t)(o + 16)) {
-                packA = count_flags_all(fgc) | (count_flags_all(facgt) << 10) | (count_flags_all(fn) << 20);
-            } else {
-                const int split = boundary < (uint64_t)(o + hi) ? (int)(boundary - o) : hi;
-                packA = count_flags(fgc, lo, split) | (count_flags(facgt, lo, split) << 10) |
-                        (count_flags(fn, lo, split) << 20);
-                packB = count_flags(fgc, split, hi) | (count_flags(facgt, split, hi) << 10) |
-                        (count_flags(fn, split, hi) << 20);
+            uint32_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sum += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
+            g += sum & 31u;
+            c += (sum >> 5) & 31u;
+            n += sum >> 10;
+        }
+        if (G == 32) {
+            g = __reduce_add_sync(0xffffffffu, g);
+            c = __reduce_add_sync(0xffffffffu, c);
+            n = __reduce_add_sync(0xffffffffu, n);
+        } else {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                g += __shfl_xor_sync(0xffffffffu, g, o);
+                c += __shfl_xor_sync(0xffffffffu, c, o);
+                n += __shfl_xor_sync(0xffffffffu, n, o);
             }
         }
-        warp_window_add(a, winA, packA);
-        if (__any_sync(0xffffffffu, packB != 0u)) warp_window_add(a, winB, packB);
+        if (cur.nchunks && sub == 0) {
+            // reference.rs:120-127: i32 counts -> f32 ratio, f32::missing() if no ACGT
+            gc[cur.W] = c == 0 ? f32_missing() : __fdiv_rn((float)g, (float)c);
+            has_gap[cur.W] = n != 0;
+        }
     }
-}
-
-// any window length (used for wl < 16): one thread per window
-__global__ void refstats_small_kernel(RefArgs a, uint64_t num_bins) {
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= num_bins) return;
-    const uint64_t lo = w * a.wl, hi = min(lo + a.wl, a.len);
-    uint32_t g = 0, c = 0, n = 0;
-    for (uint64_t i = lo; i < hi; ++i) {
-        const uint32_t b = a.seq[i];
-        const uint32_t isgc = (b & 0xDBu) == 0x43u, x = b & 0xDFu;
-        g += isgc;
-        c += isgc | (x == 0x41u) | (x == 0x54u);
-        n += x == 0x4Eu;
-    }
-    a.gc_cnt[w] = g;
-    a.acgt_cnt[w] = c;
-    a.n_cnt[w] = n;
-}
-
-__global__ void refstats_finalize_kernel(const uint32_t *__restrict__ gc_cnt,
-                                         const uint32_t *__restrict__ acgt_cnt,
-                                         const uint32_t *__restrict__ n_cnt, uint64_t num_bins,
-                                         float *__restrict__ gc, uint8_t *__restrict__ has_gap) {
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= num_bins) return;
-    const uint32_t c = acgt_cnt[w];
-    // reference.rs:120-127: i32 counts -> f32 ratio, f32::missing() if the window has no ACGT
-    gc[w] = c == 0 ? f32_missing() : __fdiv_rn((float)gc_cnt[w], (float)c);
-    has_gap[w] = n_cnt[w] != 0;
 }
 
 }  // namespace
@@ -151,13 +132,12 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
     const uint64_t nb = (len + window_length - 1) / window_length;  // reference.rs:91
     if (nb == 0) return CNVB_OK;
     CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
-    CNVB_TRY(ensure_scratch(ctx, Carver::need({nb * 4, nb * 4, nb * 4, nb * 4, nb})));
-    Carver c(ctx->scratch);
-    uint32_t *cnt = c.take<uint32_t>(nb * 3);
     float *d_gc = gc;
     uint8_t *d_gap = has_gap;
     const uint8_t *d_seq = seq;
     if (mem != CNVB_MEM_DEVICE) {
+        CNVB_TRY(ensure_scratch(ctx, Carver::need({nb * 4, nb})));
+        Carver c(ctx->scratch);
         d_gc = c.take<float>(nb);
         d_gap = c.take<uint8_t>(nb);
         CNVB_TRY(ensure_stage(ctx, len + 16));
@@ -169,28 +149,32 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
     a.seq = d_seq;
     a.len = len;
     a.wl = window_length;
-    a.div = make_fastdiv(window_length);
-    a.gc_cnt = cnt;
-    a.acgt_cnt = cnt + nb;
-    a.n_cnt = cnt + 2 * nb;
-    if (window_length >= 16) {
-        CNVB_CUDA(ctx, cudaMemsetAsync(cnt, 0, nb * 12, ctx->stream), "clearing window counters");
-        const uint64_t nchunks = (len + 15 + 15) / 16;
-        uint64_t blocks = (nchunks + 255) / 256;
-        const uint64_t mb = (uint64_t)ctx->sm_count * 8;
-        if (blocks > mb) blocks = mb;
-        {
-            KernelSpan span(ctx, "refstats_count_kernel");
-            refstats_count_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+    {
+        // lane group size: 16*G bytes must cover a window plus up to 15+15 bytes of misalignment
+        int G = 2;
+        while (G < 32 && (uint64_t)16 * G < (uint64_t)window_length + 30) G <<= 1;
+        const size_t smem = 65536 * sizeof(uint16_t);
+        const uint64_t groups = 32 / G;
+        uint64_t blocks = (nb + 32 * groups - 1) / (32 * groups);
+        if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;  // persistent: one CTA per SM
+        KernelSpan span(ctx, "refstats_lut_kernel");
+#define CNVB_REF_LAUNCH(GG)                                                                          \
+    case GG:                                                                                         \
+        CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_kernel<GG>,                                 \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                  "smem opt-in");                                                                    \
+        refstats_lut_kernel<GG><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, nb, d_gc, d_gap);  \
+        break;
+        switch (G) {
+            CNVB_REF_LAUNCH(2)
+            CNVB_REF_LAUNCH(4)
+            CNVB_REF_LAUNCH(8)
+            CNVB_REF_LAUNCH(16)
+            CNVB_REF_LAUNCH(32)
         }
-        CNVB_LAUNCHED(ctx, "refstats_count_kernel");
-    } else {
-        refstats_small_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(a, nb);
-        CNVB_LAUNCHED(ctx, "refstats_small_kernel");
+#undef CNVB_REF_LAUNCH
     }
-    refstats_finalize_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(
-        a.gc_cnt, a.acgt_cnt, a.n_cnt, nb, d_gc, d_gap);
-    CNVB_LAUNCHED(ctx, "refstats_finalize_kernel");
+    CNVB_LAUNCHED(ctx, "refstats_lut_kernel");
     if (mem != CNVB_MEM_DEVICE) {
         CNVB_CUDA(ctx, cudaMemcpyAsync(gc, d_gc, nb * 4, cudaMemcpyDeviceToHost, ctx->stream), "copy gc");
         CNVB_CUDA(ctx, cudaMemcpyAsync(has_gap, d_gap, nb, cudaMemcpyDeviceToHost, ctx->stream), "copy has_gap");

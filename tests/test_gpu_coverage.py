@@ -213,7 +213,8 @@ def test_refstats_parity(oracle, ctx, wl, off, device):
         rs = cb.ReferenceStats.look_at_chars(seq, wl, ctx=ctx)
     assert_f32_equal_bits(rs.gc_content, gc, "gc")
     assert np.array_equal(to_np(rs.has_gap), gap)
-    assert np.isnan(gc).any() and gap.any()
+    if wl <= 1000:
+        assert np.isnan(gc).any() and gap.any()
 
 
 def test_refstats_all_bytes(oracle, ctx):
@@ -231,7 +232,7 @@ def _lcv_gc(seed, n):
     gc = rng.beta(8, 11, n).astype(np.float32)
     gc[rng.random(n) < 0.01] = np.frombuffer(np.uint32(0x7F800001).tobytes(), np.float32)[0]
     gc[:3] = [0.0, 1.0, 0.999]
-    lcv = (rng.poisson(60 * (0.5 + gc.astype(np.float64).clip(0, 1)), n) / 500.0).astype(np.float32)
+    lcv = (rng.poisson(60 * (0.5 + np.nan_to_num(gc.astype(np.float64)).clip(0, 1)), n) / 500.0).astype(np.float32)
     lcvsd = rng.random(n).astype(np.float32)
     return lcv, gc, lcvsd
 
