@@ -41,6 +41,8 @@ struct cnvb_ctx {
     // pinned host slots for asynchronous read-back of per-aggregator tallies
     uint32_t *tally_slots = nullptr;  // kTallySlots x 4 u32
     uint32_t tally_next = 0;
+    // resident CTAs per SM of each persistent kernel (cudaOccupancy... is not free: cached)
+    std::unordered_map<const void *, int> occupancy;
     // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
     bool timing = false;
     std::vector<std::string> span_names;
@@ -148,6 +150,26 @@ inline int ensure_stage(cnvb_ctx *ctx, size_t bytes) {
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Grid size of a persistent (grid-stride) kernel: exactly one wave of resident CTAs, so that no
+// partial second wave leaves SMs idle at the end (148 SMs x resident CTAs per SM).
+template <typename K>
+inline unsigned persistent_grid(cnvb_ctx *ctx, K kernel, int threads, size_t smem, uint64_t work_blocks) {
+    const void *key = reinterpret_cast<const void *>(kernel);
+    auto it = ctx->occupancy.find(key);
+    int per_sm;
+    if (it == ctx->occupancy.end()) {
+        per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        ctx->occupancy[key] = per_sm;
+    } else {
+        per_sm = it->second;
+    }
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+    if (work_blocks < grid) grid = work_blocks;
+    return grid ? (unsigned)grid : 1u;
+}
 
 constexpr uint32_t kTallySlots = 4096;
 

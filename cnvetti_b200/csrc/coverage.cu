@@ -66,6 +66,8 @@ struct GwArgs {
     uint32_t *counters;
     uint32_t num_bins;
     FastDiv div;
+    uint32_t magic_up;  // ceil(2^32 / wl)
+    uint32_t wl_small;  // wl <= 32768: magic_up division is exact below 4*wl
     uint32_t min_mapq;
     const uint32_t *pile_start, *pile_end;
     uint32_t n_pile;
@@ -106,7 +108,7 @@ __device__ __forceinline__ uint32_t frag_fail2(uint32_t F) {
     return G & T;
 }
 
-template <bool PILES>
+template <bool PILES, bool WL_SMALL>
 __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
     const uint32_t nq = (uint32_t)(a.n >> 2);  // full quads (a launch covers < 2^32 reads)
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
     const uint32_t *__restrict__ mq4 = reinterpret_cast<const uint32_t *>(a.mapq);
     const uint2 *__restrict__ fl4 = reinterpret_cast<const uint2 *>(a.flags);
     const uint32_t lane = lane_id();
-    const uint32_t wl = a.div.d, wl2 = 2u * wl, wl3 = 3u * wl, wl4 = 4u * wl;
+    const uint32_t wl = a.div.d;
     const uint32_t minq = a.min_mapq, minq8 = minq << 8, minq16 = minq << 16, minq24 = minq << 24;
     constexpr uint32_t kFailFlags = 0x01000100u;  // "secondary" in both halves: never counted
     uint32_t n_proc = 0, n_skip = 0, n_oob = 0;
@@ -169,10 +171,14 @@ __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
         uint32_t acc = 0u, outl = 0u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+            // window offset k = (mid - base) / wl by a multiply-high (FMA pipe) instead of a chain
+            // of compares (ALU pipe, the binding pipe of this kernel): with the rounded-UP magic
+            // the quotient is exact for r < 4*wl whenever 4*wl^2 <= 2^32, and any r >= 4*wl still
+            // yields k >= 4, which is all the outlier test needs.
             const uint32_t r = mids[e] - base;
-            const uint32_t inc = r < wl ? 1u : (r < wl2 ? 0x100u : (r < wl3 ? 0x10000u : 0x1000000u));
-            const bool in4 = r < wl4;
-            acc += (w[e] && in4) ? inc : 0u;
+            const uint32_t k = WL_SMALL ? __umulhi(r, a.magic_up) : fastdiv(r, a.div);
+            const bool in4 = k < 4u;
+            acc += (w[e] && in4) ? (1u << (8u * k)) : 0u;
             outl |= (w[e] && !in4) ? (1u << e) : 0u;
         }
         const uint32_t tot = __reduce_add_sync(0xffffffffu, acc);
@@ -477,6 +483,8 @@ int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
         g.counters = a->d_counters;
         g.num_bins = (uint32_t)a->num_regions;
         g.div = make_fastdiv(a->opts.window_length);
+        g.magic_up = (uint32_t)(((1ull << 32) + a->opts.window_length - 1) / a->opts.window_length);
+        g.wl_small = a->opts.window_length >= 2 && a->opts.window_length <= 32768;
         g.min_mapq = a->opts.min_mapq;
         g.pile_start = a->d_pile_start;
         g.pile_end = a->d_pile_end;
@@ -485,18 +493,23 @@ int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
         const bool aligned = ((uintptr_t)g.mid % 16 == 0) && ((uintptr_t)g.mapq % 4 == 0) &&
                              ((uintptr_t)g.flags % 8 == 0);
         const uint64_t work = aligned ? (n + 3) / 4 : n;
-        uint64_t blocks = (work + 255) / 256;
-        const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;  // persistent, grid-stride
-        if (blocks > max_blocks) blocks = max_blocks;
-        if (blocks == 0) blocks = 1;
+        const uint64_t work_blocks = (work + 255) / 256;
         {
             KernelSpan span(ctx, "frag_bin_gw_kernel");
             if (aligned) {
-                if (a->n_pile) frag_bin_gw_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(g);
-                else frag_bin_gw_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(g);
+#define CNVB_GW_LAUNCH(P, S) \
+    frag_bin_gw_kernel<P, S><<<persistent_grid(ctx, frag_bin_gw_kernel<P, S>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g)
+                if (a->n_pile) {
+                    if (g.wl_small) CNVB_GW_LAUNCH(true, true); else CNVB_GW_LAUNCH(true, false);
+                } else {
+                    if (g.wl_small) CNVB_GW_LAUNCH(false, true); else CNVB_GW_LAUNCH(false, false);
+                }
+#undef CNVB_GW_LAUNCH
             } else {
-                if (a->n_pile) frag_bin_gw_scalar_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(g);
-                else frag_bin_gw_scalar_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(g);
+                if (a->n_pile)
+                    frag_bin_gw_scalar_kernel<true><<<persistent_grid(ctx, frag_bin_gw_scalar_kernel<true>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);
+                else
+                    frag_bin_gw_scalar_kernel<false><<<persistent_grid(ctx, frag_bin_gw_scalar_kernel<false>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);
             }
         }
         CNVB_LAUNCHED(ctx, "frag_bin_gw_kernel");

@@ -172,14 +172,13 @@ int put_targets(cnvb_ctx *ctx, const cnvb_read_soa *b, const uint32_t *d_ts, con
         const bool aligned = ((uintptr_t)g.pos % 16 == 0) && ((uintptr_t)g.frag_end % 16 == 0) &&
                              ((uintptr_t)g.mapq % 4 == 0) && ((uintptr_t)g.flags % 8 == 0);
         const uint64_t work = aligned ? (n + 3) / 4 : n;
-        uint64_t blocks = (work + 255) / 256;
-        const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
-        if (blocks > max_blocks) blocks = max_blocks;
-        if (blocks == 0) blocks = 1;
+        const uint64_t work_blocks = (work + 255) / 256;
         {
             KernelSpan span(ctx, "frag_bin_tgt_kernel");
-            if (aligned) frag_bin_tgt_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(g);
-            else frag_bin_tgt_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(g);
+            if (aligned)
+                frag_bin_tgt_kernel<true><<<persistent_grid(ctx, frag_bin_tgt_kernel<true>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);
+            else
+                frag_bin_tgt_kernel<false><<<persistent_grid(ctx, frag_bin_tgt_kernel<false>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);
         }
         CNVB_LAUNCHED(ctx, "frag_bin_tgt_kernel");
     }

@@ -40,6 +40,111 @@ __device__ __forceinline__ uint32_t ref_class(uint32_t b) {
     return isgc | (isacgt << 5) | (isn << 10);
 }
 
+__device__ __forceinline__ void ref_store(float *__restrict__ gc, uint8_t *__restrict__ has_gap, uint64_t W,
+                                          uint32_t g, uint32_t c, uint32_t n) {
+    // reference.rs:120-127: i32 counts -> f32 ratio, f32::missing() if the window has no ACGT
+    gc[W] = c == 0 ? f32_missing() : __fdiv_rn((float)g, (float)c);
+    has_gap[W] = n != 0;
+}
+
+// Full-warp variant (G = 32, wl >= 226): one window per warp pass.
+//  * lanes 0..30 take the interior 16-byte chunks (all bytes inside the window, no masking),
+//  * the first and the last chunk of the window are shared with the neighbouring windows; their
+//    up to 16+16 bytes are classified one byte per lane (lanes 0..15 / 16..31) through the same
+//    table (pair = byte | 0x00 << 8), so no lane ever runs a masking slow path,
+//  * window totals come from ONE REDUX over 10-bit packed fields when wl < 1024 (PACKED), else
+//    from three; the warp parks them in lane (pass mod 32) and every 32 passes all lanes do
+//    their f32 division and stores together.
+// Offsets are 32-bit (the host guarantees len + 16 < 2^32) and advance incrementally.
+template <bool PACKED>
+__global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, uint32_t num_bins,
+                                                                    float *__restrict__ gc,
+                                                                    uint8_t *__restrict__ has_gap) {
+    extern __shared__ uint16_t s_lut[];  // [65536]
+    for (uint32_t i = threadIdx.x; i < 65536u; i += blockDim.x)
+        s_lut[i] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const uint32_t step = gridDim.x * (blockDim.x >> 5);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(a.seq);
+    const uint32_t mis = (uint32_t)(addr & 15u);
+    const uint8_t *__restrict__ basep = reinterpret_cast<const uint8_t *>(addr - mis);  // 16-byte aligned
+    const int4 *__restrict__ base4 = reinterpret_cast<const int4 *>(basep);
+    const uint32_t wl = a.wl, end_off = (uint32_t)a.len + mis, stride_off = step * wl;
+    const uint32_t edge_hi = lane >= 16u;         // this lane classifies a byte of the LAST chunk
+    const uint32_t edge_lane = lane & 15u;
+
+    uint32_t st_g = 0, st_c = 0, st_n = 0, st_w = 0xffffffffu;  // parked results of this lane
+    uint32_t W = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t os = W * wl + mis;  // offset of the window start from the aligned base
+    // prefetched inputs of the window about to be counted
+    int4 raw = make_int4(0, 0, 0, 0);
+    uint32_t ebyte = 0;
+    if (W < num_bins) {
+        const uint32_t oe = min(os + wl, end_off), cf = os >> 4, cl = (oe - 1u) >> 4;
+        if (cf + 1u + lane < cl) raw = ld_stream(base4 + cf + 1u + lane);
+        const uint32_t bo = ((edge_hi ? cl : cf) << 4) + edge_lane;
+        if (edge_hi ? bo < oe : bo >= os) ebyte = basep[bo];
+    }
+    for (uint32_t pass = 0; W < num_bins; W += step, os += stride_off, ++pass) {
+        const uint32_t oe = min(os + wl, end_off), cf = os >> 4, cl = (oe - 1u) >> 4;
+        const int4 craw = raw;
+        const uint32_t cbyte = ebyte;
+        raw = make_int4(0, 0, 0, 0);
+        ebyte = 0;
+        if (W + step < num_bins) {  // next window of this warp
+            const uint32_t osn = os + stride_off, oen = min(osn + wl, end_off);
+            const uint32_t cfn = osn >> 4, cln = (oen - 1u) >> 4;
+            if (cfn + 1u + lane < cln) raw = ld_stream(base4 + cfn + 1u + lane);
+            const uint32_t bo = ((edge_hi ? cln : cfn) << 4) + edge_lane;
+            if (edge_hi ? bo < oen : bo >= osn) ebyte = basep[bo];
+        }
+        // one edge byte + eight byte pairs: packed 5-bit counts, at most 17 per field
+        uint32_t t = s_lut[cbyte];
+        {
+            const uint32_t w[4] = {(uint32_t)craw.x, (uint32_t)craw.y, (uint32_t)craw.z, (uint32_t)craw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
+        }
+        uint32_t g = t & 31u, c = (t >> 5) & 31u, n = t >> 10;
+        if (cf + 33u < cl) {  // windows longer than 31 interior chunks (warp-uniform)
+            for (uint32_t k = cf + 33u + lane; __any_sync(0xffffffffu, k < cl); k += 32u) {
+                if (k < cl) {
+                    const int4 x = ld_stream(base4 + k);
+                    const uint32_t w[4] = {(uint32_t)x.x, (uint32_t)x.y, (uint32_t)x.z, (uint32_t)x.w};
+                    uint32_t u = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) u += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
+                    g += u & 31u;
+                    c += (u >> 5) & 31u;
+                    n += u >> 10;
+                }
+            }
+        }
+        if (PACKED) {  // wl < 1024: every field of the warp total fits in 10 bits
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, g | (c << 10) | (n << 20));
+            g = tot & 1023u;
+            c = (tot >> 10) & 1023u;
+            n = tot >> 20;
+        } else {
+            g = __reduce_add_sync(0xffffffffu, g);
+            c = __reduce_add_sync(0xffffffffu, c);
+            n = __reduce_add_sync(0xffffffffu, n);
+        }
+        if (lane == (pass & 31u)) {
+            st_g = g;
+            st_c = c;
+            st_n = n;
+            st_w = W;
+        }
+        if ((pass & 31u) == 31u) {
+            if (st_w != 0xffffffffu) ref_store(gc, has_gap, st_w, st_g, st_c, st_n);
+            st_w = 0xffffffffu;
+        }
+    }
+    if (st_w != 0xffffffffu) ref_store(gc, has_gap, st_w, st_g, st_c, st_n);
+}
+
 struct RefWin {  // one window as seen by a lane group
     uintptr_t as, ae, a0;  // absolute byte addresses: window start / end, first aligned chunk
     uint32_t nchunks;      // aligned 16-byte chunks overlapping the window (0 = idle group)
@@ -59,6 +164,8 @@ __device__ __forceinline__ RefWin ref_window(const RefArgs &a, uint64_t W, uint6
     return r;
 }
 
+// General variant: a group of G lanes per window (short windows, or sequences >= 4 GB).  Chunks
+// that stick out of the window are masked in registers.
 template <int G>
 __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64_t num_bins,
                                                                float *__restrict__ gc,
@@ -71,20 +178,12 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64
     const uint32_t lane = lane_id(), sub = lane % G, grp = lane / G;
     const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t step = (uint64_t)gridDim.x * (blockDim.x >> 5) * kGroups;
-    uint64_t W0 = warp_global * kGroups;
-    // software pipeline: the first chunk of the next window is in flight while this one is counted
-    RefWin nxt = ref_window(a, W0 + grp, num_bins);
-    int4 nraw = make_int4(0, 0, 0, 0);
-    if (sub < nxt.nchunks) nraw = ld_stream(reinterpret_cast<const int4 *>(nxt.a0 + ((uintptr_t)sub << 4)));
-    for (; W0 < num_bins; W0 += step) {
-        const RefWin cur = nxt;
-        int4 raw = nraw;
-        nxt = ref_window(a, W0 + step + grp, num_bins);
-        if (sub < nxt.nchunks) nraw = ld_stream(reinterpret_cast<const int4 *>(nxt.a0 + ((uintptr_t)sub << 4)));
+    for (uint64_t W0 = warp_global * kGroups; W0 < num_bins; W0 += step) {
+        const RefWin cur = ref_window(a, W0 + grp, num_bins);
         uint32_t g = 0, c = 0, n = 0;
         for (uint32_t k = sub; k < cur.nchunks; k += G) {
             const uintptr_t ca = cur.a0 + ((uintptr_t)k << 4);
-            if (k != sub) raw = ld_stream(reinterpret_cast<const int4 *>(ca));
+            const int4 raw = ld_stream(reinterpret_cast<const int4 *>(ca));
             uint32_t w[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
             if (ca < cur.as || ca + 16 > cur.ae) {  // first / last chunk: zero the foreign bytes
                 const int lo = ca < cur.as ? (int)(cur.as - ca) : 0;
@@ -102,23 +201,13 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64
             c += (sum >> 5) & 31u;
             n += sum >> 10;
         }
-        if (G == 32) {
-            g = __reduce_add_sync(0xffffffffu, g);
-            c = __reduce_add_sync(0xffffffffu, c);
-            n = __reduce_add_sync(0xffffffffu, n);
-        } else {
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                g += __shfl_xor_sync(0xffffffffu, g, o);
-                c += __shfl_xor_sync(0xffffffffu, c, o);
-                n += __shfl_xor_sync(0xffffffffu, n, o);
-            }
+        for (int o = G / 2; o > 0; o >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            n += __shfl_xor_sync(0xffffffffu, n, o);
         }
-        if (cur.nchunks && sub == 0) {
-            // reference.rs:120-127: i32 counts -> f32 ratio, f32::missing() if no ACGT
-            gc[cur.W] = c == 0 ? f32_missing() : __fdiv_rn((float)g, (float)c);
-            has_gap[cur.W] = n != 0;
-        }
+        if (cur.nchunks && sub == 0) ref_store(gc, has_gap, cur.W, g, c, n);
     }
 }
 
@@ -158,6 +247,19 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
         uint64_t blocks = (nb + 32 * groups - 1) / (32 * groups);
         if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;  // persistent: one CTA per SM
         KernelSpan span(ctx, "refstats_lut_kernel");
+        if (G == 32 && len < 0xFFFFFF00ull) {
+            blocks = (nb + 31) / 32;
+            if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;
+            if (window_length < 1024) {
+                CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_warp_kernel<true>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
+                refstats_lut_warp_kernel<true><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_gc, d_gap);
+            } else {
+                CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_warp_kernel<false>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
+                refstats_lut_warp_kernel<false><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_gc, d_gap);
+            }
+        } else {
 #define CNVB_REF_LAUNCH(GG)                                                                          \
     case GG:                                                                                         \
         CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_kernel<GG>,                                 \
@@ -165,14 +267,15 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
                   "smem opt-in");                                                                    \
         refstats_lut_kernel<GG><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, nb, d_gc, d_gap);  \
         break;
-        switch (G) {
-            CNVB_REF_LAUNCH(2)
-            CNVB_REF_LAUNCH(4)
-            CNVB_REF_LAUNCH(8)
-            CNVB_REF_LAUNCH(16)
-            CNVB_REF_LAUNCH(32)
-        }
+            switch (G) {
+                CNVB_REF_LAUNCH(2)
+                CNVB_REF_LAUNCH(4)
+                CNVB_REF_LAUNCH(8)
+                CNVB_REF_LAUNCH(16)
+                CNVB_REF_LAUNCH(32)
+            }
 #undef CNVB_REF_LAUNCH
+        }
     }
     CNVB_LAUNCHED(ctx, "refstats_lut_kernel");
     if (mem != CNVB_MEM_DEVICE) {
