@@ -9,6 +9,8 @@ from .coverage import (AggregationStats, BamRecordAggregator, CoverageAggregator
                        CoverageOptions, FragmentsGenomeWideAggregator,
                        FragmentsTargetRegionsAggregator, ReadBatch, ReferenceStats, cov_records,
                        make_aggregator, pack_reads)
+from . import model_wis  # noqa: F401
+from .model_wis import BuildModelWisOptions  # noqa: F401
 from .normalize import run_binned_correction, run_uncorrected_normalization  # noqa: F401
 
 __version__ = "0.1.0"

@@ -30,6 +30,12 @@ class CovOpts(C.Structure):
                 ("min_raw_coverage", C.c_uint32), ("plp_flag_mask", C.c_uint32)]
 
 
+class WisOpts(C.Structure):
+    _fields_ = [("filter_z_score", C.c_double), ("filter_rel", C.c_double),
+                ("min_ref_targets", C.c_uint32), ("max_ref_targets", C.c_uint32),
+                ("max_samples_reliable", C.c_uint32), ("engine", C.c_uint32)]
+
+
 # every symbol include/cnvetti_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _u32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 SYMBOLS = {
@@ -60,6 +66,14 @@ SYMBOLS = {
                                 _vp, _vp, _vp, _int]),
     "cnvb_norm_total": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _int]),
     "cnvb_norm_gc_median": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _int]),
+    "cnvb_wis_distances": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _u32, _u32, _vp, _vp, _int]),
+    "cnvb_wis_threshold": (_int, [_vp, _vp, _u32, _u32, C.c_double, C.POINTER(C.c_float), _int]),
+    "cnvb_wis_prune": (_int, [_vp, _vp, _vp, _u32, _u32, C.c_float, _vp, _int]),
+    "cnvb_wis_calls": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, C.POINTER(WisOpts), _u32, _u32, _vp, _int]),
+    "cnvb_wis_filters": (_int, [_vp, _vp, _vp, _u32, C.POINTER(WisOpts), _vp, _int]),
+    "cnvb_wis_build": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _vp, _vp, _vp, _vp, _vp,
+                              C.POINTER(C.c_float), _int]),
+    "cnvb_modcov": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
 }
 
 _lib = None

@@ -1,0 +1,599 @@
+// wis.cu -- lib-model-wis (WISExome-style within-sample model) and lib-mod-cov on sm_100a.
+//
+//   W2 compute_distances      lib-model-wis/src/lib.rs:128-197
+//   W3 prune_distances        lib-model-wis/src/lib.rs:200-232
+//   W4 count_per_probe_calls  lib-model-wis/src/lib.rs:235-271
+//   W5 write_output filters   lib-model-wis/src/lib.rs:362-377
+//   M1 load_target_infos / write_mod_cov values   lib-mod-cov/src/lib.rs:76-164, 209-240
+//
+// The reference distance is an f32 sum accumulated over the samples IN ORDER with separate
+// multiply and add roundings, then an f32 sqrt (lib.rs:157-162).  Every distance that is
+// reported or compared here is computed exactly that way (__fsub_rn/__fmul_rn/__fadd_rn/
+// __fsqrt_rn: no FMA contraction, no re-association), so reference-target sets and their order
+// are bit-exact.  The tensor-core engine (wis_tensor.cuh) only decides WHICH pairs get that
+// exact evaluation; it never contributes a reported number.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "dd.cuh"
+
+using namespace cnvb;
+
+namespace {
+
+constexpr uint32_t kMaxK = 1024;  // max_ref_targets supported by the selection kernels
+
+// exact reference distance between two panel rows (lib.rs:157-162)
+__device__ __forceinline__ float wis_ref_distance(const float *__restrict__ a, const float *__restrict__ b,
+                                                  uint32_t S, bool vec4) {
+    float y = 0.0f;
+    if (vec4) {
+        const float4 *a4 = reinterpret_cast<const float4 *>(a);
+        const float4 *b4 = reinterpret_cast<const float4 *>(b);
+        for (uint32_t s = 0; s < (S >> 2); ++s) {
+            const float4 p = a4[s], q = __ldg(b4 + s);
+            float x = __fsub_rn(p.x, q.x);
+            y = __fadd_rn(y, __fmul_rn(x, x));
+            x = __fsub_rn(p.y, q.y);
+            y = __fadd_rn(y, __fmul_rn(x, x));
+            x = __fsub_rn(p.z, q.z);
+            y = __fadd_rn(y, __fmul_rn(x, x));
+            x = __fsub_rn(p.w, q.w);
+            y = __fadd_rn(y, __fmul_rn(x, x));
+        }
+    } else {
+        for (uint32_t s = 0; s < S; ++s) {
+            const float x = __fsub_rn(a[s], __ldg(b + s));
+            y = __fadd_rn(y, __fmul_rn(x, x));
+        }
+    }
+    return __fsqrt_rn(y);
+}
+
+// (distance, index) lexicographic order: the documented tie rule
+__device__ __forceinline__ bool ent_less(float da, uint32_t ja, float db, uint32_t jb) {
+    return da < db || (da == db && ja < jb);
+}
+
+// ---- exact engine: one CTA per target row ---------------------------------------------------------
+// Streams every other-contig row past the target, keeps the k smallest (distance, index) pairs
+// in shared memory (threshold + buffer, bitonic compaction), independent of the column order.
+// Used for small panels and as the fallback of the tensor engine.
+constexpr int kRowThreads = 256;
+constexpr uint32_t kRowBuf = 2048;
+constexpr uint32_t kRowChunk = 1024;  // columns per pass: at most this many appends
+
+__device__ void bitonic_sort_pairs(float *d, uint32_t *j, uint32_t n /* power of two */) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const uint32_t lo = (t / stride) * (stride << 1) + (t % stride), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const float dl = d[lo], dh = d[hi];
+                const uint32_t jl = j[lo], jh = j[hi];
+                const bool swap = up ? ent_less(dh, jh, dl, jl) : ent_less(dl, jl, dh, jh);
+                if (swap) {
+                    d[lo] = dh;
+                    d[hi] = dl;
+                    j[lo] = jh;
+                    j[hi] = jl;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRowThreads) wis_row_exact_kernel(
+    const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S, uint32_t k,
+    const uint32_t *__restrict__ row_list, uint32_t row_begin, float *__restrict__ out_dist,
+    uint32_t *__restrict__ out_idx) {
+    extern __shared__ float s_xi[];  // [S]
+    __shared__ float s_d[kRowBuf];
+    __shared__ uint32_t s_j[kRowBuf];
+    __shared__ uint32_t s_cnt;
+    __shared__ float s_thr;
+    const uint32_t i = row_list ? row_list[blockIdx.x] : row_begin + blockIdx.x;
+    const uint32_t ti = tid[i];
+    const bool vec4 = (S & 3u) == 0u && (reinterpret_cast<uintptr_t>(X) & 15u) == 0u;
+    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) s_xi[s] = X[(size_t)i * S + s];
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        s_thr = __int_as_float(0x7f800000);  // +inf
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < T; base += kRowChunk) {
+        const float thr = s_thr;
+#pragma unroll
+        for (uint32_t q = 0; q < kRowChunk / kRowThreads; ++q) {
+            const uint32_t j = base + q * kRowThreads + threadIdx.x;
+            if (j < T && tid[j] != ti) {  // same contig (and j == i): +inf in the reference
+                const float d = wis_ref_distance(s_xi, X + (size_t)j * S, S, vec4);
+                if (d <= thr) {
+                    const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                    s_d[slot] = d;  // slot < kRowBuf: the buffer is compacted below kRowChunk first
+                    s_j[slot] = j;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_cnt > kRowBuf - kRowChunk) {  // next pass could overflow: keep the k smallest
+            const uint32_t n = s_cnt;
+            for (uint32_t t = n + threadIdx.x; t < kRowBuf; t += blockDim.x) {
+                s_d[t] = __int_as_float(0x7f800000);
+                s_j[t] = 0xffffffffu;
+            }
+            bitonic_sort_pairs(s_d, s_j, kRowBuf);
+            if (threadIdx.x == 0) {
+                s_cnt = n < k ? n : k;
+                if (n >= k) s_thr = s_d[k - 1];
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t n = s_cnt;
+    for (uint32_t t = n + threadIdx.x; t < kRowBuf; t += blockDim.x) {
+        s_d[t] = __int_as_float(0x7f800000);
+        s_j[t] = 0xffffffffu;
+    }
+    bitonic_sort_pairs(s_d, s_j, kRowBuf);
+    const size_t o = (size_t)(i - row_begin) * k;
+    const uint32_t m = n < k ? n : k;
+    for (uint32_t t = threadIdx.x; t < m; t += blockDim.x) {
+        out_dist[o + t] = s_d[t];
+        out_idx[o + t] = s_j[t];
+    }
+    // fewer than k other-contig targets: the reference's +inf entries fill up, in index order
+    if (threadIdx.x == 0 && m < k) {
+        uint32_t w = m;
+        for (uint32_t j = 0; j < T && w < k; ++j) {
+            if (tid[j] == ti) {
+                out_dist[o + w] = __int_as_float(0x7f800000);
+                out_idx[o + w] = j;
+                ++w;
+            }
+        }
+    }
+}
+
+// ---- W3 ----------------------------------------------------------------------------------------
+// threshold = (mean + z * sd) as f32 of the nearest distances (f64; exact-sum mean, n-1 SD)
+__device__ dd block_reduce_dd_1024(dd v) {
+    __shared__ double s_hi[32], s_lo[32];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dd_add(v, dd_shfl_xor(v, o));
+    __syncthreads();
+    if (lane == 0) {
+        s_hi[warp] = v.hi;
+        s_lo[warp] = v.lo;
+    }
+    __syncthreads();
+    v = lane < nw ? dd{s_hi[lane], s_lo[lane]} : dd{0.0, 0.0};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = dd_add(v, dd_shfl_xor(v, o));
+    return v;  // valid in every thread of every warp
+}
+
+__global__ void __launch_bounds__(1024) wis_threshold_kernel(const float *__restrict__ nearest, uint32_t T,
+                                                             uint32_t stride, double z, float *__restrict__ out) {
+    dd acc{0.0, 0.0};
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) acc = dd_add_d(acc, (double)nearest[(size_t)t * stride]);
+    acc = block_reduce_dd_1024(acc);
+    const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)T);  // Stats::mean
+    dd v{0.0, 0.0};
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
+        const double x = __dsub_rn((double)nearest[(size_t)t * stride], mean);
+        v = dd_add_d(v, __dmul_rn(x, x));
+    }
+    v = block_reduce_dd_1024(v);
+    if (threadIdx.x == 0) {
+        const double var = __ddiv_rn(__dadd_rn(v.hi, v.lo), (double)(T - 1));  // stats.rs:231-232
+        const double sd = __dsqrt_rn(var);
+        out[0] = (float)__dadd_rn(mean, __dmul_rn(z, sd));  // lib.rs:216
+    }
+}
+
+__global__ void wis_prune_kernel(const float *__restrict__ dist, uint32_t *__restrict__ idx, uint32_t rows,
+                                 uint32_t k, float thr, uint32_t *__restrict__ ref_len) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t m = 0;
+    for (uint32_t q = 0; q < k; ++q)  // lib.rs:221-228: keep while distance <= threshold, in order
+        if (dist[(size_t)r * k + q] <= thr) idx[(size_t)r * k + m++] = idx[(size_t)r * k + q];
+    ref_len[r] = m;
+}
+
+// ---- W4 ----------------------------------------------------------------------------------------
+// one CTA per target; threads stride over samples so that each reference row is read coalesced
+__global__ void __launch_bounds__(128) wis_calls_kernel(const float *__restrict__ X, uint32_t S,
+                                                        const uint32_t *__restrict__ ref_idx,
+                                                        const uint32_t *__restrict__ ref_len, uint32_t k,
+                                                        uint32_t min_ref, double zthr, double rel_thr,
+                                                        uint32_t row_begin, uint32_t *__restrict__ num_calls) {
+    __shared__ uint32_t s_ref[kMaxK];
+    __shared__ uint32_t s_calls;
+    const uint32_t r = blockIdx.x, t = row_begin + r;
+    const uint32_t m = ref_len[r];
+    if (threadIdx.x == 0) s_calls = 0;
+    for (uint32_t q = threadIdx.x; q < m; q += blockDim.x) s_ref[q] = ref_idx[(size_t)r * k + q];
+    __syncthreads();
+    uint32_t calls = 0;
+    if (m >= min_ref) {  // lib.rs:254-256
+        for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
+            dd acc{0.0, 0.0};
+            for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)s_ref[q] * S + s));
+            const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)m);
+            double v = 0.0;  // stats.rs:218-234: naive left-to-right, same order as the reference
+            for (uint32_t q = 0; q < m; ++q) {
+                const double d = __dsub_rn((double)__ldg(X + (size_t)s_ref[q] * S + s), mean);
+                v = __dadd_rn(v, __dmul_rn(d, d));
+            }
+            const double var = m < 2 ? 0.0 : __ddiv_rn(v, (double)(m - 1));
+            const double sd = __dsqrt_rn(var);
+            const double x = (double)X[(size_t)t * S + s];
+            const double zs = __ddiv_rn(fabs(__dsub_rn(x, mean)), sd);  // lib.rs:260
+            const double rel = __ddiv_rn(x, mean);                      // lib.rs:262
+            if (zs > zthr && fabs(__dsub_rn(rel, 1.0)) > rel_thr) calls += 1;  // lib.rs:264-266
+        }
+    }
+    calls = __reduce_add_sync(0xffffffffu, calls);
+    if (lane_id() == 0 && calls) atomicAdd(&s_calls, calls);
+    __syncthreads();
+    if (threadIdx.x == 0) num_calls[r] = s_calls;
+}
+
+__global__ void wis_filters_kernel(const uint32_t *__restrict__ ref_len, const uint32_t *__restrict__ num_calls,
+                                   uint32_t rows, uint32_t min_ref, uint32_t max_rel, uint8_t *__restrict__ filt) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint8_t f = 0;
+    if (ref_len[r] < min_ref) f |= CNVB_WIS_FEW_REF;        // lib.rs:362-369
+    if (num_calls[r] > max_rel) f |= CNVB_WIS_UNRELIABLE;   // lib.rs:370-377
+    filt[r] = f;
+}
+
+// ---- M1 ----------------------------------------------------------------------------------------
+__global__ void modcov_kernel(const float *__restrict__ cv, uint32_t T, const uint8_t *__restrict__ model_filt,
+                              const uint32_t *__restrict__ ref_idx, const uint32_t *__restrict__ ref_len,
+                              uint32_t k, float *__restrict__ ref_mean, float *__restrict__ ref_sd,
+                              float *__restrict__ cv_rel, float *__restrict__ cvz, float *__restrict__ cv2,
+                              uint8_t *__restrict__ status) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    uint8_t st = 0;
+    float o_mean = f32_missing(), o_sd = f32_missing(), o_rel = f32_missing(), o_z = f32_missing(),
+          o_cv2 = f32_missing();
+    const uint32_t m = ref_len[t];
+    if (model_filt[t] == 0 && m > 0) {  // lib.rs:104-113 (PASS records only), :146 (non-empty)
+        const uint32_t *ri = ref_idx + (size_t)t * k;
+        dd acc{0.0, 0.0};
+        for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(cv + ri[q]));
+        const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)m);  // lib.rs:147
+        double v = 0.0;
+        for (uint32_t q = 0; q < m; ++q) {
+            const double d = __dsub_rn((double)__ldg(cv + ri[q]), mean);
+            v = __dadd_rn(v, __dmul_rn(d, d));
+        }
+        const double sd = __dsqrt_rn(m < 2 ? 0.0 : __ddiv_rn(v, (double)(m - 1)));  // lib.rs:148
+        const double x = (double)cv[t];
+        const double rel = __ddiv_rn(x, mean);                    // lib.rs:78-80
+        const double zs = __ddiv_rn(__dsub_rn(x, mean), sd);      // lib.rs:83-85
+        o_mean = (float)mean;
+        o_sd = (float)sd;
+        o_rel = (float)rel;
+        o_z = (float)zs;
+        st = CNVB_MODCOV_HAS_INFO;
+        if (isfinite(rel)) {  // lib.rs:223-232
+            o_cv2 = rel == 0.0 ? f32_missing() : (float)log2(rel);
+            st |= CNVB_MODCOV_CV2;
+        }
+    }
+    ref_mean[t] = o_mean;
+    ref_sd[t] = o_sd;
+    cv_rel[t] = o_rel;
+    cvz[t] = o_z;
+    cv2[t] = o_cv2;
+    status[t] = st;
+}
+
+}  // namespace
+
+#include "wis_tensor.cuh"
+
+// ---- host side ------------------------------------------------------------------------------------
+namespace {
+
+// device view of a caller buffer: uploads host memory into pooled device memory
+template <typename T>
+struct DevIn {
+    cnvb_ctx *ctx;
+    const T *p = nullptr;
+    T *owned = nullptr;
+    int init(cnvb_ctx *c, const T *src, size_t n, int mem, const char *what) {
+        ctx = c;
+        if (mem == CNVB_MEM_DEVICE || !src) {
+            p = src;
+            return 0;
+        }
+        cudaError_t e = pool_alloc_t(ctx, n, &owned);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, what);
+        e = cudaMemcpyAsync(owned, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, what);
+        p = owned;
+        return 0;
+    }
+    ~DevIn() {
+        if (owned) pool_release(ctx, owned);
+    }
+};
+template <typename T>
+struct DevOut {
+    cnvb_ctx *ctx;
+    T *p = nullptr;
+    T *host = nullptr;
+    T *owned = nullptr;
+    size_t n = 0;
+    int init(cnvb_ctx *c, T *dst, size_t count, int mem, const char *what) {
+        ctx = c;
+        n = count;
+        if (mem == CNVB_MEM_DEVICE || !dst) {
+            p = dst;
+            return 0;
+        }
+        cudaError_t e = pool_alloc_t(ctx, count, &owned);
+        if (e != cudaSuccess) return fail_cuda(ctx, e, what);
+        p = owned;
+        host = dst;
+        return 0;
+    }
+    int download() {  // enqueue the copy back (caller synchronises)
+        if (host && n)
+            CNVB_CUDA(ctx, cudaMemcpyAsync(host, owned, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream),
+                      "copying results to the host");
+        return 0;
+    }
+    ~DevOut() {
+        if (owned) pool_release(ctx, owned);
+    }
+};
+
+int check_wis_opts(cnvb_ctx *ctx, const cnvb_wis_opts *o, uint32_t T) {
+    if (!o) return fail(ctx, CNVB_ERR_INVALID, "null options");
+    if (o->max_ref_targets == 0)
+        return fail(ctx, CNVB_ERR_REFERENCE_PANIC, "max_ref_targets == 0: the reference panics at xs[0] (lib.rs:208)");
+    const uint32_t k = T < o->max_ref_targets ? T : o->max_ref_targets;
+    if (k > kMaxK) return fail(ctx, CNVB_ERR_INVALID, "max_ref_targets > %u is not supported", kMaxK);
+    return 0;
+}
+
+int run_rows_exact(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S, uint32_t k,
+                   const uint32_t *d_row_list, uint32_t n_rows, uint32_t row_begin, float *d_dist, uint32_t *d_idx) {
+    if (n_rows == 0) return 0;
+    const size_t smem = (size_t)S * sizeof(float);
+    if (smem > 200 * 1024) return fail(ctx, CNVB_ERR_INVALID, "more than 51200 samples are not supported");
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_row_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+              "smem opt-in");
+    KernelSpan span(ctx, "wis_row_exact_kernel");
+    wis_row_exact_kernel<<<n_rows, kRowThreads, smem, ctx->stream>>>(dX, dtid, T, S, k, d_row_list, row_begin, d_dist,
+                                                                     d_idx);
+    CNVB_LAUNCHED(ctx, "wis_row_exact_kernel");
+    return 0;
+}
+
+int wis_distances_dev(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S,
+                      const cnvb_wis_opts *o, uint32_t row_begin, uint32_t row_end, float *d_dist, uint32_t *d_idx) {
+    const uint32_t k = T < o->max_ref_targets ? T : o->max_ref_targets;
+    uint32_t engine = o->engine;
+    if (engine == CNVB_WIS_ENGINE_AUTO) engine = T >= 4096 ? CNVB_WIS_ENGINE_TENSOR : CNVB_WIS_ENGINE_EXACT;
+    if (engine == CNVB_WIS_ENGINE_TENSOR)
+        return wis_distances_tensor(ctx, dX, dtid, T, S, k, row_begin, row_end, d_dist, d_idx);
+    return run_rows_exact(ctx, dX, dtid, T, S, k, nullptr, row_end - row_begin, row_begin, d_dist, d_idx);
+}
+
+}  // namespace
+
+extern "C" int cnvb_wis_distances(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t T, uint32_t S,
+                                  const cnvb_wis_opts *opts, uint32_t row_begin, uint32_t row_end, float *ref_dist,
+                                  uint32_t *ref_idx, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    CNVB_TRY(check_wis_opts(ctx, opts, T));
+    if (!X || !tid || !ref_dist || !ref_idx || row_end > T || row_begin > row_end || S == 0)
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_distances: bad argument");
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const uint32_t k = T < opts->max_ref_targets ? T : opts->max_ref_targets;
+    const size_t rows = row_end - row_begin;
+    DevIn<float> dX;
+    DevIn<uint32_t> dt;
+    DevOut<float> od;
+    DevOut<uint32_t> oi;
+    CNVB_TRY(dX.init(ctx, X, (size_t)T * S, mem, "uploading the panel"));
+    CNVB_TRY(dt.init(ctx, tid, T, mem, "uploading contig ids"));
+    CNVB_TRY(od.init(ctx, ref_dist, rows * k, mem, "allocating distances"));
+    CNVB_TRY(oi.init(ctx, ref_idx, rows * k, mem, "allocating indices"));
+    CNVB_TRY(wis_distances_dev(ctx, dX.p, dt.p, T, S, opts, row_begin, row_end, od.p, oi.p));
+    CNVB_TRY(od.download());
+    CNVB_TRY(oi.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis distances");
+    return CNVB_OK;
+}
+
+namespace {
+int wis_threshold_dev(cnvb_ctx *ctx, const float *d_nearest, uint32_t T, uint32_t stride, double z, float *thr_host) {
+    if (T < 2) {  // lib.rs:211-213: prune_distances returns an empty Vec
+        *thr_host = __builtin_nanf("");
+        return 0;
+    }
+    CNVB_TRY(ensure_scratch(ctx, 256));
+    float *d_thr = static_cast<float *>(ctx->scratch);
+    wis_threshold_kernel<<<1, 1024, 0, ctx->stream>>>(d_nearest, T, stride, z, d_thr);
+    CNVB_LAUNCHED(ctx, "wis_threshold_kernel");
+    CNVB_CUDA(ctx, cudaMemcpyAsync(thr_host, d_thr, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "threshold");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "threshold");
+    return 0;
+}
+}  // namespace
+
+extern "C" int cnvb_wis_threshold(cnvb_ctx *ctx, const float *nearest, uint32_t T, uint32_t stride,
+                                  double filter_z_score, float *threshold, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (!threshold || (T && !nearest) || stride == 0) return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_threshold: bad argument");
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    DevIn<float> dn;
+    CNVB_TRY(dn.init(ctx, nearest, (size_t)T * stride, mem, "uploading nearest distances"));
+    return wis_threshold_dev(ctx, dn.p, T, stride, filter_z_score, threshold);
+}
+
+extern "C" int cnvb_wis_prune(cnvb_ctx *ctx, const float *ref_dist, uint32_t *ref_idx, uint32_t rows, uint32_t k,
+                              float threshold, uint32_t *ref_len, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (rows && (!ref_dist || !ref_idx || !ref_len)) return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_prune: null argument");
+    if (rows == 0) return CNVB_OK;
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    DevIn<float> dd_;
+    DevIn<uint32_t> di_in;
+    DevOut<uint32_t> di, dl;
+    CNVB_TRY(dd_.init(ctx, ref_dist, (size_t)rows * k, mem, "uploading distances"));
+    CNVB_TRY(di.init(ctx, ref_idx, (size_t)rows * k, mem, "allocating indices"));
+    CNVB_TRY(dl.init(ctx, ref_len, rows, mem, "allocating lengths"));
+    if (mem != CNVB_MEM_DEVICE)
+        CNVB_CUDA(ctx, cudaMemcpyAsync(di.p, ref_idx, (size_t)rows * k * 4, cudaMemcpyHostToDevice, ctx->stream),
+                  "uploading indices");
+    wis_prune_kernel<<<(rows + 127) / 128, 128, 0, ctx->stream>>>(dd_.p, di.p, rows, k, threshold, dl.p);
+    CNVB_LAUNCHED(ctx, "wis_prune_kernel");
+    CNVB_TRY(di.download());
+    CNVB_TRY(dl.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis prune");
+    return CNVB_OK;
+}
+
+namespace {
+int wis_calls_dev(cnvb_ctx *ctx, const float *dX, uint32_t S, const uint32_t *d_idx, const uint32_t *d_len, uint32_t k,
+                  const cnvb_wis_opts *o, uint32_t row_begin, uint32_t rows, uint32_t *d_calls) {
+    if (rows == 0) return 0;
+    KernelSpan span(ctx, "wis_calls_kernel");
+    wis_calls_kernel<<<rows, 128, 0, ctx->stream>>>(dX, S, d_idx, d_len, k, o->min_ref_targets, o->filter_z_score,
+                                                    o->filter_rel, row_begin, d_calls);
+    CNVB_LAUNCHED(ctx, "wis_calls_kernel");
+    return 0;
+}
+}  // namespace
+
+extern "C" int cnvb_wis_calls(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, const uint32_t *ref_idx,
+                              const uint32_t *ref_len, uint32_t k, const cnvb_wis_opts *opts, uint32_t row_begin,
+                              uint32_t row_end, uint32_t *num_calls, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (!opts || !X || !ref_idx || !ref_len || !num_calls || row_end > T || row_begin > row_end || k > kMaxK)
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_calls: bad argument");
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const uint32_t rows = row_end - row_begin;
+    DevIn<float> dX;
+    DevIn<uint32_t> di, dl;
+    DevOut<uint32_t> dc;
+    CNVB_TRY(dX.init(ctx, X, (size_t)T * S, mem, "uploading the panel"));
+    CNVB_TRY(di.init(ctx, ref_idx, (size_t)rows * k, mem, "uploading indices"));
+    CNVB_TRY(dl.init(ctx, ref_len, rows, mem, "uploading lengths"));
+    CNVB_TRY(dc.init(ctx, num_calls, rows, mem, "allocating call counts"));
+    CNVB_TRY(wis_calls_dev(ctx, dX.p, S, di.p, dl.p, k, opts, row_begin, rows, dc.p));
+    CNVB_TRY(dc.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis calls");
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_wis_filters(cnvb_ctx *ctx, const uint32_t *ref_len, const uint32_t *num_calls, uint32_t rows,
+                                const cnvb_wis_opts *opts, uint8_t *filt, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (!opts || (rows && (!ref_len || !num_calls || !filt))) return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_filters: null argument");
+    if (rows == 0) return CNVB_OK;
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    DevIn<uint32_t> dl, dc;
+    DevOut<uint8_t> df;
+    CNVB_TRY(dl.init(ctx, ref_len, rows, mem, "uploading lengths"));
+    CNVB_TRY(dc.init(ctx, num_calls, rows, mem, "uploading call counts"));
+    CNVB_TRY(df.init(ctx, filt, rows, mem, "allocating filters"));
+    wis_filters_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(dl.p, dc.p, rows, opts->min_ref_targets,
+                                                                    opts->max_samples_reliable, df.p);
+    CNVB_LAUNCHED(ctx, "wis_filters_kernel");
+    CNVB_TRY(df.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis filters");
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t T, uint32_t S,
+                              const cnvb_wis_opts *opts, float *ref_dist, uint32_t *ref_idx, uint32_t *ref_len,
+                              uint32_t *num_calls, uint8_t *filt, float *threshold, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    CNVB_TRY(check_wis_opts(ctx, opts, T));
+    if (!X || !tid || !ref_dist || !ref_idx || !ref_len || !num_calls || !filt || !threshold || S == 0 || T == 0)
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_build: bad argument");
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const uint32_t k = T < opts->max_ref_targets ? T : opts->max_ref_targets;
+    DevIn<float> dX;
+    DevIn<uint32_t> dt;
+    DevOut<float> od;
+    DevOut<uint32_t> oi, ol, oc;
+    DevOut<uint8_t> of;
+    CNVB_TRY(dX.init(ctx, X, (size_t)T * S, mem, "uploading the panel"));
+    CNVB_TRY(dt.init(ctx, tid, T, mem, "uploading contig ids"));
+    CNVB_TRY(od.init(ctx, ref_dist, (size_t)T * k, mem, "allocating distances"));
+    CNVB_TRY(oi.init(ctx, ref_idx, (size_t)T * k, mem, "allocating indices"));
+    CNVB_TRY(ol.init(ctx, ref_len, T, mem, "allocating lengths"));
+    CNVB_TRY(oc.init(ctx, num_calls, T, mem, "allocating call counts"));
+    CNVB_TRY(of.init(ctx, filt, T, mem, "allocating filters"));
+    CNVB_TRY(wis_distances_dev(ctx, dX.p, dt.p, T, S, opts, 0, T, od.p, oi.p));         // lib.rs:427
+    CNVB_TRY(od.download());  // distances are reported un-pruned (ascending)
+    CNVB_TRY(wis_threshold_dev(ctx, od.p, T, k, opts->filter_z_score, threshold));       // lib.rs:207-216
+    wis_prune_kernel<<<(T + 127) / 128, 128, 0, ctx->stream>>>(od.p, oi.p, T, k, *threshold, ol.p);  // :221-228
+    CNVB_LAUNCHED(ctx, "wis_prune_kernel");
+    CNVB_TRY(wis_calls_dev(ctx, dX.p, S, oi.p, ol.p, k, opts, 0, T, oc.p));              // lib.rs:429-436
+    wis_filters_kernel<<<(T + 255) / 256, 256, 0, ctx->stream>>>(ol.p, oc.p, T, opts->min_ref_targets,
+                                                                 opts->max_samples_reliable, of.p);
+    CNVB_LAUNCHED(ctx, "wis_filters_kernel");
+    CNVB_TRY(oi.download());
+    CNVB_TRY(ol.download());
+    CNVB_TRY(oc.download());
+    CNVB_TRY(of.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis build");
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_modcov(cnvb_ctx *ctx, const float *cv, uint32_t T, const uint8_t *model_filt,
+                           const uint32_t *ref_idx, const uint32_t *ref_len, uint32_t k, float *ref_mean,
+                           float *ref_sd, float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (T && (!cv || !model_filt || !ref_idx || !ref_len || !ref_mean || !ref_sd || !cv_rel || !cvz || !cv2 || !status))
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_modcov: null argument");
+    if (T == 0) return CNVB_OK;
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    DevIn<float> dcv;
+    DevIn<uint8_t> dmf;
+    DevIn<uint32_t> di, dl;
+    DevOut<float> o1, o2, o3, o4, o5;
+    DevOut<uint8_t> os;
+    CNVB_TRY(dcv.init(ctx, cv, T, mem, "uploading CV"));
+    CNVB_TRY(dmf.init(ctx, model_filt, T, mem, "uploading model filters"));
+    CNVB_TRY(di.init(ctx, ref_idx, (size_t)T * k, mem, "uploading reference targets"));
+    CNVB_TRY(dl.init(ctx, ref_len, T, mem, "uploading reference target counts"));
+    CNVB_TRY(o1.init(ctx, ref_mean, T, mem, "allocating outputs"));
+    CNVB_TRY(o2.init(ctx, ref_sd, T, mem, "allocating outputs"));
+    CNVB_TRY(o3.init(ctx, cv_rel, T, mem, "allocating outputs"));
+    CNVB_TRY(o4.init(ctx, cvz, T, mem, "allocating outputs"));
+    CNVB_TRY(o5.init(ctx, cv2, T, mem, "allocating outputs"));
+    CNVB_TRY(os.init(ctx, status, T, mem, "allocating outputs"));
+    {
+        KernelSpan span(ctx, "modcov_kernel");
+        modcov_kernel<<<(T + 127) / 128, 128, 0, ctx->stream>>>(dcv.p, T, dmf.p, di.p, dl.p, k, o1.p, o2.p, o3.p, o4.p,
+                                                                o5.p, os.p);
+    }
+    CNVB_LAUNCHED(ctx, "modcov_kernel");
+    CNVB_TRY(o1.download());
+    CNVB_TRY(o2.download());
+    CNVB_TRY(o3.download());
+    CNVB_TRY(o4.download());
+    CNVB_TRY(o5.download());
+    CNVB_TRY(os.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "modcov");
+    return CNVB_OK;
+}

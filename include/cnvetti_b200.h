@@ -172,6 +172,67 @@ int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, con
                         uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
                         float *medians, int mem);
 
+/* ---- lib-model-wis ------------------------------------------------------------------------ */
+typedef struct {
+    double filter_z_score;         /* --filter-z-score        5.64  (cli.yaml:370-376)        */
+    double filter_rel;             /* --filter-rel            0.35  (cli.yaml:377-383)        */
+    uint32_t min_ref_targets;      /* --min-ref-targets       10    (cli.yaml:384-390)        */
+    uint32_t max_ref_targets;      /* --max-ref-targets       100   (cli.yaml:391-397)        */
+    uint32_t max_samples_reliable; /* --max-samples-reliable  4     (cli.yaml:398-406)        */
+    uint32_t engine;               /* CNVB_WIS_ENGINE_*                                       */
+} cnvb_wis_opts;
+#define CNVB_WIS_ENGINE_AUTO 0   /* tensor for large panels, exact for small ones             */
+#define CNVB_WIS_ENGINE_TENSOR 1 /* tcgen05 fp16 contraction as candidate filter + exact
+                                    f32-sequential re-scoring of the candidates               */
+#define CNVB_WIS_ENGINE_EXACT 2  /* every pair in emulated f32-sequential arithmetic          */
+
+/* = compute_distances (lib-model-wis/src/lib.rs:128-197) for target rows [row_begin,row_end)
+ * of the panel X[T][S] (row-major f32, NaN-free, FORMAT/CV of the merged BCF).
+ * k = min(T, max_ref_targets).  Outputs [row_end-row_begin][k]: ascending distance, ties by
+ * index (the reference's order among equal distances is pdqselect's, which no test pins);
+ * same-contig pairs (tid equal, incl. the target itself) have distance +inf exactly as in the
+ * reference and appear only when fewer than k other-contig targets exist.
+ * The distance is sqrt_f32 of the f32 sum accumulated over samples in order with separate
+ * mul and add roundings (lib.rs:157-162) -- bit-exact, whichever engine is used. */
+int cnvb_wis_distances(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t T, uint32_t S,
+                       const cnvb_wis_opts *opts, uint32_t row_begin, uint32_t row_end,
+                       float *ref_dist, uint32_t *ref_idx, int mem);
+/* = threshold of prune_distances (lib.rs:207-216): (mean + z*sd) as f32 over the nearest
+ * distance of ALL T targets (f64, exact-sum mean, n-1 SD).  `nearest` = ref_dist[.][0].
+ * NaN for T < 2 (the reference returns an empty Vec).  *threshold is host memory. */
+int cnvb_wis_threshold(cnvb_ctx *ctx, const float *nearest, uint32_t T, uint32_t stride,
+                       double filter_z_score, float *threshold, int mem);
+/* = the filter of prune_distances (lib.rs:221-228) on `rows` rows: compacts ref_idx in place,
+ * ref_len[r] = number of reference targets kept (distance <= threshold). */
+int cnvb_wis_prune(cnvb_ctx *ctx, const float *ref_dist, uint32_t *ref_idx, uint32_t rows, uint32_t k,
+                   float threshold, uint32_t *ref_len, int mem);
+/* = count_per_probe_calls (lib.rs:235-271) for target rows [row_begin,row_end); ref_idx /
+ * ref_len / num_calls are indexed relative to row_begin. */
+int cnvb_wis_calls(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, const uint32_t *ref_idx,
+                   const uint32_t *ref_len, uint32_t k, const cnvb_wis_opts *opts,
+                   uint32_t row_begin, uint32_t row_end, uint32_t *num_calls, int mem);
+/* = FILTER column of write_output (lib.rs:362-377) */
+#define CNVB_WIS_FEW_REF 1
+#define CNVB_WIS_UNRELIABLE 2
+int cnvb_wis_filters(cnvb_ctx *ctx, const uint32_t *ref_len, const uint32_t *num_calls, uint32_t rows,
+                     const cnvb_wis_opts *opts, uint8_t *filt, int mem);
+/* = lib_model_wis::run (lib.rs:422-447) on an in-memory panel, single GPU: distances, prune,
+ * per-probe calls, filters.  Outputs as above for all T rows; *threshold is host memory. */
+int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t T, uint32_t S,
+                   const cnvb_wis_opts *opts, float *ref_dist, uint32_t *ref_idx, uint32_t *ref_len,
+                   uint32_t *num_calls, uint8_t *filt, float *threshold, int mem);
+
+/* ---- lib-mod-cov ---------------------------------------------------------------------------- */
+/* = load_target_infos + the FORMAT/INFO values of write_mod_cov (lib-mod-cov/src/lib.rs:76-164,
+ * 209-240) for one sample: cv[T] = FORMAT/CV of the sample, model_filt[T] != 0 marks model
+ * records carrying a non-PASS filter.  status bit 0: probe info exists (else FILTER NO_REF),
+ * bit 1: CV2 written.  Values without probe info are the missing pattern. */
+#define CNVB_MODCOV_HAS_INFO 1
+#define CNVB_MODCOV_CV2 2
+int cnvb_modcov(cnvb_ctx *ctx, const float *cv, uint32_t T, const uint8_t *model_filt,
+                const uint32_t *ref_idx, const uint32_t *ref_len, uint32_t k, float *ref_mean,
+                float *ref_sd, float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,115 @@
+"""Parity of the CUDA WIS / mod-coverage path (through the C ABI) against the oracle: reference
+target sets and their order, distances, threshold, call counts and filter bits bit-exact;
+mod-coverage f32 outputs bit-exact except CV2 (f64 log2, rel 1e-6)."""
+import numpy as np
+import pytest
+
+import cnvetti_b200 as cb
+from cnvetti_b200 import model_wis as mw
+from cnvetti_b200 import synth
+from util import assert_f32_equal_bits, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return cb.Context(0)
+
+
+def _dev(a):
+    import torch
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("T,S,k,ncontig,device,engine", [
+    (300, 20, 30, 5, False, mw.ENGINE_EXACT), (257, 7, 100, 3, True, mw.ENGINE_EXACT),
+    (12, 5, 8, 2, False, mw.ENGINE_EXACT), (1500, 100, 100, 22, True, mw.ENGINE_EXACT),
+    (50, 33, 100, 1, False, mw.ENGINE_EXACT),
+])
+def test_wis_distances_parity(oracle, ctx, T, S, k, ncontig, device, engine):
+    X, tids = synth.synth_panel(T + S, T, S, n_contigs=ncontig)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=4)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=engine)
+    if device:
+        dist, idx = mw.compute_distances(_dev(X), _dev(tids), opts, ctx=ctx)
+    else:
+        dist, idx = mw.compute_distances(X, tids, opts, ctx=ctx)
+    assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
+    assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
+    # a row block only (multi-GPU sharding unit)
+    lo, hi = T // 3, 2 * T // 3
+    d2, i2 = mw.compute_distances(X, tids, opts, row_begin=lo, row_end=hi, ctx=ctx)
+    assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
+
+
+@pytest.mark.parametrize("T,S,device", [(400, 24, False), (2000, 100, True)])
+def test_wis_build_parity(oracle, ctx, T, S, device):
+    X, tids = synth.synth_panel(T, T, S, n_contigs=8)
+    rng = np.random.default_rng(T)
+    X[rng.integers(0, T, 6)] *= 2.5     # unreliable / isolated targets
+    X[5, 3] *= 1.8                      # a single-sample event
+    o = dict(filter_z_score=3.0, filter_rel=0.2, min_ref_targets=10, max_ref_targets=40, max_samples_reliable=1)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=o["max_ref_targets"], nthreads=4)
+    othr, oridx, orlen = oracle.wis_prune(odist, oidx, z=o["filter_z_score"])
+    ocalls = oracle.wis_calls(X, oridx, orlen, o["min_ref_targets"], o["filter_z_score"], o["filter_rel"])
+    ofilt = oracle.wis_filters(orlen, ocalls, o["min_ref_targets"], o["max_samples_reliable"])
+    opts = mw.BuildModelWisOptions(engine=mw.ENGINE_EXACT, **o)
+    m = mw.run(_dev(X), _dev(tids), opts, ctx=ctx) if device else mw.run(X, tids, opts, ctx=ctx)
+    assert np.float32(m.threshold).view(np.uint32) == np.float32(othr).view(np.uint32)
+    assert_f32_equal_bits(to_np(m.ref_dist).ravel(), odist.ravel(), "distances")
+    rl = to_np(m.ref_len).astype(np.uint32)
+    assert np.array_equal(rl, orlen)
+    ri = to_np(m.ref_idx).astype(np.uint32)
+    for t in range(T):
+        assert np.array_equal(ri[t, :rl[t]], oridx[t, :orlen[t]]), t
+    assert np.array_equal(to_np(m.num_calls).astype(np.uint32), ocalls)
+    assert np.array_equal(to_np(m.filt), ofilt)
+    assert ocalls.sum() > 0 and (ofilt & 1).any() and (ofilt & 2).any()
+    # the separate entry points agree with the one-shot call
+    thr = mw.prune_threshold(odist[:, 0].copy(), o["filter_z_score"], ctx=ctx)
+    assert np.float32(thr).view(np.uint32) == np.float32(othr).view(np.uint32)
+    ridx2, rlen2 = mw.prune_distances(odist, oidx.copy(), thr, ctx=ctx)
+    assert np.array_equal(rlen2, orlen)
+    calls2 = mw.count_per_probe_calls(X, ridx2, rlen2, opts, row_begin=10, row_end=T - 5, ctx=ctx)
+    assert np.array_equal(calls2, ocalls[10:T - 5])
+    filt2 = mw.model_filters(orlen, ocalls, opts, ctx=ctx)
+    assert np.array_equal(filt2, ofilt)
+
+
+def test_wis_single_contig_threshold_nan(oracle, ctx):
+    X, _ = synth.synth_panel(1, 40, 6, n_contigs=1)
+    tids = np.zeros(40, np.uint32)
+    m = mw.run(X, tids, mw.BuildModelWisOptions(max_ref_targets=10, engine=mw.ENGINE_EXACT), ctx=ctx)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=10)
+    othr, _, orlen = oracle.wis_prune(odist, oidx)
+    assert np.isinf(to_np(m.ref_dist)).all() and np.isnan(m.threshold) and np.isnan(othr)
+    assert np.array_equal(to_np(m.ref_len), orlen) and (orlen == 0).all()
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_modcov_parity(oracle, ctx, device):
+    T, S = 3000, 12
+    X, tids = synth.synth_panel(9, T, S, n_contigs=10)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=50, nthreads=4)
+    _, ridx, rlen = oracle.wis_prune(odist, oidx, z=2.0)
+    rng = np.random.default_rng(1)
+    filt = (rng.random(T) < 0.1).astype(np.uint8)
+    rlen[rng.integers(0, T, 20)] = 0
+    cv = (X[:, 0] * rng.normal(1, 0.1, T)).astype(np.float32)
+    cv[17] = 0.0
+    o = oracle.modcov(cv, filt, ridx, rlen)
+    if device:
+        g = mw.mod_coverage(_dev(cv), _dev(filt), _dev(ridx), _dev(rlen), ctx=ctx)
+    else:
+        g = mw.mod_coverage(cv, filt, ridx, rlen, ctx=ctx)
+    assert np.array_equal(to_np(g["status"]), o["status"])
+    for key in ("ref_mean", "ref_sd", "cv_rel", "cvz"):
+        assert_f32_equal_bits(g[key], o[key], key)
+    a, b = to_np(g["cv2"]), o["cv2"]
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=1e-6, atol=1e-7)
+    assert (o["status"] == 0).any() and (o["status"] == 3).any()
