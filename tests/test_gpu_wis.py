@@ -73,7 +73,8 @@ def test_wis_build_parity(oracle, ctx, T, S, device):
     assert np.float32(thr).view(np.uint32) == np.float32(othr).view(np.uint32)
     ridx2, rlen2 = mw.prune_distances(odist, oidx.copy(), thr, ctx=ctx)
     assert np.array_equal(rlen2, orlen)
-    calls2 = mw.count_per_probe_calls(X, ridx2, rlen2, opts, row_begin=10, row_end=T - 5, ctx=ctx)
+    calls2 = mw.count_per_probe_calls(X, np.ascontiguousarray(ridx2[10:T - 5]), np.ascontiguousarray(rlen2[10:T - 5]), opts,
+                                      row_begin=10, row_end=T - 5, ctx=ctx)
     assert np.array_equal(calls2, ocalls[10:T - 5])
     filt2 = mw.model_filters(orlen, ocalls, opts, ctx=ctx)
     assert np.array_equal(filt2, ofilt)
