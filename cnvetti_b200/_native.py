@@ -67,6 +67,7 @@ SYMBOLS = {
     "cnvb_norm_total": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _int]),
     "cnvb_norm_gc_median": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _int]),
     "cnvb_wis_distances": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _u32, _u32, _vp, _vp, _int]),
+    "cnvb_wis_last_stats": (_int, [_vp, _vp]),
     "cnvb_wis_threshold": (_int, [_vp, _vp, _u32, _u32, C.c_double, C.POINTER(C.c_float), _int]),
     "cnvb_wis_prune": (_int, [_vp, _vp, _vp, _u32, _u32, C.c_float, _vp, _int]),
     "cnvb_wis_calls": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, C.POINTER(WisOpts), _u32, _u32, _vp, _int]),

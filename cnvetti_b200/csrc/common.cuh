@@ -43,6 +43,7 @@ struct cnvb_ctx {
     uint32_t tally_next = 0;
     // resident CTAs per SM of each persistent kernel (cudaOccupancy... is not free: cached)
     std::unordered_map<const void *, int> occupancy;
+    uint64_t wis_stats[4] = {0, 0, 0, 0};
     // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
     bool timing = false;
     std::vector<std::string> span_names;

@@ -388,12 +388,20 @@ int wis_distances_dev(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint
     const uint32_t k = T < o->max_ref_targets ? T : o->max_ref_targets;
     uint32_t engine = o->engine;
     if (engine == CNVB_WIS_ENGINE_AUTO) engine = T >= 4096 ? CNVB_WIS_ENGINE_TENSOR : CNVB_WIS_ENGINE_EXACT;
+    ctx->wis_stats[0] = row_end - row_begin;
+    ctx->wis_stats[1] = ctx->wis_stats[2] = ctx->wis_stats[3] = 0;
     if (engine == CNVB_WIS_ENGINE_TENSOR)
         return wis_distances_tensor(ctx, dX, dtid, T, S, k, row_begin, row_end, d_dist, d_idx);
     return run_rows_exact(ctx, dX, dtid, T, S, k, nullptr, row_end - row_begin, row_begin, d_dist, d_idx);
 }
 
 }  // namespace
+
+extern "C" int cnvb_wis_last_stats(const cnvb_ctx *ctx, uint64_t out[4]) {
+    if (!ctx || !out) return CNVB_ERR_INVALID;
+    for (int i = 0; i < 4; ++i) out[i] = ctx->wis_stats[i];
+    return CNVB_OK;
+}
 
 extern "C" int cnvb_wis_distances(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t T, uint32_t S,
                                   const cnvb_wis_opts *opts, uint32_t row_begin, uint32_t row_end, float *ref_dist,

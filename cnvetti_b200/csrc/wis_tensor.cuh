@@ -1,8 +1,709 @@
-// wis_tensor.cuh -- placeholder, replaced by the tcgen05 engine
+// wis_tensor.cuh -- tensor-core engine of compute_distances (lib-model-wis/src/lib.rs:128-197).
+// Included by wis.cu only.
+//
+// All-pairs distances over the panel are a norms-minus-2*H*H^T contraction.  The reference's
+// distance is an f32 sequential sum, so the tensor cores are used as a FILTER with a rigorous
+// error bound and every surviving pair is re-evaluated exactly (wis_ref_distance):
+//
+//   prep     centre the panel (distances are translation invariant), scale by a power of two,
+//            round to fp16: H[T][Kp].  Per row keep n_t = |h_t|^2 and delta_t = |u_t - h_t|
+//            (the actual rounding error norm), so that for the real distance D and the fp16
+//            distance d_h:  | D_ij - d_h,ij | <= delta_i + delta_j   (triangle inequality).
+//   sweep    wis_sweep_kernel: one CTA per 256 target rows, A operand resident in shared memory
+//            (TMA, 128B swizzle), B tiles of 128 columns streamed by TMA through an mbarrier
+//            ring, tcgen05.mma (cta_group::1, M128 N128 K16, fp16 x fp16 -> fp32) into
+//            double-buffered TMEM accumulators; 4 epilogue warps read them back with tcgen05.ld
+//            and test  n_j - 2 g_ij <= theta'_i  (one FFMA + one compare per pair), appending the
+//            rare survivors to the row's candidate buffer in HBM.
+//   compact  between sweeps over geometrically growing column sets (tiles are visited in a
+//            scattered order so that every contig is sampled early) a warp per row selects the
+//            k-th smallest candidate value and tightens theta'_i with the bound below.
+//   rescore  exact f32-sequential distance for every candidate, (distance, index) top-k.
+//
+// Bound (scaled units; eps_i = c_sq (n_i + n_max) covers tensor-core accumulation and f32
+// epilogue rounding of the squared fp16 distance, Delta_i = delta_i + delta_max, g bounds the
+// reference's own rounding relative error):  with v_k the k-th smallest approximate squared
+// distance seen so far, V = (1+g)(sqrt(v_k + eps_i) + Delta_i) is >= the final k-th reference
+// distance, and a pair can only belong to the top k if its approximate squared distance is
+// <= theta_i = (V/(1-g) + Delta_i)^2 + eps_i.  Rows whose buffer overflows fall back to the
+// exact row kernel, so the result never depends on the bound being tight.
 #pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 namespace {
-int wis_distances_tensor(cnvb_ctx *ctx, const float *, const uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t,
-                         uint32_t, float *, uint32_t *) {
-    return fail(ctx, CNVB_ERR_INVALID, "tensor engine not built");
+
+constexpr uint32_t kTileRows = 256;   // target rows per CTA (two M=128 accumulators)
+constexpr uint32_t kTileCols = 128;   // columns per B tile (UMMA N)
+constexpr uint32_t kKBlock = 64;      // fp16 elements per 128-byte swizzle row
+constexpr uint32_t kMaxKBlocks = 2;   // A stays resident: Kp <= 128
+constexpr uint32_t kStages = 8;       // B ring: 8 x 16 KB
+constexpr uint32_t kTileBytes = 128 * kKBlock * 2;  // 16 KB: 128 rows x 64 fp16
+constexpr uint32_t kCandCap = 2048;   // candidate buffer entries per row
+constexpr uint32_t kSweepThreads = 256;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 64 fp16 = 128 B, 8-row atoms of 1024 B):
+// start address >> 4 | LBO 1 | SBO 1024 B | descriptor version 1 (sm_100) | SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// kind::f16: D f32 (bit 4), A/B f16 K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | ((kTileCols >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---- prep -----------------------------------------------------------------------------------------
+__global__ void wis_colsum_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, double *__restrict__ colsum,
+                                  float *__restrict__ absmax) {
+    // grid-stride over rows; thread s-strided columns; block partial -> atomics (order-insensitive use)
+    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
+        double acc = 0.0;
+        float mx = 0.0f;
+        for (uint32_t t = blockIdx.x; t < T; t += gridDim.x) {
+            const float v = X[(size_t)t * S + s];
+            acc += (double)v;
+            mx = fmaxf(mx, fabsf(v));
+        }
+        atomicAdd(&colsum[s], acc);
+        atomicMax(reinterpret_cast<int *>(absmax), __float_as_int(mx));  // non-negative floats order as ints
+    }
+}
+
+struct WisPrep {
+    float scale;      // power of two
+    float inv_scale;
+};
+
+// one warp per row: centre, scale, round to fp16; n_t (of the fp16 row) and delta_t in f64
+__global__ void wis_pack_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, uint32_t Kp,
+                                const double *__restrict__ colsum, float scale, __half *__restrict__ H,
+                                float *__restrict__ nrm, float *__restrict__ delta, float *__restrict__ maxes) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (warp >= T) return;
+    double n = 0.0, e = 0.0;
+    for (uint32_t s = lane; s < Kp; s += 32) {
+        __half h = __float2half_rn(0.0f);
+        if (s < S) {
+            const float c = (float)(colsum[s] / (double)T);
+            const float u = __fmul_rn(__fsub_rn(X[(size_t)warp * S + s], c), scale);
+            h = __float2half_rn(u);
+            const double hf = (double)__half2float(h);
+            n += hf * hf;
+            const double r = (double)u - hf;
+            e += r * r;
+        }
+        H[(size_t)warp * Kp + s] = h;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
+    if (lane == 0) {
+        const float nf = __double2float_ru(n);
+        // rounding error norm, inflated for the f32 rounding of the centred value itself
+        const float df = __double2float_ru(sqrt(e) * (1.0 + 1.0 / 1024.0) + sqrt(n) * (1.0 / 8388608.0));
+        nrm[warp] = nf;
+        delta[warp] = df;
+        atomicMax(reinterpret_cast<int *>(maxes), __float_as_int(nf));
+        atomicMax(reinterpret_cast<int *>(maxes) + 1, __float_as_int(df));
+    }
+}
+
+__global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi, float v) {
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hi) p[i] = v;
+}
+
+// ---- sweep ------------------------------------------------------------------------------------------
+struct SweepArgs {
+    const float *nrm;        // [Tpad] (+inf beyond T)
+    const uint32_t *tid;     // [T]
+    const float *thr;        // [rows] theta'_i = theta_i - n_i  (+inf until k candidates are known)
+    const uint32_t *tiles;   // column tiles of this step
+    uint32_t n_tiles;
+    uint32_t T, row_begin, row_end;
+    uint32_t k_mmas;         // K16 slabs per tile that hold data: ceil(S / 16)
+    uint32_t n_kblocks;      // ceil(Kp / 64)
+    float *cand_val;         // [rows][kCandCap]
+    uint32_t *cand_idx;
+    uint32_t *cand_cnt;      // [rows]
+};
+
+__global__ void __launch_bounds__(kSweepThreads, 1)
+wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + 2 * kMaxKBlocks * kTileBytes;
+    const uint32_t bar_base = b_base + kStages * kTileBytes;
+    const uint32_t bar_a_full = bar_base;
+    const uint32_t bar_b_full = bar_base + 8;                 // kStages
+    const uint32_t bar_b_empty = bar_b_full + 8 * kStages;    // kStages
+    const uint32_t bar_acc_full = bar_b_empty + 8 * kStages;  // 2
+    const uint32_t bar_acc_empty = bar_acc_full + 16;         // 2
+    const uint32_t tmem_slot = bar_acc_empty + 16;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t row0 = a.row_begin + blockIdx.x * kTileRows;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(bar_a_full, 1);
+        for (uint32_t s = 0; s < kStages; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (uint32_t s = 0; s < 2; ++s) {
+            mbar_init(bar_acc_full + 8 * s, 1);
+            mbar_init(bar_acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 4 accumulators x 128 columns (2 row halves x 2 stages)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
+            for (uint32_t h = 0; h < 2; ++h)
+                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
+                    tma_load_2d(a_base + (h * kMaxKBlocks + kb) * kTileBytes, &tmap, bar_a_full, (int32_t)(kb * kKBlock),
+                                (int32_t)(row0 + h * 128));
+            uint32_t st = 0, ph = 0;
+            for (uint32_t it = 0; it < a.n_tiles; ++it) {
+                const int32_t j0 = (int32_t)(a.tiles[it] * kTileCols);
+                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
+                    mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
+                    tma_load_2d(b_base + st * kTileBytes, &tmap, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                    if (++st == kStages) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            mbar_wait(bar_a_full, 0);
+            tc_fence_after();
+            uint32_t st = 0, ph = 0, as = 0, aph = 0;
+            for (uint32_t it = 0; it < a.n_tiles; ++it) {
+                mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(bar_b_full + 8 * st, ph);
+                    tc_fence_after();
+                    const uint32_t b_addr = b_base + st * kTileBytes;
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        const uint32_t a_addr = a_base + (h * kMaxKBlocks + kb) * kTileBytes;
+                        const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
+#pragma unroll
+                        for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                            if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                tc_mma_f16(d_tmem, umma_desc(a_addr + kk * 32), umma_desc(b_addr + kk * 32), kIdesc,
+                                           (kb | kk) != 0u);
+                        }
+                    }
+                    tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
+                    if (++st == kStages) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc_commit(bar_acc_full + 8 * as);  // accumulators of this tile complete
+                if (++as == 2) {
+                    as = 0;
+                    aph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread t owns rows row0 + t and row0 + 128 + t =====
+        const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
+        const uint32_t t = q * 32 + lane;
+        uint32_t row[2], cnt[2], rtid[2];
+        float thr[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            row[h] = row0 + h * 128 + t;
+            const bool live = row[h] < a.row_end;
+            thr[h] = live ? a.thr[row[h] - a.row_begin] : -__int_as_float(0x7f800000);
+            cnt[h] = live ? a.cand_cnt[row[h] - a.row_begin] : 0u;
+            rtid[h] = live ? a.tid[row[h]] : 0xffffffffu;
+        }
+        uint32_t as = 0, aph = 0;
+        for (uint32_t it = 0; it < a.n_tiles; ++it) {
+            const uint32_t j0 = a.tiles[it] * kTileCols;
+            mbar_wait(bar_acc_full + 8 * as, aph);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols;
+                const float th = thr[h];
+                float *cv = a.cand_val + (size_t)(row[h] - a.row_begin) * kCandCap;
+                uint32_t *ci = a.cand_idx + (size_t)(row[h] - a.row_begin) * kCandCap;
+#pragma unroll 1
+                for (uint32_t c0 = 0; c0 < kTileCols; c0 += 32) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + c0, r);
+                    const float4 *nj4 = reinterpret_cast<const float4 *>(a.nrm + j0 + c0);
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 nj = __ldg(nj4 + g4);
+                        const float v0 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj.x);
+                        const float v1 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj.y);
+                        const float v2 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj.z);
+                        const float v3 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj.w);
+                        if (v0 <= th || v1 <= th || v2 <= th || v3 <= th) {
+                            const float vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint32_t j = j0 + c0 + 4 * g4 + e;
+                                if (vv[e] <= th && j < a.T && a.tid[j] != rtid[h]) {
+                                    if (cnt[h] < kCandCap) {
+                                        cv[cnt[h]] = vv[e];
+                                        ci[cnt[h]] = j;
+                                    }
+                                    cnt[h] += 1;  // beyond kCandCap: overflow, the row falls back
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+            if (++as == 2) {
+                as = 0;
+                aph ^= 1u;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (row[h] < a.row_end) a.cand_cnt[row[h] - a.row_begin] = cnt[h];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- compaction: k-th smallest candidate value per row, new threshold -----------------------------
+__device__ __forceinline__ uint32_t f32_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+struct CompactArgs {
+    float *cand_val;
+    uint32_t *cand_idx;
+    uint32_t *cand_cnt;
+    float *thr;
+    uint32_t *overflow;      // [rows] sticky flag
+    const float *nrm, *delta;  // indexed by absolute row
+    const float *maxes;      // [0] n_max, [1] delta_max
+    uint32_t rows, row_begin, k;
+    double c_sq, g_ref;
+};
+
+__global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (r >= a.rows) return;
+    uint32_t n = a.cand_cnt[r];
+    if (n > kCandCap) {
+        if (lane == 0) {
+            a.overflow[r] = 1u;
+            a.cand_cnt[r] = 0u;
+            a.thr[r] = -__int_as_float(0x7f800000);  // stop collecting: the row is recomputed exactly
+        }
+        return;
+    }
+    if (n < a.k || a.overflow[r]) return;  // not enough candidates for a bound yet
+    float *cv = a.cand_val + (size_t)r * kCandCap;
+    uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
+    constexpr uint32_t kPer = kCandCap / 32;
+    uint32_t key[kPer];
+#pragma unroll
+    for (uint32_t e = 0; e < kPer; ++e) {
+        const uint32_t c = e * 32 + lane;
+        key[e] = c < n ? f32_key(cv[c]) : 0xFFFFFFFFu;
+    }
+    // bit-descent select of the k-th smallest key
+    uint32_t prefix = 0, want = a.k;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t mask = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+        uint32_t zeros = 0;
+#pragma unroll
+        for (uint32_t e = 0; e < kPer; ++e)
+            zeros += ((key[e] & mask) == prefix && !((key[e] >> bit) & 1u) && (e * 32 + lane) < n) ? 1u : 0u;
+        zeros = __reduce_add_sync(0xffffffffu, zeros);
+        if (want > zeros) {
+            want -= zeros;
+            prefix |= 1u << bit;
+        }
+    }
+    const float vk = key_f32(prefix);  // k-th smallest  n_j - 2 g  of this row
+    const uint32_t row = a.row_begin + r;
+    const double ni = (double)a.nrm[row], nmax = (double)a.maxes[0];
+    const double Delta = (double)a.delta[row] + (double)a.maxes[1];
+    const double eps = a.c_sq * (ni + nmax);
+    const double dk2 = fmax((double)vk + ni + eps, 0.0);
+    const double V = (1.0 + a.g_ref) * (sqrt(dk2) + Delta);
+    const double w = V / (1.0 - a.g_ref) + Delta;
+    const double theta = (w * w + eps) * (1.0 + 1e-12);
+    const float thr = __double2float_ru(theta - ni);
+    // keep the survivors (order irrelevant)
+    uint32_t kept = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t c = base + lane;
+        float v = 0.0f;
+        uint32_t j = 0;
+        bool keep = false;
+        if (c < n) {
+            v = cv[c];
+            j = ci[c];
+            keep = v <= thr;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
+        __syncwarp();
+        if (keep) {
+            cv[pos] = v;  // pos <= c: compaction in place, front to back
+            ci[pos] = j;
+        }
+        kept += __popc(m);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        a.cand_cnt[r] = kept;
+        a.thr[r] = thr;
+    }
+}
+
+// ---- exact re-scoring and (distance, index) top-k ------------------------------------------------
+__global__ void __launch_bounds__(128) wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid,
+                                                          uint32_t T, uint32_t S, uint32_t k, uint32_t row_begin,
+                                                          uint32_t rows, const uint32_t *__restrict__ cand_idx,
+                                                          const uint32_t *__restrict__ cand_cnt,
+                                                          const uint32_t *__restrict__ overflow,
+                                                          float *__restrict__ out_dist, uint32_t *__restrict__ out_idx) {
+    extern __shared__ float s_dyn[];  // [S] target row | [kCandCap] exact distances
+    float *s_xi = s_dyn;
+    float *s_d = s_dyn + ((S + 3u) & ~3u);
+    __shared__ uint32_t s_j[kCandCap];
+    const uint32_t r = blockIdx.x;
+    if (overflow[r]) return;  // recomputed by the exact row kernel
+    const uint32_t i = row_begin + r;
+    const uint32_t n = cand_cnt[r];
+    const bool vec4 = (S & 3u) == 0u && (reinterpret_cast<uintptr_t>(X) & 15u) == 0u;
+    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) s_xi[s] = X[(size_t)i * S + s];
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
+        const uint32_t j = cand_idx[(size_t)r * kCandCap + c];
+        s_j[c] = j;
+        s_d[c] = wis_ref_distance(s_xi, X + (size_t)j * S, S, vec4);
+    }
+    __syncthreads();
+    const size_t o = (size_t)r * k;
+    for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
+        const float d = s_d[c];
+        const uint32_t j = s_j[c];
+        uint32_t rank = 0;
+        for (uint32_t e = 0; e < n; ++e) rank += ent_less(s_d[e], s_j[e], d, j) ? 1u : 0u;
+        if (rank < k) {
+            out_dist[o + rank] = d;
+            out_idx[o + rank] = j;
+        }
+    }
+    if (threadIdx.x == 0 && n < k) {  // +inf entries of the reference, in index order
+        const uint32_t ti = tid[i];
+        uint32_t w = n;
+        for (uint32_t j = 0; j < T && w < k; ++j) {
+            if (tid[j] == ti) {
+                out_dist[o + w] = __int_as_float(0x7f800000);
+                out_idx[o + w] = j;
+                ++w;
+            }
+        }
+    }
+}
+
+__global__ void wis_overflow_list_kernel(const uint32_t *__restrict__ overflow, const uint32_t *__restrict__ cand_cnt,
+                                         uint32_t rows, uint32_t row_begin, uint32_t *__restrict__ list,
+                                         uint32_t *__restrict__ count, unsigned long long *__restrict__ n_rescored) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c = 0;
+    if (r < rows) {
+        if (overflow[r]) list[atomicAdd(count, 1u)] = row_begin + r; else c = cand_cnt[r];
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane_id() == 0 && c) atomicAdd(n_rescored, (unsigned long long)c);
+}
+
+// ---- host orchestration ------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int make_tmap(cnvb_ctx *ctx, void *H, uint64_t T, uint64_t Kp, CUtensorMap *out) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !p) return fail(ctx, CNVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    const cuuint64_t dims[2] = {Kp, T};
+    const cuuint64_t strides[1] = {Kp * 2};
+    const cuuint32_t box[2] = {kKBlock, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, H, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, CNVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+int run_rows_exact(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S, uint32_t k,
+                   const uint32_t *d_row_list, uint32_t n_rows, uint32_t row_begin, float *d_dist, uint32_t *d_idx);
+
+struct PoolGuard {  // releases pooled blocks at scope exit
+    cnvb_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit PoolGuard(cnvb_ctx *c) : ctx(c) {}
+    template <typename T>
+    cudaError_t alloc(size_t n, T **out) {
+        cudaError_t e = pool_alloc_t(ctx, n, out);
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+    ~PoolGuard() {
+        for (void *p : ptrs) pool_release(ctx, p);
+    }
+};
+
+int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S, uint32_t k,
+                         uint32_t row_begin, uint32_t row_end, float *d_dist, uint32_t *d_idx) {
+    const uint32_t rows = row_end - row_begin;
+    if (rows == 0) return 0;
+    const uint32_t Kp = ((S + kKBlock - 1) / kKBlock) * kKBlock;
+    if (Kp > kMaxKBlocks * kKBlock)
+        return fail(ctx, CNVB_ERR_INVALID, "tensor engine: more than %u samples are not supported yet; use the exact engine",
+                    kMaxKBlocks * kKBlock);
+    if (k > kCandCap / 4) return fail(ctx, CNVB_ERR_INVALID, "tensor engine: max_ref_targets > %u", kCandCap / 4);
+    const uint32_t n_tiles = (T + kTileCols - 1) / kTileCols;
+    const uint32_t Tpad = n_tiles * kTileCols;
+    PoolGuard g(ctx);
+    double *colsum = nullptr;
+    float *scal = nullptr;  // [0] absmax | [1] n_max | [2] delta_max
+    __half *H = nullptr;
+    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *cand_val = nullptr;
+    uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *tiles = nullptr, *ovf_list = nullptr;
+    cudaError_t e;
+    if ((e = g.alloc(S, &colsum)) != cudaSuccess || (e = g.alloc(4, &scal)) != cudaSuccess ||
+        (e = g.alloc((size_t)Tpad * Kp, &H)) != cudaSuccess || (e = g.alloc(Tpad, &nrm)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &delta)) != cudaSuccess || (e = g.alloc(rows, &thr)) != cudaSuccess ||
+        (e = g.alloc((size_t)rows * kCandCap, &cand_val)) != cudaSuccess ||
+        (e = g.alloc((size_t)rows * kCandCap, &cand_idx)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
+        (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(n_tiles, &tiles)) != cudaSuccess ||
+        (e = g.alloc(rows + 1, &ovf_list)) != cudaSuccess)
+        return fail_cuda(ctx, e, "allocating the tensor engine's work space");
+    cudaStream_t st = ctx->stream;
+    cudaMemsetAsync(colsum, 0, S * sizeof(double), st);
+    cudaMemsetAsync(scal, 0, 4 * sizeof(float), st);
+    cudaMemsetAsync(cand_cnt, 0, rows * 4, st);
+    cudaMemsetAsync(overflow, 0, rows * 4, st);
+    cudaMemsetAsync(ovf_list, 0, (rows + 1) * 4, st);
+    wis_colsum_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 4), 128, 0, st>>>(dX, T, S, colsum, scal);
+    CNVB_LAUNCHED(ctx, "wis_colsum_kernel");
+    float absmax = 0.0f;
+    CNVB_CUDA(ctx, cudaMemcpyAsync(&absmax, scal, 4, cudaMemcpyDeviceToHost, st), "reading the panel range");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "reading the panel range");
+    // |x - c| <= 2 absmax; map that to about 2^13 so that fp16 keeps 11 significant bits
+    int ex = 0;
+    frexpf(absmax > 0.0f ? 2.0f * absmax : 1.0f, &ex);
+    const float scale = ldexpf(1.0f, 13 - ex);
+    wis_fill_kernel<<<(Tpad - T + 255) / 256 + 1, 256, 0, st>>>(nrm, T, Tpad, __builtin_inff());
+    CNVB_LAUNCHED(ctx, "wis_fill_kernel");
+    if (Tpad > T) cudaMemsetAsync(H + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
+    wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, T, S, Kp, colsum, scale, H, nrm, delta, scal + 1);
+    CNVB_LAUNCHED(ctx, "wis_pack_kernel");
+    wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(thr, 0, rows, __builtin_inff());
+    CNVB_LAUNCHED(ctx, "wis_fill_kernel");
+
+    CUtensorMap tmap;
+    CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap));
+    // column tiles in a scattered order (stride ~ golden ratio, coprime with the tile count)
+    std::vector<uint32_t> order(n_tiles);
+    {
+        uint32_t stride = (uint32_t)(n_tiles * 0.6180339887) | 1u;
+        auto gcd = [](uint32_t x, uint32_t y) {
+            while (y) {
+                const uint32_t t = x % y;
+                x = y;
+                y = t;
+            }
+            return x;
+        };
+        while (stride > 1 && gcd(stride, n_tiles) != 1) stride += 2;
+        if (n_tiles == 1) stride = 1;
+        uint32_t cur = 0;
+        for (uint32_t q = 0; q < n_tiles; ++q) {
+            order[q] = cur;
+            cur = (uint32_t)(((uint64_t)cur + stride) % n_tiles);
+        }
+    }
+    CNVB_CUDA(ctx, cudaMemcpyAsync(tiles, order.data(), n_tiles * 4, cudaMemcpyHostToDevice, st), "uploading the tile order");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "uploading the tile order");  // `order` dies with this scope otherwise
+
+    const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+              "smem opt-in");
+    SweepArgs sa{};
+    sa.nrm = nrm;
+    sa.tid = dtid;
+    sa.thr = thr;
+    sa.T = T;
+    sa.row_begin = row_begin;
+    sa.row_end = row_end;
+    sa.k_mmas = (S + 15) / 16;
+    sa.n_kblocks = Kp / kKBlock;
+    sa.cand_val = cand_val;
+    sa.cand_idx = cand_idx;
+    sa.cand_cnt = cand_cnt;
+    CompactArgs ca{};
+    ca.cand_val = cand_val;
+    ca.cand_idx = cand_idx;
+    ca.cand_cnt = cand_cnt;
+    ca.thr = thr;
+    ca.overflow = overflow;
+    ca.nrm = nrm;
+    ca.delta = delta;
+    ca.maxes = scal + 1;
+    ca.rows = rows;
+    ca.row_begin = row_begin;
+    ca.k = k;
+    ca.c_sq = (2.0 * Kp) / 8388608.0 + 1.0 / 1048576.0;  // tensor-core accumulation + f32 epilogue
+    ca.g_ref = (S + 4.0) / 16777216.0;                   // the reference's own f32 rounding
+
+    const uint32_t row_blocks = (rows + kTileRows - 1) / kTileRows;
+    // geometric column schedule: first at least max(8, 4k/128) tiles, then x4 each step
+    uint32_t done = 0, step = std::max<uint32_t>(8, (4 * k + kTileCols - 1) / kTileCols);
+    while (done < n_tiles) {
+        const uint32_t cnt = std::min(step, n_tiles - done);
+        sa.tiles = tiles + done;
+        sa.n_tiles = cnt;
+        {
+            KernelSpan span(ctx, "wis_sweep_kernel");
+            wis_sweep_kernel<<<row_blocks, kSweepThreads, smem, st>>>(tmap, sa);
+        }
+        CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
+        {
+            KernelSpan span(ctx, "wis_compact_kernel");
+            wis_compact_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ca);
+        }
+        CNVB_LAUNCHED(ctx, "wis_compact_kernel");
+        done += cnt;
+        ctx->wis_stats[3] += 1;
+        step = 3 * done;  // every step quadruples the columns seen so far
+    }
+    const size_t rsmem = (((size_t)S + 3) & ~(size_t)3) * 4 + kCandCap * 4;
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem),
+              "smem opt-in");
+    {
+        KernelSpan span(ctx, "wis_rescore_kernel");
+        wis_rescore_kernel<<<rows, 128, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, cand_idx, cand_cnt, overflow,
+                                                     d_dist, d_idx);
+    }
+    CNVB_LAUNCHED(ctx, "wis_rescore_kernel");
+    // rows whose candidate buffer overflowed: exact row kernel
+    unsigned long long *d_resc = reinterpret_cast<unsigned long long *>(colsum);  // prep is done: reuse 8 bytes
+    cudaMemsetAsync(d_resc, 0, 8, st);
+    wis_overflow_list_kernel<<<(rows + 255) / 256, 256, 0, st>>>(overflow, cand_cnt, rows, row_begin, ovf_list + 1,
+                                                                 ovf_list, d_resc);
+    CNVB_LAUNCHED(ctx, "wis_overflow_list_kernel");
+    uint32_t n_ovf = 0;
+    unsigned long long n_resc = 0;
+    CNVB_CUDA(ctx, cudaMemcpyAsync(&n_ovf, ovf_list, 4, cudaMemcpyDeviceToHost, st), "reading the fallback count");
+    CNVB_CUDA(ctx, cudaMemcpyAsync(&n_resc, d_resc, 8, cudaMemcpyDeviceToHost, st), "reading the re-score count");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");
+    ctx->wis_stats[1] = n_ovf;
+    ctx->wis_stats[2] = n_resc;
+    if (n_ovf) CNVB_TRY(run_rows_exact(ctx, dX, dtid, T, S, k, ovf_list + 1, n_ovf, row_begin, d_dist, d_idx));
+    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");  // work space is released on return
+    return 0;
+}
+
 }  // namespace

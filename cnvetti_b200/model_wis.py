@@ -58,6 +58,14 @@ def compute_distances(X, tids, options=None, row_begin=0, row_end=None, ctx=None
     return dist, idx
 
 
+def last_stats(ctx=None):
+    """dict(rows, fallback_rows, rescored_pairs, sweeps) of the last distance computation."""
+    ctx = ctx or default_context()
+    out = (C.c_uint64 * 4)()
+    ctx.check(N.lib().cnvb_wis_last_stats(ctx.handle, out))
+    return dict(rows=int(out[0]), fallback_rows=int(out[1]), rescored_pairs=int(out[2]), sweeps=int(out[3]))
+
+
 def prune_threshold(nearest, z, stride=1, ctx=None):
     """lib.rs:207-216: (mean + z*sd) as f32 of the nearest distances of all targets."""
     ctx = ctx or default_context()

@@ -197,6 +197,10 @@ typedef struct {
 int cnvb_wis_distances(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t T, uint32_t S,
                        const cnvb_wis_opts *opts, uint32_t row_begin, uint32_t row_end,
                        float *ref_dist, uint32_t *ref_idx, int mem);
+/* diagnostics of the last cnvb_wis_distances / cnvb_wis_build on this ctx:
+ * out[0] rows computed, out[1] rows that fell back to the exact row kernel, out[2] pairs
+ * re-scored exactly (tensor engine), out[3] column sweeps */
+int cnvb_wis_last_stats(const cnvb_ctx *ctx, uint64_t out[4]);
 /* = threshold of prune_distances (lib.rs:207-216): (mean + z*sd) as f32 over the nearest
  * distance of ALL T targets (f64, exact-sum mean, n-1 SD).  `nearest` = ref_dist[.][0].
  * NaN for T < 2 (the reference returns an empty Vec).  *threshold is host memory. */

@@ -114,3 +114,41 @@ def test_modcov_parity(oracle, ctx, device):
     assert np.array_equal(np.isfinite(a), fin)
     np.testing.assert_allclose(a[fin], b[fin], rtol=1e-6, atol=1e-7)
     assert (o["status"] == 0).any() and (o["status"] == 3).any()
+
+
+@pytest.mark.parametrize("T,S,k,ncontig,device", [(5000, 100, 100, 22, True), (4321, 37, 64, 5, False),
+                                                 (9000, 128, 100, 22, True)])
+def test_wis_tensor_engine_matches_reference_sets(oracle, ctx, T, S, k, ncontig, device):
+    """tcgen05 contraction as candidate filter + exact re-scoring: sets, order and distances
+    bit-exact against the oracle's f32-sequential distances."""
+    X, tids = synth.synth_panel(T * 7 + S, T, S, n_contigs=ncontig)
+    X[11] *= 4.0   # a far-away row (large norm, large rounding error bound)
+    X[12] = X[13]  # duplicate rows on the same contig and (below) on different contigs: ties
+    X[T - 1] = X[0]
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
+    if device:
+        dist, idx = mw.compute_distances(_dev(X), _dev(tids), opts, ctx=ctx)
+    else:
+        dist, idx = mw.compute_distances(X, tids, opts, ctx=ctx)
+    st = mw.last_stats(ctx)
+    assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
+    assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
+    assert st["rows"] == T and st["sweeps"] >= 2
+    assert st["fallback_rows"] <= T // 100, st          # the bound, not the fallback, does the work
+    assert st["rescored_pairs"] < 6 * T * k, st         # and it is tight: few pairs are re-scored
+    # row block (multi-GPU shard) starting off a tile boundary
+    lo, hi = 777, 777 + 1300
+    d2, i2 = mw.compute_distances(X, tids, opts, row_begin=lo, row_end=hi, ctx=ctx)
+    assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
+
+
+def test_wis_tensor_single_contig_and_tiny_other_contig(oracle, ctx):
+    T, S, k = 4500, 20, 50
+    X, _ = synth.synth_panel(77, T, S, n_contigs=1)
+    tids = np.zeros(T, np.uint32)
+    tids[-30:] = 1   # only 30 other-contig targets for most rows: +inf fill
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
+    dist, idx = mw.compute_distances(X, tids, opts, ctx=ctx)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist.view(np.uint32), odist.view(np.uint32))
