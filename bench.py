@@ -45,6 +45,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only (profiling runs)")
+    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis"],
+                    help="coverage = BASELINE configs[1] (default, the headline); wis = configs[2]")
+    ap.add_argument("--targets", type=int, default=200_000, help="wis: number of targets T")
+    ap.add_argument("--samples", type=int, default=100, help="wis: number of samples S")
+    ap.add_argument("--cpu-rows", type=int, default=2000, help="wis: rows of the CPU baseline sample")
     ap.add_argument("--cpu-sample-contigs", type=int, default=4, help="last k contigs form the CPU sample")
     return ap.parse_args()
 
@@ -151,8 +156,109 @@ def cpu_reference_leg(sample, steps, warmup):
     return n_reads, dt
 
 
+def bench_wis(args):
+    """BASELINE configs[2]: build-model-wis on a synthetic panel (T targets x S samples, k=100).
+    One step = compute_distances + prune + per-probe calls + filters (lib_model_wis::run)."""
+    import torch
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import model_wis as mw
+    from cnvetti_b200 import synth
+    T, S = args.targets, args.samples
+    dev = "cuda:0"
+    ctx = cb.Context(0)
+    X, tids = synth.synth_panel(3, T, S)
+    dX = torch.from_numpy(X).to(dev)
+    dt = torch.from_numpy(tids.view(np.int32)).to(dev)
+    opts = mw.BuildModelWisOptions(engine=mw.ENGINE_TENSOR)
+    workload = "cfg3: build-model-wis, synthetic panel %d targets x %d samples, k=100 (tensor engine)" % (T, S)
+
+    def step():
+        return mw.run(dX, dt, opts, ctx=ctx)
+
+    m = step()
+    torch.cuda.synchronize()
+    stats = mw.last_stats(ctx)
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    sampler = ClockSampler(0)
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count - l0
+    kern = {}
+    for kname in ("wis_sweep_kernel", "wis_compact_kernel", "wis_rescore_kernel", "wis_calls_kernel",
+                  "wis_row_exact_kernel"):
+        kms, cnt = ctx.timing_query(kname)
+        kern[kname] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps}
+    ctx.set_timing(False)
+    ctx.timing_reset()
+    value = float(T) * T / (ms * 1e-3)
+    # e2e: host panel in, model out
+    hX = torch.from_numpy(X).pin_memory()
+    ht = torch.from_numpy(tids.view(np.int32)).pin_memory()
+    k = min(T, opts.max_ref_targets)
+
+    def step_e2e():
+        mm = mw.run(hX.to(dev, non_blocking=True), ht.to(dev, non_blocking=True), opts, ctx=ctx)
+        out = [mm.ref_idx.cpu(), mm.ref_len.cpu(), mm.num_calls.cpu(), mm.filt.cpu()]
+        torch.cuda.synchronize()
+        return out
+
+    step_e2e()
+    t0 = time.perf_counter()
+    esteps = max(1, min(args.steps, 3))
+    for _ in range(esteps):
+        step_e2e()
+    e2e_s = (time.perf_counter() - t0) / esteps
+    peak_t = 1406.9
+    pfile = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pfile):
+        peak_t = float(json.load(open(pfile)).get("bf16_tflops_sustained", peak_t))
+    sweep = kern["wis_sweep_kernel"]["ms_per_step"]
+    achieved = 2.0 * T * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
+    cpu = None
+    if not args.quick:
+        import oracle
+        oracle.build()
+        rows = min(args.cpu_rows, T)
+        ncpu = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        oracle.wis_distances(X, tids, 100, 0, rows, nthreads=ncpu)
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": rows * float(T) / dt_cpu, "unit": "bin-pairs/s", "cores": ncpu, "kind": "port",
+               "sample": "compute_distances for the first %d of %d target rows (all columns), %d threads as rayon "
+                         "does; linear in rows" % (rows, T, ncpu)}
+    line = {"metric": "WIS bin-pairs/s", "value": value, "unit": "bin-pairs/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16 tensor filter + exact f32 re-score)", "data": "synthetic",
+            "config": {"workload": workload, "targets": T, "samples": S, "k": k,
+                       "l2": "panel %.0f MB + candidate buffers %.1f GB exceed L2" % (T * S * 4 / 1e6, T * 2048 * 8 / 1e9)},
+            "e2e": {"value": float(T) * T / e2e_s, "unit": "bin-pairs/s", "h2d_bytes_per_step": int(X.nbytes + tids.nbytes),
+                    "d2h_bytes_per_step": int(T * k * 4 + T * 9), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": achieved, "peak": peak_t,
+                         "unit": "TFLOP/s", "frac": achieved / peak_t, "traffic": None,
+                         "algorithmic_flop_per_pair": 2 * S, "kernel_share_of_step": sweep / ms,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern, "wis_stats": stats}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload == "wis" and args.impl == "b200":
+        return bench_wis(args)
     import torch
     import torch.distributed as dist
 

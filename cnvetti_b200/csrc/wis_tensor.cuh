@@ -20,13 +20,19 @@
 //            k-th smallest candidate value and tightens theta'_i with the bound below.
 //   rescore  exact f32-sequential distance for every candidate, (distance, index) top-k.
 //
-// Bound (scaled units; eps_i = c_sq (n_i + n_max) covers tensor-core accumulation and f32
-// epilogue rounding of the squared fp16 distance, Delta_i = delta_i + delta_max, g bounds the
-// reference's own rounding relative error):  with v_k the k-th smallest approximate squared
-// distance seen so far, V = (1+g)(sqrt(v_k + eps_i) + Delta_i) is >= the final k-th reference
-// distance, and a pair can only belong to the top k if its approximate squared distance is
-// <= theta_i = (V/(1-g) + Delta_i)^2 + eps_i.  Rows whose buffer overflows fall back to the
-// exact row kernel, so the result never depends on the bound being tight.
+// Bound (scaled units; everything per PAIR so that a few large-norm rows do not loosen it for
+// all): the fp16 squared distance d_h^2 and its tensor-core value differ by at most
+// eps_ij = 2 c_acc s_i s_j + c_rnd (n_i + n_j)  (s = sqrt(n); fp32 accumulation over Kp terms and
+// the f32 epilogue), the real distance D and d_h by at most delta_i + delta_j, the reference's
+// f32 distance and D by a relative g.  Hence per pair
+//   U_ij = (1+g)(sqrt(d2 + eps_ij) + delta_i + delta_j) >= D_ref >= (1-g)(sqrt(d2 - eps_ij) - delta_i - delta_j) = L_ij.
+// With V = k-th smallest U_ij seen so far (>= the final k-th reference distance) a pair can only
+// be among the top k if L_ij <= V.  The compaction kernel applies exactly that test; the sweep
+// uses the cheaper sufficient form (delta_j <= rho s_j, rho = max_j delta_j / s_j)
+//   n'_j - 2 g_ij - kappa_i s_j <= theta_i,   n'_j = n_j (1 - rho^2 - c_rnd),
+//   kappa_i = 2 c_acc s_i + 2 rho V'_i,  theta_i = V'_i^2 - n_i (1 - c_rnd),  V'_i = V/(1-g) + delta_i,
+// i.e. two FFMAs and a compare per pair.  Rows whose buffer overflows fall back to the exact row
+// kernel, so the result never depends on the bound being tight.
 #pragma once
 
 #include <cuda.h>
@@ -159,9 +165,24 @@ __global__ void wis_pack_kernel(const float *__restrict__ X, uint32_t T, uint32_
         const float df = __double2float_ru(sqrt(e) * (1.0 + 1.0 / 1024.0) + sqrt(n) * (1.0 / 8388608.0));
         nrm[warp] = nf;
         delta[warp] = df;
-        atomicMax(reinterpret_cast<int *>(maxes), __float_as_int(nf));
-        atomicMax(reinterpret_cast<int *>(maxes) + 1, __float_as_int(df));
+        const float rho = __double2float_ru((double)df / fmax(sqrt(n), 1.0));  // delta_j <= rho * max(s_j, 1)
+        atomicMax(reinterpret_cast<int *>(maxes), __float_as_int(rho));
     }
+}
+
+// per-column operands of the sweep test: n'_j (+inf beyond T: never a candidate) and s_j
+__global__ void wis_cols_kernel(const float *__restrict__ nrm, uint32_t T, uint32_t Tpad, const float *__restrict__ maxes,
+                                double c_rnd, float *__restrict__ nprime, float *__restrict__ snorm) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Tpad) return;
+    if (j >= T) {
+        nprime[j] = __int_as_float(0x7f800000);
+        snorm[j] = 0.0f;
+        return;
+    }
+    const double rho = (double)maxes[0], n = (double)nrm[j];
+    nprime[j] = __double2float_rd(n * (1.0 - rho * rho - c_rnd));
+    snorm[j] = __double2float_ru(fmax(sqrt(n), 1.0));
 }
 
 __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi, float v) {
@@ -171,9 +192,11 @@ __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi,
 
 // ---- sweep ------------------------------------------------------------------------------------------
 struct SweepArgs {
-    const float *nrm;        // [Tpad] (+inf beyond T)
+    const float *nprime;     // [Tpad] n'_j (+inf beyond T)
+    const float *snorm;      // [Tpad] s_j = sqrt(n_j)
     const uint32_t *tid;     // [T]
-    const float *thr;        // [rows] theta'_i = theta_i - n_i  (+inf until k candidates are known)
+    const float *thr;        // [rows] theta_i (+inf until k candidates are known)
+    const float *kap;        // [rows] kappa_i
     const uint32_t *tiles;   // column tiles of this step
     uint32_t n_tiles;
     uint32_t T, row_begin, row_end;
@@ -288,12 +311,13 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
         const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
         const uint32_t t = q * 32 + lane;
         uint32_t row[2], cnt[2], rtid[2];
-        float thr[2];
+        float thr[2], nkap[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             row[h] = row0 + h * 128 + t;
             const bool live = row[h] < a.row_end;
             thr[h] = live ? a.thr[row[h] - a.row_begin] : -__int_as_float(0x7f800000);
+            nkap[h] = live ? -a.kap[row[h] - a.row_begin] : 0.0f;
             cnt[h] = live ? a.cand_cnt[row[h] - a.row_begin] : 0u;
             rtid[h] = live ? a.tid[row[h]] : 0xffffffffu;
         }
@@ -305,27 +329,32 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols;
-                const float th = thr[h];
+                const float th = thr[h], nk = nkap[h];
                 float *cv = a.cand_val + (size_t)(row[h] - a.row_begin) * kCandCap;
                 uint32_t *ci = a.cand_idx + (size_t)(row[h] - a.row_begin) * kCandCap;
 #pragma unroll 1
                 for (uint32_t c0 = 0; c0 < kTileCols; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32(taddr + c0, r);
-                    const float4 *nj4 = reinterpret_cast<const float4 *>(a.nrm + j0 + c0);
+                    const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0 + c0);
+                    const float4 *sj4 = reinterpret_cast<const float4 *>(a.snorm + j0 + c0);
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 nj = __ldg(nj4 + g4);
+                        const float4 nj = __ldg(nj4 + g4), sj = __ldg(sj4 + g4);
+                        // v = n'_j - 2 g (stored);  v - kappa_i s_j <= theta_i decides
                         const float v0 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj.x);
                         const float v1 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj.y);
                         const float v2 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj.z);
                         const float v3 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj.w);
-                        if (v0 <= th || v1 <= th || v2 <= th || v3 <= th) {
+                        const float w0 = fmaf(nk, sj.x, v0), w1 = fmaf(nk, sj.y, v1);
+                        const float w2 = fmaf(nk, sj.z, v2), w3 = fmaf(nk, sj.w, v3);
+                        if (w0 <= th || w1 <= th || w2 <= th || w3 <= th) {
                             const float vv[4] = {v0, v1, v2, v3};
+                            const float ww[4] = {w0, w1, w2, w3};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const uint32_t j = j0 + c0 + 4 * g4 + e;
-                                if (vv[e] <= th && j < a.T && a.tid[j] != rtid[h]) {
+                                if (ww[e] <= th && j < a.T && a.tid[j] != rtid[h]) {
                                     if (cnt[h] < kCandCap) {
                                         cv[cnt[h]] = vv[e];
                                         ci[cnt[h]] = j;
@@ -367,16 +396,26 @@ __device__ __forceinline__ float key_f32(uint32_t u) {
 }
 
 struct CompactArgs {
-    float *cand_val;
+    float *cand_val;         // stored v = n'_j - 2 g
     uint32_t *cand_idx;
     uint32_t *cand_cnt;
-    float *thr;
+    float *thr, *kap;
     uint32_t *overflow;      // [rows] sticky flag
     const float *nrm, *delta;  // indexed by absolute row
-    const float *maxes;      // [0] n_max, [1] delta_max
+    const float *maxes;      // [0] rho
     uint32_t rows, row_begin, k;
-    double c_sq, g_ref;
+    double c_acc, c_rnd, g_ref;
 };
+
+// per-pair bounds on the reference distance from a stored candidate value
+__device__ __forceinline__ void pair_bounds(const CompactArgs &a, double v, double ni, double di, double rho, uint32_t j,
+                                            double &U, double &L) {
+    const double nj = (double)a.nrm[j], dj = (double)a.delta[j];
+    const double d2 = v + nj * (rho * rho + a.c_rnd) + ni;  // undo n'_j: approximate |h_i - h_j|^2
+    const double eps = 2.0 * a.c_acc * sqrt(ni * nj) + a.c_rnd * (ni + nj);
+    U = (1.0 + a.g_ref) * (sqrt(fmax(d2 + eps, 0.0)) + di + dj);
+    L = (1.0 - a.g_ref) * (sqrt(fmax(d2 - eps, 0.0)) - di - dj);
+}
 
 __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
@@ -387,18 +426,26 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
             a.overflow[r] = 1u;
             a.cand_cnt[r] = 0u;
             a.thr[r] = -__int_as_float(0x7f800000);  // stop collecting: the row is recomputed exactly
+            a.kap[r] = 0.0f;
         }
         return;
     }
     if (n < a.k || a.overflow[r]) return;  // not enough candidates for a bound yet
     float *cv = a.cand_val + (size_t)r * kCandCap;
     uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
+    const uint32_t row = a.row_begin + r;
+    const double ni = (double)a.nrm[row], di = (double)a.delta[row], rho = (double)a.maxes[0];
     constexpr uint32_t kPer = kCandCap / 32;
-    uint32_t key[kPer];
+    uint32_t key[kPer];  // upper bounds U_ij (f32, rounded up) as ordered keys
 #pragma unroll
     for (uint32_t e = 0; e < kPer; ++e) {
         const uint32_t c = e * 32 + lane;
-        key[e] = c < n ? f32_key(cv[c]) : 0xFFFFFFFFu;
+        key[e] = 0xFFFFFFFFu;
+        if (c < n) {
+            double U, L;
+            pair_bounds(a, (double)cv[c], ni, di, rho, ci[c], U, L);
+            key[e] = f32_key(__double2float_ru(U));
+        }
     }
     // bit-descent select of the k-th smallest key
     uint32_t prefix = 0, want = a.k;
@@ -414,17 +461,8 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
             prefix |= 1u << bit;
         }
     }
-    const float vk = key_f32(prefix);  // k-th smallest  n_j - 2 g  of this row
-    const uint32_t row = a.row_begin + r;
-    const double ni = (double)a.nrm[row], nmax = (double)a.maxes[0];
-    const double Delta = (double)a.delta[row] + (double)a.maxes[1];
-    const double eps = a.c_sq * (ni + nmax);
-    const double dk2 = fmax((double)vk + ni + eps, 0.0);
-    const double V = (1.0 + a.g_ref) * (sqrt(dk2) + Delta);
-    const double w = V / (1.0 - a.g_ref) + Delta;
-    const double theta = (w * w + eps) * (1.0 + 1e-12);
-    const float thr = __double2float_ru(theta - ni);
-    // keep the survivors (order irrelevant)
+    const double V = (double)key_f32(prefix);  // >= the final k-th reference distance of this row
+    // keep exactly the pairs that can still be among the top k
     uint32_t kept = 0;
     for (uint32_t base = 0; base < n; base += 32) {
         const uint32_t c = base + lane;
@@ -434,7 +472,9 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
         if (c < n) {
             v = cv[c];
             j = ci[c];
-            keep = v <= thr;
+            double U, L;
+            pair_bounds(a, (double)v, ni, di, rho, j, U, L);
+            keep = L <= V;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
@@ -447,8 +487,13 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
         __syncwarp();
     }
     if (lane == 0) {
+        // sweep test for the columns still to come (sufficient form, see the header comment)
+        const double Vp = V / (1.0 - a.g_ref) + di;
+        const double kappa = 2.0 * a.c_acc * sqrt(ni) + 2.0 * rho * Vp;
+        const double theta = Vp * Vp * (1.0 + 1e-9) - ni * (1.0 - a.c_rnd);
         a.cand_cnt[r] = kept;
-        a.thr[r] = thr;
+        a.thr[r] = __double2float_ru(theta);
+        a.kap[r] = __double2float_ru(kappa * (1.0 + 1e-6));
     }
 }
 
@@ -569,12 +614,15 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     double *colsum = nullptr;
     float *scal = nullptr;  // [0] absmax | [1] n_max | [2] delta_max
     __half *H = nullptr;
-    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *cand_val = nullptr;
+    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *cand_val = nullptr, *nprime = nullptr,
+          *snorm = nullptr;
     uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *tiles = nullptr, *ovf_list = nullptr;
     cudaError_t e;
     if ((e = g.alloc(S, &colsum)) != cudaSuccess || (e = g.alloc(4, &scal)) != cudaSuccess ||
         (e = g.alloc((size_t)Tpad * Kp, &H)) != cudaSuccess || (e = g.alloc(Tpad, &nrm)) != cudaSuccess ||
         (e = g.alloc(Tpad, &delta)) != cudaSuccess || (e = g.alloc(rows, &thr)) != cudaSuccess ||
+        (e = g.alloc(rows, &kap)) != cudaSuccess || (e = g.alloc(Tpad, &nprime)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &snorm)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_val)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_idx)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
         (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(n_tiles, &tiles)) != cudaSuccess ||
@@ -595,13 +643,16 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     int ex = 0;
     frexpf(absmax > 0.0f ? 2.0f * absmax : 1.0f, &ex);
     const float scale = ldexpf(1.0f, 13 - ex);
-    wis_fill_kernel<<<(Tpad - T + 255) / 256 + 1, 256, 0, st>>>(nrm, T, Tpad, __builtin_inff());
-    CNVB_LAUNCHED(ctx, "wis_fill_kernel");
     if (Tpad > T) cudaMemsetAsync(H + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
     wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, T, S, Kp, colsum, scale, H, nrm, delta, scal + 1);
     CNVB_LAUNCHED(ctx, "wis_pack_kernel");
+    const double c_acc = (double)Kp / 8388608.0;  // fp32 accumulation of Kp exact products, truncating adds
+    const double c_rnd = 8.0 / 16777216.0;        // f32 rounding of norms and of the epilogue FFMAs
+    wis_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nrm, T, Tpad, scal + 1, c_rnd, nprime, snorm);
+    CNVB_LAUNCHED(ctx, "wis_cols_kernel");
     wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(thr, 0, rows, __builtin_inff());
     CNVB_LAUNCHED(ctx, "wis_fill_kernel");
+    cudaMemsetAsync(kap, 0, rows * 4, st);
 
     CUtensorMap tmap;
     CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap));
@@ -632,9 +683,11 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
               "smem opt-in");
     SweepArgs sa{};
-    sa.nrm = nrm;
+    sa.nprime = nprime;
+    sa.snorm = snorm;
     sa.tid = dtid;
     sa.thr = thr;
+    sa.kap = kap;
     sa.T = T;
     sa.row_begin = row_begin;
     sa.row_end = row_end;
@@ -648,6 +701,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.cand_idx = cand_idx;
     ca.cand_cnt = cand_cnt;
     ca.thr = thr;
+    ca.kap = kap;
     ca.overflow = overflow;
     ca.nrm = nrm;
     ca.delta = delta;
@@ -655,8 +709,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.rows = rows;
     ca.row_begin = row_begin;
     ca.k = k;
-    ca.c_sq = (2.0 * Kp) / 8388608.0 + 1.0 / 1048576.0;  // tensor-core accumulation + f32 epilogue
-    ca.g_ref = (S + 4.0) / 16777216.0;                   // the reference's own f32 rounding
+    ca.c_acc = c_acc;
+    ca.c_rnd = c_rnd;
+    ca.g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
 
     const uint32_t row_blocks = (rows + kTileRows - 1) / kTileRows;
     // geometric column schedule: first at least max(8, 4k/128) tiles, then x4 each step
