@@ -47,7 +47,8 @@ constexpr uint32_t kMaxKBlocks = 2;   // A stays resident: Kp <= 128
 constexpr uint32_t kStages = 8;       // B ring: 8 x 16 KB
 constexpr uint32_t kTileBytes = 128 * kKBlock * 2;  // 16 KB: 128 rows x 64 fp16
 constexpr uint32_t kCandCap = 2048;   // candidate buffer entries per row
-constexpr uint32_t kSweepThreads = 256;
+constexpr uint32_t kEpiWarps = 16;     // 4 per TMEM lane quarter, each a quarter of the tile's columns
+constexpr uint32_t kSweepThreads = (4 + kEpiWarps) * 32;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,6 +186,16 @@ __global__ void wis_cols_kernel(const float *__restrict__ nrm, uint32_t T, uint3
     snorm[j] = __double2float_ru(fmax(sqrt(n), 1.0));
 }
 
+__global__ void wis_tile_smax_kernel(const float *__restrict__ snorm, uint32_t n_tiles, float *__restrict__ tile_smax) {
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
+    if (tile >= n_tiles) return;
+    float m = 0.0f;
+    for (uint32_t c = lane; c < kTileCols; c += 32) m = fmaxf(m, snorm[tile * kTileCols + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) tile_smax[tile] = m;
+}
+
 __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi, float v) {
     const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < hi) p[i] = v;
@@ -193,7 +204,7 @@ __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi,
 // ---- sweep ------------------------------------------------------------------------------------------
 struct SweepArgs {
     const float *nprime;     // [Tpad] n'_j (+inf beyond T)
-    const float *snorm;      // [Tpad] s_j = sqrt(n_j)
+    const float *tile_smax;  // [n column tiles] max_j s_j over the tile
     const uint32_t *tid;     // [T]
     const float *thr;        // [rows] theta_i (+inf until k candidates are known)
     const float *kap;        // [rows] kappa_i
@@ -210,6 +221,7 @@ struct SweepArgs {
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -223,6 +235,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = a.row_begin + blockIdx.x * kTileRows;
+    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
+        s_cnt[t] = row0 + t < a.row_end ? a.cand_cnt[row0 + t - a.row_begin] : 0u;
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
@@ -232,7 +246,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
         }
         for (uint32_t s = 0; s < 2; ++s) {
             mbar_init(bar_acc_full + 8 * s, 1);
-            mbar_init(bar_acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+            mbar_init(bar_acc_empty + 8 * s, kEpiWarps);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -307,60 +321,63 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread t owns rows row0 + t and row0 + 128 + t =====
-        const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
-        const uint32_t t = q * 32 + lane;
-        uint32_t row[2], cnt[2], rtid[2];
-        float thr[2], nkap[2];
+        // ===== epilogue: 16 warps.  Warp e reads TMEM lane quarter q = e & 3 (rows row0 + 32 q + lane
+        // and + 128) and the 32 columns [32 (e >> 2), +32) of both accumulators.  With four warps per
+        // scheduler the TMEM / L1 latencies of one warp hide behind the compares of the others. =====
+        const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
+        uint32_t rloc[2], rtid[2];
+        float thr[2], kap[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            row[h] = row0 + h * 128 + t;
-            const bool live = row[h] < a.row_end;
-            thr[h] = live ? a.thr[row[h] - a.row_begin] : -__int_as_float(0x7f800000);
-            nkap[h] = live ? -a.kap[row[h] - a.row_begin] : 0.0f;
-            cnt[h] = live ? a.cand_cnt[row[h] - a.row_begin] : 0u;
-            rtid[h] = live ? a.tid[row[h]] : 0xffffffffu;
+            rloc[h] = h * 128 + q * 32 + lane;  // row within the CTA's 256
+            const uint32_t row = row0 + rloc[h];
+            const bool live = row < a.row_end;
+            thr[h] = live ? a.thr[row - a.row_begin] : -__int_as_float(0x7f800000);
+            kap[h] = live ? a.kap[row - a.row_begin] : 0.0f;
+            rtid[h] = live ? a.tid[row] : 0xffffffffu;
         }
         uint32_t as = 0, aph = 0;
         for (uint32_t it = 0; it < a.n_tiles; ++it) {
-            const uint32_t j0 = a.tiles[it] * kTileCols;
+            const uint32_t tile = a.tiles[it];
+            const uint32_t j0 = tile * kTileCols + cpart * 32u;
+            // column operands of this warp's 32 columns (same addresses for all lanes: L1 broadcast)
+            float nj[32];
+            {
+                const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0);
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    const float4 v = __ldg(nj4 + g4);
+                    nj[4 * g4 + 0] = v.x;
+                    nj[4 * g4 + 1] = v.y;
+                    nj[4 * g4 + 2] = v.z;
+                    nj[4 * g4 + 3] = v.w;
+                }
+            }
+            const float smax = __ldg(a.tile_smax + tile);
             mbar_wait(bar_acc_full + 8 * as, aph);
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols;
-                const float th = thr[h], nk = nkap[h];
-                float *cv = a.cand_val + (size_t)(row[h] - a.row_begin) * kCandCap;
-                uint32_t *ci = a.cand_idx + (size_t)(row[h] - a.row_begin) * kCandCap;
-#pragma unroll 1
-                for (uint32_t c0 = 0; c0 < kTileCols; c0 += 32) {
-                    uint32_t r[32];
-                    tc_ld32(taddr + c0, r);
-                    const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0 + c0);
-                    const float4 *sj4 = reinterpret_cast<const float4 *>(a.snorm + j0 + c0);
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
+                // keep iff  n'_j - 2 g - kappa_i s_j <= theta_i;  sufficient: n'_j - 2 g <= theta_i + kappa_i smax
+                const float rhs = fmaf(kap[h], smax, thr[h]);
+                bool any = false;
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 nj = __ldg(nj4 + g4), sj = __ldg(sj4 + g4);
-                        // v = n'_j - 2 g (stored);  v - kappa_i s_j <= theta_i decides
-                        const float v0 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj.x);
-                        const float v1 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj.y);
-                        const float v2 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj.z);
-                        const float v3 = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj.w);
-                        const float w0 = fmaf(nk, sj.x, v0), w1 = fmaf(nk, sj.y, v1);
-                        const float w2 = fmaf(nk, sj.z, v2), w3 = fmaf(nk, sj.w, v3);
-                        if (w0 <= th || w1 <= th || w2 <= th || w3 <= th) {
-                            const float vv[4] = {v0, v1, v2, v3};
-                            const float ww[4] = {w0, w1, w2, w3};
+                for (int c = 0; c < 32; ++c) any |= fmaf(-2.0f, __uint_as_float(r[c]), nj[c]) <= rhs;
+                if (any) {
+                    const uint32_t row = row0 + rloc[h];
+                    float *cv = a.cand_val + (size_t)(row - a.row_begin) * kCandCap;
+                    uint32_t *ci = a.cand_idx + (size_t)(row - a.row_begin) * kCandCap;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const uint32_t j = j0 + c0 + 4 * g4 + e;
-                                if (ww[e] <= th && j < a.T && a.tid[j] != rtid[h]) {
-                                    if (cnt[h] < kCandCap) {
-                                        cv[cnt[h]] = vv[e];
-                                        ci[cnt[h]] = j;
-                                    }
-                                    cnt[h] += 1;  // beyond kCandCap: overflow, the row falls back
-                                }
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                        const uint32_t j = j0 + c;
+                        if (v <= rhs && j < a.T && a.tid[j] != rtid[h]) {
+                            const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
+                            if (slot < kCandCap) {  // beyond: overflow, the row falls back
+                                cv[slot] = v;
+                                ci[slot] = j;
                             }
                         }
                     }
@@ -374,12 +391,11 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
                 aph ^= 1u;
             }
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-            if (row[h] < a.row_end) a.cand_cnt[row[h] - a.row_begin] = cnt[h];
     }
     tc_fence_before();
     __syncthreads();
+    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
+        if (row0 + t < a.row_end) a.cand_cnt[row0 + t - a.row_begin] = s_cnt[t];
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -417,7 +433,10 @@ __device__ __forceinline__ void pair_bounds(const CompactArgs &a, double v, doub
     L = (1.0 - a.g_ref) * (sqrt(fmax(d2 - eps, 0.0)) - di - dj);
 }
 
-__global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
+// KPER = candidates per lane held in registers; rows with more than n_min candidates only (two
+// launches, KPER 16 and 64, so that the common short lists do not pay for the longest one)
+template <uint32_t KPER>
+__global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_t n_min) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (r >= a.rows) return;
     uint32_t n = a.cand_cnt[r];
@@ -431,11 +450,12 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a) {
         return;
     }
     if (n < a.k || a.overflow[r]) return;  // not enough candidates for a bound yet
+    if (n <= n_min || n > 32u * KPER) return;  // the other launch's rows
     float *cv = a.cand_val + (size_t)r * kCandCap;
     uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
     const uint32_t row = a.row_begin + r;
     const double ni = (double)a.nrm[row], di = (double)a.delta[row], rho = (double)a.maxes[0];
-    constexpr uint32_t kPer = kCandCap / 32;
+    constexpr uint32_t kPer = KPER;
     uint32_t key[kPer];  // upper bounds U_ij (f32, rounded up) as ordered keys
 #pragma unroll
     for (uint32_t e = 0; e < kPer; ++e) {
@@ -615,14 +635,14 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     float *scal = nullptr;  // [0] absmax | [1] n_max | [2] delta_max
     __half *H = nullptr;
     float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *cand_val = nullptr, *nprime = nullptr,
-          *snorm = nullptr;
+          *snorm = nullptr, *tile_smax = nullptr;
     uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *tiles = nullptr, *ovf_list = nullptr;
     cudaError_t e;
     if ((e = g.alloc(S, &colsum)) != cudaSuccess || (e = g.alloc(4, &scal)) != cudaSuccess ||
         (e = g.alloc((size_t)Tpad * Kp, &H)) != cudaSuccess || (e = g.alloc(Tpad, &nrm)) != cudaSuccess ||
         (e = g.alloc(Tpad, &delta)) != cudaSuccess || (e = g.alloc(rows, &thr)) != cudaSuccess ||
         (e = g.alloc(rows, &kap)) != cudaSuccess || (e = g.alloc(Tpad, &nprime)) != cudaSuccess ||
-        (e = g.alloc(Tpad, &snorm)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &snorm)) != cudaSuccess || (e = g.alloc(n_tiles, &tile_smax)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_val)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_idx)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
         (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(n_tiles, &tiles)) != cudaSuccess ||
@@ -650,6 +670,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     const double c_rnd = 8.0 / 16777216.0;        // f32 rounding of norms and of the epilogue FFMAs
     wis_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nrm, T, Tpad, scal + 1, c_rnd, nprime, snorm);
     CNVB_LAUNCHED(ctx, "wis_cols_kernel");
+    wis_tile_smax_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(snorm, n_tiles, tile_smax);
+    CNVB_LAUNCHED(ctx, "wis_tile_smax_kernel");
     wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(thr, 0, rows, __builtin_inff());
     CNVB_LAUNCHED(ctx, "wis_fill_kernel");
     cudaMemsetAsync(kap, 0, rows * 4, st);
@@ -684,7 +706,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
               "smem opt-in");
     SweepArgs sa{};
     sa.nprime = nprime;
-    sa.snorm = snorm;
+    sa.tile_smax = tile_smax;
     sa.tid = dtid;
     sa.thr = thr;
     sa.kap = kap;
@@ -727,7 +749,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         {
             KernelSpan span(ctx, "wis_compact_kernel");
-            wis_compact_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ca);
+            wis_compact_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(ca, 0u);
+            wis_compact_kernel<kCandCap / 32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 512u);
         }
         CNVB_LAUNCHED(ctx, "wis_compact_kernel");
         done += cnt;
