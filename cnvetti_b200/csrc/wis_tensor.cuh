@@ -362,18 +362,18 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
                 tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
                 // keep iff  n'_j - 2 g - kappa_i s_j <= theta_i;  sufficient: n'_j - 2 g <= theta_i + kappa_i smax
                 const float rhs = fmaf(kap[h], smax, thr[h]);
-                bool any = false;
+                const uint32_t row = row0 + rloc[h];
+                float *cv = a.cand_val + (size_t)(row - a.row_begin) * kCandCap;
+                uint32_t *ci = a.cand_idx + (size_t)(row - a.row_begin) * kCandCap;
+                // Survivors are rare (a few per 1024 pairs): one vote per column keeps the branch
+                // warp-uniform, so the append code runs only for columns where some row passes.
 #pragma unroll
-                for (int c = 0; c < 32; ++c) any |= fmaf(-2.0f, __uint_as_float(r[c]), nj[c]) <= rhs;
-                if (any) {
-                    const uint32_t row = row0 + rloc[h];
-                    float *cv = a.cand_val + (size_t)(row - a.row_begin) * kCandCap;
-                    uint32_t *ci = a.cand_idx + (size_t)(row - a.row_begin) * kCandCap;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                for (int c = 0; c < 32; ++c) {
+                    const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                    const bool pass = v <= rhs;
+                    if (__any_sync(0xffffffffu, pass)) {
                         const uint32_t j = j0 + c;
-                        if (v <= rhs && j < a.T && a.tid[j] != rtid[h]) {
+                        if (pass && j < a.T && a.tid[j] != rtid[h]) {
                             const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
                             if (slot < kCandCap) {  // beyond: overflow, the row falls back
                                 cv[slot] = v;
@@ -423,14 +423,15 @@ struct CompactArgs {
     double c_acc, c_rnd, g_ref;
 };
 
-// per-pair bounds on the reference distance from a stored candidate value
-__device__ __forceinline__ void pair_bounds(const CompactArgs &a, double v, double ni, double di, double rho, uint32_t j,
-                                            double &U, double &L) {
-    const double nj = (double)a.nrm[j], dj = (double)a.delta[j];
-    const double d2 = v + nj * (rho * rho + a.c_rnd) + ni;  // undo n'_j: approximate |h_i - h_j|^2
-    const double eps = 2.0 * a.c_acc * sqrt(ni * nj) + a.c_rnd * (ni + nj);
-    U = (1.0 + a.g_ref) * (sqrt(fmax(d2 + eps, 0.0)) + di + dj);
-    L = (1.0 - a.g_ref) * (sqrt(fmax(d2 - eps, 0.0)) - di - dj);
+// per-pair bounds on the reference distance from a stored candidate value v = n'_j - 2 g:
+//   U_ij = (1+g)(sqrt(d2 + eps) + delta_i + delta_j) >= D_ref,   and   D_ref > V  is certain when
+//   d2 - eps > (V/(1-g) + delta_i + delta_j)^2   (the lower bound L_ij > V, written without a sqrt)
+__device__ __forceinline__ void pair_terms(const CompactArgs &a, double v, double ni, double rho, uint32_t j,
+                                           double &d2, double &eps, double &dj) {
+    const double nj = (double)a.nrm[j];
+    dj = (double)a.delta[j];
+    d2 = v + nj * (rho * rho + a.c_rnd) + ni;  // undo n'_j: approximate |h_i - h_j|^2
+    eps = 2.0 * a.c_acc * sqrt(ni * nj) + a.c_rnd * (ni + nj);
 }
 
 // KPER = candidates per lane held in registers; rows with more than n_min candidates only (two
@@ -462,26 +463,31 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         const uint32_t c = e * 32 + lane;
         key[e] = 0xFFFFFFFFu;
         if (c < n) {
-            double U, L;
-            pair_bounds(a, (double)cv[c], ni, di, rho, ci[c], U, L);
+            double d2, eps, dj;
+            pair_terms(a, (double)cv[c], ni, rho, ci[c], d2, eps, dj);
+            const double U = (1.0 + a.g_ref) * (sqrt(fmax(d2 + eps, 0.0)) + di + dj);
             key[e] = f32_key(__double2float_ru(U));
         }
     }
-    // bit-descent select of the k-th smallest key
-    uint32_t prefix = 0, want = a.k;
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t mask = bit == 31 ? 0u : (0xFFFFFFFFu << (bit + 1));
+    // bit-descent select of the k-th smallest key.  U >= 0, so bit 31 of every key is set; the
+    // lowest 6 bits are not resolved but set, which only rounds V up (by < 2^-17 relative): any
+    // upper bound of the k-th smallest U is a valid V.
+    uint32_t prefix = 0x80000000u, want = a.k;
+    for (int bit = 30; bit >= 6; --bit) {
+        const uint32_t mask = 0xFFFFFFFFu << (bit + 1);
         uint32_t zeros = 0;
 #pragma unroll
         for (uint32_t e = 0; e < kPer; ++e)
-            zeros += ((key[e] & mask) == prefix && !((key[e] >> bit) & 1u) && (e * 32 + lane) < n) ? 1u : 0u;
+            zeros += ((key[e] & mask) == prefix && !((key[e] >> bit) & 1u)) ? 1u : 0u;  // (padding keys are all ones)
         zeros = __reduce_add_sync(0xffffffffu, zeros);
         if (want > zeros) {
             want -= zeros;
             prefix |= 1u << bit;
         }
     }
+    prefix |= 63u;
     const double V = (double)key_f32(prefix);  // >= the final k-th reference distance of this row
+    const double Vg = V / (1.0 - a.g_ref) + di;
     // keep exactly the pairs that can still be among the top k
     uint32_t kept = 0;
     for (uint32_t base = 0; base < n; base += 32) {
@@ -492,9 +498,10 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         if (c < n) {
             v = cv[c];
             j = ci[c];
-            double U, L;
-            pair_bounds(a, (double)v, ni, di, rho, j, U, L);
-            keep = L <= V;
+            double d2, eps, dj;
+            pair_terms(a, (double)v, ni, rho, j, d2, eps, dj);
+            const double w = Vg + dj;
+            keep = d2 - eps <= w * w;
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
@@ -508,7 +515,7 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
     }
     if (lane == 0) {
         // sweep test for the columns still to come (sufficient form, see the header comment)
-        const double Vp = V / (1.0 - a.g_ref) + di;
+        const double Vp = Vg;
         const double kappa = 2.0 * a.c_acc * sqrt(ni) + 2.0 * rho * Vp;
         const double theta = Vp * Vp * (1.0 + 1e-9) - ni * (1.0 - a.c_rnd);
         a.cand_cnt[r] = kept;
@@ -736,8 +743,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
 
     const uint32_t row_blocks = (rows + kTileRows - 1) / kTileRows;
-    // geometric column schedule: first at least max(8, 4k/128) tiles, then x4 each step
-    uint32_t done = 0, step = std::max<uint32_t>(8, (4 * k + kTileCols - 1) / kTileCols);
+    // geometric column schedule: first at least 4k columns, then x4 each step
+    uint32_t done = 0, step = std::max<uint32_t>(4, (4 * k + kTileCols - 1) / kTileCols);
     while (done < n_tiles) {
         const uint32_t cnt = std::min(step, n_tiles - done);
         sa.tiles = tiles + done;
