@@ -325,7 +325,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
         // and + 128) and the 32 columns [32 (e >> 2), +32) of both accumulators.  With four warps per
         // scheduler the TMEM / L1 latencies of one warp hide behind the compares of the others. =====
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
-        uint32_t rloc[2], rtid[2];
+        uint32_t rloc[2];
         float thr[2], kap[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -334,7 +334,6 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
             const bool live = row < a.row_end;
             thr[h] = live ? a.thr[row - a.row_begin] : -__int_as_float(0x7f800000);
             kap[h] = live ? a.kap[row - a.row_begin] : 0.0f;
-            rtid[h] = live ? a.tid[row] : 0xffffffffu;
         }
         uint32_t as = 0, aph = 0;
         for (uint32_t it = 0; it < a.n_tiles; ++it) {
@@ -373,7 +372,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
                     const bool pass = v <= rhs;
                     if (__any_sync(0xffffffffu, pass)) {
                         const uint32_t j = j0 + c;
-                        if (pass && j < a.T && a.tid[j] != rtid[h]) {
+                        if (pass && j < a.T) {  // (same-contig pairs are dropped by the compaction)
                             const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
                             if (slot < kCandCap) {  // beyond: overflow, the row falls back
                                 cv[slot] = v;
@@ -419,6 +418,7 @@ struct CompactArgs {
     uint32_t *overflow;      // [rows] sticky flag
     const float *nrm, *delta;  // indexed by absolute row
     const float *maxes;      // [0] rho
+    const uint32_t *tid;     // contig ids: same-contig pairs (incl. the row itself) are not candidates
     uint32_t rows, row_begin, k;
     double c_acc, c_rnd, g_ref;
 };
@@ -450,25 +450,33 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         }
         return;
     }
-    if (n < a.k || a.overflow[r]) return;  // not enough candidates for a bound yet
+    if (a.overflow[r]) return;
     if (n <= n_min || n > 32u * KPER) return;  // the other launch's rows
     float *cv = a.cand_val + (size_t)r * kCandCap;
     uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
     const uint32_t row = a.row_begin + r;
     const double ni = (double)a.nrm[row], di = (double)a.delta[row], rho = (double)a.maxes[0];
+    const uint32_t ti = a.tid[row];
     constexpr uint32_t kPer = KPER;
-    uint32_t key[kPer];  // upper bounds U_ij (f32, rounded up) as ordered keys
+    uint32_t key[kPer];  // upper bounds U_ij (f32, rounded up) as ordered keys; all ones = not a candidate
+    uint32_t n_valid = 0;
 #pragma unroll
     for (uint32_t e = 0; e < kPer; ++e) {
         const uint32_t c = e * 32 + lane;
         key[e] = 0xFFFFFFFFu;
         if (c < n) {
-            double d2, eps, dj;
-            pair_terms(a, (double)cv[c], ni, rho, ci[c], d2, eps, dj);
-            const double U = (1.0 + a.g_ref) * (sqrt(fmax(d2 + eps, 0.0)) + di + dj);
-            key[e] = f32_key(__double2float_ru(U));
+            const uint32_t j = ci[c];
+            if (a.tid[j] != ti) {
+                double d2, eps, dj;
+                pair_terms(a, (double)cv[c], ni, rho, j, d2, eps, dj);
+                const double U = (1.0 + a.g_ref) * (sqrt(fmax(d2 + eps, 0.0)) + di + dj);
+                key[e] = f32_key(__double2float_ru(U));
+                n_valid += 1;
+            }
         }
     }
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    const bool have_bound = n_valid >= a.k;  // otherwise: only drop the same-contig entries
     // bit-descent select of the k-th smallest key.  U >= 0, so bit 31 of every key is set; the
     // lowest 6 bits are not resolved but set, which only rounds V up (by < 2^-17 relative): any
     // upper bound of the k-th smallest U is a valid V.
@@ -486,7 +494,8 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         }
     }
     prefix |= 63u;
-    const double V = (double)key_f32(prefix);  // >= the final k-th reference distance of this row
+    // >= the final k-th reference distance of this row (+inf while fewer than k candidates exist)
+    const double V = have_bound ? (double)key_f32(prefix) : (double)__int_as_float(0x7f800000);
     const double Vg = V / (1.0 - a.g_ref) + di;
     // keep exactly the pairs that can still be among the top k
     uint32_t kept = 0;
@@ -498,10 +507,12 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         if (c < n) {
             v = cv[c];
             j = ci[c];
-            double d2, eps, dj;
-            pair_terms(a, (double)v, ni, rho, j, d2, eps, dj);
-            const double w = Vg + dj;
-            keep = d2 - eps <= w * w;
+            if (a.tid[j] != ti) {
+                double d2, eps, dj;
+                pair_terms(a, (double)v, ni, rho, j, d2, eps, dj);
+                const double w = Vg + dj;
+                keep = !have_bound || d2 - eps <= w * w;
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
@@ -519,8 +530,10 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         const double kappa = 2.0 * a.c_acc * sqrt(ni) + 2.0 * rho * Vp;
         const double theta = Vp * Vp * (1.0 + 1e-9) - ni * (1.0 - a.c_rnd);
         a.cand_cnt[r] = kept;
-        a.thr[r] = __double2float_ru(theta);
-        a.kap[r] = __double2float_ru(kappa * (1.0 + 1e-6));
+        if (have_bound) {
+            a.thr[r] = __double2float_ru(theta);
+            a.kap[r] = __double2float_ru(kappa * (1.0 + 1e-6));
+        }
     }
 }
 
@@ -735,6 +748,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.nrm = nrm;
     ca.delta = delta;
     ca.maxes = scal + 1;
+    ca.tid = dtid;
     ca.rows = rows;
     ca.row_begin = row_begin;
     ca.k = k;
