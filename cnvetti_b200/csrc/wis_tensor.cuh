@@ -364,19 +364,36 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
                 const uint32_t row = row0 + rloc[h];
                 float *cv = a.cand_val + (size_t)(row - a.row_begin) * kCandCap;
                 uint32_t *ci = a.cand_idx + (size_t)(row - a.row_begin) * kCandCap;
-                // Survivors are rare (a few per 1024 pairs): one vote per column keeps the branch
-                // warp-uniform, so the append code runs only for columns where some row passes.
+                // Survivors are rare (a few per 1024 pairs).  All 32 compares are independent; groups of
+                // four columns fold into one predicate each, the eight group bits of all lanes are
+                // OR-reduced with one REDUX, and the append code runs (warp-uniformly) only for groups in
+                // which some row passes.
+                uint32_t gmask = 0u;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
-                    const bool pass = v <= rhs;
-                    if (__any_sync(0xffffffffu, pass)) {
-                        const uint32_t j = j0 + c;
-                        if (pass && j < a.T) {  // (same-contig pairs are dropped by the compaction)
-                            const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
-                            if (slot < kCandCap) {  // beyond: overflow, the row falls back
-                                cv[slot] = v;
-                                ci[slot] = j;
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    const bool p = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj[4 * g4 + 0]) <= rhs ||
+                                   fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj[4 * g4 + 1]) <= rhs ||
+                                   fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj[4 * g4 + 2]) <= rhs ||
+                                   fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj[4 * g4 + 3]) <= rhs;
+                    gmask |= p ? (1u << g4) : 0u;
+                }
+                const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+                if (wmask) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        if (wmask & (1u << g4)) {
+#pragma unroll
+                            for (int e4 = 0; e4 < 4; ++e4) {
+                                const int c = 4 * g4 + e4;
+                                const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                                const uint32_t j = j0 + c;
+                                if (v <= rhs && j < a.T) {  // (same-contig pairs are dropped by the compaction)
+                                    const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
+                                    if (slot < kCandCap) {  // beyond: overflow, the row falls back
+                                        cv[slot] = v;
+                                        ci[slot] = j;
+                                    }
+                                }
                             }
                         }
                     }
