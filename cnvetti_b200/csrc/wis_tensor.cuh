@@ -452,7 +452,7 @@ __device__ __forceinline__ void pair_terms(const CompactArgs &a, double v, doubl
 }
 
 // KPER = candidates per lane held in registers; rows with more than n_min candidates only (two
-// launches, KPER 16 and 64, so that the common short lists do not pay for the longest one)
+// launches by list length, KPER 16 / 32 / 64, so that short lists do not pay for the longest one)
 template <uint32_t KPER>
 __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_t n_min) {
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
@@ -788,7 +788,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         {
             KernelSpan span(ctx, "wis_compact_kernel");
             wis_compact_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(ca, 0u);
-            wis_compact_kernel<kCandCap / 32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 512u);
+            wis_compact_kernel<32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 512u);
+            wis_compact_kernel<kCandCap / 32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 1024u);
         }
         CNVB_LAUNCHED(ctx, "wis_compact_kernel");
         done += cnt;
