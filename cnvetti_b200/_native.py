@@ -36,6 +36,10 @@ class WisOpts(C.Structure):
                 ("max_samples_reliable", C.c_uint32), ("engine", C.c_uint32)]
 
 
+class HmmOpts(C.Structure):
+    _fields_ = [("sigma0", C.c_double), ("eps_cn", C.c_double), ("p_move", C.c_double)]
+
+
 # every symbol include/cnvetti_b200.h declares: name -> (restype, argtypes)
 _vp, _u64, _u32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 SYMBOLS = {
@@ -74,6 +78,7 @@ SYMBOLS = {
     "cnvb_wis_filters": (_int, [_vp, _vp, _vp, _u32, C.POINTER(WisOpts), _vp, _int]),
     "cnvb_wis_build": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _vp, _vp, _vp, _vp, _vp,
                               C.POINTER(C.c_float), _int]),
+    "cnvb_hmm_segment": (_int, [_vp, _vp, _vp, _u32, _vp, C.POINTER(HmmOpts), _vp, _vp, _int]),
     "cnvb_modcov": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
 }
 

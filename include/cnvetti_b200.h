@@ -237,6 +237,25 @@ int cnvb_modcov(cnvb_ctx *ctx, const float *cv, uint32_t T, const uint8_t *model
                 const uint32_t *ref_idx, const uint32_t *ref_len, uint32_t k, float *ref_mean,
                 float *ref_sd, float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem);
 
+/* ---- lib-discover (builder-defined: the reference has no implementation, only the CLI stub
+ * cnvetti/src/cli.yaml:457-469 and `bail!("cmd discover not implemented!")`,
+ * cnvetti/src/main.rs:135; spec in DESIGN.md "HMM") ------------------------------------------- */
+#define CNVB_HMM_STATES 5 /* copy number 0..4 */
+typedef struct {
+    double sigma0;  /* additive emission SD               (default 0.02) */
+    double eps_cn;  /* copy number used for state CN0     (default 0.1)  */
+    double p_move;  /* probability of each state change   (default 1e-4) */
+} cnvb_hmm_opts;
+/* Segmentation of `n_lanes` independent lanes (one per sample and contig).  cv holds the lanes'
+ * FORMAT/CV values back to back, lane l = cv[lane_off[l] .. lane_off[l+1]); sigma_s[l] is the
+ * lane's noise scale (1.4826 * MAD of CV).  Non-finite CV (missing) emits log-likelihood 0 in
+ * every state.  state[i] = Viterbi copy-number state (log-space f64, strictly sequential
+ * recurrence, ties -> lowest state); posterior (nullable) = [total bins][5] forward-backward
+ * posteriors.  lane_off and sigma_s are host arrays; cv/state/posterior follow `mem`. */
+int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *lane_off, uint32_t n_lanes,
+                     const double *sigma_s, const cnvb_hmm_opts *opts, uint8_t *state, double *posterior,
+                     int mem);
+
 #ifdef __cplusplus
 }
 #endif

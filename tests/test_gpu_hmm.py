@@ -1,0 +1,70 @@
+"""Parity of the CUDA HMM segmentation against the repo's CPU oracle (builder-defined spec: the
+reference has no `cmd discover`).  State paths bit-exact; posteriors within rel 1e-6."""
+import numpy as np
+import pytest
+
+import cnvetti_b200 as cb
+from cnvetti_b200 import discover, synth
+from util import to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return cb.Context(0)
+
+
+def _lanes(seed, lengths):
+    cvs, cns = [], []
+    for i, n in enumerate(lengths):
+        cv, cn = synth.synth_cv_lanes(seed * 100 + i, n, n_cnv=max(1, n // 500), missing_frac=0.002)
+        cvs.append(cv)
+        cns.append(cn)
+    off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    return np.concatenate(cvs) if cvs else np.zeros(0, np.float32), np.concatenate(cns) if cns else np.zeros(0), off
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_viterbi_paths_bit_exact(oracle, ctx, device):
+    lengths = [5000, 1, 0, 77, 12345, 3000, 2, 40000] + [900] * 40
+    cv, cn, off = _lanes(4, lengths)
+    rng = np.random.default_rng(0)
+    sig = rng.uniform(0.05, 0.15, len(lengths))
+    opts = discover.DiscoverOptions()
+    x = cv
+    if device:
+        import torch
+        x = torch.from_numpy(cv).cuda()
+    st = to_np(discover.hmm_segment(x, off, sig, opts, ctx=ctx))
+    for l, n in enumerate(lengths):
+        t = oracle.hmm_tables(float(sig[l]), opts.sigma0, opts.eps_cn, opts.p_move)
+        ref = oracle.hmm_viterbi(cv[int(off[l]):int(off[l + 1])], t)
+        assert np.array_equal(st[int(off[l]):int(off[l + 1])], ref), l
+    # the planted CNVs are found (sanity of the model, not parity)
+    l = 4
+    seg = st[int(off[l]):int(off[l + 1])]
+    truth = cn[int(off[l]):int(off[l + 1])]
+    assert (seg == truth).mean() > 0.97
+    segs = discover.segments_from_states(st, off)
+    assert len(segs) > 10 and all(s[3] != 2 for s in segs)
+
+
+def test_posteriors_within_tolerance(oracle, ctx):
+    lengths = [3000, 500, 8000]
+    cv, _, off = _lanes(5, lengths)
+    sig = np.array([0.08, 0.1, 0.12])
+    opts = discover.DiscoverOptions(p_move=1e-3)
+    st, post = discover.hmm_segment(cv, off, sig, opts, posterior=True, ctx=ctx)
+    for l in range(len(lengths)):
+        t = oracle.hmm_tables(float(sig[l]), opts.sigma0, opts.eps_cn, opts.p_move)
+        sl = slice(int(off[l]), int(off[l + 1]))
+        ref = oracle.hmm_posterior(cv[sl], t)
+        np.testing.assert_allclose(post[sl], ref, rtol=1e-6, atol=1e-300)   # north_star: rel 1e-6 in f64
+        assert np.array_equal(st[sl], oracle.hmm_viterbi(cv[sl], t))
+    np.testing.assert_allclose(post.sum(axis=1), 1.0, rtol=1e-12)
+
+
+def test_hmm_argument_errors(ctx):
+    with pytest.raises(cb.CnvbError):
+        discover.hmm_segment(np.zeros(4, np.float32), [0, 4], [0.1], discover.DiscoverOptions(p_move=0.5), ctx=ctx)
