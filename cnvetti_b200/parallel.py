@@ -1,0 +1,144 @@
+"""Multi-GPU drivers: one process per GPU, `torch.distributed` (NCCL over NVLink on the GPU box,
+gloo in CPU tests) for the plumbing.  SURVEY.md section 8(e):
+
+  * coverage / refstats / HMM shard by region (contig) or lane with NO data-path collective;
+    only the finished per-window columns are gathered (`gather_columns`);
+  * WIS shards by target-row block: all-gather of the panel, local distances for the rank's
+    rows, all-gather of one f32 per target (the nearest distance) for the global prune
+    threshold, then local prune / per-probe calls / filters.
+
+The compute backend is injectable so that the host logic (partitioning, collectives, result
+assembly) can be exercised with gloo on a CPU-only box; the default backend is the CUDA one and
+there is no CPU fallback in the product.
+"""
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def shard_rows(n, rank, world):
+    """Contiguous, balanced row block [lo, hi) of rank `rank`."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_by_weight(weights, world):
+    """Longest-processing-time assignment of work items (contigs, lanes) to ranks.
+    Returns a list of index lists, one per rank; deterministic."""
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    loads = [0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda q: (loads[q], q))
+        out[r].append(i)
+        loads[r] += weights[i]
+    for lst in out:
+        lst.sort()
+    return out
+
+
+def _world(group=None):
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def all_gather_rows(block, group=None):
+    """All-gather row blocks of possibly different lengths along dim 0 (sizes are exchanged
+    first; NCCL needs equal shapes, so blocks are padded to the longest)."""
+    rank, world = _world(group)
+    if world == 1:
+        return block
+    n = torch.tensor([block.shape[0]], dtype=torch.int64, device=block.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pad = torch.zeros((m,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+    pad[:block.shape[0]] = block
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+class CudaWisBackend:
+    """The product backend: cnvetti_b200.model_wis on the rank's GPU."""
+
+    def __init__(self, ctx=None):
+        from . import model_wis
+        self.mw = model_wis
+        self.ctx = ctx
+
+    def distances(self, X, tids, options, lo, hi):
+        return self.mw.compute_distances(X, tids, options, row_begin=lo, row_end=hi, ctx=self.ctx)
+
+    def threshold(self, nearest, z):
+        return self.mw.prune_threshold(nearest, z, ctx=self.ctx)
+
+    def prune(self, dist_, idx, thr):
+        return self.mw.prune_distances(dist_, idx, thr, ctx=self.ctx)
+
+    def calls(self, X, ref_idx, ref_len, options, lo, hi):
+        return self.mw.count_per_probe_calls(X, ref_idx, ref_len, options, row_begin=lo, row_end=hi, ctx=self.ctx)
+
+    def filters(self, ref_len, calls, options):
+        return self.mw.model_filters(ref_len, calls, options, ctx=self.ctx)
+
+
+def wis_run_distributed(X_block, tids_block, options, backend=None, group=None):
+    """`build-model-wis` with targets sharded by row block.
+
+    Every rank passes ITS rows of the panel (`X_block[rows_r][S]`, `tids_block[rows_r]`, row
+    blocks in rank order = target order).  Returns the model of the rank's rows as a dict
+    (ref_dist, ref_idx, ref_len, num_calls, filt, threshold, rows=(lo, hi)); ref_idx are global
+    target indices."""
+    rank, world = _world(group)
+    backend = backend or CudaWisBackend()
+    X = all_gather_rows(X_block, group)            # panel: 80 MB (cfg 3) / 12 GB (cfg 5) over NVLink
+    tids = all_gather_rows(tids_block, group)
+    sizes = torch.tensor([X_block.shape[0]], dtype=torch.int64, device=X_block.device)
+    if world > 1:
+        allsz = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes, group=group)
+        lo = int(sum(int(s.item()) for s in allsz[:rank]))
+    else:
+        lo = 0
+    hi = lo + int(X_block.shape[0])
+    dist_, idx = backend.distances(X, tids, options, lo, hi)
+    nearest_local = dist_[:, 0].contiguous() if hasattr(dist_, "contiguous") else np.ascontiguousarray(dist_[:, 0])
+    if world > 1:
+        nearest_t = nearest_local if torch.is_tensor(nearest_local) else torch.from_numpy(nearest_local)
+        nearest_t = nearest_t.to(X_block.device)
+        nearest = all_gather_rows(nearest_t, group)  # one f32 per target
+    else:
+        nearest = nearest_local
+    thr = backend.threshold(nearest, options.filter_z_score)   # identical on every rank
+    ref_idx, ref_len = backend.prune(dist_, idx, thr)
+    calls = backend.calls(X, ref_idx, ref_len, options, lo, hi)
+    filt = backend.filters(ref_len, calls, options)
+    return dict(ref_dist=dist_, ref_idx=ref_idx, ref_len=ref_len, num_calls=calls, filt=filt,
+                threshold=thr, rows=(lo, hi))
+
+
+def gather_columns(local_columns, owner_of_region, region_sizes, dtype, device, group=None):
+    """Assemble per-window columns computed region-by-region on different ranks into the
+    genome-order table on every rank.  `local_columns`: {region index: 1-D tensor} for the
+    regions this rank owns.  No arithmetic, only broadcasts and a concatenation."""
+    rank, world = _world(group)
+    out = []
+    for r, n in enumerate(region_sizes):
+        owner = owner_of_region[r]
+        if owner == rank or world == 1:
+            t = local_columns[r].contiguous()
+        else:
+            t = torch.empty(n, dtype=dtype, device=device)
+        if world > 1:
+            dist.broadcast(t, src=owner, group=group)
+        out.append(t)
+    return torch.cat(out) if out else torch.empty(0, dtype=dtype, device=device)
