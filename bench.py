@@ -112,12 +112,14 @@ def measured_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def ncu_traffic(n_reads, launches_per_step):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/roofline_traffic.json holds dram bytes per read of the captured launch)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p):
+    if os.path.exists(p) and launches_per_step:
         try:
-            return json.load(open(p)).get("frag_bin_gw_kernel")
+            per_read = float(json.load(open(p))["frag_bin_gw_kernel"]["dram_bytes_per_read"])
+            return per_read * n_reads / launches_per_step
         except Exception:
             return None
     return None
@@ -445,8 +447,10 @@ def main():
     gw = kern["frag_bin_gw_kernel"]
     achieved = BYTES_PER_READ_GW * n_reads / (gw["ms_per_step"] * 1e-3) / 1e9 if gw["ms_per_step"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "frag_bin_gw_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(n_reads, gw["launches_per_step"]), "peak_source": peak_src,
                 "algorithmic_bytes_per_read": BYTES_PER_READ_GW,
+                "algorithmic_bytes_per_launch": BYTES_PER_READ_GW * n_reads / max(1.0, gw["launches_per_step"]),
                 "kernel_share_of_step": gw["ms_per_step"] / ms}
     rs = kern["refstats_lut_kernel"]
     total_bp = sum(L for _, L in regs)
