@@ -37,6 +37,11 @@ READS_PER_BP = 900e6 / 2_875_001_522      # ~900 M reads over chr1-22
 BYTES_PER_READ_GW = 7                     # mid i32 + mapq u8 + flags u16
 
 
+HMM_KERNELS = ("hmm_viterbi_kernel", "hmm_chunk_matrix_kernel", "hmm_chunk_path_kernel", "hmm_boundary_kernel",
+               "hmm_backtrack_kernel", "hmm_states_kernel")
+HMM_BYTES_PER_BIN = 5  # 4 B CV read + 1 B state written
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -45,10 +50,11 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only (profiling runs)")
-    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis"],
+    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm"],
                     help="coverage = BASELINE configs[1] (default, the headline); wis = configs[2]")
     ap.add_argument("--targets", type=int, default=200_000, help="wis: number of targets T")
     ap.add_argument("--samples", type=int, default=100, help="wis: number of samples S")
+    ap.add_argument("--hmm-samples", type=int, default=100, help="hmm: number of samples (22 lanes each)")
     ap.add_argument("--cpu-rows", type=int, default=2000, help="wis: rows of the CPU baseline sample")
     ap.add_argument("--cpu-sample-contigs", type=int, default=4, help="last k contigs form the CPU sample")
     return ap.parse_args()
@@ -257,8 +263,128 @@ def bench_wis(args):
     return 0
 
 
+def bench_hmm(args):
+    """BASELINE configs[3]: `cmd discover` on 100 samples x ~2.9 M bins (22 autosomes, 1 kbp windows):
+    one lane per (sample, contig).  One step = Viterbi segmentation of all lanes (state per bin)."""
+    import torch
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import discover
+    from cnvetti_b200.synth import HG38_AUTOSOMES
+    n_samples = args.hmm_samples
+    dev = "cuda:0"
+    ctx = cb.Context(0)
+    lens = [(L + 999) // 1000 for _, L in HG38_AUTOSOMES]
+    lane_len = np.array(lens * n_samples, np.int64)
+    lane_off = np.concatenate([[0], np.cumsum(lane_len)]).astype(np.uint64)
+    n_bins = int(lane_off[-1])
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    cn = torch.full((n_bins,), 2.0, device=dev)
+    # planted segments: ~20 per lane, 5..500 bins, cn in {0,1,3,4}
+    nseg = 20 * len(lane_len)
+    seg_start = (torch.rand(nseg, generator=g, device=dev) * (n_bins - 600)).long()
+    seg_len = (torch.rand(nseg, generator=g, device=dev) * 495).long() + 5
+    seg_cn = torch.tensor([0.0, 1.0, 3.0, 4.0], device=dev)[(torch.rand(nseg, generator=g, device=dev) * 4).long().clamp_(0, 3)]
+    delta = torch.zeros(n_bins + 1, device=dev)
+    delta.index_add_(0, seg_start, seg_cn - 2.0)
+    delta.index_add_(0, seg_start + seg_len, -(seg_cn - 2.0))
+    cn = (cn + torch.cumsum(delta[:-1], 0)).clamp_(0.0, 4.0).round_()
+    mu = cn / 2.0
+    cv = (mu + torch.randn(n_bins, generator=g, device=dev) * (0.08 * mu.sqrt() + 0.02)).float().contiguous()
+    del delta, cn, mu
+    sigma = np.full(len(lane_len), 0.08)
+    opts = discover.DiscoverOptions()
+    workload = "cfg4: cmd discover (5-state HMM Viterbi), %d samples x %d bins = %d lanes" % (
+        n_samples, n_bins // n_samples, len(lane_len))
+
+    def step():
+        return discover.hmm_segment(cv, lane_off, sigma, opts, ctx=ctx)
+
+    st = step()
+    torch.cuda.synchronize()
+    frac_cn2 = float((st == 2).float().mean().item())
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    sampler = ClockSampler(0)
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count - l0
+    kern = {}
+    for kname in HMM_KERNELS:
+        kms, cnt = ctx.timing_query(kname)
+        if cnt:
+            kern[kname] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps}
+    ctx.set_timing(False)
+    ctx.timing_reset()
+    # e2e: pinned host CV in, states out
+    hcv = torch.empty(n_bins, dtype=torch.float32, pin_memory=True)
+    hcv.copy_(cv)
+    hst = torch.empty(n_bins, dtype=torch.uint8, pin_memory=True)
+
+    def step_e2e():
+        s_ = discover.hmm_segment(hcv.to(dev, non_blocking=True), lane_off, sigma, opts, ctx=ctx)
+        hst.copy_(s_, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    esteps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        step_e2e()
+    e2e_s = (time.perf_counter() - t0) / esteps
+    peak, peak_src = measured_peak()
+    dom = max(kern, key=lambda k_: kern[k_]["ms_per_step"]) if kern else None
+    dom_ms = kern[dom]["ms_per_step"] if dom else 0.0
+    achieved = HMM_BYTES_PER_BIN * n_bins / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    cpu = None
+    if not args.quick:
+        import oracle
+        from concurrent.futures import ThreadPoolExecutor
+        oracle.build()
+        ncpu = os.cpu_count() or 1
+        nl = min(len(lens), 22)
+        host = cv[:int(lane_off[nl])].cpu().numpy()
+        tab = oracle.hmm_tables(0.08, opts.sigma0, opts.eps_cn, opts.p_move)
+        lanes = [host[int(lane_off[i]):int(lane_off[i + 1])] for i in range(nl)]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(ncpu) as ex:
+            list(ex.map(lambda x: oracle.hmm_viterbi(x, tab), lanes))
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": host.size / dt_cpu, "unit": "bins/s", "cores": min(ncpu, nl), "kind": "port",
+               "sample": "one sample (22 lanes, %d bins), oracle Viterbi, one lane per thread" % host.size}
+    line = {"metric": "HMM bins/s", "value": n_bins / (ms * 1e-3), "unit": "bins/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fixed-point i32 scores from f64 emissions", "data": "synthetic",
+            "config": {"workload": workload, "samples": n_samples, "bins": n_bins, "lanes": len(lane_len),
+                       "frac_cn2": frac_cn2,
+                       "l2": "CV %.1f GB/step exceeds L2" % (n_bins * 4 / 1e9)},
+            "e2e": {"value": n_bins / e2e_s, "unit": "bins/s", "h2d_bytes_per_step": n_bins * 4,
+                    "d2h_bytes_per_step": n_bins, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_bin": HMM_BYTES_PER_BIN,
+                         "kernel_share_of_step": dom_ms / ms if ms else None},
+            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload == "hmm" and args.impl == "b200":
+        return bench_hmm(args)
     if args.workload == "wis" and args.impl == "b200":
         return bench_wis(args)
     import torch
@@ -343,8 +469,10 @@ def main():
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t_gen
 
+    prep_dev = pipeline.PreparedRegions(dev_regions, opts)
+
     def step_device():
-        t = pipeline.coverage_run(dev_regions, opts, ctx=ctx)
+        t = pipeline.coverage_run(prep_dev, opts, ctx=ctx)
         return pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx)
 
     def barrier():
@@ -417,8 +545,10 @@ def main():
                                  ("gap", torch.uint8))}
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
+    prep_host = pipeline.PreparedRegions(host_regions, opts)
+
     def step_e2e():
-        tt = pipeline.coverage_run(host_regions, opts, ctx=ctx)
+        tt = pipeline.coverage_run(prep_host, opts, ctx=ctx)
         pipeline.normalize_run(tt, "MedianGcBinned", ctx=ctx)
         for kcol, h in out_host.items():
             h.copy_(getattr(tt, kcol), non_blocking=True)

@@ -30,6 +30,18 @@ class CovOpts(C.Structure):
                 ("min_raw_coverage", C.c_uint32), ("plp_flag_mask", C.c_uint32)]
 
 
+class Region(C.Structure):
+    _fields_ = [("region_end", C.c_uint32), ("reads", ReadSoa), ("seq", C.c_void_p),
+                ("seq_len", C.c_uint64), ("seq_mem", C.c_int),
+                ("tgt_start", C.c_void_p), ("tgt_end", C.c_void_p), ("n_tgt", C.c_uint32),
+                ("pile_start", C.c_void_p), ("pile_end", C.c_void_p), ("n_pile", C.c_uint32)]
+
+
+class CovColumns(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("start", "end", "rcv", "rcvsd", "lcv", "lcvsd", "frm", "gc",
+                                          "mean_mapq", "gap", "ft")]
+
+
 class WisOpts(C.Structure):
     _fields_ = [("filter_z_score", C.c_double), ("filter_rel", C.c_double),
                 ("min_ref_targets", C.c_uint32), ("max_ref_targets", C.c_uint32),
@@ -68,6 +80,9 @@ SYMBOLS = {
     "cnvb_refstats": (_int, [_vp, _vp, _u64, _u32, _vp, _vp, _int]),
     "cnvb_cov_records": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp, _int, C.POINTER(CovOpts),
                                 _vp, _vp, _vp, _int]),
+    "cnvb_coverage_rows": (_u64, [C.POINTER(CovOpts), _int, C.POINTER(Region), _u32]),
+    "cnvb_coverage_run": (_int, [_vp, C.POINTER(CovOpts), _int, C.POINTER(Region), _u32,
+                                 C.POINTER(CovColumns), _vp, _vp, _int]),
     "cnvb_norm_total": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _int]),
     "cnvb_norm_gc_median": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _int]),
     "cnvb_wis_distances": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _u32, _u32, _vp, _vp, _int]),

@@ -9,8 +9,10 @@ from typing import List, Optional
 
 import numpy as np
 
+import ctypes as C
+
 from . import _native as N
-from .context import default_context
+from .context import buf, default_context
 from .coverage import AggregationStats, ReferenceStats, cov_records, make_aggregator
 from .normalize import run_binned_correction, run_uncorrected_normalization
 
@@ -58,55 +60,86 @@ def _num_regions(options, r):
     return (r.length + wl - 1) // wl
 
 
+_KIND = {("Fragments", "GenomeWide"): N.FRAGMENTS_GENOME_WIDE,
+         ("Fragments", "TargetRegions"): N.FRAGMENTS_TARGET_REGIONS,
+         ("Coverage", "GenomeWide"): N.COVERAGE}
+
+
+class PreparedRegions:
+    """The regions of one run as the C array `cnvb_coverage_run` takes (built once, reusable while
+    the underlying buffers stay alive and in place)."""
+
+    def __init__(self, regions, options):
+        key = (options.count_kind, options.considered_regions)
+        if key not in _KIND:
+            raise ValueError("Invalid combination of coverage/on-target regions")  # lib.rs:528
+        self.kind = _KIND[key]
+        self.regions = list(regions)
+        self.c_opts = options.c_opts()
+        self.keep = []
+        arr = (N.Region * max(1, len(self.regions)))()
+        for i, r in enumerate(self.regions):
+            c = arr[i]
+            c.region_end = int(r.length)
+            soa, keep = r.reads.c_soa()
+            c.reads = soa
+            self.keep.append(keep)
+            if r.sequence is not None and options.window_length and self.kind != N.FRAGMENTS_TARGET_REGIONS:
+                p, mem, k = buf(r.sequence, np.uint8)
+                c.seq, c.seq_len, c.seq_mem = p, int(k.shape[0]), mem
+                self.keep.append(k)
+            if r.targets is not None and self.kind == N.FRAGMENTS_TARGET_REGIONS:
+                ts = np.ascontiguousarray(r.targets[0], np.uint32)
+                te = np.ascontiguousarray(r.targets[1], np.uint32)
+                c.tgt_start, c.tgt_end, c.n_tgt = ts.ctypes.data, te.ctypes.data, ts.size
+                self.keep += [ts, te]
+            if r.piles is not None and self.kind == N.FRAGMENTS_GENOME_WIDE:
+                ps = np.ascontiguousarray(r.piles[0], np.uint32)
+                pe = np.ascontiguousarray(r.piles[1], np.uint32)
+                c.pile_start, c.pile_end, c.n_pile = ps.ctypes.data, pe.ctypes.data, ps.size
+                self.keep += [ps, pe]
+        self.array = arr
+        self.n = len(self.regions)
+        self.have_ref = any(arr[i].seq for i in range(self.n))
+        self.counts = [int(N.lib().cnvb_coverage_rows(C.byref(self.c_opts), self.kind,
+                                                      C.cast(C.byref(arr[i]), C.POINTER(N.Region)), 1))
+                       for i in range(self.n)]
+        self.offsets = np.concatenate([[0], np.cumsum(self.counts)]).astype(np.int64).tolist()
+        self.names = [r.name for r in self.regions]
+
+
 def coverage_run(regions, options, ctx=None, device=True):
-    """`cnvetti cmd coverage` on in-memory inputs: one aggregator per region, in order."""
+    """`cnvetti cmd coverage` on in-memory inputs: the region loop of lib_coverage::run
+    (lib.rs:768-781) as one native call (cnvb_coverage_run); columns stay in HBM."""
     import torch
     ctx = ctx or default_context()
+    prep = regions if isinstance(regions, PreparedRegions) else PreparedRegions(regions, options)
     dev = "cuda:%d" % ctx.device
-    counts = [_num_regions(options, r) for r in regions]
-    total = int(sum(counts))
+    total = prep.offsets[-1]
     t = CoverageTable()
-    t.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64).tolist()
-    t.names = [r.name for r in regions]
+    t.offsets = prep.offsets
+    t.names = prep.names
+    is_cov = prep.kind == N.COVERAGE
+    is_gw = prep.kind == N.FRAGMENTS_GENOME_WIDE
     f32 = lambda: torch.empty(total, dtype=torch.float32, device=dev)
+    u8 = lambda: torch.empty(total, dtype=torch.uint8, device=dev)
     i32 = lambda: torch.empty(total, dtype=torch.int32, device=dev)
-    t.start, t.end, t.rcv, t.lcv = i32(), i32(), f32(), f32()
-    t.ft = torch.empty(total, dtype=torch.uint8, device=dev)
-    is_cov = options.count_kind == "Coverage"
-    is_tgt = options.considered_regions == "TargetRegions"
+    t.start, t.end, t.rcv, t.lcv, t.ft = i32(), i32(), f32(), f32(), u8()
     if is_cov:
         t.rcvsd, t.lcvsd = f32(), f32()
-    if not is_cov and not is_tgt:
+    if is_gw:
         t.frm = f32()
-    mq = f32()
-    have_ref = any(r.sequence is not None for r in regions) and options.window_length
-    if have_ref:
-        t.gc = f32()
-        t.gap = torch.empty(total, dtype=torch.uint8, device=dev)
-    aggs = []
-    for r, lo, hi in zip(regions, t.offsets[:-1], t.offsets[1:]):
-        sl = slice(lo, hi)
-        if have_ref and r.sequence is not None:  # lib.rs:440-454
-            seq = r.sequence
-            if not (hasattr(seq, "is_cuda") and seq.is_cuda):  # host bytes: one async H2D copy
-                seq = torch.as_tensor(seq).to(dev, non_blocking=True)
-            ReferenceStats.look_at_chars(seq, options.window_length, ctx=ctx, out=(t.gc[sl], t.gap[sl]))
-        agg = make_aggregator(options, r.length, targets=r.targets, piles=r.piles, ctx=ctx)  # lib.rs:510-529
-        agg.put_fetched_records(r.reads)                                                    # lib.rs:547
-        out = AggregationStats(t.rcv[sl], t.rcvsd[sl] if is_cov else None, t.start[sl], t.end[sl],
-                               t.frm[sl] if t.frm is not None else None, mq[sl])
-        agg.get_all_stats(device=True, out=out)                                             # lib.rs:560-561
-        aggs.append(agg)
-    # FORMAT assembly for all rows at once (lib.rs:623-668)
-    stats = AggregationStats(t.rcv, t.rcvsd, t.start, t.end, t.frm, mq)
-    lcv, lcvsd, ft = cov_records(stats, options, is_tgt, ctx=ctx)
-    t.lcv, t.lcvsd, t.ft = lcv, lcvsd, ft
-    # the single synchronisation point: tallies + reference-panic checks of every region
-    for agg in aggs:
-        agg.finish()
-        t.num_processed.append(agg.num_processed())
-        t.num_skipped.append(agg.num_skipped())
-        agg.close()
+    if prep.have_ref:
+        t.gc, t.gap = f32(), u8()
+    ptr = lambda x: x.data_ptr() if x is not None else None
+    cols = N.CovColumns(ptr(t.start), ptr(t.end), ptr(t.rcv), ptr(t.rcvsd), ptr(t.lcv), ptr(t.lcvsd),
+                        ptr(t.frm), ptr(t.gc), None, ptr(t.gap), ptr(t.ft))
+    nproc = np.zeros(max(1, prep.n), np.uint64)
+    nskip = np.zeros(max(1, prep.n), np.uint64)
+    ctx.check(N.lib().cnvb_coverage_run(ctx.handle, C.byref(prep.c_opts), prep.kind, prep.array, prep.n,
+                                        C.byref(cols), nproc.ctypes.data, nskip.ctypes.data, N.MEM_DEVICE))
+    t.num_processed = [int(x) for x in nproc[:prep.n]]
+    t.num_skipped = [int(x) for x in nskip[:prep.n]]
     return t
 
 

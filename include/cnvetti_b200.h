@@ -156,6 +156,41 @@ int cnvb_cov_records(cnvb_ctx *ctx, uint64_t n, const float *cov, const float *c
                      int is_targets, const cnvb_cov_opts *opts, float *lcv, float *lcvsd,
                      uint8_t *ft, int mem);
 
+/* ---- lib-coverage: the region loop --------------------------------------------------------- */
+/* One GenomeRegions entry (lib-shared/src/regions.rs:15-19) with its inputs. */
+typedef struct {
+    uint32_t region_end;       /* end of the region == the `contig_length` the aggregators get  */
+    cnvb_read_soa reads;       /* what fetch() yields for the region, coordinate order          */
+    const uint8_t *seq;        /* contig bytes for GC/GAP (lib.rs:440-454) or NULL              */
+    uint64_t seq_len;
+    int seq_mem;               /* CNVB_MEM_HOST | CNVB_MEM_DEVICE                               */
+    const uint32_t *tgt_start, *tgt_end; /* TARGET_REGIONS only (host)                          */
+    uint32_t n_tgt;
+    const uint32_t *pile_start, *pile_end; /* GENOME_WIDE only (host)                           */
+    uint32_t n_pile;
+} cnvb_region;
+
+/* One column per BCF tag `cmd coverage` writes, rows of all regions concatenated in region
+ * order; NULL = not wanted.  start/end/rcv/lcv are required.  rcvsd/lcvsd only for COVERAGE,
+ * frm only for GENOME_WIDE, gc/gap (together) only for windowed kinds. */
+typedef struct {
+    uint32_t *start, *end;
+    float *rcv, *rcvsd, *lcv, *lcvsd, *frm, *gc, *mean_mapq;
+    uint8_t *gap, *ft;
+} cnvb_cov_columns;
+
+/* number of table rows the regions produce (windows or targets) */
+uint64_t cnvb_coverage_rows(const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
+                            uint32_t n_regions);
+/* = the region loop of lib_coverage::run (lib-coverage/src/lib.rs:768-781) with process_region
+ * (:422-676) per region: refstats, aggregator, get_stats, FORMAT assembly -- enqueued back to
+ * back, one host wait at the end.  `mem` is where the columns live; num_processed/num_skipped
+ * (host, n_regions entries, may be NULL) receive the per-region tallies.  A region whose input
+ * makes the reference panic fails the call with CNVB_ERR_REFERENCE_PANIC ("region i caused by"). */
+int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
+                      uint32_t n_regions, const cnvb_cov_columns *out, uint64_t *num_processed,
+                      uint64_t *num_skipped, int mem);
+
 /* ---- lib-normalize ------------------------------------------------------------------------ */
 /* = run_uncorrected_normalization (lib-normalize/src/uncorrected.rs:20-96).  lcvsd/cvsd may be
  * NULL.  *lcv_sum (host, may be NULL) receives the f64 sum. */

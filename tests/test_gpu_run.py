@@ -1,0 +1,126 @@
+"""The native region loop (cnvb_coverage_run = lib_coverage::run's loop, lib.rs:768-781) against the
+oracle run region by region, plus the chained normaliser; host and device inputs, all three kinds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cnvetti_b200 as cb
+from cnvetti_b200 import _native as N
+from cnvetti_b200 import pipeline, synth
+from util import assert_f32_equal_bits, oracle_reads, simple_reads, soa_batch, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return cb.Context(0)
+
+
+def _regions(device, with_targets=False):
+    import torch
+    out, raw = [], []
+    for i, L in enumerate((700_123, 310_000, 50_000)):
+        d = synth.synth_bam_records(50 + i, L, 9_000 if L > 100_000 else 600)
+        seq = synth.synth_reference(60 + i, L)
+        tg = synth.synth_targets(70 + i, L, 40 if L > 100_000 else 5) if with_targets else None
+        s = torch.from_numpy(seq).to(device) if device else seq
+        out.append(pipeline.Region("chr%d" % (i + 1), L, soa_batch(d, device=device), s, targets=tg))
+        raw.append((d, seq, tg, L))
+    return out, raw
+
+
+@pytest.mark.parametrize("device", [None, "cuda"])
+def test_region_loop_fragments_gw(oracle, ctx, device):
+    wl = 500
+    regions, raw = _regions(device)
+    opts = cb.CoverageOptions(window_length=wl, min_mapq=10)
+    t = pipeline.coverage_run(regions, opts, ctx=ctx)
+    oopts = oracle.cov_opts(window_length=wl, min_mapq=10)
+    lcv_all, gc_all = [], []
+    for r, (d, seq, _, L), lo, hi in zip(regions, raw, t.offsets[:-1], t.offsets[1:]):
+        counts, proc, skip = oracle.frag_gw(oracle_reads(oracle, d), oopts, L)
+        cov, start, end, frm = oracle.frag_gw_stats(counts, oopts, L)
+        gc, gap = oracle.refstats(seq, wl)
+        lcv, _, ft = oracle.cov_records(cov, None, start, end, frm, False, oopts)
+        assert hi - lo == counts.size
+        assert_f32_equal_bits(t.rcv[lo:hi], cov, "rcv")
+        assert np.array_equal(to_np(t.start[lo:hi]), start) and np.array_equal(to_np(t.end[lo:hi]), end)
+        assert_f32_equal_bits(t.frm[lo:hi], frm, "frm")
+        assert_f32_equal_bits(t.gc[lo:hi], gc, "gc")
+        assert np.array_equal(to_np(t.gap[lo:hi]).astype(bool), gap.astype(bool))
+        assert_f32_equal_bits(t.lcv[lo:hi], lcv, "lcv")
+        assert np.array_equal(to_np(t.ft[lo:hi]), ft)
+        lcv_all.append(lcv)
+        gc_all.append(gc)
+    assert t.num_processed == [oracle.frag_gw(oracle_reads(oracle, d), oopts, L)[1] for d, _, _, L in raw]
+    pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx)
+    cv, cv2, _, flags, _ = oracle.norm_gc_median(np.concatenate(lcv_all), np.concatenate(gc_all))
+    assert np.array_equal(to_np(t.norm_flags), flags)
+    has = (flags & N.N2_CV).astype(bool)
+    assert has.sum() > 100
+    assert_f32_equal_bits(to_np(t.cv)[has], cv[has], "cv")
+
+
+def test_region_loop_targets_and_coverage(oracle, ctx):
+    regions, raw = _regions("cuda", with_targets=True)
+    opts = cb.CoverageOptions(window_length=None, considered_regions="TargetRegions", min_raw_coverage=3)
+    t = pipeline.coverage_run(regions, opts, ctx=ctx)
+    oopts = oracle.cov_opts(window_length=0, min_raw_coverage=3)
+    for (d, _, tg, L), lo, hi in zip(raw, t.offsets[:-1], t.offsets[1:]):
+        counts, proc, skip = oracle.frag_targets(oracle_reads(oracle, d), oopts, tg[0], tg[1])
+        assert np.array_equal(to_np(t.rcv[lo:hi]), counts.astype(np.float32))
+        assert np.array_equal(to_np(t.ft[lo:hi]) & 1, (counts < 3).astype(np.uint8))
+    assert t.gc is None and t.frm is None
+    # Coverage kind: mean/sd per window
+    opts = cb.CoverageOptions(window_length=1000, count_kind="Coverage")
+    t = pipeline.coverage_run(regions, opts, ctx=ctx)
+    for (d, _, _, L), lo, hi in zip(raw, t.offsets[:-1], t.offsets[1:]):
+        mean, sd = oracle.coverage(oracle_reads(oracle, d), oracle.cov_opts(window_length=1000), L)[:2]
+        assert_f32_equal_bits(t.rcv[lo:hi], mean, "mean")
+        np.testing.assert_allclose(to_np(t.rcvsd[lo:hi]), sd, rtol=1e-6)
+
+
+def test_region_loop_host_columns_and_panic(oracle, ctx):
+    """C ABI called directly with HOST columns; a region that makes the reference panic fails the run."""
+    wl = 100
+    d0 = simple_reads([10, 250, 900], [60, 300, 950])
+    d0["isize"][:] = 40
+    d0["flag"][:] = 0x3
+    d1 = simple_reads([5], [40])           # unpaired: centre = pos + end_pos = 45 -> bin 0 (fine)
+    L = [1000, 50]
+    batches = [soa_batch(d0), soa_batch(d1)]
+    arr = (N.Region * 2)()
+    keep = []
+    for i, b in enumerate(batches):
+        soa, k = b.c_soa()
+        keep.append(k)
+        arr[i].region_end = L[i]
+        arr[i].reads = soa
+    o = cb.CoverageOptions(window_length=wl, min_mapq=0).c_opts()
+    total = int(N.lib().cnvb_coverage_rows(C.byref(o), N.FRAGMENTS_GENOME_WIDE, arr, 2))
+    assert total == 11
+    cols = {k: np.zeros(total, np.float32) for k in ("rcv", "lcv", "frm")}
+    cols.update({k: np.zeros(total, np.uint32) for k in ("start", "end")})
+    ft = np.zeros(total, np.uint8)
+    cc = N.CovColumns(cols["start"].ctypes.data, cols["end"].ctypes.data, cols["rcv"].ctypes.data, None,
+                      cols["lcv"].ctypes.data, None, cols["frm"].ctypes.data, None, None, None, ft.ctypes.data)
+    nproc = np.zeros(2, np.uint64)
+    nskip = np.zeros(2, np.uint64)
+    ctx.check(N.lib().cnvb_coverage_run(ctx.handle, C.byref(o), N.FRAGMENTS_GENOME_WIDE, arr, 2, C.byref(cc),
+                                        nproc.ctypes.data, nskip.ctypes.data, N.MEM_HOST))
+    oo = oracle.cov_opts(window_length=wl, min_mapq=0)
+    exp = np.concatenate([oracle.frag_gw(oracle_reads(oracle, d), oo, l)[0] for d, l in zip((d0, d1), L)])
+    assert np.array_equal(cols["rcv"], exp.astype(np.float32))
+    assert cols["end"][-1] == 50 and cols["start"][10] == 0 and cols["end"][9] == 1000
+    assert nproc.tolist() == [3, 1]
+    # an unpaired read far right: centre = pos + end_pos lands outside -> reference panics (agg.rs:144)
+    d2 = simple_reads([40], [49])
+    soa, k = soa_batch(d2).c_soa()
+    arr[1].reads = soa
+    rc = N.lib().cnvb_coverage_run(ctx.handle, C.byref(o), N.FRAGMENTS_GENOME_WIDE, arr, 2, C.byref(cc),
+                                   nproc.ctypes.data, nskip.ctypes.data, N.MEM_HOST)
+    assert rc == N.ERR_REFERENCE_PANIC
+    with pytest.raises(cb.ReferencePanic, match="region 1"):
+        ctx.check(rc)
