@@ -15,9 +15,14 @@
 //            double-buffered TMEM accumulators; 4 epilogue warps read them back with tcgen05.ld
 //            and test  n_j - 2 g_ij <= theta'_i  (one FFMA + one compare per pair), appending the
 //            rare survivors to the row's candidate buffer in HBM.
-//   compact  between sweeps over geometrically growing column sets (tiles are visited in a
-//            scattered order so that every contig is sampled early) a warp per row selects the
-//            k-th smallest candidate value and tightens theta'_i with the bound below.
+//   order    rows are sorted by their projection p_t on the all-ones direction (the panel's first
+//            principal direction: targets differ mostly by capture efficiency).  A projection is
+//            1-Lipschitz, |p_i - p_j| <= D_ij, so a column can only be among the k nearest of row
+//            i if |p_j - p_i| <= V_i (k-th smallest upper bound seen so far): in sorted order
+//            every block of 256 rows needs one contiguous WINDOW of column tiles.
+//   compact  between sweeps over windows that grow geometrically around the block's own
+//            position (x4 per round, never beyond what V_i still allows) a warp per row selects
+//            the k-th smallest candidate value and tightens theta'_i with the bound below.
 //   rescore  exact f32-sequential distance for every candidate, (distance, index) top-k.
 //
 // Bound (scaled units; everything per PAIR so that a few large-norm rows do not loosen it for
@@ -37,6 +42,10 @@
 
 #include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 namespace {
 
@@ -135,18 +144,54 @@ struct WisPrep {
     float inv_scale;
 };
 
-// one warp per row: centre, scale, round to fp16; n_t (of the fp16 row) and delta_t in f64
-__global__ void wis_pack_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, uint32_t Kp,
-                                const double *__restrict__ colsum, float scale, __half *__restrict__ H,
-                                float *__restrict__ nrm, float *__restrict__ delta, float *__restrict__ maxes) {
+// one warp per row: projection of the centred, scaled row on ones/sqrt(S), in f64 from the raw
+// values (so |p_i - p_j| <= scale |x_i - x_j| holds up to the f64 summation error, covered by
+// the window slack); written as an order-preserving u32 key of the f32-rounded value
+__device__ __forceinline__ uint32_t f32_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+__global__ void wis_proj_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, const double *__restrict__ colsum,
+                                float scale, uint32_t *__restrict__ pkey, uint32_t *__restrict__ ident,
+                                float *__restrict__ pabs_max) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (warp >= T) return;
+    double acc = 0.0;
+    for (uint32_t s = lane; s < S; s += 32) {
+        const float c = (float)(colsum[s] / (double)T);
+        acc += (double)X[(size_t)warp * S + s] - (double)c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float p = (float)(acc * (double)scale / sqrt((double)S));
+        pkey[warp] = f32_key(p);
+        ident[warp] = warp;
+        atomicMax(reinterpret_cast<int *>(pabs_max), __float_as_int(fabsf(p)));
+    }
+}
+
+// one warp per SORTED position: centre, scale, round the row perm[pos] to fp16; n_t (of the fp16
+// row) and delta_t in f64; contig id and projection in sorted order
+__global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S,
+                                uint32_t Kp, const double *__restrict__ colsum, float scale,
+                                const uint32_t *__restrict__ perm, const uint32_t *__restrict__ pkey_sorted,
+                                __half *__restrict__ H, float *__restrict__ nrm, float *__restrict__ delta,
+                                uint32_t *__restrict__ tid_sorted, float *__restrict__ psorted,
+                                float *__restrict__ maxes) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (warp >= T) return;
+    const uint32_t src = perm[warp];
     double n = 0.0, e = 0.0;
     for (uint32_t s = lane; s < Kp; s += 32) {
         __half h = __float2half_rn(0.0f);
         if (s < S) {
             const float c = (float)(colsum[s] / (double)T);
-            const float u = __fmul_rn(__fsub_rn(X[(size_t)warp * S + s], c), scale);
+            const float u = __fmul_rn(__fsub_rn(X[(size_t)src * S + s], c), scale);
             h = __float2half_rn(u);
             const double hf = (double)__half2float(h);
             n += hf * hf;
@@ -166,9 +211,27 @@ __global__ void wis_pack_kernel(const float *__restrict__ X, uint32_t T, uint32_
         const float df = __double2float_ru(sqrt(e) * (1.0 + 1.0 / 1024.0) + sqrt(n) * (1.0 / 8388608.0));
         nrm[warp] = nf;
         delta[warp] = df;
+        tid_sorted[warp] = tid[src];
+        psorted[warp] = key_f32(pkey_sorted[warp]);
         const float rho = __double2float_ru((double)df / fmax(sqrt(n), 1.0));  // delta_j <= rho * max(s_j, 1)
         atomicMax(reinterpret_cast<int *>(maxes), __float_as_int(rho));
     }
+}
+
+// row subset [row_begin, row_end): flags over sorted positions, and the gather of their fp16 rows
+__global__ void wis_rowflag_kernel(const uint32_t *__restrict__ perm, uint32_t T, uint32_t row_begin, uint32_t row_end,
+                                   uint8_t *__restrict__ flag) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < T) flag[j] = (perm[j] >= row_begin && perm[j] < row_end) ? 1 : 0;
+}
+__global__ void wis_gather_rows_kernel(const __half *__restrict__ H, uint32_t Kp, const uint32_t *__restrict__ rows_a,
+                                       uint32_t rows, uint32_t rows_pad, __half *__restrict__ HA) {
+    const uint32_t r = blockIdx.x;
+    const uint32_t words = Kp / 2;  // Kp is a multiple of 64
+    const uint32_t *src = r < rows ? reinterpret_cast<const uint32_t *>(H + (size_t)rows_a[r] * Kp) : nullptr;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(HA + (size_t)r * Kp);
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src ? src[w] : 0u;
+    (void)rows_pad;
 }
 
 // per-column operands of the sweep test: n'_j (+inf beyond T: never a candidate) and s_j
@@ -203,14 +266,12 @@ __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi,
 
 // ---- sweep ------------------------------------------------------------------------------------------
 struct SweepArgs {
-    const float *nprime;     // [Tpad] n'_j (+inf beyond T)
+    const float *nprime;     // [Tpad] n'_j (+inf beyond T), sorted column order
     const float *tile_smax;  // [n column tiles] max_j s_j over the tile
-    const uint32_t *tid;     // [T]
     const float *thr;        // [rows] theta_i (+inf until k candidates are known)
     const float *kap;        // [rows] kappa_i
-    const uint32_t *tiles;   // column tiles of this step
-    uint32_t n_tiles;
-    uint32_t T, row_begin, row_end;
+    const uint4 *rng;        // [row blocks] column tiles of this round: [x, y) and [z, w)
+    uint32_t T, rows;
     uint32_t k_mmas;         // K16 slabs per tile that hold data: ceil(S / 16)
     uint32_t n_kblocks;      // ceil(Kp / 64)
     float *cand_val;         // [rows][kCandCap]
@@ -219,7 +280,13 @@ struct SweepArgs {
 };
 
 __global__ void __launch_bounds__(kSweepThreads, 1)
-wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
+wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const SweepArgs a) {
+    // this block's share of the round: two tile ranges either side of what it has swept before
+    const uint4 rng = a.rng[blockIdx.x];
+    const uint32_t n_lo = rng.y - rng.x, n_tiles = n_lo + (rng.w - rng.z);
+    if (n_tiles == 0) return;
+    auto tile_at = [&](uint32_t it) { return it < n_lo ? rng.x + it : rng.z + (it - n_lo); };
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
@@ -234,9 +301,9 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
     const uint32_t bar_acc_empty = bar_acc_full + 16;         // 2
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t row0 = a.row_begin + blockIdx.x * kTileRows;
+    const uint32_t row0 = blockIdx.x * kTileRows;  // position in the sorted row list
     for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
-        s_cnt[t] = row0 + t < a.row_end ? a.cand_cnt[row0 + t - a.row_begin] : 0u;
+        s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
@@ -267,15 +334,15 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
             mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
             for (uint32_t h = 0; h < 2; ++h)
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
-                    tma_load_2d(a_base + (h * kMaxKBlocks + kb) * kTileBytes, &tmap, bar_a_full, (int32_t)(kb * kKBlock),
+                    tma_load_2d(a_base + (h * kMaxKBlocks + kb) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
                                 (int32_t)(row0 + h * 128));
             uint32_t st = 0, ph = 0;
-            for (uint32_t it = 0; it < a.n_tiles; ++it) {
-                const int32_t j0 = (int32_t)(a.tiles[it] * kTileCols);
+            for (uint32_t it = 0; it < n_tiles; ++it) {
+                const int32_t j0 = (int32_t)(tile_at(it) * kTileCols);
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                     mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
                     mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
-                    tma_load_2d(b_base + st * kTileBytes, &tmap, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                    tma_load_2d(b_base + st * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
                     if (++st == kStages) {
                         st = 0;
                         ph ^= 1u;
@@ -289,7 +356,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
             mbar_wait(bar_a_full, 0);
             tc_fence_after();
             uint32_t st = 0, ph = 0, as = 0, aph = 0;
-            for (uint32_t it = 0; it < a.n_tiles; ++it) {
+            for (uint32_t it = 0; it < n_tiles; ++it) {
                 mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
                 tc_fence_after();
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
@@ -331,13 +398,13 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
         for (int h = 0; h < 2; ++h) {
             rloc[h] = h * 128 + q * 32 + lane;  // row within the CTA's 256
             const uint32_t row = row0 + rloc[h];
-            const bool live = row < a.row_end;
-            thr[h] = live ? a.thr[row - a.row_begin] : -__int_as_float(0x7f800000);
-            kap[h] = live ? a.kap[row - a.row_begin] : 0.0f;
+            const bool live = row < a.rows;
+            thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
+            kap[h] = live ? a.kap[row] : 0.0f;
         }
         uint32_t as = 0, aph = 0;
-        for (uint32_t it = 0; it < a.n_tiles; ++it) {
-            const uint32_t tile = a.tiles[it];
+        for (uint32_t it = 0; it < n_tiles; ++it) {
+            const uint32_t tile = tile_at(it);
             const uint32_t j0 = tile * kTileCols + cpart * 32u;
             // column operands of this warp's 32 columns (same addresses for all lanes: L1 broadcast)
             float nj[32];
@@ -362,8 +429,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
                 // keep iff  n'_j - 2 g - kappa_i s_j <= theta_i;  sufficient: n'_j - 2 g <= theta_i + kappa_i smax
                 const float rhs = fmaf(kap[h], smax, thr[h]);
                 const uint32_t row = row0 + rloc[h];
-                float *cv = a.cand_val + (size_t)(row - a.row_begin) * kCandCap;
-                uint32_t *ci = a.cand_idx + (size_t)(row - a.row_begin) * kCandCap;
+                float *cv = a.cand_val + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
+                uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
                 // Survivors are rare (a few per 1024 pairs).  All 32 compares are independent; groups of
                 // four columns fold into one predicate each, the eight group bits of all lanes are
                 // OR-reduced with one REDUX, and the append code runs (warp-uniformly) only for groups in
@@ -411,32 +478,116 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap, const SweepArgs a) {
     tc_fence_before();
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
-        if (row0 + t < a.row_end) a.cand_cnt[row0 + t - a.row_begin] = s_cnt[t];
+        if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-// ---- compaction: k-th smallest candidate value per row, new threshold -----------------------------
-__device__ __forceinline__ uint32_t f32_key(float v) {
-    const uint32_t b = __float_as_uint(v);
-    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+// ---- windows: which column tiles a block of rows still has to see --------------------------------
+struct WindowArgs {
+    const float *psorted;     // [T] projections, ascending
+    const uint32_t *rows_a;   // [rows] sorted position of every row (nullptr: identity)
+    const float *vg;          // [rows] V'_i = V_i / (1 - g) + delta_i (+inf: no bound yet)
+    const uint32_t *overflow; // [rows] rows that fell back to the exact kernel need nothing
+    uint32_t T, n_tiles, rows;
+    uint32_t round, w0, grow; // round 0: own tiles +- w0; later: at most `grow` more tiles per side
+    float slack;              // projection rounding slack (absolute)
+    uint4 *rng;               // [row blocks] out: tile ranges [x, y) and [z, w) of this round
+    uint2 *done;              // [row blocks] in/out: tiles swept so far [x, y)
+    unsigned long long *tiles_swept;
+};
+
+__device__ __forceinline__ uint32_t lower_bound_f32(const float *p, uint32_t n, float v) {  // first idx with p[idx] >= v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
-__device__ __forceinline__ float key_f32(uint32_t u) {
-    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+__device__ __forceinline__ uint32_t upper_bound_f32(const float *p, uint32_t n, float v) {  // first idx with p[idx] > v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
 
+__global__ void __launch_bounds__(kTileRows) wis_window_kernel(WindowArgs a) {
+    __shared__ float s_lo[kTileRows / 32], s_hi[kTileRows / 32];
+    const uint32_t r = blockIdx.x * kTileRows + threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    float lo = inf, hi = -inf;
+    if (r < a.rows && !(a.round > 0 && a.overflow[r])) {
+        const float p = a.psorted[a.rows_a ? a.rows_a[r] : r];
+        float w = 0.0f;
+        if (a.round > 0) w = __fadd_ru(__fmul_ru(a.vg[r], 1.0f + 1.0f / 1048576.0f), a.slack);  // inf stays inf
+        lo = __fsub_rd(p, w);
+        hi = __fadd_ru(p, w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane_id() == 0) {
+        s_lo[threadIdx.x >> 5] = lo;
+        s_hi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (uint32_t w = 1; w < kTileRows / 32; ++w) {
+        lo = fminf(lo, s_lo[w]);
+        hi = fmaxf(hi, s_hi[w]);
+    }
+    uint4 out = make_uint4(0, 0, 0, 0);
+    uint2 dn = a.round ? a.done[blockIdx.x] : make_uint2(0, 0);
+    if (lo <= hi) {  // some row of the block still takes part
+        const uint32_t req_lo = lower_bound_f32(a.psorted, a.T, lo) / kTileCols;
+        const uint32_t ub = upper_bound_f32(a.psorted, a.T, hi);
+        const uint32_t req_hi = min(a.n_tiles, (ub + kTileCols - 1) / kTileCols);
+        if (a.round == 0) {
+            // 2 (1 + w0) tiles centred on the block (every pair of this window is appended, so its
+            // size is bounded by the candidate buffer; rows of a sparse subset see an off-centre
+            // window, which only loosens their first bound)
+            const uint32_t c = (req_lo + req_hi) >> 1, half = 1u + a.w0;
+            const uint32_t size = min(a.n_tiles, 2u * half);
+            out.x = c > half ? c - half : 0u;
+            if (out.x + size > a.n_tiles) out.x = a.n_tiles - size;
+            out.y = out.x + size;
+            dn = make_uint2(out.x, out.y);
+        } else {
+            const uint32_t lim_lo = dn.x > a.grow ? dn.x - a.grow : 0u;
+            const uint32_t lim_hi = min(a.n_tiles, dn.y + a.grow);
+            const uint32_t new_lo = min(dn.x, max(req_lo, lim_lo));
+            const uint32_t new_hi = max(dn.y, min(req_hi, lim_hi));
+            out = make_uint4(new_lo, dn.x, dn.y, new_hi);
+            dn = make_uint2(new_lo, new_hi);
+        }
+    }
+    a.rng[blockIdx.x] = out;
+    a.done[blockIdx.x] = dn;
+    const uint32_t n = (out.y - out.x) + (out.w - out.z);
+    if (n) atomicAdd(a.tiles_swept, (unsigned long long)n);
+}
+
+// ---- compaction: k-th smallest candidate value per row, new threshold -----------------------------
 struct CompactArgs {
     float *cand_val;         // stored v = n'_j - 2 g
     uint32_t *cand_idx;
     uint32_t *cand_cnt;
     float *thr, *kap;
     uint32_t *overflow;      // [rows] sticky flag
-    const float *nrm, *delta;  // indexed by absolute row
+    uint32_t *seen;          // [rows] list length after the row's last compaction (unchanged lists are skipped)
+    float *vg;               // [rows] out: V'_i for the window kernel
+    const uint32_t *rows_a;  // [rows] sorted position of every row (nullptr: identity)
+    const float *nrm, *delta;  // indexed by sorted position
     const float *maxes;      // [0] rho
-    const uint32_t *tid;     // contig ids: same-contig pairs (incl. the row itself) are not candidates
-    uint32_t rows, row_begin, k;
+    const uint32_t *tid;     // contig ids by sorted position: same-contig pairs (incl. the row itself) are not candidates
+    uint32_t rows, k;
     double c_acc, c_rnd, g_ref;
 };
 
@@ -469,9 +620,10 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
     }
     if (a.overflow[r]) return;
     if (n <= n_min || n > 32u * KPER) return;  // the other launch's rows
+    if (n == a.seen[r]) return;                // nothing new since the last compaction
     float *cv = a.cand_val + (size_t)r * kCandCap;
     uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
-    const uint32_t row = a.row_begin + r;
+    const uint32_t row = a.rows_a ? a.rows_a[r] : r;
     const double ni = (double)a.nrm[row], di = (double)a.delta[row], rho = (double)a.maxes[0];
     const uint32_t ti = a.tid[row];
     constexpr uint32_t kPer = KPER;
@@ -547,9 +699,11 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         const double kappa = 2.0 * a.c_acc * sqrt(ni) + 2.0 * rho * Vp;
         const double theta = Vp * Vp * (1.0 + 1e-9) - ni * (1.0 - a.c_rnd);
         a.cand_cnt[r] = kept;
+        a.seen[r] = kept;
         if (have_bound) {
             a.thr[r] = __double2float_ru(theta);
             a.kap[r] = __double2float_ru(kappa * (1.0 + 1e-6));
+            a.vg[r] = __double2float_ru(Vg);
         }
     }
 }
@@ -557,7 +711,9 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
 // ---- exact re-scoring and (distance, index) top-k ------------------------------------------------
 __global__ void __launch_bounds__(128) wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid,
                                                           uint32_t T, uint32_t S, uint32_t k, uint32_t row_begin,
-                                                          uint32_t rows, const uint32_t *__restrict__ cand_idx,
+                                                          uint32_t rows, const uint32_t *__restrict__ perm,
+                                                          const uint32_t *__restrict__ rows_a,
+                                                          const uint32_t *__restrict__ cand_idx,
                                                           const uint32_t *__restrict__ cand_cnt,
                                                           const uint32_t *__restrict__ overflow,
                                                           float *__restrict__ out_dist, uint32_t *__restrict__ out_idx) {
@@ -567,18 +723,18 @@ __global__ void __launch_bounds__(128) wis_rescore_kernel(const float *__restric
     __shared__ uint32_t s_j[kCandCap];
     const uint32_t r = blockIdx.x;
     if (overflow[r]) return;  // recomputed by the exact row kernel
-    const uint32_t i = row_begin + r;
+    const uint32_t i = perm[rows_a ? rows_a[r] : r];  // target index of this row
     const uint32_t n = cand_cnt[r];
     const bool vec4 = (S & 3u) == 0u && (reinterpret_cast<uintptr_t>(X) & 15u) == 0u;
     for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) s_xi[s] = X[(size_t)i * S + s];
     __syncthreads();
     for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
-        const uint32_t j = cand_idx[(size_t)r * kCandCap + c];
+        const uint32_t j = perm[cand_idx[(size_t)r * kCandCap + c]];
         s_j[c] = j;
         s_d[c] = wis_ref_distance(s_xi, X + (size_t)j * S, S, vec4);
     }
     __syncthreads();
-    const size_t o = (size_t)r * k;
+    const size_t o = (size_t)(i - row_begin) * k;
     for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
         const float d = s_d[c];
         const uint32_t j = s_j[c];
@@ -603,12 +759,13 @@ __global__ void __launch_bounds__(128) wis_rescore_kernel(const float *__restric
 }
 
 __global__ void wis_overflow_list_kernel(const uint32_t *__restrict__ overflow, const uint32_t *__restrict__ cand_cnt,
-                                         uint32_t rows, uint32_t row_begin, uint32_t *__restrict__ list,
+                                         uint32_t rows, const uint32_t *__restrict__ perm,
+                                         const uint32_t *__restrict__ rows_a, uint32_t *__restrict__ list,
                                          uint32_t *__restrict__ count, unsigned long long *__restrict__ n_rescored) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t c = 0;
     if (r < rows) {
-        if (overflow[r]) list[atomicAdd(count, 1u)] = row_begin + r; else c = cand_cnt[r];
+        if (overflow[r]) list[atomicAdd(count, 1u)] = perm[rows_a ? rows_a[r] : r]; else c = cand_cnt[r];
     }
     c = __reduce_add_sync(0xffffffffu, c);
     if (lane_id() == 0 && c) atomicAdd(n_rescored, (unsigned long long)c);
@@ -667,30 +824,56 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (k > kCandCap / 4) return fail(ctx, CNVB_ERR_INVALID, "tensor engine: max_ref_targets > %u", kCandCap / 4);
     const uint32_t n_tiles = (T + kTileCols - 1) / kTileCols;
     const uint32_t Tpad = n_tiles * kTileCols;
+    const bool subset = rows != T;
+    const uint32_t row_blocks = (rows + kTileRows - 1) / kTileRows;
+    const uint32_t rows_pad = row_blocks * kTileRows;
     PoolGuard g(ctx);
     double *colsum = nullptr;
-    float *scal = nullptr;  // [0] absmax | [1] n_max | [2] delta_max
-    __half *H = nullptr;
-    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *cand_val = nullptr, *nprime = nullptr,
-          *snorm = nullptr, *tile_smax = nullptr;
-    uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *tiles = nullptr, *ovf_list = nullptr;
+    float *scal = nullptr;  // [0] absmax | [1] rho | [2] max |p|
+    __half *H = nullptr, *HA = nullptr;
+    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *vg = nullptr, *cand_val = nullptr,
+          *nprime = nullptr, *snorm = nullptr, *tile_smax = nullptr, *psorted = nullptr;
+    uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *seen = nullptr, *ovf_list = nullptr,
+             *pkey = nullptr, *pkey_sorted = nullptr, *ident = nullptr, *perm = nullptr, *tid_sorted = nullptr,
+             *rows_a = nullptr, *n_sel = nullptr;
+    uint8_t *rflag = nullptr;
+    uint4 *rng = nullptr;
+    uint2 *done = nullptr;
+    unsigned long long *counters = nullptr;  // [0] tiles swept | [1] pairs re-scored
+    void *cub_tmp = nullptr;
+    size_t sort_bytes = 0, sel_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, ctx->stream);
+    if (subset)
+        cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<uint32_t>(0), rflag, rows_a, n_sel, (int)T,
+                                   ctx->stream);
     cudaError_t e;
     if ((e = g.alloc(S, &colsum)) != cudaSuccess || (e = g.alloc(4, &scal)) != cudaSuccess ||
         (e = g.alloc((size_t)Tpad * Kp, &H)) != cudaSuccess || (e = g.alloc(Tpad, &nrm)) != cudaSuccess ||
         (e = g.alloc(Tpad, &delta)) != cudaSuccess || (e = g.alloc(rows, &thr)) != cudaSuccess ||
-        (e = g.alloc(rows, &kap)) != cudaSuccess || (e = g.alloc(Tpad, &nprime)) != cudaSuccess ||
-        (e = g.alloc(Tpad, &snorm)) != cudaSuccess || (e = g.alloc(n_tiles, &tile_smax)) != cudaSuccess ||
+        (e = g.alloc(rows, &kap)) != cudaSuccess || (e = g.alloc(rows, &vg)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &nprime)) != cudaSuccess || (e = g.alloc(Tpad, &snorm)) != cudaSuccess ||
+        (e = g.alloc(n_tiles, &tile_smax)) != cudaSuccess || (e = g.alloc(T, &psorted)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_val)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_idx)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
-        (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(n_tiles, &tiles)) != cudaSuccess ||
-        (e = g.alloc(rows + 1, &ovf_list)) != cudaSuccess)
+        (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(rows, &seen)) != cudaSuccess ||
+        (e = g.alloc(rows + 1, &ovf_list)) != cudaSuccess || (e = g.alloc(T, &pkey)) != cudaSuccess ||
+        (e = g.alloc(T, &pkey_sorted)) != cudaSuccess || (e = g.alloc(T, &ident)) != cudaSuccess ||
+        (e = g.alloc(T, &perm)) != cudaSuccess || (e = g.alloc(T, &tid_sorted)) != cudaSuccess ||
+        (e = g.alloc(row_blocks, &rng)) != cudaSuccess || (e = g.alloc(row_blocks, &done)) != cudaSuccess ||
+        (e = g.alloc(2, &counters)) != cudaSuccess ||
+        (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
+        return fail_cuda(ctx, e, "allocating the tensor engine's work space");
+    if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
+                   (e = g.alloc(1, &n_sel)) != cudaSuccess || (e = g.alloc((size_t)rows_pad * Kp, &HA)) != cudaSuccess))
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     cudaStream_t st = ctx->stream;
     cudaMemsetAsync(colsum, 0, S * sizeof(double), st);
     cudaMemsetAsync(scal, 0, 4 * sizeof(float), st);
     cudaMemsetAsync(cand_cnt, 0, rows * 4, st);
     cudaMemsetAsync(overflow, 0, rows * 4, st);
+    cudaMemsetAsync(seen, 0, rows * 4, st);
     cudaMemsetAsync(ovf_list, 0, (rows + 1) * 4, st);
+    cudaMemsetAsync(counters, 0, 16, st);
     wis_colsum_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 4), 128, 0, st>>>(dX, T, S, colsum, scal);
     CNVB_LAUNCHED(ctx, "wis_colsum_kernel");
     float absmax = 0.0f;
@@ -700,8 +883,15 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     int ex = 0;
     frexpf(absmax > 0.0f ? 2.0f * absmax : 1.0f, &ex);
     const float scale = ldexpf(1.0f, 13 - ex);
+    // sort the targets by their projection on the all-ones direction
+    wis_proj_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, T, S, colsum, scale, pkey, ident, scal + 2);
+    CNVB_LAUNCHED(ctx, "wis_proj_kernel");
+    CNVB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, st),
+              "sorting the projections");
+    ctx->launches += 1;
     if (Tpad > T) cudaMemsetAsync(H + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
-    wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, T, S, Kp, colsum, scale, H, nrm, delta, scal + 1);
+    wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, dtid, T, S, Kp, colsum, scale, perm, pkey_sorted, H, nrm, delta,
+                                                 tid_sorted, psorted, scal + 1);
     CNVB_LAUNCHED(ctx, "wis_pack_kernel");
     const double c_acc = (double)Kp / 8388608.0;  // fp32 accumulation of Kp exact products, truncating adds
     const double c_rnd = 8.0 / 16777216.0;        // f32 rounding of norms and of the epilogue FFMAs
@@ -711,32 +901,25 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     CNVB_LAUNCHED(ctx, "wis_tile_smax_kernel");
     wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(thr, 0, rows, __builtin_inff());
     CNVB_LAUNCHED(ctx, "wis_fill_kernel");
+    wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(vg, 0, rows, __builtin_inff());
+    CNVB_LAUNCHED(ctx, "wis_fill_kernel");
     cudaMemsetAsync(kap, 0, rows * 4, st);
-
-    CUtensorMap tmap;
-    CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap));
-    // column tiles in a scattered order (stride ~ golden ratio, coprime with the tile count)
-    std::vector<uint32_t> order(n_tiles);
-    {
-        uint32_t stride = (uint32_t)(n_tiles * 0.6180339887) | 1u;
-        auto gcd = [](uint32_t x, uint32_t y) {
-            while (y) {
-                const uint32_t t = x % y;
-                x = y;
-                y = t;
-            }
-            return x;
-        };
-        while (stride > 1 && gcd(stride, n_tiles) != 1) stride += 2;
-        if (n_tiles == 1) stride = 1;
-        uint32_t cur = 0;
-        for (uint32_t q = 0; q < n_tiles; ++q) {
-            order[q] = cur;
-            cur = (uint32_t)(((uint64_t)cur + stride) % n_tiles);
-        }
+    if (subset) {  // the rows of this call, in sorted order, and their fp16 rows as the A operand
+        wis_rowflag_kernel<<<(T + 255) / 256, 256, 0, st>>>(perm, T, row_begin, row_end, rflag);
+        CNVB_LAUNCHED(ctx, "wis_rowflag_kernel");
+        CNVB_CUDA(ctx, cub::DeviceSelect::Flagged(cub_tmp, sel_bytes, cub::CountingInputIterator<uint32_t>(0), rflag, rows_a,
+                                                  n_sel, (int)T, st), "selecting the rows");
+        ctx->launches += 1;
+        wis_gather_rows_kernel<<<rows_pad, 64, 0, st>>>(H, Kp, rows_a, rows, rows_pad, HA);
+        CNVB_LAUNCHED(ctx, "wis_gather_rows_kernel");
     }
-    CNVB_CUDA(ctx, cudaMemcpyAsync(tiles, order.data(), n_tiles * 4, cudaMemcpyHostToDevice, st), "uploading the tile order");
-    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "uploading the tile order");  // `order` dies with this scope otherwise
+    float pabs = 0.0f;
+    CNVB_CUDA(ctx, cudaMemcpyAsync(&pabs, scal + 2, 4, cudaMemcpyDeviceToHost, st), "reading the projection range");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "reading the projection range");
+
+    CUtensorMap tmap_b, tmap_a;
+    CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b));
+    if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
     CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -744,12 +927,11 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     SweepArgs sa{};
     sa.nprime = nprime;
     sa.tile_smax = tile_smax;
-    sa.tid = dtid;
     sa.thr = thr;
     sa.kap = kap;
+    sa.rng = rng;
     sa.T = T;
-    sa.row_begin = row_begin;
-    sa.row_end = row_end;
+    sa.rows = rows;
     sa.k_mmas = (S + 15) / 16;
     sa.n_kblocks = Kp / kKBlock;
     sa.cand_val = cand_val;
@@ -762,27 +944,44 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.thr = thr;
     ca.kap = kap;
     ca.overflow = overflow;
+    ca.seen = seen;
+    ca.vg = vg;
+    ca.rows_a = rows_a;
     ca.nrm = nrm;
     ca.delta = delta;
     ca.maxes = scal + 1;
-    ca.tid = dtid;
+    ca.tid = tid_sorted;
     ca.rows = rows;
-    ca.row_begin = row_begin;
     ca.k = k;
     ca.c_acc = c_acc;
     ca.c_rnd = c_rnd;
     ca.g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
+    WindowArgs wa{};
+    wa.psorted = psorted;
+    wa.rows_a = rows_a;
+    wa.vg = vg;
+    wa.overflow = overflow;
+    wa.T = T;
+    wa.n_tiles = n_tiles;
+    wa.rows = rows;
+    // the first window holds max(768, 3k) columns (all of them are appended: at most kCandCap)
+    wa.w0 = std::min<uint32_t>(7, std::max<uint32_t>(2, ((3 * k + kTileCols - 1) / kTileCols - 2 + 1) / 2));
+    // f32 rounding of the projections (2 x half an ulp of the largest) plus their f64 summation error
+    wa.slack = pabs * (1.0f / 4194304.0f) + 1e-30f;
+    wa.rng = rng;
+    wa.done = done;
+    wa.tiles_swept = counters;
 
-    const uint32_t row_blocks = (rows + kTileRows - 1) / kTileRows;
-    // geometric column schedule: first at least 4k columns, then x4 each step
-    uint32_t done = 0, step = std::max<uint32_t>(4, (4 * k + kTileCols - 1) / kTileCols);
-    while (done < n_tiles) {
-        const uint32_t cnt = std::min(step, n_tiles - done);
-        sa.tiles = tiles + done;
-        sa.n_tiles = cnt;
+    // windows grow x4 per round around the block's own position until they span every tile
+    uint32_t half = 1 + wa.w0;
+    for (uint32_t round = 0;; ++round) {
+        wa.round = round;
+        wa.grow = 3 * half;
+        wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
+        CNVB_LAUNCHED(ctx, "wis_window_kernel");
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
-            wis_sweep_kernel<<<row_blocks, kSweepThreads, smem, st>>>(tmap, sa);
+            wis_sweep_kernel<<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         {
@@ -792,32 +991,31 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
             wis_compact_kernel<kCandCap / 32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 1024u);
         }
         CNVB_LAUNCHED(ctx, "wis_compact_kernel");
-        done += cnt;
-        ctx->wis_stats[3] += 1;
-        step = 3 * done;  // every step quadruples the columns seen so far
+        if (round > 0) half *= 4;
+        if (half >= n_tiles && round > 0) break;
+        if (n_tiles <= 2 * (1 + wa.w0)) break;  // the first window already spans everything
     }
     const size_t rsmem = (((size_t)S + 3) & ~(size_t)3) * 4 + kCandCap * 4;
     CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem),
               "smem opt-in");
     {
         KernelSpan span(ctx, "wis_rescore_kernel");
-        wis_rescore_kernel<<<rows, 128, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, cand_idx, cand_cnt, overflow,
-                                                     d_dist, d_idx);
+        wis_rescore_kernel<<<rows, 128, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, perm, rows_a, cand_idx, cand_cnt,
+                                                     overflow, d_dist, d_idx);
     }
     CNVB_LAUNCHED(ctx, "wis_rescore_kernel");
     // rows whose candidate buffer overflowed: exact row kernel
-    unsigned long long *d_resc = reinterpret_cast<unsigned long long *>(colsum);  // prep is done: reuse 8 bytes
-    cudaMemsetAsync(d_resc, 0, 8, st);
-    wis_overflow_list_kernel<<<(rows + 255) / 256, 256, 0, st>>>(overflow, cand_cnt, rows, row_begin, ovf_list + 1,
-                                                                 ovf_list, d_resc);
+    wis_overflow_list_kernel<<<(rows + 255) / 256, 256, 0, st>>>(overflow, cand_cnt, rows, perm, rows_a, ovf_list + 1,
+                                                                 ovf_list, counters + 1);
     CNVB_LAUNCHED(ctx, "wis_overflow_list_kernel");
     uint32_t n_ovf = 0;
-    unsigned long long n_resc = 0;
+    unsigned long long h_cnt[2] = {0, 0};
     CNVB_CUDA(ctx, cudaMemcpyAsync(&n_ovf, ovf_list, 4, cudaMemcpyDeviceToHost, st), "reading the fallback count");
-    CNVB_CUDA(ctx, cudaMemcpyAsync(&n_resc, d_resc, 8, cudaMemcpyDeviceToHost, st), "reading the re-score count");
+    CNVB_CUDA(ctx, cudaMemcpyAsync(h_cnt, counters, 16, cudaMemcpyDeviceToHost, st), "reading the engine counters");
     CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");
     ctx->wis_stats[1] = n_ovf;
-    ctx->wis_stats[2] = n_resc;
+    ctx->wis_stats[2] = h_cnt[1];
+    ctx->wis_stats[3] = h_cnt[0];
     if (n_ovf) CNVB_TRY(run_rows_exact(ctx, dX, dtid, T, S, k, ovf_list + 1, n_ovf, row_begin, d_dist, d_idx));
     CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");  // work space is released on return
     return 0;

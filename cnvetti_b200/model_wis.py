@@ -59,11 +59,12 @@ def compute_distances(X, tids, options=None, row_begin=0, row_end=None, ctx=None
 
 
 def last_stats(ctx=None):
-    """dict(rows, fallback_rows, rescored_pairs, sweeps) of the last distance computation."""
+    """dict(rows, fallback_rows, rescored_pairs, tiles) of the last distance computation
+    (tiles = 256x128 tiles of the pair matrix the tensor sweep visited)."""
     ctx = ctx or default_context()
     out = (C.c_uint64 * 4)()
     ctx.check(N.lib().cnvb_wis_last_stats(ctx.handle, out))
-    return dict(rows=int(out[0]), fallback_rows=int(out[1]), rescored_pairs=int(out[2]), sweeps=int(out[3]))
+    return dict(rows=int(out[0]), fallback_rows=int(out[1]), rescored_pairs=int(out[2]), tiles=int(out[3]))
 
 
 def prune_threshold(nearest, z, stride=1, ctx=None):

@@ -234,7 +234,7 @@ int cnvb_wis_distances(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint3
                        float *ref_dist, uint32_t *ref_idx, int mem);
 /* diagnostics of the last cnvb_wis_distances / cnvb_wis_build on this ctx:
  * out[0] rows computed, out[1] rows that fell back to the exact row kernel, out[2] pairs
- * re-scored exactly (tensor engine), out[3] column sweeps */
+ * re-scored exactly (tensor engine), out[3] 256x128 tiles the tensor sweep visited */
 int cnvb_wis_last_stats(const cnvb_ctx *ctx, uint64_t out[4]);
 /* = threshold of prune_distances (lib.rs:207-216): (mean + z*sd) as f32 over the nearest
  * distance of ALL T targets (f64, exact-sum mean, n-1 SD).  `nearest` = ref_dist[.][0].

@@ -116,7 +116,7 @@ def test_region_loop_host_columns_and_panic(oracle, ctx):
     assert cols["end"][-1] == 50 and cols["start"][10] == 0 and cols["end"][9] == 1000
     assert nproc.tolist() == [3, 1]
     # an unpaired read far right: centre = pos + end_pos lands outside -> reference panics (agg.rs:144)
-    d2 = simple_reads([40], [49])
+    d2 = simple_reads([45], [60])          # centre 105 -> window 1 of 1
     soa, k = soa_batch(d2).c_soa()
     arr[1].reads = soa
     rc = N.lib().cnvb_coverage_run(ctx.handle, C.byref(o), N.FRAGMENTS_GENOME_WIDE, arr, 2, C.byref(cc),
