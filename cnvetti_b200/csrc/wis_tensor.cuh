@@ -123,20 +123,43 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | ((kTileCols >> 3) << 17) | ((128u >> 4) << 24);
 
 // ---- prep -----------------------------------------------------------------------------------------
-__global__ void wis_colsum_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, double *__restrict__ colsum,
-                                  float *__restrict__ absmax) {
-    // grid-stride over rows; thread s-strided columns; block partial -> atomics (order-insensitive use)
-    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
-        double acc = 0.0;
-        float mx = 0.0f;
-        for (uint32_t t = blockIdx.x; t < T; t += gridDim.x) {
-            const float v = X[(size_t)t * S + s];
-            acc += (double)v;
-            mx = fmaxf(mx, fabsf(v));
+// column sums (f64) and the largest magnitude: a warp walks rows, lanes hold the columns lane + 32 q
+__global__ void __launch_bounds__(256) wis_colsum_kernel(const float *__restrict__ X, uint32_t T, uint32_t S,
+                                                         double *__restrict__ colsum, float *__restrict__ absmax) {
+    constexpr uint32_t kQ = kMaxKBlocks * kKBlock / 32;  // S <= 128
+    __shared__ double s_sum[kMaxKBlocks * kKBlock];
+    for (uint32_t s = threadIdx.x; s < kMaxKBlocks * kKBlock; s += blockDim.x) s_sum[s] = 0.0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), n_warps = gridDim.x * (blockDim.x >> 5);
+    double acc[kQ];
+    float mx = 0.0f;
+#pragma unroll
+    for (uint32_t q = 0; q < kQ; ++q) acc[q] = 0.0;
+    for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < T; t += n_warps) {
+#pragma unroll
+        for (uint32_t q = 0; q < kQ; ++q) {
+            const uint32_t c = lane + 32 * q;
+            if (c < S) {
+                const float v = X[(size_t)t * S + c];
+                acc[q] += (double)v;
+                mx = fmaxf(mx, fabsf(v));
+            }
         }
-        atomicAdd(&colsum[s], acc);
-        atomicMax(reinterpret_cast<int *>(absmax), __float_as_int(mx));  // non-negative floats order as ints
     }
+#pragma unroll
+    for (uint32_t q = 0; q < kQ; ++q)
+        if (lane + 32 * q < S) atomicAdd(&s_sum[lane + 32 * q], acc[q]);
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < S; c += blockDim.x) atomicAdd(&colsum[c], s_sum[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) atomicMax(reinterpret_cast<int *>(absmax), __float_as_int(mx));  // non-negative floats order as ints
+}
+
+// the centre that is subtracted from every row (any vector works: distances are translation invariant)
+__global__ void wis_cmean_kernel(const double *__restrict__ colsum, uint32_t T, uint32_t S, float *__restrict__ cmean) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < S) cmean[c] = (float)(colsum[c] / (double)T);
 }
 
 struct WisPrep {
@@ -155,16 +178,13 @@ __device__ __forceinline__ float key_f32(uint32_t u) {
     return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
 }
 
-__global__ void wis_proj_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, const double *__restrict__ colsum,
+__global__ void wis_proj_kernel(const float *__restrict__ X, uint32_t T, uint32_t S, const float *__restrict__ cmean,
                                 float scale, uint32_t *__restrict__ pkey, uint32_t *__restrict__ ident,
                                 float *__restrict__ pabs_max) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (warp >= T) return;
     double acc = 0.0;
-    for (uint32_t s = lane; s < S; s += 32) {
-        const float c = (float)(colsum[s] / (double)T);
-        acc += (double)X[(size_t)warp * S + s] - (double)c;
-    }
+    for (uint32_t s = lane; s < S; s += 32) acc += (double)X[(size_t)warp * S + s] - (double)cmean[s];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -178,7 +198,7 @@ __global__ void wis_proj_kernel(const float *__restrict__ X, uint32_t T, uint32_
 // one warp per SORTED position: centre, scale, round the row perm[pos] to fp16; n_t (of the fp16
 // row) and delta_t in f64; contig id and projection in sorted order
 __global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S,
-                                uint32_t Kp, const double *__restrict__ colsum, float scale,
+                                uint32_t Kp, const float *__restrict__ cmean, float scale,
                                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ pkey_sorted,
                                 __half *__restrict__ H, float *__restrict__ nrm, float *__restrict__ delta,
                                 uint32_t *__restrict__ tid_sorted, float *__restrict__ psorted,
@@ -190,8 +210,7 @@ __global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__r
     for (uint32_t s = lane; s < Kp; s += 32) {
         __half h = __float2half_rn(0.0f);
         if (s < S) {
-            const float c = (float)(colsum[s] / (double)T);
-            const float u = __fmul_rn(__fsub_rn(X[(size_t)src * S + s], c), scale);
+            const float u = __fmul_rn(__fsub_rn(X[(size_t)src * S + s], cmean[s]), scale);
             h = __float2half_rn(u);
             const double hf = (double)__half2float(h);
             n += hf * hf;
@@ -235,18 +254,28 @@ __global__ void wis_gather_rows_kernel(const __half *__restrict__ H, uint32_t Kp
 }
 
 // per-column operands of the sweep test: n'_j (+inf beyond T: never a candidate) and s_j
-__global__ void wis_cols_kernel(const float *__restrict__ nrm, uint32_t T, uint32_t Tpad, const float *__restrict__ maxes,
-                                double c_rnd, float *__restrict__ nprime, float *__restrict__ snorm) {
+struct ColMeta {  // per target, sorted order: everything the bounds need in one 16-byte load
+    float nrm, delta, s;
+    uint32_t tid;
+};
+
+__global__ void wis_cols_kernel(const float *__restrict__ nrm, const float *__restrict__ delta,
+                                const uint32_t *__restrict__ tid_sorted, uint32_t T, uint32_t Tpad,
+                                const float *__restrict__ maxes, double c_rnd, float *__restrict__ nprime,
+                                float *__restrict__ snorm, ColMeta *__restrict__ meta) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Tpad) return;
     if (j >= T) {
         nprime[j] = __int_as_float(0x7f800000);
         snorm[j] = 0.0f;
+        meta[j] = ColMeta{0.0f, 0.0f, 0.0f, 0xFFFFFFFFu};
         return;
     }
     const double rho = (double)maxes[0], n = (double)nrm[j];
     nprime[j] = __double2float_rd(n * (1.0 - rho * rho - c_rnd));
-    snorm[j] = __double2float_ru(fmax(sqrt(n), 1.0));
+    const float sj = __double2float_ru(fmax(sqrt(n), 1.0));
+    snorm[j] = sj;
+    meta[j] = ColMeta{nrm[j], delta[j], sj, tid_sorted[j]};
 }
 
 __global__ void wis_tile_smax_kernel(const float *__restrict__ snorm, uint32_t n_tiles, float *__restrict__ tile_smax) {
@@ -264,6 +293,39 @@ __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi,
     if (i < hi) p[i] = v;
 }
 
+// ---- the error bounds in f32 with directed rounding (upper bounds round up, lower bounds down) --------
+struct BoundConsts {
+    float c_acc2;        // 2 c_acc, rounded up
+    float c_rnd;         // rounded up
+    float one_plus_g;    // 1 + g, rounded up
+    float inv_1mg;       // 1 / (1 - g), rounded up
+    float one_m_crnd;    // 1 - c_rnd, rounded down
+    const float *maxes;  // [0] rho
+};
+
+// >= D_ref for the pair behind a stored value v = n'_j - 2 g  (U_ij of the header comment)
+__device__ __forceinline__ float pair_upper(float v, const ColMeta &mi, const ColMeta &mj, float rho2c, const BoundConsts &c) {
+    const float d2 = __fadd_ru(__fadd_ru(v, __fmul_ru(mj.nrm, rho2c)), mi.nrm);
+    const float eps = __fadd_ru(__fmul_ru(__fmul_ru(c.c_acc2, mi.s), mj.s), __fmul_ru(c.c_rnd, __fadd_ru(mi.nrm, mj.nrm)));
+    const float sq = __fsqrt_ru(fmaxf(__fadd_ru(d2, eps), 0.0f));
+    return __fmul_ru(c.one_plus_g, __fadd_ru(__fadd_ru(sq, mi.delta), mj.delta));
+}
+// can the pair still be among the k nearest?  L_ij <= V, written without a sqrt: d2 - eps <= (V' + delta_j)^2
+__device__ __forceinline__ bool pair_alive(float v, const ColMeta &mi, const ColMeta &mj, float rho2c_rd, float vg,
+                                           const BoundConsts &c) {
+    const float d2 = __fadd_rd(__fadd_rd(v, __fmul_rd(mj.nrm, rho2c_rd)), mi.nrm);
+    const float eps = __fadd_ru(__fmul_ru(__fmul_ru(c.c_acc2, mi.s), mj.s), __fmul_ru(c.c_rnd, __fadd_ru(mi.nrm, mj.nrm)));
+    const float w = __fadd_ru(vg, mj.delta);
+    return __fsub_rd(d2, eps) <= __fmul_ru(w, w);
+}
+// V (>= the row's final k-th reference distance) -> V' for the windows, theta and kappa for the sweep test
+__device__ __forceinline__ void bound_to_thresholds(float V, const ColMeta &mi, float rho, const BoundConsts &c, float &vg,
+                                                    float &theta, float &kappa) {
+    vg = __fadd_ru(__fmul_ru(V, c.inv_1mg), mi.delta);
+    theta = __fsub_ru(__fmul_ru(__fmul_ru(vg, vg), 1.0f + 1.0f / 4194304.0f), __fmul_rd(mi.nrm, c.one_m_crnd));
+    kappa = __fmul_ru(__fadd_ru(__fmul_ru(c.c_acc2, mi.s), __fmul_ru(__fmul_ru(2.0f, rho), vg)), 1.0f + 1.0f / 1048576.0f);
+}
+
 // ---- sweep ------------------------------------------------------------------------------------------
 struct SweepArgs {
     const float *nprime;     // [Tpad] n'_j (+inf beyond T), sorted column order
@@ -272,6 +334,13 @@ struct SweepArgs {
     const float *kap;        // [rows] kappa_i
     const uint4 *rng;        // [row blocks] column tiles of this round: [x, y) and [z, w)
     uint32_t T, rows;
+    // first round only (no candidates are stored; the epilogue derives the first bound itself)
+    const ColMeta *meta;     // [Tpad] sorted order
+    const uint32_t *tid_sorted;  // [Tpad] contig of every column (0xFFFFFFFF beyond T)
+    const uint32_t *rows_a;  // [rows] sorted position of every row (nullptr: identity)
+    float *thr_out, *kap_out, *vg_out;
+    uint32_t k, m_sel;       // m_sel-th smallest of each (tile, column quarter) group, 4 n_tiles m_sel >= k
+    BoundConsts bc;
     uint32_t k_mmas;         // K16 slabs per tile that hold data: ceil(S / 16)
     uint32_t n_kblocks;      // ceil(Kp / 64)
     float *cand_val;         // [rows][kCandCap]
@@ -279,6 +348,7 @@ struct SweepArgs {
     uint32_t *cand_cnt;      // [rows]
 };
 
+template <bool FIRST>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
@@ -286,9 +356,11 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint4 rng = a.rng[blockIdx.x];
     const uint32_t n_lo = rng.y - rng.x, n_tiles = n_lo + (rng.w - rng.z);
     if (n_tiles == 0) return;
-    auto tile_at = [&](uint32_t it) { return it < n_lo ? rng.x + it : rng.z + (it - n_lo); };
+    const uint32_t rng_x = rng.x, rng_z = rng.z;
+#define CNVB_TILE_AT(it) ((it) < n_lo ? rng_x + (it) : rng_z + ((it) - n_lo))
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
+    __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA (FIRST: values behind s_v0)
+    __shared__ uint32_t s_v0[kTileRows];   // FIRST: largest group bound of the row (bits of a non-negative float)
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -302,8 +374,10 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blockIdx.x * kTileRows;  // position in the sorted row list
-    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
-        s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
+    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
+        s_cnt[t] = (!FIRST && row0 + t < a.rows) ? a.cand_cnt[row0 + t] : 0u;
+        s_v0[t] = 0u;
+    }
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
@@ -338,7 +412,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 (int32_t)(row0 + h * 128));
             uint32_t st = 0, ph = 0;
             for (uint32_t it = 0; it < n_tiles; ++it) {
-                const int32_t j0 = (int32_t)(tile_at(it) * kTileCols);
+                const int32_t j0 = (int32_t)(CNVB_TILE_AT(it) * kTileCols);
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                     mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
                     mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
@@ -394,6 +468,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
         uint32_t rloc[2];
         float thr[2], kap[2];
+        ColMeta mrow[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             rloc[h] = h * 128 + q * 32 + lane;  // row within the CTA's 256
@@ -401,10 +476,13 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const bool live = row < a.rows;
             thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
             kap[h] = live ? a.kap[row] : 0.0f;
+            if (FIRST) mrow[h] = live ? a.meta[a.rows_a ? a.rows_a[row] : row] : ColMeta{0.0f, 0.0f, 0.0f, 0xFFFFFFFEu};
         }
+        const float rho = FIRST ? a.bc.maxes[0] : 0.0f;
+        const float rho2c = FIRST ? __fadd_ru(__fmul_ru(rho, rho), a.bc.c_rnd) : 0.0f;
         uint32_t as = 0, aph = 0;
         for (uint32_t it = 0; it < n_tiles; ++it) {
-            const uint32_t tile = tile_at(it);
+            const uint32_t tile = CNVB_TILE_AT(it);
             const uint32_t j0 = tile * kTileCols + cpart * 32u;
             // column operands of this warp's 32 columns (same addresses for all lanes: L1 broadcast)
             float nj[32];
@@ -420,12 +498,55 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
             const float smax = __ldg(a.tile_smax + tile);
+            uint32_t tj[FIRST ? 32 : 1];
+            if (FIRST) {
+                const uint4 *tj4 = reinterpret_cast<const uint4 *>(a.tid_sorted + j0);
+#pragma unroll
+                for (int g4 = 0; g4 < (FIRST ? 8 : 0); ++g4) {
+                    const uint4 v = __ldg(tj4 + g4);
+                    tj[4 * g4 + 0] = v.x;
+                    tj[4 * g4 + 1] = v.y;
+                    tj[4 * g4 + 2] = v.z;
+                    tj[4 * g4 + 3] = v.w;
+                }
+            }
             mbar_wait(bar_acc_full + 8 * as, aph);
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
+                if (FIRST) {
+                    // first bound without storing anything: the m-th smallest value of this row's 32
+                    // columns of the tile.  Groups are disjoint, so the largest of the groups' m-th
+                    // smallest upper bounds has at least (groups x m) >= k pairs at or below it.
+                    const float inf = __int_as_float(0x7f800000);
+                    float top[8];
+#pragma unroll
+                    for (int t8 = 0; t8 < 8; ++t8) top[t8] = inf;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float v = tj[c] == mrow[h].tid ? inf : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+#pragma unroll
+                        for (int t8 = 0; t8 < 8; ++t8) {  // sorted insertion
+                            const float lo = fminf(top[t8], v);
+                            v = fmaxf(top[t8], v);
+                            top[t8] = lo;
+                        }
+                    }
+                    float vm = top[0];
+#pragma unroll
+                    for (int t8 = 1; t8 < 8; ++t8) vm = (uint32_t)t8 < a.m_sel ? top[t8] : vm;
+                    if (vm < inf) {
+                        // every column of the tile has n_j <= smax^2, s_j <= smax, delta_j <= rho smax
+                        const float smax2 = __fmul_ru(smax, smax);
+                        const ColMeta mt{smax2, __fmul_ru(rho, smax), smax, 0u};
+                        const float U = pair_upper(vm, mrow[h], mt, rho2c, a.bc);
+                        atomicMax(&s_v0[rloc[h]], __float_as_uint(U));
+                        atomicAdd(&s_cnt[rloc[h]], a.m_sel);
+                    }
+                    continue;
+                }
                 // keep iff  n'_j - 2 g - kappa_i s_j <= theta_i;  sufficient: n'_j - 2 g <= theta_i + kappa_i smax
                 const float rhs = fmaf(kap[h], smax, thr[h]);
                 const uint32_t row = row0 + rloc[h];
@@ -477,13 +598,26 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
-        if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
+    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
+        if (row0 + t >= a.rows) continue;
+        if (!FIRST) {
+            a.cand_cnt[row0 + t] = s_cnt[t];
+        } else if (s_cnt[t] >= a.k) {  // enough groups reported: a first bound exists
+            const ColMeta mi = a.meta[a.rows_a ? a.rows_a[row0 + t] : row0 + t];
+            float vg, theta, kappa;
+            bound_to_thresholds(__uint_as_float(s_v0[t]), mi, a.bc.maxes[0], a.bc, vg, theta, kappa);
+            a.vg_out[row0 + t] = vg;
+            a.thr_out[row0 + t] = theta;
+            a.kap_out[row0 + t] = kappa;
+        }
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
+
+#undef CNVB_TILE_AT
 
 // ---- windows: which column tiles a block of rows still has to see --------------------------------
 struct WindowArgs {
@@ -550,15 +684,15 @@ __global__ void __launch_bounds__(kTileRows) wis_window_kernel(WindowArgs a) {
         const uint32_t ub = upper_bound_f32(a.psorted, a.T, hi);
         const uint32_t req_hi = min(a.n_tiles, (ub + kTileCols - 1) / kTileCols);
         if (a.round == 0) {
-            // 2 (1 + w0) tiles centred on the block (every pair of this window is appended, so its
-            // size is bounded by the candidate buffer; rows of a sparse subset see an off-centre
-            // window, which only loosens their first bound)
-            const uint32_t c = (req_lo + req_hi) >> 1, half = 1u + a.w0;
+            // 2 (1 + w0) tiles centred on the block, for the first bound only (rows of a sparse
+            // subset see an off-centre window, which merely loosens that bound); nothing is stored
+            // in this round, so no tile counts as swept yet
+            const uint32_t c = min((req_lo + req_hi) >> 1, a.n_tiles), half = 1u + a.w0;
             const uint32_t size = min(a.n_tiles, 2u * half);
             out.x = c > half ? c - half : 0u;
             if (out.x + size > a.n_tiles) out.x = a.n_tiles - size;
             out.y = out.x + size;
-            dn = make_uint2(out.x, out.y);
+            dn = make_uint2(c, c);
         } else {
             const uint32_t lim_lo = dn.x > a.grow ? dn.x - a.grow : 0u;
             const uint32_t lim_hi = min(a.n_tiles, dn.y + a.grow);
@@ -577,95 +711,147 @@ __global__ void __launch_bounds__(kTileRows) wis_window_kernel(WindowArgs a) {
 // ---- compaction: k-th smallest candidate value per row, new threshold -----------------------------
 struct CompactArgs {
     float *cand_val;         // stored v = n'_j - 2 g
-    uint32_t *cand_idx;
+    uint32_t *cand_idx;      // sorted column position
     uint32_t *cand_cnt;
     float *thr, *kap;
     uint32_t *overflow;      // [rows] sticky flag
     uint32_t *seen;          // [rows] list length after the row's last compaction (unchanged lists are skipped)
     float *vg;               // [rows] out: V'_i for the window kernel
     const uint32_t *rows_a;  // [rows] sorted position of every row (nullptr: identity)
-    const float *nrm, *delta;  // indexed by sorted position
-    const float *maxes;      // [0] rho
-    const uint32_t *tid;     // contig ids by sorted position: same-contig pairs (incl. the row itself) are not candidates
+    const ColMeta *meta;     // [Tpad] sorted order
     uint32_t rows, k;
-    double c_acc, c_rnd, g_ref;
+    BoundConsts bc;
 };
 
-// per-pair bounds on the reference distance from a stored candidate value v = n'_j - 2 g:
-//   U_ij = (1+g)(sqrt(d2 + eps) + delta_i + delta_j) >= D_ref,   and   D_ref > V  is certain when
-//   d2 - eps > (V/(1-g) + delta_i + delta_j)^2   (the lower bound L_ij > V, written without a sqrt)
-__device__ __forceinline__ void pair_terms(const CompactArgs &a, double v, double ni, double rho, uint32_t j,
-                                           double &d2, double &eps, double &dj) {
-    const double nj = (double)a.nrm[j];
-    dj = (double)a.delta[j];
-    d2 = v + nj * (rho * rho + a.c_rnd) + ni;  // undo n'_j: approximate |h_i - h_j|^2
-    eps = 2.0 * a.c_acc * sqrt(ni * nj) + a.c_rnd * (ni + nj);
+constexpr uint32_t kCompactWarps = 8;
+constexpr uint32_t kKeyRegs = 16;  // candidates per lane whose keys stay in registers (lists up to 512)
+
+// the bin (of 256, warp-private in shared memory) that holds the want-th smallest entry; returns the
+// bin and leaves in `want` the rank inside it
+__device__ __forceinline__ uint32_t hist_find(const uint32_t *hist, uint32_t &want) {
+    const uint32_t lane = lane_id();
+    uint32_t c[8], sum = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        c[t] = hist[8 * lane + t];
+        sum += c[t];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += u;
+    }
+    const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, incl >= want)) - 1;  // want <= total by construction
+    uint32_t bin = 0, rest = 0;
+    if (lane == owner) {
+        uint32_t w = want - (incl - sum);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (w > c[t] && t < 7) {
+                w -= c[t];
+            } else {
+                bin = 8 * lane + t;
+                rest = w;
+                break;
+            }
+        }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, owner);
+    want = __shfl_sync(0xffffffffu, rest, owner);
+    return bin;
 }
 
-// KPER = candidates per lane held in registers; rows with more than n_min candidates only (two
-// launches by list length, KPER 16 / 32 / 64, so that short lists do not pay for the longest one)
-template <uint32_t KPER>
-__global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_t n_min) {
+// One warp per row: upper bounds U_ij of all stored pairs, V = (an upper bound of) the k-th smallest of
+// them by a two-level 256-bin histogram over the key range, then only the pairs with L_ij <= V stay.
+__global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(CompactArgs a) {
+    __shared__ uint32_t s_hist[kCompactWarps][256];
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (r >= a.rows) return;
-    uint32_t n = a.cand_cnt[r];
+    const uint32_t n = a.cand_cnt[r];
     if (n > kCandCap) {
         if (lane == 0) {
             a.overflow[r] = 1u;
             a.cand_cnt[r] = 0u;
+            a.seen[r] = 0u;
             a.thr[r] = -__int_as_float(0x7f800000);  // stop collecting: the row is recomputed exactly
             a.kap[r] = 0.0f;
         }
         return;
     }
-    if (a.overflow[r]) return;
-    if (n <= n_min || n > 32u * KPER) return;  // the other launch's rows
-    if (n == a.seen[r]) return;                // nothing new since the last compaction
+    if (a.overflow[r] || n == a.seen[r]) return;  // nothing new since the last compaction
+    uint32_t *hist = s_hist[threadIdx.x >> 5];
     float *cv = a.cand_val + (size_t)r * kCandCap;
     uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
-    const uint32_t row = a.rows_a ? a.rows_a[r] : r;
-    const double ni = (double)a.nrm[row], di = (double)a.delta[row], rho = (double)a.maxes[0];
-    const uint32_t ti = a.tid[row];
-    constexpr uint32_t kPer = KPER;
-    uint32_t key[kPer];  // upper bounds U_ij (f32, rounded up) as ordered keys; all ones = not a candidate
-    uint32_t n_valid = 0;
+    const ColMeta mi = a.meta[a.rows_a ? a.rows_a[r] : r];
+    const float rho = a.bc.maxes[0];
+    const float rho2c = __fadd_ru(__fmul_ru(rho, rho), a.bc.c_rnd), rho2c_rd = __fadd_rd(__fmul_rd(rho, rho), a.bc.c_rnd);
+    // key of candidate c: ordered bits of U_ij, all ones for same-contig pairs (never candidates)
+    auto key_of = [&](uint32_t c) -> uint32_t {
+        const ColMeta mj = a.meta[ci[c]];
+        if (mj.tid == mi.tid) return 0xFFFFFFFFu;
+        return __float_as_uint(pair_upper(cv[c], mi, mj, rho2c, a.bc)) | 0x80000000u;  // U >= 0
+    };
+    uint32_t key[kKeyRegs];
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u, n_valid = 0;
 #pragma unroll
-    for (uint32_t e = 0; e < kPer; ++e) {
+    for (uint32_t e = 0; e < kKeyRegs; ++e) {
         const uint32_t c = e * 32 + lane;
-        key[e] = 0xFFFFFFFFu;
-        if (c < n) {
-            const uint32_t j = ci[c];
-            if (a.tid[j] != ti) {
-                double d2, eps, dj;
-                pair_terms(a, (double)cv[c], ni, rho, j, d2, eps, dj);
-                const double U = (1.0 + a.g_ref) * (sqrt(fmax(d2 + eps, 0.0)) + di + dj);
-                key[e] = f32_key(__double2float_ru(U));
-                n_valid += 1;
-            }
+        key[e] = c < n ? key_of(c) : 0xFFFFFFFFu;
+        if (key[e] != 0xFFFFFFFFu) {
+            kmin = min(kmin, key[e]);
+            kmax = max(kmax, key[e]);
+            n_valid += 1;
+        }
+    }
+    for (uint32_t c = kKeyRegs * 32 + lane; c < n; c += 32) {  // long lists: keys are recomputed per pass
+        const uint32_t kk = key_of(c);
+        if (kk != 0xFFFFFFFFu) {
+            kmin = min(kmin, kk);
+            kmax = max(kmax, kk);
+            n_valid += 1;
         }
     }
     n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
     const bool have_bound = n_valid >= a.k;  // otherwise: only drop the same-contig entries
-    // bit-descent select of the k-th smallest key.  U >= 0, so bit 31 of every key is set; the
-    // lowest 6 bits are not resolved but set, which only rounds V up (by < 2^-17 relative): any
-    // upper bound of the k-th smallest U is a valid V.
-    uint32_t prefix = 0x80000000u, want = a.k;
-    for (int bit = 30; bit >= 6; --bit) {
-        const uint32_t mask = 0xFFFFFFFFu << (bit + 1);
-        uint32_t zeros = 0;
+    float vg = __int_as_float(0x7f800000), theta = vg, kappa = 0.0f;
+    if (have_bound) {
+        // quantise the key range to 16 bits, select in two 8-bit levels
+        const uint32_t span = kmax - kmin;
+        const uint32_t sh = span >> 16 ? (32u - (uint32_t)__clz(span)) - 16u : 0u;
+        uint32_t want = a.k;
+        for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0u;
+        __syncwarp();
 #pragma unroll
-        for (uint32_t e = 0; e < kPer; ++e)
-            zeros += ((key[e] & mask) == prefix && !((key[e] >> bit) & 1u)) ? 1u : 0u;  // (padding keys are all ones)
-        zeros = __reduce_add_sync(0xffffffffu, zeros);
-        if (want > zeros) {
-            want -= zeros;
-            prefix |= 1u << bit;
+        for (uint32_t e = 0; e < kKeyRegs; ++e)
+            if (key[e] != 0xFFFFFFFFu) atomicAdd(&hist[((key[e] - kmin) >> sh) >> 8], 1u);
+        for (uint32_t c = kKeyRegs * 32 + lane; c < n; c += 32) {
+            const uint32_t kk = key_of(c);
+            if (kk != 0xFFFFFFFFu) atomicAdd(&hist[((kk - kmin) >> sh) >> 8], 1u);
         }
+        __syncwarp();
+        const uint32_t b1 = hist_find(hist, want);
+        __syncwarp();
+        for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (uint32_t e = 0; e < kKeyRegs; ++e) {
+            const uint32_t qk = (key[e] - kmin) >> sh;
+            if (key[e] != 0xFFFFFFFFu && (qk >> 8) == b1) atomicAdd(&hist[qk & 255u], 1u);
+        }
+        for (uint32_t c = kKeyRegs * 32 + lane; c < n; c += 32) {
+            const uint32_t kk = key_of(c), qk = (kk - kmin) >> sh;
+            if (kk != 0xFFFFFFFFu && (qk >> 8) == b1) atomicAdd(&hist[qk & 255u], 1u);
+        }
+        __syncwarp();
+        const uint32_t b2 = hist_find(hist, want);
+        __syncwarp();
+        // largest key of the selected fine bin: >= the k-th smallest U, hence >= the row's final k-th distance
+        const uint32_t vkey = min(kmax, kmin + ((((b1 << 8) | b2) + 1u) << sh) - 1u);
+        bound_to_thresholds(__uint_as_float(vkey & 0x7FFFFFFFu), mi, rho, a.bc, vg, theta, kappa);
     }
-    prefix |= 63u;
-    // >= the final k-th reference distance of this row (+inf while fewer than k candidates exist)
-    const double V = have_bound ? (double)key_f32(prefix) : (double)__int_as_float(0x7f800000);
-    const double Vg = V / (1.0 - a.g_ref) + di;
     // keep exactly the pairs that can still be among the top k
     uint32_t kept = 0;
     for (uint32_t base = 0; base < n; base += 32) {
@@ -676,12 +862,8 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         if (c < n) {
             v = cv[c];
             j = ci[c];
-            if (a.tid[j] != ti) {
-                double d2, eps, dj;
-                pair_terms(a, (double)v, ni, rho, j, d2, eps, dj);
-                const double w = Vg + dj;
-                keep = !have_bound || d2 - eps <= w * w;
-            }
+            const ColMeta mj = a.meta[j];
+            keep = mj.tid != mi.tid && (!have_bound || pair_alive(v, mi, mj, rho2c_rd, vg, a.bc));
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
@@ -694,16 +876,12 @@ __global__ void __launch_bounds__(256) wis_compact_kernel(CompactArgs a, uint32_
         __syncwarp();
     }
     if (lane == 0) {
-        // sweep test for the columns still to come (sufficient form, see the header comment)
-        const double Vp = Vg;
-        const double kappa = 2.0 * a.c_acc * sqrt(ni) + 2.0 * rho * Vp;
-        const double theta = Vp * Vp * (1.0 + 1e-9) - ni * (1.0 - a.c_rnd);
         a.cand_cnt[r] = kept;
         a.seen[r] = kept;
         if (have_bound) {
-            a.thr[r] = __double2float_ru(theta);
-            a.kap[r] = __double2float_ru(kappa * (1.0 + 1e-6));
-            a.vg[r] = __double2float_ru(Vg);
+            a.thr[r] = theta;
+            a.kap[r] = kappa;
+            a.vg[r] = vg;
         }
     }
 }
@@ -837,6 +1015,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
              *pkey = nullptr, *pkey_sorted = nullptr, *ident = nullptr, *perm = nullptr, *tid_sorted = nullptr,
              *rows_a = nullptr, *n_sel = nullptr;
     uint8_t *rflag = nullptr;
+    float *cmean = nullptr;
+    ColMeta *meta = nullptr;
     uint4 *rng = nullptr;
     uint2 *done = nullptr;
     unsigned long long *counters = nullptr;  // [0] tiles swept | [1] pairs re-scored
@@ -858,9 +1038,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(rows, &seen)) != cudaSuccess ||
         (e = g.alloc(rows + 1, &ovf_list)) != cudaSuccess || (e = g.alloc(T, &pkey)) != cudaSuccess ||
         (e = g.alloc(T, &pkey_sorted)) != cudaSuccess || (e = g.alloc(T, &ident)) != cudaSuccess ||
-        (e = g.alloc(T, &perm)) != cudaSuccess || (e = g.alloc(T, &tid_sorted)) != cudaSuccess ||
+        (e = g.alloc(T, &perm)) != cudaSuccess || (e = g.alloc(Tpad, &tid_sorted)) != cudaSuccess ||
         (e = g.alloc(row_blocks, &rng)) != cudaSuccess || (e = g.alloc(row_blocks, &done)) != cudaSuccess ||
-        (e = g.alloc(2, &counters)) != cudaSuccess ||
+        (e = g.alloc(2, &counters)) != cudaSuccess || (e = g.alloc(S, &cmean)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &meta)) != cudaSuccess ||
         (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
@@ -874,7 +1055,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     cudaMemsetAsync(seen, 0, rows * 4, st);
     cudaMemsetAsync(ovf_list, 0, (rows + 1) * 4, st);
     cudaMemsetAsync(counters, 0, 16, st);
-    wis_colsum_kernel<<<std::min<uint32_t>(T, (uint32_t)ctx->sm_count * 4), 128, 0, st>>>(dX, T, S, colsum, scal);
+    wis_colsum_kernel<<<std::min<uint32_t>((T + 7) / 8, (uint32_t)ctx->sm_count * 8), 256, 0, st>>>(dX, T, S, colsum, scal);
     CNVB_LAUNCHED(ctx, "wis_colsum_kernel");
     float absmax = 0.0f;
     CNVB_CUDA(ctx, cudaMemcpyAsync(&absmax, scal, 4, cudaMemcpyDeviceToHost, st), "reading the panel range");
@@ -883,19 +1064,22 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     int ex = 0;
     frexpf(absmax > 0.0f ? 2.0f * absmax : 1.0f, &ex);
     const float scale = ldexpf(1.0f, 13 - ex);
+    wis_cmean_kernel<<<(S + 127) / 128, 128, 0, st>>>(colsum, T, S, cmean);
+    CNVB_LAUNCHED(ctx, "wis_cmean_kernel");
     // sort the targets by their projection on the all-ones direction
-    wis_proj_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, T, S, colsum, scale, pkey, ident, scal + 2);
+    wis_proj_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, T, S, cmean, scale, pkey, ident, scal + 2);
     CNVB_LAUNCHED(ctx, "wis_proj_kernel");
     CNVB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, st),
               "sorting the projections");
     ctx->launches += 1;
     if (Tpad > T) cudaMemsetAsync(H + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
-    wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, dtid, T, S, Kp, colsum, scale, perm, pkey_sorted, H, nrm, delta,
+    wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, dtid, T, S, Kp, cmean, scale, perm, pkey_sorted, H, nrm, delta,
                                                  tid_sorted, psorted, scal + 1);
     CNVB_LAUNCHED(ctx, "wis_pack_kernel");
     const double c_acc = (double)Kp / 8388608.0;  // fp32 accumulation of Kp exact products, truncating adds
     const double c_rnd = 8.0 / 16777216.0;        // f32 rounding of norms and of the epilogue FFMAs
-    wis_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nrm, T, Tpad, scal + 1, c_rnd, nprime, snorm);
+    if (Tpad > T) cudaMemsetAsync(tid_sorted + T, 0xFF, (size_t)(Tpad - T) * 4, st);
+    wis_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nrm, delta, tid_sorted, T, Tpad, scal + 1, c_rnd, nprime, snorm, meta);
     CNVB_LAUNCHED(ctx, "wis_cols_kernel");
     wis_tile_smax_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(snorm, n_tiles, tile_smax);
     CNVB_LAUNCHED(ctx, "wis_tile_smax_kernel");
@@ -922,8 +1106,22 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
-    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
               "smem opt-in");
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+              "smem opt-in");
+    BoundConsts bc{};
+    {
+        const double g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
+        auto up = [](double v) { return std::nextafterf((float)v, INFINITY); };
+        auto down = [](double v) { return std::nextafterf((float)v, -INFINITY); };
+        bc.c_acc2 = up(2.0 * c_acc);
+        bc.c_rnd = up(c_rnd);
+        bc.one_plus_g = up(1.0 + g_ref);
+        bc.inv_1mg = up(1.0 / (1.0 - g_ref));
+        bc.one_m_crnd = down(1.0 - c_rnd);
+        bc.maxes = scal + 1;
+    }
     SweepArgs sa{};
     sa.nprime = nprime;
     sa.tile_smax = tile_smax;
@@ -932,6 +1130,14 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.rng = rng;
     sa.T = T;
     sa.rows = rows;
+    sa.meta = meta;
+    sa.tid_sorted = tid_sorted;
+    sa.rows_a = rows_a;
+    sa.thr_out = thr;
+    sa.kap_out = kap;
+    sa.vg_out = vg;
+    sa.k = k;
+    sa.bc = bc;
     sa.k_mmas = (S + 15) / 16;
     sa.n_kblocks = Kp / kKBlock;
     sa.cand_val = cand_val;
@@ -947,15 +1153,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.seen = seen;
     ca.vg = vg;
     ca.rows_a = rows_a;
-    ca.nrm = nrm;
-    ca.delta = delta;
-    ca.maxes = scal + 1;
-    ca.tid = tid_sorted;
+    ca.meta = meta;
     ca.rows = rows;
     ca.k = k;
-    ca.c_acc = c_acc;
-    ca.c_rnd = c_rnd;
-    ca.g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
+    ca.bc = bc;
     WindowArgs wa{};
     wa.psorted = psorted;
     wa.rows_a = rows_a;
@@ -964,36 +1165,59 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     wa.T = T;
     wa.n_tiles = n_tiles;
     wa.rows = rows;
-    // the first window holds max(768, 3k) columns (all of them are appended: at most kCandCap)
-    wa.w0 = std::min<uint32_t>(7, std::max<uint32_t>(2, ((3 * k + kTileCols - 1) / kTileCols - 2 + 1) / 2));
+    // first window: 2 (1 + w0) tiles; every (tile, column quarter) group contributes its m-th smallest
+    // value (m <= 8) to the first bound, so 4 x tiles x m >= k
+    wa.w0 = std::min<uint32_t>(7, std::max<uint32_t>(2, (k + 63) / 64 - 1));
+    const uint32_t tiles0 = std::min<uint32_t>(n_tiles, 2 * (1 + wa.w0));
+    sa.m_sel = (k + 4 * tiles0 - 1) / (4 * tiles0);
     // f32 rounding of the projections (2 x half an ulp of the largest) plus their f64 summation error
     wa.slack = pabs * (1.0f / 4194304.0f) + 1e-30f;
     wa.rng = rng;
     wa.done = done;
     wa.tiles_swept = counters;
 
-    // windows grow x4 per round around the block's own position until they span every tile
-    uint32_t half = 1 + wa.w0;
-    for (uint32_t round = 0;; ++round) {
-        wa.round = round;
-        wa.grow = 3 * half;
+    // round 0: a first bound per row from the window around its own position; nothing is stored.
+    // (Too few columns for that -- tiny panels -- : the first real round collects everything.)
+    wa.round = 0;
+    wa.grow = 0;
+    if (sa.m_sel <= 8) {
         wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
         CNVB_LAUNCHED(ctx, "wis_window_kernel");
+        KernelSpan span(ctx, "wis_sweep_kernel");
+        wis_sweep_kernel<true><<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+        CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
+    } else {
+        wa.w0 = 0;  // only marks the centre
+        wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
+        CNVB_LAUNCHED(ctx, "wis_window_kernel");
+    }
+    // rounds 1..: windows reach 4^r (1 + w0) tiles either side of the block's own position, never
+    // beyond what the rows' bounds still allow; stop when a round has nothing left to sweep
+    unsigned long long tiles_before = 0;
+    uint32_t half_prev = 0, half = 4 * (tiles0 / 2 ? tiles0 / 2 : 1);
+    for (uint32_t round = 1;; ++round) {
+        wa.round = round;
+        wa.grow = half - half_prev;
+        wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
+        CNVB_LAUNCHED(ctx, "wis_window_kernel");
+        unsigned long long tiles_now = 0;
+        CNVB_CUDA(ctx, cudaMemcpyAsync(&tiles_now, counters, 8, cudaMemcpyDeviceToHost, st), "reading the round size");
+        CNVB_CUDA(ctx, cudaStreamSynchronize(st), "reading the round size");
+        if (tiles_now == tiles_before && round > 1) break;
+        tiles_before = tiles_now;
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
-            wis_sweep_kernel<<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+            wis_sweep_kernel<false><<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         {
             KernelSpan span(ctx, "wis_compact_kernel");
-            wis_compact_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(ca, 0u);
-            wis_compact_kernel<32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 512u);
-            wis_compact_kernel<kCandCap / 32><<<(rows + 7) / 8, 256, 0, st>>>(ca, 1024u);
+            wis_compact_kernel<<<(rows + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, st>>>(ca);
         }
         CNVB_LAUNCHED(ctx, "wis_compact_kernel");
-        if (round > 0) half *= 4;
-        if (half >= n_tiles && round > 0) break;
-        if (n_tiles <= 2 * (1 + wa.w0)) break;  // the first window already spans everything
+        if (half_prev >= n_tiles) break;  // the last round was allowed to reach every tile
+        half_prev = half;
+        half *= 4;
     }
     const size_t rsmem = (((size_t)S + 3) & ~(size_t)3) * 4 + kCandCap * 4;
     CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem),
@@ -1015,7 +1239,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");
     ctx->wis_stats[1] = n_ovf;
     ctx->wis_stats[2] = h_cnt[1];
-    ctx->wis_stats[3] = h_cnt[0];
+    ctx->wis_stats[3] = h_cnt[0];  // (includes the first window, swept twice)
     if (n_ovf) CNVB_TRY(run_rows_exact(ctx, dX, dtid, T, S, k, ovf_list + 1, n_ovf, row_begin, d_dist, d_idx));
     CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");  // work space is released on return
     return 0;
