@@ -56,6 +56,7 @@ constexpr uint32_t kMaxKBlocks = 2;   // A stays resident: Kp <= 128
 constexpr uint32_t kStages = 8;       // B ring: 8 x 16 KB
 constexpr uint32_t kTileBytes = 128 * kKBlock * 2;  // 16 KB: 128 rows x 64 fp16
 constexpr uint32_t kCandCap = 2048;   // candidate buffer entries per row
+constexpr uint32_t kMaxTensorK = 384;  // 32 x 16 first-window candidates must hold k after same-contig drops
 constexpr uint32_t kEpiWarps = 16;     // 4 per TMEM lane quarter, each a quarter of the tile's columns
 constexpr uint32_t kSweepThreads = (4 + kEpiWarps) * 32;
 
@@ -334,13 +335,9 @@ struct SweepArgs {
     const float *kap;        // [rows] kappa_i
     const uint4 *rng;        // [row blocks] column tiles of this round: [x, y) and [z, w)
     uint32_t T, rows;
-    // first round only (no candidates are stored; the epilogue derives the first bound itself)
-    const ColMeta *meta;     // [Tpad] sorted order
+    // first round only
     const uint32_t *tid_sorted;  // [Tpad] contig of every column (0xFFFFFFFF beyond T)
     const uint32_t *rows_a;  // [rows] sorted position of every row (nullptr: identity)
-    float *thr_out, *kap_out, *vg_out;
-    uint32_t k, m_sel;       // m_sel-th smallest of each (tile, column quarter) group, 4 n_tiles m_sel >= k
-    BoundConsts bc;
     uint32_t k_mmas;         // K16 slabs per tile that hold data: ceil(S / 16)
     uint32_t n_kblocks;      // ceil(Kp / 64)
     float *cand_val;         // [rows][kCandCap]
@@ -359,8 +356,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t rng_x = rng.x, rng_z = rng.z;
 #define CNVB_TILE_AT(it) ((it) < n_lo ? rng_x + (it) : rng_z + ((it) - n_lo))
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA (FIRST: values behind s_v0)
-    __shared__ uint32_t s_v0[kTileRows];   // FIRST: largest group bound of the row (bits of a non-negative float)
+    __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -374,10 +370,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blockIdx.x * kTileRows;  // position in the sorted row list
-    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
-        s_cnt[t] = (!FIRST && row0 + t < a.rows) ? a.cand_cnt[row0 + t] : 0u;
-        s_v0[t] = 0u;
-    }
+    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
+        s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
@@ -468,7 +462,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
         uint32_t rloc[2];
         float thr[2], kap[2];
-        ColMeta mrow[2];
+        uint32_t trow[2];  // FIRST: contig of the row (a value no column has for rows beyond the end)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             rloc[h] = h * 128 + q * 32 + lane;  // row within the CTA's 256
@@ -476,10 +470,9 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const bool live = row < a.rows;
             thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
             kap[h] = live ? a.kap[row] : 0.0f;
-            if (FIRST) mrow[h] = live ? a.meta[a.rows_a ? a.rows_a[row] : row] : ColMeta{0.0f, 0.0f, 0.0f, 0xFFFFFFFEu};
+            trow[h] = 0xFFFFFFFEu;
+            if (FIRST && live) trow[h] = a.tid_sorted[a.rows_a ? a.rows_a[row] : row];
         }
-        const float rho = FIRST ? a.bc.maxes[0] : 0.0f;
-        const float rho2c = FIRST ? __fadd_ru(__fmul_ru(rho, rho), a.bc.c_rnd) : 0.0f;
         uint32_t as = 0, aph = 0;
         for (uint32_t it = 0; it < n_tiles; ++it) {
             const uint32_t tile = CNVB_TILE_AT(it);
@@ -517,16 +510,17 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
                 if (FIRST) {
-                    // first bound without storing anything: the m-th smallest value of this row's 32
-                    // columns of the tile.  Groups are disjoint, so the largest of the groups' m-th
-                    // smallest upper bounds has at least (groups x m) >= k pairs at or below it.
+                    // First window, no bound yet: store only the 8 smallest values of this row's 32
+                    // columns (same-contig columns excluded).  The k-th smallest upper bound among the
+                    // stored ones is a valid -- and nearly exact -- first bound; the lists are thrown
+                    // away after it has been derived and the window is swept again with the bound.
                     const float inf = __int_as_float(0x7f800000);
                     float top[8];
 #pragma unroll
                     for (int t8 = 0; t8 < 8; ++t8) top[t8] = inf;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        float v = tj[c] == mrow[h].tid ? inf : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                        float v = tj[c] == trow[h] ? inf : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
 #pragma unroll
                         for (int t8 = 0; t8 < 8; ++t8) {  // sorted insertion
                             const float lo = fminf(top[t8], v);
@@ -534,16 +528,21 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             top[t8] = lo;
                         }
                     }
-                    float vm = top[0];
+                    const uint32_t row = row0 + rloc[h];
+                    float *cv = a.cand_val + (size_t)row * kCandCap;
+                    uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
+                    if (top[0] < inf && row < a.rows) {
 #pragma unroll
-                    for (int t8 = 1; t8 < 8; ++t8) vm = (uint32_t)t8 < a.m_sel ? top[t8] : vm;
-                    if (vm < inf) {
-                        // every column of the tile has n_j <= smax^2, s_j <= smax, delta_j <= rho smax
-                        const float smax2 = __fmul_ru(smax, smax);
-                        const ColMeta mt{smax2, __fmul_ru(rho, smax), smax, 0u};
-                        const float U = pair_upper(vm, mrow[h], mt, rho2c, a.bc);
-                        atomicMax(&s_v0[rloc[h]], __float_as_uint(U));
-                        atomicAdd(&s_cnt[rloc[h]], a.m_sel);
+                        for (int c = 0; c < 32; ++c) {
+                            const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                            if (v <= top[7] && tj[c] != trow[h]) {
+                                const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);
+                                if (slot < kCandCap) {
+                                    cv[slot] = v;
+                                    ci[slot] = j0 + c;
+                                }
+                            }
+                        }
                     }
                     continue;
                 }
@@ -598,19 +597,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
-        if (row0 + t >= a.rows) continue;
-        if (!FIRST) {
-            a.cand_cnt[row0 + t] = s_cnt[t];
-        } else if (s_cnt[t] >= a.k) {  // enough groups reported: a first bound exists
-            const ColMeta mi = a.meta[a.rows_a ? a.rows_a[row0 + t] : row0 + t];
-            float vg, theta, kappa;
-            bound_to_thresholds(__uint_as_float(s_v0[t]), mi, a.bc.maxes[0], a.bc, vg, theta, kappa);
-            a.vg_out[row0 + t] = vg;
-            a.thr_out[row0 + t] = theta;
-            a.kap_out[row0 + t] = kappa;
-        }
-    }
+    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
+        if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -720,6 +708,7 @@ struct CompactArgs {
     const uint32_t *rows_a;  // [rows] sorted position of every row (nullptr: identity)
     const ColMeta *meta;     // [Tpad] sorted order
     uint32_t rows, k;
+    uint32_t discard;        // first round: derive the bound, then drop the list (the window is swept again)
     BoundConsts bc;
 };
 
@@ -854,7 +843,7 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
     }
     // keep exactly the pairs that can still be among the top k
     uint32_t kept = 0;
-    for (uint32_t base = 0; base < n; base += 32) {
+    for (uint32_t base = 0; base < (a.discard ? 0u : n); base += 32) {
         const uint32_t c = base + lane;
         float v = 0.0f;
         uint32_t j = 0;
@@ -999,7 +988,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (Kp > kMaxKBlocks * kKBlock)
         return fail(ctx, CNVB_ERR_INVALID, "tensor engine: more than %u samples are not supported yet; use the exact engine",
                     kMaxKBlocks * kKBlock);
-    if (k > kCandCap / 4) return fail(ctx, CNVB_ERR_INVALID, "tensor engine: max_ref_targets > %u", kCandCap / 4);
+    if (k > kMaxTensorK) return fail(ctx, CNVB_ERR_INVALID, "tensor engine: max_ref_targets > %u", kMaxTensorK);
     const uint32_t n_tiles = (T + kTileCols - 1) / kTileCols;
     const uint32_t Tpad = n_tiles * kTileCols;
     const bool subset = rows != T;
@@ -1130,14 +1119,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.rng = rng;
     sa.T = T;
     sa.rows = rows;
-    sa.meta = meta;
     sa.tid_sorted = tid_sorted;
     sa.rows_a = rows_a;
-    sa.thr_out = thr;
-    sa.kap_out = kap;
-    sa.vg_out = vg;
-    sa.k = k;
-    sa.bc = bc;
     sa.k_mmas = (S + 15) / 16;
     sa.n_kblocks = Kp / kKBlock;
     sa.cand_val = cand_val;
@@ -1165,31 +1148,35 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     wa.T = T;
     wa.n_tiles = n_tiles;
     wa.rows = rows;
-    // first window: 2 (1 + w0) tiles; every (tile, column quarter) group contributes its m-th smallest
-    // value (m <= 8) to the first bound, so 4 x tiles x m >= k
-    wa.w0 = std::min<uint32_t>(7, std::max<uint32_t>(2, (k + 63) / 64 - 1));
+    // first window: 2 (1 + w0) tiles; every (tile, column quarter) group stores its 8 smallest values,
+    // so 32 x tiles candidates per row, of which at least k must remain after the same-contig ones
+    wa.w0 = std::min<uint32_t>(7, std::max<uint32_t>(2, (5 * k / 4 + 63) / 64 - 1));
     const uint32_t tiles0 = std::min<uint32_t>(n_tiles, 2 * (1 + wa.w0));
-    sa.m_sel = (k + 4 * tiles0 - 1) / (4 * tiles0);
     // f32 rounding of the projections (2 x half an ulp of the largest) plus their f64 summation error
     wa.slack = pabs * (1.0f / 4194304.0f) + 1e-30f;
     wa.rng = rng;
     wa.done = done;
     wa.tiles_swept = counters;
 
-    // round 0: a first bound per row from the window around its own position; nothing is stored.
-    // (Too few columns for that -- tiny panels -- : the first real round collects everything.)
+    // round 0: a first bound per row from the window around its own position; the lists are dropped
+    // again.  (Too few columns for that -- tiny panels -- : the first real round collects everything.)
     wa.round = 0;
     wa.grow = 0;
-    if (sa.m_sel <= 8) {
-        wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
-        CNVB_LAUNCHED(ctx, "wis_window_kernel");
-        KernelSpan span(ctx, "wis_sweep_kernel");
-        wis_sweep_kernel<true><<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+    wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
+    CNVB_LAUNCHED(ctx, "wis_window_kernel");
+    if (32 * tiles0 >= 5 * k / 4) {
+        {
+            KernelSpan span(ctx, "wis_sweep_kernel");
+            wis_sweep_kernel<true><<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+        }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
-    } else {
-        wa.w0 = 0;  // only marks the centre
-        wis_window_kernel<<<row_blocks, kTileRows, 0, st>>>(wa);
-        CNVB_LAUNCHED(ctx, "wis_window_kernel");
+        ca.discard = 1;
+        {
+            KernelSpan span(ctx, "wis_compact_kernel");
+            wis_compact_kernel<<<(rows + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, st>>>(ca);
+        }
+        CNVB_LAUNCHED(ctx, "wis_compact_kernel");
+        ca.discard = 0;
     }
     // rounds 1..: windows reach 4^r (1 + w0) tiles either side of the block's own position, never
     // beyond what the rows' bounds still allow; stop when a round has nothing left to sweep
