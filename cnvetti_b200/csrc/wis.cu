@@ -159,8 +159,11 @@ __global__ void __launch_bounds__(kRowThreads) wis_row_exact_kernel(
 }
 
 // ---- W3 ----------------------------------------------------------------------------------------
-// threshold = (mean + z * sd) as f32 of the nearest distances (f64; exact-sum mean, n-1 SD)
-__device__ dd block_reduce_dd_1024(dd v) {
+// threshold = (mean + z * sd) as f32 of the nearest distances (f64; exact-sum mean, n-1 SD).
+// Two grid-wide reductions in double-double; the block that finishes last folds the partials.
+constexpr uint32_t kThrBlocks = 128, kThrThreads = 256;
+
+__device__ dd block_reduce_dd_all(dd v) {  // result valid in warp 0
     __shared__ double s_hi[32], s_lo[32];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -174,75 +177,137 @@ __device__ dd block_reduce_dd_1024(dd v) {
     v = lane < nw ? dd{s_hi[lane], s_lo[lane]} : dd{0.0, 0.0};
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = dd_add(v, dd_shfl_xor(v, o));
-    return v;  // valid in every thread of every warp
+    return v;
 }
 
-__global__ void __launch_bounds__(1024) wis_threshold_kernel(const float *__restrict__ nearest, uint32_t T,
-                                                             uint32_t stride, double z, float *__restrict__ out) {
+// PASS 0: sum of x -> ws[0] = mean.  PASS 1: sum of (x - mean)^2 -> out[0] = threshold.
+// ws: [0] mean | [1] ticket (as u64) | [2 ..] per-block partials (hi, lo)
+template <int PASS>
+__global__ void __launch_bounds__(kThrThreads) wis_threshold_kernel(const float *__restrict__ nearest, uint32_t T,
+                                                                    uint32_t stride, double z, double *__restrict__ ws,
+                                                                    float *__restrict__ out) {
+    __shared__ bool s_last;
+    const double mean = PASS ? ws[0] : 0.0;
     dd acc{0.0, 0.0};
-    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) acc = dd_add_d(acc, (double)nearest[(size_t)t * stride]);
-    acc = block_reduce_dd_1024(acc);
-    const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)T);  // Stats::mean
-    dd v{0.0, 0.0};
-    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x) {
-        const double x = __dsub_rn((double)nearest[(size_t)t * stride], mean);
-        v = dd_add_d(v, __dmul_rn(x, x));
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+        double x = (double)nearest[(size_t)t * stride];
+        if (PASS) {
+            x = __dsub_rn(x, mean);
+            x = __dmul_rn(x, x);
+        }
+        acc = dd_add_d(acc, x);
     }
-    v = block_reduce_dd_1024(v);
+    acc = block_reduce_dd_all(acc);
+    unsigned long long *ticket = reinterpret_cast<unsigned long long *>(ws + 1);
     if (threadIdx.x == 0) {
-        const double var = __ddiv_rn(__dadd_rn(v.hi, v.lo), (double)(T - 1));  // stats.rs:231-232
-        const double sd = __dsqrt_rn(var);
-        out[0] = (float)__dadd_rn(mean, __dmul_rn(z, sd));  // lib.rs:216
+        ws[2 + 2 * blockIdx.x] = acc.hi;
+        ws[3 + 2 * blockIdx.x] = acc.lo;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1ull) == (unsigned long long)(gridDim.x * (PASS + 1)) - 1ull;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    dd tot{0.0, 0.0};
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+        tot = dd_add(tot, dd{((volatile double *)ws)[2 + 2 * b], ((volatile double *)ws)[3 + 2 * b]});
+    tot = block_reduce_dd_all(tot);
+    if (threadIdx.x == 0) {
+        if (!PASS) {
+            ws[0] = __ddiv_rn(__dadd_rn(tot.hi, tot.lo), (double)T);  // Stats::mean
+        } else {
+            const double var = __ddiv_rn(__dadd_rn(tot.hi, tot.lo), (double)(T - 1));  // stats.rs:231-232
+            const double sd = __dsqrt_rn(var);
+            out[0] = (float)__dadd_rn(mean, __dmul_rn(z, sd));  // lib.rs:216
+        }
     }
 }
 
-__global__ void wis_prune_kernel(const float *__restrict__ dist, uint32_t *__restrict__ idx, uint32_t rows,
-                                 uint32_t k, float thr, uint32_t *__restrict__ ref_len) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per row: keep the entries with distance <= threshold, in order (lib.rs:221-228)
+__global__ void __launch_bounds__(256) wis_prune_kernel(const float *__restrict__ dist, uint32_t *__restrict__ idx,
+                                                        uint32_t rows, uint32_t k, float thr,
+                                                        uint32_t *__restrict__ ref_len) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (r >= rows) return;
     uint32_t m = 0;
-    for (uint32_t q = 0; q < k; ++q)  // lib.rs:221-228: keep while distance <= threshold, in order
-        if (dist[(size_t)r * k + q] <= thr) idx[(size_t)r * k + m++] = idx[(size_t)r * k + q];
-    ref_len[r] = m;
+    for (uint32_t base = 0; base < k; base += 32) {
+        const uint32_t q = base + lane;
+        const bool keep = q < k && dist[(size_t)r * k + q] <= thr;
+        const uint32_t j = q < k ? idx[(size_t)r * k + q] : 0u;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) idx[(size_t)r * k + m + __popc(mask & ((1u << lane) - 1u))] = j;  // target slot <= q
+        m += __popc(mask);
+        __syncwarp();
+    }
+    if (lane == 0) ref_len[r] = m;
 }
 
 // ---- W4 ----------------------------------------------------------------------------------------
-// one CTA per target; threads stride over samples so that each reference row is read coalesced
-__global__ void __launch_bounds__(128) wis_calls_kernel(const float *__restrict__ X, uint32_t S,
-                                                        const uint32_t *__restrict__ ref_idx,
-                                                        const uint32_t *__restrict__ ref_len, uint32_t k,
-                                                        uint32_t min_ref, double zthr, double rel_thr,
-                                                        uint32_t row_begin, uint32_t *__restrict__ num_calls) {
-    __shared__ uint32_t s_ref[kMaxK];
-    __shared__ uint32_t s_calls;
-    const uint32_t r = blockIdx.x, t = row_begin + r;
-    const uint32_t m = ref_len[r];
-    if (threadIdx.x == 0) s_calls = 0;
-    for (uint32_t q = threadIdx.x; q < m; q += blockDim.x) s_ref[q] = ref_idx[(size_t)r * k + q];
-    __syncthreads();
-    uint32_t calls = 0;
-    if (m >= min_ref) {  // lib.rs:254-256
-        for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
-            dd acc{0.0, 0.0};
-            for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)s_ref[q] * S + s));
-            const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)m);
-            double v = 0.0;  // stats.rs:218-234: naive left-to-right, same order as the reference
-            for (uint32_t q = 0; q < m; ++q) {
-                const double d = __dsub_rn((double)__ldg(X + (size_t)s_ref[q] * S + s), mean);
-                v = __dadd_rn(v, __dmul_rn(d, d));
-            }
-            const double var = m < 2 ? 0.0 : __ddiv_rn(v, (double)(m - 1));
-            const double sd = __dsqrt_rn(var);
-            const double x = (double)X[(size_t)t * S + s];
-            const double zs = __ddiv_rn(fabs(__dsub_rn(x, mean)), sd);  // lib.rs:260
-            const double rel = __ddiv_rn(x, mean);                      // lib.rs:262
-            if (zs > zthr && fabs(__dsub_rn(rel, 1.0)) > rel_thr) calls += 1;  // lib.rs:264-266
-        }
+// A CTA takes kCallsGroup targets; its threads walk the flattened (target, sample) items so that all
+// lanes work whatever S is, and neighbouring lanes read neighbouring samples of the same reference row.
+// Mean = correctly rounded exact sum / m (Stats::sum, stats.rs:165-197): when the addends' exponents
+// lie close enough together a plain f64 sum of m f32 values is exact, otherwise double-double.
+constexpr uint32_t kCallsGroup = 32, kCallsThreads = 256;
+
+__global__ void __launch_bounds__(kCallsThreads) wis_calls_kernel(const float *__restrict__ X, uint32_t S,
+                                                                  const uint32_t *__restrict__ ref_idx,
+                                                                  const uint32_t *__restrict__ ref_len, uint32_t k,
+                                                                  uint32_t min_ref, double zthr, double rel_thr,
+                                                                  uint32_t row_begin, uint32_t rows,
+                                                                  uint32_t *__restrict__ num_calls) {
+    extern __shared__ uint32_t s_ref[];  // [kCallsGroup][k]
+    __shared__ uint32_t s_len[kCallsGroup], s_calls[kCallsGroup];
+    const uint32_t r0 = blockIdx.x * kCallsGroup;
+    const uint32_t groups = min(kCallsGroup, rows - r0);
+    for (uint32_t g = threadIdx.x; g < kCallsGroup; g += blockDim.x) {
+        s_len[g] = g < groups ? ref_len[r0 + g] : 0u;
+        s_calls[g] = 0u;
     }
-    calls = __reduce_add_sync(0xffffffffu, calls);
-    if (lane_id() == 0 && calls) atomicAdd(&s_calls, calls);
     __syncthreads();
-    if (threadIdx.x == 0) num_calls[r] = s_calls;
+    for (uint32_t e = threadIdx.x; e < groups * k; e += blockDim.x) {
+        const uint32_t g = e / k, q = e - g * k;
+        if (q < s_len[g]) s_ref[e] = ref_idx[(size_t)(r0 + g) * k + q];
+    }
+    __syncthreads();
+    for (uint32_t item = threadIdx.x; item < groups * S; item += blockDim.x) {
+        const uint32_t g = item / S, s = item - g * S;
+        const uint32_t m = s_len[g];
+        if (m < min_ref) continue;  // lib.rs:254-256
+        const uint32_t *ref = s_ref + g * k;
+        double sum = 0.0;
+        uint32_t amax = 0u, amin = 0x7FFFFFFFu;
+        for (uint32_t q = 0; q < m; ++q) {
+            const float xf = __ldg(X + (size_t)ref[q] * S + s);
+            const uint32_t bits = __float_as_uint(xf) & 0x7FFFFFFFu;
+            amax = max(amax, bits);
+            amin = min(amin, bits ? bits : 0x7FFFFFFFu);
+            sum = __dadd_rn(sum, (double)xf);
+        }
+        // every addend is a multiple of 2^(emin - 23) and every partial sum is below 2^(emax + 1 + log2 m):
+        // no rounding happened if that span fits 53 bits
+        const int span = (int)(amax >> 23) - (int)max(amin >> 23, 1u);
+        const int room = 29 - (32 - __clz((int)m - 1));  // 29 - ceil(log2 m)
+        if (amax != 0u && span > room) {
+            dd acc{0.0, 0.0};
+            for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)ref[q] * S + s));
+            sum = __dadd_rn(acc.hi, acc.lo);
+        }
+        const double mean = __ddiv_rn(sum, (double)m);
+        double v = 0.0;  // stats.rs:218-234: naive left-to-right, same order as the reference
+        for (uint32_t q = 0; q < m; ++q) {
+            const double d = __dsub_rn((double)__ldg(X + (size_t)ref[q] * S + s), mean);
+            v = __dadd_rn(v, __dmul_rn(d, d));
+        }
+        const double var = m < 2 ? 0.0 : __ddiv_rn(v, (double)(m - 1));
+        const double sd = __dsqrt_rn(var);
+        const double x = (double)X[(size_t)(row_begin + r0 + g) * S + s];
+        const double zs = __ddiv_rn(fabs(__dsub_rn(x, mean)), sd);  // lib.rs:260
+        const double rel = __ddiv_rn(x, mean);                      // lib.rs:262
+        if (zs > zthr && fabs(__dsub_rn(rel, 1.0)) > rel_thr) atomicAdd(&s_calls[g], 1u);  // lib.rs:264-266
+    }
+    __syncthreads();
+    for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) num_calls[r0 + g] = s_calls[g];
 }
 
 __global__ void wis_filters_kernel(const uint32_t *__restrict__ ref_len, const uint32_t *__restrict__ num_calls,
@@ -436,9 +501,14 @@ int wis_threshold_dev(cnvb_ctx *ctx, const float *d_nearest, uint32_t T, uint32_
         *thr_host = __builtin_nanf("");
         return 0;
     }
-    CNVB_TRY(ensure_scratch(ctx, 256));
-    float *d_thr = static_cast<float *>(ctx->scratch);
-    wis_threshold_kernel<<<1, 1024, 0, ctx->stream>>>(d_nearest, T, stride, z, d_thr);
+    CNVB_TRY(ensure_scratch(ctx, 8192));
+    double *ws = static_cast<double *>(ctx->scratch);  // mean | ticket | block partials
+    float *d_thr = reinterpret_cast<float *>(static_cast<char *>(ctx->scratch) + 4096 + 2048);
+    CNVB_CUDA(ctx, cudaMemsetAsync(ws, 0, 16, ctx->stream), "threshold");
+    const unsigned blocks = std::min<unsigned>(kThrBlocks, (T + kThrThreads - 1) / kThrThreads);
+    wis_threshold_kernel<0><<<blocks, kThrThreads, 0, ctx->stream>>>(d_nearest, T, stride, z, ws, d_thr);
+    CNVB_LAUNCHED(ctx, "wis_threshold_kernel");
+    wis_threshold_kernel<1><<<blocks, kThrThreads, 0, ctx->stream>>>(d_nearest, T, stride, z, ws, d_thr);
     CNVB_LAUNCHED(ctx, "wis_threshold_kernel");
     CNVB_CUDA(ctx, cudaMemcpyAsync(thr_host, d_thr, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "threshold");
     CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "threshold");
@@ -471,7 +541,7 @@ extern "C" int cnvb_wis_prune(cnvb_ctx *ctx, const float *ref_dist, uint32_t *re
     if (mem != CNVB_MEM_DEVICE)
         CNVB_CUDA(ctx, cudaMemcpyAsync(di.p, ref_idx, (size_t)rows * k * 4, cudaMemcpyHostToDevice, ctx->stream),
                   "uploading indices");
-    wis_prune_kernel<<<(rows + 127) / 128, 128, 0, ctx->stream>>>(dd_.p, di.p, rows, k, threshold, dl.p);
+    wis_prune_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(dd_.p, di.p, rows, k, threshold, dl.p);
     CNVB_LAUNCHED(ctx, "wis_prune_kernel");
     CNVB_TRY(di.download());
     CNVB_TRY(dl.download());
@@ -483,9 +553,12 @@ namespace {
 int wis_calls_dev(cnvb_ctx *ctx, const float *dX, uint32_t S, const uint32_t *d_idx, const uint32_t *d_len, uint32_t k,
                   const cnvb_wis_opts *o, uint32_t row_begin, uint32_t rows, uint32_t *d_calls) {
     if (rows == 0) return 0;
+    const size_t smem = (size_t)kCallsGroup * k * sizeof(uint32_t);
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_calls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+              "smem opt-in");
     KernelSpan span(ctx, "wis_calls_kernel");
-    wis_calls_kernel<<<rows, 128, 0, ctx->stream>>>(dX, S, d_idx, d_len, k, o->min_ref_targets, o->filter_z_score,
-                                                    o->filter_rel, row_begin, d_calls);
+    wis_calls_kernel<<<(rows + kCallsGroup - 1) / kCallsGroup, kCallsThreads, smem, ctx->stream>>>(
+        dX, S, d_idx, d_len, k, o->min_ref_targets, o->filter_z_score, o->filter_rel, row_begin, rows, d_calls);
     CNVB_LAUNCHED(ctx, "wis_calls_kernel");
     return 0;
 }
@@ -555,7 +628,7 @@ extern "C" int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid
     CNVB_TRY(wis_distances_dev(ctx, dX.p, dt.p, T, S, opts, 0, T, od.p, oi.p));         // lib.rs:427
     CNVB_TRY(od.download());  // distances are reported un-pruned (ascending)
     CNVB_TRY(wis_threshold_dev(ctx, od.p, T, k, opts->filter_z_score, threshold));       // lib.rs:207-216
-    wis_prune_kernel<<<(T + 127) / 128, 128, 0, ctx->stream>>>(od.p, oi.p, T, k, *threshold, ol.p);  // :221-228
+    wis_prune_kernel<<<(T + 7) / 8, 256, 0, ctx->stream>>>(od.p, oi.p, T, k, *threshold, ol.p);  // :221-228
     CNVB_LAUNCHED(ctx, "wis_prune_kernel");
     CNVB_TRY(wis_calls_dev(ctx, dX.p, S, oi.p, ol.p, k, opts, 0, T, oc.p));              // lib.rs:429-436
     wis_filters_kernel<<<(T + 255) / 256, 256, 0, ctx->stream>>>(ol.p, oc.p, T, opts->min_ref_targets,

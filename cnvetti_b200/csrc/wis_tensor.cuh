@@ -876,40 +876,83 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
 }
 
 // ---- exact re-scoring and (distance, index) top-k ------------------------------------------------
-__global__ void __launch_bounds__(128) wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid,
-                                                          uint32_t T, uint32_t S, uint32_t k, uint32_t row_begin,
-                                                          uint32_t rows, const uint32_t *__restrict__ perm,
-                                                          const uint32_t *__restrict__ rows_a,
-                                                          const uint32_t *__restrict__ cand_idx,
-                                                          const uint32_t *__restrict__ cand_cnt,
-                                                          const uint32_t *__restrict__ overflow,
-                                                          float *__restrict__ out_dist, uint32_t *__restrict__ out_idx) {
-    extern __shared__ float s_dyn[];  // [S] target row | [kCandCap] exact distances
-    float *s_xi = s_dyn;
-    float *s_d = s_dyn + ((S + 3u) & ~3u);
-    __shared__ uint32_t s_j[kCandCap];
+constexpr uint32_t kRescoreWarps = 4;
+constexpr uint32_t kStageF4 = 13;              // float4 per staged row chunk (52 samples)
+constexpr uint32_t kStageStride = kStageF4 * 4;  // 52 words: float4 reads of 8 consecutive rows hit 8 distinct bank groups
+
+// One CTA per row.  STAGED: every warp copies 32 candidate rows chunk by chunk into shared memory
+// with coalesced 16-byte loads (a lane walking its own row costs a 32-byte sector per 16 bytes and is
+// bound by L1 throughput), then lane c accumulates candidate c in the reference's order.
+template <bool STAGED>
+__global__ void __launch_bounds__(kRescoreWarps * 32)
+wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S, uint32_t k,
+                   uint32_t row_begin, uint32_t rows, const uint32_t *__restrict__ perm,
+                   const uint32_t *__restrict__ rows_a, const uint32_t *__restrict__ cand_idx,
+                   const uint32_t *__restrict__ cand_cnt, const uint32_t *__restrict__ overflow,
+                   float *__restrict__ out_dist, uint32_t *__restrict__ out_idx) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    // [kCandCap] u64 keys (distance bits << 32 | target index) | [S4] target row | STAGED: [warps][32][52] stage
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_raw);
+    float *s_xi = reinterpret_cast<float *>(s_raw + (size_t)kCandCap * 8);
+    const uint32_t S4 = (S + 3u) & ~3u;
+    float *s_stage = s_xi + S4;
     const uint32_t r = blockIdx.x;
     if (overflow[r]) return;  // recomputed by the exact row kernel
     const uint32_t i = perm[rows_a ? rows_a[r] : r];  // target index of this row
     const uint32_t n = cand_cnt[r];
-    const bool vec4 = (S & 3u) == 0u && (reinterpret_cast<uintptr_t>(X) & 15u) == 0u;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) s_xi[s] = X[(size_t)i * S + s];
     __syncthreads();
-    for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
-        const uint32_t j = perm[cand_idx[(size_t)r * kCandCap + c]];
-        s_j[c] = j;
-        s_d[c] = wis_ref_distance(s_xi, X + (size_t)j * S, S, vec4);
+    if (STAGED) {  // S % 4 == 0 and X 16-byte aligned
+        float *stage = s_stage + (size_t)warp * 32 * kStageStride;
+        const uint32_t row_f4 = S >> 2;
+        for (uint32_t c0 = warp * 32; c0 < n; c0 += kRescoreWarps * 32) {
+            const uint32_t c = c0 + lane;
+            const uint32_t j = c < n ? perm[cand_idx[(size_t)r * kCandCap + c]] : i;  // (padding lanes: any valid row)
+            float y = 0.0f;
+            for (uint32_t f0 = 0; f0 < row_f4; f0 += kStageF4) {
+                const uint32_t nf = min(kStageF4, row_f4 - f0);
+                __syncwarp();
+                for (uint32_t e = lane; e < 32 * nf; e += 32) {
+                    const uint32_t cc = e / nf, f = e - cc * nf;
+                    const uint32_t jj = __shfl_sync(0xffffffffu, j, cc);
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(X + (size_t)jj * S) + f0 + f);
+                    *reinterpret_cast<float4 *>(stage + cc * kStageStride + 4 * f) = v;
+                }
+                __syncwarp();
+                const float4 *mine = reinterpret_cast<const float4 *>(stage + lane * kStageStride);
+                const float4 *xi4 = reinterpret_cast<const float4 *>(s_xi) + f0;
+                for (uint32_t f = 0; f < nf; ++f) {
+                    const float4 p = xi4[f], q4 = mine[f];
+                    float x = __fsub_rn(p.x, q4.x);
+                    y = __fadd_rn(y, __fmul_rn(x, x));
+                    x = __fsub_rn(p.y, q4.y);
+                    y = __fadd_rn(y, __fmul_rn(x, x));
+                    x = __fsub_rn(p.z, q4.z);
+                    y = __fadd_rn(y, __fmul_rn(x, x));
+                    x = __fsub_rn(p.w, q4.w);
+                    y = __fadd_rn(y, __fmul_rn(x, x));
+                }
+            }
+            if (c < n) s_key[c] = ((unsigned long long)__float_as_uint(__fsqrt_rn(y)) << 32) | j;
+        }
+    } else {
+        for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
+            const uint32_t j = perm[cand_idx[(size_t)r * kCandCap + c]];
+            s_key[c] = ((unsigned long long)__float_as_uint(wis_ref_distance(s_xi, X + (size_t)j * S, S, false)) << 32) | j;
+        }
     }
     __syncthreads();
+    // (distance, index) rank of every candidate: distances are non-negative, so their bit patterns
+    // order like the values and one 64-bit compare implements the documented tie rule
     const size_t o = (size_t)(i - row_begin) * k;
     for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
-        const float d = s_d[c];
-        const uint32_t j = s_j[c];
+        const unsigned long long mine = s_key[c];
         uint32_t rank = 0;
-        for (uint32_t e = 0; e < n; ++e) rank += ent_less(s_d[e], s_j[e], d, j) ? 1u : 0u;
+        for (uint32_t e = 0; e < n; ++e) rank += s_key[e] < mine ? 1u : 0u;
         if (rank < k) {
-            out_dist[o + rank] = d;
-            out_idx[o + rank] = j;
+            out_dist[o + rank] = __uint_as_float((uint32_t)(mine >> 32));
+            out_idx[o + rank] = (uint32_t)mine;
         }
     }
     if (threadIdx.x == 0 && n < k) {  // +inf entries of the reference, in index order
@@ -1206,13 +1249,15 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         half_prev = half;
         half *= 4;
     }
-    const size_t rsmem = (((size_t)S + 3) & ~(size_t)3) * 4 + kCandCap * 4;
-    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem),
-              "smem opt-in");
+    const bool staged = (S & 3u) == 0u && (reinterpret_cast<uintptr_t>(dX) & 15u) == 0u;
+    const size_t rsmem = (size_t)kCandCap * 8 + (((size_t)S + 3) & ~(size_t)3) * 4 +
+                         (staged ? (size_t)kRescoreWarps * 32 * kStageStride * 4 : 0);
     {
+        auto kern = staged ? wis_rescore_kernel<true> : wis_rescore_kernel<false>;
+        CNVB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem), "smem opt-in");
         KernelSpan span(ctx, "wis_rescore_kernel");
-        wis_rescore_kernel<<<rows, 128, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, perm, rows_a, cand_idx, cand_cnt,
-                                                     overflow, d_dist, d_idx);
+        kern<<<rows, kRescoreWarps * 32, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, perm, rows_a, cand_idx, cand_cnt,
+                                                      overflow, d_dist, d_idx);
     }
     CNVB_LAUNCHED(ctx, "wis_rescore_kernel");
     // rows whose candidate buffer overflowed: exact row kernel
