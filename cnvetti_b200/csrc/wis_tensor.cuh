@@ -709,6 +709,7 @@ struct CompactArgs {
     const ColMeta *meta;     // [Tpad] sorted order
     uint32_t rows, k;
     uint32_t discard;        // first round: derive the bound, then drop the list (the window is swept again)
+    unsigned long long *max_len;  // longest list any compaction left behind
     BoundConsts bc;
 };
 
@@ -867,6 +868,7 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
     if (lane == 0) {
         a.cand_cnt[r] = kept;
         a.seen[r] = kept;
+        if (kept > 64u) atomicMax(a.max_len, (unsigned long long)kept);  // (at least 64 is assumed anyway)
         if (have_bound) {
             a.thr[r] = theta;
             a.kap[r] = kappa;
@@ -877,8 +879,8 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
 
 // ---- exact re-scoring and (distance, index) top-k ------------------------------------------------
 constexpr uint32_t kRescoreWarps = 4;
-constexpr uint32_t kStageF4 = 13;              // float4 per staged row chunk (52 samples)
-constexpr uint32_t kStageStride = kStageF4 * 4;  // 52 words: float4 reads of 8 consecutive rows hit 8 distinct bank groups
+constexpr uint32_t kStageF4 = 7;               // float4 per staged row chunk (28 samples)
+constexpr uint32_t kStageStride = kStageF4 * 4;  // 28 words: float4 reads of 8 consecutive rows hit 8 distinct bank groups
 
 // One CTA per row.  STAGED: every warp copies 32 candidate rows chunk by chunk into shared memory
 // with coalesced 16-byte loads (a lane walking its own row costs a 32-byte sector per 16 bytes and is
@@ -888,12 +890,12 @@ __global__ void __launch_bounds__(kRescoreWarps * 32)
 wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S, uint32_t k,
                    uint32_t row_begin, uint32_t rows, const uint32_t *__restrict__ perm,
                    const uint32_t *__restrict__ rows_a, const uint32_t *__restrict__ cand_idx,
-                   const uint32_t *__restrict__ cand_cnt, const uint32_t *__restrict__ overflow,
+                   const uint32_t *__restrict__ cand_cnt, const uint32_t *__restrict__ overflow, uint32_t key_cap,
                    float *__restrict__ out_dist, uint32_t *__restrict__ out_idx) {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    // [kCandCap] u64 keys (distance bits << 32 | target index) | [S4] target row | STAGED: [warps][32][52] stage
+    // [key_cap] u64 keys (distance bits << 32 | target index) | [S4] target row | STAGED: [warps][32][28] stage
     unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_raw);
-    float *s_xi = reinterpret_cast<float *>(s_raw + (size_t)kCandCap * 8);
+    float *s_xi = reinterpret_cast<float *>(s_raw + (size_t)key_cap * 8);
     const uint32_t S4 = (S + 3u) & ~3u;
     float *s_stage = s_xi + S4;
     const uint32_t r = blockIdx.x;
@@ -1051,7 +1053,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ColMeta *meta = nullptr;
     uint4 *rng = nullptr;
     uint2 *done = nullptr;
-    unsigned long long *counters = nullptr;  // [0] tiles swept | [1] pairs re-scored
+    unsigned long long *counters = nullptr;  // [0] tiles swept | [1] pairs re-scored | [2] longest list
     void *cub_tmp = nullptr;
     size_t sort_bytes = 0, sel_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, ctx->stream);
@@ -1072,7 +1074,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(T, &pkey_sorted)) != cudaSuccess || (e = g.alloc(T, &ident)) != cudaSuccess ||
         (e = g.alloc(T, &perm)) != cudaSuccess || (e = g.alloc(Tpad, &tid_sorted)) != cudaSuccess ||
         (e = g.alloc(row_blocks, &rng)) != cudaSuccess || (e = g.alloc(row_blocks, &done)) != cudaSuccess ||
-        (e = g.alloc(2, &counters)) != cudaSuccess || (e = g.alloc(S, &cmean)) != cudaSuccess ||
+        (e = g.alloc(4, &counters)) != cudaSuccess || (e = g.alloc(S, &cmean)) != cudaSuccess ||
         (e = g.alloc(Tpad, &meta)) != cudaSuccess ||
         (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
@@ -1086,7 +1088,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     cudaMemsetAsync(overflow, 0, rows * 4, st);
     cudaMemsetAsync(seen, 0, rows * 4, st);
     cudaMemsetAsync(ovf_list, 0, (rows + 1) * 4, st);
-    cudaMemsetAsync(counters, 0, 16, st);
+    cudaMemsetAsync(counters, 0, 32, st);
     wis_colsum_kernel<<<std::min<uint32_t>((T + 7) / 8, (uint32_t)ctx->sm_count * 8), 256, 0, st>>>(dX, T, S, colsum, scal);
     CNVB_LAUNCHED(ctx, "wis_colsum_kernel");
     float absmax = 0.0f;
@@ -1180,6 +1182,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ca.vg = vg;
     ca.rows_a = rows_a;
     ca.meta = meta;
+    ca.max_len = counters + 2;
     ca.rows = rows;
     ca.k = k;
     ca.bc = bc;
@@ -1250,14 +1253,19 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         half *= 4;
     }
     const bool staged = (S & 3u) == 0u && (reinterpret_cast<uintptr_t>(dX) & 15u) == 0u;
-    const size_t rsmem = (size_t)kCandCap * 8 + (((size_t)S + 3) & ~(size_t)3) * 4 +
+    // the longest list decides the key buffer (more CTAs per SM when the lists are short, as they are)
+    unsigned long long h_maxn = 0;
+    CNVB_CUDA(ctx, cudaMemcpyAsync(&h_maxn, counters + 2, 8, cudaMemcpyDeviceToHost, st), "reading the longest list");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(st), "reading the longest list");
+    const uint32_t key_cap = (uint32_t)std::min<unsigned long long>(kCandCap, (std::max<unsigned long long>(h_maxn, 64) + 1) & ~1ull);
+    const size_t rsmem = (size_t)key_cap * 8 + (((size_t)S + 3) & ~(size_t)3) * 4 +
                          (staged ? (size_t)kRescoreWarps * 32 * kStageStride * 4 : 0);
     {
         auto kern = staged ? wis_rescore_kernel<true> : wis_rescore_kernel<false>;
         CNVB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem), "smem opt-in");
         KernelSpan span(ctx, "wis_rescore_kernel");
         kern<<<rows, kRescoreWarps * 32, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, perm, rows_a, cand_idx, cand_cnt,
-                                                      overflow, d_dist, d_idx);
+                                                      overflow, key_cap, d_dist, d_idx);
     }
     CNVB_LAUNCHED(ctx, "wis_rescore_kernel");
     // rows whose candidate buffer overflowed: exact row kernel
