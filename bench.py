@@ -39,7 +39,7 @@ BYTES_PER_READ_GW = 7                     # mid i32 + mapq u8 + 
 
 HMM_KERNELS = ("hmm_viterbi_kernel", "hmm_chunk_matrix_kernel", "hmm_chunk_path_kernel", "hmm_boundary_kernel",
                "hmm_backtrack_kernel", "hmm_states_kernel")
-HMM_BYTES_PER_BIN = 5  # 4 B CV read + 1 B state written
+HMM_BYTES_PER_BIN = 11  # SURVEY 8(d) cfg 4: 4 B CV + 5 B back-pointers + 1 B trace-back read + 1 B state
 
 
 def parse_args():

@@ -56,7 +56,9 @@ class CovOpts(C.Structure):
 
 class HmmTables(C.Structure):
     _fields_ = [("log_start", C.c_double * 5), ("log_trans", (C.c_double * 5) * 5),
-                ("mu", C.c_double * 5), ("inv_sd", C.c_double * 5), ("log_norm", C.c_double * 5)]
+                ("mu", C.c_double * 5), ("inv_sd", C.c_double * 5), ("log_norm", C.c_double * 5),
+                ("mu_f", C.c_float * 5), ("inv_sd_f", C.c_float * 5), ("log_norm_sc", C.c_float * 5),
+                ("sc_start", C.c_int32), ("sc_stay", C.c_int32), ("sc_move", C.c_int32)]
 
 
 def _declare(L):
@@ -111,6 +113,8 @@ def _declare(L):
     L.orc_hmm_make_tables.argtypes = [d, d, d, d, C.POINTER(HmmTables)]
     L.orc_hmm_viterbi.restype = None
     L.orc_hmm_viterbi.argtypes = [vp, C.c_uint64, C.POINTER(HmmTables), vp]
+    L.orc_hmm_emit_scores.restype = None
+    L.orc_hmm_emit_scores.argtypes = [C.c_float, C.POINTER(HmmTables), vp]
     L.orc_hmm_posterior.restype = None
     L.orc_hmm_posterior.argtypes = [vp, C.c_uint64, C.POINTER(HmmTables), vp]
 
@@ -354,6 +358,12 @@ def hmm_viterbi(cv, tables):
     state = np.zeros(cv.size, np.uint8)
     lib().orc_hmm_viterbi(_p(cv), cv.size, C.byref(tables), _p(state))
     return state
+
+
+def hmm_emit_scores(x, tables):
+    e = np.zeros(HMM_STATES, np.int32)
+    lib().orc_hmm_emit_scores(float(np.float32(x)), C.byref(tables), _p(e))
+    return e
 
 
 def hmm_posterior(cv, tables):

@@ -900,6 +900,34 @@ void orc_hmm_make_tables(double sigma_s, double sigma0, double eps_cn, double p_
         t->log_start[c] = log(1.0 / (double)K);
         for (int d = 0; d < K; ++d)
             t->log_trans[c][d] = (c == d) ? log(1.0 - (double)(K - 1) * p_move) : log(p_move);
+        t->mu_f[c] = (float)t->mu[c];
+        t->inv_sd_f[c] = (float)t->inv_sd[c];
+        t->log_norm_sc[c] = (float)(t->log_norm[c] * ORC_HMM_SCALE);
+    }
+    t->sc_start = (int32_t)llrint(t->log_start[0] * ORC_HMM_SCALE);
+    t->sc_stay = (int32_t)llrint(t->log_trans[0][0] * ORC_HMM_SCALE);
+    t->sc_move = (int32_t)llrint(t->log_trans[0][1] * ORC_HMM_SCALE);
+}
+
+/* Integer emission score: f32 arithmetic, one rounding per operation (no contraction),
+ * floored at -64 nat, rounded to the nearest integer (ties to even) by the 1.5 * 2^23 trick,
+ * which is exact for |score| <= 2^22. */
+void orc_hmm_emit_scores(float cv, const orc_hmm_tables *t, int32_t *e) {
+    for (int s = 0; s < ORC_HMM_STATES; ++s) {
+        if (!isfinite(cv)) {
+            e[s] = 0;
+            continue;
+        }
+        float t1 = cv - t->mu_f[s];
+        float z = t1 * t->inv_sd_f[s];
+        float q = z * z;
+        float h = 32768.0f * q;
+        float ll = t->log_norm_sc[s] - h;
+        if (!(ll >= -ORC_HMM_FLOOR)) ll = -ORC_HMM_FLOOR;
+        float r = ll + 12582912.0f;
+        uint32_t bits;
+        memcpy(&bits, &r, 4);
+        e[s] = (int32_t)(bits - 0x4B400000u);
     }
 }
 
@@ -922,16 +950,17 @@ void orc_hmm_viterbi(const float *cv, uint64_t n, const orc_hmm_tables *t, uint8
     const int K = ORC_HMM_STATES;
     if (n == 0) return;
     uint8_t *bp = (uint8_t *)malloc(n * K);
-    double d[ORC_HMM_STATES], nd[ORC_HMM_STATES], e[ORC_HMM_STATES];
-    hmm_emit((double)cv[0], !isfinite(cv[0]), t, e);
-    for (int s = 0; s < K; ++s) d[s] = t->log_start[s] + e[s];
+    int64_t d[ORC_HMM_STATES], nd[ORC_HMM_STATES];
+    int32_t e[ORC_HMM_STATES];
+    orc_hmm_emit_scores(cv[0], t, e);
+    for (int s = 0; s < K; ++s) d[s] = (int64_t)t->sc_start + e[s];
     for (uint64_t b = 1; b < n; ++b) {
-        hmm_emit((double)cv[b], !isfinite(cv[b]), t, e);
+        orc_hmm_emit_scores(cv[b], t, e);
         for (int s = 0; s < K; ++s) {
-            double best = d[0] + t->log_trans[0][s];
+            int64_t best = d[0] + (s == 0 ? t->sc_stay : t->sc_move);
             int arg = 0;
             for (int r = 1; r < K; ++r) {
-                double c = d[r] + t->log_trans[r][s];
+                int64_t c = d[r] + (r == s ? t->sc_stay : t->sc_move);
                 if (c > best) { /* strict: ties keep the lowest state */
                     best = c;
                     arg = r;

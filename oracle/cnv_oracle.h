@@ -156,7 +156,17 @@ typedef struct {
     double mu[ORC_HMM_STATES];
     double inv_sd[ORC_HMM_STATES];
     double log_norm[ORC_HMM_STATES]; /* -log(sd) - 0.5*log(2*pi) */
+    /* Viterbi works on integer scores in units of 2^-16 nat (exactly associative, so any
+     * evaluation order gives the same path): f32 emission parameters and integer transitions */
+    float mu_f[ORC_HMM_STATES];
+    float inv_sd_f[ORC_HMM_STATES];
+    float log_norm_sc[ORC_HMM_STATES]; /* (float)(log_norm * 65536) */
+    int32_t sc_start, sc_stay, sc_move;  /* llrint(log(.) * 65536) */
 } orc_hmm_tables;
+#define ORC_HMM_SCALE 65536.0
+#define ORC_HMM_FLOOR 4194304.0f /* emission scores are floored at -64 nat */
+/* integer emission scores of one observation (0 for a missing value) */
+void orc_hmm_emit_scores(float cv, const orc_hmm_tables *t, int32_t *e);
 void orc_hmm_make_tables(double sigma_s, double sigma0, double eps_cn, double p_move,
                          orc_hmm_tables *t);
 void orc_hmm_viterbi(const float *cv, uint64_t n, const orc_hmm_tables *t, uint8_t *state);

@@ -50,6 +50,39 @@ def test_viterbi_paths_bit_exact(oracle, ctx, device):
     assert len(segs) > 10 and all(s[3] != 2 for s in segs)
 
 
+@pytest.mark.parametrize("p_move", [1e-4, 0.2, 1e-30, 0.05])
+def test_viterbi_chunk_edges_and_ties(oracle, ctx, p_move):
+    """Lanes around the 64-bin chunk size, constant / missing / outlier observations (long runs of
+    equal scores exercise the tie rule), stay == move (p = 0.2) and a vanishing move probability."""
+    rng = np.random.default_rng(17)
+    missing = np.frombuffer(np.uint32(0x7F800001).tobytes(), np.float32)[0]
+    lanes = []
+    for n in (1, 2, 63, 64, 65, 127, 128, 129, 191, 192, 193, 1000, 4097):
+        lanes.append(rng.normal(1.0, 0.1, n).astype(np.float32))
+    lanes.append(np.full(300, 0.75, np.float32))                 # exactly between CN1 and CN2
+    lanes.append(np.full(200, missing, np.float32))              # no information at all
+    lanes.append(np.zeros(150, np.float32))
+    x = rng.normal(1.0, 0.1, 700).astype(np.float32)
+    x[100:140] = missing
+    x[300] = 1e30
+    x[301] = -5.0
+    x[400:470] = 0.5
+    x[600:] = np.float32(np.inf)
+    lanes.append(x)
+    q = np.round(rng.normal(1.0, 0.3, 5000) * 4) / 4             # heavily quantised: many exact ties
+    lanes.append(q.astype(np.float32))
+    lengths = [len(v) for v in lanes]
+    off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    cv = np.concatenate(lanes)
+    sig = rng.uniform(0.03, 0.2, len(lanes))
+    opts = discover.DiscoverOptions(p_move=p_move)
+    st = to_np(discover.hmm_segment(cv, off, sig, opts, ctx=ctx))
+    for l in range(len(lanes)):
+        t = oracle.hmm_tables(float(sig[l]), opts.sigma0, opts.eps_cn, opts.p_move)
+        ref = oracle.hmm_viterbi(lanes[l], t)
+        assert np.array_equal(st[int(off[l]):int(off[l + 1])], ref), (l, lengths[l])
+
+
 def test_posteriors_within_tolerance(oracle, ctx):
     lengths = [3000, 500, 8000]
     cv, _, off = _lanes(5, lengths)
