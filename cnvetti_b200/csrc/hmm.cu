@@ -21,7 +21,7 @@
 //   D  backtrack      thread per lane: end state of every chunk, last chunk first
 //   E  states         thread per chunk: trace back inside the chunk, one state byte per bin
 // CV, back-pointers and states move between HBM and the per-thread rows through shared-memory
-// tiles so that every global access is coalesced.  Per bin: 4 B CV read twice, 2 B back-pointer
+// tiles so that every global access is coalesced.  Per bin: 4 B CV read twice, 1 B back-pointer
 // written and read, 1 B state written (+ ~2 B of per-chunk data).
 // Posteriors (optional) stay a per-lane f64 forward-backward pass.
 #include <algorithm>
@@ -39,13 +39,15 @@ constexpr int K = CNVB_HMM_STATES;
 constexpr uint32_t kChunk = 64;          // bins per chunk
 constexpr uint32_t kChunkThreads = 128;  // chunks per CTA
 constexpr uint32_t kCvStride = kChunk + 1;   // words: conflict-free rows
-constexpr uint32_t kBpStride = kChunk + 2;   // halfwords (33 words)
+constexpr uint32_t kBpStride = kChunk + 4;   // bytes (17 words)
 constexpr uint32_t kStStride = kChunk + 4;   // bytes (17 words)
 constexpr uint32_t kMatStride = 28;          // ints per stored matrix (25 used; 16-byte aligned rows)
 
-struct HmmTables {  // per lane
-    double log_start[K], log_trans[K][K], mu[K], inv_sd[K], log_norm[K];  // posterior (f64)
-    float mu_f[K], inv_sd_f[K], log_norm_sc[K];                           // integer-score emissions
+struct HmmTables {  // per lane, posterior pass (f64)
+    double log_start[K], log_trans[K][K], mu[K], inv_sd[K], log_norm[K];
+};
+struct VitTables {  // per lane, integer-score Viterbi
+    float mu_f[K], inv_sd_f[K], log_norm_sc[K];  // inv_sd_f = (float)(inv_sd * sqrt(32768)), log_norm_sc = (float)(log_norm * 65536)
     int32_t sc_start, sc_stay, sc_move;
 };
 
@@ -70,7 +72,7 @@ __device__ __forceinline__ void hmm_emit(float cvf, const HmmTables &t, double (
 struct EmitF {
     float mu[K], inv_sd[K], ln[K];
 };
-// integer emission scores: five f32 roundings, floor at -2^22, round to nearest even by the
+// integer emission scores: four f32 roundings, floor at -2^22, round to nearest even by the
 // 1.5 * 2^23 trick (exact for |score| <= 2^22); 0 for a missing observation
 __device__ __forceinline__ void emit_scores(float x, const EmitF &t, int (&e)[K]) {
     const bool ok = isfinite(x);
@@ -79,9 +81,7 @@ __device__ __forceinline__ void emit_scores(float x, const EmitF &t, int (&e)[K]
         const float t1 = __fsub_rn(x, t.mu[s]);
         const float z = __fmul_rn(t1, t.inv_sd[s]);
         const float q = __fmul_rn(z, z);
-        const float h = __fmul_rn(32768.0f, q);
-        float ll = __fsub_rn(t.ln[s], h);
-        if (!(ll >= -4194304.0f)) ll = -4194304.0f;
+        const float ll = fmaxf(__fsub_rn(t.ln[s], q), -4194304.0f);  // (x finite: ll is a number or -inf)
         e[s] = ok ? (int)(__float_as_uint(__fadd_rn(ll, 12582912.0f)) - 0x4B400000u) : 0;
     }
 }
@@ -90,7 +90,7 @@ struct VitArgs {
     const float *cv;
     const unsigned long long *lane_off;   // [n_lanes + 1] bins
     const unsigned long long *chunk_off;  // [n_lanes + 1] chunks
-    const HmmTables *tables;              // [n_lanes]
+    const VitTables *tables;              // [n_lanes]
     uint32_t n_lanes;
     unsigned long long n_chunks;
     int *mat;             // [n_chunks][kMatStride]
@@ -98,7 +98,7 @@ struct VitArgs {
     uint16_t *org;        // [n_chunks] chunk-end state -> state at the end of the previous chunk
     uint8_t *end_state;   // [n_chunks]
     uint8_t *fin_state;   // [n_lanes]
-    uint16_t *bp;         // [bins]
+    uint8_t *bp;          // [bins] best predecessor overall (3 bits) | per state: moved there? (5 bits)
     uint8_t *state;       // [bins]
 };
 
@@ -136,7 +136,7 @@ __device__ __forceinline__ void load_cv_tile(const VitArgs &a, const ChunkPos &p
     __syncwarp();
 }
 
-__device__ __forceinline__ EmitF load_emit(const HmmTables &t) {
+__device__ __forceinline__ EmitF load_emit(const VitTables &t) {
     EmitF f;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_matrix_kernel(VitArgs
     if (valid) p = locate_chunk(a, chunk);
     load_cv_tile(a, p, valid, s_cv);
     if (!valid) return;
-    const HmmTables &tab = a.tables[p.lane];
+    const VitTables &tab = a.tables[p.lane];
     const EmitF em = load_emit(tab);
     const int stay = tab.sc_stay, move = tab.sc_move;
     const float *x = s_cv + threadIdx.x * kCvStride;
@@ -180,13 +180,10 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_matrix_kernel(VitArgs
     for (uint32_t i = 1; i < p.len; ++i) {
         emit_scores(x[i], em, e);
 #pragma unroll
-        for (int r = 0; r < K; ++r) {
-            int m = d[r][0];
+        for (int r = 0; r < K; ++r) {  // DPX: three-way max and fused add-max
+            const int m = __vimax3_s32(__vimax3_s32(d[r][0], d[r][1], d[r][2]), d[r][3], d[r][4]) + move;
 #pragma unroll
-            for (int c = 1; c < K; ++c) m = max(m, d[r][c]);
-            m += move;
-#pragma unroll
-            for (int c = 0; c < K; ++c) d[r][c] = max(d[r][c] + stay, m) + e[c];
+            for (int c = 0; c < K; ++c) d[r][c] = __viaddmax_s32(d[r][c], stay, m) + e[c];
         }
         if ((i & 15u) == 0u) {  // keep the scores small: a common constant changes no decision
             int g = d[0][0];
@@ -297,22 +294,26 @@ __global__ void __launch_bounds__(kLaneWarps * 32) hmm_boundary_kernel(VitArgs a
 }
 
 // ---- C: back-pointers of every chunk from its true entry scores ------------------------------
+// The best predecessor of state c is either c itself (stay) or the best state overall (r*), so a
+// bin's back-pointers fit one byte: r* in bits 0..2, "moved" flags of the five states in bits 3..7.
 __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_path_kernel(VitArgs a) {
     extern __shared__ float s_cv[];
-    uint16_t *s_bp = reinterpret_cast<uint16_t *>(s_cv + kChunkThreads * kCvStride);
+    uint8_t *s_bp = reinterpret_cast<uint8_t *>(s_cv + kChunkThreads * kCvStride);
     const unsigned long long chunk = (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
     const bool valid = chunk < a.n_chunks;
     ChunkPos p{0, 0, 0, 0};
     if (valid) p = locate_chunk(a, chunk);
     load_cv_tile(a, p, valid, s_cv);
     if (valid) {
-        const HmmTables &tab = a.tables[p.lane];
+        const VitTables &tab = a.tables[p.lane];
         const EmitF em = load_emit(tab);
         const int stay = tab.sc_stay, move = tab.sc_move;
         const float *x = s_cv + threadIdx.x * kCvStride;
-        uint16_t *bp = s_bp + threadIdx.x * kBpStride;
+        uint8_t *bp = s_bp + threadIdx.x * kBpStride;
         int d[K], e[K];
-        uint32_t org = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
+        uint32_t o[K];  // state at the end of the previous chunk that a path ending in c came from
+#pragma unroll
+        for (int c = 0; c < K; ++c) o[c] = c;
         uint32_t first = 0;
         if (p.k == 0) {
             emit_scores(x[0], em, e);
@@ -329,34 +330,34 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_path_kernel(VitArgs a
             int m = d[0];
             uint32_t rstar = 0;
 #pragma unroll
-            for (int c = 1; c < K; ++c) {
-                if (d[c] > m) {  // lowest state among the best predecessors
-                    m = d[c];
-                    rstar = c;
-                }
+            for (int c = 1; c < K; ++c) {  // lowest state among the best predecessors: ties keep the earlier one
+                bool keep;
+                m = __vibmax_s32(m, d[c], &keep);
+                rstar = keep ? rstar : (uint32_t)c;
             }
             const int mv = m + move;
-            uint32_t packed = 0, norg = 0;
+            // origin of the best predecessor; in the first bin of a later chunk the predecessors ARE the origins
+            uint32_t orig = o[0];
+#pragma unroll
+            for (int c = 1; c < K; ++c) orig = rstar == (uint32_t)c ? o[c] : orig;
+            uint32_t packed = rstar;
 #pragma unroll
             for (int c = 0; c < K; ++c) {
                 const int sv = d[c] + stay;
-                // predecessor: staying (c) or the best other state (rstar); equal scores -> lower index
-                const uint32_t arg = sv > mv ? (uint32_t)c : (sv < mv ? rstar : min((uint32_t)c, rstar));
+                // staying wins unless moving is strictly better, or equally good from a lower state
+                const bool moved = sv < mv + ((uint32_t)c > rstar ? 1 : 0);
                 d[c] = max(sv, mv) + e[c];
-                packed |= arg << (3 * c);
-                norg |= ((org >> (3 * arg)) & 7u) << (3 * c);
+                packed |= moved ? (8u << c) : 0u;
+                o[c] = moved ? orig : o[c];
             }
-            org = (i == 0) ? packed : norg;  // the first bin of a later chunk points into the previous chunk
-            bp[i] = (uint16_t)packed;
+            bp[i] = (uint8_t)packed;
             if ((i & 15u) == 15u) {
-                int g = d[0];
-#pragma unroll
-                for (int c = 1; c < K; ++c) g = max(g, d[c]);
+                const int g = __vimax3_s32(__vimax3_s32(d[0], d[1], d[2]), d[3], d[4]);
 #pragma unroll
                 for (int c = 0; c < K; ++c) d[c] -= g;
             }
         }
-        a.org[chunk] = (uint16_t)org;
+        a.org[chunk] = (uint16_t)(o[0] | (o[1] << 3) | (o[2] << 6) | (o[3] << 9) | (o[4] << 12));
     }
     __syncwarp();
     {   // coalesced copy of the warp's back-pointer rows to HBM
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_path_kernel(VitArgs a
         for (uint32_t j = 0; j < 32; ++j) {
             const unsigned long long b0 = __shfl_sync(0xffffffffu, p.b0, j);
             const uint32_t len = __shfl_sync(0xffffffffu, valid ? p.len : 0u, j);
-            const uint16_t *row = s_bp + (wbase + j) * kBpStride;
+            const uint8_t *row = s_bp + (wbase + j) * kBpStride;
             if (lane < len) a.bp[b0 + lane] = row[lane];
             if (lane + 32 < len) a.bp[b0 + lane + 32] = row[lane + 32];
         }
@@ -403,8 +404,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32) hmm_backtrack_kernel(VitArgs 
 // ---- E: states inside every chunk ----------------------------------------------------------------
 __global__ void __launch_bounds__(kChunkThreads) hmm_states_kernel(VitArgs a) {
     extern __shared__ float s_dyn[];
-    uint16_t *s_bp = reinterpret_cast<uint16_t *>(s_dyn);
-    uint8_t *s_st = reinterpret_cast<uint8_t *>(s_bp + kChunkThreads * kBpStride);
+    uint8_t *s_bp = reinterpret_cast<uint8_t *>(s_dyn);
+    uint8_t *s_st = s_bp + kChunkThreads * kBpStride;
     const unsigned long long chunk = (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
     const bool valid = chunk < a.n_chunks;
     ChunkPos p{0, 0, 0, 0};
@@ -413,18 +414,19 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_states_kernel(VitArgs a) {
     for (uint32_t j = 0; j < 32; ++j) {
         const unsigned long long b0 = __shfl_sync(0xffffffffu, p.b0, j);
         const uint32_t len = __shfl_sync(0xffffffffu, valid ? p.len : 0u, j);
-        uint16_t *row = s_bp + (wbase + j) * kBpStride;
+        uint8_t *row = s_bp + (wbase + j) * kBpStride;
         if (lane < len) row[lane] = a.bp[b0 + lane];
         if (lane + 32 < len) row[lane + 32] = a.bp[b0 + lane + 32];
     }
     __syncwarp();
     if (valid) {
-        const uint16_t *bp = s_bp + threadIdx.x * kBpStride;
+        const uint8_t *bp = s_bp + threadIdx.x * kBpStride;
         uint8_t *st = s_st + threadIdx.x * kStStride;
         uint32_t s = a.end_state[chunk];
         for (uint32_t i = p.len; i-- > 0;) {
             st[i] = (uint8_t)s;
-            if (i > 0) s = ((uint32_t)bp[i] >> (3 * s)) & 7u;
+            const uint32_t b = bp[i];
+            if (i > 0) s = ((b >> (3 + s)) & 1u) ? (b & 7u) : s;
         }
     }
     __syncwarp();
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(32) hmm_posterior_kernel(HmmArgs a) {
 }
 
 // same arithmetic, in the same order, as the CPU checker's table builder (host libm on both sides)
-void make_tables(double sigma_s, const cnvb_hmm_opts &o, HmmTables &t) {
+void make_tables(double sigma_s, const cnvb_hmm_opts &o, HmmTables &t, VitTables &v) {
     for (int c = 0; c < K; ++c) {
         const double cn = (double)c > o.eps_cn ? (double)c : o.eps_cn;
         t.mu[c] = cn / 2.0;
@@ -523,13 +525,13 @@ void make_tables(double sigma_s, const cnvb_hmm_opts &o, HmmTables &t) {
         t.log_start[c] = std::log(1.0 / (double)K);
         for (int d = 0; d < K; ++d)
             t.log_trans[c][d] = (c == d) ? std::log(1.0 - (double)(K - 1) * o.p_move) : std::log(o.p_move);
-        t.mu_f[c] = (float)t.mu[c];
-        t.inv_sd_f[c] = (float)t.inv_sd[c];
-        t.log_norm_sc[c] = (float)(t.log_norm[c] * 65536.0);
+        v.mu_f[c] = (float)t.mu[c];
+        v.inv_sd_f[c] = (float)(t.inv_sd[c] * 181.01933598375618);  // sqrt(32768): folds the 1/2 and the score unit
+        v.log_norm_sc[c] = (float)(t.log_norm[c] * 65536.0);
     }
-    t.sc_start = (int32_t)std::llrint(t.log_start[0] * 65536.0);
-    t.sc_stay = (int32_t)std::llrint(t.log_trans[0][0] * 65536.0);
-    t.sc_move = (int32_t)std::llrint(t.log_trans[0][1] * 65536.0);
+    v.sc_start = (int32_t)std::llrint(t.log_start[0] * 65536.0);
+    v.sc_stay = (int32_t)std::llrint(t.log_trans[0][0] * 65536.0);
+    v.sc_move = (int32_t)std::llrint(t.log_trans[0][1] * 65536.0);
 }
 
 }  // namespace
@@ -554,7 +556,8 @@ extern "C" int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *
     const uint64_t base = lane_off[0], total = lane_off[n_lanes] - base;
     if (total == 0) return CNVB_OK;
     std::vector<HmmTables> tabs(n_lanes);
-    for (uint32_t l = 0; l < n_lanes; ++l) make_tables(sigma_s[l], *opts, tabs[l]);
+    std::vector<VitTables> vtabs(n_lanes);
+    for (uint32_t l = 0; l < n_lanes; ++l) make_tables(sigma_s[l], *opts, tabs[l], vtabs[l]);
     std::vector<unsigned long long> offs(n_lanes + 1), coffs(n_lanes + 1);
     coffs[0] = 0;
     for (uint32_t l = 0; l <= n_lanes; ++l) offs[l] = lane_off[l] - base;
@@ -577,7 +580,7 @@ extern "C" int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *
          *d_mat = nullptr, *d_din = nullptr, *d_org = nullptr, *d_end = nullptr, *d_fin = nullptr;
     cudaError_t e;
     if ((e = alloc((n_lanes + 1) * 8, &d_off)) != cudaSuccess || (e = alloc((n_lanes + 1) * 8, &d_coff)) != cudaSuccess ||
-        (e = alloc(n_lanes * sizeof(HmmTables), &d_tabs)) != cudaSuccess || (e = alloc(total * 2, &d_bp)) != cudaSuccess ||
+        (e = alloc(n_lanes * sizeof(VitTables), &d_tabs)) != cudaSuccess || (e = alloc(total, &d_bp)) != cudaSuccess ||
         (e = alloc(n_chunks * kMatStride * 4, &d_mat)) != cudaSuccess || (e = alloc(n_chunks * K * 4, &d_din)) != cudaSuccess ||
         (e = alloc(n_chunks * 2, &d_org)) != cudaSuccess || (e = alloc(n_chunks, &d_end)) != cudaSuccess ||
         (e = alloc(n_lanes, &d_fin)) != cudaSuccess)
@@ -593,13 +596,13 @@ extern "C" int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *
     }
     CNVB_CUDA(ctx, cudaMemcpyAsync(d_off, offs.data(), (n_lanes + 1) * 8, cudaMemcpyHostToDevice, ctx->stream), "lanes");
     CNVB_CUDA(ctx, cudaMemcpyAsync(d_coff, coffs.data(), (n_lanes + 1) * 8, cudaMemcpyHostToDevice, ctx->stream), "lanes");
-    CNVB_CUDA(ctx, cudaMemcpyAsync(d_tabs, tabs.data(), n_lanes * sizeof(HmmTables), cudaMemcpyHostToDevice, ctx->stream),
+    CNVB_CUDA(ctx, cudaMemcpyAsync(d_tabs, vtabs.data(), n_lanes * sizeof(VitTables), cudaMemcpyHostToDevice, ctx->stream),
               "tables");
     VitArgs va{};
     va.cv = host ? static_cast<const float *>(d_cv) : cvp;
     va.lane_off = static_cast<const unsigned long long *>(d_off);
     va.chunk_off = static_cast<const unsigned long long *>(d_coff);
-    va.tables = static_cast<const HmmTables *>(d_tabs);
+    va.tables = static_cast<const VitTables *>(d_tabs);
     va.n_lanes = n_lanes;
     va.n_chunks = n_chunks;
     va.mat = static_cast<int *>(d_mat);
@@ -607,14 +610,14 @@ extern "C" int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *
     va.org = static_cast<uint16_t *>(d_org);
     va.end_state = static_cast<uint8_t *>(d_end);
     va.fin_state = static_cast<uint8_t *>(d_fin);
-    va.bp = static_cast<uint16_t *>(d_bp);
+    va.bp = static_cast<uint8_t *>(d_bp);
     va.state = host ? static_cast<uint8_t *>(d_state) : stp;
     const unsigned cblocks = (unsigned)((n_chunks + kChunkThreads - 1) / kChunkThreads);
     const unsigned lblocks = (n_lanes + kLaneWarps - 1) / kLaneWarps;
     const unsigned pblocks = (n_lanes + 31) / 32;
     const size_t smem_a = (size_t)kChunkThreads * kCvStride * 4;
-    const size_t smem_c = smem_a + (size_t)kChunkThreads * kBpStride * 2;
-    const size_t smem_e = (size_t)kChunkThreads * kBpStride * 2 + (size_t)kChunkThreads * kStStride;
+    const size_t smem_c = smem_a + (size_t)kChunkThreads * kBpStride;
+    const size_t smem_e = (size_t)kChunkThreads * kBpStride + (size_t)kChunkThreads * kStStride;
     CNVB_CUDA(ctx, cudaFuncSetAttribute(hmm_chunk_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c),
               "smem opt-in");
     {
@@ -648,16 +651,19 @@ extern "C" int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
             return lane_off[x + 1] - lane_off[x] > lane_off[y + 1] - lane_off[y];
         });
-        void *d_order = nullptr, *d_alpha = nullptr, *d_post = nullptr;
-        if ((e = alloc(n_lanes * 4, &d_order)) != cudaSuccess || (e = alloc(total * K * 8, &d_alpha)) != cudaSuccess)
+        void *d_order = nullptr, *d_alpha = nullptr, *d_post = nullptr, *d_ptabs = nullptr;
+        if ((e = alloc(n_lanes * 4, &d_order)) != cudaSuccess || (e = alloc(total * K * 8, &d_alpha)) != cudaSuccess ||
+            (e = alloc(n_lanes * sizeof(HmmTables), &d_ptabs)) != cudaSuccess)
             return fail_cuda(ctx, e, "allocating forward variables");
+        CNVB_CUDA(ctx, cudaMemcpyAsync(d_ptabs, tabs.data(), n_lanes * sizeof(HmmTables), cudaMemcpyHostToDevice, ctx->stream),
+                  "tables");
         if (host && (e = alloc(total * K * 8, &d_post)) != cudaSuccess) return fail_cuda(ctx, e, "allocating posteriors");
         CNVB_CUDA(ctx, cudaMemcpyAsync(d_order, order.data(), n_lanes * 4, cudaMemcpyHostToDevice, ctx->stream), "lanes");
         HmmArgs a{};
         a.cv = va.cv;
         a.lane_off = va.lane_off;
         a.order = static_cast<const uint32_t *>(d_order);
-        a.tables = va.tables;
+        a.tables = static_cast<const HmmTables *>(d_ptabs);
         a.n_lanes = n_lanes;
         a.alpha = static_cast<double *>(d_alpha);
         a.post = host ? static_cast<double *>(d_post) : pop;

@@ -901,7 +901,7 @@ void orc_hmm_make_tables(double sigma_s, double sigma0, double eps_cn, double p_
         for (int d = 0; d < K; ++d)
             t->log_trans[c][d] = (c == d) ? log(1.0 - (double)(K - 1) * p_move) : log(p_move);
         t->mu_f[c] = (float)t->mu[c];
-        t->inv_sd_f[c] = (float)t->inv_sd[c];
+        t->inv_sd_f[c] = (float)(t->inv_sd[c] * ORC_HMM_ZSCALE); /* folds the 1/2 and the score unit into z */
         t->log_norm_sc[c] = (float)(t->log_norm[c] * ORC_HMM_SCALE);
     }
     t->sc_start = (int32_t)llrint(t->log_start[0] * ORC_HMM_SCALE);
@@ -909,7 +909,7 @@ void orc_hmm_make_tables(double sigma_s, double sigma0, double eps_cn, double p_
     t->sc_move = (int32_t)llrint(t->log_trans[0][1] * ORC_HMM_SCALE);
 }
 
-/* Integer emission score: f32 arithmetic, one rounding per operation (no contraction),
+/* Integer emission score: four f32 operations, one rounding each (no contraction),
  * floored at -64 nat, rounded to the nearest integer (ties to even) by the 1.5 * 2^23 trick,
  * which is exact for |score| <= 2^22. */
 void orc_hmm_emit_scores(float cv, const orc_hmm_tables *t, int32_t *e) {
@@ -921,8 +921,7 @@ void orc_hmm_emit_scores(float cv, const orc_hmm_tables *t, int32_t *e) {
         float t1 = cv - t->mu_f[s];
         float z = t1 * t->inv_sd_f[s];
         float q = z * z;
-        float h = 32768.0f * q;
-        float ll = t->log_norm_sc[s] - h;
+        float ll = t->log_norm_sc[s] - q;
         if (!(ll >= -ORC_HMM_FLOOR)) ll = -ORC_HMM_FLOOR;
         float r = ll + 12582912.0f;
         uint32_t bits;

@@ -159,11 +159,12 @@ typedef struct {
     /* Viterbi works on integer scores in units of 2^-16 nat (exactly associative, so any
      * evaluation order gives the same path): f32 emission parameters and integer transitions */
     float mu_f[ORC_HMM_STATES];
-    float inv_sd_f[ORC_HMM_STATES];
+    float inv_sd_f[ORC_HMM_STATES];    /* (float)(inv_sd * sqrt(65536 / 2)) */
     float log_norm_sc[ORC_HMM_STATES]; /* (float)(log_norm * 65536) */
     int32_t sc_start, sc_stay, sc_move;  /* llrint(log(.) * 65536) */
 } orc_hmm_tables;
 #define ORC_HMM_SCALE 65536.0
+#define ORC_HMM_ZSCALE 181.01933598375618 /* sqrt(32768) */
 #define ORC_HMM_FLOOR 4194304.0f /* emission scores are floored at -64 nat */
 /* integer emission scores of one observation (0 for a missing value) */
 void orc_hmm_emit_scores(float cv, const orc_hmm_tables *t, int32_t *e);
