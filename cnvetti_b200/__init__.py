@@ -9,7 +9,7 @@ from .coverage import (AggregationStats, BamRecordAggregator, CoverageAggregator
                        CoverageOptions, FragmentsGenomeWideAggregator,
                        FragmentsTargetRegionsAggregator, ReadBatch, ReferenceStats, cov_records,
                        make_aggregator, pack_reads)
-from . import discover, model_wis  # noqa: F401
+from . import discover, model_wis, piles  # noqa: F401
 from .model_wis import BuildModelWisOptions  # noqa: F401
 from .normalize import run_binned_correction, run_uncorrected_normalization  # noqa: F401
 

@@ -83,6 +83,11 @@ SYMBOLS = {
     "cnvb_coverage_rows": (_u64, [C.POINTER(CovOpts), _int, C.POINTER(Region), _u32]),
     "cnvb_coverage_run": (_int, [_vp, C.POINTER(CovOpts), _int, C.POINTER(Region), _u32,
                                  C.POINTER(CovColumns), _vp, _vp, _int]),
+    "cnvb_piles_collect": (_int, [_vp, C.POINTER(ReadSoa), C.POINTER(CovOpts), _u32, _u32, C.POINTER(_vp)]),
+    "cnvb_piles_count": (_u64, [_vp]),
+    "cnvb_piles_get": (_int, [_vp, _vp, _vp, _vp, _int]),
+    "cnvb_piles_destroy": (None, [_vp]),
+    "cnvb_pile_threshold": (_int, [_vp, _u64, C.c_double, C.POINTER(_u32), C.c_char_p, _u64]),
     "cnvb_norm_total": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _int]),
     "cnvb_norm_gc_median": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _int]),
     "cnvb_wis_distances": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _u32, _u32, _vp, _vp, _int]),

@@ -191,6 +191,27 @@ int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const 
                       uint32_t n_regions, const cnvb_cov_columns *out, uint64_t *num_processed,
                       uint64_t *num_skipped, int mem);
 
+/* ---- lib-coverage: pile collection for --mask-piles --------------------------------------- */
+typedef struct cnvb_piles cnvb_piles;
+/* = PileCollector::collect_piles (lib-coverage/src/piles.rs:31-127) for the reads fetch() yields
+ * for one contig (coordinate order; pos, end, mapq, flags): maximal runs of covered bases with
+ * gaps <= pile_max_gap, size = largest depth.  Depth counts the alignments of a pileup column
+ * (htslib's column mask = opts->plp_flag_mask, 0 = default 0x704) that pass piles.rs:45-58 with
+ * opts->min_mapq.  region_end = contig length: an alignment reaching past it makes the reference
+ * panic (CNVB_ERR_REFERENCE_PANIC).  The result is an opaque list (device memory). */
+int cnvb_piles_collect(cnvb_ctx *ctx, const cnvb_read_soa *reads, const cnvb_cov_opts *opts,
+                       uint32_t pile_max_gap, uint32_t region_end, cnvb_piles **out);
+uint64_t cnvb_piles_count(const cnvb_piles *piles);
+/* PileInfo { start, end, size } (piles.rs:67-75) of every pile, in position order; any of the
+ * three may be NULL */
+int cnvb_piles_get(cnvb_piles *piles, uint32_t *start, uint32_t *end, uint32_t *size, int mem);
+void cnvb_piles_destroy(cnvb_piles *piles);
+/* = compute_threshold (lib-coverage/src/lib.rs:265-351): depth threshold from the histogram of
+ * pile sizes (abs_freq[size] = number of piles, all contigs) at the given FDR.  Pure host
+ * arithmetic, no context; on failure the reference's bail! text is copied to err (may be NULL). */
+int cnvb_pile_threshold(const uint64_t *abs_freq, uint64_t n, double fdr_cutoff, uint32_t *threshold,
+                        char *err, uint64_t err_len);
+
 /* ---- lib-normalize ------------------------------------------------------------------------ */
 /* = run_uncorrected_normalization (lib-normalize/src/uncorrected.rs:20-96).  lcvsd/cvsd may be
  * NULL.  *lcv_sum (host, may be NULL) receives the f64 sum. */

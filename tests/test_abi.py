@@ -58,3 +58,34 @@ def test_pack_reads_host_only():
     end, mid, frag_end, flags = cb.pack_reads(pos, isize, flag, cigar_off, cigar, 0.6)
     assert end.tolist() == [200, 230] and mid.tolist() == [250, 50] and frag_end.tolist() == [400, -100]
     assert flags.tolist() == [99, 147 | 0x1000 | 0x2000]
+
+
+def test_pile_threshold_host_function(oracle):
+    """cnvb_pile_threshold is pure host arithmetic (no GPU): the reference's own known-answer test
+    (lib-coverage/src/lib.rs:797-807) and random histograms against the oracle."""
+    import json
+    import os
+    from cnvetti_b200 import _native as N
+    from cnvetti_b200 import piles
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stats_kat.json")))["pile_threshold"]
+    assert piles.compute_threshold(kat["y"], kat["fdr"]) == kat["expected"]
+    rng = np.random.default_rng(5)
+    checked = 0
+    for _ in range(300):
+        n = int(rng.integers(3, 40))
+        y = np.sort(rng.integers(0, 5000, n))[::-1].astype(np.uint64)
+        y[0] = 0
+        fdr = float(rng.choice([1e-4, 1e-3, 1e-2, 0.05]))
+        try:
+            exp = oracle.pile_threshold(y, fdr)
+        except oracle.OraclePanic:
+            with pytest.raises(N.CnvbError):
+                piles.compute_threshold(y, fdr)
+            continue
+        assert piles.compute_threshold(y, fdr) == exp
+        checked += 1
+    assert checked > 50
+    with pytest.raises(N.CnvbError, match="No coverage above 1"):
+        piles.compute_threshold([0, 3], 0.01)
+    with pytest.raises(N.CnvbError, match="y\\[0\\] must be == 0"):
+        piles.compute_threshold([1, 3, 2], 0.01)
