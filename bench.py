@@ -45,12 +45,12 @@ HMM_BYTES_PER_BIN = 11  # SURVEY 8(d) cfg 4: 4 B CV + 5 B back-pointers + 1 B tr
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only (profiling runs)")
-    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm"],
+    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm", "piles"],
                     help="coverage = BASELINE configs[1] (default, the headline); wis = configs[2]")
     ap.add_argument("--targets", type=int, default=200_000, help="wis: number of targets T")
     ap.add_argument("--samples", type=int, default=100, help="wis: number of samples S")
@@ -66,39 +66,65 @@ def contigs(scale):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  One
+    long-running `nvidia-smi -lms 20` is started early (`arm`, before the warm-up: the tool needs
+    ~100 ms to come up); `start`/`stop` bracket the timed region by wall clock and only the samples
+    stamped inside it are reported.  A timed region shorter than the sampling period falls back to
+    the samples taken under the same load since `arm`, and says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
+        self.arm()
 
-    def start(self):
+    def arm(self):
+        if self.proc:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def start(self):
+        t_wait = time.time()
+        while self.proc and not self.rows and time.time() - t_wait < 0.5:  # the tool is up once it has printed a line
+            time.sleep(0.005)
+        self.t0 = time.time()
+
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = time.time()
+            self.rows.append((ts, r))
 
     def stop(self):
+        self.t1 = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)  # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 - 0.01 <= ts <= self.t1 + 0.01]
+        window = "timed region"
+        if not inside:
+            inside = [r for ts, r in self.rows if ts <= self.t1 + 0.01][-10:]
+            window = "timed region shorter than the 20 ms sampling period: last samples under the same load (warm-up)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -108,7 +134,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -186,11 +212,11 @@ def bench_wis(args):
     m = step()
     torch.cuda.synchronize()
     stats = mw.last_stats(ctx)
+    sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
     for _ in range(max(0, args.warmup - 1)):
         step()
     ctx.set_timing(True)
     ctx.timing_reset()
-    sampler = ClockSampler(0)
     torch.cuda.synchronize()
     sampler.start()
     l0 = ctx.launch_count
@@ -312,11 +338,11 @@ def bench_hmm(args):
     st = step()
     torch.cuda.synchronize()
     frac_cn2 = float((st == 2).float().mean().item())
+    sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
     for _ in range(max(0, args.warmup - 1)):
         step()
     ctx.set_timing(True)
     ctx.timing_reset()
-    sampler = ClockSampler(0)
     torch.cuda.synchronize()
     sampler.start()
     l0 = ctx.launch_count
@@ -390,8 +416,84 @@ def bench_hmm(args):
     return 0
 
 
+def bench_piles(args):
+    """`--mask-piles` pass of cmd coverage (lib-coverage/src/piles.rs) on BASELINE configs[0]'s input:
+    chr22, ~15 M reads.  One step = collect_piles of the contig (pile list in HBM)."""
+    import torch
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import piles as pl
+    from cnvetti_b200 import synth_torch
+    from cnvetti_b200.synth import CHR22_LEN
+    dev = "cuda:0"
+    ctx = cb.Context(0)
+    L = int(CHR22_LEN * args.scale)
+    n_pairs = int(7_600_000 * args.scale)
+    soa = synth_torch.synth_soa_contig(22, L, n_pairs, dev)
+    batch = cb.ReadBatch(pos=soa["pos"].contiguous(), end=soa["end"].contiguous(), mapq=soa["mapq"].contiguous(),
+                         flags=soa["flags"].contiguous())
+    n_reads = len(batch)
+    Lc = int(soa["end"].max().item()) + 1
+    col = pl.PileCollector(20, MIN_MAPQ, ctx=ctx)
+    got = col.collect_piles(batch, Lc)
+    sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
+    for _ in range(max(0, args.warmup - 1)):
+        col.collect_piles(batch, Lc)
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        col.collect_piles(batch, Lc)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count - l0
+    hb = cb.ReadBatch(**{k: getattr(batch, k).cpu().pin_memory() for k in ("pos", "end", "mapq", "flags")})
+    col.collect_piles(hb, Lc)
+    t0 = time.perf_counter()
+    esteps = max(1, min(args.steps, 3))
+    for _ in range(esteps):
+        col.collect_piles(hb, Lc)
+    e2e_s = (time.perf_counter() - t0) / esteps
+    cpu = None
+    if not args.quick:
+        import oracle
+        oracle.build()
+        nsub = min(n_reads, 4_000_000)
+        d = synth_torch.soa_to_oracle_records(soa, 0, nsub)
+        Ls = int(d["pos"].max()) + 1000
+        rb = oracle.ReadBatch(d["pos"], d["isize"], d["flag"], d["mapq"], d["cigar_off"], d["cigar"])
+        t0 = time.perf_counter()
+        depth = oracle.coverage(rb, oracle.cov_opts(window_length=1000, min_mapq=MIN_MAPQ), Ls, debug=True)[3]
+        oracle.piles_from_depths(depth[:Ls], 20)
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": nsub / dt_cpu, "unit": "reads/s", "cores": 1, "kind": "port",
+               "sample": "first %d reads of the contig: per-base depth pass + base-by-base pile walk, single thread" % nsub}
+    peak, peak_src = measured_peak()
+    line = {"metric": "aligned reads/s (pile collection)", "value": n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "cfg1 input (chr22, %d reads): cmd coverage --mask-piles, pile collection" % n_reads,
+                       "piles": len(got), "max_pile_size": int(got.size.max()) if len(got) else 0,
+                       "l2": "read columns %.0f MB exceed L2" % (n_reads * 11 / 1e6)},
+            "e2e": {"value": n_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n_reads * 11,
+                    "d2h_bytes_per_step": len(got) * 12, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "cub sort/scan + pile kernels", "achieved": n_reads * 11 / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": n_reads * 11 / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_read": 11,
+                         "note": "whole call (two host syncs for the counts included), not a single kernel"},
+            "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload == "piles" and args.impl == "b200":
+        return bench_piles(args)
     if args.workload == "hmm" and args.impl == "b200":
         return bench_hmm(args)
     if args.workload == "wis" and args.impl == "b200":
@@ -494,9 +596,9 @@ def main():
     torch.cuda.synchronize()
     assert int(t.rcv.double().sum().item()) == sum(t.num_processed) - sum(t.num_skipped), "checksum"
     n_windows = int(t.rcv.numel())
+    sampler = ClockSampler(local_rank)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
     for _ in range(max(0, args.warmup - 1)):
         step_device()
-    sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     launches0 = ctx.launch_count
