@@ -74,19 +74,32 @@ __device__ __forceinline__ uint64_t upper_bound_u32(const uint32_t *__restrict__
     return lo;
 }
 
-__global__ void pile_emit_kernel(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ pmax,
-                                 const uint32_t *__restrict__ head, const uint32_t *__restrict__ pid1,
-                                 const uint32_t *__restrict__ ends_sorted, uint64_t n, uint32_t *__restrict__ start,
-                                 uint32_t *__restrict__ end, uint32_t *__restrict__ size) {
+// Pile ids are non-decreasing along the reads, so the 256 reads of a CTA touch at most 256
+// consecutive piles: the maxima are combined in shared memory first and every (CTA, pile) pair
+// issues one global atomic -- a deep-coverage contig is ONE pile, and 15 M atomics on one address
+// would serialise.
+__global__ void __launch_bounds__(256) pile_emit_kernel(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ pmax,
+                                                        const uint32_t *__restrict__ head, const uint32_t *__restrict__ pid1,
+                                                        const uint32_t *__restrict__ ends_sorted, uint64_t n,
+                                                        uint32_t *__restrict__ start, uint32_t *__restrict__ end,
+                                                        uint32_t *__restrict__ size) {
+    __shared__ uint32_t s_max[256];
+    __shared__ uint32_t s_first;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t pile = pid1[i] - 1u;
-    const uint32_t p = pos[i];
-    // reads 0..i have started; those whose end is <= p have ended (ties in p: the last one sees them all)
-    const uint32_t depth = (uint32_t)(i + 1 - upper_bound_u32(ends_sorted, n, p));
-    atomicMax(&size[pile], depth);
-    if (head[i]) start[pile] = p;
-    if (i + 1 == n || head[i + 1]) end[pile] = pmax[i];
+    s_max[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) s_first = pid1[(uint64_t)blockIdx.x * blockDim.x] - 1u;
+    __syncthreads();
+    if (i < n) {
+        const uint32_t pile = pid1[i] - 1u;
+        const uint32_t p = pos[i];
+        // reads 0..i have started; those whose end is <= p have ended (ties in p: the last one sees them all)
+        const uint32_t depth = (uint32_t)(i + 1 - upper_bound_u32(ends_sorted, n, p));
+        atomicMax(&s_max[pile - s_first], depth);
+        if (head[i]) start[pile] = p;
+        if (i + 1 == n || head[i + 1]) end[pile] = pmax[i];
+    }
+    __syncthreads();
+    if (s_max[threadIdx.x]) atomicMax(&size[s_first + threadIdx.x], s_max[threadIdx.x]);
 }
 
 struct MaxOp {

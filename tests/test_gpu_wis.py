@@ -152,3 +152,32 @@ def test_wis_tensor_single_contig_and_tiny_other_contig(oracle, ctx):
     opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
     dist, idx = mw.compute_distances(X, tids, opts, ctx=ctx)
     assert np.array_equal(idx, oidx) and np.array_equal(dist.view(np.uint32), odist.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["flat_projection", "two_clusters", "sparse_shard"])
+def test_wis_tensor_windows_adversarial(oracle, ctx, kind):
+    """The projection windows prune, they never decide: panels whose all-ones projection carries no
+    information (every window must grow to the full width), two far-apart efficiency clusters (windows
+    end at the gap) and a sparse row shard (a CTA's rows span many column tiles)."""
+    rng = np.random.default_rng(123)
+    T, S, k = 4600, 64, 40
+    if kind == "flat_projection":
+        X = rng.normal(0.0, 1.0, (T, S)).astype(np.float32)
+        X -= X.mean(axis=1, keepdims=True)          # all row sums (projections) ~ 0
+        X += 5.0
+    elif kind == "two_clusters":
+        eff = np.where(rng.random(T) < 0.5, 1.0, 7.0)
+        X = (eff[:, None] * rng.normal(1.0, 0.05, (T, S))).astype(np.float32)
+    else:
+        X, _ = synth.synth_panel(99, T, S, n_contigs=8)
+    tids = rng.integers(0, 8, T).astype(np.uint32)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
+    if kind == "sparse_shard":
+        lo, hi = 100, 100 + 460   # 10 % of the rows: their sorted positions are spread over all tiles
+        dist, idx = mw.compute_distances(X, tids, opts, row_begin=lo, row_end=hi, ctx=ctx)
+        odist, oidx = odist[lo:hi], oidx[lo:hi]
+    else:
+        dist, idx = mw.compute_distances(X, tids, opts, ctx=ctx)
+    assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
+    assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
