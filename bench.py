@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only (profiling runs)")
-    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm", "piles"],
+    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm", "piles", "cfg1"],
                     help="coverage = BASELINE configs[1] (default, the headline); wis = configs[2]")
     ap.add_argument("--targets", type=int, default=200_000, help="wis: number of targets T")
     ap.add_argument("--samples", type=int, default=100, help="wis: number of samples S")
@@ -490,8 +490,105 @@ def bench_piles(args):
     return 0
 
 
+def bench_cfg1(args):
+    """BASELINE configs[0]: one contig (chr22, ~15 M reads), 1 kbp windows, MAPQ >= 20; the three
+    aggregator kinds of lib-coverage/src/lib.rs:510-529.  `value` is count kind Coverage (per-base
+    depth mean/SD per window, the heaviest kind); the two Fragments kinds are reported beside it."""
+    import torch
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import pipeline, synth, synth_torch
+    from cnvetti_b200.synth import CHR22_LEN
+    dev = "cuda:0"
+    ctx = cb.Context(0)
+    L = int(CHR22_LEN * args.scale)
+    soa = synth_torch.synth_soa_contig(22, L, int(7_600_000 * args.scale), dev)
+    Lc = int(soa["end"].max().item()) + 1000
+    batch = cb.ReadBatch(**{k: soa[k].contiguous() for k in ("pos", "end", "mid", "frag_end", "mapq", "flags")})
+    n_reads = len(batch)
+    ts, te = synth.synth_targets(22, L, int(4000 * args.scale) + 10)
+    kinds = {
+        "coverage": (cb.CoverageOptions(window_length=1000, min_mapq=MIN_MAPQ, count_kind="Coverage"), None, 11),
+        "fragments_gw": (cb.CoverageOptions(window_length=1000, min_mapq=MIN_MAPQ), None, 7),
+        "fragments_targets": (cb.CoverageOptions(window_length=None, min_mapq=MIN_MAPQ, considered_regions="TargetRegions"),
+                              (ts, te), 11),
+    }
+    res = {}
+    clocks = None
+    launches = 0
+    for name, (opts, targets, bpr) in kinds.items():
+        prep = pipeline.PreparedRegions([pipeline.Region("chr22", Lc, batch, None, targets=targets)], opts)
+        for _ in range(max(1, args.warmup)):
+            pipeline.coverage_run(prep, opts, ctx=ctx)
+        sampler = ClockSampler(0) if name == "coverage" else None
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            pipeline.coverage_run(prep, opts, ctx=ctx)
+        e1.record()
+        torch.cuda.synchronize()
+        if sampler:
+            clocks = sampler.stop()
+            launches = ctx.launch_count - l0
+        ms = e0.elapsed_time(e1) / args.steps
+        res[name] = {"ms_per_step": ms, "reads_per_s": n_reads / (ms * 1e-3), "algorithmic_gbs": n_reads * bpr / (ms * 1e-3) / 1e9}
+    # end to end (Coverage kind): pinned host columns in, table out
+    opts = kinds["coverage"][0]
+    hb = cb.ReadBatch(**{k: getattr(batch, k).cpu().pin_memory() for k in ("pos", "end", "mapq", "flags")})
+    hprep = pipeline.PreparedRegions([pipeline.Region("chr22", Lc, hb, None)], opts)
+
+    def step_e2e():
+        t = pipeline.coverage_run(hprep, opts, ctx=ctx)
+        out = [t.rcv.cpu(), t.rcvsd.cpu(), t.lcv.cpu()]
+        torch.cuda.synchronize()
+        return out
+
+    step_e2e()
+    esteps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        out = step_e2e()
+    e2e_s = (time.perf_counter() - t0) / esteps
+    cpu = None
+    if not args.quick:
+        import oracle
+        oracle.build()
+        nsub = min(n_reads, 4_000_000)
+        d = synth_torch.soa_to_oracle_records(soa, 0, nsub)
+        Ls = int(d["pos"].max()) + 2000
+        rb = oracle.ReadBatch(d["pos"], d["isize"], d["flag"], d["mapq"], d["cigar_off"], d["cigar"])
+        t0 = time.perf_counter()
+        oracle.coverage(rb, oracle.cov_opts(window_length=1000, min_mapq=MIN_MAPQ), Ls)
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": nsub / dt_cpu, "unit": "reads/s", "cores": 1, "kind": "port",
+               "sample": "first %d reads of the contig, CoverageAggregator restatement, single thread" % nsub}
+    peak, peak_src = measured_peak()
+    cov = res["coverage"]
+    line = {"metric": "aligned reads/s binned (count kind Coverage)", "value": cov["reads_per_s"], "unit": "reads/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cov["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 depths, f32 mean/sd", "data": "synthetic",
+            "config": {"workload": "cfg1: chr22, %d reads, 1 kbp windows, MAPQ>=%d; Coverage / Fragments GW / Fragments targets"
+                                   % (n_reads, MIN_MAPQ), "targets": int(ts.size),
+                       "l2": "read columns %.0f MB exceed L2" % (n_reads * 11 / 1e6)},
+            "e2e": {"value": n_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n_reads * 11,
+                    "d2h_bytes_per_step": int(sum(o.numel() * 4 for o in out)), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "coverage_run (depth_prepare + depth_tile + finalize)",
+                         "achieved": cov["algorithmic_gbs"], "peak": peak, "unit": "GB/s", "frac": cov["algorithmic_gbs"] / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_read": 11,
+                         "note": "whole region call, not a single kernel"},
+            "cpu_baseline": cpu, "clocks": clocks, "kinds": res}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload == "cfg1" and args.impl == "b200":
+        return bench_cfg1(args)
     if args.workload == "piles" and args.impl == "b200":
         return bench_piles(args)
     if args.workload == "hmm" and args.impl == "b200":

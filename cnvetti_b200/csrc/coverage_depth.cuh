@@ -59,6 +59,8 @@ struct DepthArgs {
     uint32_t *scal;
     uint32_t *stats;  // [2] out-of-range alignments, [3] sortedness violations
     float *mean, *sd;
+    unsigned long long *tile_lo, *tile_hi;  // [tiles] alignments that can overlap the tile: [lo, hi)
+    uint32_t *blk_min, *blk_top;            // [window blocks] smallest covered window | [2 x] the two largest
 };
 
 // pass 0: maximum span, bounds and order checks
@@ -83,27 +85,33 @@ __global__ void depth_prepare_kernel(DepthArgs a) {
     }
 }
 
+// pass 0b: which alignments can overlap a tile -- one thread per tile, so that the latency of the
+// two binary searches overlaps across tiles instead of stalling every tile CTA at its start
+__global__ void depth_ranges_kernel(DepthArgs a, uint64_t tiles) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tiles) return;
+    const uint64_t t0 = t * kTile;
+    const uint64_t t1 = (t0 + kTile < a.L) ? t0 + kTile : a.L;
+    a.tile_lo[t] = lower_bound_i32(a.pos, a.n, (int64_t)t0 - (int64_t)a.scal[3] + 1);
+    a.tile_hi[t] = lower_bound_i32(a.pos, a.n, (int64_t)t1);
+}
+
 // pass 1: one CTA per tile of kTile positions
 __global__ void __launch_bounds__(256) depth_tile_kernel(DepthArgs a) {
     __shared__ uint32_t d[kTile];
     __shared__ uint32_t s_warp_tot[8];
-    __shared__ unsigned long long s_range[2];
     __shared__ uint32_t s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t t0 = (uint64_t)blockIdx.x * kTile;
     const uint64_t t1 = (t0 + kTile < a.L) ? t0 + kTile : a.L;
-    const uint32_t max_span = a.scal[3];
+    const uint64_t r_lo = a.tile_lo[blockIdx.x], r_hi = a.tile_hi[blockIdx.x];
 
     for (uint32_t i = tid; i < kTile; i += 256) d[i] = 0u;
-    if (tid == 0) {
-        s_carry = 0u;
-        s_range[0] = lower_bound_i32(a.pos, a.n, (int64_t)t0 - (int64_t)max_span + 1);
-        s_range[1] = lower_bound_i32(a.pos, a.n, (int64_t)t1);
-    }
+    if (tid == 0) s_carry = 0u;
     __syncthreads();
     // events of the alignments overlapping the tile
     uint32_t carry = 0u;
-    for (uint64_t i = s_range[0] + tid; i < s_range[1]; i += 256) {
+    for (uint64_t i = r_lo + tid; i < r_hi; i += 256) {
         const uint32_t f = a.flags[i];
         const int64_t p = a.pos[i], e = a.end[i];
         if ((f & a.plp_mask) == 0u && p >= 0 && e > (int64_t)t0 && e > p) {
@@ -173,50 +181,105 @@ __global__ void __launch_bounds__(256) depth_tile_kernel(DepthArgs a) {
     }
 }
 
-// pass 2 (one CTA): next covered window for every window, plus first / last / second-to-last
+// pass 2: next covered window for every window, plus first / last / second-to-last covered window.
+// A reverse exclusive min-scan of (covered ? W : none) over the windows: 1024 windows per CTA,
+// (2a) per-CTA summaries, (2b) carry from the CTAs to the right + scan inside the CTA.
+__global__ void __launch_bounds__(1024) covered_blocks_kernel(DepthArgs a) {
+    __shared__ uint32_t s_min[32], s_t1[32], s_t2[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t W = blockIdx.x * 1024u + tid;
+    const bool cov = W < a.num_bins && a.ncol[W] > 0u;
+    uint32_t mn = cov ? W : kNone;
+    // two largest covered windows as (t1 > t2), kNone = absent; kept as W + 1 so that 0 = absent
+    uint32_t t1 = cov ? W + 1u : 0u, t2 = 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+        const uint32_t hi = max(t1, o1), lo = max(min(t1, o1), max(t2, o2));  // (distinct windows per lane)
+        t1 = hi;
+        t2 = lo;
+    }
+    if (lane == 0) {
+        s_min[warp] = mn;
+        s_t1[warp] = t1;
+        s_t2[warp] = t2;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        mn = s_min[lane];
+        t1 = s_t1[lane];
+        t2 = s_t2[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+            const uint32_t hi = max(t1, o1), lo = max(min(t1, o1), max(t2, o2));
+            t1 = hi;
+            t2 = lo;
+        }
+        if (lane == 0) {
+            a.blk_min[blockIdx.x] = mn;
+            a.blk_top[2 * blockIdx.x] = t1;
+            a.blk_top[2 * blockIdx.x + 1] = t2;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024) next_covered_kernel(DepthArgs a) {
     __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_carry;  // smallest covered window index seen so far (to the right)
+    __shared__ uint32_t s_red[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) {
-        s_carry = kNone;
-        a.scal[1] = kNone;
-        a.scal[2] = kNone;
-    }
+    const uint32_t nblk = gridDim.x;
+    // carry: smallest covered window in the CTAs to the right
+    uint32_t carry = kNone;
+    for (uint32_t bb = blockIdx.x + 1u + tid; bb < nblk; bb += 1024u) carry = min(carry, a.blk_min[bb]);
+    carry = __reduce_min_sync(0xffffffffu, carry);
+    if (lane == 0) s_red[warp] = carry;
     __syncthreads();
-    const uint32_t nb = a.num_bins;
-    const uint32_t chunks = (nb + 1023u) / 1024u;
-    for (uint32_t c = 0; c < chunks; ++c) {
-        // walk from the right end; within a chunk thread 0 holds the right-most window
-        const int64_t W = (int64_t)nb - 1 - ((int64_t)c * 1024 + tid);
-        const bool cov = W >= 0 && a.ncol[W] > 0u;
-        uint32_t v = cov ? (uint32_t)W : kNone;  // inclusive min over this and earlier threads
+    carry = s_red[0];
+    for (uint32_t u = 1; u < 32; ++u) carry = min(carry, s_red[u]);
+    // inside the CTA walk from the right end: thread 0 holds the right-most window of the chunk
+    const int64_t W = (int64_t)blockIdx.x * 1024 + 1023 - (int64_t)tid;
+    const bool cov = W < (int64_t)a.num_bins && a.ncol[W < (int64_t)a.num_bins ? W : 0] > 0u;
+    uint32_t v = cov ? (uint32_t)W : kNone;  // inclusive min over this and earlier threads
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
-            if ((int)lane >= o) v = min(v, y);
-        }
-        if (lane == 31) s_w[warp] = v;
-        __syncthreads();
-        uint32_t pre = s_carry;
-        for (uint32_t u = 0; u < warp; ++u) pre = min(pre, s_w[u]);
-        uint32_t excl = __shfl_up_sync(0xffffffffu, v, 1);  // windows strictly to the right
-        if (lane == 0) excl = kNone;
-        excl = min(excl, pre);
-        if (W >= 0) a.next[W] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry = min(pre, v);
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v = min(v, y);
     }
-    if (tid == 0) a.scal[0] = s_carry;  // first covered window, kNone if nothing is covered
-    // last covered window: covered and nothing covered to its right; the one before it: covered
-    // and its next covered window is the last one
-    for (uint32_t W = tid; W < nb; W += 1024)
-        if (a.ncol[W] > 0u && a.next[W] == kNone) a.scal[1] = W;
+    if (lane == 31) s_w[warp] = v;
     __syncthreads();
-    const uint32_t last = a.scal[1];
-    for (uint32_t W = tid; W < nb; W += 1024)
-        if (last != kNone && a.ncol[W] > 0u && a.next[W] == last) a.scal[2] = W;
+    uint32_t pre = carry;
+    for (uint32_t u = 0; u < warp; ++u) pre = min(pre, s_w[u]);
+    uint32_t excl = __shfl_up_sync(0xffffffffu, v, 1);  // windows strictly to the right
+    if (lane == 0) excl = kNone;
+    excl = min(excl, pre);
+    if (W < (int64_t)a.num_bins) a.next[W] = excl;
+    if (blockIdx.x == 0 && warp == 0) {
+        // first covered window = smallest summary; last and the one before it = the two largest
+        uint32_t mn = kNone, t1 = 0u, t2 = 0u;
+        for (uint32_t bb = lane; bb < nblk; bb += 32u) {
+            mn = min(mn, a.blk_min[bb]);
+            const uint32_t o1 = a.blk_top[2 * bb], o2 = a.blk_top[2 * bb + 1];
+            const uint32_t hi = max(t1, o1), lo = max(min(t1, o1), max(t2, o2));
+            t1 = hi;
+            t2 = lo;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+            const uint32_t hi = max(t1, o1), lo = max(min(t1, o1), max(t2, o2));
+            t1 = hi;
+            t2 = lo;
+        }
+        if (lane == 0) {
+            a.scal[0] = mn;
+            a.scal[1] = t1 ? t1 - 1u : kNone;
+            a.scal[2] = t2 ? t2 - 1u : kNone;
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t depth_at(const DepthArgs &a, uint64_t q, uint32_t max_span) {
@@ -330,8 +393,16 @@ struct DepthState {
     unsigned long long *S = nullptr, *Q = nullptr, *first = nullptr;
     uint32_t *ncol = nullptr, *next = nullptr, *scal = nullptr;
     float *mean = nullptr, *sd = nullptr;
+    unsigned long long *tile_lo = nullptr, *tile_hi = nullptr;
+    uint32_t *blk_min = nullptr, *blk_top = nullptr;
 
     void release(cnvb_ctx *ctx) {
+        pool_release(ctx, tile_lo);
+        pool_release(ctx, tile_hi);
+        pool_release(ctx, blk_min);
+        pool_release(ctx, blk_top);
+        tile_lo = tile_hi = nullptr;
+        blk_min = blk_top = nullptr;
         if (owns) {
             pool_release(ctx, pos);
             pool_release(ctx, end);
@@ -444,6 +515,13 @@ struct DepthState {
             (e = pool_alloc_t(ctx, nb, &next)) != cudaSuccess || (e = pool_alloc_t(ctx, 4, &scal)) != cudaSuccess ||
             (e = pool_alloc_t(ctx, nb, &mean)) != cudaSuccess || (e = pool_alloc_t(ctx, nb, &sd)) != cudaSuccess)
             return fail_cuda(ctx, e, "allocating window moments");
+        const uint64_t n_tiles = ((uint64_t)num_bins * o.window_length + kTile - 1) / kTile;
+        const uint32_t n_wblk = (num_bins + 1023u) / 1024u;
+        if ((e = pool_alloc_t(ctx, n_tiles ? n_tiles : 1, &tile_lo)) != cudaSuccess ||
+            (e = pool_alloc_t(ctx, n_tiles ? n_tiles : 1, &tile_hi)) != cudaSuccess ||
+            (e = pool_alloc_t(ctx, n_wblk ? n_wblk : 1, &blk_min)) != cudaSuccess ||
+            (e = pool_alloc_t(ctx, 2 * (n_wblk ? n_wblk : 1), &blk_top)) != cudaSuccess)
+            return fail_cuda(ctx, e, "allocating window moments");
         cudaMemsetAsync(S, 0, nb * 8, ctx->stream);
         cudaMemsetAsync(Q, 0, nb * 8, ctx->stream);
         cudaMemsetAsync(first, 0xff, nb * 8, ctx->stream);
@@ -469,6 +547,10 @@ struct DepthState {
         a.stats = d_stats;
         a.mean = mean;
         a.sd = sd;
+        a.tile_lo = tile_lo;
+        a.tile_hi = tile_hi;
+        a.blk_min = blk_min;
+        a.blk_top = blk_top;
         if (num_bins == 0) return 0;
         if (n) {
             uint64_t blocks = (n + 255) / 256;
@@ -477,13 +559,17 @@ struct DepthState {
             depth_prepare_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
             CNVB_LAUNCHED(ctx, "depth_prepare_kernel");
             const uint64_t tiles = (a.L + kTile - 1) / kTile;
+            depth_ranges_kernel<<<(unsigned)((tiles + 127) / 128), 128, 0, ctx->stream>>>(a, tiles);
+            CNVB_LAUNCHED(ctx, "depth_ranges_kernel");
             {
                 KernelSpan span(ctx, "depth_tile_kernel");
                 depth_tile_kernel<<<(unsigned)tiles, 256, 0, ctx->stream>>>(a);
             }
             CNVB_LAUNCHED(ctx, "depth_tile_kernel");
         }
-        next_covered_kernel<<<1, 1024, 0, ctx->stream>>>(a);
+        covered_blocks_kernel<<<n_wblk, 1024, 0, ctx->stream>>>(a);
+        CNVB_LAUNCHED(ctx, "covered_blocks_kernel");
+        next_covered_kernel<<<n_wblk, 1024, 0, ctx->stream>>>(a);
         CNVB_LAUNCHED(ctx, "next_covered_kernel");
         window_finalize_kernel<<<(num_bins + 127) / 128, 128, 0, ctx->stream>>>(a);
         CNVB_LAUNCHED(ctx, "window_finalize_kernel");

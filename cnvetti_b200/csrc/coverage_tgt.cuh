@@ -61,6 +61,56 @@ __device__ __forceinline__ uint32_t tgt_best(const TgtArgs &a, uint32_t begin, u
     return best;
 }
 
+// First index of a sorted array with arr[i] > key (GT) or arr[i] >= key (!GT), found by the whole
+// warp: 32 probes per step, three steps cover 32768 targets.  `key` must be warp-uniform.
+template <bool GT>
+__device__ __forceinline__ uint32_t warp_first(const uint32_t *__restrict__ arr, uint32_t n, uint32_t key) {
+    const uint32_t lane = lane_id();
+    uint32_t lo = 0, hi = n;  // the answer lies in [lo, hi]
+    while (hi - lo > 32u) {
+        const uint32_t step = (hi - lo + 31u) / 32u;
+        const uint32_t idx = lo + (lane + 1u) * step - 1u;
+        bool p = true;
+        if (idx < hi) {
+            const uint32_t v = __ldg(arr + idx);
+            p = GT ? v > key : v >= key;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, p);
+        if (b == 0u) {
+            lo = hi;
+            break;
+        }
+        const uint32_t f = __ffs(b) - 1u;
+        hi = min(hi, lo + (f + 1u) * step - 1u);
+        lo = lo + f * step;
+    }
+    const uint32_t idx = lo + lane;
+    bool p = true;
+    if (idx < hi) {
+        const uint32_t v = __ldg(arr + idx);
+        p = GT ? v > key : v >= key;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    return b ? lo + (uint32_t)__ffs(b) - 1u : hi;
+}
+
+// the scan of tgt_best over a candidate range that is a superset of the intersecting targets
+__device__ __forceinline__ uint32_t tgt_best_in(const TgtArgs &a, uint32_t begin, uint32_t end, uint32_t lo, uint32_t ub) {
+    const uint32_t centre = (begin + end) >> 1;  // agg.rs:321 (u32)
+    uint32_t best = 0xffffffffu, best_d = 0xffffffffu;
+    for (uint32_t t = lo; t < ub; ++t) {
+        const uint32_t s = __ldg(a.ts + t), e = __ldg(a.te + t);
+        if (!(begin < e) || !(s < end)) continue;  // does not intersect [begin, end)
+        const uint32_t d = tgt_dist(s, e, centre);
+        if (best == 0xffffffffu || d < best_d) {
+            best = t;
+            best_d = d;
+            if (d == 0u) break;  // nothing later can be strictly smaller
+        }
+    }
+    return best;
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256, 4) frag_bin_tgt_kernel(TgtArgs a) {
     constexpr int E = VEC ? 4 : 1;
@@ -98,12 +148,32 @@ __global__ void __launch_bounds__(256, 4) frag_bin_tgt_kernel(TgtArgs a) {
             mq[0] = valid ? a.mapq[q] : 0u;
             fl[0] = valid ? a.flags[q] : 0u;
         }
+        // Coordinate-sorted reads: the 32 E fragments of this warp step lie within a few hundred
+        // bases, so ONE cooperative search per bound (over the smallest begin / the largest end of
+        // the warp) yields a candidate range that holds every fragment's intersecting targets --
+        // usually one to four of them -- instead of two 12-step binary searches per read.
+        bool pass[E];
+        uint32_t bmin = 0xffffffffu, emax = 0u;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            pass[e] = valid && frag_pass(fl[e], mq[e], a.min_mapq);
+            if (pass[e]) {
+                bmin = min(bmin, begin[e]);
+                emax = max(emax, fend[e]);
+            }
+        }
+        bmin = __reduce_min_sync(0xffffffffu, bmin);
+        emax = __reduce_max_sync(0xffffffffu, emax);
+        if (emax == 0u && bmin == 0xffffffffu) continue;  // no fragment passes the filter (warp-uniform)
+        const uint32_t lo_w = warp_first<true>(a.pmax, a.n_tgt, bmin);    // first target whose running max end > begin
+        const uint32_t ub_w = warp_first<false>(a.ts, a.n_tgt, emax);     // first target starting at or after the end
+        const bool narrow = ub_w <= lo_w + 16u;  // otherwise (unsorted input, giant fragments): per-read search
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             uint32_t best = 0xffffffffu, cnt = 0;
-            if (valid && frag_pass(fl[e], mq[e], a.min_mapq)) {
+            if (pass[e]) {
                 n_proc += 1;
-                best = tgt_best(a, begin[e], fend[e]);
+                best = narrow ? tgt_best_in(a, begin[e], fend[e], lo_w, ub_w) : tgt_best(a, begin[e], fend[e]);
                 if (best == 0xffffffffu) n_skip += 1; else cnt = 1;  // agg.rs:340-345
             }
             warp_bin_add(a.counters, best, cnt);

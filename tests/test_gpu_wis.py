@@ -181,3 +181,32 @@ def test_wis_tensor_windows_adversarial(oracle, ctx, kind):
         dist, idx = mw.compute_distances(X, tids, opts, ctx=ctx)
     assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
     assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
+
+
+def test_wis_full_size_engines_agree(oracle, ctx):
+    """BASELINE config 3 at full size (T = 200 000, S = 100, k = 100): the tensor engine's reference
+    sets for a block of rows equal the exact engine's (every pair in emulated f32-sequential
+    arithmetic) and, for a few rows, the oracle's."""
+    T, S, k = 200_000, 100, 100
+    X, tids = synth.synth_panel(3, T, S)
+    dX, dt = _dev(X), _dev(tids)
+    full_d, full_i = mw.compute_distances(dX, dt, mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR), ctx=ctx)
+    st = mw.last_stats(ctx)
+    assert st["fallback_rows"] == 0 and st["tiles"] * 256 * 128 < 0.3 * T * T, st
+    lo, hi = 123_456, 123_456 + 192
+    ex_d, ex_i = mw.compute_distances(dX, dt, mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_EXACT),
+                                      row_begin=lo, row_end=hi, ctx=ctx)
+    assert np.array_equal(to_np(full_i)[lo:hi], to_np(ex_i))
+    assert_f32_equal_bits(to_np(full_d)[lo:hi].ravel(), to_np(ex_d).ravel(), "distances")
+    rows = [0, 77_777, T - 1]
+    for r in rows:
+        od, oi = oracle.wis_distances(X, tids, max_ref_targets=k, row_begin=r, row_end=r + 1, nthreads=16)
+        assert np.array_equal(to_np(full_i)[r].astype(np.uint32), oi[0])
+        assert_f32_equal_bits(to_np(full_d)[r], od[0], "distances")
+    # size-independent properties: ascending distances, no same-contig reference, no duplicates
+    d = to_np(full_d)
+    i = to_np(full_i).astype(np.int64)
+    assert (np.diff(d, axis=1) >= 0).all()
+    assert (tids[i] != tids[:, None]).all()
+    s = np.sort(i[::97], axis=1)
+    assert (np.diff(s, axis=1) > 0).all()
