@@ -63,18 +63,33 @@ struct DepthArgs {
     uint32_t *blk_min, *blk_top;            // [window blocks] smallest covered window | [2 x] the two largest
 };
 
-// pass 0: maximum span, bounds and order checks
+// pass 0: maximum span, bounds and order checks (four alignments per thread and step when the
+// columns are 16 / 8-byte aligned, which pooled and torch allocations are)
 __global__ void depth_prepare_kernel(DepthArgs a) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t span = 0, oob = 0, unsorted = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        const int32_t p = a.pos[i], e = a.end[i];
-        if (i && a.pos[i - 1] > p) unsorted += 1;
-        if ((a.flags[i] & a.plp_mask) == 0u && p >= 0) {
+    auto one = [&](int32_t prev, int32_t p, int32_t e, uint32_t f, bool has_prev) {
+        if (has_prev && prev > p) unsorted += 1;
+        if ((f & a.plp_mask) == 0u && p >= 0) {
             if (e > p) span = max(span, (uint32_t)(e - p));
             if ((uint64_t)(int64_t)e > a.L) oob += 1;
         }
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(a.pos) | reinterpret_cast<uintptr_t>(a.end)) & 15u) == 0u &&
+                     (reinterpret_cast<uintptr_t>(a.flags) & 7u) == 0u;
+    const uint64_t nq = vec ? a.n >> 2 : 0;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+        const int4 p = ld_stream(reinterpret_cast<const int4 *>(a.pos) + q);
+        const int4 e = ld_stream(reinterpret_cast<const int4 *>(a.end) + q);
+        const uint2 f = ld_stream(reinterpret_cast<const uint2 *>(a.flags) + q);
+        const int32_t prev = q ? a.pos[4 * q - 1] : 0;
+        one(prev, p.x, e.x, f.x & 0xffffu, q != 0);
+        one(p.x, p.y, e.y, f.x >> 16, true);
+        one(p.y, p.z, e.z, f.y & 0xffffu, true);
+        one(p.z, p.w, e.w, f.y >> 16, true);
     }
+    for (uint64_t i = (nq << 2) + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
+        one(i ? a.pos[i - 1] : 0, a.pos[i], a.end[i], a.flags[i], i != 0);
     span = __reduce_max_sync(0xffffffffu, span);
     oob = __reduce_add_sync(0xffffffffu, oob);
     unsorted = __reduce_add_sync(0xffffffffu, unsorted);
@@ -98,7 +113,7 @@ __global__ void depth_ranges_kernel(DepthArgs a, uint64_t tiles) {
 
 // pass 1: one CTA per tile of kTile positions
 __global__ void __launch_bounds__(256) depth_tile_kernel(DepthArgs a) {
-    __shared__ uint32_t d[kTile];
+    __shared__ __align__(16) uint32_t d[kTile];
     __shared__ uint32_t s_warp_tot[8];
     __shared__ uint32_t s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -106,7 +121,7 @@ __global__ void __launch_bounds__(256) depth_tile_kernel(DepthArgs a) {
     const uint64_t t1 = (t0 + kTile < a.L) ? t0 + kTile : a.L;
     const uint64_t r_lo = a.tile_lo[blockIdx.x], r_hi = a.tile_hi[blockIdx.x];
 
-    for (uint32_t i = tid; i < kTile; i += 256) d[i] = 0u;
+    for (uint32_t i = tid; i < kTile / 4; i += 256) reinterpret_cast<uint4 *>(d)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_carry = 0u;
     __syncthreads();
     // events of the alignments overlapping the tile
@@ -123,24 +138,39 @@ __global__ void __launch_bounds__(256) depth_tile_kernel(DepthArgs a) {
     carry = __reduce_add_sync(0xffffffffu, carry);
     if (lane == 0 && carry) atomicAdd(&s_carry, carry);
     __syncthreads();
-    // prefix scan in place: warp w owns d[w*1024 .. w*1024+1023]
+    // prefix scan in place: warp w owns d[w*1024 .. w*1024+1023]; a lane takes four consecutive
+    // values per step (one 128-bit access, conflict-free), the warp scans the 32 lane totals
     const uint32_t seg = warp * 1024u;
+    uint4 *d4 = reinterpret_cast<uint4 *>(d + seg);
     uint32_t tot = 0u;
-#pragma unroll 8
-    for (uint32_t k = 0; k < 32; ++k) tot += d[seg + k * 32u + lane];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) {
+        const uint4 v = d4[k * 32u + lane];
+        tot += v.x + v.y + v.z + v.w;
+    }
     tot = __reduce_add_sync(0xffffffffu, tot);
     if (lane == 0) s_warp_tot[warp] = tot;
     __syncthreads();
     uint32_t run = s_carry;
     for (uint32_t u = 0; u < warp; ++u) run += s_warp_tot[u];
-    for (uint32_t k = 0; k < 32; ++k) {
-        uint32_t x = d[seg + k * 32u + lane];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) {
+        uint4 v = d4[k * 32u + lane];
+        v.y += v.x;
+        v.z += v.y;
+        v.w += v.z;
+        uint32_t x = v.w;  // lane total -> inclusive scan over the lanes
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
             if ((int)lane >= o) x += y;
         }
-        d[seg + k * 32u + lane] = run + x;
+        const uint32_t base = run + x - v.w;  // everything before this lane's four values
+        v.x += base;
+        v.y += base;
+        v.z += base;
+        v.w += base;
+        d4[k * 32u + lane] = v;
         run += __shfl_sync(0xffffffffu, x, 31);
     }
     __syncthreads();
