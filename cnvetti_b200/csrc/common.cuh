@@ -44,6 +44,8 @@ struct cnvb_ctx {
     // resident CTAs per SM of each persistent kernel (cudaOccupancy... is not free: cached)
     std::unordered_map<const void *, int> occupancy;
     uint64_t wis_stats[4] = {0, 0, 0, 0};
+    // refstats: the byte-pair classification table (128 KB), built once per context
+    void *ref_lut = nullptr;
     // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
     bool timing = false;
     std::vector<std::string> span_names;

@@ -65,6 +65,7 @@ extern "C" void cnvb_ctx_destroy(cnvb_ctx *ctx) {
     cnvb::pool_destroy(ctx);
     if (ctx->tally_slots) cudaFreeHost(ctx->tally_slots);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ref_lut) cudaFree(ctx->ref_lut);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -56,14 +56,31 @@ __device__ __forceinline__ void ref_store(float *__restrict__ gc, uint8_t *__res
 //    from three; the warp parks them in lane (pass mod 32) and every 32 passes all lanes do
 //    their f32 division and stores together.
 // Offsets are 32-bit (the host guarantees len + 16 < 2^32) and advance incrementally.
+// the table is built once per context in HBM (L2-resident afterwards); every CTA copies its 128 KB
+// with 16-byte loads instead of classifying 65536 pairs again at every launch
+__global__ void refstats_build_lut_kernel(uint16_t *__restrict__ lut) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // entry of the pair (b0, b1) lives at index (b1 << 8) | (b0 ^ b1): the shared-memory bank of an entry
+    // is (index >> 1) & 31, and genomic text uses ~10 byte values, so indexing by b0 alone would put all
+    // lookups of a warp into 5 banks; the XOR spreads the ~25 common pairs over 11
+    if (i < 65536u) lut[i ^ (i >> 8)] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
+}
+// the two table indices of a 32-bit word, in place: bytes (b0^b1, b1, b2^b3, b3)
+__device__ __forceinline__ uint32_t lut_swizzle(uint32_t w) { return w ^ ((w >> 8) & 0x00FF00FFu); }
+__device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__restrict__ lut) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(lut);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+    for (uint32_t i = threadIdx.x; i < 65536u * 2u / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
 template <bool PACKED>
 __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, uint32_t num_bins,
+                                                                    const uint16_t *__restrict__ lut,
                                                                     float *__restrict__ gc,
                                                                     uint8_t *__restrict__ has_gap) {
-    extern __shared__ uint16_t s_lut[];  // [65536]
-    for (uint32_t i = threadIdx.x; i < 65536u; i += blockDim.x)
-        s_lut[i] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
-    __syncthreads();
+    extern __shared__ __align__(16) uint16_t s_lut[];  // [65536]
+    load_lut(s_lut, lut);
     const uint32_t lane = lane_id();
     const uint32_t step = gridDim.x * (blockDim.x >> 5);
     const uintptr_t addr = reinterpret_cast<uintptr_t>(a.seq);
@@ -102,7 +119,8 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, u
         // one edge byte + eight byte pairs: packed 5-bit counts, at most 17 per field
         uint32_t t = s_lut[cbyte];
         {
-            const uint32_t w[4] = {(uint32_t)craw.x, (uint32_t)craw.y, (uint32_t)craw.z, (uint32_t)craw.w};
+            const uint32_t w[4] = {lut_swizzle((uint32_t)craw.x), lut_swizzle((uint32_t)craw.y), lut_swizzle((uint32_t)craw.z),
+                                   lut_swizzle((uint32_t)craw.w)};
 #pragma unroll
             for (int j = 0; j < 4; ++j) t += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
         }
@@ -111,7 +129,8 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, u
             for (uint32_t k = cf + 33u + lane; __any_sync(0xffffffffu, k < cl); k += 32u) {
                 if (k < cl) {
                     const int4 x = ld_stream(base4 + k);
-                    const uint32_t w[4] = {(uint32_t)x.x, (uint32_t)x.y, (uint32_t)x.z, (uint32_t)x.w};
+                    const uint32_t w[4] = {lut_swizzle((uint32_t)x.x), lut_swizzle((uint32_t)x.y), lut_swizzle((uint32_t)x.z),
+                                           lut_swizzle((uint32_t)x.w)};
                     uint32_t u = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) u += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
@@ -168,12 +187,11 @@ __device__ __forceinline__ RefWin ref_window(const RefArgs &a, uint64_t W, uint6
 // that stick out of the window are masked in registers.
 template <int G>
 __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64_t num_bins,
+                                                               const uint16_t *__restrict__ lut,
                                                                float *__restrict__ gc,
                                                                uint8_t *__restrict__ has_gap) {
-    extern __shared__ uint16_t s_lut[];  // [65536]
-    for (uint32_t i = threadIdx.x; i < 65536u; i += blockDim.x)
-        s_lut[i] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
-    __syncthreads();
+    extern __shared__ __align__(16) uint16_t s_lut[];  // [65536]
+    load_lut(s_lut, lut);
     constexpr uint32_t kGroups = 32 / G;
     const uint32_t lane = lane_id(), sub = lane % G, grp = lane / G;
     const uint64_t warp_global = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -196,7 +214,10 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64
             }
             uint32_t sum = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sum += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t x = lut_swizzle(w[j]);
+                sum += (uint32_t)s_lut[x & 0xffffu] + (uint32_t)s_lut[x >> 16];
+            }
             g += sum & 31u;
             c += (sum >> 5) & 31u;
             n += sum >> 10;
@@ -234,6 +255,12 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
                   "host-to-device copy of the reference sequence");
         d_seq = static_cast<const uint8_t *>(ctx->stage);
     }
+    if (!ctx->ref_lut) {
+        CNVB_CUDA(ctx, cudaMalloc(&ctx->ref_lut, 65536 * sizeof(uint16_t)), "allocating the classification table");
+        refstats_build_lut_kernel<<<256, 256, 0, ctx->stream>>>(static_cast<uint16_t *>(ctx->ref_lut));
+        CNVB_LAUNCHED(ctx, "refstats_build_lut_kernel");
+    }
+    const uint16_t *d_lut = static_cast<const uint16_t *>(ctx->ref_lut);
     RefArgs a{};
     a.seq = d_seq;
     a.len = len;
@@ -253,11 +280,11 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
             if (window_length < 1024) {
                 CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_warp_kernel<true>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
-                refstats_lut_warp_kernel<true><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_gc, d_gap);
+                refstats_lut_warp_kernel<true><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_lut, d_gc, d_gap);
             } else {
                 CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_warp_kernel<false>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
-                refstats_lut_warp_kernel<false><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_gc, d_gap);
+                refstats_lut_warp_kernel<false><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_lut, d_gc, d_gap);
             }
         } else {
 #define CNVB_REF_LAUNCH(GG)                                                                          \
@@ -265,7 +292,7 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
         CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_kernel<GG>,                                 \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                   "smem opt-in");                                                                    \
-        refstats_lut_kernel<GG><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, nb, d_gc, d_gap);  \
+        refstats_lut_kernel<GG><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, nb, d_lut, d_gc, d_gap);  \
         break;
             switch (G) {
                 CNVB_REF_LAUNCH(2)
