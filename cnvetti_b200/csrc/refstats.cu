@@ -58,15 +58,21 @@ __device__ __forceinline__ void ref_store(float *__restrict__ gc, uint8_t *__res
 // Offsets are 32-bit (the host guarantees len + 16 < 2^32) and advance incrementally.
 // the table is built once per context in HBM (L2-resident afterwards); every CTA copies its 128 KB
 // with 16-byte loads instead of classifying 65536 pairs again at every launch
+// the two table indices of a 32-bit word (two byte pairs), in place; a bijection on each 16-bit half
+__device__ __forceinline__ uint32_t lut_swizzle(uint32_t w) {
+    return w ^ ((w >> 6) & 0x00180018u) ^ ((w >> 8) & 0x00200020u);
+}
+__device__ __forceinline__ uint32_t lut_index(uint32_t pair) { return lut_swizzle(pair) & 0xffffu; }
+
 __global__ void refstats_build_lut_kernel(uint16_t *__restrict__ lut) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // entry of the pair (b0, b1) lives at index (b1 << 8) | (b0 ^ b1): the shared-memory bank of an entry
-    // is (index >> 1) & 31, and genomic text uses ~10 byte values, so indexing by b0 alone would put all
-    // lookups of a warp into 5 banks; the XOR spreads the ~25 common pairs over 11
-    if (i < 65536u) lut[i ^ (i >> 8)] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
+    // The shared-memory bank of an entry is (index >> 1) & 31.  Genomic text uses about ten byte values,
+    // so indexing by (b1 << 8 | b0) would put all lookups of a warp into the five banks that b0 alone
+    // selects.  A, C, G, T differ in bits 1 and 2; the index therefore keeps b0's bits 1, 2 and mixes
+    // b1's bits 1, 2 into bits 3, 4 and b1's case bit into bit 5: the 16 upper-case pairs (and the 16
+    // lower-case ones) get 16 different banks, lanes with the same pair share one address (broadcast).
+    if (i < 65536u) lut[lut_index(i)] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
 }
-// the two table indices of a 32-bit word, in place: bytes (b0^b1, b1, b2^b3, b3)
-__device__ __forceinline__ uint32_t lut_swizzle(uint32_t w) { return w ^ ((w >> 8) & 0x00FF00FFu); }
 __device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__restrict__ lut) {
     const uint4 *src = reinterpret_cast<const uint4 *>(lut);
     uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, u
             if (edge_hi ? bo < oen : bo >= osn) ebyte = basep[bo];
         }
         // one edge byte + eight byte pairs: packed 5-bit counts, at most 17 per field
-        uint32_t t = s_lut[cbyte];
+        uint32_t t = s_lut[lut_index(cbyte)];
         {
             const uint32_t w[4] = {lut_swizzle((uint32_t)craw.x), lut_swizzle((uint32_t)craw.y), lut_swizzle((uint32_t)craw.z),
                                    lut_swizzle((uint32_t)craw.w)};
@@ -162,6 +168,94 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, u
         }
     }
     if (st_w != 0xffffffffu) ref_store(gc, has_gap, st_w, st_g, st_c, st_n);
+}
+
+// Lane-group variant (wl >= 128): G lanes own one window and walk its 16-byte chunks in turn, so the
+// inner loop is nothing but load -> eight table lookups -> add; the window logic (offsets, edge
+// masking, the G-lane reduction, the store) is paid once per window and lane instead of once per warp
+// pass.  G >= 2 so that the lanes of a group read whole 32-byte sectors; larger G only serves to fill
+// the machine when a contig has few windows.
+__device__ __forceinline__ uint32_t lut_counts(const uint16_t *s_lut, const uint32_t (&w)[4]) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t x = lut_swizzle(w[j]);
+        t += (uint32_t)s_lut[x & 0xffffu] + (uint32_t)s_lut[x >> 16];
+    }
+    return t;  // 5-bit fields, at most 16 each
+}
+
+constexpr int kInFlight = 4;  // 16-byte loads per lane in flight (8 measured the same)
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint32_t num_bins,
+                                                                const uint16_t *__restrict__ lut,
+                                                                float *__restrict__ gc, uint8_t *__restrict__ has_gap) {
+    extern __shared__ __align__(16) uint16_t s_lut[];  // [65536]
+    load_lut(s_lut, lut);
+    const uint32_t lane = lane_id(), sub = lane % G;
+    const uint32_t n_groups = gridDim.x * (blockDim.x / G);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(a.seq);
+    const uint32_t mis = (uint32_t)(addr & 15u);
+    const int4 *__restrict__ base4 = reinterpret_cast<const int4 *>(addr - mis);  // 16-byte aligned
+    const uint32_t wl = a.wl, end_off = (uint32_t)a.len + mis;  // (the host guarantees len + 16 < 2^32)
+    // warp-uniform trip count so that the group shuffles below stay converged
+    const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t warp_first = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / G;
+    for (uint32_t W0 = warp_first, W = first; W0 < num_bins; W0 += n_groups, W += n_groups) {
+        uint32_t g = 0, c = 0, n = 0;
+        if (W < num_bins) {
+            const uint32_t os = W * wl + mis, oe = min(os + wl, end_off);
+            const uint32_t cf = os >> 4, cl = (oe - 1u) >> 4;
+            uint32_t acc = 0;  // 10-bit fields; flushed before they can overflow
+            uint32_t since = 0;
+            // the G lanes take the chunks of the window in turn (together they read G x 16 contiguous
+            // bytes); kInFlight loads per lane are in flight before the first is consumed -- with one, the
+            // 1024 threads of an SM keep only 16 KB in flight, less than half of what HBM latency needs
+            for (uint32_t k = cf + sub; k <= cl; k += kInFlight * G) {
+                int4 raw[kInFlight];
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) {
+                    const uint32_t kk = k + u * G;
+                    raw[u] = kk <= cl ? __ldg(base4 + kk) : make_int4(0, 0, 0, 0);  // (0x00 is in no class)
+                }
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) {
+                    const uint32_t kk = k + u * G;
+                    uint32_t w[4] = {(uint32_t)raw[u].x, (uint32_t)raw[u].y, (uint32_t)raw[u].z, (uint32_t)raw[u].w};
+                    if (kk == cf || kk == cl) {  // window edges: zero the bytes of the neighbours
+                        const uint32_t c0 = kk << 4;
+                        const int lo = os > c0 ? (int)(os - c0) : 0, hi = oe < c0 + 16u ? (int)(oe - c0) : 16;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int x = min(max(lo - 4 * j, 0), 4), y = min(max(hi - 4 * j, 0), 4);
+                            w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
+                        }
+                    }
+                    const uint32_t t = lut_counts(s_lut, w);
+                    acc += (t & 0x1Fu) | ((t & 0x3E0u) << 5) | ((t & 0x7C00u) << 10);
+                }
+                since += kInFlight;
+                if (since + kInFlight > 63u) {  // 63 x 16 < 1024
+                    g += acc & 1023u;
+                    c += (acc >> 10) & 1023u;
+                    n += acc >> 20;
+                    acc = 0;
+                    since = 0;
+                }
+            }
+            g += acc & 1023u;
+            c += (acc >> 10) & 1023u;
+            n += acc >> 20;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+        }
+        if (W < num_bins && sub == 0) ref_store(gc, has_gap, W, g, c, n);
+    }
 }
 
 struct RefWin {  // one window as seen by a lane group
@@ -274,7 +368,28 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
         uint64_t blocks = (nb + 32 * groups - 1) / (32 * groups);
         if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;  // persistent: one CTA per SM
         KernelSpan span(ctx, "refstats_lut_kernel");
-        if (G == 32 && len < 0xFFFFFF00ull) {
+        if (window_length >= 128 && len < 0xFFFFFF00ull) {
+            // lanes per window: 1 when the contig has enough windows to fill the machine, more otherwise
+            // (every lane keeps at least four chunks)
+            int GL = 2;
+            while (GL < 32 && nb * (uint64_t)GL < (uint64_t)ctx->sm_count * 1024 && (uint64_t)window_length / (2 * GL) >= 32) GL <<= 1;
+            blocks = (nb * GL + 1023) / 1024;
+            if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;
+#define CNVB_REF_LANE(GG)                                                                                              \
+    case GG:                                                                                                           \
+        CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lane_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                            (int)smem), "smem opt-in");                                                \
+        refstats_lane_kernel<GG><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_lut, d_gc, d_gap);   \
+        break;
+            switch (GL) {
+                CNVB_REF_LANE(2)
+                CNVB_REF_LANE(4)
+                CNVB_REF_LANE(8)
+                CNVB_REF_LANE(16)
+                CNVB_REF_LANE(32)
+            }
+#undef CNVB_REF_LANE
+        } else if (G == 32 && len < 0xFFFFFF00ull) {
             blocks = (nb + 31) / 32;
             if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;
             if (window_length < 1024) {
