@@ -8,7 +8,7 @@
 // TWO bytes per shared-memory lookup: a 65536-entry u16 table (128 KB, built in the CTA's shared
 // memory at kernel start; one persistent 1024-thread CTA per SM) maps a byte pair to its packed
 // class counts
-//   bits 0..4 #[GCgc]   bits 5..9 #[ACGTacgt]   bits 10..14 #[Nn]
+//   bits 0..6 #[GCgc]   bits 7..13 #[ACGTacgt]   bits 14.. #[Nn]   (entries hold 0..2 per field)
 // with   [CGcg] <=> (b & 0xDB) == 0x43    [Aa] <=> (b & 0xDF) == 0x41
 //        [Tt]   <=> (b & 0xDF) == 0x54    [Nn] <=> (b & 0xDF) == 0x4E
 // so a lane turns its 16 bytes (one 128-bit load) into counts with 8 LDS.U16 + 7 adds.  A group
@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t ref_class(uint32_t b) {
     const uint32_t isgc = (b & 0xDBu) == 0x43u, x = b & 0xDFu;
     const uint32_t isacgt = isgc | (x == 0x41u) | (x == 0x54u);
     const uint32_t isn = x == 0x4Eu;
-    return isgc | (isacgt << 5) | (isn << 10);
+    return isgc | (isacgt << 7) | (isn << 14);  // 7-bit fields: a lane may add up 63 pairs before unpacking
 }
 
 __device__ __forceinline__ void ref_store(float *__restrict__ gc, uint8_t *__restrict__ has_gap, uint64_t W,
@@ -59,9 +59,7 @@ __device__ __forceinline__ void ref_store(float *__restrict__ gc, uint8_t *__res
 // the table is built once per context in HBM (L2-resident afterwards); every CTA copies its 128 KB
 // with 16-byte loads instead of classifying 65536 pairs again at every launch
 // the two table indices of a 32-bit word (two byte pairs), in place; a bijection on each 16-bit half
-__device__ __forceinline__ uint32_t lut_swizzle(uint32_t w) {
-    return w ^ ((w >> 6) & 0x00180018u) ^ ((w >> 8) & 0x00200020u);
-}
+__device__ __forceinline__ uint32_t lut_swizzle(uint32_t w) { return w ^ ((w >> 6) & 0x00180018u); }
 __device__ __forceinline__ uint32_t lut_index(uint32_t pair) { return lut_swizzle(pair) & 0xffffu; }
 
 __global__ void refstats_build_lut_kernel(uint16_t *__restrict__ lut) {
@@ -69,8 +67,10 @@ __global__ void refstats_build_lut_kernel(uint16_t *__restrict__ lut) {
     // The shared-memory bank of an entry is (index >> 1) & 31.  Genomic text uses about ten byte values,
     // so indexing by (b1 << 8 | b0) would put all lookups of a warp into the five banks that b0 alone
     // selects.  A, C, G, T differ in bits 1 and 2; the index therefore keeps b0's bits 1, 2 and mixes
-    // b1's bits 1, 2 into bits 3, 4 and b1's case bit into bit 5: the 16 upper-case pairs (and the 16
+    // b1's bits 1, 2 into bits 3, 4: the 16 upper-case pairs (and the 16
     // lower-case ones) get 16 different banks, lanes with the same pair share one address (broadcast).
+    // (b0's case bit is bank bit 4 already; mixing in b1's too costs two more instructions per word and
+    // only matters where a warp reads upper- and lower-case text at once.)
     if (i < 65536u) lut[lut_index(i)] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
 }
 __device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__restrict__ lut) {
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, u
 #pragma unroll
             for (int j = 0; j < 4; ++j) t += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
         }
-        uint32_t g = t & 31u, c = (t >> 5) & 31u, n = t >> 10;
+        uint32_t g = t & 127u, c = (t >> 7) & 127u, n = t >> 14;
         if (cf + 33u < cl) {  // windows longer than 31 interior chunks (warp-uniform)
             for (uint32_t k = cf + 33u + lane; __any_sync(0xffffffffu, k < cl); k += 32u) {
                 if (k < cl) {
@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, u
                     uint32_t u = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) u += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
-                    g += u & 31u;
-                    c += (u >> 5) & 31u;
-                    n += u >> 10;
+                    g += u & 127u;
+                    c += (u >> 7) & 127u;
+                    n += u >> 14;
                 }
             }
         }
@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t lut_counts(const uint16_t *s_lut, const uint
         const uint32_t x = lut_swizzle(w[j]);
         t += (uint32_t)s_lut[x & 0xffffu] + (uint32_t)s_lut[x >> 16];
     }
-    return t;  // 5-bit fields, at most 16 each
+    return t;  // 7-bit fields, at most 16 each
 }
 
 constexpr int kInFlight = 4;  // 16-byte loads per lane in flight (8 measured the same)
@@ -207,8 +207,7 @@ __global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint3
         if (W < num_bins) {
             const uint32_t os = W * wl + mis, oe = min(os + wl, end_off);
             const uint32_t cf = os >> 4, cl = (oe - 1u) >> 4;
-            uint32_t acc = 0;  // 10-bit fields; flushed before they can overflow
-            uint32_t since = 0;
+            uint32_t acc = 0;  // packed 7-bit fields of the chunks in flight
             // the G lanes take the chunks of the window in turn (together they read G x 16 contiguous
             // bytes); kInFlight loads per lane are in flight before the first is consumed -- with one, the
             // 1024 threads of an SM keep only 16 KB in flight, less than half of what HBM latency needs
@@ -232,21 +231,13 @@ __global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint3
                             w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
                         }
                     }
-                    const uint32_t t = lut_counts(s_lut, w);
-                    acc += (t & 0x1Fu) | ((t & 0x3E0u) << 5) | ((t & 0x7C00u) << 10);
+                    acc += lut_counts(s_lut, w);  // 7-bit fields: kInFlight x 16 <= 127
                 }
-                since += kInFlight;
-                if (since + kInFlight > 63u) {  // 63 x 16 < 1024
-                    g += acc & 1023u;
-                    c += (acc >> 10) & 1023u;
-                    n += acc >> 20;
-                    acc = 0;
-                    since = 0;
-                }
+                g += acc & 127u;
+                c += (acc >> 7) & 127u;
+                n += acc >> 14;
+                acc = 0;
             }
-            g += acc & 1023u;
-            c += (acc >> 10) & 1023u;
-            n += acc >> 20;
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
@@ -312,9 +303,9 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64
                 const uint32_t x = lut_swizzle(w[j]);
                 sum += (uint32_t)s_lut[x & 0xffffu] + (uint32_t)s_lut[x >> 16];
             }
-            g += sum & 31u;
-            c += (sum >> 5) & 31u;
-            n += sum >> 10;
+            g += sum & 127u;
+            c += (sum >> 7) & 127u;
+            n += sum >> 14;
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
