@@ -424,28 +424,37 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(bar_a_full, 0);
             tc_fence_after();
             uint32_t st = 0, ph = 0, as = 0, aph = 0;
+            // descriptors differ from these bases only in the start-address field (16-byte units):
+            // +2 per K16 slab inside a 128-byte swizzle row, + kTileBytes / 16 per B stage
+            uint64_t adesc[2][kMaxKBlocks];
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h)
+#pragma unroll
+                for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) adesc[h][kb] = umma_desc(a_base + (h * kMaxKBlocks + kb) * kTileBytes);
+            const uint64_t bdesc0 = umma_desc(b_base);
             for (uint32_t it = 0; it < n_tiles; ++it) {
                 mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
                 tc_fence_after();
-                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
-                    mbar_wait(bar_b_full + 8 * st, ph);
-                    tc_fence_after();
-                    const uint32_t b_addr = b_base + st * kTileBytes;
 #pragma unroll
-                    for (uint32_t h = 0; h < 2; ++h) {
-                        const uint32_t a_addr = a_base + (h * kMaxKBlocks + kb) * kTileBytes;
-                        const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
+                for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) {
+                    if (kb < a.n_kblocks) {
+                        mbar_wait(bar_b_full + 8 * st, ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kTileBytes >> 4));
 #pragma unroll
-                        for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                            if (kb * (kKBlock / 16) + kk < a.k_mmas)
-                                tc_mma_f16(d_tmem, umma_desc(a_addr + kk * 32), umma_desc(b_addr + kk * 32), kIdesc,
-                                           (kb | kk) != 0u);
+                        for (uint32_t h = 0; h < 2; ++h) {
+                            const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
+#pragma unroll
+                            for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                                if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                    tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
+                            }
                         }
-                    }
-                    tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
-                    if (++st == kStages) {
-                        st = 0;
-                        ph ^= 1u;
+                        tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
+                        if (++st == kStages) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
                 tc_commit(bar_acc_full + 8 * as);  // accumulators of this tile complete
@@ -491,6 +500,11 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
             const float smax = __ldg(a.tile_smax + tile);
+            if (it + 1 < n_tiles) {  // the next tile's column operands: in L1 by the time they are needed
+                const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + cpart * 32u;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
+                if (FIRST) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.tid_sorted + jn));
+            }
             uint32_t tj[FIRST ? 32 : 1];
             if (FIRST) {
                 const uint4 *tj4 = reinterpret_cast<const uint4 *>(a.tid_sorted + j0);
