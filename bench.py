@@ -42,6 +42,15 @@ HMM_KERNELS = ("hmm_viterbi_kernel", "hmm_chunk_matrix_kernel", "hmm_chunk_path_
 HMM_BYTES_PER_BIN = 11  # SURVEY 8(d) cfg 4: 4 B CV + 5 B back-pointers + 1 B trace-back read + 1 B state
 
 
+def host_buffer(shape, dtype, torch):
+    """Pinned host memory where the box grants it (the e2e leg copies from it every step); pageable
+    otherwise -- eight ranks pinning ~9 GB each can exceed what a node allows."""
+    try:
+        return torch.empty(shape, dtype=dtype, pin_memory=True), True
+    except RuntimeError:
+        return torch.empty(shape, dtype=dtype), False
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -738,15 +747,18 @@ def main():
     # ---- end to end: pinned host SoA in, table out -----------------------------------------------------
     host_regions = []
     h2d = 0
+    all_pinned = True
     for r in dev_regions:
         cols = {}
         for kcol in ("mid", "mapq", "flags"):
             src = getattr(r.reads, kcol)
-            h = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            h, pinned = host_buffer(src.shape, src.dtype, torch)
+            all_pinned = all_pinned and pinned
             h.copy_(src)
             cols[kcol] = h
             h2d += h.numel() * h.element_size()
-        hseq = torch.empty(r.sequence.shape, dtype=torch.uint8, pin_memory=True)
+        hseq, pinned = host_buffer(r.sequence.shape, torch.uint8, torch)
+        all_pinned = all_pinned and pinned
         hseq.copy_(r.sequence)
         h2d += hseq.numel()
         host_regions.append(pipeline.Region(r.name, r.length, cb.ReadBatch(**cols), hseq))
@@ -819,7 +831,8 @@ def main():
                          ((BYTES_PER_READ_GW * n_reads + total_bp) / 1e9),
                    "parallelism": "one sample per GPU, no collective" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps},
+                "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
+                "host_memory": "pinned" if all_pinned else "pageable (pinning refused)"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "kernels": kern, "gen_seconds": gen_s,
     }
