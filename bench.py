@@ -595,6 +595,8 @@ def bench_cfg1(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     if args.workload == "cfg1" and args.impl == "b200":
         return bench_cfg1(args)
