@@ -157,3 +157,37 @@ def normalize_run(table, normalization="MedianGcBinned", ctx=None):
     else:
         raise ValueError("Unknown normalization")
     return table
+
+
+def merge_cov(tables):
+    """`cnvetti cmd merge-cov` on in-memory tables (lib-merge-cov/src/lib.rs:102-232): the per-sample
+    FORMAT/CV columns side by side -> panel X[T][S] (row-major f32) and the contig id of every record
+    (ModelInput, lib-model-wis/src/lib.rs:49-62).  All samples must describe the same records."""
+    import torch
+    if not tables:
+        raise ValueError("merge_cov: no input")
+    first = tables[0]
+    for t in tables[1:]:
+        if t.offsets != first.offsets or not torch.equal(t.start, first.start) or not torch.equal(t.end, first.end):
+            raise N.CnvbError(N.ERR_INVALID, "merge-cov: the inputs do not describe the same regions")
+    X = torch.stack([t.cv for t in tables], dim=1).contiguous()
+    tids = torch.empty(first.offsets[-1], dtype=torch.int32, device=X.device)
+    for i, (lo, hi) in enumerate(zip(first.offsets[:-1], first.offsets[1:])):
+        tids[lo:hi] = i
+    return X, tids
+
+
+def quick_wis_build_model(samples, wis_options=None, ctx=None):
+    """`cnvetti quick wis-build-model` (cnvetti/src/quick_wis_build_model.rs:133-214) on in-memory
+    inputs: per sample cmd coverage (Fragments on TargetRegions, MAPQ >= 0, min_unclipped 0.6; :44-70)
+    and cmd normalize (TotalCovSum; :72-80), merge-cov, build-model-wis.  `samples`: one list of
+    Region objects (with .targets) per sample.  Returns (model, X, tids)."""
+    from .coverage import CoverageOptions
+    from . import model_wis
+    ctx = ctx or default_context()
+    opts = CoverageOptions(window_length=None, count_kind="Fragments", considered_regions="TargetRegions",
+                           min_mapq=0, min_unclipped=0.6, min_window_remaining=0.5)
+    tables = [normalize_run(coverage_run(regions, opts, ctx=ctx), "TotalCovSum", ctx=ctx) for regions in samples]
+    X, tids = merge_cov(tables)
+    model = model_wis.run(X, tids, wis_options or model_wis.BuildModelWisOptions(), ctx=ctx)
+    return model, X, tids

@@ -124,3 +124,36 @@ def test_region_loop_host_columns_and_panic(oracle, ctx):
     assert rc == N.ERR_REFERENCE_PANIC
     with pytest.raises(cb.ReferencePanic, match="region 1"):
         ctx.check(rc)
+
+
+def test_quick_wis_build_model_chain(oracle, ctx):
+    """quick wis-build-model (coverage on targets -> TotalCovSum -> merge-cov -> build-model-wis) for a
+    small cohort, every stage against the oracle chain."""
+    from cnvetti_b200 import model_wis as mw
+    n_samples, lens = 12, (400_000, 250_000, 150_000)
+    tgts = [synth.synth_targets(80 + i, L, 90) for i, L in enumerate(lens)]
+    samples, ocols = [], []
+    for s in range(n_samples):
+        regions, lcvs = [], []
+        for i, L in enumerate(lens):
+            d = synth.synth_bam_records(1000 + 10 * s + i, L, 5000)
+            regions.append(pipeline.Region("chr%d" % (i + 1), L, soa_batch(d, device="cuda"), None, targets=tgts[i]))
+            counts, _, _ = oracle.frag_targets(oracle_reads(oracle, d), oracle.cov_opts(window_length=0, min_mapq=0),
+                                               tgts[i][0], tgts[i][1])
+            lcv, _, _ = oracle.cov_records(counts.astype(np.float32), None, tgts[i][0], tgts[i][1], None, True,
+                                           oracle.cov_opts(window_length=0, min_mapq=0))
+            lcvs.append(lcv)
+        samples.append(regions)
+        ocols.append(oracle.norm_total(np.concatenate(lcvs))[1])
+    opts = mw.BuildModelWisOptions(max_ref_targets=20, min_ref_targets=3)
+    model, X, tids = pipeline.quick_wis_build_model(samples, opts, ctx=ctx)
+    oX = np.stack(ocols, axis=1)
+    assert_f32_equal_bits(to_np(X), oX, "panel")
+    otids = np.concatenate([np.full(len(t[0]), i, np.uint32) for i, t in enumerate(tgts)])
+    assert np.array_equal(to_np(tids).astype(np.uint32), otids)
+    odist, oidx = oracle.wis_distances(oX, otids, max_ref_targets=20)
+    thr, pidx, plen = oracle.wis_prune(odist, oidx, opts.filter_z_score)
+    assert np.array_equal(to_np(model.ref_len), plen)
+    assert_f32_equal_bits(to_np(model.ref_dist), odist, "distances")
+    calls = oracle.wis_calls(oX, pidx, plen, 3, opts.filter_z_score, opts.filter_rel)
+    assert np.array_equal(to_np(model.num_calls), calls)
