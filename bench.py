@@ -595,8 +595,6 @@ def bench_cfg1(args):
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse_args()
     if args.workload == "cfg1" and args.impl == "b200":
         return bench_cfg1(args)
@@ -845,4 +843,13 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 behind Python's
+    # back (NCCL prints its version banner there), so fd 1 is pointed at stderr for the run and the
+    # real stdout is kept aside for the result line(s) that main() prints.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w", buffering=1)
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)
