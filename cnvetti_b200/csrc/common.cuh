@@ -46,6 +46,10 @@ struct cnvb_ctx {
     uint64_t wis_stats[4] = {0, 0, 0, 0};
     // refstats: the byte-pair classification table (128 KB), built once per context
     void *ref_lut = nullptr;
+    // side streams of the region loop (cnvb_coverage_run): consecutive regions run on different
+    // streams so that the ramp-down of one region's kernels overlaps the ramp-up of the next
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t side_fork = nullptr, side_join[3] = {nullptr, nullptr, nullptr};
     // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
     bool timing = false;
     std::vector<std::string> span_names;
@@ -54,6 +58,8 @@ struct cnvb_ctx {
 };
 
 namespace cnvb {
+
+int refstats_prepare(cnvb_ctx *ctx);  // refstats.cu: builds the classification table on ctx->stream if missing
 
 // error chain in the style of error-chain's "error: ... / caused by: ..." (cnvetti/src/main.rs)
 inline int fail(cnvb_ctx *ctx, int code, const char *fmt, ...) {

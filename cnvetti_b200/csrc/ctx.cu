@@ -66,6 +66,11 @@ extern "C" void cnvb_ctx_destroy(cnvb_ctx *ctx) {
     if (ctx->tally_slots) cudaFreeHost(ctx->tally_slots);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ref_lut) cudaFree(ctx->ref_lut);
+    for (int i = 0; i < 3; ++i) {
+        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+        if (ctx->side_join[i]) cudaEventDestroy(ctx->side_join[i]);
+    }
+    if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

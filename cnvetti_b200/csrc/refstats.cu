@@ -319,6 +319,14 @@ __global__ void __launch_bounds__(1024, 1) refstats_lut_kernel(RefArgs a, uint64
 
 }  // namespace
 
+int cnvb::refstats_prepare(cnvb_ctx *ctx) {
+    if (ctx->ref_lut) return 0;
+    CNVB_CUDA(ctx, cudaMalloc(&ctx->ref_lut, 65536 * sizeof(uint16_t)), "allocating the classification table");
+    refstats_build_lut_kernel<<<256, 256, 0, ctx->stream>>>(static_cast<uint16_t *>(ctx->ref_lut));
+    CNVB_LAUNCHED(ctx, "refstats_build_lut_kernel");
+    return 0;
+}
+
 extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, uint32_t window_length,
                              float *gc, uint8_t *has_gap, int mem) {
     if (!ctx) return CNVB_ERR_INVALID;
@@ -340,11 +348,7 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
                   "host-to-device copy of the reference sequence");
         d_seq = static_cast<const uint8_t *>(ctx->stage);
     }
-    if (!ctx->ref_lut) {
-        CNVB_CUDA(ctx, cudaMalloc(&ctx->ref_lut, 65536 * sizeof(uint16_t)), "allocating the classification table");
-        refstats_build_lut_kernel<<<256, 256, 0, ctx->stream>>>(static_cast<uint16_t *>(ctx->ref_lut));
-        CNVB_LAUNCHED(ctx, "refstats_build_lut_kernel");
-    }
+    CNVB_TRY(refstats_prepare(ctx));
     const uint16_t *d_lut = static_cast<const uint16_t *>(ctx->ref_lut);
     RefArgs a{};
     a.seq = d_seq;

@@ -64,7 +64,10 @@ extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int k
     Cols d;
     std::vector<void *> temps;
     std::vector<cnvb_cov *> aggs;
+    bool forked = false;
     auto cleanup = [&](int rc) {
+        if (rc != 0 && forked)  // an error path leaves work in flight on the side streams: wait before buffers are recycled
+            for (int q = 0; q < 3; ++q) cudaStreamSynchronize(ctx->side[q]);
         for (cnvb_cov *a : aggs) cnvb_cov_destroy(a);
         for (void *p : temps) pool_release(ctx, p);
         return rc;
@@ -101,10 +104,45 @@ extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int k
     }
 
     aggs.reserve(n_regions);
+    // Device-resident inputs: consecutive regions go to different side streams (fork / join with events),
+    // so the tail of one region's persistent kernels overlaps the head of the next region's and the small
+    // per-region operations (memsets, window statistics, tally copies) run beside the big ones.  Host
+    // inputs share one staging buffer and stay on the context stream.
+    // (Per-kernel timing mode keeps everything on one stream: a kernel's duration is only meaningful
+    // when it has the device to itself.)
+    bool fan = n_regions > 1 && !ctx->timing;
+    for (uint32_t i = 0; i < n_regions && fan; ++i)
+        fan = regions[i].reads.mem == CNVB_MEM_DEVICE && (!regions[i].seq || regions[i].seq_mem == CNVB_MEM_DEVICE);
+    cudaStream_t main_stream = ctx->stream;
+    if (fan) {
+        for (int q = 0; q < 3 && fan; ++q) {
+            if (!ctx->side[q] && cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking) != cudaSuccess) fan = false;
+            if (fan && !ctx->side_join[q] && cudaEventCreateWithFlags(&ctx->side_join[q], cudaEventDisableTiming) != cudaSuccess)
+                fan = false;
+        }
+        if (fan && !ctx->side_fork && cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming) != cudaSuccess) fan = false;
+    }
+    if (fan) {
+        if (d.gc) {
+            const int rc = refstats_prepare(ctx);  // the shared table is built before the streams fork
+            if (rc) return cleanup(rc);
+        }
+        if ((e = cudaEventRecord(ctx->side_fork, main_stream)) != cudaSuccess) return cleanup(fail_cuda(ctx, e, "forking streams"));
+        for (int q = 0; q < 3; ++q)
+            if ((e = cudaStreamWaitEvent(ctx->side[q], ctx->side_fork, 0)) != cudaSuccess)
+                return cleanup(fail_cuda(ctx, e, "forking streams"));
+        forked = true;
+    }
+    struct StreamGuard {  // whatever happens, the context gets its own stream back
+        cnvb_ctx *c;
+        cudaStream_t s;
+        ~StreamGuard() { c->stream = s; }
+    } stream_guard{ctx, main_stream};
     uint64_t off = 0;
     for (uint32_t i = 0; i < n_regions; ++i) {
         const cnvb_region *r = &regions[i];
         const uint64_t rows = rows_of(opts, kind, r);
+        if (fan) ctx->stream = ctx->side[i % 3];
         // lib.rs:440-454: GC content and gap flag per window from the contig bytes
         if (r->seq && (d.gc || d.gap)) {
             if (!d.gc || !d.gap)
@@ -142,6 +180,14 @@ extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int k
                                      CNVB_MEM_DEVICE)) != 0)
             return cleanup(rc);
         off += rows;
+    }
+    ctx->stream = main_stream;
+    if (fan) {
+        for (int q = 0; q < 3; ++q) {
+            if ((e = cudaEventRecord(ctx->side_join[q], ctx->side[q])) != cudaSuccess ||
+                (e = cudaStreamWaitEvent(main_stream, ctx->side_join[q], 0)) != cudaSuccess)
+                return cleanup(fail_cuda(ctx, e, "joining streams"));
+        }
     }
     // lib.rs:623-668 for all rows at once
     if (total) {
