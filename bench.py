@@ -224,8 +224,6 @@ def bench_wis(args):
     sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
     for _ in range(max(0, args.warmup - 1)):
         step()
-    ctx.set_timing(True)
-    ctx.timing_reset()
     torch.cuda.synchronize()
     sampler.start()
     l0 = ctx.launch_count
@@ -238,6 +236,12 @@ def bench_wis(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     launches = ctx.launch_count - l0
+    # per-kernel times: a second, instrumented pass (timing mode serialises what the timed steps overlap)
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
     kern = {}
     for kname in ("wis_sweep_kernel", "wis_compact_kernel", "wis_rescore_kernel", "wis_calls_kernel",
                   "wis_row_exact_kernel"):
@@ -350,8 +354,6 @@ def bench_hmm(args):
     sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
     for _ in range(max(0, args.warmup - 1)):
         step()
-    ctx.set_timing(True)
-    ctx.timing_reset()
     torch.cuda.synchronize()
     sampler.start()
     l0 = ctx.launch_count
@@ -364,6 +366,12 @@ def bench_hmm(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     launches = ctx.launch_count - l0
+    # per-kernel times: a second, instrumented pass (timing mode serialises what the timed steps overlap)
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
     kern = {}
     for kname in HMM_KERNELS:
         kms, cnt = ctx.timing_query(kname)

@@ -93,6 +93,10 @@ struct VitArgs {
     const VitTables *tables;              // [n_lanes]
     uint32_t n_lanes;
     unsigned long long n_chunks;
+    // the lanes [lane_lo, lane_hi) = chunks [chunk_lo, chunk_hi) this launch works on (lane groups run
+    // their five-kernel chains on different streams)
+    uint32_t lane_lo, lane_hi;
+    unsigned long long chunk_lo, chunk_hi;
     int *mat;             // [n_chunks][kMatStride]
     int *din;             // [n_chunks][K] scores entering the chunk (normalised)
     uint16_t *org;        // [n_chunks] chunk-end state -> state at the end of the previous chunk
@@ -150,8 +154,8 @@ __device__ __forceinline__ EmitF load_emit(const VitTables &t) {
 // ---- A: transfer matrix of every chunk ---------------------------------------------------------
 __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_matrix_kernel(VitArgs a) {
     extern __shared__ float s_cv[];
-    const unsigned long long chunk = (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
-    const bool valid = chunk < a.n_chunks;
+    const unsigned long long chunk = a.chunk_lo + (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
+    const bool valid = chunk < a.chunk_hi;
     ChunkPos p{0, 0, 0, 0};
     if (valid) p = locate_chunk(a, chunk);
     load_cv_tile(a, p, valid, s_cv);
@@ -221,8 +225,8 @@ constexpr uint32_t kLaneWarps = 4;
 
 __global__ void __launch_bounds__(kLaneWarps * 32) hmm_boundary_kernel(VitArgs a) {
     __shared__ int4 s_m[kLaneWarps][32 * kMatStride / 4];
-    const uint32_t lane_idx = blockIdx.x * kLaneWarps + (threadIdx.x >> 5), lane = lane_id();
-    if (lane_idx >= a.n_lanes) return;
+    const uint32_t lane_idx = a.lane_lo + blockIdx.x * kLaneWarps + (threadIdx.x >> 5), lane = lane_id();
+    if (lane_idx >= a.lane_hi) return;
     const unsigned long long c0 = a.chunk_off[lane_idx], c1 = a.chunk_off[lane_idx + 1];
     if (c1 == c0) return;
     int4 *sm = s_m[threadIdx.x >> 5];
@@ -299,8 +303,8 @@ __global__ void __launch_bounds__(kLaneWarps * 32) hmm_boundary_kernel(VitArgs a
 __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_path_kernel(VitArgs a) {
     extern __shared__ float s_cv[];
     uint8_t *s_bp = reinterpret_cast<uint8_t *>(s_cv + kChunkThreads * kCvStride);
-    const unsigned long long chunk = (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
-    const bool valid = chunk < a.n_chunks;
+    const unsigned long long chunk = a.chunk_lo + (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
+    const bool valid = chunk < a.chunk_hi;
     ChunkPos p{0, 0, 0, 0};
     if (valid) p = locate_chunk(a, chunk);
     load_cv_tile(a, p, valid, s_cv);
@@ -375,8 +379,8 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_path_kernel(VitArgs a
 // ---- D: end state of every chunk ---------------------------------------------------------------
 // One warp per lane, 32 chunks per coalesced load, the serial walk through shuffles.
 __global__ void __launch_bounds__(kLaneWarps * 32) hmm_backtrack_kernel(VitArgs a) {
-    const uint32_t lane_idx = blockIdx.x * kLaneWarps + (threadIdx.x >> 5), lane = lane_id();
-    if (lane_idx >= a.n_lanes) return;
+    const uint32_t lane_idx = a.lane_lo + blockIdx.x * kLaneWarps + (threadIdx.x >> 5), lane = lane_id();
+    if (lane_idx >= a.lane_hi) return;
     const unsigned long long c0 = a.chunk_off[lane_idx], c1 = a.chunk_off[lane_idx + 1];
     if (c1 == c0) return;
     uint32_t s = a.fin_state[lane_idx];
@@ -406,8 +410,8 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_states_kernel(VitArgs a) {
     extern __shared__ float s_dyn[];
     uint8_t *s_bp = reinterpret_cast<uint8_t *>(s_dyn);
     uint8_t *s_st = s_bp + kChunkThreads * kBpStride;
-    const unsigned long long chunk = (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
-    const bool valid = chunk < a.n_chunks;
+    const unsigned long long chunk = a.chunk_lo + (unsigned long long)blockIdx.x * kChunkThreads + threadIdx.x;
+    const bool valid = chunk < a.chunk_hi;
     ChunkPos p{0, 0, 0, 0};
     if (valid) p = locate_chunk(a, chunk);
     const uint32_t lane = lane_id(), wbase = (threadIdx.x & ~31u);
@@ -612,39 +616,82 @@ extern "C" int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *
     va.fin_state = static_cast<uint8_t *>(d_fin);
     va.bp = static_cast<uint8_t *>(d_bp);
     va.state = host ? static_cast<uint8_t *>(d_state) : stp;
-    const unsigned cblocks = (unsigned)((n_chunks + kChunkThreads - 1) / kChunkThreads);
-    const unsigned lblocks = (n_lanes + kLaneWarps - 1) / kLaneWarps;
-    const unsigned pblocks = (n_lanes + 31) / 32;
     const size_t smem_a = (size_t)kChunkThreads * kCvStride * 4;
     const size_t smem_c = smem_a + (size_t)kChunkThreads * kBpStride;
     const size_t smem_e = (size_t)kChunkThreads * kBpStride + (size_t)kChunkThreads * kStStride;
     CNVB_CUDA(ctx, cudaFuncSetAttribute(hmm_chunk_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c),
               "smem opt-in");
-    {
-        KernelSpan span(ctx, "hmm_chunk_matrix_kernel");
-        hmm_chunk_matrix_kernel<<<cblocks, kChunkThreads, smem_a, ctx->stream>>>(va);
+    // Lane groups on side streams: the per-lane scans (B, D) are latency-bound with one warp per lane
+    // and the chunk kernels (A, C) are issue-bound, so the chains of different groups overlap well.
+    // Groups are contiguous lane ranges with about the same number of chunks.  (Timing mode: one group.)
+    constexpr int kGroups = 3;
+    int n_groups = (ctx->timing || n_lanes < 2 * kGroups) ? 1 : kGroups;
+    if (n_groups > 1) {
+        for (int q = 0; q < kGroups && n_groups > 1; ++q) {
+            if (!ctx->side[q] && cudaStreamCreateWithFlags(&ctx->side[q], cudaStreamNonBlocking) != cudaSuccess) n_groups = 1;
+            if (n_groups > 1 && !ctx->side_join[q] &&
+                cudaEventCreateWithFlags(&ctx->side_join[q], cudaEventDisableTiming) != cudaSuccess)
+                n_groups = 1;
+        }
+        if (n_groups > 1 && !ctx->side_fork && cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming) != cudaSuccess)
+            n_groups = 1;
     }
-    CNVB_LAUNCHED(ctx, "hmm_chunk_matrix_kernel");
-    {
-        KernelSpan span(ctx, "hmm_boundary_kernel");
-        hmm_boundary_kernel<<<lblocks, kLaneWarps * 32, 0, ctx->stream>>>(va);
+    cudaStream_t main_stream = ctx->stream;
+    if (n_groups > 1) {
+        CNVB_CUDA(ctx, cudaEventRecord(ctx->side_fork, main_stream), "forking streams");
+        for (int q = 0; q < n_groups; ++q) CNVB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[q], ctx->side_fork, 0), "forking streams");
     }
-    CNVB_LAUNCHED(ctx, "hmm_boundary_kernel");
-    {
-        KernelSpan span(ctx, "hmm_chunk_path_kernel");
-        hmm_chunk_path_kernel<<<cblocks, kChunkThreads, smem_c, ctx->stream>>>(va);
+    uint32_t lane_cursor = 0;
+    for (int q = 0; q < n_groups; ++q) {
+        // lanes of group q: up to the lane where the chunk count passes (q + 1) / n_groups of the total
+        uint32_t l_hi = n_lanes;
+        if (q + 1 < n_groups) {
+            const unsigned long long want = n_chunks * (unsigned long long)(q + 1) / (unsigned long long)n_groups;
+            l_hi = lane_cursor;
+            while (l_hi < n_lanes && coffs[l_hi + 1] <= want) ++l_hi;
+        }
+        va.lane_lo = lane_cursor;
+        va.lane_hi = l_hi;
+        va.chunk_lo = coffs[lane_cursor];
+        va.chunk_hi = coffs[l_hi];
+        lane_cursor = l_hi;
+        const unsigned long long gc = va.chunk_hi - va.chunk_lo;
+        if (gc == 0) continue;
+        cudaStream_t st = n_groups > 1 ? ctx->side[q] : main_stream;
+        const unsigned cblocks = (unsigned)((gc + kChunkThreads - 1) / kChunkThreads);
+        const unsigned lblocks = (va.lane_hi - va.lane_lo + kLaneWarps - 1) / kLaneWarps;
+        ctx->stream = st;  // (KernelSpan records on the launching stream)
+        {
+            KernelSpan span(ctx, "hmm_chunk_matrix_kernel");
+            hmm_chunk_matrix_kernel<<<cblocks, kChunkThreads, smem_a, st>>>(va);
+        }
+        {
+            KernelSpan span(ctx, "hmm_boundary_kernel");
+            hmm_boundary_kernel<<<lblocks, kLaneWarps * 32, 0, st>>>(va);
+        }
+        {
+            KernelSpan span(ctx, "hmm_chunk_path_kernel");
+            hmm_chunk_path_kernel<<<cblocks, kChunkThreads, smem_c, st>>>(va);
+        }
+        {
+            KernelSpan span(ctx, "hmm_backtrack_kernel");
+            hmm_backtrack_kernel<<<lblocks, kLaneWarps * 32, 0, st>>>(va);
+        }
+        {
+            KernelSpan span(ctx, "hmm_states_kernel");
+            hmm_states_kernel<<<cblocks, kChunkThreads, smem_e, st>>>(va);
+        }
+        ctx->stream = main_stream;
+        ctx->launches += 5;
+        if (cudaGetLastError() != cudaSuccess) return fail(ctx, CNVB_ERR_CUDA, "launch of the HMM kernels");
     }
-    CNVB_LAUNCHED(ctx, "hmm_chunk_path_kernel");
-    {
-        KernelSpan span(ctx, "hmm_backtrack_kernel");
-        hmm_backtrack_kernel<<<lblocks, kLaneWarps * 32, 0, ctx->stream>>>(va);
+    if (n_groups > 1) {
+        for (int q = 0; q < n_groups; ++q) {
+            CNVB_CUDA(ctx, cudaEventRecord(ctx->side_join[q], ctx->side[q]), "joining streams");
+            CNVB_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->side_join[q], 0), "joining streams");
+        }
     }
-    CNVB_LAUNCHED(ctx, "hmm_backtrack_kernel");
-    {
-        KernelSpan span(ctx, "hmm_states_kernel");
-        hmm_states_kernel<<<cblocks, kChunkThreads, smem_e, ctx->stream>>>(va);
-    }
-    CNVB_LAUNCHED(ctx, "hmm_states_kernel");
+    const unsigned pblocks = (n_lanes + 31) / 32;
     if (posterior) {
         std::vector<uint32_t> order(n_lanes);
         std::iota(order.begin(), order.end(), 0u);
