@@ -4,19 +4,17 @@
 // HBM-streaming byte kernel, algorithmic traffic 1 B/base in, 5 B/window out.
 //
 // A byte-at-a-time (or SWAR) classifier is instruction-issue bound long before HBM is busy
-// (round-1 ncu: 0.8 warp instructions per byte, 12 % DRAM throughput).  This kernel classifies
-// TWO bytes per shared-memory lookup: a 65536-entry u16 table (128 KB, built in the CTA's shared
-// memory at kernel start; one persistent 1024-thread CTA per SM) maps a byte pair to its packed
-// class counts
+// (round-1 ncu: 0.8 warp instructions per byte, 12 % DRAM throughput).  The kernels classify TWO
+// bytes per shared-memory lookup: a 65536-entry u16 table (128 KB, built once per context, copied by
+// every CTA; one persistent 1024-thread CTA per SM) maps a byte pair to its packed class counts
 //   bits 0..6 #[GCgc]   bits 7..13 #[ACGTacgt]   bits 14.. #[Nn]   (entries hold 0..2 per field)
 // with   [CGcg] <=> (b & 0xDB) == 0x43    [Aa] <=> (b & 0xDF) == 0x41
 //        [Tt]   <=> (b & 0xDF) == 0x54    [Nn] <=> (b & 0xDF) == 0x4E
-// so a lane turns its 16 bytes (one 128-bit load) into counts with 8 LDS.U16 + 7 adds.  A group
-// of G lanes (power of two, 16*G >= wl + 30) owns one window per pass: the lanes read the
-// aligned 16-byte chunks overlapping the window (coalesced), bytes outside the window are zeroed
-// (0x00 belongs to no class), the group reduces with REDUX / shuffles and its first lane writes
-// gc and has_gap directly -- no counters in HBM, no atomics, no memset, no finalize pass,
-// bit-reproducible.
+// so a lane turns 16 bytes (one 128-bit load) into counts with 8 LDS.U16 + 8 adds.
+//   wl >= 128: refstats_lane_kernel -- G lanes walk one window's chunks in turn (see there);
+//   shorter windows / sequences >= 4 GB: refstats_lut_kernel -- a group of G lanes (16 G >= wl + 30)
+//   reads the aligned chunks overlapping the window once, masking the bytes of the neighbours.
+// No counters in HBM, no atomics, no memset, no finalize pass, bit-reproducible.
 #include "common.cuh"
 
 using namespace cnvb;
@@ -47,30 +45,20 @@ __device__ __forceinline__ void ref_store(float *__restrict__ gc, uint8_t *__res
     has_gap[W] = n != 0;
 }
 
-// Full-warp variant (G = 32, wl >= 226): one window per warp pass.
-//  * lanes 0..30 take the interior 16-byte chunks (all bytes inside the window, no masking),
-//  * the first and the last chunk of the window are shared with the neighbouring windows; their
-//    up to 16+16 bytes are classified one byte per lane (lanes 0..15 / 16..31) through the same
-//    table (pair = byte | 0x00 << 8), so no lane ever runs a masking slow path,
-//  * window totals come from ONE REDUX over 10-bit packed fields when wl < 1024 (PACKED), else
-//    from three; the warp parks them in lane (pass mod 32) and every 32 passes all lanes do
-//    their f32 division and stores together.
-// Offsets are 32-bit (the host guarantees len + 16 < 2^32) and advance incrementally.
-// the table is built once per context in HBM (L2-resident afterwards); every CTA copies its 128 KB
-// with 16-byte loads instead of classifying 65536 pairs again at every launch
-// the two table indices of a 32-bit word (two byte pairs), in place; a bijection on each 16-bit half
+// The two table indices of a 32-bit word (two byte pairs), in place; a bijection on each 16-bit half.
+// The shared-memory bank of an entry is (index >> 1) & 31.  Genomic text uses about ten byte values, so
+// indexing by (b1 << 8 | b0) would put all lookups of a warp into the five banks that b0 alone selects.
+// A, C, G, T differ in bits 1 and 2; the index keeps b0's bits 1, 2 and mixes b1's bits 1, 2 into bits
+// 3, 4: the 16 upper-case pairs (and the 16 lower-case ones) get 16 different banks, lanes with the same
+// pair share one address (broadcast).  (b0's case bit is bank bit 4 already; mixing in b1's too costs
+// two more instructions per word and only matters where a warp reads both cases at once.)
 __device__ __forceinline__ uint32_t lut_swizzle(uint32_t w) { return w ^ ((w >> 6) & 0x00180018u); }
 __device__ __forceinline__ uint32_t lut_index(uint32_t pair) { return lut_swizzle(pair) & 0xffffu; }
 
+// the table is built once per context in HBM (L2-resident afterwards); every CTA copies its 128 KB
+// with 16-byte loads instead of classifying 65536 pairs again at every launch
 __global__ void refstats_build_lut_kernel(uint16_t *__restrict__ lut) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // The shared-memory bank of an entry is (index >> 1) & 31.  Genomic text uses about ten byte values,
-    // so indexing by (b1 << 8 | b0) would put all lookups of a warp into the five banks that b0 alone
-    // selects.  A, C, G, T differ in bits 1 and 2; the index therefore keeps b0's bits 1, 2 and mixes
-    // b1's bits 1, 2 into bits 3, 4: the 16 upper-case pairs (and the 16
-    // lower-case ones) get 16 different banks, lanes with the same pair share one address (broadcast).
-    // (b0's case bit is bank bit 4 already; mixing in b1's too costs two more instructions per word and
-    // only matters where a warp reads upper- and lower-case text at once.)
     if (i < 65536u) lut[lut_index(i)] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
 }
 __device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__restrict__ lut) {
@@ -78,96 +66,6 @@ __device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__rest
     uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
     for (uint32_t i = threadIdx.x; i < 65536u * 2u / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
-}
-
-template <bool PACKED>
-__global__ void __launch_bounds__(1024, 1) refstats_lut_warp_kernel(RefArgs a, uint32_t num_bins,
-                                                                    const uint16_t *__restrict__ lut,
-                                                                    float *__restrict__ gc,
-                                                                    uint8_t *__restrict__ has_gap) {
-    extern __shared__ __align__(16) uint16_t s_lut[];  // [65536]
-    load_lut(s_lut, lut);
-    const uint32_t lane = lane_id();
-    const uint32_t step = gridDim.x * (blockDim.x >> 5);
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(a.seq);
-    const uint32_t mis = (uint32_t)(addr & 15u);
-    const uint8_t *__restrict__ basep = reinterpret_cast<const uint8_t *>(addr - mis);  // 16-byte aligned
-    const int4 *__restrict__ base4 = reinterpret_cast<const int4 *>(basep);
-    const uint32_t wl = a.wl, end_off = (uint32_t)a.len + mis, stride_off = step * wl;
-    const uint32_t edge_hi = lane >= 16u;         // this lane classifies a byte of the LAST chunk
-    const uint32_t edge_lane = lane & 15u;
-
-    uint32_t st_g = 0, st_c = 0, st_n = 0, st_w = 0xffffffffu;  // parked results of this lane
-    uint32_t W = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t os = W * wl + mis;  // offset of the window start from the aligned base
-    // prefetched inputs of the window about to be counted
-    int4 raw = make_int4(0, 0, 0, 0);
-    uint32_t ebyte = 0;
-    if (W < num_bins) {
-        const uint32_t oe = min(os + wl, end_off), cf = os >> 4, cl = (oe - 1u) >> 4;
-        if (cf + 1u + lane < cl) raw = ld_stream(base4 + cf + 1u + lane);
-        const uint32_t bo = ((edge_hi ? cl : cf) << 4) + edge_lane;
-        if (edge_hi ? bo < oe : bo >= os) ebyte = basep[bo];
-    }
-    for (uint32_t pass = 0; W < num_bins; W += step, os += stride_off, ++pass) {
-        const uint32_t oe = min(os + wl, end_off), cf = os >> 4, cl = (oe - 1u) >> 4;
-        const int4 craw = raw;
-        const uint32_t cbyte = ebyte;
-        raw = make_int4(0, 0, 0, 0);
-        ebyte = 0;
-        if (W + step < num_bins) {  // next window of this warp
-            const uint32_t osn = os + stride_off, oen = min(osn + wl, end_off);
-            const uint32_t cfn = osn >> 4, cln = (oen - 1u) >> 4;
-            if (cfn + 1u + lane < cln) raw = ld_stream(base4 + cfn + 1u + lane);
-            const uint32_t bo = ((edge_hi ? cln : cfn) << 4) + edge_lane;
-            if (edge_hi ? bo < oen : bo >= osn) ebyte = basep[bo];
-        }
-        // one edge byte + eight byte pairs: packed 5-bit counts, at most 17 per field
-        uint32_t t = s_lut[lut_index(cbyte)];
-        {
-            const uint32_t w[4] = {lut_swizzle((uint32_t)craw.x), lut_swizzle((uint32_t)craw.y), lut_swizzle((uint32_t)craw.z),
-                                   lut_swizzle((uint32_t)craw.w)};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) t += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
-        }
-        uint32_t g = t & 127u, c = (t >> 7) & 127u, n = t >> 14;
-        if (cf + 33u < cl) {  // windows longer than 31 interior chunks (warp-uniform)
-            for (uint32_t k = cf + 33u + lane; __any_sync(0xffffffffu, k < cl); k += 32u) {
-                if (k < cl) {
-                    const int4 x = ld_stream(base4 + k);
-                    const uint32_t w[4] = {lut_swizzle((uint32_t)x.x), lut_swizzle((uint32_t)x.y), lut_swizzle((uint32_t)x.z),
-                                           lut_swizzle((uint32_t)x.w)};
-                    uint32_t u = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) u += (uint32_t)s_lut[w[j] & 0xffffu] + (uint32_t)s_lut[w[j] >> 16];
-                    g += u & 127u;
-                    c += (u >> 7) & 127u;
-                    n += u >> 14;
-                }
-            }
-        }
-        if (PACKED) {  // wl < 1024: every field of the warp total fits in 10 bits
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, g | (c << 10) | (n << 20));
-            g = tot & 1023u;
-            c = (tot >> 10) & 1023u;
-            n = tot >> 20;
-        } else {
-            g = __reduce_add_sync(0xffffffffu, g);
-            c = __reduce_add_sync(0xffffffffu, c);
-            n = __reduce_add_sync(0xffffffffu, n);
-        }
-        if (lane == (pass & 31u)) {
-            st_g = g;
-            st_c = c;
-            st_n = n;
-            st_w = W;
-        }
-        if ((pass & 31u) == 31u) {
-            if (st_w != 0xffffffffu) ref_store(gc, has_gap, st_w, st_g, st_c, st_n);
-            st_w = 0xffffffffu;
-        }
-    }
-    if (st_w != 0xffffffffu) ref_store(gc, has_gap, st_w, st_g, st_c, st_n);
 }
 
 // Lane-group variant (wl >= 128): G lanes own one window and walk its 16-byte chunks in turn, so the
@@ -384,18 +282,6 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
                 CNVB_REF_LANE(32)
             }
 #undef CNVB_REF_LANE
-        } else if (G == 32 && len < 0xFFFFFF00ull) {
-            blocks = (nb + 31) / 32;
-            if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;
-            if (window_length < 1024) {
-                CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_warp_kernel<true>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
-                refstats_lut_warp_kernel<true><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_lut, d_gc, d_gap);
-            } else {
-                CNVB_CUDA(ctx, cudaFuncSetAttribute(refstats_lut_warp_kernel<false>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
-                refstats_lut_warp_kernel<false><<<(unsigned)blocks, 1024, smem, ctx->stream>>>(a, (uint32_t)nb, d_lut, d_gc, d_gap);
-            }
         } else {
 #define CNVB_REF_LAUNCH(GG)                                                                          \
     case GG:                                                                                         \
