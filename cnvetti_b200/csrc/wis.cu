@@ -452,8 +452,8 @@ int wis_distances_dev(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint
                       const cnvb_wis_opts *o, uint32_t row_begin, uint32_t row_end, float *d_dist, uint32_t *d_idx) {
     const uint32_t k = T < o->max_ref_targets ? T : o->max_ref_targets;
     uint32_t engine = o->engine;
-    if (engine == CNVB_WIS_ENGINE_AUTO)  // the tensor engine pays off for large panels and holds A resident (S <= 128)
-        engine = (T >= 4096 && S <= kMaxKBlocks * kKBlock && k <= kMaxTensorK) ? CNVB_WIS_ENGINE_TENSOR
+    if (engine == CNVB_WIS_ENGINE_AUTO)  // the tensor engine pays off for large panels
+        engine = (T >= 4096 && S <= kMaxTensorS && k <= kMaxTensorK) ? CNVB_WIS_ENGINE_TENSOR
                                                                              : CNVB_WIS_ENGINE_EXACT;
     ctx->wis_stats[0] = row_end - row_begin;
     ctx->wis_stats[1] = ctx->wis_stats[2] = ctx->wis_stats[3] = 0;

@@ -56,6 +56,7 @@ constexpr uint32_t kMaxKBlocks = 2;   // A stays resident: Kp <= 128
 constexpr uint32_t kStages = 8;       // B ring: 8 x 16 KB
 constexpr uint32_t kTileBytes = 128 * kKBlock * 2;  // 16 KB: 128 rows x 64 fp16
 constexpr uint32_t kCandCap = 2048;   // candidate buffer entries per row
+constexpr uint32_t kMaxTensorS = 4096;  // samples (K dimension) the tensor engine takes
 constexpr uint32_t kMaxTensorK = 384;  // 32 x 16 first-window candidates must hold k after same-contig drops
 constexpr uint32_t kEpiWarps = 16;     // 4 per TMEM lane quarter, each a quarter of the tile's columns
 constexpr uint32_t kSweepThreads = (4 + kEpiWarps) * 32;
@@ -124,14 +125,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | ((kTileCols >> 3) << 17) | ((128u >> 4) << 24);
 
 // ---- prep -----------------------------------------------------------------------------------------
-// column sums (f64) and the largest magnitude: a warp walks rows, lanes hold the columns lane + 32 q
+// column sums (f64) and the largest magnitude: a warp walks rows, lanes hold the columns lane + 32 q of
+// the 128-column slice blockIdx.y
 __global__ void __launch_bounds__(256) wis_colsum_kernel(const float *__restrict__ X, uint32_t T, uint32_t S,
                                                          double *__restrict__ colsum, float *__restrict__ absmax) {
-    constexpr uint32_t kQ = kMaxKBlocks * kKBlock / 32;  // S <= 128
-    __shared__ double s_sum[kMaxKBlocks * kKBlock];
-    for (uint32_t s = threadIdx.x; s < kMaxKBlocks * kKBlock; s += blockDim.x) s_sum[s] = 0.0;
+    constexpr uint32_t kQ = 4;
+    __shared__ double s_sum[128];
+    for (uint32_t s = threadIdx.x; s < 128u; s += blockDim.x) s_sum[s] = 0.0;
     __syncthreads();
-    const uint32_t lane = lane_id(), n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t lane = lane_id(), n_warps = gridDim.x * (blockDim.x >> 5), c0 = blockIdx.y * 128u;
     double acc[kQ];
     float mx = 0.0f;
 #pragma unroll
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) wis_colsum_kernel(const float *__restrict
     for (uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < T; t += n_warps) {
 #pragma unroll
         for (uint32_t q = 0; q < kQ; ++q) {
-            const uint32_t c = lane + 32 * q;
+            const uint32_t c = c0 + lane + 32 * q;
             if (c < S) {
                 const float v = X[(size_t)t * S + c];
                 acc[q] += (double)v;
@@ -149,9 +151,9 @@ __global__ void __launch_bounds__(256) wis_colsum_kernel(const float *__restrict
     }
 #pragma unroll
     for (uint32_t q = 0; q < kQ; ++q)
-        if (lane + 32 * q < S) atomicAdd(&s_sum[lane + 32 * q], acc[q]);
+        if (c0 + lane + 32 * q < S) atomicAdd(&s_sum[lane + 32 * q], acc[q]);
     __syncthreads();
-    for (uint32_t c = threadIdx.x; c < S; c += blockDim.x) atomicAdd(&colsum[c], s_sum[c]);
+    for (uint32_t c = threadIdx.x; c < 128u && c0 + c < S; c += blockDim.x) atomicAdd(&colsum[c0 + c], s_sum[c]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) atomicMax(reinterpret_cast<int *>(absmax), __float_as_int(mx));  // non-negative floats order as ints
@@ -345,7 +347,11 @@ struct SweepArgs {
     uint32_t *cand_cnt;      // [rows]
 };
 
-template <bool FIRST>
+// STREAM: more than kMaxKBlocks K-blocks (S > 128): the A operand does not fit beside the B ring, so
+// both operands stream through kStreamStages stages of (A rows 0..127 | A rows 128..255 | B) K-blocks.
+constexpr uint32_t kStreamStages = 4;  // x 48 KB
+
+template <bool FIRST, bool STREAM>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
@@ -399,19 +405,30 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
-            for (uint32_t h = 0; h < 2; ++h)
-                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
-                    tma_load_2d(a_base + (h * kMaxKBlocks + kb) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
-                                (int32_t)(row0 + h * 128));
+            if (!STREAM) {
+                mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
+                for (uint32_t h = 0; h < 2; ++h)
+                    for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
+                        tma_load_2d(a_base + (h * kMaxKBlocks + kb) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
+                                    (int32_t)(row0 + h * 128));
+            }
+            constexpr uint32_t n_stages = STREAM ? kStreamStages : kStages;
             uint32_t st = 0, ph = 0;
             for (uint32_t it = 0; it < n_tiles; ++it) {
                 const int32_t j0 = (int32_t)(CNVB_TILE_AT(it) * kTileCols);
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                     mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
-                    mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
-                    tma_load_2d(b_base + st * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
-                    if (++st == kStages) {
+                    if (STREAM) {
+                        const uint32_t sb = a_base + st * 3u * kTileBytes;
+                        mbar_expect_tx(bar_b_full + 8 * st, 3u * kTileBytes);
+                        tma_load_2d(sb, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)row0);
+                        tma_load_2d(sb + kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)(row0 + 128));
+                        tma_load_2d(sb + 2u * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                    } else {
+                        mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
+                        tma_load_2d(b_base + st * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                    }
+                    if (++st == n_stages) {
                         st = 0;
                         ph ^= 1u;
                     }
@@ -421,39 +438,65 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            mbar_wait(bar_a_full, 0);
-            tc_fence_after();
+            if (!STREAM) {
+                mbar_wait(bar_a_full, 0);
+                tc_fence_after();
+            }
+            constexpr uint32_t n_stages = STREAM ? kStreamStages : kStages;
             uint32_t st = 0, ph = 0, as = 0, aph = 0;
             // descriptors differ from these bases only in the start-address field (16-byte units):
-            // +2 per K16 slab inside a 128-byte swizzle row, + kTileBytes / 16 per B stage
+            // +2 per K16 slab inside a 128-byte swizzle row, + bytes / 16 per tile or stage
             uint64_t adesc[2][kMaxKBlocks];
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h)
 #pragma unroll
                 for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) adesc[h][kb] = umma_desc(a_base + (h * kMaxKBlocks + kb) * kTileBytes);
-            const uint64_t bdesc0 = umma_desc(b_base);
+            const uint64_t bdesc0 = umma_desc(b_base), sdesc0 = umma_desc(a_base);
             for (uint32_t it = 0; it < n_tiles; ++it) {
                 mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
                 tc_fence_after();
-#pragma unroll
-                for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) {
-                    if (kb < a.n_kblocks) {
+                if (STREAM) {
+                    for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                         mbar_wait(bar_b_full + 8 * st, ph);
                         tc_fence_after();
-                        const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kTileBytes >> 4));
+                        const uint64_t sd = sdesc0 + (uint64_t)(st * (3u * kTileBytes >> 4));
 #pragma unroll
                         for (uint32_t h = 0; h < 2; ++h) {
                             const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
 #pragma unroll
                             for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
                                 if (kb * (kKBlock / 16) + kk < a.k_mmas)
-                                    tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
+                                    tc_mma_f16(d_tmem, sd + (uint64_t)(h * (kTileBytes >> 4)) + 2u * kk,
+                                               sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, kIdesc, (kb | kk) != 0u);
                             }
                         }
-                        tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
-                        if (++st == kStages) {
+                        tc_commit(bar_b_empty + 8 * st);
+                        if (++st == n_stages) {
                             st = 0;
                             ph ^= 1u;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) {
+                        if (kb < a.n_kblocks) {
+                            mbar_wait(bar_b_full + 8 * st, ph);
+                            tc_fence_after();
+                            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kTileBytes >> 4));
+#pragma unroll
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
+#pragma unroll
+                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                                    if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                        tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
+                                }
+                            }
+                            tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
+                            if (++st == n_stages) {
+                                st = 0;
+                                ph ^= 1u;
+                            }
                         }
                     }
                 }
@@ -1044,9 +1087,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     const uint32_t rows = row_end - row_begin;
     if (rows == 0) return 0;
     const uint32_t Kp = ((S + kKBlock - 1) / kKBlock) * kKBlock;
-    if (Kp > kMaxKBlocks * kKBlock)
-        return fail(ctx, CNVB_ERR_INVALID, "tensor engine: more than %u samples are not supported yet; use the exact engine",
-                    kMaxKBlocks * kKBlock);
+    if (Kp > kMaxTensorS)
+        return fail(ctx, CNVB_ERR_INVALID, "tensor engine: more than %u samples; use the exact engine", kMaxTensorS);
+    const bool stream_a = Kp > kMaxKBlocks * kKBlock;  // A no longer fits beside the B ring: stream both operands
     if (k > kMaxTensorK) return fail(ctx, CNVB_ERR_INVALID, "tensor engine: max_ref_targets > %u", kMaxTensorK);
     const uint32_t n_tiles = (T + kTileCols - 1) / kTileCols;
     const uint32_t Tpad = n_tiles * kTileCols;
@@ -1103,7 +1146,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     cudaMemsetAsync(seen, 0, rows * 4, st);
     cudaMemsetAsync(ovf_list, 0, (rows + 1) * 4, st);
     cudaMemsetAsync(counters, 0, 32, st);
-    wis_colsum_kernel<<<std::min<uint32_t>((T + 7) / 8, (uint32_t)ctx->sm_count * 8), 256, 0, st>>>(dX, T, S, colsum, scal);
+    wis_colsum_kernel<<<dim3(std::min<uint32_t>((T + 7) / 8, (uint32_t)ctx->sm_count * 8), (S + 127) / 128), 256, 0, st>>>(
+        dX, T, S, colsum, scal);
     CNVB_LAUNCHED(ctx, "wis_colsum_kernel");
     float absmax = 0.0f;
     CNVB_CUDA(ctx, cudaMemcpyAsync(&absmax, scal, 4, cudaMemcpyDeviceToHost, st), "reading the panel range");
@@ -1154,10 +1198,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
-    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-              "smem opt-in");
-    CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-              "smem opt-in");
+    auto sweep_first = stream_a ? wis_sweep_kernel<true, true> : wis_sweep_kernel<true, false>;
+    auto sweep_next = stream_a ? wis_sweep_kernel<false, true> : wis_sweep_kernel<false, false>;
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
+    CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     BoundConsts bc{};
     {
         const double g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
@@ -1227,7 +1271,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (32 * tiles0 >= 5 * k / 4) {
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
-            wis_sweep_kernel<true><<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+            sweep_first<<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         ca.discard = 1;
@@ -1254,7 +1298,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         tiles_before = tiles_now;
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
-            wis_sweep_kernel<false><<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+            sweep_next<<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         {

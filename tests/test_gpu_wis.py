@@ -117,7 +117,9 @@ def test_modcov_parity(oracle, ctx, device):
 
 
 @pytest.mark.parametrize("T,S,k,ncontig,device", [(5000, 100, 100, 22, True), (4321, 37, 64, 5, False),
-                                                 (9000, 128, 100, 22, True)])
+                                                 (9000, 128, 100, 22, True),
+                                                 # more than 128 samples: both operands stream through the K-block ring
+                                                 (4400, 300, 50, 7, True), (4100, 130, 40, 5, False), (4200, 1000, 30, 4, True)])
 def test_wis_tensor_engine_matches_reference_sets(oracle, ctx, T, S, k, ncontig, device):
     """tcgen05 contraction as candidate filter + exact re-scoring: sets, order and distances
     bit-exact against the oracle's f32-sequential distances."""
