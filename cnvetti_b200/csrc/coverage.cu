@@ -108,96 +108,174 @@ __device__ __forceinline__ uint32_t frag_fail2(uint32_t F) {
     return G & T;
 }
 
-template <bool PILES, bool WL_SMALL>
+// 1 << s with PTX semantics: shift amounts of 32 or more give 0 (no branch, no select)
+__device__ __forceinline__ uint32_t shl_clamp1(uint32_t s) {
+    uint32_t r;
+    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(s));
+    return r;
+}
+
+// Pass bits of four consecutive reads, as bit 7 of byte e (0x80808080-masked):
+//   * mapq >= minq for the four packed bytes at once: t = (mq | H) - (minq4 & ~H) cannot borrow
+//     between bytes and has bit 7 = (low 7 bits of mapq >= low 7 bits of minq); the top bits
+//     decide when they differ;
+//   * frag_fail2 leaves a non-zero 16-bit half (<= 0x3F02) for a failing read: + 0x7FFF carries
+//     it into bit 15 of the half without touching the neighbour; PRMT gathers the four bits.
+__device__ __forceinline__ uint32_t frag_pass4(uint32_t mq, uint2 fl, uint32_t minq4) {
+    constexpr uint32_t H = 0x80808080u;
+    const uint32_t t = (mq | H) - (minq4 & ~H);
+    const uint32_t d = mq ^ minq4;
+    const uint32_t ge = (~d & t) | (d & mq);
+    const uint32_t nz0 = frag_fail2(fl.x) + 0x7fff7fffu, nz1 = frag_fail2(fl.y) + 0x7fff7fffu;
+    const uint32_t fail = __byte_perm(nz0, nz1, 0x7531);
+    return ge & ~fail & H;
+}
+
+template <bool PILES, bool WL_SMALL, int Q>
 __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
+    // A warp step covers Q consecutive groups of 32 quads (Q x 128 reads): lane l owns quad
+    // qb + 32 u + l of group u, so every load instruction of the warp is one contiguous
+    // 512 / 128 / 256-byte run.  The per-step warp work (anchor, division, REDUX, counter REDs)
+    // is paid once per Q x 128 reads; the per-read work is integer arithmetic on packed words
+    // without predicates (the earlier predicate-per-read form ran out of predicate registers).
     const uint32_t nq = (uint32_t)(a.n >> 2);  // full quads (a launch covers < 2^32 reads)
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t stride = gridDim.x * blockDim.x * Q;
     const int4 *__restrict__ mid4 = reinterpret_cast<const int4 *>(a.mid);
     const uint32_t *__restrict__ mq4 = reinterpret_cast<const uint32_t *>(a.mapq);
     const uint2 *__restrict__ fl4 = reinterpret_cast<const uint2 *>(a.flags);
     const uint32_t lane = lane_id();
     const uint32_t wl = a.div.d;
-    const uint32_t minq = a.min_mapq, minq8 = minq << 8, minq16 = minq << 16, minq24 = minq << 24;
+    const uint32_t minq4 = a.min_mapq * 0x01010101u;  // (launcher: min_mapq <= 255)
     constexpr uint32_t kFailFlags = 0x01000100u;  // "secondary" in both halves: never counted
     uint32_t n_proc = 0, n_skip = 0, n_oob = 0;
 
     // warp-uniform trip count so that the warp collectives below stay converged
-    uint32_t qb = blockIdx.x * blockDim.x + threadIdx.x - lane;
+    uint32_t qb = (blockIdx.x * blockDim.x + threadIdx.x - lane) * Q;
     // software pipeline: the loads of step i+1 are in flight while step i is classified
-    int4 m = make_int4(0, 0, 0, 0);
-    uint32_t mq = 0;
-    uint2 fl = make_uint2(kFailFlags, kFailFlags);
-    if (qb + lane < nq) {
-        m = ld_stream(mid4 + qb + lane);
-        mq = ld_stream(mq4 + qb + lane);
-        fl = ld_stream(fl4 + qb + lane);
+    int4 m[Q];
+    uint32_t mq[Q];
+    uint2 fl[Q];
+#pragma unroll
+    for (int u = 0; u < Q; ++u) {
+        m[u] = make_int4(0, 0, 0, 0);
+        mq[u] = 0;
+        fl[u] = make_uint2(kFailFlags, kFailFlags);
+        const uint32_t i = qb + 32u * u + lane;
+        if (i < nq) {
+            m[u] = ld_stream(mid4 + i);
+            mq[u] = ld_stream(mq4 + i);
+            fl[u] = ld_stream(fl4 + i);
+        }
     }
     for (; qb < nq; qb += stride) {
-        const int4 cm = m;
-        const uint32_t cmq = mq;
-        const uint2 cfl = fl;
-        const uint32_t nx = qb + stride + lane;
-        fl = make_uint2(kFailFlags, kFailFlags);
-        if (nx < nq && nx >= stride) {  // (second test: no wrap-around of the 32-bit index)
-            m = ld_stream(mid4 + nx);
-            mq = ld_stream(mq4 + nx);
-            fl = ld_stream(fl4 + nx);
-        }
-        const uint32_t mids[4] = {(uint32_t)cm.x, (uint32_t)cm.y, (uint32_t)cm.z, (uint32_t)cm.w};
-        const uint32_t x0 = frag_fail2(cfl.x), x1 = frag_fail2(cfl.y);
-        bool w[4];
-        // mapq bytes are compared in place (byte e >= minq  <=>  masked word >= minq << 8e)
-        w[0] = ((x0 & 0xffffu) == 0u) && ((cmq & 0xffu) >= minq);
-        w[1] = ((x0 >> 16) == 0u) && ((cmq & 0xff00u) >= minq8);
-        w[2] = ((x1 & 0xffffu) == 0u) && ((cmq & 0xff0000u) >= minq16);
-        w[3] = ((x1 >> 16) == 0u) && (cmq >= minq24);
-        if (PILES) {
+        uint32_t mids[Q][4], pass[Q];
+        const uint32_t nb = qb + stride;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                n_proc += w[e];
-                if (w[e] && pile_hit(a.pile_start, a.pile_end, a.n_pile, mids[e])) {
-                    w[e] = false;
-                    n_skip += 1;
+        for (int u = 0; u < Q; ++u) {
+            mids[u][0] = (uint32_t)m[u].x;
+            mids[u][1] = (uint32_t)m[u].y;
+            mids[u][2] = (uint32_t)m[u].z;
+            mids[u][3] = (uint32_t)m[u].w;
+            pass[u] = frag_pass4(mq[u], fl[u], minq4);
+            const uint32_t nx = nb + 32u * u + lane;
+            fl[u] = make_uint2(kFailFlags, kFailFlags);
+            if (nx < nq && nb >= stride) {  // (second test: no wrap-around of the 32-bit index)
+                m[u] = ld_stream(mid4 + nx);
+                mq[u] = ld_stream(mq4 + nx);
+                fl[u] = ld_stream(fl4 + nx);
+            }
+            if (PILES) {
+                n_proc += __popc(pass[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if ((pass[u] >> (8 * e + 7) & 1u) && pile_hit(a.pile_start, a.pile_end, a.n_pile, mids[u][e])) {
+                        pass[u] &= ~(0x80u << (8 * e));
+                        n_skip += 1;
+                    }
                 }
             }
         }
-        // anchor window: the first counting read of the warp
-        const uint32_t lane_anchor = w[0] ? mids[0] : (w[1] ? mids[1] : (w[2] ? mids[2] : mids[3]));
-        const unsigned has = __ballot_sync(0xffffffffu, w[0] || w[1] || w[2] || w[3]);
-        if (has == 0u) continue;
-        const uint32_t amid = __shfl_sync(0xffffffffu, lane_anchor, __ffs(has) - 1);
-        const uint32_t A = fastdiv(amid, a.div);
-        const uint32_t base = (A - 1u) * wl;  // may wrap for A == 0; differences below stay exact
-        uint32_t acc = 0u, outl = 0u;
+        // anchor window: the smallest first-of-quad counting read of the step's first group;
+        // if none of those 32 reads counts the anchor is far away and the step takes the
+        // per-read path below
+        uint32_t any_pass = pass[0];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            // window offset k = (mid - base) / wl by a multiply-high (FMA pipe) instead of a chain
-            // of compares (ALU pipe, the binding pipe of this kernel): with the rounded-UP magic
-            // the quotient is exact for r < 4*wl whenever 4*wl^2 <= 2^32, and any r >= 4*wl still
-            // yields k >= 4, which is all the outlier test needs.
-            const uint32_t r = mids[e] - base;
-            const uint32_t k = WL_SMALL ? __umulhi(r, a.magic_up) : fastdiv(r, a.div);
-            const bool in4 = k < 4u;
-            acc += (w[e] && in4) ? (1u << (8u * k)) : 0u;
-            outl |= (w[e] && !in4) ? (1u << e) : 0u;
-        }
-        const uint32_t tot = __reduce_add_sync(0xffffffffu, acc);
-        // without piles every read passing the filter is counted: tally per warp, not per read
-        if (!PILES && lane == 0u) n_proc += (tot * 0x01010101u) >> 24;
-        if (lane < 4u) {
-            const uint32_t cnt = (tot >> (8u * lane)) & 0xffu;
-            const uint32_t bin = A - 1u + lane;
-            if (cnt) {
-                if (bin < a.num_bins) atomicAdd(&a.counters[bin], cnt); else n_oob += cnt;
+        for (int u = 1; u < Q; ++u) any_pass |= pass[u];
+        if (!__any_sync(0xffffffffu, any_pass != 0u)) continue;
+        const uint32_t amid = __reduce_min_sync(0xffffffffu, (pass[0] & 0x80u) ? mids[0][0] : 0xffffffffu);
+        if (amid >= 0x80000000u) {
+            // No usable anchor (none of the 32 candidates counts, or a negative centre): window
+            // offsets relative to a base near 2^32 would be ambiguous modulo 2^32, so every counting
+            // read of the step takes the per-read path.  (Never happens for sorted, sane input.)
+#pragma unroll
+            for (int u = 0; u < Q; ++u) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (pass[u] >> (8 * e + 7) & 1u) {
+                        if (!PILES) n_proc += 1;
+                        const uint32_t b = fastdiv(mids[u][e], a.div);
+                        if (b < a.num_bins) atomicAdd(&a.counters[b], 1u); else n_oob += 1;
+                    }
+                }
             }
+            continue;
         }
-        if (__any_sync(0xffffffffu, outl != 0u)) {  // reads far from the anchor: one RED each
+        const uint32_t A = fastdiv(amid, a.div);
+        // base < 2^31 (or -wl for A == 0): r = mid - base is the true difference or >= 2^31
+        const uint32_t base = (A - 1u) * wl;
+        uint32_t acc[Q], n_out = 0u;
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            acc[u] = 0u;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (outl & (1u << e)) {
-                    if (!PILES) n_proc += 1;
-                    const uint32_t b = fastdiv(mids[e], a.div);
-                    if (b < a.num_bins) atomicAdd(&a.counters[b], 1u); else n_oob += 1;
+                // window offset k = (mid - base) / wl by a multiply-high with the rounded-UP magic:
+                // exact for r < 4*wl whenever 4*wl^2 <= 2^32, and any r >= 4*wl still yields k >= 4.
+                // A failing read gets bit 31 of r set (k >= 2^31 / wl >= 4); 8 k < 2^32 for wl >= 16,
+                // so its shift amount is >= 32 and it contributes nothing.
+                const uint32_t failbit = ~(pass[u] << (24 - 8 * e)) & 0x80000000u;
+                const uint32_t r = (mids[u][e] - base) | failbit;
+                if (WL_SMALL) {
+                    acc[u] += shl_clamp1(__umulhi(r, a.magic_up) << 3);
+                } else {
+                    const uint32_t k = fastdiv(r, a.div);
+                    acc[u] += (k < 4u && !failbit) ? (1u << (8u * k)) : 0u;
+                }
+            }
+            // counting reads of the quad that fell outside the four windows
+            n_out += __popc(pass[u]) - ((acc[u] * 0x01010101u) >> 24);
+        }
+        // 8-bit fields: one group adds at most 128 to a field over the warp, two could reach 256,
+        // so every group has its own REDUX
+        uint32_t cnt4 = 0u, tot_all = 0u;
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, acc[u]);
+            cnt4 += (tot >> (8u * (lane & 3u))) & 0xffu;
+            tot_all += (tot * 0x01010101u) >> 24;
+        }
+        // without piles every read passing the filter is counted: tally per warp, not per read
+        if (!PILES && lane == 0u) n_proc += tot_all;
+        if (lane < 4u) {
+            const uint32_t bin = A - 1u + lane;
+            if (cnt4) {
+                if (bin < a.num_bins) atomicAdd(&a.counters[bin], cnt4); else n_oob += cnt4;
+            }
+        }
+        if (__any_sync(0xffffffffu, n_out != 0u)) {  // reads far from the anchor: one RED each
+#pragma unroll
+            for (int u = 0; u < Q; ++u) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (n_out != 0u && (pass[u] >> (8 * e + 7) & 1u)) {
+                        const uint32_t r = mids[u][e] - base;
+                        const uint32_t k = WL_SMALL ? __umulhi(r, a.magic_up) : fastdiv(r, a.div);
+                        if (k >= 4u) {
+                            if (!PILES) n_proc += 1;
+                            const uint32_t b = fastdiv(mids[u][e], a.div);
+                            if (b < a.num_bins) atomicAdd(&a.counters[b], 1u); else n_oob += 1;
+                        }
+                    }
                 }
             }
         }
@@ -484,27 +562,34 @@ int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
         g.num_bins = (uint32_t)a->num_regions;
         g.div = make_fastdiv(a->opts.window_length);
         g.magic_up = (uint32_t)(((1ull << 32) + a->opts.window_length - 1) / a->opts.window_length);
-        g.wl_small = a->opts.window_length >= 2 && a->opts.window_length <= 32768;
+        g.wl_small = a->opts.window_length >= 16 && a->opts.window_length <= 32768;
         g.min_mapq = a->opts.min_mapq;
         g.pile_start = a->d_pile_start;
         g.pile_end = a->d_pile_end;
         g.n_pile = a->n_pile;
         g.stats = a->d_stats;
         const bool aligned = ((uintptr_t)g.mid % 16 == 0) && ((uintptr_t)g.mapq % 4 == 0) &&
-                             ((uintptr_t)g.flags % 8 == 0);
+                             ((uintptr_t)g.flags % 8 == 0) && g.min_mapq <= 255u;  // (packed byte compare)
         const uint64_t work = aligned ? (n + 3) / 4 : n;
         const uint64_t work_blocks = (work + 255) / 256;
+        static const int gw_quads = [] {  // quads per lane and step (tuning knob; 2 measured best)
+            const char *e = getenv("CNVB_GW_QUADS");
+            return e && atoi(e) == 1 ? 1 : 2;
+        }();
         {
             KernelSpan span(ctx, "frag_bin_gw_kernel");
             if (aligned) {
+#define CNVB_GW_LAUNCH_Q(P, S, Q) \
+    frag_bin_gw_kernel<P, S, Q><<<persistent_grid(ctx, frag_bin_gw_kernel<P, S, Q>, 256, 0, (work_blocks + Q - 1) / Q), 256, 0, ctx->stream>>>(g)
 #define CNVB_GW_LAUNCH(P, S) \
-    frag_bin_gw_kernel<P, S><<<persistent_grid(ctx, frag_bin_gw_kernel<P, S>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g)
+    do { if (gw_quads == 2) CNVB_GW_LAUNCH_Q(P, S, 2); else CNVB_GW_LAUNCH_Q(P, S, 1); } while (0)
                 if (a->n_pile) {
                     if (g.wl_small) CNVB_GW_LAUNCH(true, true); else CNVB_GW_LAUNCH(true, false);
                 } else {
                     if (g.wl_small) CNVB_GW_LAUNCH(false, true); else CNVB_GW_LAUNCH(false, false);
                 }
 #undef CNVB_GW_LAUNCH
+#undef CNVB_GW_LAUNCH_Q
             } else {
                 if (a->n_pile)
                     frag_bin_gw_scalar_kernel<true><<<persistent_grid(ctx, frag_bin_gw_scalar_kernel<true>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);

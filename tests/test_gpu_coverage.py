@@ -48,6 +48,31 @@ def test_frag_gw_parity(oracle, ctx, wl, min_mapq, device):
     assert lcvsd is None and np.array_equal(to_np(ft), oft)
 
 
+@pytest.mark.parametrize("wl,min_mapq", [(8, 0), (16, 127), (16, 128), (500, 200), (32768, 255), (40_000, 1),
+                                         (1000, 60)])
+def test_frag_gw_packed_filter_adversarial(oracle, ctx, wl, min_mapq):
+    """The kernel tests four mapq bytes / two flag words per instruction and forces failing reads
+    out of the window arithmetic: every mapq byte value, random flag bits, reads far from their
+    neighbours (per-read path), window lengths either side of the multiply-high fast path."""
+    L0, L = 1_400_000, 3_000_000  # unpaired centres are pos + end_pos: keep them inside the contig
+    d = synth.synth_bam_records(7, L0, 50_000)
+    rng = np.random.default_rng(1000 * wl + min_mapq)
+    n = d["pos"].size
+    d["mapq"] = rng.integers(0, 256, n).astype(np.uint8)
+    d["flag"] = (rng.integers(0, 4096, n) & rng.integers(0, 4096, n)).astype(np.uint16)
+    far = rng.random(n) < 0.05
+    d["pos"] = np.where(far, rng.integers(0, L0 - 1000, n), d["pos"]).astype(np.int32)
+    oopts = oracle.cov_opts(window_length=wl, min_mapq=min_mapq)
+    counts, proc, skip = oracle.frag_gw(oracle_reads(oracle, d), oopts, L)
+    assert proc > 0
+    opts = cb.CoverageOptions(window_length=wl, min_mapq=min_mapq)
+    for device in (None, "cuda"):
+        agg = cb.FragmentsGenomeWideAggregator(None, opts, L, ctx=ctx)
+        agg.put_fetched_records(soa_batch(d, device=device))
+        assert np.array_equal(to_np(agg.counts()), counts)
+        assert agg.num_processed() == proc and agg.num_skipped() == skip
+
+
 def test_frag_gw_streaming_unaligned_and_piles(oracle, ctx):
     L = 1_500_000
     d = synth.synth_bam_records(5, L, 40_000)
