@@ -68,11 +68,15 @@ __device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__rest
     __syncthreads();
 }
 
-// Lane-group variant (wl >= 128): G lanes own one window and walk its 16-byte chunks in turn, so the
-// inner loop is nothing but load -> eight table lookups -> add; the window logic (offsets, edge
-// masking, the G-lane reduction, the store) is paid once per window and lane instead of once per warp
-// pass.  G >= 2 so that the lanes of a group read whole 32-byte sectors; larger G only serves to fill
-// the machine when a contig has few windows.
+// Lane-group variant (wl >= 128): G lanes own one window and walk its interior 16-byte chunks in turn,
+// so the inner loop is nothing but load -> eight table lookups -> add.  The two edge chunks of a window
+// (whose foreign bytes must be masked) are peeled out of the loop: lane 0 of the group takes the first,
+// lane 1 the last, once per window.  G >= 2 so that the lanes of a group read whole 32-byte sectors;
+// larger G only serves to fill the machine when a contig has few windows.
+//
+// (Round-1 experiments on the index arithmetic -- halves by PRMT, doubling and adds as IMAD on the FMA
+// pipe, right shifts as IMAD.HI -- cut the ALU-pipe instructions by up to 30 % and left the time unchanged
+// (IMAD.HI / IMAD.WIDE made it worse): after the edge peeling the kernel waits on its loads, not on a pipe.)
 __device__ __forceinline__ uint32_t lut_counts(const uint16_t *s_lut, const uint32_t (&w)[4]) {
     uint32_t t = 0;
 #pragma unroll
@@ -105,36 +109,45 @@ __global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint3
         if (W < num_bins) {
             const uint32_t os = W * wl + mis, oe = min(os + wl, end_off);
             const uint32_t cf = os >> 4, cl = (oe - 1u) >> 4;
-            uint32_t acc = 0;  // packed 7-bit fields of the chunks in flight
-            // the G lanes take the chunks of the window in turn (together they read G x 16 contiguous
-            // bytes); kInFlight loads per lane are in flight before the first is consumed -- with one, the
-            // 1024 threads of an SM keep only 16 KB in flight, less than half of what HBM latency needs
-            for (uint32_t k = cf + sub; k <= cl; k += kInFlight * G) {
+            // edge chunks: issued first, consumed last
+            const uint32_t ek = sub == 0 ? cf : cl;
+            const bool has_edge = sub == 0 || (sub == 1 && cl != cf);
+            int4 edge = make_int4(0, 0, 0, 0);
+            if (has_edge) edge = __ldg(base4 + ek);
+            // the G lanes take the interior chunks of the window in turn (together they read G x 16
+            // contiguous bytes); kInFlight loads per lane are in flight before the first is consumed --
+            // with one, the 1024 threads of an SM keep only 16 KB in flight, less than half of what HBM
+            // latency needs
+            for (uint32_t k = cf + 1u + sub; k < cl; k += kInFlight * G) {
                 int4 raw[kInFlight];
 #pragma unroll
                 for (int u = 0; u < kInFlight; ++u) {
                     const uint32_t kk = k + u * G;
-                    raw[u] = kk <= cl ? __ldg(base4 + kk) : make_int4(0, 0, 0, 0);  // (0x00 is in no class)
+                    raw[u] = kk < cl ? __ldg(base4 + kk) : make_int4(0, 0, 0, 0);  // (0x00 is in no class)
                 }
+                uint32_t acc = 0;  // packed 7-bit fields: kInFlight x 16 <= 127
 #pragma unroll
                 for (int u = 0; u < kInFlight; ++u) {
-                    const uint32_t kk = k + u * G;
-                    uint32_t w[4] = {(uint32_t)raw[u].x, (uint32_t)raw[u].y, (uint32_t)raw[u].z, (uint32_t)raw[u].w};
-                    if (kk == cf || kk == cl) {  // window edges: zero the bytes of the neighbours
-                        const uint32_t c0 = kk << 4;
-                        const int lo = os > c0 ? (int)(os - c0) : 0, hi = oe < c0 + 16u ? (int)(oe - c0) : 16;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int x = min(max(lo - 4 * j, 0), 4), y = min(max(hi - 4 * j, 0), 4);
-                            w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
-                        }
-                    }
-                    acc += lut_counts(s_lut, w);  // 7-bit fields: kInFlight x 16 <= 127
+                    const uint32_t w[4] = {(uint32_t)raw[u].x, (uint32_t)raw[u].y, (uint32_t)raw[u].z, (uint32_t)raw[u].w};
+                    acc += lut_counts(s_lut, w);
                 }
                 g += acc & 127u;
                 c += (acc >> 7) & 127u;
                 n += acc >> 14;
-                acc = 0;
+            }
+            if (has_edge) {  // zero the bytes of the neighbouring windows
+                uint32_t w[4] = {(uint32_t)edge.x, (uint32_t)edge.y, (uint32_t)edge.z, (uint32_t)edge.w};
+                const uint32_t c0 = ek << 4;
+                const int lo = os > c0 ? (int)(os - c0) : 0, hi = oe < c0 + 16u ? (int)(oe - c0) : 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = min(max(lo - 4 * j, 0), 4), y = min(max(hi - 4 * j, 0), 4);
+                    w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
+                }
+                const uint32_t acc = lut_counts(s_lut, w);
+                g += acc & 127u;
+                c += (acc >> 7) & 127u;
+                n += acc >> 14;
             }
         }
 #pragma unroll
