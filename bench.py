@@ -59,10 +59,10 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only (profiling runs)")
-    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm", "piles", "cfg1"],
+    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm", "piles", "cfg1", "cfg5"],
                     help="coverage = BASELINE configs[1] (default, the headline); wis = configs[2]")
-    ap.add_argument("--targets", type=int, default=200_000, help="wis: number of targets T")
-    ap.add_argument("--samples", type=int, default=100, help="wis: number of samples S")
+    ap.add_argument("--targets", type=int, default=None, help="wis / cfg5: number of targets T (200 000 / 3 000 000)")
+    ap.add_argument("--samples", type=int, default=None, help="wis / cfg5: number of samples S (100 / 1000)")
     ap.add_argument("--hmm-samples", type=int, default=100, help="hmm: number of samples (22 lanes each)")
     ap.add_argument("--cpu-rows", type=int, default=2000, help="wis: rows of the CPU baseline sample")
     ap.add_argument("--cpu-sample-contigs", type=int, default=4, help="last k contigs form the CPU sample")
@@ -206,7 +206,7 @@ def bench_wis(args):
     import cnvetti_b200 as cb
     from cnvetti_b200 import model_wis as mw
     from cnvetti_b200 import synth
-    T, S = args.targets, args.samples
+    T, S = args.targets or 200_000, args.samples or 100
     dev = "cuda:0"
     ctx = cb.Context(0)
     X, tids = synth.synth_panel(3, T, S)
@@ -255,11 +255,18 @@ def bench_wis(args):
     ht = torch.from_numpy(tids.view(np.int32)).pin_memory()
     k = min(T, opts.max_ref_targets)
 
+    h_idx = torch.empty((T, k), dtype=torch.int32, pin_memory=True)
+    h_len = torch.empty(T, dtype=torch.int32, pin_memory=True)
+    h_calls = torch.empty(T, dtype=torch.int32, pin_memory=True)
+    h_filt = torch.empty(T, dtype=torch.uint8, pin_memory=True)
+
     def step_e2e():
         mm = mw.run(hX.to(dev, non_blocking=True), ht.to(dev, non_blocking=True), opts, ctx=ctx)
-        out = [mm.ref_idx.cpu(), mm.ref_len.cpu(), mm.num_calls.cpu(), mm.filt.cpu()]
+        h_idx.copy_(mm.ref_idx, non_blocking=True)
+        h_len.copy_(mm.ref_len, non_blocking=True)
+        h_calls.copy_(mm.num_calls, non_blocking=True)
+        h_filt.copy_(mm.filt, non_blocking=True)
         torch.cuda.synchronize()
-        return out
 
     step_e2e()
     t0 = time.perf_counter()
@@ -602,8 +609,162 @@ def bench_cfg1(args):
     return 0
 
 
+def bench_cfg5(args):
+    """BASELINE configs[4]: end-to-end WIS germline calling of a synthetic cohort (T targets x S samples):
+    TotalCovSum per sample -> merge-cov -> build-model-wis -> mod-coverage for every sample -> HMM.
+    Strong scaling: the cohort is fixed; samples are sharded for normalise / segmentation, target rows for
+    the model and mod-coverage (one NCCL all-gather of the panel, one all-to-all of the relative coverage)."""
+    import torch
+    import torch.distributed as dist
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import model_wis as mw, parallel, pipeline, synth_torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    ctx = cb.Context(local)
+    T, S = args.targets or 3_000_000, args.samples or 1000
+    ranges = [parallel.shard_rows(S, r, world) for r in range(world)]
+    a, b = ranges[rank]
+    lcv, tids = synth_torch.synth_cohort_lcv(5, T, a, b, dev)
+    opts = mw.BuildModelWisOptions(engine=mw.ENGINE_TENSOR)
+    workload = ("cfg5: WIS germline calling, synthetic cohort %d targets x %d samples: TotalCovSum, merge-cov, "
+                "build-model-wis (k=100, tensor engine), mod-coverage, HMM segmentation" % (T, S))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(timings=None):
+        r = pipeline.wis_call_cohort(lcv, tids, sample_ranges=ranges, wis_options=opts, sigma=0.08, ctx=ctx,
+                                     timings=timings)
+        n_alt = int((r["states"] != 2).sum().item())  # the step's result, read back
+        return r, n_alt
+
+    r, n_alt = step()
+    stats = mw.last_stats(ctx)
+    # spot check at full size: 64 rows of this rank's block against the exact f32 engine
+    lo, hi = r["rows"]
+    m = r["model"]
+    pick = torch.linspace(0, hi - lo - 1, 64).long().tolist() if hi > lo else []
+    exact_opts = mw.BuildModelWisOptions(engine=mw.ENGINE_EXACT)
+    spot_ok = True
+    for q in pick:
+        d1, i1 = mw.compute_distances(r["panel"], tids, exact_opts, row_begin=lo + q, row_end=lo + q + 1, ctx=ctx)
+        spot_ok &= bool(torch.equal(d1[0].view(torch.int32), m["ref_dist"][q].view(torch.int32)))
+    del r, m
+    sampler = ClockSampler(local)
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = ctx.launch_count - l0
+    # stage breakdown (host clock around each stage, one extra step) and the sweep's share
+    stages = {}
+    step(stages)
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    step()
+    torch.cuda.synchronize()
+    kern = {}
+    for kname in ("wis_sweep_kernel", "wis_compact_kernel", "wis_rescore_kernel", "wis_calls_kernel",
+                  "modcov_panel_kernel") + tuple(HMM_KERNELS):
+        kms, cnt = ctx.timing_query(kname)
+        if cnt:
+            kern[kname] = {"ms_per_step": kms, "launches_per_step": cnt}
+    ctx.set_timing(False)
+    ctx.timing_reset()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak_t = 1406.9
+    pfile = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pfile):
+        peak_t = float(json.load(open(pfile)).get("bf16_tflops_sustained", peak_t))
+    sweep = kern.get("wis_sweep_kernel", {}).get("ms_per_step", 0.0)
+    rows = hi - lo
+    kp = ((S + 63) // 64) * 64
+    tiles = float(stats["tiles"]) if stats else 0.0
+    executed = 2.0 * tiles * 256 * 128 * kp / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
+    achieved = 2.0 * rows * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
+    cpu = None
+    e2e = None
+    if not args.quick and world == 1:
+        # end to end from pinned host memory: LCV columns in, state paths out
+        h_in = torch.empty(lcv.shape, dtype=torch.float32, pin_memory=True)
+        h_in.copy_(lcv)
+        h_out = torch.empty((S, T), dtype=torch.uint8, pin_memory=True)
+        del lcv
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d_in = h_in.to(dev, non_blocking=True)
+        rr = pipeline.wis_call_cohort(d_in, tids, sample_ranges=ranges, wis_options=opts, sigma=0.08, ctx=ctx)
+        h_out.copy_(rr["states"], non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": float(T) * T / e2e_s, "unit": "bin-pairs/s", "h2d_bytes_per_step": int(h_in.numel() * 4),
+               "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_s * 1e3, "steps": 1}
+        # CPU baseline: a bounded sample of the stage that dominates the CPU run
+        import oracle
+        oracle.build()
+        ncpu = os.cpu_count() or 1
+        nrows, cols = min(args.cpu_rows, 256), min(T, 200_000)
+        Xs = np.ascontiguousarray(rr["panel"][:cols].cpu().numpy())
+        th = tids[:cols].cpu().numpy().astype(np.uint32)
+        del rr, d_in
+        t0 = time.perf_counter()
+        oracle.wis_distances(Xs, th, 100, 0, nrows, nthreads=ncpu)
+        dt_cpu = time.perf_counter() - t0
+        cpu = {"value": nrows * float(cols) / dt_cpu, "unit": "bin-pairs/s", "cores": ncpu, "kind": "port",
+               "sample": "compute_distances (the stage that dominates the CPU run) for %d target rows x %d columns x %d "
+                         "samples, %d threads as rayon does; linear in rows and columns" % (nrows, cols, S, ncpu)}
+    line = {"metric": "WIS bin-pairs/s", "value": float(T) * T / (ms * 1e-3), "unit": "bin-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (fp16 tensor filter + exact f32 re-score), f64 statistics, i32 HMM scores",
+            "data": "synthetic",
+            "config": {"workload": workload, "targets": T, "samples": S, "k": 100, "bins_segmented": T * S,
+                       "parallelism": "single GPU" if world == 1 else "samples/%d for normalise+HMM, target rows/%d for "
+                                      "WIS+mod-coverage" % (world, world),
+                       "l2": "panel %.1f GB exceeds L2" % (T * S * 4 / 1e9)},
+            "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": achieved, "peak": peak_t,
+                         "unit": "TFLOP/s", "frac": achieved / peak_t, "traffic": None,
+                         "executed_tflops": executed, "executed_frac": executed / peak_t,
+                         "tile_fraction_visited": tiles * 256 * 128 / (float(rows) * T) if rows else None,
+                         "kernel_share_of_step": sweep / ms if ms else None,
+                         "note": "achieved = 2*rows*T*S / sweep time (rank 0's row block); executed_tflops = visited "
+                                 "256x128 tiles x padded K: what the tensor pipe did",
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern,
+            "stages_s": {k_: round(v, 4) for k_, v in stages.items()}, "wis_stats": stats,
+            "checks": {"alt_bins": n_alt, "spot_rows_vs_exact_engine": len(pick), "spot_identical": spot_ok}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if spot_ok else 1
+
+
 def main():
     args = parse_args()
+    if args.workload == "cfg5" and args.impl == "b200":
+        return bench_cfg5(args)
     if args.workload == "cfg1" and args.impl == "b200":
         return bench_cfg1(args)
     if args.workload == "piles" and args.impl == "b200":

@@ -100,6 +100,7 @@ SYMBOLS = {
                               C.POINTER(C.c_float), _int]),
     "cnvb_hmm_segment": (_int, [_vp, _vp, _vp, _u32, _vp, C.POINTER(HmmOpts), _vp, _vp, _int]),
     "cnvb_modcov": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
+    "cnvb_modcov_panel": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
 }
 
 _lib = None

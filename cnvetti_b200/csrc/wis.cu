@@ -364,6 +364,95 @@ __global__ void modcov_kernel(const float *__restrict__ cv, uint32_t T, const ui
     status[t] = st;
 }
 
+
+// M1 for a batch of samples at once: X[T][S] holds FORMAT/CV of S samples side by side (the merge-cov
+// layout); outputs are sample-major [S][T], i.e. one contiguous per-sample column each, as the per-sample
+// call writes them (and as the segmentation reads them).  A CTA takes 32 targets; warp w handles targets
+// w, w+8, .. for the 32 samples of a chunk (neighbouring lanes read neighbouring samples of the same
+// reference row: whole 128-byte lines), results are transposed through shared memory so that the stores
+// run along the target axis.  Arithmetic and its order are those of modcov_kernel.
+constexpr uint32_t kPanelGroup = 32, kPanelThreads = 256;
+
+struct PanelOut {
+    float *ref_mean, *ref_sd, *cv_rel, *cvz, *cv2;
+    uint8_t *status;
+};
+
+__global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float *__restrict__ X, uint32_t S,
+                                                                     uint32_t row_begin, uint32_t rows,
+                                                                     const uint8_t *__restrict__ model_filt,
+                                                                     const uint32_t *__restrict__ ref_idx,
+                                                                     const uint32_t *__restrict__ ref_len, uint32_t k,
+                                                                     PanelOut o) {
+    extern __shared__ uint32_t s_ref[];  // [kPanelGroup][k]
+    __shared__ uint32_t s_len[kPanelGroup];
+    __shared__ float s_out[5][32][kPanelGroup + 1];  // [value][sample in chunk][target]
+    __shared__ uint8_t s_st[32][kPanelGroup + 4];
+    const uint32_t r0 = blockIdx.x * kPanelGroup;  // relative to row_begin, like every per-row argument
+    const uint32_t groups = min(kPanelGroup, rows - r0);
+    for (uint32_t g = threadIdx.x; g < kPanelGroup; g += blockDim.x)
+        s_len[g] = (g < groups && model_filt[r0 + g] == 0) ? ref_len[r0 + g] : 0u;  // lib.rs:104-113, :146
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < groups * k; e += blockDim.x) {
+        const uint32_t g = e / k, q = e - g * k;
+        if (q < s_len[g]) s_ref[e] = ref_idx[(size_t)(r0 + g) * k + q];
+    }
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (uint32_t s0 = 0; s0 < S; s0 += 32) {
+        const uint32_t sm = s0 + lane;
+        for (uint32_t g = warp; g < groups; g += kPanelThreads / 32) {
+            uint8_t st = 0;
+            float o_mean = f32_missing(), o_sd = f32_missing(), o_rel = f32_missing(), o_z = f32_missing(),
+                  o_cv2 = f32_missing();
+            const uint32_t m = s_len[g];
+            if (m > 0 && sm < S) {
+                const uint32_t *ref = s_ref + g * k;
+                dd acc{0.0, 0.0};
+                for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)ref[q] * S + sm));
+                const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)m);  // lib.rs:147
+                double v = 0.0;
+                for (uint32_t q = 0; q < m; ++q) {
+                    const double d = __dsub_rn((double)__ldg(X + (size_t)ref[q] * S + sm), mean);
+                    v = __dadd_rn(v, __dmul_rn(d, d));
+                }
+                const double sd = __dsqrt_rn(m < 2 ? 0.0 : __ddiv_rn(v, (double)(m - 1)));  // lib.rs:148
+                const double x = (double)X[(size_t)(row_begin + r0 + g) * S + sm];
+                const double rel = __ddiv_rn(x, mean);                // lib.rs:78-80
+                const double zs = __ddiv_rn(__dsub_rn(x, mean), sd);  // lib.rs:83-85
+                o_mean = (float)mean;
+                o_sd = (float)sd;
+                o_rel = (float)rel;
+                o_z = (float)zs;
+                st = CNVB_MODCOV_HAS_INFO;
+                if (isfinite(rel)) {  // lib.rs:223-232
+                    o_cv2 = rel == 0.0 ? f32_missing() : (float)log2(rel);
+                    st |= CNVB_MODCOV_CV2;
+                }
+            }
+            s_out[0][lane][g] = o_mean;
+            s_out[1][lane][g] = o_sd;
+            s_out[2][lane][g] = o_rel;
+            s_out[3][lane][g] = o_z;
+            s_out[4][lane][g] = o_cv2;
+            s_st[lane][g] = st;
+        }
+        __syncthreads();
+        float *const outs[5] = {o.ref_mean, o.ref_sd, o.cv_rel, o.cvz, o.cv2};
+        for (uint32_t e = threadIdx.x; e < 32 * kPanelGroup; e += blockDim.x) {
+            const uint32_t sl = e / kPanelGroup, g = e % kPanelGroup;
+            if (s0 + sl < S && g < groups) {
+                const size_t at = (size_t)(s0 + sl) * rows + r0 + g;
+#pragma unroll
+                for (int v = 0; v < 5; ++v)
+                    if (outs[v]) outs[v][at] = s_out[v][sl][g];
+                if (o.status) o.status[at] = s_st[sl][g];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 #include "wis_tensor.cuh"
@@ -639,6 +728,55 @@ extern "C" int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid
     CNVB_TRY(oc.download());
     CNVB_TRY(of.download());
     if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis build");
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, uint32_t row_begin,
+                                 uint32_t row_end, const uint8_t *model_filt, const uint32_t *ref_idx,
+                                 const uint32_t *ref_len, uint32_t k, float *ref_mean, float *ref_sd, float *cv_rel,
+                                 float *cvz, float *cv2, uint8_t *status, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (row_end > T || row_begin > row_end) return fail(ctx, CNVB_ERR_INVALID, "cnvb_modcov_panel: bad row range");
+    const uint32_t rows = row_end - row_begin;
+    if (rows && S && (!X || !model_filt || !ref_idx || !ref_len))
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_modcov_panel: null argument");
+    if (rows == 0 || S == 0) return CNVB_OK;
+    if (k > kMaxK) return fail(ctx, CNVB_ERR_INVALID, "more than %u reference targets per target are not supported", kMaxK);
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const size_t n = (size_t)rows * S;
+    DevIn<float> dx;
+    DevIn<uint8_t> dmf;
+    DevIn<uint32_t> di, dl;
+    DevOut<float> o1, o2, o3, o4, o5;
+    DevOut<uint8_t> os;
+    CNVB_TRY(dx.init(ctx, X, (size_t)T * S, mem, "uploading the CV panel"));
+    CNVB_TRY(dmf.init(ctx, model_filt, rows, mem, "uploading model filters"));
+    CNVB_TRY(di.init(ctx, ref_idx, (size_t)rows * k, mem, "uploading reference targets"));
+    CNVB_TRY(dl.init(ctx, ref_len, rows, mem, "uploading reference target counts"));
+    CNVB_TRY(o1.init(ctx, ref_mean, n, mem, "allocating outputs"));
+    CNVB_TRY(o2.init(ctx, ref_sd, n, mem, "allocating outputs"));
+    CNVB_TRY(o3.init(ctx, cv_rel, n, mem, "allocating outputs"));
+    CNVB_TRY(o4.init(ctx, cvz, n, mem, "allocating outputs"));
+    CNVB_TRY(o5.init(ctx, cv2, n, mem, "allocating outputs"));
+    CNVB_TRY(os.init(ctx, status, n, mem, "allocating outputs"));
+    {
+        KernelSpan span(ctx, "modcov_panel_kernel");
+        const PanelOut po{o1.p, o2.p, o3.p, o4.p, o5.p, os.p};
+        const size_t smem = (size_t)kPanelGroup * k * sizeof(uint32_t);
+        if (smem > 24 * 1024)
+            CNVB_CUDA(ctx, cudaFuncSetAttribute(modcov_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "smem opt-in");
+        modcov_panel_kernel<<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, smem, ctx->stream>>>(
+            dx.p, S, row_begin, rows, dmf.p, di.p, dl.p, k, po);
+    }
+    CNVB_LAUNCHED(ctx, "modcov_panel_kernel");
+    CNVB_TRY(o1.download());
+    CNVB_TRY(o2.download());
+    CNVB_TRY(o3.download());
+    CNVB_TRY(o4.download());
+    CNVB_TRY(o5.download());
+    CNVB_TRY(os.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "modcov panel");
     return CNVB_OK;
 }
 

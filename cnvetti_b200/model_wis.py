@@ -164,3 +164,29 @@ def mod_coverage(cv, model_filt, ref_idx, ref_len, ctx=None):
     ctx.check(N.lib().cnvb_modcov(ctx.handle, pc, T, pf, pi, pl, k, *[buf(o)[0] for o in outs],
                                   buf(status)[0], mem))
     return dict(ref_mean=outs[0], ref_sd=outs[1], cv_rel=outs[2], cvz=outs[3], cv2=outs[4], status=status)
+
+
+def mod_coverage_panel(X, model_filt, ref_idx, ref_len, want=("cv_rel", "cvz"), row_begin=0, row_end=None,
+                       ctx=None):
+    """lib-mod-cov for S samples at once: X[T][S] = FORMAT/CV of the samples side by side, target
+    rows [row_begin, row_end) (model_filt / ref_idx / ref_len relative to row_begin).  Returns
+    sample-major [S][rows] arrays for the names in `want` (ref_mean, ref_sd, cv_rel, cvz, cv2,
+    status); row s equals mod_coverage(X[:, s], ...)[row_begin:row_end]."""
+    ctx = ctx or default_context()
+    px, mx, kx = buf(X, np.float32)
+    pf, mf, kf = buf(model_filt, np.uint8)
+    pi, mi, ki = buf(ref_idx, None if hasattr(ref_idx, "is_cuda") else np.uint32)
+    pl, ml, kl = buf(ref_len, None if hasattr(ref_len, "is_cuda") else np.uint32)
+    mem = same_mem(mx, mf, mi, ml)
+    T, S, k = int(kx.shape[0]), int(kx.shape[1]), int(ki.shape[1])
+    row_end = T if row_end is None else row_end
+    rows = row_end - row_begin
+    names = ("ref_mean", "ref_sd", "cv_rel", "cvz", "cv2", "status")
+    unknown = set(want) - set(names)
+    if unknown:
+        raise ValueError("unknown outputs: %s" % sorted(unknown))
+    outs = {n: (ctx.empty(S * rows, np.uint8 if n == "status" else np.float32, mem) if n in want else None)
+            for n in names}
+    ctx.check(N.lib().cnvb_modcov_panel(ctx.handle, px, T, S, row_begin, row_end, pf, pi, pl, k,
+                                        *[buf(outs[n])[0] for n in names], mem))
+    return {n: v.reshape(S, rows) for n, v in outs.items() if v is not None}

@@ -7,18 +7,19 @@ from . import _native as N
 from .context import buf, default_context
 
 
-def run_uncorrected_normalization(lcv, lcvsd=None, ctx=None):
+def run_uncorrected_normalization(lcv, lcvsd=None, ctx=None, want_sum=True, out=None):
     """Normalization::TotalCovSum (lib-normalize/src/uncorrected.rs:51-96).
-    Returns (cv, cvsd or None, lcv_sum)."""
+    Returns (cv, cvsd or None, lcv_sum).  want_sum=False leaves the sum on the device (no host wait
+    for device-resident columns; lcv_sum is None); `out` = preallocated cv."""
     ctx = ctx or default_context()
     p, mem, keep = buf(lcv, np.float32)
     n = int(keep.shape[0])
-    cv = ctx.empty(n, np.float32, mem)
+    cv = ctx.empty(n, np.float32, mem) if out is None else out
     cvsd = ctx.empty(n, np.float32, mem) if lcvsd is not None else None
     s = C.c_double(0.0)
     ctx.check(N.lib().cnvb_norm_total(ctx.handle, p, buf(lcvsd, np.float32)[0], n, buf(cv)[0],
-                                      buf(cvsd)[0], C.addressof(s), mem))
-    return cv, cvsd, s.value
+                                      buf(cvsd)[0], C.addressof(s) if want_sum else None, mem))
+    return cv, cvsd, (s.value if want_sum else None)
 
 
 def run_binned_correction(lcv, gc, lcvsd=None, ctx=None):

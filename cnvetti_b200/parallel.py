@@ -90,6 +90,19 @@ class CudaWisBackend:
     def filters(self, ref_len, calls, options):
         return self.mw.model_filters(ref_len, calls, options, ctx=self.ctx)
 
+    # the stages either side of build-model-wis in the cohort pipeline (pipeline.wis_call_cohort)
+    def normalize_total(self, lcv_row, out_row):
+        from .normalize import run_uncorrected_normalization
+        run_uncorrected_normalization(lcv_row, ctx=self.ctx, want_sum=False, out=out_row)
+
+    def modcov_panel(self, X, filt, ref_idx, ref_len, lo, hi):
+        return self.mw.mod_coverage_panel(X, filt, ref_idx, ref_len, want=("cv_rel", "cvz"), row_begin=lo,
+                                          row_end=hi, ctx=self.ctx)
+
+    def segment(self, cv_flat, lane_off, sigma, options):
+        from . import discover
+        return discover.hmm_segment(cv_flat, lane_off, sigma, options, ctx=self.ctx)
+
 
 def wis_run_distributed(X_block, tids_block, options, backend=None, group=None):
     """`build-model-wis` with targets sharded by row block.
@@ -110,11 +123,21 @@ def wis_run_distributed(X_block, tids_block, options, backend=None, group=None):
     else:
         lo = 0
     hi = lo + int(X_block.shape[0])
+    return wis_rows_distributed(X, tids, options, lo, hi, backend=backend, group=group)
+
+
+def wis_rows_distributed(X, tids, options, lo, hi, backend=None, group=None):
+    """The part of `build-model-wis` after the panel exchange: every rank holds the whole panel
+    X[T][S] and computes the model of its target rows [lo, hi) (row blocks in rank order).  The
+    one exchange is the all-gather of the nearest distance of every target, from which all ranks
+    derive the same prune threshold."""
+    rank, world = _world(group)
+    backend = backend or CudaWisBackend()
     dist_, idx = backend.distances(X, tids, options, lo, hi)
     nearest_local = dist_[:, 0].contiguous() if hasattr(dist_, "contiguous") else np.ascontiguousarray(dist_[:, 0])
     if world > 1:
         nearest_t = nearest_local if torch.is_tensor(nearest_local) else torch.from_numpy(nearest_local)
-        nearest_t = nearest_t.to(X_block.device)
+        nearest_t = nearest_t.to(X.device)
         nearest = all_gather_rows(nearest_t, group)  # one f32 per target
     else:
         nearest = nearest_local
@@ -124,6 +147,37 @@ def wis_run_distributed(X_block, tids_block, options, backend=None, group=None):
     filt = backend.filters(ref_len, calls, options)
     return dict(ref_dist=dist_, ref_idx=ref_idx, ref_len=ref_len, num_calls=calls, filt=filt,
                 threshold=thr, rows=(lo, hi))
+
+
+def exchange_rows_to_samples(block, sample_ranges, group=None):
+    """All-to-all between the two shardings of a [S][T] table: every rank holds ALL samples for
+    ITS target rows (`block[S][rows_r]`, row blocks in rank order) and receives ITS samples
+    (`sample_ranges[r] = (s_lo, s_hi)`) for ALL targets -> [S_r][T]."""
+    rank, world = _world(group)
+    if world == 1:
+        return block
+    send = [block[a:b].contiguous() for a, b in sample_ranges]
+    n_rows = torch.tensor([block.shape[1]], dtype=torch.int64, device=block.device)
+    rows = [torch.zeros_like(n_rows) for _ in range(world)]
+    dist.all_gather(rows, n_rows, group=group)
+    s_lo, s_hi = sample_ranges[rank]
+    recv = [torch.empty((s_hi - s_lo, int(r.item())), dtype=block.dtype, device=block.device) for r in rows]
+    if dist.get_backend(group) == "gloo":  # (CPU tests: gloo has no all_to_all)
+        for src in range(world):
+            if src == rank:
+                recv[src].copy_(send[src])
+        work = []
+        for q in range(world):
+            if q != rank:
+                work.append(dist.isend(send[q], q, group=group))
+        for q in range(world):
+            if q != rank:
+                dist.recv(recv[q], q, group=group)
+        for w in work:
+            w.wait()
+    else:
+        dist.all_to_all(recv, send, group=group)
+    return torch.cat(recv, dim=1)
 
 
 def gather_columns(local_columns, owner_of_region, region_sizes, dtype, device, group=None):

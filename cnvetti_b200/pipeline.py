@@ -191,3 +191,77 @@ def quick_wis_build_model(samples, wis_options=None, ctx=None):
     X, tids = merge_cov(tables)
     model = model_wis.run(X, tids, wis_options or model_wis.BuildModelWisOptions(), ctx=ctx)
     return model, X, tids
+
+
+def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_options=None, sigma=0.08,
+                    segment=True, ctx=None, group=None, backend=None, timings=None):
+    """BASELINE config 5, in memory: germline calling of a whole cohort against its own panel --
+    per sample `cmd normalize --normalization TotalCovSum`, `merge-cov`, `build-model-wis`,
+    per sample `mod-coverage` (the chain of cnvetti/src/quick_wis_build_model.rs:133-214 and
+    quick_wis_call.rs:124-190 without the files), then `discover` on the relative coverage.
+
+    `lcv[S_r][T]`: FORMAT/LCV of THIS rank's samples (device tensor, one row per sample);
+    `sample_ranges[r] = (s_lo, s_hi)` for every rank (None: single process); `tids[T]` contig id of
+    every target (targets in genome order).  Sharding: normalisation by
+    sample, then ONE all-gather of the normalised panel; distances / prune / calls / mod-coverage by
+    target-row block (one all-gather of T nearest distances for the threshold); an all-to-all brings
+    the relative coverage back to sample-major shards for the (sample, contig) HMM lanes.
+    `backend` (default: the CUDA library on this rank's GPU) is injectable so that the host logic can
+    be exercised with gloo on a CPU-only box.
+
+    Returns dict(model=..., rows=(lo, hi), cv_rel[S_r][T], cvz_rows[S][rows], states[S_r][T] uint8)."""
+    import time
+    import torch
+    from . import model_wis, parallel
+    backend = backend or parallel.CudaWisBackend(ctx or default_context())
+    wis_options = wis_options or model_wis.BuildModelWisOptions()
+    rank, world = parallel._world(group)
+    S_r, T = int(lcv.shape[0]), int(lcv.shape[1])
+    if sample_ranges is None:
+        sample_ranges = [(0, S_r)]
+    S = sample_ranges[-1][1]
+    dev = lcv.device
+
+    def mark(name, t0):
+        if timings is not None:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            timings[name] = timings.get(name, 0.0) + (time.perf_counter() - t0)
+        return time.perf_counter()
+
+    t0 = time.perf_counter()
+    # cmd normalize, one sample at a time (its sum runs over all targets of the sample)
+    cv = torch.empty_like(lcv)
+    for s in range(S_r):
+        backend.normalize_total(lcv[s], cv[s])
+    t0 = mark("normalize", t0)
+    # merge-cov: the one big exchange, then the panel in ModelInput layout X[T][S]
+    X = parallel.all_gather_rows(cv, group).t().contiguous()  # (single process: just the transpose)
+    del cv
+    t0 = mark("merge_cov", t0)
+    lo, hi = parallel.shard_rows(T, rank, world)
+    m = parallel.wis_rows_distributed(X, tids, wis_options, lo, hi, backend=backend, group=group)
+    t0 = mark("build_model_wis", t0)
+    mc = backend.modcov_panel(X, m["filt"], m["ref_idx"], m["ref_len"], lo, hi)
+    t0 = mark("mod_coverage", t0)
+    rel = parallel.exchange_rows_to_samples(mc["cv_rel"], sample_ranges, group=group)  # [S_r][T]
+    t0 = mark("exchange", t0)
+    out = dict(model=m, rows=(lo, hi), cv_rel=rel, cvz_rows=mc["cvz"], panel=X, n_samples=S)
+    if segment:
+        # (sample, contig) lanes: contig boundaries from the tids of the targets
+        t_host = tids.cpu().numpy() if hasattr(tids, "cpu") else np.asarray(tids)
+        cuts = np.concatenate([[0], np.flatnonzero(np.diff(t_host)) + 1, [T]]).astype(np.int64)
+        lane_off = np.concatenate([s * T + cuts[:-1] for s in range(S_r)] + [[S_r * T]]).astype(np.uint64)
+        per = cuts.size - 1  # lanes per sample
+        sig = np.full(S_r * per, float(sigma)) if np.isscalar(sigma) else np.asarray(sigma, np.float64)
+        states = torch.empty((S_r, T), dtype=torch.uint8, device=dev)
+        step = max(1, (1 << 29) // max(T, 1))  # samples per call: at most 2^29 bins each
+        for a in range(0, S_r, step):
+            b = min(S_r, a + step)
+            off = (lane_off[a * per:b * per + 1] - lane_off[a * per]).astype(np.uint64)
+            st = backend.segment(rel[a:b].reshape(-1), off, sig[a * per:b * per], discover_options)
+            states[a:b] = st.reshape(b - a, T)
+        out["states"] = states
+        out["lane_off"] = lane_off
+        mark("discover", t0)
+    return out

@@ -111,3 +111,32 @@ def soa_to_oracle_records(soa, lo=0, hi=None):
     cigar[first[clipfail] + 1] = (READ_LEN << 4) | 0
     return dict(pos=pos, isize=isize, flag=(fl & 0x0FFF).astype(np.uint16), mapq=mapq,
                 cigar_off=cigar_off, cigar=cigar)
+
+
+def synth_cohort_lcv(seed, T, s_lo, s_hi, device, n_contigs=22, cnv_per_sample=20):
+    """Raw length-normalised coverage LCV[s_hi - s_lo][T] (f32, sample-major) of a cohort as SURVEY
+    8(d) configs 3/5: target efficiency eff_t ~ LogNormal(0, 0.4) shared by all samples, per-sample
+    depth factor, noise ~ N(1, 0.08), a few planted CNV segments per sample (x 0.5 / x 1.5).  Sample s
+    is generated from (seed, s) alone, so any sharding of the samples yields the same cohort.
+    Returns (lcv, tids int32[T])."""
+    from .synth import HG38_AUTOSOMES
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    eff = torch.empty(T, device=device).log_normal_(0.0, 0.4, generator=g)
+    w = np.array(HG38_AUTOSOMES[:n_contigs], np.float64)
+    bounds = np.floor(np.cumsum(w) / w.sum() * T).astype(np.int64)
+    tids = np.minimum(np.searchsorted(bounds, np.arange(T), side="right"), n_contigs - 1).astype(np.int32)
+    out = torch.empty((s_hi - s_lo, T), dtype=torch.float32, device=device)
+    for s in range(s_lo, s_hi):
+        g.manual_seed(int(seed) * 1_000_003 + s + 1)
+        depth = 20.0 + 20.0 * float(torch.rand(1, generator=g, device=device).item())
+        row = out[s - s_lo]
+        row.normal_(1.0, 0.08, generator=g)
+        row.mul_(eff).mul_(depth).clamp_(min=0.0)
+        if cnv_per_sample and T > 600:
+            st = (torch.rand(cnv_per_sample, generator=g, device=device) * (T - 600)).long().tolist()
+            ln = ((torch.rand(cnv_per_sample, generator=g, device=device) * 495).long() + 5).tolist()
+            up = (torch.rand(cnv_per_sample, generator=g, device=device) < 0.5).tolist()
+            for a, n, u in zip(st, ln, up):
+                row[a:a + n].mul_(1.5 if u else 0.5)
+    return out, torch.from_numpy(tids).to(device)

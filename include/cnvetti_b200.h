@@ -292,6 +292,16 @@ int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t 
 int cnvb_modcov(cnvb_ctx *ctx, const float *cv, uint32_t T, const uint8_t *model_filt,
                 const uint32_t *ref_idx, const uint32_t *ref_len, uint32_t k, float *ref_mean,
                 float *ref_sd, float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem);
+/* The same for S samples in one call (the per-sample loop of `quick wis-call` over a cohort,
+ * cnvetti/src/quick_wis_call.rs:171-181): X[T][S] row-major holds FORMAT/CV of the samples side
+ * by side (the merge-cov layout, lib-merge-cov/src/lib.rs:102-232).  Target rows [row_begin,
+ * row_end) are computed (a GPU's share when targets are sharded); model_filt / ref_idx / ref_len
+ * and the outputs are indexed relative to row_begin.  Outputs are sample-major [S][rows] --
+ * row s is exactly what cnvb_modcov writes for cv = X[:, s] -- and each may be NULL. */
+int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, uint32_t row_begin,
+                      uint32_t row_end, const uint8_t *model_filt, const uint32_t *ref_idx,
+                      const uint32_t *ref_len, uint32_t k, float *ref_mean, float *ref_sd,
+                      float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem);
 
 /* ---- lib-discover (builder-defined: the reference has no implementation, only the CLI stub
  * cnvetti/src/cli.yaml:457-469 and `bail!("cmd discover not implemented!")`,

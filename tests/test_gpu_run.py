@@ -157,3 +157,42 @@ def test_quick_wis_build_model_chain(oracle, ctx):
     assert_f32_equal_bits(to_np(model.ref_dist), odist, "distances")
     calls = oracle.wis_calls(oX, pidx, plen, 3, opts.filter_z_score, opts.filter_rel)
     assert np.array_equal(to_np(model.num_calls), calls)
+
+
+def test_wis_call_cohort_chain(oracle, ctx):
+    """BASELINE config 5 in miniature (pipeline.wis_call_cohort): TotalCovSum per sample -> merge-cov ->
+    build-model-wis (tensor engine) -> mod-coverage for the whole cohort -> HMM segmentation, every stage
+    against the oracle chain; integer outputs and single-rounding f32 outputs bit-exact."""
+    import torch
+    from cnvetti_b200 import model_wis as mw, synth_torch
+    T, S = 4500, 24
+    lcv, tids = synth_torch.synth_cohort_lcv(5, T, 0, S, "cuda", n_contigs=5, cnv_per_sample=3)
+    opts = mw.BuildModelWisOptions(max_ref_targets=30, min_ref_targets=5)
+    timings = {}
+    r = pipeline.wis_call_cohort(lcv, tids, wis_options=opts, sigma=0.08, ctx=ctx, timings=timings)
+    assert set(timings) >= {"normalize", "merge_cov", "build_model_wis", "mod_coverage", "discover"}
+    h = lcv.cpu().numpy()
+    oX = np.stack([oracle.norm_total(np.ascontiguousarray(h[s]))[1] for s in range(S)], axis=1)
+    assert_f32_equal_bits(to_np(r["panel"]), oX, "panel")
+    otids = tids.cpu().numpy().astype(np.uint32)
+    odist, oidx = oracle.wis_distances(oX, otids, max_ref_targets=30, nthreads=8)
+    thr, pidx, plen = oracle.wis_prune(odist, oidx, opts.filter_z_score)
+    m = r["model"]
+    assert np.float32(m["threshold"]) == np.float32(thr)
+    assert np.array_equal(to_np(m["ref_len"]), plen)
+    assert_f32_equal_bits(to_np(m["ref_dist"]), odist, "distances")
+    calls = oracle.wis_calls(oX, pidx, plen, 5, opts.filter_z_score, opts.filter_rel)
+    filt = oracle.wis_filters(plen, calls, 5, opts.max_samples_reliable)
+    assert np.array_equal(to_np(m["num_calls"]), calls) and np.array_equal(to_np(m["filt"]), filt)
+    cuts = np.concatenate([[0], np.flatnonzero(np.diff(otids)) + 1, [T]])
+    tab = oracle.hmm_tables(0.08)
+    n_alt = 0
+    for s in range(S):
+        o = oracle.modcov(np.ascontiguousarray(oX[:, s]), filt, pidx, plen)
+        assert_f32_equal_bits(to_np(r["cv_rel"])[s], o["cv_rel"], "cv_rel[%d]" % s)
+        assert_f32_equal_bits(to_np(r["cvz_rows"])[s], o["cvz"], "cvz[%d]" % s)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            st = oracle.hmm_viterbi(np.ascontiguousarray(o["cv_rel"][a:b]), tab)
+            assert np.array_equal(to_np(r["states"])[s, a:b], st), (s, a, b)
+            n_alt += int((st != 2).sum())
+    assert n_alt > 0

@@ -116,6 +116,45 @@ def test_modcov_parity(oracle, ctx, device):
     assert (o["status"] == 0).any() and (o["status"] == 3).any()
 
 
+@pytest.mark.parametrize("T,S,device", [(3000, 12, True), (1037, 70, False), (40, 33, True)])
+def test_modcov_panel_matches_per_sample_oracle(oracle, ctx, T, S, device):
+    """cnvb_modcov_panel: every column of the sample-major outputs equals the oracle's per-sample
+    mod-coverage of that sample (bit-exact; CV2 = log2 within the north_star tolerance)."""
+    X, tids = synth.synth_panel(31 + T, T, S, n_contigs=6)
+    k = min(T, 50)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=4)
+    _, ridx, rlen = oracle.wis_prune(odist, oidx, z=2.0)
+    rng = np.random.default_rng(2)
+    filt = (rng.random(T) < 0.1).astype(np.uint8)
+    rlen[rng.integers(0, T, 5)] = 0
+    Y = (X * rng.normal(1, 0.1, X.shape)).astype(np.float32)  # the samples being called
+    Y[17 % T, 3] = 0.0
+    names = ("ref_mean", "ref_sd", "cv_rel", "cvz", "cv2", "status")
+    if device:
+        g = mw.mod_coverage_panel(_dev(Y), _dev(filt), _dev(ridx), _dev(rlen), want=names, ctx=ctx)
+    else:
+        g = mw.mod_coverage_panel(Y, filt, ridx, rlen, want=names, ctx=ctx)
+    for s in range(S):
+        o = oracle.modcov(np.ascontiguousarray(Y[:, s]), filt, ridx, rlen)
+        assert np.array_equal(to_np(g["status"])[s], o["status"])
+        for key in ("ref_mean", "ref_sd", "cv_rel", "cvz"):
+            assert_f32_equal_bits(to_np(g[key])[s], o[key], "%s[%d]" % (key, s))
+        a, b = to_np(g["cv2"])[s], o["cv2"]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        np.testing.assert_allclose(a[fin], b[fin], rtol=1e-6, atol=1e-7)
+    # nullable outputs
+    h = mw.mod_coverage_panel(_dev(Y), _dev(filt), _dev(ridx), _dev(rlen), want=("cvz",), ctx=ctx)
+    assert list(h) == ["cvz"]
+    assert_f32_equal_bits(to_np(h["cvz"]), to_np(g["cvz"]), "cvz only")
+    # a row block (a GPU's share of the targets)
+    lo, hi = T // 3, T - 5
+    h = mw.mod_coverage_panel(Y, filt[lo:hi], ridx[lo:hi], rlen[lo:hi], want=("cvz", "status"), row_begin=lo,
+                              row_end=hi, ctx=ctx)
+    assert_f32_equal_bits(to_np(h["cvz"]), to_np(g["cvz"])[:, lo:hi], "cvz rows")
+    assert np.array_equal(to_np(h["status"]), to_np(g["status"])[:, lo:hi])
+
+
 @pytest.mark.parametrize("T,S,k,ncontig,device", [(5000, 100, 100, 22, True), (4321, 37, 64, 5, False),
                                                  (9000, 128, 100, 22, True),
                                                  # more than 128 samples: both operands stream through the K-block ring

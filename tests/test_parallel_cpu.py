@@ -54,6 +54,90 @@ class OracleWisBackend:
         return self.o.wis_filters(ref_len, calls, options.min_ref_targets, options.max_samples_reliable)
 
 
+class OracleCohortBackend(OracleWisBackend):
+    """The remaining stages of pipeline.wis_call_cohort on the oracle."""
+
+    def normalize_total(self, lcv_row, out_row):
+        out_row.copy_(torch.from_numpy(self.o.norm_total(lcv_row.numpy())[1]))
+
+    def modcov_panel(self, X, filt, ref_idx, ref_len, lo, hi):
+        Xn = X.numpy()
+        T, S = Xn.shape
+        k = np.asarray(ref_idx).shape[1]
+        fi = np.zeros((T, k), np.uint32)
+        fl = np.zeros(T, np.uint32)
+        ff = np.zeros(T, np.uint8)
+        fi[lo:hi], fl[lo:hi], ff[lo:hi] = np.asarray(ref_idx), np.asarray(ref_len), np.asarray(filt)
+        rel = np.empty((S, hi - lo), np.float32)
+        z = np.empty((S, hi - lo), np.float32)
+        for s_ in range(S):
+            o = self.o.modcov(np.ascontiguousarray(Xn[:, s_]), ff, fi, fl)
+            rel[s_], z[s_] = o["cv_rel"][lo:hi], o["cvz"][lo:hi]
+        return dict(cv_rel=torch.from_numpy(rel), cvz=torch.from_numpy(z))
+
+    def segment(self, cv_flat, lane_off, sigma, options):
+        cv = cv_flat.numpy()
+        out = np.empty(cv.size, np.uint8)
+        for i in range(len(lane_off) - 1):
+            a, b = int(lane_off[i]), int(lane_off[i + 1])
+            out[a:b] = self.o.hmm_viterbi(np.ascontiguousarray(cv[a:b]), self.o.hmm_tables(float(sigma[i])))
+        return torch.from_numpy(out)
+
+
+def _cohort_inputs():
+    rng = np.random.default_rng(11)
+    T, S = 180, 6
+    eff = rng.lognormal(0, 0.4, T)
+    lcv = (eff[None, :] * rng.normal(1, 0.08, (S, T)) * rng.uniform(20, 40, (S, 1))).astype(np.float32)
+    lcv[2, 40:70] *= 0.5
+    lcv[4, 100:130] *= 1.5
+    tids = np.repeat(np.arange(3), [70, 60, 50]).astype(np.int64)
+    return lcv, tids
+
+
+def _cohort_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cnvetti_b200 import pipeline
+        lcv, tids = _cohort_inputs()
+        S = lcv.shape[0]
+        ranges = [parallel.shard_rows(S, r, world) for r in range(world)]
+        a, b = ranges[rank]
+        opts = BuildModelWisOptions(filter_z_score=2.0, filter_rel=0.1, max_ref_targets=15, min_ref_targets=3,
+                                    max_samples_reliable=2)
+        r = pipeline.wis_call_cohort(torch.from_numpy(lcv[a:b].copy()), torch.from_numpy(tids), sample_ranges=ranges,
+                                     wis_options=opts, sigma=0.1, backend=OracleCohortBackend())
+        out[rank] = dict(samples=(a, b), rows=r["rows"], cv_rel=r["cv_rel"].numpy().copy(),
+                         cvz=r["cvz_rows"].numpy().copy(), states=r["states"].numpy().copy(),
+                         ref_len=np.asarray(r["model"]["ref_len"]).copy(), thr=float(r["model"]["threshold"]))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_cohort_pipeline_sharded_matches_single_process(oracle):
+    """pipeline.wis_call_cohort: samples sharded for normalise / segmentation, target rows sharded for the
+    model and mod-coverage, one all-gather of the panel and one all-to-all of the relative coverage --
+    world size 2 over gloo must reproduce the single-process result bit for bit."""
+    mgr = mp.Manager()
+    one, two = mgr.dict(), mgr.dict()
+    mp.spawn(_cohort_worker, args=(1, _free_port(), one), nprocs=1, join=True)
+    mp.spawn(_cohort_worker, args=(2, _free_port(), two), nprocs=2, join=True)
+    ref = one[0]
+    assert ref["states"].shape == (6, 180) and (ref["states"] != 2).any()
+    for rank in range(2):
+        r = two[rank]
+        (a, b), (lo, hi) = r["samples"], r["rows"]
+        assert np.float32(r["thr"]) == np.float32(ref["thr"])
+        assert np.array_equal(r["ref_len"], ref["ref_len"][lo:hi])
+        assert np.array_equal(r["cv_rel"].view(np.uint32), ref["cv_rel"][a:b].view(np.uint32))
+        assert np.array_equal(r["cvz"].view(np.uint32), ref["cvz"][:, lo:hi].view(np.uint32))
+        assert np.array_equal(r["states"], ref["states"][a:b])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
