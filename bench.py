@@ -629,7 +629,16 @@ def bench_cfg5(args):
     T, S = args.targets or 3_000_000, args.samples or 1000
     ranges = [parallel.shard_rows(S, r, world) for r in range(world)]
     a, b = ranges[rank]
+    t_gen = time.perf_counter()
     lcv, tids = synth_torch.synth_cohort_lcv(5, T, a, b, dev)
+    torch.cuda.synchronize()
+
+    def log(msg):
+        if rank == 0:
+            sys.stderr.write("[cfg5 %7.1f s] %s\n" % (time.perf_counter() - t_gen, msg))
+            sys.stderr.flush()
+
+    log("cohort generated: %d targets x %d samples" % (T, b - a))
     opts = mw.BuildModelWisOptions(engine=mw.ENGINE_TENSOR)
     workload = ("cfg5: WIS germline calling, synthetic cohort %d targets x %d samples: TotalCovSum, merge-cov, "
                 "build-model-wis (k=100, tensor engine), mod-coverage, HMM segmentation" % (T, S))
@@ -645,8 +654,10 @@ def bench_cfg5(args):
         n_alt = int((r["states"] != 2).sum().item())  # the step's result, read back
         return r, n_alt
 
-    r, n_alt = step()
+    first = {}
+    r, n_alt = step(first)
     stats = mw.last_stats(ctx)
+    log("first step: stages %s; engine %s; alt bins %d" % ({k_: round(v, 3) for k_, v in first.items()}, stats, n_alt))
     # spot check at full size: 64 rows of this rank's block against the exact f32 engine
     lo, hi = r["rows"]
     m = r["model"]
@@ -657,6 +668,7 @@ def bench_cfg5(args):
         d1, i1 = mw.compute_distances(r["panel"], tids, exact_opts, row_begin=lo + q, row_end=lo + q + 1, ctx=ctx)
         spot_ok &= bool(torch.equal(d1[0].view(torch.int32), m["ref_dist"][q].view(torch.int32)))
     del r, m
+    log("spot check of %d rows against the exact engine: %s" % (len(pick), spot_ok))
     sampler = ClockSampler(local)
     for _ in range(max(0, args.warmup - 1)):
         step()

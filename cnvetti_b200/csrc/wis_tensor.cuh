@@ -199,25 +199,43 @@ __global__ void wis_proj_kernel(const float *__restrict__ X, uint32_t T, uint32_
 }
 
 // one warp per SORTED position: centre, scale, round the row perm[pos] to fp16; n_t (of the fp16
-// row) and delta_t in f64; contig id and projection in sorted order
+// row) and delta_t in f64; contig id and projection in sorted order.
+//
+// ortho (panels with more than 128 samples): the component along the all-ones direction is taken out
+// of the fp16 row and carried as the f32 projection q_t instead, u_t = q_t 1 + h_t + r_t with
+// 1 = ones / sqrt(S).  The sweep then evaluates  d^2 = (q_i - q_j)^2 + |h_i - h_j|^2, the first term in
+// f32 in the epilogue.  Why: the accumulation error of the tensor dot product is bounded by
+// c_acc s_i s_j with c_acc proportional to K; targets far from the panel mean relative to their noise
+// (low capture efficiency) have norms s dominated by exactly this component, and at K = 1024 the
+// bound let so many columns pass that their candidate buffers overflowed (6 % of the rows of a
+// 10^6 x 1000 panel fell back to the exact kernel).  Without it s is the norm of the noise alone.
+// The rounded h_t is not exactly orthogonal to 1: |u_i - u_j|^2 has the cross term
+// 2 (q_i - q_j)(e_i - e_j), e_t = 1 . h_t, which moves the distance by at most 2 (|e_i| + |e_j|);
+// delta_t = |r_t| + 2 |e_t| covers it (all measured in f64 from the raw values).
 __global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S,
                                 uint32_t Kp, const float *__restrict__ cmean, float scale,
                                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ pkey_sorted,
                                 __half *__restrict__ H, float *__restrict__ nrm, float *__restrict__ delta,
                                 uint32_t *__restrict__ tid_sorted, float *__restrict__ psorted,
-                                float *__restrict__ maxes) {
+                                float *__restrict__ maxes, int ortho) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (warp >= T) return;
     const uint32_t src = perm[warp];
-    double n = 0.0, e = 0.0;
+    const float q = key_f32(pkey_sorted[warp]);
+    const double inv_sqrt_s = 1.0 / sqrt((double)S);
+    const double qc = ortho ? (double)q * inv_sqrt_s : 0.0;  // the component removed from every sample
+    const float qcf = (float)qc;
+    double n = 0.0, e = 0.0, eps = 0.0;
     for (uint32_t s = lane; s < Kp; s += 32) {
         __half h = __float2half_rn(0.0f);
         if (s < S) {
-            const float u = __fmul_rn(__fsub_rn(X[(size_t)src * S + s], cmean[s]), scale);
+            const float u = __fsub_rn(__fmul_rn(__fsub_rn(X[(size_t)src * S + s], cmean[s]), scale), qcf);
             h = __float2half_rn(u);
             const double hf = (double)__half2float(h);
             n += hf * hf;
-            const double r = (double)u - hf;
+            eps += hf;
+            // against the exact value (scale is a power of two; f64 rounding is far below the f32 / fp16 ones)
+            const double r = ((double)X[(size_t)src * S + s] - (double)cmean[s]) * (double)scale - qc - hf;
             e += r * r;
         }
         H[(size_t)warp * Kp + s] = h;
@@ -226,15 +244,18 @@ __global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__r
     for (int o = 16; o > 0; o >>= 1) {
         n += __shfl_xor_sync(0xffffffffu, n, o);
         e += __shfl_xor_sync(0xffffffffu, e, o);
+        eps += __shfl_xor_sync(0xffffffffu, eps, o);
     }
     if (lane == 0) {
         const float nf = __double2float_ru(n);
         // rounding error norm, inflated for the f32 rounding of the centred value itself
-        const float df = __double2float_ru(sqrt(e) * (1.0 + 1.0 / 1024.0) + sqrt(n) * (1.0 / 8388608.0));
+        double d = sqrt(e) * (1.0 + 1.0 / 1024.0) + sqrt(n) * (1.0 / 8388608.0);
+        if (ortho) d += 2.0 * fabs(eps) * inv_sqrt_s * (1.0 + 1.0 / 1024.0);
+        const float df = __double2float_ru(d);
         nrm[warp] = nf;
         delta[warp] = df;
         tid_sorted[warp] = tid[src];
-        psorted[warp] = key_f32(pkey_sorted[warp]);
+        psorted[warp] = q;
         const float rho = __double2float_ru((double)df / fmax(sqrt(n), 1.0));  // delta_j <= rho * max(s_j, 1)
         atomicMax(reinterpret_cast<int *>(maxes), __float_as_int(rho));
     }
@@ -298,6 +319,8 @@ __global__ void wis_fill_kernel(float *__restrict__ p, uint32_t lo, uint32_t hi,
 
 // ---- the error bounds in f32 with directed rounding (upper bounds round up, lower bounds down) --------
 struct BoundConsts {
+    float up_infl;       // ortho mode: stored values are rounded-down sums v + (q_i - q_j)^2; the exact sum is at
+                         // most v (1 + up_infl) + up_infl (n_i + n_j)   (1 otherwise: no inflation)
     float c_acc2;        // 2 c_acc, rounded up
     float c_rnd;         // rounded up
     float one_plus_g;    // 1 + g, rounded up
@@ -308,8 +331,12 @@ struct BoundConsts {
 
 // >= D_ref for the pair behind a stored value v = n'_j - 2 g  (U_ij of the header comment)
 __device__ __forceinline__ float pair_upper(float v, const ColMeta &mi, const ColMeta &mj, float rho2c, const BoundConsts &c) {
-    const float d2 = __fadd_ru(__fadd_ru(v, __fmul_ru(mj.nrm, rho2c)), mi.nrm);
-    const float eps = __fadd_ru(__fmul_ru(__fmul_ru(c.c_acc2, mi.s), mj.s), __fmul_ru(c.c_rnd, __fadd_ru(mi.nrm, mj.nrm)));
+    const float nn = __fadd_ru(mi.nrm, mj.nrm);
+    // (ortho: |v| <= the exact value + n_i + n_j, and the exact one exceeds v by at most 2^-21 of that)
+    // (v = +inf for the padding columns of the first window: no 0 * inf)
+    const float vu = c.up_infl > 0.0f ? __fadd_ru(v, __fmul_ru(c.up_infl, __fadd_ru(fabsf(v), nn))) : v;
+    const float d2 = __fadd_ru(__fadd_ru(vu, __fmul_ru(mj.nrm, rho2c)), mi.nrm);
+    const float eps = __fadd_ru(__fmul_ru(__fmul_ru(c.c_acc2, mi.s), mj.s), __fmul_ru(c.c_rnd, nn));
     const float sq = __fsqrt_ru(fmaxf(__fadd_ru(d2, eps), 0.0f));
     return __fmul_ru(c.one_plus_g, __fadd_ru(__fadd_ru(sq, mi.delta), mj.delta));
 }
@@ -333,6 +360,7 @@ __device__ __forceinline__ void bound_to_thresholds(float V, const ColMeta &mi, 
 struct SweepArgs {
     const float *nprime;     // [Tpad] n'_j (+inf beyond T), sorted column order
     const float *tile_smax;  // [n column tiles] max_j s_j over the tile
+    const float *psorted;    // [Tpad] projections q_j in sorted order (STREAM mode: the (q_i - q_j)^2 term)
     const float *thr;        // [rows] theta_i (+inf until k candidates are known)
     const float *kap;        // [rows] kappa_i
     const uint4 *rng;        // [row blocks] column tiles of this round: [x, y) and [z, w)
@@ -513,7 +541,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // scheduler the TMEM / L1 latencies of one warp hide behind the compares of the others. =====
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
         uint32_t rloc[2];
-        float thr[2], kap[2];
+        float thr[2], kap[2], qrow[2];
         uint32_t trow[2];  // FIRST: contig of the row (a value no column has for rows beyond the end)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -523,7 +551,9 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
             kap[h] = live ? a.kap[row] : 0.0f;
             trow[h] = 0xFFFFFFFEu;
+            qrow[h] = 0.0f;
             if (FIRST && live) trow[h] = a.tid_sorted[a.rows_a ? a.rows_a[row] : row];
+            if (STREAM && live) qrow[h] = a.psorted[a.rows_a ? a.rows_a[row] : row];
         }
         uint32_t as = 0, aph = 0;
         for (uint32_t it = 0; it < n_tiles; ++it) {
@@ -547,6 +577,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + cpart * 32u;
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
                 if (FIRST) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.tid_sorted + jn));
+                if (STREAM) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
             }
             uint32_t tj[FIRST ? 32 : 1];
             if (FIRST) {
@@ -566,6 +597,28 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int h = 0; h < 2; ++h) {
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
+                if (STREAM) {
+                    // ortho mode: r[c] <- n'_j - 2 g + (q_j - q_i)^2.  The difference is rounded towards zero
+                    // and the FMA down, so the value never exceeds the exact one: a column that passes the
+                    // exact test passes this one, and the stored value is a lower bound (the compaction
+                    // inflates it for the upper bound).  The projections are loaded after n'_j has been
+                    // consumed, into the same registers.
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaf(-2.0f, __uint_as_float(r[c]), nj[c]));
+                    const float4 *pj4 = reinterpret_cast<const float4 *>(a.psorted + j0);
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 pv = __ldg(pj4 + g4);
+                        const float d0 = __fsub_rz(pv.x, qrow[h]), d1 = __fsub_rz(pv.y, qrow[h]);
+                        const float d2 = __fsub_rz(pv.z, qrow[h]), d3 = __fsub_rz(pv.w, qrow[h]);
+                        r[4 * g4 + 0] = __float_as_uint(__fmaf_rd(d0, d0, __uint_as_float(r[4 * g4 + 0])));
+                        r[4 * g4 + 1] = __float_as_uint(__fmaf_rd(d1, d1, __uint_as_float(r[4 * g4 + 1])));
+                        r[4 * g4 + 2] = __float_as_uint(__fmaf_rd(d2, d2, __uint_as_float(r[4 * g4 + 2])));
+                        r[4 * g4 + 3] = __float_as_uint(__fmaf_rd(d3, d3, __uint_as_float(r[4 * g4 + 3])));
+                    }
+                }
+                // the value of column c under test: already formed in ortho mode
+#define CNVB_VAL(c) (STREAM ? __uint_as_float(r[c]) : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]))
                 if (FIRST) {
                     // First window, no bound yet: store only the 8 smallest values of this row's 32
                     // columns (same-contig columns excluded).  The k-th smallest upper bound among the
@@ -577,7 +630,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int t8 = 0; t8 < 8; ++t8) top[t8] = inf;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        float v = tj[c] == trow[h] ? inf : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                        float v = tj[c] == trow[h] ? inf : CNVB_VAL(c);
 #pragma unroll
                         for (int t8 = 0; t8 < 8; ++t8) {  // sorted insertion
                             const float lo = fminf(top[t8], v);
@@ -591,7 +644,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (top[0] < inf && row < a.rows) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                            const float v = CNVB_VAL(c);
                             if (v <= top[7] && tj[c] != trow[h]) {
                                 const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);
                                 if (slot < kCandCap) {
@@ -615,10 +668,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint32_t gmask = 0u;
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
-                    const bool p = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj[4 * g4 + 0]) <= rhs ||
-                                   fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj[4 * g4 + 1]) <= rhs ||
-                                   fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj[4 * g4 + 2]) <= rhs ||
-                                   fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj[4 * g4 + 3]) <= rhs;
+                    const bool p = CNVB_VAL(4 * g4 + 0) <= rhs || CNVB_VAL(4 * g4 + 1) <= rhs ||
+                                   CNVB_VAL(4 * g4 + 2) <= rhs || CNVB_VAL(4 * g4 + 3) <= rhs;
                     gmask |= p ? (1u << g4) : 0u;
                 }
                 const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
@@ -629,7 +680,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                             for (int e4 = 0; e4 < 4; ++e4) {
                                 const int c = 4 * g4 + e4;
-                                const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                                const float v = CNVB_VAL(c);
                                 const uint32_t j = j0 + c;
                                 if (v <= rhs && j < a.T) {  // (same-contig pairs are dropped by the compaction)
                                     const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
@@ -663,6 +714,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 #undef CNVB_TILE_AT
+#undef CNVB_VAL
 
 // ---- windows: which column tiles a block of rows still has to see --------------------------------
 struct WindowArgs {
@@ -1123,7 +1175,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(Tpad, &delta)) != cudaSuccess || (e = g.alloc(rows, &thr)) != cudaSuccess ||
         (e = g.alloc(rows, &kap)) != cudaSuccess || (e = g.alloc(rows, &vg)) != cudaSuccess ||
         (e = g.alloc(Tpad, &nprime)) != cudaSuccess || (e = g.alloc(Tpad, &snorm)) != cudaSuccess ||
-        (e = g.alloc(n_tiles, &tile_smax)) != cudaSuccess || (e = g.alloc(T, &psorted)) != cudaSuccess ||
+        (e = g.alloc(n_tiles, &tile_smax)) != cudaSuccess || (e = g.alloc(Tpad, &psorted)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_val)) != cudaSuccess ||
         (e = g.alloc((size_t)rows * kCandCap, &cand_idx)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
         (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(rows, &seen)) != cudaSuccess ||
@@ -1166,11 +1218,12 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ctx->launches += 1;
     if (Tpad > T) cudaMemsetAsync(H + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
     wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, dtid, T, S, Kp, cmean, scale, perm, pkey_sorted, H, nrm, delta,
-                                                 tid_sorted, psorted, scal + 1);
+                                                 tid_sorted, psorted, scal + 1, stream_a ? 1 : 0);
     CNVB_LAUNCHED(ctx, "wis_pack_kernel");
     const double c_acc = (double)Kp / 8388608.0;  // fp32 accumulation of Kp exact products, truncating adds
     const double c_rnd = 8.0 / 16777216.0;        // f32 rounding of norms and of the epilogue FFMAs
     if (Tpad > T) cudaMemsetAsync(tid_sorted + T, 0xFF, (size_t)(Tpad - T) * 4, st);
+    if (Tpad > T) cudaMemsetAsync(psorted + T, 0, (size_t)(Tpad - T) * 4, st);  // (n'_j = +inf there)
     wis_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nrm, delta, tid_sorted, T, Tpad, scal + 1, c_rnd, nprime, snorm, meta);
     CNVB_LAUNCHED(ctx, "wis_cols_kernel");
     wis_tile_smax_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(snorm, n_tiles, tile_smax);
@@ -1207,6 +1260,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         const double g_ref = (S + 4.0) / 16777216.0;  // the reference's own f32 rounding (sequential sum + sqrt)
         auto up = [](double v) { return std::nextafterf((float)v, INFINITY); };
         auto down = [](double v) { return std::nextafterf((float)v, -INFINITY); };
+        bc.up_infl = stream_a ? up(1.0 / 1048576.0) : 0.0f;
         bc.c_acc2 = up(2.0 * c_acc);
         bc.c_rnd = up(c_rnd);
         bc.one_plus_g = up(1.0 + g_ref);
@@ -1217,6 +1271,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     SweepArgs sa{};
     sa.nprime = nprime;
     sa.tile_smax = tile_smax;
+    sa.psorted = psorted;
     sa.thr = thr;
     sa.kap = kap;
     sa.rng = rng;

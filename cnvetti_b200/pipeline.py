@@ -210,6 +210,8 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
     be exercised with gloo on a CPU-only box.
 
     Returns dict(model=..., rows=(lo, hi), cv_rel[S_r][T], cvz_rows[S][rows], states[S_r][T] uint8)."""
+    import os
+    import sys
     import time
     import torch
     from . import model_wis, parallel
@@ -222,7 +224,14 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
     S = sample_ranges[-1][1]
     dev = lcv.device
 
+    progress = bool(os.environ.get("CNVB_PROGRESS"))
+
     def mark(name, t0):
+        if progress:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            sys.stderr.write("[wis_call_cohort] %s done (%.3f s)\n" % (name, time.perf_counter() - t0))
+            sys.stderr.flush()
         if timings is not None:
             if dev.type == "cuda":
                 torch.cuda.synchronize(dev)

@@ -184,6 +184,29 @@ def test_wis_tensor_engine_matches_reference_sets(oracle, ctx, T, S, k, ncontig,
     assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
 
 
+def test_wis_tensor_low_efficiency_rows_many_samples(oracle, ctx):
+    """More than 128 samples: the all-ones component is carried in f32 beside the fp16 residual (ortho
+    mode).  Targets with a very low or very high capture efficiency -- whose fp16 norms used to be
+    dominated by that component, so that the K-proportional error bound let their candidate buffers
+    overflow on dense panels -- must stay on the tensor path and match the oracle bit for bit."""
+    T, S, k = 6000, 256, 60
+    rng = np.random.default_rng(77)
+    eff = rng.lognormal(0.0, 1.0, T)            # a wide range: 0.05 .. 20
+    eff[:300] = rng.uniform(0.02, 0.06, 300)    # a dense cluster of low-efficiency targets
+    X = (eff[:, None] * rng.normal(1.0, 0.08, (T, S)))
+    X = (np.maximum(X, 0.0) / X.sum(axis=0, keepdims=True)).astype(np.float32)
+    X[5] = X[6]
+    tids = (np.arange(T) * 4 // T).astype(np.uint32)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
+    dist, idx = mw.compute_distances(_dev(X), _dev(tids), opts, ctx=ctx)
+    st = mw.last_stats(ctx)
+    assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
+    assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
+    assert st["fallback_rows"] == 0, st
+    assert st["rescored_pairs"] < 4 * T * k, st
+
+
 def test_wis_tensor_single_contig_and_tiny_other_contig(oracle, ctx):
     T, S, k = 4500, 20, 50
     X, _ = synth.synth_panel(77, T, S, n_contigs=1)
