@@ -738,8 +738,9 @@ def bench_cfg5(args):
         oracle.build()
         ncpu = os.cpu_count() or 1
         nrows, cols = min(args.cpu_rows, 256), min(T, 200_000)
-        Xs = np.ascontiguousarray(rr["panel"][:cols].cpu().numpy())
-        th = tids[:cols].cpu().numpy().astype(np.uint32)
+        pick_c = torch.arange(cols, device=dev) * (T // cols)  # spread over the genome (all contigs)
+        Xs = np.ascontiguousarray(rr["panel"][pick_c].cpu().numpy())
+        th = tids[pick_c].cpu().numpy().astype(np.uint32)
         del rr, d_in
         t0 = time.perf_counter()
         oracle.wis_distances(Xs, th, 100, 0, nrows, nthreads=ncpu)

@@ -66,6 +66,16 @@ SYMBOLS = {
     "cnvb_ctx_timing_reset": (_int, [_vp]),
     "cnvb_ctx_timing_query": (_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "cnvb_pack_reads": (_int, [_u64, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]),
+    "cnvb_bam_open": (_int, [C.c_char_p, _int, C.POINTER(_vp)]),
+    "cnvb_bam_error": (C.c_char_p, [_vp]),
+    "cnvb_bam_n_refs": (_u32, [_vp]),
+    "cnvb_bam_ref_name": (C.c_char_p, [_vp, _u32]),
+    "cnvb_bam_ref_len": (_u32, [_vp, _u32]),
+    "cnvb_bam_header_text": (_vp, [_vp, C.POINTER(_u64)]),
+    "cnvb_bam_decode": (_int, [_vp, C.c_float, _int]),
+    "cnvb_bam_ref_reads": (_int, [_vp, _u32, C.POINTER(ReadSoa)]),
+    "cnvb_bam_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
+    "cnvb_bam_close": (None, [_vp]),
     "cnvb_cov_create": (_int, [_vp, C.POINTER(CovOpts), _int, _u32, _vp, _vp, _u32, _vp, _vp,
                                _u32, C.POINTER(_vp)]),
     "cnvb_cov_put_records": (_int, [_vp, C.POINTER(ReadSoa)]),

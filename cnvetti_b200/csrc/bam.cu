@@ -1,0 +1,468 @@
+// bam.cu -- host BGZF/BAM decoder: file -> per-contig structure-of-arrays read batches.
+//
+// Replaces what the reference gets from rust-htslib for the coverage path: `bam::IndexedReader`
+// + `fetch(tid, 0, len)` + `read(&mut record)` per region (lib-coverage/src/lib.rs:533-547,
+// agg.rs:224-228) and the per-record derivations of the aggregators (agg.rs:124-133, 174-198,
+// 312-320).  `cmd coverage` visits every contig of the file in turn, so the decoder makes ONE
+// pass over the file instead of one index seek per region: BGZF blocks are inflated on host
+// threads (zlib raw inflate, one block per task), record boundaries are walked once, and the
+// threads derive the SoA columns of disjoint record ranges.  The columns of a contig are what
+// `fetch` on that contig yields, in file (= coordinate) order: every record whose refID is the
+// contig, including unmapped reads placed at their mate's position; records without a
+// reference (refID < 0) are counted and dropped.
+//
+// Pure host code.  Buffers are page-locked (cudaHostAlloc) on request so that the SoA columns
+// can be handed to cnvb_cov_put_records / cnvb_coverage_run and copied by DMA.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace cnvb;
+
+namespace {
+
+template <typename T>
+struct HostColumn {  // growing array, optionally page-locked
+    T *p = nullptr;
+    uint64_t n = 0, cap = 0;
+    bool pinned = false;
+    bool reserve(uint64_t want, bool pin) {
+        if (want <= cap) return true;
+        uint64_t ncap = std::max<uint64_t>(want, cap ? cap * 2 : 1 << 16);
+        T *q = nullptr;
+        bool got_pinned = false;
+        if (pin && cudaHostAlloc(reinterpret_cast<void **>(&q), ncap * sizeof(T), cudaHostAllocDefault) == cudaSuccess) {
+            got_pinned = true;
+        } else {
+            cudaGetLastError();
+            q = static_cast<T *>(malloc(ncap * sizeof(T)));
+            if (!q) return false;
+        }
+        if (n) memcpy(q, p, n * sizeof(T));
+        release();
+        p = q;
+        cap = ncap;
+        pinned = got_pinned;
+        return true;
+    }
+    void release() {
+        if (!p) return;
+        if (pinned) cudaFreeHost(p); else free(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct RefReads {
+    HostColumn<int32_t> pos, end, mid, frag_end;
+    HostColumn<uint8_t> mapq;
+    HostColumn<uint16_t> flags;
+    uint64_t n = 0;
+    bool reserve(uint64_t want, bool pin) {
+        return pos.reserve(want, pin) && end.reserve(want, pin) && mid.reserve(want, pin) &&
+               frag_end.reserve(want, pin) && mapq.reserve(want, pin) && flags.reserve(want, pin);
+    }
+    void release() {
+        pos.release(); end.release(); mid.release(); frag_end.release(); mapq.release(); flags.release();
+    }
+};
+
+struct Block {  // one BGZF block inside the file image
+    uint64_t off;     // start of the deflate stream
+    uint32_t clen;    // compressed payload length
+    uint32_t isize;   // uncompressed length (trailer)
+    uint32_t crc;
+    uint64_t uoff;    // offset in the chunk's uncompressed buffer
+};
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+// the per-record derivation shared with cnvb_pack_reads (ctx.cu)
+inline void derive(int32_t pos, int32_t isize, uint16_t f, const uint8_t *cigar, uint32_t n_cigar, float min_unclipped,
+                   int32_t &o_end, int32_t &o_mid, int32_t &o_frag_end, uint16_t &o_flags) {
+    uint32_t ref_len = 0, clipped = 0, unclipped = 0;
+    for (uint32_t c = 0; c < n_cigar; ++c) {
+        const uint32_t w = rd32(cigar + 4 * c), op = w & 0xFu, len = w >> 4;
+        switch (op) {
+        case 0: case 7: case 8: ref_len += len; unclipped += len; break;  // M = X
+        case 1: unclipped += len; break;                                  // I
+        case 2: case 3: ref_len += len; break;                            // D N
+        case 4: case 5: clipped += len; break;                            // S H
+        default: break;                                                   // P
+        }
+    }
+    const int32_t end_pos = pos + (int32_t)ref_len;  // CigarStringView::end_pos()
+    uint32_t rlen = 1;                               // htslib bam_endpos()
+    if (!(f & 0x4) && n_cigar > 0) rlen = ref_len ? ref_len : 1;
+    o_end = pos + (int32_t)rlen;
+    const bool paired = f & 0x1;
+    o_mid = paired ? pos + isize / 2 : pos + end_pos;          // agg.rs:124-133
+    o_frag_end = paired ? pos + isize : end_pos;               // agg.rs:312-320
+    uint16_t x = f & 0x0FFF;
+    const float ratio = (float)unclipped / (float)(clipped + unclipped);  // agg.rs:174-193 (f32; NaN compares false)
+    if (ratio < min_unclipped) x |= CNVB_FLAG_CLIPFAIL;
+    if (isize <= 0) x |= CNVB_FLAG_ISIZE_NONPOS;               // agg.rs:196-198
+    o_flags = x;
+}
+
+void run_parallel(int n_threads, uint64_t n_items, const std::function<void(uint64_t, uint64_t, int)> &fn) {
+    if (n_threads <= 1 || n_items < 2) {
+        fn(0, n_items, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    const uint64_t per = (n_items + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const uint64_t a = std::min<uint64_t>(n_items, per * t), b = std::min<uint64_t>(n_items, a + per);
+        if (a < b) th.emplace_back(fn, a, b, t);
+    }
+    for (auto &x : th) x.join();
+}
+
+}  // namespace
+
+struct cnvb_bam {
+    std::string path, error, text;
+    std::vector<std::string> ref_names;
+    std::vector<uint32_t> ref_lens;
+    std::vector<RefReads> refs;
+    int n_threads = 1;
+    uint64_t n_records = 0, n_unplaced = 0, bytes_compressed = 0, bytes_uncompressed = 0;
+    double t_inflate = 0.0, t_parse = 0.0, t_total = 0.0;
+    bool decoded = false;
+    ~cnvb_bam() {
+        for (auto &r : refs) r.release();
+    }
+};
+
+namespace {
+
+int bam_fail(cnvb_bam *b, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    b->error = buf;
+    return code;
+}
+
+// The whole decode: one pass, chunks of BGZF blocks.
+int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    FILE *f = fopen(b->path.c_str(), "rb");
+    if (!f) return bam_fail(b, CNVB_ERR_INVALID, "Could not open BAM file %s", b->path.c_str());
+    const uint64_t kChunkBytes = header_only ? (1ull << 20) : (64ull << 20);  // compressed bytes per chunk
+    std::vector<uint8_t> cbuf, ubuf, carry;
+    std::vector<Block> blocks;
+    std::vector<uint64_t> rec_off;
+    bool header_done = false, eof = false;
+    uint64_t file_pos = 0;
+    std::vector<uint8_t> left;  // compressed bytes of an incomplete block at the end of the last read
+    struct ChunkOut {
+        std::vector<int32_t> tid, pos, end, mid, frag_end;
+        std::vector<uint8_t> mapq;
+        std::vector<uint16_t> flags;
+    } co;
+    int rc = CNVB_OK;
+    while (!eof && rc == CNVB_OK) {
+        // ---- read compressed bytes, cut into whole blocks
+        cbuf.assign(left.begin(), left.end());
+        const uint64_t have = cbuf.size();
+        cbuf.resize(have + kChunkBytes);
+        const size_t got = fread(cbuf.data() + have, 1, kChunkBytes, f);
+        cbuf.resize(have + got);
+        file_pos += got;
+        if (got == 0) eof = true;
+        blocks.clear();
+        uint64_t p = 0, utotal = 0;
+        while (p + 18 <= cbuf.size()) {
+            const uint8_t *h = cbuf.data() + p;
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
+                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: not a BGZF file (bad block header at compressed offset %llu)",
+                              b->path.c_str(), (unsigned long long)(file_pos - cbuf.size() + p));
+                break;
+            }
+            const uint32_t xlen = rd16(h + 10);
+            if (p + 12 + xlen > cbuf.size()) break;
+            uint32_t bsize = 0;
+            for (uint32_t x = 0; x + 4 <= xlen;) {  // extra subfields: find BC
+                const uint8_t *e = h + 12 + x;
+                const uint32_t slen = rd16(e + 2);
+                if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(e + 4) + 1;
+                x += 4 + slen;
+            }
+            if (bsize < 12 + xlen + 8) {
+                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: BGZF block without a valid BC subfield", b->path.c_str());
+                break;
+            }
+            if (p + bsize > cbuf.size()) break;  // incomplete block: next read
+            Block bl;
+            bl.off = p + 12 + xlen;
+            bl.clen = bsize - (12 + xlen) - 8;
+            bl.crc = rd32(h + bsize - 8);
+            bl.isize = rd32(h + bsize - 4);
+            bl.uoff = utotal;
+            utotal += bl.isize;
+            blocks.push_back(bl);
+            p += bsize;
+        }
+        if (rc != CNVB_OK) break;
+        left.assign(cbuf.begin() + p, cbuf.end());
+        if (eof && !left.empty()) {
+            rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BGZF block at the end of the file", b->path.c_str());
+            break;
+        }
+        b->bytes_compressed += p;
+        b->bytes_uncompressed += utotal;
+        // ---- inflate the blocks of the chunk in parallel, behind the carried-over partial record
+        const auto t0 = clk::now();
+        const uint64_t c0 = carry.size();
+        ubuf.resize(c0 + utotal);
+        if (c0) memcpy(ubuf.data(), carry.data(), c0);
+        std::atomic<int> bad{0};
+        run_parallel(b->n_threads, blocks.size(), [&](uint64_t lo, uint64_t hi, int) {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) {
+                bad = 1;
+                return;
+            }
+            for (uint64_t i = lo; i < hi; ++i) {
+                const Block &bl = blocks[i];
+                if (bl.isize == 0) continue;
+                inflateReset(&zs);
+                zs.next_in = cbuf.data() + bl.off;
+                zs.avail_in = bl.clen;
+                zs.next_out = ubuf.data() + c0 + bl.uoff;
+                zs.avail_out = bl.isize;
+                const int r = inflate(&zs, Z_FINISH);
+                if (r != Z_STREAM_END || zs.avail_out != 0 ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), ubuf.data() + c0 + bl.uoff, bl.isize) != bl.crc)
+                    bad = 1;
+            }
+            inflateEnd(&zs);
+        });
+        b->t_inflate += std::chrono::duration<double>(clk::now() - t0).count();
+        if (bad) {
+            rc = bam_fail(b, CNVB_ERR_INVALID, "%s: corrupt BGZF block (inflate or CRC failure)", b->path.c_str());
+            break;
+        }
+        // ---- header (once), then records
+        const auto t1 = clk::now();
+        const uint8_t *u = ubuf.data();
+        const uint64_t un = ubuf.size();
+        uint64_t q = 0;
+        if (!header_done) {
+            bool complete = false;
+            do {
+                if (un < 12) break;
+                if (memcmp(u, "BAM\1", 4) != 0) {
+                    rc = bam_fail(b, CNVB_ERR_INVALID, "%s: not a BAM file (bad magic)", b->path.c_str());
+                    break;
+                }
+                const uint64_t l_text = rd32(u + 4);
+                if (un < 12 + l_text) break;
+                const uint32_t n_ref = rd32(u + 8 + l_text);
+                uint64_t w = 12 + l_text;
+                std::vector<std::string> names;
+                std::vector<uint32_t> lens;
+                bool ok = true;
+                for (uint32_t r = 0; r < n_ref; ++r) {
+                    if (un < w + 4) { ok = false; break; }
+                    const uint64_t l_name = rd32(u + w);
+                    if (un < w + 4 + l_name + 4) { ok = false; break; }
+                    names.emplace_back(reinterpret_cast<const char *>(u + w + 4), l_name ? l_name - 1 : 0);
+                    lens.push_back(rd32(u + w + 4 + l_name));
+                    w += 8 + l_name;
+                }
+                if (!ok) break;
+                b->text.assign(reinterpret_cast<const char *>(u + 8), l_text);
+                while (!b->text.empty() && b->text.back() == '\0') b->text.pop_back();
+                b->ref_names = names;
+                b->ref_lens = lens;
+                b->refs.resize(n_ref);
+                q = w;
+                complete = true;
+            } while (false);
+            if (rc != CNVB_OK) break;
+            if (!complete) {  // header spans more than this chunk: read on
+                if (eof) {
+                    rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BAM header", b->path.c_str());
+                    break;
+                }
+                carry.assign(ubuf.begin(), ubuf.end());
+                continue;
+            }
+            header_done = true;
+            if (header_only) break;
+        }
+        // record boundaries
+        rec_off.clear();
+        while (q + 4 <= un) {
+            const uint64_t bs = rd32(u + q);
+            if (bs < 32) {
+                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: corrupt BAM record (block_size %llu)", b->path.c_str(),
+                              (unsigned long long)bs);
+                break;
+            }
+            if (q + 4 + bs > un) break;
+            rec_off.push_back(q);
+            q += 4 + bs;
+        }
+        if (rc != CNVB_OK) break;
+        const uint64_t nr = rec_off.size();
+        co.tid.resize(nr); co.pos.resize(nr); co.end.resize(nr); co.mid.resize(nr); co.frag_end.resize(nr);
+        co.mapq.resize(nr); co.flags.resize(nr);
+        std::atomic<int> badrec{0};
+        run_parallel(b->n_threads, nr, [&](uint64_t lo, uint64_t hi, int) {
+            for (uint64_t i = lo; i < hi; ++i) {
+                const uint8_t *r = u + rec_off[i];
+                const uint32_t bs = rd32(r);
+                const int32_t tid = (int32_t)rd32(r + 4), pos = (int32_t)rd32(r + 8);
+                const uint32_t l_name = r[12], mapq = r[13], n_cigar = rd16(r + 16);
+                const uint16_t flag = rd16(r + 18);
+                const int32_t tlen = (int32_t)rd32(r + 32);
+                if (36ull + l_name + 4ull * n_cigar > 4ull + bs) {
+                    badrec = 1;
+                    continue;
+                }
+                co.tid[i] = tid;
+                co.pos[i] = pos;
+                co.mapq[i] = (uint8_t)mapq;
+                derive(pos, tlen, flag, r + 36 + l_name, n_cigar, min_unclipped, co.end[i], co.mid[i], co.frag_end[i],
+                       co.flags[i]);
+            }
+        });
+        if (badrec) {
+            rc = bam_fail(b, CNVB_ERR_INVALID, "%s: corrupt BAM record (CIGAR past the end of the record)", b->path.c_str());
+            break;
+        }
+        // append runs of equal refID to the contig's columns (file order is kept)
+        for (uint64_t i = 0; i < nr;) {
+            uint64_t j = i + 1;
+            const int32_t tid = co.tid[i];
+            while (j < nr && co.tid[j] == tid) ++j;
+            const uint64_t m = j - i;
+            if (tid < 0) {
+                b->n_unplaced += m;
+            } else if ((uint64_t)tid >= b->refs.size()) {
+                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: record with refID %d but the header has %zu references",
+                              b->path.c_str(), tid, b->refs.size());
+                break;
+            } else {
+                RefReads &rr = b->refs[tid];
+                if (!rr.reserve(rr.n + m, pinned)) {
+                    rc = bam_fail(b, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
+                    break;
+                }
+                memcpy(rr.pos.p + rr.n, co.pos.data() + i, m * 4);
+                memcpy(rr.end.p + rr.n, co.end.data() + i, m * 4);
+                memcpy(rr.mid.p + rr.n, co.mid.data() + i, m * 4);
+                memcpy(rr.frag_end.p + rr.n, co.frag_end.data() + i, m * 4);
+                memcpy(rr.mapq.p + rr.n, co.mapq.data() + i, m);
+                memcpy(rr.flags.p + rr.n, co.flags.data() + i, m * 2);
+                rr.n += m;
+                rr.pos.n = rr.end.n = rr.mid.n = rr.frag_end.n = rr.mapq.n = rr.flags.n = rr.n;
+            }
+            i = j;
+        }
+        b->n_records += nr;
+        carry.assign(ubuf.begin() + q, ubuf.end());
+        b->t_parse += std::chrono::duration<double>(clk::now() - t1).count();
+    }
+    fclose(f);
+    if (rc == CNVB_OK && !header_done) rc = bam_fail(b, CNVB_ERR_INVALID, "%s: empty or truncated BAM file", b->path.c_str());
+    if (rc == CNVB_OK && !header_only && !carry.empty())
+        rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BAM record at the end of the file", b->path.c_str());
+    b->t_total += std::chrono::duration<double>(clk::now() - t_begin).count();
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int cnvb_bam_open(const char *path, int n_threads, cnvb_bam **out) {
+    if (!path || !out) return CNVB_ERR_INVALID;
+    cnvb_bam *b = new (std::nothrow) cnvb_bam();
+    if (!b) return CNVB_ERR_NOMEM;
+    b->path = path;
+    const unsigned hw = std::thread::hardware_concurrency();
+    b->n_threads = n_threads > 0 ? n_threads : (hw ? (int)hw : 1);
+    *out = b;
+    return decode(b, 0.0f, false, true);  // header only; the handle is returned even on failure (error text)
+}
+
+extern "C" const char *cnvb_bam_error(const cnvb_bam *b) { return b ? b->error.c_str() : "null BAM handle"; }
+extern "C" uint32_t cnvb_bam_n_refs(const cnvb_bam *b) { return b ? (uint32_t)b->ref_names.size() : 0; }
+extern "C" const char *cnvb_bam_ref_name(const cnvb_bam *b, uint32_t tid) {
+    return b && tid < b->ref_names.size() ? b->ref_names[tid].c_str() : nullptr;
+}
+extern "C" uint32_t cnvb_bam_ref_len(const cnvb_bam *b, uint32_t tid) {
+    return b && tid < b->ref_lens.size() ? b->ref_lens[tid] : 0;
+}
+extern "C" const char *cnvb_bam_header_text(const cnvb_bam *b, uint64_t *len) {
+    if (!b) return nullptr;
+    if (len) *len = b->text.size();
+    return b->text.c_str();
+}
+
+extern "C" int cnvb_bam_decode(cnvb_bam *b, float min_unclipped, int pinned) {
+    if (!b) return CNVB_ERR_INVALID;
+    if (!b->error.empty()) return CNVB_ERR_STATE;
+    for (auto &r : b->refs) {
+        r.n = 0;
+        r.pos.n = r.end.n = r.mid.n = r.frag_end.n = r.mapq.n = r.flags.n = 0;
+    }
+    b->n_records = b->n_unplaced = b->bytes_compressed = b->bytes_uncompressed = 0;
+    b->t_inflate = b->t_parse = b->t_total = 0.0;
+    const int rc = decode(b, min_unclipped, pinned != 0, false);
+    b->decoded = rc == CNVB_OK;
+    return rc;
+}
+
+extern "C" int cnvb_bam_ref_reads(const cnvb_bam *b, uint32_t tid, cnvb_read_soa *out) {
+    if (!b || !out || tid >= b->refs.size() || !b->decoded) return CNVB_ERR_INVALID;
+    const RefReads &r = b->refs[tid];
+    memset(out, 0, sizeof *out);
+    out->n = r.n;
+    out->pos = r.pos.p;
+    out->end = r.end.p;
+    out->mid = r.mid.p;
+    out->frag_end = r.frag_end.p;
+    out->mapq = r.mapq.p;
+    out->flags = r.flags.p;
+    out->mem = CNVB_MEM_HOST;
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_bam_stats(const cnvb_bam *b, uint64_t counts[4], double seconds[3]) {
+    if (!b) return CNVB_ERR_INVALID;
+    if (counts) {
+        counts[0] = b->n_records;
+        counts[1] = b->n_unplaced;
+        counts[2] = b->bytes_compressed;
+        counts[3] = b->bytes_uncompressed;
+    }
+    if (seconds) {
+        seconds[0] = b->t_total;
+        seconds[1] = b->t_inflate;
+        seconds[2] = b->t_parse;
+    }
+    return CNVB_OK;
+}
+
+extern "C" void cnvb_bam_close(cnvb_bam *b) { delete b; }

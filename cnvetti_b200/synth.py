@@ -202,3 +202,95 @@ def synth_cv_lanes(seed, n_bins, n_cnv=20, noise=0.08, sigma0=0.02, missing_frac
     miss = rng.random(n_bins) < missing_frac
     cv[miss] = np.frombuffer(np.uint32(0x7F800001).tobytes(), np.float32)[0]
     return cv, cn
+
+
+# ---- synthetic BAM files (tests and the host-decode leg of bench.py) ------------------------------
+def _bgzf_block(payload, level):
+    import struct
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    data = c.compress(payload) + c.flush()
+    head = struct.pack("<4BI2BH2BHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord("B"), ord("C"), 2, len(data) + 25)
+    return head + data + struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload))
+
+
+def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, block_payload=0xff00):
+    """Write a coordinate-sorted BAM file.  `contigs`: [(name, length)]; `records`: one dict per contig (or
+    None) with the BAM-level arrays of `synth_bam_records` (pos, isize, flag, mapq, cigar_off, cigar);
+    an optional entry with key -1 in a dict `records` holds reads without a reference.  Read names,
+    sequences and qualities are fillers (the coverage path never looks at them).  The records are laid
+    out with numpy, so tens of millions of reads are practical."""
+    import struct
+    if isinstance(records, dict):
+        extra = records.get(-1)
+        records = [records.get(i) for i in range(len(contigs))]
+    else:
+        extra = None
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % c for c in contigs) + \
+           "@RG\tID:rg1\tSM:%s\n" % sample
+    head = b"BAM\x01" + struct.pack("<I", len(text)) + text.encode() + struct.pack("<I", len(contigs))
+    for name, length in contigs:
+        head += struct.pack("<I", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<I", length)
+    chunks = [np.frombuffer(head, np.uint8)]
+    l_name = 8  # "r" + 6 characters + NUL
+    for tid, d in list(enumerate(records)) + [(-1, extra)]:
+        if d is None or len(d["pos"]) == 0:
+            continue
+        n = len(d["pos"])
+        coff = np.asarray(d["cigar_off"], np.int64)
+        ncig = (coff[1:] - coff[:-1]).astype(np.int64)
+        cig = np.asarray(d["cigar"], np.uint32)
+        # query length = sum of M I S = X ops (what l_seq must be)
+        ops, lens = cig & 0xF, (cig >> 4).astype(np.int64)
+        q = np.where(np.isin(ops, (0, 1, 4, 7, 8)), lens, 0)
+        cs = np.concatenate([[0], np.cumsum(q)])
+        l_seq = (cs[coff[1:]] - cs[coff[:-1]]).astype(np.int64)
+        if read_len is not None:
+            l_seq = np.full(n, int(read_len), np.int64)
+        size = 32 + l_name + 4 * ncig + (l_seq + 1) // 2 + l_seq          # block_size
+        off = np.concatenate([[0], np.cumsum(size + 4)]).astype(np.int64)
+        buf = np.zeros(int(off[-1]), np.uint8)
+        o = off[:-1]
+
+        def put(at, val, nbytes):
+            v = np.asarray(val).astype(np.int64)
+            for k in range(nbytes):
+                buf[o + at + k] = (v >> (8 * k)) & 0xFF
+
+        pos = np.asarray(d["pos"], np.int64)
+        put(0, size, 4)
+        put(4, np.full(n, tid, np.int64) & 0xFFFFFFFF, 4)
+        put(8, pos & 0xFFFFFFFF, 4)
+        put(12, np.full(n, l_name), 1)
+        put(13, d["mapq"], 1)
+        put(14, np.full(n, 4680), 2)                                       # bin: unused here
+        put(16, ncig, 2)
+        put(18, d["flag"], 2)
+        put(20, l_seq, 4)
+        put(24, np.full(n, tid, np.int64) & 0xFFFFFFFF, 4)                 # mate on the same contig
+        put(28, (pos + np.asarray(d["isize"], np.int64)) & 0xFFFFFFFF, 4)  # (filler)
+        put(32, np.asarray(d["isize"], np.int64) & 0xFFFFFFFF, 4)
+        idx = np.arange(n)
+        buf[o + 36] = ord("r")
+        for k in range(6):
+            buf[o + 37 + k] = 48 + (idx // 10 ** (5 - k)) % 10
+        # CIGAR words: record of every op, position inside its record
+        rec_of = np.repeat(np.arange(n), ncig)
+        within = np.arange(cig.size) - np.repeat(coff[:-1], ncig)
+        base = o[rec_of] + 36 + l_name + 4 * within
+        for k in range(4):
+            buf[base + k] = (cig >> (8 * k)) & 0xFF
+        # qualities 0xFF (missing)
+        qbase = o + 36 + l_name + 4 * ncig + (l_seq + 1) // 2
+        if (l_seq == l_seq[0]).all():
+            buf[(qbase[:, None] + np.arange(int(l_seq[0]))[None, :]).ravel()] = 0xFF
+        else:
+            for i in range(n):
+                buf[qbase[i]:qbase[i] + l_seq[i]] = 0xFF
+        chunks.append(buf)
+    stream = np.concatenate(chunks)
+    with open(path, "wb") as f:
+        for a in range(0, stream.size, block_payload):
+            f.write(_bgzf_block(stream[a:a + block_payload].tobytes(), level))
+        f.write(_bgzf_block(b"", level))  # EOF marker
+    return path

@@ -212,6 +212,33 @@ void cnvb_piles_destroy(cnvb_piles *piles);
 int cnvb_pile_threshold(const uint64_t *abs_freq, uint64_t n, double fdr_cutoff, uint32_t *threshold,
                         char *err, uint64_t err_len);
 
+/* ---- host BGZF/BAM decoder ------------------------------------------
+ * Replaces, for the coverage path, rust-htslib's bam::IndexedReader + fetch(tid, 0, len) +
+ * read(&mut record) per region (lib-coverage/src/lib.rs:533-547, agg.rs:224-228) together with
+ * the per-record derivations of cnvb_pack_reads: one pass over the file, BGZF blocks inflated on
+ * n_threads host threads (<= 0: all cores), records turned into per-contig SoA columns in file
+ * (= coordinate) order.  The columns of contig tid are what `fetch` on the whole contig yields;
+ * records with refID < 0 are counted and dropped.  Pure host code: no context, no device.
+ * cnvb_bam_open reads the header only; on failure *out still holds a handle whose
+ * cnvb_bam_error() text says why (close it). */
+typedef struct cnvb_bam cnvb_bam;
+int cnvb_bam_open(const char *path, int n_threads, cnvb_bam **out);
+const char *cnvb_bam_error(const cnvb_bam *b);
+uint32_t cnvb_bam_n_refs(const cnvb_bam *b);
+const char *cnvb_bam_ref_name(const cnvb_bam *b, uint32_t tid);
+uint32_t cnvb_bam_ref_len(const cnvb_bam *b, uint32_t tid);
+/* SAM header text (@RG SM: = the sample name of the output, lib-coverage/src/lib.rs:36-64) */
+const char *cnvb_bam_header_text(const cnvb_bam *b, uint64_t *len);
+/* Decode the whole file.  pinned != 0: page-locked columns (cudaHostAlloc; plain memory if no
+ * CUDA runtime is usable).  min_unclipped as in cnvb_pack_reads. */
+int cnvb_bam_decode(cnvb_bam *b, float min_unclipped, int pinned);
+/* The decoded columns of one contig (pointers stay valid until the next decode / close). */
+int cnvb_bam_ref_reads(const cnvb_bam *b, uint32_t tid, cnvb_read_soa *out);
+/* counts: records decoded | records without reference | compressed bytes | uncompressed bytes;
+ * seconds: whole decode | inflate phases | record walk + SoA derivation (wall clock). */
+int cnvb_bam_stats(const cnvb_bam *b, uint64_t counts[4], double seconds[3]);
+void cnvb_bam_close(cnvb_bam *b);
+
 /* ---- lib-normalize ------------------------------------------------------------------------ */
 /* = run_uncorrected_normalization (lib-normalize/src/uncorrected.rs:20-96).  lcvsd/cvsd may be
  * NULL.  *lcv_sum (host, may be NULL) receives the f64 sum. */

@@ -1,0 +1,115 @@
+"""Host BGZF/BAM decoder (csrc/bam.cu): the SoA columns decoded from a BAM file
+must equal, bit for bit, the columns the packer derives from the same BAM-level arrays -- i.e. the
+file path and the array path feed the kernels identical input.  Pure host code: runs without a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import cnvetti_b200 as cb
+from cnvetti_b200 import bam, synth
+
+
+def _expected(d, min_unclipped):
+    end, mid, frag_end, flags = cb.pack_reads(d["pos"], d["isize"], d["flag"], d["cigar_off"], d["cigar"], min_unclipped)
+    return dict(pos=np.asarray(d["pos"], np.int32), end=end, mid=mid, frag_end=frag_end,
+                mapq=np.asarray(d["mapq"], np.uint8), flags=flags)
+
+
+def _check(batch, exp):
+    for k, v in exp.items():
+        got = np.asarray(getattr(batch, k))
+        assert got.dtype == v.dtype and np.array_equal(got, v), k
+
+
+@pytest.mark.parametrize("threads,min_unclipped", [(1, 0.6), (4, 0.6), (3, 0.95)])
+def test_bam_decode_matches_packer(tmp_path, threads, min_unclipped):
+    contigs = [("chr1", 300_000), ("chr2", 200_000), ("chrUn_x", 50_000), ("chr3", 100_000)]
+    recs = {0: synth.synth_bam_records(1, 300_000, 30_000), 1: synth.synth_bam_records(2, 200_000, 12_345),
+            3: synth.synth_bam_records(3, 100_000, 1),      # chrUn_x stays empty
+            -1: synth.synth_bam_records(4, 1000, 17)}       # reads without a reference
+    path = synth.write_bam(str(tmp_path / "a.bam"), contigs, recs, sample="NA12878")
+    with bam.BamReader(path, threads=threads) as r:
+        assert r.references == [c[0] for c in contigs] and r.lengths == [c[1] for c in contigs]
+        assert r.sample_names() == ["NA12878"]
+        with pytest.raises(bam.BamError):
+            r.fetch(0)
+        r.decode(min_unclipped=min_unclipped, pinned=False)
+        st = r.stats()
+        n_all = sum(len(v["pos"]) for v in recs.values())
+        assert st["records"] == n_all and st["unplaced"] == len(recs[-1]["pos"])
+        assert st["uncompressed_bytes"] > st["compressed_bytes"] > 0 and st["decode_seconds"] > 0
+        for tid in (0, 1, 3):
+            _check(r.fetch(tid), _expected(recs[tid], min_unclipped))
+        assert len(r.fetch("chrUn_x")) == 0
+        regs = r.regions()  # default --contig-regex ^(chr)?\d\d?$ (cli.yaml:111): chrUn_x is left out
+        assert [g.name for g in regs] == ["chr1", "chr2", "chr3"] and regs[1].length == 200_000
+        # decoding again (other options) replaces the columns
+        r.decode(min_unclipped=0.0, pinned=False)
+        _check(r.fetch(1), _expected(recs[1], 0.0))
+
+
+def test_bam_small_blocks_and_odd_records(tmp_path):
+    """Records and the header straddle BGZF blocks (tiny blocks); unpaired, unmapped-placed and
+    clipped reads; CIGARs with every operator."""
+    pos = np.array([10, 10, 25, 40, 40, 77], np.int32)
+    cig, off = [], [0]
+    for ops in ([(50, 0)], [(5, 4), (20, 0), (3, 1), (22, 0)], [(10, 5), (30, 0), (1000, 3), (10, 7), (4, 8), (2, 2)],
+                [], [(60, 4), (40, 0)], [(3, 6), (50, 0)]):
+        cig += [(n << 4) | o for n, o in ops]
+        off.append(len(cig))
+    d = dict(pos=pos, isize=np.array([300, -300, 0, 0, 120, 5], np.int32),
+             flag=np.array([99, 147, 0, 4 | 1 | 8, 1 | 2 | 0x400, 16], np.uint16),
+             mapq=np.array([60, 0, 255, 0, 13, 37], np.uint8),
+             cigar_off=np.array(off, np.uint64), cigar=np.array(cig, np.uint32))
+    contigs = [("%d" % i, 1000 + i) for i in range(1, 41)]  # a header longer than one tiny block
+    path = synth.write_bam(str(tmp_path / "b.bam"), contigs, {4: d}, block_payload=97)
+    with bam.BamReader(path, threads=2) as r:
+        assert len(r.references) == 40 and r.lengths[39] == 1040
+        r.decode(min_unclipped=0.6, pinned=False)
+        _check(r.fetch(4), _expected(d, 0.6))
+        assert all(len(r.fetch(t)) == 0 for t in range(40) if t != 4)
+
+
+def test_bam_errors_are_loud(tmp_path):
+    with pytest.raises(bam.BamError, match="Could not open"):
+        bam.BamReader(str(tmp_path / "missing.bam"))
+    p = tmp_path / "text.bam"
+    p.write_bytes(b"not a bam file at all, just text that is long enough")
+    with pytest.raises(bam.BamError, match="BGZF"):
+        bam.BamReader(str(p))
+    good = synth.write_bam(str(tmp_path / "c.bam"), [("chr1", 100_000)], [synth.synth_bam_records(5, 100_000, 5000)])
+    raw = open(good, "rb").read()
+    cut = tmp_path / "cut.bam"
+    cut.write_bytes(raw[:len(raw) // 2])
+    with bam.BamReader(str(cut)) as r:
+        with pytest.raises(bam.BamError, match="truncated"):
+            r.decode(pinned=False)
+    flip = bytearray(raw)
+    flip[len(raw) // 2] ^= 0x55
+    bad = tmp_path / "flip.bam"
+    bad.write_bytes(bytes(flip))
+    with pytest.raises(bam.BamError, match="corrupt"):  # (a small file: found while reading the header)
+        with bam.BamReader(str(bad)) as r:
+            r.decode(pinned=False)
+
+
+@pytest.mark.gpu
+def test_coverage_from_bam_equals_arrays(tmp_path):
+    """`cmd coverage` fed from the file equals the run fed from the arrays (region loop, three kinds)."""
+    from cnvetti_b200 import pipeline
+    from util import soa_batch, to_np
+    ctx = cb.Context(0)
+    lens = (400_000, 250_000)
+    recs = [synth.synth_bam_records(21 + i, L, 20_000) for i, L in enumerate(lens)]
+    path = synth.write_bam(str(tmp_path / "d.bam"), [("chr1", lens[0]), ("chr2", lens[1])], recs)
+    for kind in ("Fragments", "Coverage"):
+        opts = cb.CoverageOptions(window_length=500, min_mapq=20, count_kind=kind)
+        with bam.BamReader(path) as r:
+            r.decode(min_unclipped=opts.min_unclipped, pinned=True)
+            t1 = pipeline.coverage_run(r.regions(), opts, ctx=ctx)
+            ref = [pipeline.Region("chr%d" % (i + 1), L, soa_batch(d)) for i, (L, d) in enumerate(zip(lens, recs))]
+            t2 = pipeline.coverage_run(ref, opts, ctx=ctx)
+            for col in ("start", "end", "rcv", "lcv", "ft"):
+                assert np.array_equal(to_np(getattr(t1, col)), to_np(getattr(t2, col))), (kind, col)
+            assert t1.num_processed == t2.num_processed
