@@ -166,6 +166,32 @@ def ncu_traffic(n_reads, launches_per_step):
     return None
 
 
+def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468):
+    """Host BAM decode, timed on its own (north_star: reported separately from device time): a synthetic
+    coordinate-sorted BAM of the config-1 read mix is written, then decoded by the library's BGZF/BAM
+    decoder (zlib on all host threads) into pinned SoA columns."""
+    import tempfile
+    from cnvetti_b200 import bam, synth
+    scale = n_pairs / 7_600_000.0
+    L = max(100_000, int(contig_len * scale))
+    d = synth.synth_bam_records(22, L, n_pairs)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d])
+        size = os.path.getsize(path)
+        best = None
+        with bam.BamReader(path) as r:
+            for _ in range(3):
+                r.decode(min_unclipped=0.6, pinned=True)
+                st = r.stats()
+                if best is None or st["decode_seconds"] < best["decode_seconds"]:
+                    best = st
+    return {"reads": best["records"], "file_bytes": size, "uncompressed_bytes": best["uncompressed_bytes"],
+            "seconds": best["decode_seconds"], "inflate_seconds": best["inflate_seconds"],
+            "parse_seconds": best["parse_seconds"], "reads_per_s": best["records"] / best["decode_seconds"],
+            "threads": os.cpu_count(), "what": "BGZF inflate (zlib, level-1 file) + record walk + SoA derivation into "
+                                               "pinned columns; best of 3; not part of value / e2e"}
+
+
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_leg(sample, steps, warmup):
     """Times the oracle (restated reference CPU path) on the sample: coverage (Fragments,
@@ -604,7 +630,8 @@ def bench_cfg1(args):
                          "achieved": cov["algorithmic_gbs"], "peak": peak, "unit": "GB/s", "frac": cov["algorithmic_gbs"] / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_read": 11,
                          "note": "whole region call, not a single kernel"},
-            "cpu_baseline": cpu, "clocks": clocks, "kinds": res}
+            "cpu_baseline": cpu, "clocks": clocks, "kinds": res,
+            "host_bam_decode": host_bam_decode_leg() if not args.quick else None}
     print(json.dumps(line))
     return 0
 
@@ -1033,6 +1060,7 @@ def main():
                 "host_memory": "pinned" if all_pinned else "pageable (pinning refused)"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "kernels": kern, "gen_seconds": gen_s,
+        "host_bam_decode": host_bam_decode_leg() if (rank == 0 and not args.quick) else None,
     }
     print(json.dumps(line))
     if distributed:

@@ -79,6 +79,26 @@ struct RefReads {
     }
 };
 
+struct RawBuf {  // byte buffer without value-initialisation (std::vector::resize would memset every chunk)
+    uint8_t *p = nullptr;
+    uint64_t n = 0, cap = 0;
+    bool resize(uint64_t want, bool keep) {
+        if (want > cap) {
+            const uint64_t ncap = std::max<uint64_t>(want, cap + cap / 2);
+            uint8_t *q = static_cast<uint8_t *>(keep ? realloc(p, ncap) : malloc(ncap));
+            if (!q) return false;
+            if (!keep) free(p);
+            p = q;
+            cap = ncap;
+        }
+        n = want;
+        return true;
+    }
+    uint8_t *data() { return p; }
+    uint64_t size() const { return n; }
+    ~RawBuf() { free(p); }
+};
+
 struct Block {  // one BGZF block inside the file image
     uint64_t off;     // start of the deflate stream
     uint32_t clen;    // compressed payload length
@@ -143,6 +163,7 @@ struct cnvb_bam {
     uint64_t n_records = 0, n_unplaced = 0, bytes_compressed = 0, bytes_uncompressed = 0;
     double t_inflate = 0.0, t_parse = 0.0, t_total = 0.0;
     bool decoded = false;
+    RawBuf cbuf, ubuf;  // chunk buffers, kept across chunks and calls (no page faults after the first chunk)
     ~cnvb_bam() {
         for (auto &r : refs) r.release();
     }
@@ -167,7 +188,8 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
     FILE *f = fopen(b->path.c_str(), "rb");
     if (!f) return bam_fail(b, CNVB_ERR_INVALID, "Could not open BAM file %s", b->path.c_str());
     const uint64_t kChunkBytes = header_only ? (1ull << 20) : (64ull << 20);  // compressed bytes per chunk
-    std::vector<uint8_t> cbuf, ubuf, carry;
+    RawBuf &cbuf = b->cbuf, &ubuf = b->ubuf;
+    std::vector<uint8_t> carry;
     std::vector<Block> blocks;
     std::vector<uint64_t> rec_off;
     bool header_done = false, eof = false;
@@ -181,11 +203,14 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
     int rc = CNVB_OK;
     while (!eof && rc == CNVB_OK) {
         // ---- read compressed bytes, cut into whole blocks
-        cbuf.assign(left.begin(), left.end());
-        const uint64_t have = cbuf.size();
-        cbuf.resize(have + kChunkBytes);
+        const uint64_t have = left.size();
+        if (!cbuf.resize(have + kChunkBytes, false)) {
+            rc = bam_fail(b, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
+            break;
+        }
+        if (have) memcpy(cbuf.data(), left.data(), have);
         const size_t got = fread(cbuf.data() + have, 1, kChunkBytes, f);
-        cbuf.resize(have + got);
+        cbuf.n = have + got;
         file_pos += got;
         if (got == 0) eof = true;
         blocks.clear();
@@ -222,7 +247,7 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             p += bsize;
         }
         if (rc != CNVB_OK) break;
-        left.assign(cbuf.begin() + p, cbuf.end());
+        left.assign(cbuf.data() + p, cbuf.data() + cbuf.size());
         if (eof && !left.empty()) {
             rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BGZF block at the end of the file", b->path.c_str());
             break;
@@ -232,7 +257,10 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
         // ---- inflate the blocks of the chunk in parallel, behind the carried-over partial record
         const auto t0 = clk::now();
         const uint64_t c0 = carry.size();
-        ubuf.resize(c0 + utotal);
+        if (!ubuf.resize(c0 + utotal, false)) {
+            rc = bam_fail(b, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
+            break;
+        }
         if (c0) memcpy(ubuf.data(), carry.data(), c0);
         std::atomic<int> bad{0};
         run_parallel(b->n_threads, blocks.size(), [&](uint64_t lo, uint64_t hi, int) {
@@ -305,7 +333,7 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
                     rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BAM header", b->path.c_str());
                     break;
                 }
-                carry.assign(ubuf.begin(), ubuf.end());
+                carry.assign(ubuf.data(), ubuf.data() + ubuf.size());
                 continue;
             }
             header_done = true;
@@ -382,7 +410,7 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             i = j;
         }
         b->n_records += nr;
-        carry.assign(ubuf.begin() + q, ubuf.end());
+        carry.assign(ubuf.data() + q, ubuf.data() + ubuf.size());
         b->t_parse += std::chrono::duration<double>(clk::now() - t1).count();
     }
     fclose(f);
