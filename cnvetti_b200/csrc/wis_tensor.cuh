@@ -90,10 +90,33 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same load delivered to every CTA of `mask` (same CTA-relative offsets, each CTA's own barrier)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+        "%4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the barrier at the same offset in every CTA of `mask` when the MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -379,16 +402,32 @@ struct SweepArgs {
 // both operands stream through kStreamStages stages of (A rows 0..127 | A rows 128..255 | B) K-blocks.
 constexpr uint32_t kStreamStages = 4;  // x 48 KB
 
-template <bool FIRST, bool STREAM>
+// CLUSTER (with STREAM): two CTAs of a cluster share one block of 256 rows and take its column tiles in
+// turn.  The streamed sweep is bound by L2 -> SM traffic (48 KB of operands per 256 x 128 x 64 MMA block =
+// 87 flop/B against ~6300 B/clk of L2 bandwidth: measured 3.6-3.7 kflop/clk/SM, 45 % of the tensor
+// peak); with the A K-block of the shared rows fetched once per pair -- each CTA loads one half and
+// TMA-multicasts it into both shared memories -- a CTA moves 32 KB per block (131 flop/B).  A stage is
+// refilled when BOTH consumers are done with it: the MMA issuers commit to the stage's empty barrier in
+// both CTAs (multicast commit), which therefore counts two arrivals.  Candidate slots come from the
+// global per-row counter (two CTAs append to the same rows).
+template <bool FIRST, bool STREAM, bool CLUSTER>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
+    static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
+    const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
+    const uint32_t blk = CLUSTER ? blockIdx.x >> 1 : blockIdx.x;
     // this block's share of the round: two tile ranges either side of what it has swept before
-    const uint4 rng = a.rng[blockIdx.x];
-    const uint32_t n_lo = rng.y - rng.x, n_tiles = n_lo + (rng.w - rng.z);
-    if (n_tiles == 0) return;
+    const uint4 rng = a.rng[blk];
+    const uint32_t n_lo = rng.y - rng.x, n_all = n_lo + (rng.w - rng.z);
+    if (n_all == 0) return;  // (both CTAs of a cluster)
+    // CLUSTER: tile i of this CTA is tile 2 i + rank of the block; both CTAs make `steps` passes through the
+    // operand ring (the second one without a tile of its own in the last pass when the count is odd)
+    const uint32_t n_tiles = CLUSTER ? (n_all + 1u - crank) >> 1 : n_all;
+    const uint32_t steps = CLUSTER ? (n_all + 1u) >> 1 : n_all;
     const uint32_t rng_x = rng.x, rng_z = rng.z;
-#define CNVB_TILE_AT(it) ((it) < n_lo ? rng_x + (it) : rng_z + ((it) - n_lo))
+#define CNVB_TILE_G(g) ((g) < n_lo ? rng_x + (g) : rng_z + ((g) - n_lo))
+#define CNVB_TILE_AT(it) CNVB_TILE_G(CLUSTER ? 2u * (it) + crank : (it))
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
@@ -403,15 +442,16 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t bar_acc_empty = bar_acc_full + 16;         // 2
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t row0 = blockIdx.x * kTileRows;  // position in the sorted row list
-    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
-        s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
+    const uint32_t row0 = blk * kTileRows;  // position in the sorted row list
+    if (!CLUSTER)
+        for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
+            s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
         for (uint32_t s = 0; s < kStages; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
-            mbar_init(bar_b_empty + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, CLUSTER ? 2 : 1);  // CLUSTER: both CTAs' MMAs release a stage
         }
         for (uint32_t s = 0; s < 2; ++s) {
             mbar_init(bar_acc_full + 8 * s, 1);
@@ -426,6 +466,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -442,16 +483,22 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             constexpr uint32_t n_stages = STREAM ? kStreamStages : kStages;
             uint32_t st = 0, ph = 0;
-            for (uint32_t it = 0; it < n_tiles; ++it) {
-                const int32_t j0 = (int32_t)(CNVB_TILE_AT(it) * kTileCols);
+            for (uint32_t it = 0; it < steps; ++it) {
+                const bool have = it < n_tiles;  // (CLUSTER: the last pass may only serve the peer)
+                const int32_t j0 = have ? (int32_t)(CNVB_TILE_AT(it) * kTileCols) : 0;
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                     mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
                     if (STREAM) {
                         const uint32_t sb = a_base + st * 3u * kTileBytes;
-                        mbar_expect_tx(bar_b_full + 8 * st, 3u * kTileBytes);
-                        tma_load_2d(sb, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)row0);
-                        tma_load_2d(sb + kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)(row0 + 128));
-                        tma_load_2d(sb + 2u * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                        mbar_expect_tx(bar_b_full + 8 * st, (have ? 3u : 2u) * kTileBytes);
+                        if (CLUSTER) {  // this CTA's half of the rows, into both CTAs
+                            tma_load_2d_mc(sb + crank * kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock),
+                                           (int32_t)(row0 + crank * 128u), (uint16_t)3);
+                        } else {
+                            tma_load_2d(sb, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)row0);
+                            tma_load_2d(sb + kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)(row0 + 128));
+                        }
+                        if (have) tma_load_2d(sb + 2u * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
                     } else {
                         mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
                         tma_load_2d(b_base + st * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
@@ -480,25 +527,31 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) adesc[h][kb] = umma_desc(a_base + (h * kMaxKBlocks + kb) * kTileBytes);
             const uint64_t bdesc0 = umma_desc(b_base), sdesc0 = umma_desc(a_base);
-            for (uint32_t it = 0; it < n_tiles; ++it) {
-                mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
-                tc_fence_after();
+            for (uint32_t it = 0; it < steps; ++it) {
+                const bool have = it < n_tiles;
+                if (have) {
+                    mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
+                    tc_fence_after();
+                }
                 if (STREAM) {
                     for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                         mbar_wait(bar_b_full + 8 * st, ph);
                         tc_fence_after();
                         const uint64_t sd = sdesc0 + (uint64_t)(st * (3u * kTileBytes >> 4));
+                        if (have) {
 #pragma unroll
-                        for (uint32_t h = 0; h < 2; ++h) {
-                            const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
 #pragma unroll
-                            for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                                if (kb * (kKBlock / 16) + kk < a.k_mmas)
-                                    tc_mma_f16(d_tmem, sd + (uint64_t)(h * (kTileBytes >> 4)) + 2u * kk,
-                                               sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, kIdesc, (kb | kk) != 0u);
+                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                                    if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                        tc_mma_f16(d_tmem, sd + (uint64_t)(h * (kTileBytes >> 4)) + 2u * kk,
+                                                   sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, kIdesc, (kb | kk) != 0u);
+                                }
                             }
                         }
-                        tc_commit(bar_b_empty + 8 * st);
+                        // frees the stage (in both CTAs: the peer's producer writes into this one's too)
+                        if (CLUSTER) tc_commit_mc(bar_b_empty + 8 * st, (uint16_t)3); else tc_commit(bar_b_empty + 8 * st);
                         if (++st == n_stages) {
                             st = 0;
                             ph ^= 1u;
@@ -528,10 +581,12 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                 }
-                tc_commit(bar_acc_full + 8 * as);  // accumulators of this tile complete
-                if (++as == 2) {
-                    as = 0;
-                    aph ^= 1u;
+                if (have) {
+                    tc_commit(bar_acc_full + 8 * as);  // accumulators of this tile complete
+                    if (++as == 2) {
+                        as = 0;
+                        aph ^= 1u;
+                    }
                 }
             }
         }
@@ -646,7 +701,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int c = 0; c < 32; ++c) {
                             const float v = CNVB_VAL(c);
                             if (v <= top[7] && tj[c] != trow[h]) {
-                                const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);
+                                const uint32_t slot = CLUSTER ? atomicAdd(&a.cand_cnt[row], 1u) : atomicAdd(&s_cnt[rloc[h]], 1u);
                                 if (slot < kCandCap) {
                                     cv[slot] = v;
                                     ci[slot] = j0 + c;
@@ -683,7 +738,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const float v = CNVB_VAL(c);
                                 const uint32_t j = j0 + c;
                                 if (v <= rhs && j < a.T) {  // (same-contig pairs are dropped by the compaction)
-                                    const uint32_t slot = atomicAdd(&s_cnt[rloc[h]], 1u);  // 4 warps share a row
+                                    const uint32_t slot =  // 4 warps (CLUSTER: of two CTAs) share a row
+                                        CLUSTER ? atomicAdd(&a.cand_cnt[row], 1u) : atomicAdd(&s_cnt[rloc[h]], 1u);
                                     if (slot < kCandCap) {  // beyond: overflow, the row falls back
                                         cv[slot] = v;
                                         ci[slot] = j;
@@ -705,8 +761,10 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
-        if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
+    if (!CLUSTER)
+        for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
+            if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
+    if (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still send to it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -714,6 +772,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 #undef CNVB_TILE_AT
+#undef CNVB_TILE_G
 #undef CNVB_VAL
 
 // ---- windows: which column tiles a block of rows still has to see --------------------------------
@@ -1251,8 +1310,16 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
-    auto sweep_first = stream_a ? wis_sweep_kernel<true, true> : wis_sweep_kernel<true, false>;
-    auto sweep_next = stream_a ? wis_sweep_kernel<false, true> : wis_sweep_kernel<false, false>;
+    // streamed sweep: CTA pairs share their rows' operand through TMA multicast (CNVB_WIS_CLUSTER=0: one CTA per block)
+    static const bool use_cluster = [] {
+        const char *e = getenv("CNVB_WIS_CLUSTER");
+        return !(e && atoi(e) == 0);
+    }();
+    const bool cluster = stream_a && use_cluster;
+    auto sweep_first = cluster ? wis_sweep_kernel<true, true, true>
+                               : (stream_a ? wis_sweep_kernel<true, true, false> : wis_sweep_kernel<true, false, false>);
+    auto sweep_next = cluster ? wis_sweep_kernel<false, true, true>
+                              : (stream_a ? wis_sweep_kernel<false, true, false> : wis_sweep_kernel<false, false, false>);
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     BoundConsts bc{};
@@ -1284,6 +1351,21 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.cand_val = cand_val;
     sa.cand_idx = cand_idx;
     sa.cand_cnt = cand_cnt;
+    auto launch_sweep = [&](decltype(sweep_first) kern) -> cudaError_t {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cluster ? 2 * row_blocks : row_blocks);
+        cfg.blockDim = dim3(kSweepThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, sa);
+    };
     CompactArgs ca{};
     ca.cand_val = cand_val;
     ca.cand_idx = cand_idx;
@@ -1326,7 +1408,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (32 * tiles0 >= 5 * k / 4) {
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
-            sweep_first<<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+            CNVB_CUDA(ctx, launch_sweep(sweep_first), "launching the first sweep");
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         ca.discard = 1;
@@ -1353,7 +1435,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         tiles_before = tiles_now;
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
-            sweep_next<<<row_blocks, kSweepThreads, smem, st>>>(tmap_a, tmap_b, sa);
+            CNVB_CUDA(ctx, launch_sweep(sweep_next), "launching the sweep");
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         {
