@@ -430,6 +430,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #define CNVB_TILE_AT(it) CNVB_TILE_G(CLUSTER ? 2u * (it) + crank : (it))
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
+    __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -616,7 +617,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t j0 = tile * kTileCols + cpart * 32u;
             // column operands of this warp's 32 columns (same addresses for all lanes: L1 broadcast)
             float nj[32];
-            {
+            if (!STREAM) {
                 const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0);
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
@@ -626,6 +627,14 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     nj[4 * g4 + 2] = v.z;
                     nj[4 * g4 + 3] = v.w;
                 }
+            } else {
+                // ortho mode needs two operands per column; 64 registers for them beside the 32 accumulator
+                // values would spill.  Each lane fetches one column's pair (two coalesced 128-byte loads, before
+                // the accumulator wait) into the warp's own shared-memory strip, and the values come back four
+                // at a time as broadcast LDS.128 while the accumulators are consumed.
+                s_col[e][lane] = __ldg(a.nprime + j0 + lane);
+                s_col[e][32 + lane] = __ldg(a.psorted + j0 + lane);
+                __syncwarp();
             }
             const float smax = __ldg(a.tile_smax + tile);
             if (it + 1 < n_tiles) {  // the next tile's column operands: in L1 by the time they are needed
@@ -656,20 +665,17 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     // ortho mode: r[c] <- n'_j - 2 g + (q_j - q_i)^2.  The difference is rounded towards zero
                     // and the FMA down, so the value never exceeds the exact one: a column that passes the
                     // exact test passes this one, and the stored value is a lower bound (the compaction
-                    // inflates it for the upper bound).  The projections are loaded after n'_j has been
-                    // consumed, into the same registers.
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaf(-2.0f, __uint_as_float(r[c]), nj[c]));
-                    const float4 *pj4 = reinterpret_cast<const float4 *>(a.psorted + j0);
+                    // inflates it for the upper bound).
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 pv = __ldg(pj4 + g4);
+                        const float4 nv = *reinterpret_cast<const float4 *>(&s_col[e][4 * g4]);
+                        const float4 pv = *reinterpret_cast<const float4 *>(&s_col[e][32 + 4 * g4]);
                         const float d0 = __fsub_rz(pv.x, qrow[h]), d1 = __fsub_rz(pv.y, qrow[h]);
                         const float d2 = __fsub_rz(pv.z, qrow[h]), d3 = __fsub_rz(pv.w, qrow[h]);
-                        r[4 * g4 + 0] = __float_as_uint(__fmaf_rd(d0, d0, __uint_as_float(r[4 * g4 + 0])));
-                        r[4 * g4 + 1] = __float_as_uint(__fmaf_rd(d1, d1, __uint_as_float(r[4 * g4 + 1])));
-                        r[4 * g4 + 2] = __float_as_uint(__fmaf_rd(d2, d2, __uint_as_float(r[4 * g4 + 2])));
-                        r[4 * g4 + 3] = __float_as_uint(__fmaf_rd(d3, d3, __uint_as_float(r[4 * g4 + 3])));
+                        r[4 * g4 + 0] = __float_as_uint(__fmaf_rd(d0, d0, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nv.x)));
+                        r[4 * g4 + 1] = __float_as_uint(__fmaf_rd(d1, d1, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nv.y)));
+                        r[4 * g4 + 2] = __float_as_uint(__fmaf_rd(d2, d2, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nv.z)));
+                        r[4 * g4 + 3] = __float_as_uint(__fmaf_rd(d3, d3, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nv.w)));
                     }
                 }
                 // the value of column c under test: already formed in ortho mode
