@@ -60,6 +60,9 @@ struct cnvb_ctx {
 namespace cnvb {
 
 int refstats_prepare(cnvb_ctx *ctx);  // refstats.cu: builds the classification table on ctx->stream if missing
+// refstats.cu: reference statistics of all regions in one launch; 1 = not applicable (go region by region)
+int refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const *seq, const uint64_t *len, const uint64_t *out_off,
+                          uint32_t window_length, float *gc, uint8_t *has_gap, bool shares_sms);
 
 // error chain in the style of error-chain's "error: ... / caused by: ..." (cnvetti/src/main.rs)
 inline int fail(cnvb_ctx *ctx, int code, const char *fmt, ...) {

@@ -61,11 +61,35 @@ __global__ void refstats_build_lut_kernel(uint16_t *__restrict__ lut) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 65536u) lut[lut_index(i)] = (uint16_t)(ref_class(i & 0xffu) + ref_class(i >> 8));
 }
+// 128 KB per CTA and launch: one thread issues four 32 KB bulk async copies (TMA engine, L2 -> shared memory)
+// and the CTA waits on their mbarrier -- 1024 threads fetching 8 x 16 bytes each took ~8 us of exposed
+// latency per launch, a fifth of the 22-launch step.
 __device__ __forceinline__ void load_lut(uint16_t *s_lut, const uint16_t *__restrict__ lut) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(lut);
-    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-    for (uint32_t i = threadIdx.x; i < 65536u * 2u / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
-    __syncthreads();
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_lut);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(65536u * 2u) : "memory");
+#pragma unroll
+        for (uint32_t part = 0; part < 4; ++part)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst + part * 32768u),
+                         "l"(reinterpret_cast<const char *>(lut) + part * 32768u), "r"(32768u), "r"(bar)
+                         : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar)
+            : "memory");
+    } while (!ok);
 }
 
 // Lane-group variant (wl >= 128): G lanes own one window and walk its interior 16-byte chunks in turn,
@@ -89,6 +113,52 @@ __device__ __forceinline__ uint32_t lut_counts(const uint16_t *s_lut, const uint
 
 constexpr int kInFlight = 4;  // 16-byte loads per lane in flight (8 measured the same)
 
+// counts of one window for lane `sub` of its group: interior chunks in turn, lanes 0 / 1 also an edge chunk
+template <int G>
+__device__ __forceinline__ void ref_window_counts(const uint16_t *s_lut, const int4 *__restrict__ base4, uint32_t os,
+                                                  uint32_t oe, uint32_t sub, uint32_t &g, uint32_t &c, uint32_t &n) {
+    const uint32_t cf = os >> 4, cl = (oe - 1u) >> 4;
+    // edge chunks: issued first, consumed last
+    const uint32_t ek = sub == 0 ? cf : cl;
+    const bool has_edge = sub == 0 || (sub == 1 && cl != cf);
+    int4 edge = make_int4(0, 0, 0, 0);
+    if (has_edge) edge = __ldg(base4 + ek);
+    // the G lanes take the interior chunks of the window in turn (together they read G x 16 contiguous
+    // bytes); kInFlight loads per lane are in flight before the first is consumed -- with one, the 1024
+    // threads of an SM keep only 16 KB in flight, less than half of what HBM latency needs
+    for (uint32_t k = cf + 1u + sub; k < cl; k += kInFlight * G) {
+        int4 raw[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const uint32_t kk = k + u * G;
+            raw[u] = kk < cl ? __ldg(base4 + kk) : make_int4(0, 0, 0, 0);  // (0x00 is in no class)
+        }
+        uint32_t acc = 0;  // packed 7-bit fields: kInFlight x 16 <= 127
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const uint32_t w[4] = {(uint32_t)raw[u].x, (uint32_t)raw[u].y, (uint32_t)raw[u].z, (uint32_t)raw[u].w};
+            acc += lut_counts(s_lut, w);
+        }
+        g += acc & 127u;
+        c += (acc >> 7) & 127u;
+        n += acc >> 14;
+    }
+    if (has_edge) {  // zero the bytes of the neighbouring windows
+        uint32_t w[4] = {(uint32_t)edge.x, (uint32_t)edge.y, (uint32_t)edge.z, (uint32_t)edge.w};
+        const uint32_t c0 = ek << 4;
+        const int lo = os > c0 ? (int)(os - c0) : 0, hi = oe < c0 + 16u ? (int)(oe - c0) : 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = min(max(lo - 4 * j, 0), 4), y = min(max(hi - 4 * j, 0), 4);
+            w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
+        }
+        const uint32_t acc = lut_counts(s_lut, w);
+        g += acc & 127u;
+        c += (acc >> 7) & 127u;
+        n += acc >> 14;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint32_t num_bins,
                                                                 const uint16_t *__restrict__ lut,
@@ -108,47 +178,7 @@ __global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint3
         uint32_t g = 0, c = 0, n = 0;
         if (W < num_bins) {
             const uint32_t os = W * wl + mis, oe = min(os + wl, end_off);
-            const uint32_t cf = os >> 4, cl = (oe - 1u) >> 4;
-            // edge chunks: issued first, consumed last
-            const uint32_t ek = sub == 0 ? cf : cl;
-            const bool has_edge = sub == 0 || (sub == 1 && cl != cf);
-            int4 edge = make_int4(0, 0, 0, 0);
-            if (has_edge) edge = __ldg(base4 + ek);
-            // the G lanes take the interior chunks of the window in turn (together they read G x 16
-            // contiguous bytes); kInFlight loads per lane are in flight before the first is consumed --
-            // with one, the 1024 threads of an SM keep only 16 KB in flight, less than half of what HBM
-            // latency needs
-            for (uint32_t k = cf + 1u + sub; k < cl; k += kInFlight * G) {
-                int4 raw[kInFlight];
-#pragma unroll
-                for (int u = 0; u < kInFlight; ++u) {
-                    const uint32_t kk = k + u * G;
-                    raw[u] = kk < cl ? __ldg(base4 + kk) : make_int4(0, 0, 0, 0);  // (0x00 is in no class)
-                }
-                uint32_t acc = 0;  // packed 7-bit fields: kInFlight x 16 <= 127
-#pragma unroll
-                for (int u = 0; u < kInFlight; ++u) {
-                    const uint32_t w[4] = {(uint32_t)raw[u].x, (uint32_t)raw[u].y, (uint32_t)raw[u].z, (uint32_t)raw[u].w};
-                    acc += lut_counts(s_lut, w);
-                }
-                g += acc & 127u;
-                c += (acc >> 7) & 127u;
-                n += acc >> 14;
-            }
-            if (has_edge) {  // zero the bytes of the neighbouring windows
-                uint32_t w[4] = {(uint32_t)edge.x, (uint32_t)edge.y, (uint32_t)edge.z, (uint32_t)edge.w};
-                const uint32_t c0 = ek << 4;
-                const int lo = os > c0 ? (int)(os - c0) : 0, hi = oe < c0 + 16u ? (int)(oe - c0) : 16;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int x = min(max(lo - 4 * j, 0), 4), y = min(max(hi - 4 * j, 0), 4);
-                    w[j] &= byte_mask_below(y) & ~byte_mask_below(x);
-                }
-                const uint32_t acc = lut_counts(s_lut, w);
-                g += acc & 127u;
-                c += (acc >> 7) & 127u;
-                n += acc >> 14;
-            }
+            ref_window_counts<G>(s_lut, base4, os, oe, sub, g, c, n);
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
@@ -157,6 +187,60 @@ __global__ void __launch_bounds__(1024, 1) refstats_lane_kernel(RefArgs a, uint3
             n += __shfl_xor_sync(0xffffffffu, n, o);
         }
         if (W < num_bins && sub == 0) ref_store(gc, has_gap, W, g, c, n);
+    }
+}
+
+// The same for all regions of a run in ONE launch.  A launch of this kernel costs ~12 us before the first
+// byte is counted (1024-thread CTAs with 128 KB of shared memory: the SMs switch their L1 / shared-memory
+// split against the binning kernels'), which over the 22 contig launches of a genome was a third of the
+// reference-statistics time.  Windows are numbered through all regions; a lane group finds its region by
+// binary search in a shared-memory copy of the region table.
+struct RefRegion {
+    const uint8_t *seq;
+    uint32_t len;
+    uint32_t first;    // number of windows in the regions before this one
+    uint64_t out_off;  // row of the region's first window in the output columns
+};
+constexpr uint32_t kMaxBatchRegions = 512;
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1) refstats_batch_kernel(const RefRegion *__restrict__ regs, uint32_t n_regs,
+                                                                 uint32_t wl, uint32_t total_bins,
+                                                                 const uint16_t *__restrict__ lut, float *__restrict__ gc,
+                                                                 uint8_t *__restrict__ has_gap) {
+    extern __shared__ __align__(16) uint16_t s_lut[];  // [65536]
+    __shared__ RefRegion s_regs[kMaxBatchRegions];
+    for (uint32_t i = threadIdx.x; i < n_regs; i += blockDim.x) s_regs[i] = regs[i];
+    load_lut(s_lut, lut);  // (its __syncthreads covers the region table too)
+    const uint32_t lane = lane_id(), sub = lane % G;
+    const uint32_t n_groups = gridDim.x * (blockDim.x / G);
+    const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t warp_first = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / G;
+    for (uint32_t W0 = warp_first, W = first; W0 < total_bins; W0 += n_groups, W += n_groups) {
+        uint32_t g = 0, c = 0, n = 0;
+        uint64_t out = 0;
+        if (W < total_bins) {
+            uint32_t lo = 0, hi = n_regs;  // last region with first <= W
+            while (hi - lo > 1u) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_regs[mid].first <= W) lo = mid; else hi = mid;
+            }
+            const RefRegion r = s_regs[lo];
+            const uint32_t Wl = W - r.first;
+            out = r.out_off + Wl;
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(r.seq);
+            const uint32_t mis = (uint32_t)(addr & 15u);
+            const int4 *__restrict__ base4 = reinterpret_cast<const int4 *>(addr - mis);
+            const uint32_t os = Wl * wl + mis, oe = min(os + wl, r.len + mis);
+            ref_window_counts<G>(s_lut, base4, os, oe, sub, g, c, n);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+        }
+        if (W < total_bins && sub == 0) ref_store(gc, has_gap, out, g, c, n);
     }
 }
 
@@ -320,4 +404,76 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
         CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "refstats");
     }
     return CNVB_OK;
+}
+
+
+// All regions of a run in one launch (device-resident sequences; window length >= 128, each region below
+// 4 GB).  out_off[i] = row of region i's first window in gc / has_gap.  Returns 1 if the batch form does
+// not apply (the caller then goes region by region), 0 on success, a negative error otherwise.
+int cnvb::refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const *seq, const uint64_t *len,
+                                const uint64_t *out_off, uint32_t window_length, float *gc, uint8_t *has_gap,
+                                bool shares_sms) {
+    if (n == 0) return 0;
+    if (window_length < 128 || n > kMaxBatchRegions) return 1;
+    std::vector<RefRegion> regs(n);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (len[i] >= 0xFFFFFF00ull) return 1;
+        regs[i].seq = seq[i];
+        regs[i].len = (uint32_t)len[i];
+        regs[i].first = (uint32_t)total;
+        regs[i].out_off = out_off[i];
+        total += (len[i] + window_length - 1) / window_length;
+    }
+    if (total == 0) return 0;
+    if (total >= 0xFFFFFF00ull) return 1;
+    CNVB_TRY(refstats_prepare(ctx));
+    RefRegion *d_regs = nullptr;
+    cudaError_t e = pool_alloc_t(ctx, (size_t)n, &d_regs);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "allocating the region table");
+    // (pageable source: the copy is staged by the runtime before the call returns, so `regs` may go)
+    e = cudaMemcpyAsync(d_regs, regs.data(), n * sizeof(RefRegion), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        pool_release(ctx, d_regs);
+        return fail_cuda(ctx, e, "uploading the region table");
+    }
+    const size_t smem = 65536 * sizeof(uint16_t);
+    int GL = 2;
+    while (GL < 32 && total * (uint64_t)GL < (uint64_t)ctx->sm_count * 1024 && (uint64_t)window_length / (2 * GL) >= 32) GL <<= 1;
+    // Threads per CTA (one CTA per SM: the table takes 128 KB).  Alone, 1024 threads are fastest (0.60 ms per
+    // config-2 step against 0.70 with 512).  Beside the binning kernel (the region loop's side streams), 1024
+    // threads x 56 registers leave no room for a binning CTA on the SM and the two kernels merely take
+    // turns; with 512 two binning CTAs fit and the ALU-bound table lookups run under the HBM-bound binning:
+    // 1.82 -> 1.72 ms per step (768: 1.79, 256: 1.81).  CNVB_REF_THREADS overrides.
+    static const unsigned ref_threads_env = [] {
+        const char *e = getenv("CNVB_REF_THREADS");
+        const int v = e ? atoi(e) : 0;
+        return v == 256 || v == 512 || v == 768 || v == 1024 ? (unsigned)v : 0u;
+    }();
+    const unsigned ref_threads = ref_threads_env ? ref_threads_env : (shares_sms ? 512u : 1024u);
+    uint64_t blocks = (total * GL + ref_threads - 1) / ref_threads;
+    if (blocks > (uint64_t)ctx->sm_count) blocks = ctx->sm_count;
+    const uint16_t *d_lut = static_cast<const uint16_t *>(ctx->ref_lut);
+    {
+        KernelSpan span(ctx, "refstats_lut_kernel");
+#define CNVB_REF_BATCH(GG)                                                                                             \
+    case GG:                                                                                                           \
+        e = cudaFuncSetAttribute(refstats_batch_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e == cudaSuccess)                                                                                          \
+            refstats_batch_kernel<GG><<<(unsigned)blocks, ref_threads, smem, ctx->stream>>>(d_regs, n, window_length,   \
+                                                                                     (uint32_t)total, d_lut, gc, has_gap); \
+        break;
+        switch (GL) {
+            CNVB_REF_BATCH(2)
+            CNVB_REF_BATCH(4)
+            CNVB_REF_BATCH(8)
+            CNVB_REF_BATCH(16)
+            CNVB_REF_BATCH(32)
+        }
+#undef CNVB_REF_BATCH
+    }
+    pool_release(ctx, d_regs);  // stream-ordered reuse
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "smem opt-in");
+    CNVB_LAUNCHED(ctx, "refstats_lut_kernel");
+    return 0;
 }

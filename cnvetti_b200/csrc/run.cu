@@ -138,13 +138,47 @@ extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int k
         cudaStream_t s;
         ~StreamGuard() { c->stream = s; }
     } stream_guard{ctx, main_stream};
+    // lib.rs:440-454 for all regions at once when every sequence is in device memory: one launch instead of
+    // one per region (each costs ~12 us before its first byte; refstats.cu).  It runs on the third side
+    // stream beside the binning of the first regions.
+    bool ref_batched = false;
+    if (d.gc && d.gap && opts->window_length) {
+        std::vector<const uint8_t *> bs;
+        std::vector<uint64_t> bl, bo;
+        bool all_dev = true;
+        uint64_t o = 0;
+        for (uint32_t i = 0; i < n_regions; ++i) {
+            const cnvb_region *r = &regions[i];
+            const uint64_t rows = rows_of(opts, kind, r);
+            if (r->seq) {
+                const uint64_t wl = opts->window_length;
+                if (r->seq_mem != CNVB_MEM_DEVICE || (r->seq_len + wl - 1) / wl != rows) all_dev = false;
+                bs.push_back(r->seq);
+                bl.push_back(r->seq_len);
+                bo.push_back(o);
+            }
+            o += rows;
+        }
+        static const bool batch_on = [] {
+            const char *e = getenv("CNVB_REF_BATCH");
+            return !(e && atoi(e) == 0);
+        }();
+        if (all_dev && bs.size() > 1 && batch_on) {
+            if (fan) ctx->stream = ctx->side[2];
+            const int rc = refstats_batch_device(ctx, (uint32_t)bs.size(), bs.data(), bl.data(), bo.data(),
+                                                 opts->window_length, d.gc, d.gap, fan);
+            ctx->stream = main_stream;
+            if (rc < 0) return cleanup(rc);
+            ref_batched = rc == 0;
+        }
+    }
     uint64_t off = 0;
     for (uint32_t i = 0; i < n_regions; ++i) {
         const cnvb_region *r = &regions[i];
         const uint64_t rows = rows_of(opts, kind, r);
-        if (fan) ctx->stream = ctx->side[i % 3];
+        if (fan) ctx->stream = ctx->side[ref_batched ? i % 2 : i % 3];
         // lib.rs:440-454: GC content and gap flag per window from the contig bytes
-        if (r->seq && (d.gc || d.gap)) {
+        if (r->seq && (d.gc || d.gap) && !ref_batched) {
             if (!d.gc || !d.gap)
                 return cleanup(fail(ctx, CNVB_ERR_INVALID, "GC and GAP columns come together"));
             const uint64_t wl = opts->window_length;
