@@ -187,7 +187,11 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
     const auto t_begin = clk::now();
     FILE *f = fopen(b->path.c_str(), "rb");
     if (!f) return bam_fail(b, CNVB_ERR_INVALID, "Could not open BAM file %s", b->path.c_str());
-    const uint64_t kChunkBytes = header_only ? (1ull << 20) : (64ull << 20);  // compressed bytes per chunk
+    uint64_t kChunkBytes = header_only ? (1ull << 20) : (64ull << 20);  // compressed bytes per chunk
+    if (const char *e = getenv("CNVB_BAM_CHUNK")) {  // (tests: small chunks exercise the chunk seams)
+        const long v = atol(e);
+        if (v >= 64) kChunkBytes = (uint64_t)v;
+    }
     RawBuf &cbuf = b->cbuf, &ubuf = b->ubuf;
     std::vector<uint8_t> carry;
     std::vector<Block> blocks;

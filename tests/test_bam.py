@@ -71,6 +71,26 @@ def test_bam_small_blocks_and_odd_records(tmp_path):
         assert all(len(r.fetch(t)) == 0 for t in range(40) if t != 4)
 
 
+def test_bam_chunk_seams(tmp_path, monkeypatch):
+    """The decoder reads the file in chunks of compressed bytes: BGZF blocks cut by a chunk end are
+    completed by the next read, records cut by the end of a chunk's last block are carried over, and
+    the header may span chunks.  Tiny chunks put a seam every few blocks."""
+    contigs = [("chr%d" % i, 150_000) for i in range(1, 30)]  # a 700-byte header
+    recs = {0: synth.synth_bam_records(11, 150_000, 4000), 7: synth.synth_bam_records(12, 150_000, 2500),
+            28: synth.synth_bam_records(13, 150_000, 1)}
+    path = synth.write_bam(str(tmp_path / "seams.bam"), contigs, recs, block_payload=1500)
+    expected = {t: _expected(d, 0.6) for t, d in recs.items()}
+    for chunk in ("64", "333", "5000", "70001"):
+        monkeypatch.setenv("CNVB_BAM_CHUNK", chunk)
+        with bam.BamReader(path, threads=3) as r:
+            assert len(r.references) == 29
+            r.decode(min_unclipped=0.6, pinned=False)
+            assert r.stats()["records"] == sum(len(d["pos"]) for d in recs.values())
+            for t, exp in expected.items():
+                _check(r.fetch(t), exp)
+    monkeypatch.delenv("CNVB_BAM_CHUNK")
+
+
 def test_bam_errors_are_loud(tmp_path):
     with pytest.raises(bam.BamError, match="Could not open"):
         bam.BamReader(str(tmp_path / "missing.bam"))
