@@ -196,3 +196,29 @@ def test_wis_call_cohort_chain(oracle, ctx):
             assert np.array_equal(to_np(r["states"])[s, a:b], st), (s, a, b)
             n_alt += int((st != 2).sum())
     assert n_alt > 0
+
+
+@pytest.mark.parametrize("n_regions,wl", [(3, 100), (3, 128), (40, 500), (520, 200)])
+def test_region_loop_reference_statistics_batched_and_not(oracle, ctx, n_regions, wl):
+    """GC / GAP columns of the region loop with device-resident sequences: one batched launch for all regions
+    (window length >= 128, at most 512 regions) or region by region otherwise -- both against the oracle,
+    with regions of odd lengths and misaligned sequence buffers."""
+    import torch
+    rng = np.random.default_rng(n_regions * 1000 + wl)
+    big = torch.empty(n_regions * 70_000 + 64, dtype=torch.uint8, device="cuda")
+    regions, seqs, at = [], [], 0
+    for i in range(n_regions):
+        L = int(rng.integers(wl + 1, 60_000))
+        seq = synth.synth_reference(100 + i, L)
+        at += int(rng.integers(0, 16))               # sequences start at arbitrary byte offsets
+        view = big[at:at + L]
+        view.copy_(torch.from_numpy(seq))
+        at += L
+        d = synth.synth_bam_records(200 + i, L, 2 if i == 1 else 50)
+        regions.append(pipeline.Region("r%d" % i, L, soa_batch(d, device="cuda"), view))
+        seqs.append(seq)
+    t = pipeline.coverage_run(regions, cb.CoverageOptions(window_length=wl, min_mapq=0), ctx=ctx)
+    for seq, lo, hi in zip(seqs, t.offsets[:-1], t.offsets[1:]):
+        gc, gap = oracle.refstats(seq, wl)
+        assert_f32_equal_bits(t.gc[lo:hi], gc, "gc")
+        assert np.array_equal(to_np(t.gap[lo:hi]).astype(bool), gap.astype(bool))
