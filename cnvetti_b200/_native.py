@@ -42,6 +42,18 @@ class CovColumns(C.Structure):
                                           "mean_mapq", "gap", "ft")]
 
 
+class VcfOpts(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("sample", C.c_char_p), ("n_contigs", C.c_uint32),
+                ("contig_names", C.POINTER(C.c_char_p)), ("contig_lens", C.c_void_p),
+                ("command_line", C.c_char_p), ("file_date", C.c_char_p), ("is_targets", C.c_int),
+                ("n_threads", C.c_int)]
+
+
+class VcfColumns(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("contig", "start", "end", "rcv", "rcvsd", "lcv", "lcvsd", "frm", "gc",
+                                          "gap", "mean_mapq", "ft", "cv", "cv2", "cvsd", "norm_flags")]
+
+
 class WisOpts(C.Structure):
     _fields_ = [("filter_z_score", C.c_double), ("filter_rel", C.c_double),
                 ("min_ref_targets", C.c_uint32), ("max_ref_targets", C.c_uint32),
@@ -76,6 +88,7 @@ SYMBOLS = {
     "cnvb_bam_ref_reads": (_int, [_vp, _u32, C.POINTER(ReadSoa)]),
     "cnvb_bam_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
     "cnvb_bam_close": (None, [_vp]),
+    "cnvb_vcf_write_coverage": (_int, [_vp, _vp, _u64, C.c_char_p, _u64]),
     "cnvb_cov_create": (_int, [_vp, C.POINTER(CovOpts), _int, _u32, _vp, _vp, _u32, _vp, _vp,
                                _u32, C.POINTER(_vp)]),
     "cnvb_cov_put_records": (_int, [_vp, C.POINTER(ReadSoa)]),

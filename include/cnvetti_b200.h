@@ -255,6 +255,38 @@ int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, con
                         uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
                         float *medians, int mem);
 
+/* ---- coverage VCF writer (text containers) ---------------------------
+ * Replaces the htslib record assembly and output of process_region (lib-coverage/src/lib.rs:
+ * 560-673) under the header of build_header (:67-166), plus what lib-normalize adds (FORMAT CV /
+ * CV2 / CVSD, INFO FEW_GCWINDOWS; uncorrected.rs:51-96, correct_binned.rs:77-146), for the
+ * containers the extension selects in lib-shared/src/bcf_utils.rs:47-82: `.vcf` and `.vcf.gz`
+ * (BGZF).  Binary `.bcf` and the CSI / TBI index are not implemented (a `.bcf` path is an error).
+ * All columns are HOST arrays of n_rows entries; optional ones may be NULL.  Pure host code. */
+typedef struct {
+    const char *path;                 /* *.vcf or *.vcf.gz                                       */
+    const char *sample;               /* sample column (get_sample_name, lib.rs:36-64)           */
+    uint32_t n_contigs;
+    const char *const *contig_names;  /* ##contig lines, in this order                           */
+    const uint32_t *contig_lens;
+    const char *command_line;         /* ##cnvetti_cmdCoverageCommand (NULL: a placeholder)      */
+    const char *file_date;            /* YYYYMMDD (NULL: today, UTC)                             */
+    int is_targets;                   /* ALT <TARGET> instead of <WINDOW>                        */
+    int n_threads;                    /* <= 0: all cores                                         */
+} cnvb_vcf_opts;
+typedef struct {
+    const uint32_t *contig;   /* index into contig_names per row                                */
+    const int32_t *start, *end;
+    const float *rcv, *rcvsd, *lcv, *lcvsd, *frm;   /* rcvsd / lcvsd / frm optional             */
+    const float *gc;          /* optional: INFO GC (+ GAP from `gap`)                           */
+    const uint8_t *gap;
+    const float *mean_mapq;   /* optional: 60 when NULL (agg.rs:241)                            */
+    const uint8_t *ft;        /* optional: CNVB_FT_* bits -> FORMAT/FT "LOWCOV;PILE"            */
+    const float *cv, *cv2, *cvsd;  /* optional: normalised values                               */
+    const uint8_t *norm_flags;     /* optional: CNVB_N2_* bits say which of them a row carries  */
+} cnvb_vcf_columns;
+int cnvb_vcf_write_coverage(const cnvb_vcf_opts *opts, const cnvb_vcf_columns *cols, uint64_t n_rows,
+                            char *err, uint64_t err_len);
+
 /* ---- lib-model-wis ------------------------------------------------------------------------ */
 typedef struct {
     double filter_z_score;         /* --filter-z-score        5.64  (cli.yaml:370-376)        */
