@@ -274,3 +274,104 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
         out["lane_off"] = lane_off
         mark("discover", t0)
     return out
+
+
+# ---- file-level drivers: the two commands of the path with the reference's inputs and outputs -----------
+def read_fasta(path):
+    """{name: uint8 array} of a FASTA file (`--reference`; the reference reads contigs through an
+    indexed reader, lib-coverage/src/reference.rs:58-71 -- same bytes, line breaks removed)."""
+    import gzip
+    out, name, parts = {}, None, []
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as f:
+        for line in f:
+            if line.startswith(b">"):
+                if name is not None:
+                    out[name] = np.frombuffer(b"".join(parts), np.uint8)
+                name, parts = line[1:].split()[0].decode(), []
+            else:
+                parts.append(line.rstrip(b"\r\n"))
+    if name is not None:
+        out[name] = np.frombuffer(b"".join(parts), np.uint8)
+    return out
+
+
+def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(chr)?\d\d?$", targets=None, ctx=None,
+                 threads=0, command_line=None):
+    """`cnvetti cmd coverage --input X.bam --output Y.vcf[.gz] [--reference R.fa] ...` (lib_coverage::run,
+    lib-coverage/src/lib.rs:679-795, without pile masking): BAM decode on host threads, the region loop on
+    the GPU, the coverage VCF written on host threads.  Returns (table, timings) with the host decode /
+    device / write times apart."""
+    import time
+    import torch
+    from . import bam as bam_mod
+    from . import vcf
+    ctx = ctx or default_context()
+    timings = {}
+    t0 = time.perf_counter()
+    with bam_mod.BamReader(input_bam, threads=threads) as reader:
+        samples = reader.sample_names()
+        reader.decode(min_unclipped=options.min_unclipped, pinned=True)
+        timings["bam_decode"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        seqs = read_fasta(reference) if reference else None
+        timings["fasta"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        regions = reader.regions(contig_regex=contig_regex, sequences=seqs, targets=targets)
+        if seqs is not None:
+            missing = [r.name for r in regions if r.sequence is None]
+            if missing:
+                raise N.CnvbError(N.ERR_INVALID, "Could not load reference sequence for %s" % missing[0])
+        table = coverage_run(regions, options, ctx=ctx)
+        torch.cuda.synchronize()
+        timings["device"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        contigs = list(zip(reader.references, reader.lengths))
+        vcf.write_coverage_vcf(output, table, ",".join(samples) if samples else "sample", contigs,
+                               is_targets=options.considered_regions == "TargetRegions", command_line=command_line,
+                               threads=threads)
+        timings["write"] = time.perf_counter() - t0
+    return table, timings
+
+
+def cmd_normalize(input_vcf, output, normalization="MedianGcBinned", ctx=None, threads=0, command_line=None):
+    """`cnvetti cmd normalize --input X.vcf[.gz] --output Y.vcf[.gz] --normalization ...`
+    (lib_normalize::run, lib-normalize/src/lib.rs:43-66): FORMAT/LCV (LCVSD) and INFO/GC in, the same
+    records plus FORMAT/CV (CV2, CVSD) and INFO/FEW_GCWINDOWS out."""
+    from . import vcf
+    ctx = ctx or default_context()
+    r = vcf.read_coverage_vcf(input_vcf)
+    t = CoverageTable()
+    n = len(r["chrom"])
+    names, offsets = [], [0]
+    for i, c in enumerate(r["chrom"]):
+        if not names or names[-1] != c:
+            if names:
+                offsets.append(i)
+            names.append(c)
+    offsets.append(n)
+    t.names, t.offsets = names, offsets
+    t.start = r["pos"].astype(np.int32)
+    t.end = np.array([int(x) for x in r["info"]["END"]], np.int32)
+    f = r["format"]
+    t.rcv, t.lcv = f["RCV"], f["LCV"]
+    t.rcvsd, t.lcvsd, t.frm = f.get("RCVSD"), f.get("LCVSD"), f.get("FRM")
+    ft = f.get("FT")
+    if ft is not None:
+        t.ft = np.array([(N.FT_LOWCOV if x and "LOWCOV" in x else 0) | (N.FT_PILE if x and "PILE" in x else 0)
+                         for x in ft], np.uint8)
+    if "GC" in r["info"]:
+        miss = np.frombuffer(np.uint32(N.F32_MISSING_BITS).tobytes(), np.float32)[0]
+        t.gc = np.array([miss if (x is None or x == ".") else np.float32(x) for x in r["info"]["GC"]], np.float32)
+        t.gap = np.array([1 if x else 0 for x in r["info"].get("GAP", [None] * n)], np.uint8)
+    normalize_run(t, normalization, ctx=ctx)
+    contigs = []
+    for line in r["header"]:
+        if line.startswith("##contig=<ID="):
+            body = line[len("##contig=<"):-1]
+            kv = dict(x.split("=", 1) for x in body.split(","))
+            contigs.append((kv["ID"], int(kv.get("length", 0))))
+    vcf.write_coverage_vcf(output, t, r["samples"][0] if r["samples"] else "sample", contigs,
+                           is_targets=bool(r["alt"]) and r["alt"][0] == "<TARGET>", command_line=command_line,
+                           threads=threads)
+    return t

@@ -133,3 +133,50 @@ def test_coverage_from_bam_equals_arrays(tmp_path):
             for col in ("start", "end", "rcv", "lcv", "ft"):
                 assert np.array_equal(to_np(getattr(t1, col)), to_np(getattr(t2, col))), (kind, col)
             assert t1.num_processed == t2.num_processed
+
+
+@pytest.mark.gpu
+def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
+    """The two commands of the path at file level: BAM (+ FASTA) in, coverage VCF out, normalised VCF out;
+    the values in the files are the oracle's (text precision of %g for the floats)."""
+    from cnvetti_b200 import pipeline, vcf
+    from util import oracle_reads
+    ctx = cb.Context(0)
+    lens = (300_000, 200_000)
+    names = ("chr1", "chr2")
+    recs = [synth.synth_bam_records(31 + i, L, 15_000) for i, L in enumerate(lens)]
+    seqs = [synth.synth_reference(41 + i, L) for i, L in enumerate(lens)]
+    bam_path = synth.write_bam(str(tmp_path / "in.bam"), list(zip(names, lens)) + [("chrUn", 1000)], recs, sample="S1")
+    fa = tmp_path / "ref.fa"
+    with open(fa, "wb") as f:
+        for n_, s in zip(names, seqs):
+            f.write(b">" + n_.encode() + b" synthetic\n")
+            for a in range(0, s.size, 60):
+                f.write(s[a:a + 60].tobytes() + b"\n")
+    opts = cb.CoverageOptions(window_length=500, min_mapq=20)
+    out1 = str(tmp_path / "cov.vcf.gz")
+    table, timings = pipeline.cmd_coverage(bam_path, out1, opts, reference=str(fa), ctx=ctx)
+    assert set(timings) == {"bam_decode", "fasta", "device", "write"} and table.names == ["chr1", "chr2"]
+    r = vcf.read_coverage_vcf(out1)
+    assert r["samples"] == ["S1"] and "##contig=<ID=chrUn,length=1000>" in r["header"]
+    oopts = oracle.cov_opts(window_length=500, min_mapq=20)
+    lcv_all, gc_all = [], []
+    for d, s, L in zip(recs, seqs, lens):
+        counts, _, _ = oracle.frag_gw(oracle_reads(oracle, d), oopts, L)
+        cov, start, end, frm = oracle.frag_gw_stats(counts, oopts, L)
+        lcv_all.append(oracle.cov_records(cov, None, start, end, frm, False, oopts)[0])
+        gc_all.append(oracle.refstats(s, 500)[0])
+    lcv, gc = np.concatenate(lcv_all), np.concatenate(gc_all)
+    np.testing.assert_allclose(r["format"]["LCV"], lcv, rtol=1e-5)
+    got_gc = np.array([np.nan if x == "." else float(x) for x in r["info"]["GC"]])
+    np.testing.assert_allclose(got_gc[np.isfinite(gc)], gc[np.isfinite(gc)], rtol=1e-5)
+    out2 = str(tmp_path / "norm.vcf")
+    pipeline.cmd_normalize(out1, out2, "MedianGcBinned", ctx=ctx)
+    r2 = vcf.read_coverage_vcf(out2)
+    # the oracle on the values as they stand in the first file (what lib-normalize reads)
+    cv, _, _, flags, _ = oracle.norm_gc_median(r["format"]["LCV"], np.array(
+        [np.frombuffer(np.uint32(0x7F800001).tobytes(), np.float32)[0] if x == "." else np.float32(x) for x in r["info"]["GC"]], np.float32))
+    has = (flags & 1).astype(bool)
+    assert has.sum() > 100
+    np.testing.assert_allclose(r2["format"]["CV"][has], cv[has], rtol=1e-5)
+    assert np.array_equal(r2["pos"], r["pos"]) and r2["id"] == r["id"]
