@@ -408,9 +408,25 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
             const uint32_t m = s_len[g];
             if (m > 0 && sm < S) {
                 const uint32_t *ref = s_ref + g * k;
-                dd acc{0.0, 0.0};
-                for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)ref[q] * S + sm));
-                const double mean = __ddiv_rn(__dadd_rn(acc.hi, acc.lo), (double)m);  // lib.rs:147
+                // exact sum (Stats::sum): a plain f64 sum of m f32 values is exact when their exponents lie
+                // close together (see wis_calls_kernel); double-double otherwise
+                double sum = 0.0;
+                uint32_t amax = 0u, amin = 0x7FFFFFFFu;
+                for (uint32_t q = 0; q < m; ++q) {
+                    const float xf = __ldg(X + (size_t)ref[q] * S + sm);
+                    const uint32_t bits = __float_as_uint(xf) & 0x7FFFFFFFu;
+                    amax = max(amax, bits);
+                    amin = min(amin, bits ? bits : 0x7FFFFFFFu);
+                    sum = __dadd_rn(sum, (double)xf);
+                }
+                const int span = (int)(amax >> 23) - (int)max(amin >> 23, 1u);
+                const int room = 29 - (32 - __clz((int)m - 1));  // 29 - ceil(log2 m)
+                if (amax != 0u && span > room) {
+                    dd acc{0.0, 0.0};
+                    for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)ref[q] * S + sm));
+                    sum = __dadd_rn(acc.hi, acc.lo);
+                }
+                const double mean = __ddiv_rn(sum, (double)m);  // lib.rs:147
                 double v = 0.0;
                 for (uint32_t q = 0; q < m; ++q) {
                     const double d = __dsub_rn((double)__ldg(X + (size_t)ref[q] * S + sm), mean);
