@@ -301,3 +301,46 @@ def test_norm_gc_median_parity(oracle, ctx, device, n):
     np.testing.assert_allclose(g2[fin], o2[fin], rtol=RTOL, atol=1e-7)
     if n > 1000:
         assert (flags & oracle.N2_FEW_GC).any() and (flags & oracle.N2_CV).any() and (flags == 0).any()
+
+
+# ---- BASELINE sizes: size-independent checks against an independent torch model --------------------
+def test_full_size_contig_fragments_and_refstats_against_torch_model(ctx):
+    """One config-2 contig at full size (chr1: 249 Mbp, 78 M reads, 500 bp windows) -- far beyond what the
+    CPU oracle finishes in seconds.  The filter, the window index and the per-window GC fraction are
+    restated with plain torch tensor operations (an independent model: no shared code with the kernels)
+    and must agree exactly: counts per window, the processed tally, GC bits and gap flags."""
+    import torch
+    from cnvetti_b200 import synth_torch
+    from cnvetti_b200.synth import HG38_AUTOSOMES
+    L, wl, minq = HG38_AUTOSOMES[0], 500, 20
+    soa = synth_torch.synth_soa_contig(2001, L, int(L * 0.313 / 2), "cuda")
+    n_bins = (L + wl - 1) // wl
+    agg = cb.FragmentsGenomeWideAggregator(None, cb.CoverageOptions(window_length=wl, min_mapq=minq), L, ctx=ctx)
+    agg.put_fetched_records(cb.ReadBatch(mid=soa["mid"].contiguous(), mapq=soa["mapq"].contiguous(),
+                                         flags=soa["flags"].contiguous()))
+    counts = agg.counts()
+    fl = soa["flags"].to(torch.int32) & 0xFFFF
+    paired = (fl & 1) != 0
+    ok = (soa["mapq"].to(torch.int32) >= minq) & ((fl & (0x100 | 0x200 | 0x400 | 0x800 | 0x1000)) == 0)
+    ok &= ~paired | (((fl & 0x2) != 0) & ((fl & 0x2000) == 0))
+    model = torch.bincount((soa["mid"][ok] // wl).to(torch.int64), minlength=n_bins)
+    assert model.numel() == n_bins and int(ok.sum()) > 20_000_000
+    assert torch.equal(torch.as_tensor(counts).to(torch.int64).cuda(), model)
+    assert agg.num_processed() == int(ok.sum()) and agg.num_skipped() == 0
+    del soa, fl, ok, model
+    # reference statistics of the same contig
+    seq = synth_torch.synth_reference_torch(2001, L, "cuda")
+    rs = cb.ReferenceStats.look_at_chars(seq, wl, ctx=ctx)
+    gc, gap = rs.gc_content, rs.has_gap
+    pad = n_bins * wl - L
+    s = torch.cat([seq, torch.zeros(pad, dtype=torch.uint8, device="cuda")]).view(n_bins, wl)
+    up = s & 0xDF
+    is_gc = ((up == ord("G")) | (up == ord("C"))).sum(1)
+    is_acgt = ((up == ord("A")) | (up == ord("C")) | (up == ord("G")) | (up == ord("T"))).sum(1)
+    is_n = (up == ord("N")).sum(1)
+    want = is_gc.to(torch.float32) / is_acgt.to(torch.float32)          # one IEEE division of exact integers
+    got = torch.as_tensor(gc).cuda()
+    have = is_acgt > 0
+    assert torch.equal(got[have].view(torch.int32), want[have].view(torch.int32))
+    assert bool((got[~have].view(torch.int32) == 0x7F800001).all())
+    assert torch.equal(torch.as_tensor(gap).cuda().bool(), is_n > 0)
