@@ -101,3 +101,44 @@ def test_posteriors_within_tolerance(oracle, ctx):
 def test_hmm_argument_errors(ctx):
     with pytest.raises(cb.CnvbError):
         discover.hmm_segment(np.zeros(4, np.float32), [0, 4], [0.1], discover.DiscoverOptions(p_move=0.5), ctx=ctx)
+
+
+def test_full_size_lanes_match_oracle_and_are_independent(oracle, ctx):
+    """BASELINE config 4 at full size (100 samples x 22 contigs at 1 kbp: 2200 lanes, 2.9e8 bins): lanes
+    drawn across the range of lengths are recomputed by the oracle (a single lane is milliseconds on the
+    CPU) and must be identical; the lanes of a second call on a subset must equal those of the full call
+    (a lane's path depends on nothing but the lane)."""
+    import torch
+    from cnvetti_b200.synth import HG38_AUTOSOMES
+    n_samples = 100
+    lens = [(L + 999) // 1000 for L in HG38_AUTOSOMES]
+    lane_len = np.array(lens * n_samples, np.int64)
+    off = np.concatenate([[0], np.cumsum(lane_len)]).astype(np.uint64)
+    n = int(off[-1])
+    g = torch.Generator(device="cuda")
+    g.manual_seed(44)
+    cn = torch.full((n,), 2.0, device="cuda")
+    nseg = 20 * len(lane_len)
+    st = (torch.rand(nseg, generator=g, device="cuda") * (n - 600)).long()
+    ln = (torch.rand(nseg, generator=g, device="cuda") * 495).long() + 5
+    val = torch.tensor([0.0, 1.0, 3.0, 4.0], device="cuda")[(torch.rand(nseg, generator=g, device="cuda") * 4).long().clamp_(0, 3)]
+    delta = torch.zeros(n + 1, device="cuda")
+    delta.index_add_(0, st, val - 2.0)
+    delta.index_add_(0, st + ln, -(val - 2.0))
+    mu = (cn + torch.cumsum(delta[:-1], 0)).clamp_(0.0, 4.0).round_() / 2.0
+    cv = (mu + torch.randn(n, generator=g, device="cuda") * (0.08 * mu.sqrt() + 0.02)).float().contiguous()
+    sigma = np.full(len(lane_len), 0.08)
+    states = discover.hmm_segment(cv, off, sigma, ctx=ctx)
+    assert int((states != 2).sum()) > 1_000_000
+    tab = oracle.hmm_tables(0.08)
+    rng = np.random.default_rng(5)
+    pick = sorted(set([0, 21, len(lane_len) - 1] + rng.integers(0, len(lane_len), 30).tolist()))
+    for lane in pick:
+        a, b = int(off[lane]), int(off[lane + 1])
+        want = oracle.hmm_viterbi(cv[a:b].cpu().numpy(), tab)
+        assert np.array_equal(states[a:b].cpu().numpy(), want), lane
+    # a subset of whole samples in a call of its own
+    lo_lane, hi_lane = 22 * 37, 22 * 41
+    a, b = int(off[lo_lane]), int(off[hi_lane])
+    sub = discover.hmm_segment(cv[a:b].contiguous(), off[lo_lane:hi_lane + 1] - off[lo_lane], sigma[lo_lane:hi_lane], ctx=ctx)
+    assert torch.equal(sub, states[a:b])
