@@ -163,7 +163,7 @@ struct cnvb_bam {
     uint64_t n_records = 0, n_unplaced = 0, bytes_compressed = 0, bytes_uncompressed = 0;
     double t_inflate = 0.0, t_parse = 0.0, t_total = 0.0;
     bool decoded = false;
-    RawBuf cbuf, ubuf;  // chunk buffers, kept across chunks and calls (no page faults after the first chunk)
+    RawBuf cbuf, ubuf, ubuf2;  // chunk buffers, kept across chunks and calls (no page faults after the first chunks)
     ~cnvb_bam() {
         for (auto &r : refs) r.release();
     }
@@ -171,142 +171,76 @@ struct cnvb_bam {
 
 namespace {
 
-int bam_fail(cnvb_bam *b, int code, const char *fmt, ...) {
+int fail_to(std::string &dst, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    b->error = buf;
+    dst = buf;
     return code;
 }
 
-// The whole decode: one pass, chunks of BGZF blocks.
+struct Run {  // consecutive records of one refID inside a chunk
+    uint64_t first;  // index of its first record in the chunk
+    int32_t tid;
+    uint64_t dst;    // row in the contig's columns where the run starts
+};
+
+// The whole decode: one pass over the file in chunks of compressed bytes.  Two stages per chunk --
+// (A) read, cut into BGZF blocks, inflate on all threads; (B) header / record walk / SoA derivation -- and
+// stage B of chunk k runs on a helper thread while stage A of chunk k+1 proceeds (two uncompressed
+// buffers).  Stage B is sequential from chunk to chunk (it hands the partial record at the end of a chunk
+// to the next one); its serial part, the record walk, is what the overlap hides.
 int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
     FILE *f = fopen(b->path.c_str(), "rb");
-    if (!f) return bam_fail(b, CNVB_ERR_INVALID, "Could not open BAM file %s", b->path.c_str());
-    uint64_t kChunkBytes = header_only ? (1ull << 20) : (64ull << 20);  // compressed bytes per chunk
+    if (!f) return fail_to(b->error, CNVB_ERR_INVALID, "Could not open BAM file %s", b->path.c_str());
+    uint64_t kChunkBytes = header_only ? (1ull << 20) : (8ull << 20);  // compressed bytes per chunk
     if (const char *e = getenv("CNVB_BAM_CHUNK")) {  // (tests: small chunks exercise the chunk seams)
         const long v = atol(e);
         if (v >= 64) kChunkBytes = (uint64_t)v;
     }
-    RawBuf &cbuf = b->cbuf, &ubuf = b->ubuf;
-    std::vector<uint8_t> carry;
+    constexpr uint64_t kHead = 1ull << 16;  // room in front of a chunk's bytes for the carried-over partial record
+    RawBuf &cbuf = b->cbuf;
+    RawBuf *ubufs[2] = {&b->ubuf, &b->ubuf2};
     std::vector<Block> blocks;
-    std::vector<uint64_t> rec_off;
-    bool header_done = false, eof = false;
-    uint64_t file_pos = 0;
     std::vector<uint8_t> left;  // compressed bytes of an incomplete block at the end of the last read
-    struct Run {  // consecutive records of one refID inside a chunk
-        uint64_t first;  // index of its first record in the chunk
-        int32_t tid;
-        uint64_t dst;    // row in the contig's columns where the run starts
-    };
-    std::vector<Run> runs;
+    uint64_t file_pos = 0;
+    bool eof = false;
     int rc = CNVB_OK;
-    while (!eof && rc == CNVB_OK) {
-        // ---- read compressed bytes, cut into whole blocks
-        const uint64_t have = left.size();
-        if (!cbuf.resize(have + kChunkBytes, false)) {
-            rc = bam_fail(b, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
-            break;
-        }
-        if (have) memcpy(cbuf.data(), left.data(), have);
-        const size_t got = fread(cbuf.data() + have, 1, kChunkBytes, f);
-        cbuf.n = have + got;
-        file_pos += got;
-        if (got == 0) eof = true;
-        blocks.clear();
-        uint64_t p = 0, utotal = 0;
-        while (p + 18 <= cbuf.size()) {
-            const uint8_t *h = cbuf.data() + p;
-            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
-                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: not a BGZF file (bad block header at compressed offset %llu)",
-                              b->path.c_str(), (unsigned long long)(file_pos - cbuf.size() + p));
-                break;
-            }
-            const uint32_t xlen = rd16(h + 10);
-            if (p + 12 + xlen > cbuf.size()) break;
-            uint32_t bsize = 0;
-            for (uint32_t x = 0; x + 4 <= xlen;) {  // extra subfields: find BC
-                const uint8_t *e = h + 12 + x;
-                const uint32_t slen = rd16(e + 2);
-                if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(e + 4) + 1;
-                x += 4 + slen;
-            }
-            if (bsize < 12 + xlen + 8) {
-                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: BGZF block without a valid BC subfield", b->path.c_str());
-                break;
-            }
-            if (p + bsize > cbuf.size()) break;  // incomplete block: next read
-            Block bl;
-            bl.off = p + 12 + xlen;
-            bl.clen = bsize - (12 + xlen) - 8;
-            bl.crc = rd32(h + bsize - 8);
-            bl.isize = rd32(h + bsize - 4);
-            bl.uoff = utotal;
-            utotal += bl.isize;
-            blocks.push_back(bl);
-            p += bsize;
-        }
-        if (rc != CNVB_OK) break;
-        left.assign(cbuf.data() + p, cbuf.data() + cbuf.size());
-        if (eof && !left.empty()) {
-            rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BGZF block at the end of the file", b->path.c_str());
-            break;
-        }
-        b->bytes_compressed += p;
-        b->bytes_uncompressed += utotal;
-        // ---- inflate the blocks of the chunk in parallel, behind the carried-over partial record
-        const auto t0 = clk::now();
-        const uint64_t c0 = carry.size();
-        if (!ubuf.resize(c0 + utotal, false)) {
-            rc = bam_fail(b, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
-            break;
-        }
-        if (c0) memcpy(ubuf.data(), carry.data(), c0);
-        std::atomic<int> bad{0};
-        run_parallel(b->n_threads, blocks.size(), [&](uint64_t lo, uint64_t hi, int) {
-            z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) {
-                bad = 1;
-                return;
-            }
-            for (uint64_t i = lo; i < hi; ++i) {
-                const Block &bl = blocks[i];
-                if (bl.isize == 0) continue;
-                inflateReset(&zs);
-                zs.next_in = cbuf.data() + bl.off;
-                zs.avail_in = bl.clen;
-                zs.next_out = ubuf.data() + c0 + bl.uoff;
-                zs.avail_out = bl.isize;
-                const int r = inflate(&zs, Z_FINISH);
-                if (r != Z_STREAM_END || zs.avail_out != 0 ||
-                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), ubuf.data() + c0 + bl.uoff, bl.isize) != bl.crc)
-                    bad = 1;
-            }
-            inflateEnd(&zs);
-        });
-        b->t_inflate += std::chrono::duration<double>(clk::now() - t0).count();
-        if (bad) {
-            rc = bam_fail(b, CNVB_ERR_INVALID, "%s: corrupt BGZF block (inflate or CRC failure)", b->path.c_str());
-            break;
-        }
-        // ---- header (once), then records
+
+    // ---- stage B state (touched by the helper thread only while it runs)
+    std::vector<uint8_t> carry, joined;
+    std::vector<uint64_t> rec_off;
+    std::vector<Run> runs;
+    bool header_done = false, stop_after_header = false;
+    std::string werr;
+    int wrc = CNVB_OK;
+    double t_parse = 0.0;
+    auto parse = [&](RawBuf *ub, uint64_t n_data, bool last) {
         const auto t1 = clk::now();
-        const uint8_t *u = ubuf.data();
-        const uint64_t un = ubuf.size();
+        const uint8_t *u;
+        uint64_t un;
+        if (carry.size() <= kHead) {
+            u = ub->data() + kHead - carry.size();
+            if (!carry.empty()) memcpy(const_cast<uint8_t *>(u), carry.data(), carry.size());
+            un = carry.size() + n_data;
+        } else {  // (a header or record longer than the head-room: join in a buffer of its own)
+            joined.assign(carry.begin(), carry.end());
+            joined.insert(joined.end(), ub->data() + kHead, ub->data() + kHead + n_data);
+            u = joined.data();
+            un = joined.size();
+        }
         uint64_t q = 0;
         if (!header_done) {
             bool complete = false;
             do {
                 if (un < 12) break;
                 if (memcmp(u, "BAM\1", 4) != 0) {
-                    rc = bam_fail(b, CNVB_ERR_INVALID, "%s: not a BAM file (bad magic)", b->path.c_str());
-                    break;
+                    wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: not a BAM file (bad magic)", b->path.c_str());
+                    return;
                 }
                 const uint64_t l_text = rd32(u + 4);
                 if (un < 12 + l_text) break;
@@ -332,17 +266,19 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
                 q = w;
                 complete = true;
             } while (false);
-            if (rc != CNVB_OK) break;
             if (!complete) {  // header spans more than this chunk: read on
-                if (eof) {
-                    rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BAM header", b->path.c_str());
-                    break;
+                if (last) {
+                    wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: truncated BAM header", b->path.c_str());
+                    return;
                 }
-                carry.assign(ubuf.data(), ubuf.data() + ubuf.size());
-                continue;
+                carry.assign(u, u + un);
+                return;
             }
             header_done = true;
-            if (header_only) break;
+            if (header_only) {
+                stop_after_header = true;
+                return;
+            }
         }
         // record boundaries, and the runs of equal refID among them (the refID sits next to block_size)
         rec_off.clear();
@@ -351,9 +287,9 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
         while (q + 4 <= un) {
             const uint64_t bs = rd32(u + q);
             if (bs < 32) {
-                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: corrupt BAM record (block_size %llu)", b->path.c_str(),
+                wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: corrupt BAM record (block_size %llu)", b->path.c_str(),
                               (unsigned long long)bs);
-                break;
+                return;
             }
             if (q + 4 + bs > un) break;
             // the walk is a chain of dependent loads, one cache line per record (~55 ns each when cold): records
@@ -368,32 +304,29 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             rec_off.push_back(q);
             q += 4 + bs;
         }
-        if (rc != CNVB_OK) break;
         const uint64_t nr = rec_off.size();
-        const auto t_walk = clk::now();
         // room in the contigs' columns first (file order is kept: a run is appended where its contig ends),
         // then the threads derive disjoint record ranges straight into them
-        for (size_t k = 0; k < runs.size() && rc == CNVB_OK; ++k) {
+        for (size_t k = 0; k < runs.size(); ++k) {
             Run &run = runs[k];
             const uint64_t m = (k + 1 < runs.size() ? runs[k + 1].first : nr) - run.first;
             if (run.tid < 0) {
                 b->n_unplaced += m;
             } else if ((uint64_t)run.tid >= b->refs.size()) {
-                rc = bam_fail(b, CNVB_ERR_INVALID, "%s: record with refID %d but the header has %zu references",
+                wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: record with refID %d but the header has %zu references",
                               b->path.c_str(), run.tid, b->refs.size());
+                return;
             } else {
                 RefReads &rr = b->refs[run.tid];
                 if (!rr.reserve(rr.n + m, pinned)) {
-                    rc = bam_fail(b, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
-                } else {
-                    run.dst = rr.n;
-                    rr.n += m;
-                    rr.pos.n = rr.end.n = rr.mid.n = rr.frag_end.n = rr.mapq.n = rr.flags.n = rr.n;
+                    wrc = fail_to(werr, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
+                    return;
                 }
+                run.dst = rr.n;
+                rr.n += m;
+                rr.pos.n = rr.end.n = rr.mid.n = rr.frag_end.n = rr.mapq.n = rr.flags.n = rr.n;
             }
         }
-        if (rc != CNVB_OK) break;
-        const auto t_res = clk::now();
         std::atomic<int> badrec{0};
         run_parallel(b->n_threads, nr, [&](uint64_t lo, uint64_t hi, int) {
             // the run holding record lo: last run with first <= lo
@@ -422,21 +355,126 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             }
         });
         if (badrec) {
-            rc = bam_fail(b, CNVB_ERR_INVALID, "%s: corrupt BAM record (CIGAR past the end of the record)", b->path.c_str());
+            wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: corrupt BAM record (CIGAR past the end of the record)", b->path.c_str());
+            return;
+        }
+        b->n_records += nr;
+        carry.assign(u + q, u + un);  // (may alias `joined`: assign from a range of another vector is fine)
+        t_parse += std::chrono::duration<double>(clk::now() - t1).count();
+    };
+
+    std::thread worker;
+    auto join_worker = [&]() {
+        if (worker.joinable()) worker.join();
+    };
+    for (uint64_t k = 0; !eof && rc == CNVB_OK; ++k) {
+        // ---- stage A: read compressed bytes, cut into whole blocks
+        const uint64_t have = left.size();
+        if (!cbuf.resize(have + kChunkBytes, false)) {
+            rc = fail_to(b->error, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
             break;
         }
-        if (getenv("CNVB_BAM_DEBUG"))
-            fprintf(stderr, "[bam] chunk: %llu records, walk %.1f ms, reserve %.1f ms, derive %.1f ms\n", (unsigned long long)nr,
-                    std::chrono::duration<double>(t_walk - t1).count() * 1e3, std::chrono::duration<double>(t_res - t_walk).count() * 1e3,
-                    std::chrono::duration<double>(clk::now() - t_res).count() * 1e3);
-        b->n_records += nr;
-        carry.assign(ubuf.data() + q, ubuf.data() + ubuf.size());
-        b->t_parse += std::chrono::duration<double>(clk::now() - t1).count();
+        if (have) memcpy(cbuf.data(), left.data(), have);
+        const size_t got = fread(cbuf.data() + have, 1, kChunkBytes, f);
+        cbuf.n = have + got;
+        file_pos += got;
+        if (got == 0) eof = true;
+        blocks.clear();
+        uint64_t p = 0, utotal = 0;
+        while (p + 18 <= cbuf.size()) {
+            const uint8_t *h = cbuf.data() + p;
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
+                rc = fail_to(b->error, CNVB_ERR_INVALID, "%s: not a BGZF file (bad block header at compressed offset %llu)",
+                             b->path.c_str(), (unsigned long long)(file_pos - cbuf.size() + p));
+                break;
+            }
+            const uint32_t xlen = rd16(h + 10);
+            if (p + 12 + xlen > cbuf.size()) break;
+            uint32_t bsize = 0;
+            for (uint32_t x = 0; x + 4 <= xlen;) {  // extra subfields: find BC
+                const uint8_t *e = h + 12 + x;
+                const uint32_t slen = rd16(e + 2);
+                if (e[0] == 'B' && e[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(e + 4) + 1;
+                x += 4 + slen;
+            }
+            if (bsize < 12 + xlen + 8) {
+                rc = fail_to(b->error, CNVB_ERR_INVALID, "%s: BGZF block without a valid BC subfield", b->path.c_str());
+                break;
+            }
+            if (p + bsize > cbuf.size()) break;  // incomplete block: next read
+            Block bl;
+            bl.off = p + 12 + xlen;
+            bl.clen = bsize - (12 + xlen) - 8;
+            bl.crc = rd32(h + bsize - 8);
+            bl.isize = rd32(h + bsize - 4);
+            bl.uoff = utotal;
+            utotal += bl.isize;
+            blocks.push_back(bl);
+            p += bsize;
+        }
+        if (rc != CNVB_OK) break;
+        left.assign(cbuf.data() + p, cbuf.data() + cbuf.size());
+        if (eof && !left.empty()) {
+            rc = fail_to(b->error, CNVB_ERR_INVALID, "%s: truncated BGZF block at the end of the file", b->path.c_str());
+            break;
+        }
+        b->bytes_compressed += p;
+        b->bytes_uncompressed += utotal;
+        // ---- inflate the blocks of the chunk in parallel (the helper may still be parsing the previous chunk)
+        const auto t0 = clk::now();
+        RawBuf *ub = ubufs[k & 1];
+        if (!ub->resize(kHead + utotal, false)) {
+            rc = fail_to(b->error, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
+            break;
+        }
+        std::atomic<int> bad{0};
+        run_parallel(b->n_threads, blocks.size(), [&](uint64_t lo, uint64_t hi, int) {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) {
+                bad = 1;
+                return;
+            }
+            for (uint64_t i = lo; i < hi; ++i) {
+                const Block &bl = blocks[i];
+                if (bl.isize == 0) continue;
+                inflateReset(&zs);
+                zs.next_in = cbuf.data() + bl.off;
+                zs.avail_in = bl.clen;
+                zs.next_out = ub->data() + kHead + bl.uoff;
+                zs.avail_out = bl.isize;
+                const int r = inflate(&zs, Z_FINISH);
+                if (r != Z_STREAM_END || zs.avail_out != 0 ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), ub->data() + kHead + bl.uoff, bl.isize) != bl.crc)
+                    bad = 1;
+            }
+            inflateEnd(&zs);
+        });
+        b->t_inflate += std::chrono::duration<double>(clk::now() - t0).count();
+        if (bad) {
+            rc = fail_to(b->error, CNVB_ERR_INVALID, "%s: corrupt BGZF block (inflate or CRC failure)", b->path.c_str());
+            break;
+        }
+        // ---- stage B of this chunk, after stage B of the previous one
+        join_worker();
+        if (wrc != CNVB_OK || stop_after_header) break;
+        const bool last = eof;
+        worker = std::thread(parse, ub, utotal, last);
+        if (header_only) {  // opening reads no further than the header needs
+            join_worker();
+            if (wrc != CNVB_OK || stop_after_header) break;
+        }
     }
+    join_worker();
     fclose(f);
-    if (rc == CNVB_OK && !header_done) rc = bam_fail(b, CNVB_ERR_INVALID, "%s: empty or truncated BAM file", b->path.c_str());
+    if (rc == CNVB_OK && wrc != CNVB_OK) {
+        rc = wrc;
+        b->error = werr;
+    }
+    b->t_parse += t_parse;
+    if (rc == CNVB_OK && !header_done) rc = fail_to(b->error, CNVB_ERR_INVALID, "%s: empty or truncated BAM file", b->path.c_str());
     if (rc == CNVB_OK && !header_only && !carry.empty())
-        rc = bam_fail(b, CNVB_ERR_INVALID, "%s: truncated BAM record at the end of the file", b->path.c_str());
+        rc = fail_to(b->error, CNVB_ERR_INVALID, "%s: truncated BAM record at the end of the file", b->path.c_str());
     b->t_total += std::chrono::duration<double>(clk::now() - t_begin).count();
     return rc;
 }
