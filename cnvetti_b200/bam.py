@@ -69,9 +69,12 @@ class BamReader:
     def decode_seconds(self):
         return self.stats()["decode_seconds"]
 
-    def fetch(self, tid):
+    def fetch(self, tid, start=None, end=None):
         """The records of contig `tid` (name or index) as a ReadBatch over the decoder's buffers
-        (valid while this reader is open and not decoded again)."""
+        (valid while this reader is open and not decoded again).  With `start` / `end` (0-based,
+        half-open): the records htslib's `fetch(tid, start, end)` yields, i.e. those overlapping the
+        interval (pos < end and bam_endpos > start), in file order -- a selection from the decoded
+        contig (records are in coordinate order: the candidates end at the first pos >= end)."""
         from .coverage import ReadBatch
         if not self.decoded:
             raise BamError(N.ERR_STATE, "BamReader.fetch before decode()")
@@ -93,6 +96,12 @@ class BamReader:
                       mid=col(soa.mid, C.c_int32, np.int32), frag_end=col(soa.frag_end, C.c_int32, np.int32),
                       mapq=col(soa.mapq, C.c_uint8, np.uint8), flags=col(soa.flags, C.c_uint16, np.uint16))
         b._owner = self  # keep the buffers alive
+        if start is not None or end is not None:
+            lo_pos = 0 if start is None else int(start)
+            hi = n if end is None else int(np.searchsorted(b.pos, int(end), side="left"))
+            keep = np.flatnonzero(b.end[:hi] > lo_pos)
+            b = ReadBatch(**{k: np.ascontiguousarray(getattr(b, k)[keep])
+                             for k in ("pos", "end", "mid", "frag_end", "mapq", "flags")})
         return b
 
     def regions(self, contig_regex=r"^(chr)?\d\d?$", sequences=None, targets=None):

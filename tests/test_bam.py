@@ -44,6 +44,13 @@ def test_bam_decode_matches_packer(tmp_path, threads, min_unclipped):
         assert len(r.fetch("chrUn_x")) == 0
         regs = r.regions()  # default --contig-regex ^(chr)?\d\d?$ (cli.yaml:111): chrUn_x is left out
         assert [g.name for g in regs] == ["chr1", "chr2", "chr3"] and regs[1].length == 200_000
+        # sub-region: what fetch(tid, start, end) of an indexed reader yields (overlap semantics)
+        full = _expected(recs[0], min_unclipped)
+        for a, z in ((0, 1000), (120_000, 121_000), (299_000, 10**9), (5, 6)):
+            sel = np.flatnonzero((full["pos"] < z) & (full["end"] > a))
+            sub = r.fetch("chr1", a, z)
+            assert len(sub) == sel.size
+            _check(sub, {k: v[sel] for k, v in full.items()})
         # decoding again (other options) replaces the columns
         r.decode(min_unclipped=0.0, pinned=False)
         _check(r.fetch(1), _expected(recs[1], 0.0))
