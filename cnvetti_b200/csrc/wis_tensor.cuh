@@ -401,6 +401,7 @@ struct SweepArgs {
 // STREAM: more than kMaxKBlocks K-blocks (S > 128): the A operand does not fit beside the B ring, so
 // both operands stream through kStreamStages stages of (A rows 0..127 | A rows 128..255 | B) K-blocks.
 constexpr uint32_t kStreamStages = 4;  // x 48 KB
+constexpr int kDefaultCluster = 2;      // CTAs per cluster of the streamed sweep
 
 // CLUSTER (with STREAM): two CTAs of a cluster share one block of 256 rows and take its column tiles in
 // turn.  The streamed sweep is bound by L2 -> SM traffic (48 KB of operands per 256 x 128 x 64 MMA block =
@@ -410,24 +411,26 @@ constexpr uint32_t kStreamStages = 4;  // x 48 KB
 // refilled when BOTH consumers are done with it: the MMA issuers commit to the stage's empty barrier in
 // both CTAs (multicast commit), which therefore counts two arrivals.  Candidate slots come from the
 // global per-row counter (two CTAs append to the same rows).
-template <bool FIRST, bool STREAM, bool CLUSTER>
+template <bool FIRST, bool STREAM, int CL>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
+    constexpr bool CLUSTER = CL > 1;
+    static_assert(CL == 1 || CL == 2 || CL == 4, "clusters of 2 or 4 CTAs");
     static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
     const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
-    const uint32_t blk = CLUSTER ? blockIdx.x >> 1 : blockIdx.x;
+    const uint32_t blk = blockIdx.x / CL;
     // this block's share of the round: two tile ranges either side of what it has swept before
     const uint4 rng = a.rng[blk];
     const uint32_t n_lo = rng.y - rng.x, n_all = n_lo + (rng.w - rng.z);
     if (n_all == 0) return;  // (both CTAs of a cluster)
     // CLUSTER: tile i of this CTA is tile 2 i + rank of the block; both CTAs make `steps` passes through the
     // operand ring (the second one without a tile of its own in the last pass when the count is odd)
-    const uint32_t n_tiles = CLUSTER ? (n_all + 1u - crank) >> 1 : n_all;
-    const uint32_t steps = CLUSTER ? (n_all + 1u) >> 1 : n_all;
+    const uint32_t n_tiles = (n_all + CL - 1u - crank) / CL;
+    const uint32_t steps = (n_all + CL - 1u) / CL;
     const uint32_t rng_x = rng.x, rng_z = rng.z;
 #define CNVB_TILE_G(g) ((g) < n_lo ? rng_x + (g) : rng_z + ((g) - n_lo))
-#define CNVB_TILE_AT(it) CNVB_TILE_G(CLUSTER ? 2u * (it) + crank : (it))
+#define CNVB_TILE_AT(it) CNVB_TILE_G((uint32_t)CL * (it) + crank)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
@@ -452,7 +455,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_init(bar_a_full, 1);
         for (uint32_t s = 0; s < kStages; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
-            mbar_init(bar_b_empty + 8 * s, CLUSTER ? 2 : 1);  // CLUSTER: both CTAs' MMAs release a stage
+            mbar_init(bar_b_empty + 8 * s, CL);  // CLUSTER: the MMAs of all CTAs of the cluster release a stage
         }
         for (uint32_t s = 0; s < 2; ++s) {
             mbar_init(bar_acc_full + 8 * s, 1);
@@ -492,9 +495,10 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (STREAM) {
                         const uint32_t sb = a_base + st * 3u * kTileBytes;
                         mbar_expect_tx(bar_b_full + 8 * st, (have ? 3u : 2u) * kTileBytes);
-                        if (CLUSTER) {  // this CTA's half of the rows, into both CTAs
-                            tma_load_2d_mc(sb + crank * kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock),
-                                           (int32_t)(row0 + crank * 128u), (uint16_t)3);
+                        if (CLUSTER) {  // this CTA's share of the rows (256 / CL of them), into all CTAs of the cluster
+                            tma_load_2d_mc(sb + crank * (2u * kTileBytes / CL), &tmap_a, bar_b_full + 8 * st,
+                                           (int32_t)(kb * kKBlock), (int32_t)(row0 + crank * (256u / CL)),
+                                           (uint16_t)((1u << CL) - 1u));
                         } else {
                             tma_load_2d(sb, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)row0);
                             tma_load_2d(sb + kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)(row0 + 128));
@@ -552,7 +556,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                         }
                         // frees the stage (in both CTAs: the peer's producer writes into this one's too)
-                        if (CLUSTER) tc_commit_mc(bar_b_empty + 8 * st, (uint16_t)3); else tc_commit(bar_b_empty + 8 * st);
+                        if (CLUSTER) tc_commit_mc(bar_b_empty + 8 * st, (uint16_t)((1u << CL) - 1u)); else tc_commit(bar_b_empty + 8 * st);
                         if (++st == n_stages) {
                             st = 0;
                             ph ^= 1u;
@@ -1162,7 +1166,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-inline int make_tmap(cnvb_ctx *ctx, void *H, uint64_t T, uint64_t Kp, CUtensorMap *out) {
+inline int make_tmap(cnvb_ctx *ctx, void *H, uint64_t T, uint64_t Kp, CUtensorMap *out, uint32_t box_rows = 128) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -1173,7 +1177,7 @@ inline int make_tmap(cnvb_ctx *ctx, void *H, uint64_t T, uint64_t Kp, CUtensorMa
     }
     const cuuint64_t dims[2] = {Kp, T};
     const cuuint64_t strides[1] = {Kp * 2};
-    const cuuint32_t box[2] = {kKBlock, 128};
+    const cuuint32_t box[2] = {kKBlock, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, H, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1316,16 +1320,21 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
-    // streamed sweep: CTA pairs share their rows' operand through TMA multicast (CNVB_WIS_CLUSTER=0: one CTA per block)
-    static const bool use_cluster = [] {
+    // streamed sweep: the CTAs of a cluster share their rows' operand through TMA multicast
+    // (CNVB_WIS_CLUSTER = 1: one CTA per block, 2 or 4: CTAs per cluster)
+    static const int cluster_env = [] {
         const char *e = getenv("CNVB_WIS_CLUSTER");
-        return !(e && atoi(e) == 0);
+        const int v = e ? atoi(e) : -1;
+        return v == 0 ? 1 : v;
     }();
-    const bool cluster = stream_a && use_cluster;
-    auto sweep_first = cluster ? wis_sweep_kernel<true, true, true>
-                               : (stream_a ? wis_sweep_kernel<true, true, false> : wis_sweep_kernel<true, false, false>);
-    auto sweep_next = cluster ? wis_sweep_kernel<false, true, true>
-                              : (stream_a ? wis_sweep_kernel<false, true, false> : wis_sweep_kernel<false, false, false>);
+    const int cl = !stream_a ? 1 : (cluster_env == 1 || cluster_env == 2 || cluster_env == 4 ? cluster_env : kDefaultCluster);
+    if (cl == 4) CNVB_TRY(make_tmap(ctx, subset ? (void *)HA : (void *)H, subset ? rows_pad : Tpad, Kp, &tmap_a, 64));  // quarter loads
+    auto sweep_first = cl == 4 ? wis_sweep_kernel<true, true, 4>
+                     : cl == 2 ? wis_sweep_kernel<true, true, 2>
+                               : (stream_a ? wis_sweep_kernel<true, true, 1> : wis_sweep_kernel<true, false, 1>);
+    auto sweep_next = cl == 4 ? wis_sweep_kernel<false, true, 4>
+                    : cl == 2 ? wis_sweep_kernel<false, true, 2>
+                              : (stream_a ? wis_sweep_kernel<false, true, 1> : wis_sweep_kernel<false, false, 1>);
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     BoundConsts bc{};
@@ -1359,13 +1368,13 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.cand_cnt = cand_cnt;
     auto launch_sweep = [&](decltype(sweep_first) kern) -> cudaError_t {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(cluster ? 2 * row_blocks : row_blocks);
+        cfg.gridDim = dim3((unsigned)cl * row_blocks);
         cfg.blockDim = dim3(kSweepThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cluster ? 2 : 1;
+        attr[0].val.clusterDim.x = (unsigned)cl;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;

@@ -1,7 +1,8 @@
 # guarded probe of the cluster-multicast sweep (every step under its own timeout)
-timeout 150 python -m pytest tests/test_gpu_wis.py -m gpu -x -q 2>&1 | tail -4
-echo "tests rc=$?"
-for c in 0 1; do
+for c in 2 4; do
+  CNVB_WIS_CLUSTER=$c timeout 150 python -m pytest tests/test_gpu_wis.py -m gpu -x -q 2>&1 | tail -2
+done
+for c in 2 4; do
   CNVB_WIS_CLUSTER=$c timeout 150 python bench.py --workload cfg5 --targets 300000 --quick --steps 3 --warmup 2 > gpurun_out/cl_$c.json 2> gpurun_out/cl_$c.err
   echo "cluster=$c rc=$?"
   python -c "
