@@ -146,6 +146,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 }
 // kind::f16: D f32 (bit 4), A/B f16 K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | ((kTileCols >> 3) << 17) | ((128u >> 4) << 24);
+// transposed tile: M = the 128 columns of the B tile, N = the 256 rows of the block
+constexpr uint32_t kIdescX = (1u << 4) | ((kTileRows >> 3) << 17) | ((kTileCols >> 4) << 24);
 
 // ---- prep -----------------------------------------------------------------------------------------
 // column sums (f64) and the largest magnitude: a warp walks rows, lanes hold the columns lane + 32 q of
@@ -411,12 +413,13 @@ constexpr int kDefaultCluster = 2;      // CTAs per cluster of the streamed swee
 // refilled when BOTH consumers are done with it: the MMA issuers commit to the stage's empty barrier in
 // both CTAs (multicast commit), which therefore counts two arrivals.  Candidate slots come from the
 // global per-row counter (two CTAs append to the same rows).
-template <bool FIRST, bool STREAM, int CL>
+template <bool FIRST, bool STREAM, int CL, bool XPOSE>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
     constexpr bool CLUSTER = CL > 1;
     static_assert(CL == 1 || CL == 2 || CL == 4, "clusters of 2 or 4 CTAs");
+    static_assert(!XPOSE || (STREAM && !FIRST), "the transposed tile exists for the streamed sweep's later rounds");
     static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
     const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
     const uint32_t blk = blockIdx.x / CL;
@@ -434,6 +437,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
+    __shared__ __align__(16) float4 s_row[XPOSE ? kTileRows : 1];      // XPOSE: per-row operands (q_i, theta_i, kappa_i)
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -447,9 +451,16 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blk * kTileRows;  // position in the sorted row list
-    if (!CLUSTER)
+    if (!CLUSTER && !XPOSE)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
+    if (XPOSE)  // row operands (projection, theta, kappa): constant for the whole launch, read back as broadcasts
+        for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
+            const uint32_t row = row0 + t;
+            const bool live = row < a.rows;
+            s_row[t] = make_float4(live ? a.psorted[a.rows_a ? a.rows_a[row] : row] : 0.0f,
+                                   live ? a.thr[row] : -__int_as_float(0x7f800000), live ? a.kap[row] : 0.0f, 0.0f);
+        }
 
     if (warp == 0 && lane == 0) {
         mbar_init(bar_a_full, 1);
@@ -543,7 +554,18 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         mbar_wait(bar_b_full + 8 * st, ph);
                         tc_fence_after();
                         const uint64_t sd = sdesc0 + (uint64_t)(st * (3u * kTileBytes >> 4));
-                        if (have) {
+                        if (have && XPOSE) {
+                            // one M128 x N256 MMA per K16 slab: the B tile's 128 columns on the M axis, the block's
+                            // 256 rows (two adjacent 16 KB tiles) on the N axis -- 12 KB of operands per 128-cycle
+                            // slot instead of 8 KB per 64-cycle slot
+                            const uint32_t d_tmem = tmem_base + as * kTileRows;
+#pragma unroll
+                            for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                                if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                    tc_mma_f16(d_tmem, sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, sd + 2u * kk, kIdescX,
+                                               (kb | kk) != 0u);
+                            }
+                        } else if (have) {
 #pragma unroll
                             for (uint32_t h = 0; h < 2; ++h) {
                                 const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
@@ -600,6 +622,69 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // and + 128) and the 32 columns [32 (e >> 2), +32) of both accumulators.  With four warps per
         // scheduler the TMEM / L1 latencies of one warp hide behind the compares of the others. =====
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
+        if (XPOSE) {
+            // Transposed tile: TMEM lane = column of the tile (this thread's column j = 32 q + lane), TMEM
+            // column = row of the block; warp e takes the rows [64 cpart, 64 cpart + 64).  The column operands
+            // are two registers per thread; the row operands come from shared memory as broadcasts.
+            uint32_t as = 0, aph = 0;
+            for (uint32_t it = 0; it < n_tiles; ++it) {
+                const uint32_t tile = CNVB_TILE_AT(it);
+                const uint32_t j = tile * kTileCols + q * 32u + lane;
+                const float nj = __ldg(a.nprime + j), pj = __ldg(a.psorted + j);
+                const float smax = __ldg(a.tile_smax + tile);
+                if (it + 1 < n_tiles) {
+                    const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + q * 32u;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
+                }
+                mbar_wait(bar_acc_full + 8 * as, aph);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t r0 = cpart * 64u + (uint32_t)h * 32u;  // first row of this batch within the block
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((q * 32u) << 16) + as * kTileRows + r0, r);
+                    uint32_t gmask = 0u;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float4 ro = s_row[r0 + c];  // (q_i, theta_i, kappa_i): same address for all lanes
+                        const float d = __fsub_rz(pj, ro.x);
+                        const float v = __fmaf_rd(d, d, fmaf(-2.0f, __uint_as_float(r[c]), nj));
+                        r[c] = __float_as_uint(v);
+                        gmask |= (v <= fmaf(ro.z, smax, ro.y)) ? (1u << (c >> 2)) : 0u;
+                    }
+                    const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+                    if (wmask) {  // survivors are rare: the append code runs only for row groups in which some column passes
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            if (wmask & (1u << g4)) {
+#pragma unroll
+                                for (int e4 = 0; e4 < 4; ++e4) {
+                                    const int c = 4 * g4 + e4;
+                                    const float4 ro = s_row[r0 + c];
+                                    const float v = __uint_as_float(r[c]);
+                                    if (v <= fmaf(ro.z, smax, ro.y) && j < a.T) {  // (rows beyond the end: theta = -inf)
+                                        const uint32_t row = row0 + r0 + c;
+                                        const uint32_t slot = atomicAdd(&a.cand_cnt[row], 1u);
+                                        if (slot < kCandCap) {  // beyond: overflow, the row falls back
+                                            a.cand_val[(size_t)row * kCandCap + slot] = v;
+                                            a.cand_idx[(size_t)row * kCandCap + slot] = j;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+                if (++as == 2) {
+                    as = 0;
+                    aph ^= 1u;
+                }
+            }
+        } else {
         uint32_t rloc[2];
         float thr[2], kap[2], qrow[2];
         uint32_t trow[2];  // FIRST: contig of the row (a value no column has for rows beyond the end)
@@ -768,10 +853,11 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 aph ^= 1u;
             }
         }
+        }  // !XPOSE
     }
     tc_fence_before();
     __syncthreads();
-    if (!CLUSTER)
+    if (!CLUSTER && !XPOSE)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
     if (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still send to it
@@ -1329,12 +1415,23 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     }();
     const int cl = !stream_a ? 1 : (cluster_env == 1 || cluster_env == 2 || cluster_env == 4 ? cluster_env : kDefaultCluster);
     if (cl == 4) CNVB_TRY(make_tmap(ctx, subset ? (void *)HA : (void *)H, subset ? rows_pad : Tpad, Kp, &tmap_a, 64));  // quarter loads
-    auto sweep_first = cl == 4 ? wis_sweep_kernel<true, true, 4>
-                     : cl == 2 ? wis_sweep_kernel<true, true, 2>
-                               : (stream_a ? wis_sweep_kernel<true, true, 1> : wis_sweep_kernel<true, false, 1>);
-    auto sweep_next = cl == 4 ? wis_sweep_kernel<false, true, 4>
-                    : cl == 2 ? wis_sweep_kernel<false, true, 2>
-                              : (stream_a ? wis_sweep_kernel<false, true, 1> : wis_sweep_kernel<false, false, 1>);
+    // Later rounds of the streamed sweep on transposed tiles (one M128 x N256 MMA per K16 slab, rows on the N
+    // axis; see the kernel).  Measured at both ends: 300 000 x 1000 targets, sweeps of ~10 ms at full clock:
+    // 40.3 against 36.5 ms (its epilogue fetches the row operands per pair); 3 000 000 x 1000, seconds under
+    // the power cap: 3.40 against 3.63 s (886 TFLOP/s executed; a third less shared-memory operand traffic per
+    // flop).  So it is used for large panels; CNVB_WIS_XPOSE = 0 / 1 forces the choice.
+    static const int xpose_env = [] {
+        const char *e = getenv("CNVB_WIS_XPOSE");
+        return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }();
+    const bool xp = stream_a && (xpose_env >= 0 ? xpose_env == 1 : T >= 1000000u);
+    auto sweep_first = cl == 4 ? wis_sweep_kernel<true, true, 4, false>
+                     : cl == 2 ? wis_sweep_kernel<true, true, 2, false>
+                               : (stream_a ? wis_sweep_kernel<true, true, 1, false> : wis_sweep_kernel<true, false, 1, false>);
+    auto sweep_next = cl == 4 ? (xp ? wis_sweep_kernel<false, true, 4, true> : wis_sweep_kernel<false, true, 4, false>)
+                    : cl == 2 ? (xp ? wis_sweep_kernel<false, true, 2, true> : wis_sweep_kernel<false, true, 2, false>)
+                    : stream_a ? (xp ? wis_sweep_kernel<false, true, 1, true> : wis_sweep_kernel<false, true, 1, false>)
+                               : wis_sweep_kernel<false, false, 1, false>;
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     BoundConsts bc{};
