@@ -1408,7 +1408,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
     // streamed sweep: the CTAs of a cluster share their rows' operand through TMA multicast
     // (CNVB_WIS_CLUSTER = 1: one CTA per block, 2 or 4: CTAs per cluster)
-    static const int cluster_env = [] {
+    const int cluster_env = [] {  // (read at every call: the tests switch it)
         const char *e = getenv("CNVB_WIS_CLUSTER");
         const int v = e ? atoi(e) : -1;
         return v == 0 ? 1 : v;
@@ -1420,7 +1420,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     // 40.3 against 36.5 ms (its epilogue fetches the row operands per pair); 3 000 000 x 1000, seconds under
     // the power cap: 3.40 against 3.63 s (886 TFLOP/s executed; a third less shared-memory operand traffic per
     // flop).  So it is used for large panels; CNVB_WIS_XPOSE = 0 / 1 forces the choice.
-    static const int xpose_env = [] {
+    const int xpose_env = [] {
         const char *e = getenv("CNVB_WIS_XPOSE");
         return e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }();

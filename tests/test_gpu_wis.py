@@ -208,6 +208,28 @@ def test_wis_tensor_low_efficiency_rows_many_samples(oracle, ctx):
     assert st["rescored_pairs"] < 4 * T * k, st
 
 
+@pytest.mark.parametrize("cluster,xpose", [(1, 0), (1, 1), (2, 1), (4, 0), (4, 1)])
+def test_wis_streamed_sweep_variants(oracle, ctx, monkeypatch, cluster, xpose):
+    """The forms of the streamed sweep that the defaults do not pick at test sizes -- one CTA per row block,
+    clusters of four, transposed M128 x N256 tiles (the default from 10^6 targets) -- against the oracle."""
+    monkeypatch.setenv("CNVB_WIS_CLUSTER", str(cluster))
+    monkeypatch.setenv("CNVB_WIS_XPOSE", str(xpose))
+    T, S, k = 5300, 200, 40
+    X, tids = synth.synth_panel(900 + cluster * 10 + xpose, T, S, n_contigs=6)
+    X[21] *= 3.0
+    X[30] = X[31]
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
+    dist, idx = mw.compute_distances(_dev(X), _dev(tids), opts, ctx=ctx)
+    st = mw.last_stats(ctx)
+    assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
+    assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
+    assert st["fallback_rows"] == 0, st
+    lo, hi = 333, 333 + 2100   # a row block off the tile boundaries
+    d2, i2 = mw.compute_distances(X, tids, opts, row_begin=lo, row_end=hi, ctx=ctx)
+    assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
+
+
 def test_wis_tensor_single_contig_and_tiny_other_contig(oracle, ctx):
     T, S, k = 4500, 20, 50
     X, _ = synth.synth_panel(77, T, S, n_contigs=1)
