@@ -124,6 +124,8 @@ SYMBOLS = {
     "cnvb_hmm_segment": (_int, [_vp, _vp, _vp, _u32, _vp, C.POINTER(HmmOpts), _vp, _vp, _int]),
     "cnvb_modcov": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
     "cnvb_modcov_panel": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
+    "cnvb_wis_calls_modcov_panel": (_int, [_vp, _vp, _u32, _u32, _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _int]),
 }
 
 _lib = None

@@ -378,20 +378,39 @@ struct PanelOut {
     uint8_t *status;
 };
 
+// CALLS: the per-probe call counts of build-model-wis (count_per_probe_calls, lib.rs:235-271) come out of the
+// same pass -- both stages gather the same reference rows and form the same mean / sd, and at cohort scale
+// the gathers (1.2 TB at config 5) are all there is.  The model filters are not known yet in that case
+// (UNRELIABLE depends on the counts): values are written for every target with enough reference targets
+// and modcov_mask_kernel blanks the filtered ones afterwards.
+struct PanelCalls {
+    uint32_t min_ref;
+    double zthr, rel_thr;
+    uint32_t *num_calls;
+};
+
+template <bool CALLS>
 __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float *__restrict__ X, uint32_t S,
                                                                      uint32_t row_begin, uint32_t rows,
                                                                      const uint8_t *__restrict__ model_filt,
                                                                      const uint32_t *__restrict__ ref_idx,
                                                                      const uint32_t *__restrict__ ref_len, uint32_t k,
-                                                                     PanelOut o) {
+                                                                     PanelOut o, PanelCalls pc) {
     extern __shared__ uint32_t s_ref[];  // [kPanelGroup][k]
-    __shared__ uint32_t s_len[kPanelGroup];
+    __shared__ uint32_t s_len[kPanelGroup], s_calls[kPanelGroup];
     __shared__ float s_out[5][32][kPanelGroup + 1];  // [value][sample in chunk][target]
     __shared__ uint8_t s_st[32][kPanelGroup + 4];
     const uint32_t r0 = blockIdx.x * kPanelGroup;  // relative to row_begin, like every per-row argument
     const uint32_t groups = min(kPanelGroup, rows - r0);
-    for (uint32_t g = threadIdx.x; g < kPanelGroup; g += blockDim.x)
-        s_len[g] = (g < groups && model_filt[r0 + g] == 0) ? ref_len[r0 + g] : 0u;  // lib.rs:104-113, :146
+    for (uint32_t g = threadIdx.x; g < kPanelGroup; g += blockDim.x) {
+        if (CALLS) {  // lib.rs:254-256: targets with fewer than min_ref_targets reference targets take no part
+            const uint32_t m = g < groups ? ref_len[r0 + g] : 0u;
+            s_len[g] = (m >= pc.min_ref) ? m : 0u;
+            s_calls[g] = 0u;
+        } else {
+            s_len[g] = (g < groups && model_filt[r0 + g] == 0) ? ref_len[r0 + g] : 0u;  // lib.rs:104-113, :146
+        }
+    }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < groups * k; e += blockDim.x) {
         const uint32_t g = e / k, q = e - g * k;
@@ -405,6 +424,7 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
             uint8_t st = 0;
             float o_mean = f32_missing(), o_sd = f32_missing(), o_rel = f32_missing(), o_z = f32_missing(),
                   o_cv2 = f32_missing();
+            double o_zd = 0.0, o_reld = 1.0;  // CALLS: the f64 values behind cvz / cv_rel
             const uint32_t m = s_len[g];
             if (m > 0 && sm < S) {
                 const uint32_t *ref = s_ref + g * k;
@@ -440,11 +460,18 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
                 o_sd = (float)sd;
                 o_rel = (float)rel;
                 o_z = (float)zs;
+                o_zd = zs;
+                o_reld = rel;
                 st = CNVB_MODCOV_HAS_INFO;
                 if (isfinite(rel)) {  // lib.rs:223-232
                     o_cv2 = rel == 0.0 ? f32_missing() : (float)log2(rel);
                     st |= CNVB_MODCOV_CV2;
                 }
+            }
+            if (CALLS) {  // lib.rs:260-266 (|x - mean| / sd = |(x - mean) / sd| bit for bit)
+                const bool hit = (st & CNVB_MODCOV_HAS_INFO) && fabs((double)o_zd) > pc.zthr && fabs(__dsub_rn(o_reld, 1.0)) > pc.rel_thr;
+                const uint32_t n_hit = __popc(__ballot_sync(0xffffffffu, hit));
+                if (lane == 0 && n_hit) atomicAdd(&s_calls[g], n_hit);
             }
             s_out[0][lane][g] = o_mean;
             s_out[1][lane][g] = o_sd;
@@ -467,6 +494,19 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
         }
         __syncthreads();
     }
+    if (CALLS)
+        for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) pc.num_calls[r0 + g] = s_calls[g];
+}
+
+// after the fused pass: targets whose model record carries a filter have no probe info (lib.rs:104-113)
+__global__ void modcov_mask_kernel(const uint8_t *__restrict__ filt, uint32_t rows, uint64_t n, PanelOut o) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || filt[i % rows] == 0) return;
+    float *const outs[5] = {o.ref_mean, o.ref_sd, o.cv_rel, o.cvz, o.cv2};
+#pragma unroll
+    for (int v = 0; v < 5; ++v)
+        if (outs[v]) outs[v][i] = f32_missing();
+    if (o.status) o.status[i] = 0;
 }
 
 }  // namespace
@@ -780,10 +820,10 @@ extern "C" int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint
         const PanelOut po{o1.p, o2.p, o3.p, o4.p, o5.p, os.p};
         const size_t smem = (size_t)kPanelGroup * k * sizeof(uint32_t);
         if (smem > 24 * 1024)
-            CNVB_CUDA(ctx, cudaFuncSetAttribute(modcov_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            CNVB_CUDA(ctx, cudaFuncSetAttribute(modcov_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "smem opt-in");
-        modcov_panel_kernel<<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, smem, ctx->stream>>>(
-            dx.p, S, row_begin, rows, dmf.p, di.p, dl.p, k, po);
+        modcov_panel_kernel<false><<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, smem, ctx->stream>>>(
+            dx.p, S, row_begin, rows, dmf.p, di.p, dl.p, k, po, PanelCalls{});
     }
     CNVB_LAUNCHED(ctx, "modcov_panel_kernel");
     CNVB_TRY(o1.download());
@@ -793,6 +833,69 @@ extern "C" int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint
     CNVB_TRY(o5.download());
     CNVB_TRY(os.download());
     if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "modcov panel");
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_wis_calls_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, const uint32_t *ref_idx,
+                                           const uint32_t *ref_len, uint32_t k, const cnvb_wis_opts *opts,
+                                           uint32_t row_begin, uint32_t row_end, uint32_t *num_calls, uint8_t *filt,
+                                           float *ref_mean, float *ref_sd, float *cv_rel, float *cvz, float *cv2,
+                                           uint8_t *status, int mem) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (!opts || row_end > T || row_begin > row_end || k > kMaxK)
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_calls_modcov_panel: bad argument");
+    const uint32_t rows = row_end - row_begin;
+    if (rows && S && (!X || !ref_idx || !ref_len || !num_calls || !filt))
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_calls_modcov_panel: null argument");
+    if (rows == 0) return CNVB_OK;
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const size_t n = (size_t)rows * S;
+    DevIn<float> dx;
+    DevIn<uint32_t> di, dl;
+    DevOut<uint32_t> oc;
+    DevOut<uint8_t> of, os;
+    DevOut<float> o1, o2, o3, o4, o5;
+    CNVB_TRY(dx.init(ctx, X, (size_t)T * S, mem, "uploading the CV panel"));
+    CNVB_TRY(di.init(ctx, ref_idx, (size_t)rows * k, mem, "uploading reference targets"));
+    CNVB_TRY(dl.init(ctx, ref_len, rows, mem, "uploading reference target counts"));
+    CNVB_TRY(oc.init(ctx, num_calls, rows, mem, "allocating outputs"));
+    CNVB_TRY(of.init(ctx, filt, rows, mem, "allocating outputs"));
+    CNVB_TRY(o1.init(ctx, ref_mean, n, mem, "allocating outputs"));
+    CNVB_TRY(o2.init(ctx, ref_sd, n, mem, "allocating outputs"));
+    CNVB_TRY(o3.init(ctx, cv_rel, n, mem, "allocating outputs"));
+    CNVB_TRY(o4.init(ctx, cvz, n, mem, "allocating outputs"));
+    CNVB_TRY(o5.init(ctx, cv2, n, mem, "allocating outputs"));
+    CNVB_TRY(os.init(ctx, status, n, mem, "allocating outputs"));
+    const PanelOut po{o1.p, o2.p, o3.p, o4.p, o5.p, os.p};
+    if (S == 0) {
+        CNVB_CUDA(ctx, cudaMemsetAsync(oc.p, 0, rows * sizeof(uint32_t), ctx->stream), "clearing the call counts");
+    } else {
+        KernelSpan span(ctx, "modcov_panel_kernel");
+        const size_t smem = (size_t)kPanelGroup * k * sizeof(uint32_t);
+        if (smem > 24 * 1024)
+            CNVB_CUDA(ctx, cudaFuncSetAttribute(modcov_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "smem opt-in");
+        const PanelCalls pc{opts->min_ref_targets, opts->filter_z_score, opts->filter_rel, oc.p};
+        modcov_panel_kernel<true><<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, smem, ctx->stream>>>(
+            dx.p, S, row_begin, rows, nullptr, di.p, dl.p, k, po, pc);
+    }
+    CNVB_LAUNCHED(ctx, "modcov_panel_kernel");
+    wis_filters_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(dl.p, oc.p, rows, opts->min_ref_targets,
+                                                                    opts->max_samples_reliable, of.p);
+    CNVB_LAUNCHED(ctx, "wis_filters_kernel");
+    if (n) {
+        modcov_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(of.p, rows, n, po);
+        CNVB_LAUNCHED(ctx, "modcov_mask_kernel");
+    }
+    CNVB_TRY(oc.download());
+    CNVB_TRY(of.download());
+    CNVB_TRY(o1.download());
+    CNVB_TRY(o2.download());
+    CNVB_TRY(o3.download());
+    CNVB_TRY(o4.download());
+    CNVB_TRY(o5.download());
+    CNVB_TRY(os.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "calls + modcov panel");
     return CNVB_OK;
 }
 

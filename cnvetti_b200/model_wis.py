@@ -190,3 +190,30 @@ def mod_coverage_panel(X, model_filt, ref_idx, ref_len, want=("cv_rel", "cvz"), 
     ctx.check(N.lib().cnvb_modcov_panel(ctx.handle, px, T, S, row_begin, row_end, pf, pi, pl, k,
                                         *[buf(outs[n])[0] for n in names], mem))
     return {n: v.reshape(S, rows) for n, v in outs.items() if v is not None}
+
+
+def calls_and_mod_coverage_panel(X, ref_idx, ref_len, options=None, want=("cv_rel", "cvz"), row_begin=0, row_end=None,
+                                 ctx=None):
+    """count_per_probe_calls + model filters + mod_coverage_panel in one pass over the panel (calling a cohort
+    against the model built from it).  Returns (num_calls, filt, {name: [S][rows] array})."""
+    ctx = ctx or default_context()
+    options = options or BuildModelWisOptions()
+    px, mx, kx = buf(X, np.float32)
+    pi, mi, ki = buf(ref_idx, None if hasattr(ref_idx, "is_cuda") else np.uint32)
+    pl, ml, kl = buf(ref_len, None if hasattr(ref_len, "is_cuda") else np.uint32)
+    mem = same_mem(mx, mi, ml)
+    T, S, k = int(kx.shape[0]), int(kx.shape[1]), int(ki.shape[1])
+    row_end = T if row_end is None else row_end
+    rows = row_end - row_begin
+    names = ("ref_mean", "ref_sd", "cv_rel", "cvz", "cv2", "status")
+    unknown = set(want) - set(names)
+    if unknown:
+        raise ValueError("unknown outputs: %s" % sorted(unknown))
+    calls = ctx.empty(rows, np.int32 if mem == N.MEM_DEVICE else np.uint32, mem)
+    filt = ctx.empty(rows, np.uint8, mem)
+    outs = {n: (ctx.empty(S * rows, np.uint8 if n == "status" else np.float32, mem) if n in want else None)
+            for n in names}
+    o = options.c_opts()
+    ctx.check(N.lib().cnvb_wis_calls_modcov_panel(ctx.handle, px, T, S, pi, pl, k, C.byref(o), row_begin, row_end,
+                                                  buf(calls)[0], buf(filt)[0], *[buf(outs[n])[0] for n in names], mem))
+    return calls, filt, {n: v.reshape(S, rows) for n, v in outs.items() if v is not None}

@@ -99,6 +99,11 @@ class CudaWisBackend:
         return self.mw.mod_coverage_panel(X, filt, ref_idx, ref_len, want=("cv_rel", "cvz"), row_begin=lo,
                                           row_end=hi, ctx=self.ctx)
 
+    def calls_modcov_panel(self, X, ref_idx, ref_len, options, lo, hi):
+        """per-probe calls, filters and mod-coverage of the cohort in one pass -> (calls, filt, dict)"""
+        return self.mw.calls_and_mod_coverage_panel(X, ref_idx, ref_len, options, want=("cv_rel", "cvz"), row_begin=lo,
+                                                    row_end=hi, ctx=self.ctx)
+
     def segment(self, cv_flat, lane_off, sigma, options):
         from . import discover
         return discover.hmm_segment(cv_flat, lane_off, sigma, options, ctx=self.ctx)
@@ -126,11 +131,13 @@ def wis_run_distributed(X_block, tids_block, options, backend=None, group=None):
     return wis_rows_distributed(X, tids, options, lo, hi, backend=backend, group=group)
 
 
-def wis_rows_distributed(X, tids, options, lo, hi, backend=None, group=None):
+def wis_rows_distributed(X, tids, options, lo, hi, backend=None, group=None, with_modcov=False):
     """The part of `build-model-wis` after the panel exchange: every rank holds the whole panel
     X[T][S] and computes the model of its target rows [lo, hi) (row blocks in rank order).  The
     one exchange is the all-gather of the nearest distance of every target, from which all ranks
-    derive the same prune threshold."""
+    derive the same prune threshold.  with_modcov: the cohort is called against its own model, and a
+    backend that can do so forms the per-probe calls and the mod-coverage values in one pass over the
+    panel (key "modcov" of the result)."""
     rank, world = _world(group)
     backend = backend or CudaWisBackend()
     dist_, idx = backend.distances(X, tids, options, lo, hi)
@@ -143,10 +150,14 @@ def wis_rows_distributed(X, tids, options, lo, hi, backend=None, group=None):
         nearest = nearest_local
     thr = backend.threshold(nearest, options.filter_z_score)   # identical on every rank
     ref_idx, ref_len = backend.prune(dist_, idx, thr)
-    calls = backend.calls(X, ref_idx, ref_len, options, lo, hi)
-    filt = backend.filters(ref_len, calls, options)
+    modcov = None
+    if with_modcov and hasattr(backend, "calls_modcov_panel"):
+        calls, filt, modcov = backend.calls_modcov_panel(X, ref_idx, ref_len, options, lo, hi)
+    else:
+        calls = backend.calls(X, ref_idx, ref_len, options, lo, hi)
+        filt = backend.filters(ref_len, calls, options)
     return dict(ref_dist=dist_, ref_idx=ref_idx, ref_len=ref_len, num_calls=calls, filt=filt,
-                threshold=thr, rows=(lo, hi))
+                threshold=thr, rows=(lo, hi), modcov=modcov)
 
 
 def exchange_rows_to_samples(block, sample_ranges, group=None):

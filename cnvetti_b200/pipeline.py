@@ -249,9 +249,11 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
     del cv
     t0 = mark("merge_cov", t0)
     lo, hi = parallel.shard_rows(T, rank, world)
-    m = parallel.wis_rows_distributed(X, tids, wis_options, lo, hi, backend=backend, group=group)
+    m = parallel.wis_rows_distributed(X, tids, wis_options, lo, hi, backend=backend, group=group, with_modcov=True)
     t0 = mark("build_model_wis", t0)
-    mc = backend.modcov_panel(X, m["filt"], m["ref_idx"], m["ref_len"], lo, hi)
+    mc = m.pop("modcov")  # (the CUDA backend forms the per-probe calls and these values in one pass)
+    if mc is None:
+        mc = backend.modcov_panel(X, m["filt"], m["ref_idx"], m["ref_len"], lo, hi)
     t0 = mark("mod_coverage", t0)
     rel = parallel.exchange_rows_to_samples(mc["cv_rel"], sample_ranges, group=group)  # [S_r][T]
     t0 = mark("exchange", t0)

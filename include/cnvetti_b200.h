@@ -361,6 +361,17 @@ int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, uin
                       uint32_t row_end, const uint8_t *model_filt, const uint32_t *ref_idx,
                       const uint32_t *ref_len, uint32_t k, float *ref_mean, float *ref_sd,
                       float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem);
+/* count_per_probe_calls (lib-model-wis/src/lib.rs:235-271), the FILTER column (:362-377) and
+ * cnvb_modcov_panel in one pass over the panel, for calling a cohort against the model built from
+ * it: the two stages gather the same reference rows and form the same mean / sd, and at cohort
+ * scale the gathers are the cost.  num_calls / filt are what cnvb_wis_calls + cnvb_wis_filters give
+ * for rows [row_begin, row_end); the value outputs (each may be NULL) are those of
+ * cnvb_modcov_panel with model_filt = filt. */
+int cnvb_wis_calls_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S,
+                                const uint32_t *ref_idx, const uint32_t *ref_len, uint32_t k,
+                                const cnvb_wis_opts *opts, uint32_t row_begin, uint32_t row_end,
+                                uint32_t *num_calls, uint8_t *filt, float *ref_mean, float *ref_sd,
+                                float *cv_rel, float *cvz, float *cv2, uint8_t *status, int mem);
 
 /* ---- lib-discover (builder-defined: the reference has no implementation, only the CLI stub
  * cnvetti/src/cli.yaml:457-469 and `bail!("cmd discover not implemented!")`,

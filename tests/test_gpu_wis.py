@@ -208,6 +208,38 @@ def test_wis_tensor_low_efficiency_rows_many_samples(oracle, ctx):
     assert st["rescored_pairs"] < 4 * T * k, st
 
 
+@pytest.mark.parametrize("T,S,device,min_ref,max_rel", [(3000, 40, True, 10, 1), (777, 70, False, 0, 0), (40, 33, True, 3, 4)])
+def test_calls_and_modcov_in_one_pass(oracle, ctx, T, S, device, min_ref, max_rel):
+    """cnvb_wis_calls_modcov_panel = count_per_probe_calls + FILTER + mod-coverage of the cohort: identical to
+    the separate stages (which are held against the oracle elsewhere), bit for bit."""
+    X, tids = synth.synth_panel(61 + T, T, S, n_contigs=6)
+    rng = np.random.default_rng(T)
+    X[rng.integers(0, T, T // 20), rng.integers(0, S, T // 20)] *= 3.0   # outliers: calls
+    k = min(T, 50)
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=4)
+    _, ridx, rlen = oracle.wis_prune(odist, oidx, z=2.0)
+    rlen[rng.integers(0, T, 7)] = 0
+    rlen[rng.integers(0, T, 7)] = 2
+    opts = mw.BuildModelWisOptions(filter_z_score=2.5, filter_rel=0.1, min_ref_targets=min_ref, max_samples_reliable=max_rel)
+    conv = _dev if device else (lambda a: a)
+    names = ("ref_mean", "ref_sd", "cv_rel", "cvz", "cv2", "status")
+    calls, filt, g = mw.calls_and_mod_coverage_panel(conv(X), conv(ridx), conv(rlen), opts, want=names, ctx=ctx)
+    calls0 = mw.count_per_probe_calls(conv(X), conv(ridx), conv(rlen), opts, ctx=ctx)
+    filt0 = mw.model_filters(conv(rlen), calls0, opts, ctx=ctx)
+    g0 = mw.mod_coverage_panel(conv(X), filt0, conv(ridx), conv(rlen), want=names, ctx=ctx)
+    ocalls = oracle.wis_calls(X, ridx, rlen, min_ref, 2.5, 0.1)
+    assert np.array_equal(to_np(calls0).astype(np.uint32), ocalls) and ocalls.sum() > 0
+    assert np.array_equal(to_np(calls).astype(np.uint32), ocalls)
+    assert np.array_equal(to_np(filt), to_np(filt0)) and (to_np(filt) != 0).any() and (to_np(filt) == 0).any()
+    for key in names:
+        a, b = to_np(g[key]), to_np(g0[key])
+        assert np.array_equal(a.view(np.uint8 if key == "status" else np.uint32), b.view(np.uint8 if key == "status" else np.uint32)), key
+    lo, hi = T // 4, T - 3
+    c2, f2, h = mw.calls_and_mod_coverage_panel(X, ridx[lo:hi], rlen[lo:hi], opts, want=("cvz",), row_begin=lo, row_end=hi, ctx=ctx)
+    assert np.array_equal(c2, ocalls[lo:hi]) and np.array_equal(f2, to_np(filt)[lo:hi])
+    assert np.array_equal(h["cvz"].view(np.uint32), to_np(g["cvz"])[:, lo:hi].view(np.uint32))
+
+
 @pytest.mark.parametrize("cluster,xpose", [(1, 0), (1, 1), (2, 1), (4, 0), (4, 1)])
 def test_wis_streamed_sweep_variants(oracle, ctx, monkeypatch, cluster, xpose):
     """The forms of the streamed sweep that the defaults do not pick at test sizes -- one CTA per row block,
