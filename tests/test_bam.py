@@ -187,3 +187,43 @@ def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
     assert has.sum() > 100
     np.testing.assert_allclose(r2["format"]["CV"][has], cv[has], rtol=1e-5)
     assert np.array_equal(r2["pos"], r["pos"]) and r2["id"] == r["id"]
+
+
+def test_bam_decode_property_random_records(tmp_path):
+    """Randomised records (hypothesis): arbitrary flags / mapq / template lengths, CIGARs of every operator
+    mix and length, positions in file order over several contigs -- file path == array path."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    cigar_op = st.tuples(st.integers(0, 1 << 20), st.integers(0, 8))
+    record = st.tuples(st.integers(0, 2_000_000), st.integers(-5000, 5000), st.integers(0, 4095), st.integers(0, 255),
+                       st.lists(cigar_op, min_size=0, max_size=6))
+    counter = [0]
+
+    @settings(max_examples=20, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.lists(record, min_size=0, max_size=40), min_size=1, max_size=4), st.floats(0.0, 1.0, width=32))
+    def run(per_contig, min_unclipped):
+        recs = {}
+        for tid, rows in enumerate(per_contig):
+            if not rows:
+                continue
+            rows = sorted(rows, key=lambda r: r[0])
+            cig, off = [], [0]
+            for r in rows:
+                cig += [(n << 4) | o for n, o in r[4]]
+                off.append(len(cig))
+            recs[tid] = dict(pos=np.array([r[0] for r in rows], np.int32), isize=np.array([r[1] for r in rows], np.int32),
+                             flag=np.array([r[2] for r in rows], np.uint16), mapq=np.array([r[3] for r in rows], np.uint8),
+                             cigar_off=np.array(off, np.uint64), cigar=np.array(cig, np.uint32))
+        counter[0] += 1
+        path = synth.write_bam(str(tmp_path / ("p%d.bam" % counter[0])), [("c%d" % i, 3_000_000) for i in range(len(per_contig))],
+                               recs, read_len=10, block_payload=700)
+        with bam.BamReader(path, threads=2) as r:
+            r.decode(min_unclipped=min_unclipped, pinned=False)
+            assert r.stats()["records"] == sum(len(v["pos"]) for v in recs.values())
+            for tid in range(len(per_contig)):
+                if tid in recs:
+                    _check(r.fetch(tid), _expected(recs[tid], min_unclipped))
+                else:
+                    assert len(r.fetch(tid)) == 0
+
+    run()
