@@ -438,6 +438,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
     __shared__ __align__(16) float4 s_row[XPOSE ? kTileRows : 1];      // XPOSE: per-row operands (q_i, theta_i, kappa_i)
+    __shared__ __align__(16) float2 s_rq[XPOSE ? kEpiWarps : 1][64];   // XPOSE: per warp and tile, (q_i, theta_i + kappa_i smax)
     // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
@@ -627,11 +628,17 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // column = row of the block; warp e takes the rows [64 cpart, 64 cpart + 64).  The column operands
             // are two registers per thread; the row operands come from shared memory as broadcasts.
             uint32_t as = 0, aph = 0;
+            // this warp's 64 rows: two per lane, kept in registers; per tile the lanes publish (q_i, theta_i +
+            // kappa_i smax) to the warp's strip, and the pairs of two rows come back as one broadcast LDS.128
+            const float4 ro0 = s_row[cpart * 64u + lane], ro1 = s_row[cpart * 64u + 32u + lane];
             for (uint32_t it = 0; it < n_tiles; ++it) {
                 const uint32_t tile = CNVB_TILE_AT(it);
                 const uint32_t j = tile * kTileCols + q * 32u + lane;
                 const float nj = __ldg(a.nprime + j), pj = __ldg(a.psorted + j);
                 const float smax = __ldg(a.tile_smax + tile);
+                s_rq[e][lane] = make_float2(ro0.x, fmaf(ro0.z, smax, ro0.y));
+                s_rq[e][32u + lane] = make_float2(ro1.x, fmaf(ro1.z, smax, ro1.y));
+                __syncwarp();
                 if (it + 1 < n_tiles) {
                     const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + q * 32u;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
@@ -646,12 +653,15 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tc_ld32(tmem_base + ((q * 32u) << 16) + as * kTileRows + r0, r);
                     uint32_t gmask = 0u;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float4 ro = s_row[r0 + c];  // (q_i, theta_i, kappa_i): same address for all lanes
-                        const float d = __fsub_rz(pj, ro.x);
-                        const float v = __fmaf_rd(d, d, fmaf(-2.0f, __uint_as_float(r[c]), nj));
-                        r[c] = __float_as_uint(v);
-                        gmask |= (v <= fmaf(ro.z, smax, ro.y)) ? (1u << (c >> 2)) : 0u;
+                    for (int c = 0; c < 32; c += 2) {
+                        // (q, rhs) of rows c and c + 1: same address for all lanes
+                        const float4 two = *reinterpret_cast<const float4 *>(&s_rq[e][32 * h + c]);
+                        const float d0 = __fsub_rz(pj, two.x), d1 = __fsub_rz(pj, two.z);
+                        const float v0 = __fmaf_rd(d0, d0, fmaf(-2.0f, __uint_as_float(r[c]), nj));
+                        const float v1 = __fmaf_rd(d1, d1, fmaf(-2.0f, __uint_as_float(r[c + 1]), nj));
+                        r[c] = __float_as_uint(v0);
+                        r[c + 1] = __float_as_uint(v1);
+                        gmask |= (v0 <= two.y || v1 <= two.w) ? (1u << (c >> 2)) : 0u;
                     }
                     const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
                     if (wmask) {  // survivors are rare: the append code runs only for row groups in which some column passes
@@ -661,9 +671,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                                 for (int e4 = 0; e4 < 4; ++e4) {
                                     const int c = 4 * g4 + e4;
-                                    const float4 ro = s_row[r0 + c];
                                     const float v = __uint_as_float(r[c]);
-                                    if (v <= fmaf(ro.z, smax, ro.y) && j < a.T) {  // (rows beyond the end: theta = -inf)
+                                    if (v <= s_rq[e][32 * h + c].y && j < a.T) {  // (rows beyond the end: theta = -inf)
                                         const uint32_t row = row0 + r0 + c;
                                         const uint32_t slot = atomicAdd(&a.cand_cnt[row], 1u);
                                         if (slot < kCandCap) {  // beyond: overflow, the row falls back
