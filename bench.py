@@ -192,6 +192,28 @@ def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468):
                                                "pinned columns; best of 3; not part of value / e2e"}
 
 
+def file_level_leg(n_pairs=1_000_000, contig_len=50_818_468):
+    """`cmd coverage` at file level (pipeline.cmd_coverage): synthetic BAM in, coverage VCF out, with the host
+    decode, the device part and the VCF write timed apart (second run of two: buffers and pools are warm)."""
+    import tempfile
+    from cnvetti_b200 import pipeline, synth
+    import cnvetti_b200 as cb
+    scale = n_pairs / 7_600_000.0
+    L = max(100_000, int(contig_len * scale))
+    d = synth.synth_bam_records(22, L, n_pairs)
+    opts = cb.CoverageOptions(window_length=1000, min_mapq=MIN_MAPQ)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("22", L)], [d])
+        out = os.path.join(tmp, "cov.vcf.gz")
+        timings = None
+        for _ in range(2):
+            table, timings = pipeline.cmd_coverage(path, out, opts)
+        return {"reads": 2 * n_pairs, "windows": table.offsets[-1], "bam_bytes": os.path.getsize(path),
+                "vcf_bytes": os.path.getsize(out), "seconds": {k: round(v, 5) for k, v in timings.items()},
+                "what": "BAM decode on host threads | region loop on the GPU from pinned columns (incl. H2D) | "
+                        "VCF formatting + BGZF on host threads"}
+
+
 # ---------------------------------------------------------------------------------------------
 def cpu_reference_leg(sample, steps, warmup):
     """Times the oracle (restated reference CPU path) on the sample: coverage (Fragments,
@@ -631,7 +653,8 @@ def bench_cfg1(args):
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_read": 11,
                          "note": "whole region call, not a single kernel"},
             "cpu_baseline": cpu, "clocks": clocks, "kinds": res,
-            "host_bam_decode": host_bam_decode_leg() if not args.quick else None}
+            "host_bam_decode": host_bam_decode_leg() if not args.quick else None,
+            "file_level": file_level_leg() if not args.quick else None}
     print(json.dumps(line))
     return 0
 
