@@ -299,11 +299,12 @@ def read_fasta(path):
 
 
 def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(chr)?\d\d?$", targets=None, ctx=None,
-                 threads=0, command_line=None):
-    """`cnvetti cmd coverage --input X.bam --output Y.vcf[.gz] [--reference R.fa] ...` (lib_coverage::run,
-    lib-coverage/src/lib.rs:679-795, without pile masking): BAM decode on host threads, the region loop on
-    the GPU, the coverage VCF written on host threads.  Returns (table, timings) with the host decode /
-    device / write times apart."""
+                 threads=0, command_line=None, mask_piles=False, mask_piles_fdr=0.0001, pile_max_gap=20):
+    """`cnvetti cmd coverage --input X.bam --output Y.vcf[.gz] [--reference R.fa] [--mask-piles] ...`
+    (lib_coverage::run, lib-coverage/src/lib.rs:679-795): BAM decode on host threads, with --mask-piles the
+    pile collection and its FDR threshold (gather_piles, :353-419), the region loop on the GPU, the coverage
+    VCF written on host threads.  Returns (table, timings) with the host decode / device / write times
+    apart."""
     import time
     import torch
     from . import bam as bam_mod
@@ -324,6 +325,12 @@ def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(ch
             missing = [r.name for r in regions if r.sequence is None]
             if missing:
                 raise N.CnvbError(N.ERR_INVALID, "Could not load reference sequence for %s" % missing[0])
+        if mask_piles:  # (lib.rs:755-764: whatever the count kind; only the genome-wide fragment counter uses them)
+            from . import piles as piles_mod
+            masks, _ = piles_mod.gather_piles(regions, min_mapq=options.min_mapq, pile_max_gap=pile_max_gap,
+                                              mask_piles_fdr=mask_piles_fdr, ctx=ctx)
+            for r, m in zip(regions, masks):
+                r.piles = m
         table = coverage_run(regions, options, ctx=ctx)
         torch.cuda.synchronize()
         timings["device"] = time.perf_counter() - t0

@@ -147,7 +147,7 @@ def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
     """The two commands of the path at file level: BAM (+ FASTA) in, coverage VCF out, normalised VCF out;
     the values in the files are the oracle's (text precision of %g for the floats)."""
     from cnvetti_b200 import pipeline, vcf
-    from util import oracle_reads
+    from util import oracle_reads, to_np as to_np3
     ctx = cb.Context(0)
     lens = (300_000, 200_000)
     names = ("chr1", "chr2")
@@ -187,6 +187,24 @@ def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
     assert has.sum() > 100
     np.testing.assert_allclose(r2["format"]["CV"][has], cv[has], rtol=1e-5)
     assert np.array_equal(r2["pos"], r["pos"]) and r2["id"] == r["id"]
+    # --mask-piles: the file-level driver == pile collection + region loop on the decoded regions
+    from cnvetti_b200 import piles as piles_mod
+    # (a sparse BAM: isolated piles of depth 1 and 2 are what the Poisson fit of compute_threshold needs)
+    sparse = [synth.synth_bam_records(51 + i, L, 6_000) for i, L in enumerate(lens)]
+    bam_path = synth.write_bam(str(tmp_path / "sparse.bam"), list(zip(names, lens)), sparse, sample="S2")
+    opts = cb.CoverageOptions(window_length=500, min_mapq=0)
+    out3 = str(tmp_path / "masked.vcf")
+    t3, _ = pipeline.cmd_coverage(bam_path, out3, opts, ctx=ctx, mask_piles=True, mask_piles_fdr=0.01)
+    with bam.BamReader(bam_path) as rd:
+        rd.decode(min_unclipped=opts.min_unclipped, pinned=False)
+        regs = rd.regions()
+        masks, thresh = piles_mod.gather_piles(regs, min_mapq=opts.min_mapq, mask_piles_fdr=0.01, ctx=ctx)
+        for g_, m_ in zip(regs, masks):
+            g_.piles = m_
+        t4 = pipeline.coverage_run(regs, opts, ctx=ctx)
+    assert sum(len(m_[0]) for m_ in masks) > 0
+    assert np.array_equal(to_np3(t3.rcv), to_np3(t4.rcv)) and np.array_equal(to_np3(t3.frm), to_np3(t4.frm))
+    assert t3.num_skipped == t4.num_skipped and sum(t3.num_skipped) > 0
 
 
 def test_bam_decode_property_random_records(tmp_path):
