@@ -84,26 +84,24 @@ class OracleCohortBackend(OracleWisBackend):
         return torch.from_numpy(out)
 
 
-def _cohort_inputs():
+def _cohort_inputs(T=180, S=6):
     rng = np.random.default_rng(11)
-    T, S = 180, 6
     eff = rng.lognormal(0, 0.4, T)
     lcv = (eff[None, :] * rng.normal(1, 0.08, (S, T)) * rng.uniform(20, 40, (S, 1))).astype(np.float32)
     lcv[2, 40:70] *= 0.5
     lcv[4, 100:130] *= 1.5
-    tids = np.repeat(np.arange(3), [70, 60, 50]).astype(np.int64)
+    tids = np.repeat(np.arange(3), [70, 60, T - 130]).astype(np.int64)
     return lcv, tids
 
 
-def _cohort_worker(rank, world, port, out):
+def _cohort_worker(rank, world, port, out, T=180, S=6):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from cnvetti_b200 import pipeline
-        lcv, tids = _cohort_inputs()
-        S = lcv.shape[0]
+        lcv, tids = _cohort_inputs(T, S)
         ranges = [parallel.shard_rows(S, r, world) for r in range(world)]
         a, b = ranges[rank]
         opts = BuildModelWisOptions(filter_z_score=2.0, filter_rel=0.1, max_ref_targets=15, min_ref_targets=3,
@@ -118,16 +116,17 @@ def _cohort_worker(rank, world, port, out):
             dist.destroy_process_group()
 
 
-def test_cohort_pipeline_sharded_matches_single_process(oracle):
+@pytest.mark.parametrize("T,S", [(180, 6), (181, 7)])
+def test_cohort_pipeline_sharded_matches_single_process(oracle, T, S):
     """pipeline.wis_call_cohort: samples sharded for normalise / segmentation, target rows sharded for the
     model and mod-coverage, one all-gather of the panel and one all-to-all of the relative coverage --
     world size 2 over gloo must reproduce the single-process result bit for bit."""
     mgr = mp.Manager()
     one, two = mgr.dict(), mgr.dict()
-    mp.spawn(_cohort_worker, args=(1, _free_port(), one), nprocs=1, join=True)
-    mp.spawn(_cohort_worker, args=(2, _free_port(), two), nprocs=2, join=True)
+    mp.spawn(_cohort_worker, args=(1, _free_port(), one, T, S), nprocs=1, join=True)
+    mp.spawn(_cohort_worker, args=(2, _free_port(), two, T, S), nprocs=2, join=True)  # (181, 7): uneven shards
     ref = one[0]
-    assert ref["states"].shape == (6, 180) and (ref["states"] != 2).any()
+    assert ref["states"].shape == (S, T) and (ref["states"] != 2).any()
     for rank in range(2):
         r = two[rank]
         (a, b), (lo, hi) = r["samples"], r["rows"]
