@@ -419,7 +419,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const SweepArgs a) {
     constexpr bool CLUSTER = CL > 1;
     static_assert(CL == 1 || CL == 2 || CL == 4, "clusters of 2 or 4 CTAs");
-    static_assert(!XPOSE || (STREAM && !FIRST), "the transposed tile exists for the streamed sweep's later rounds");
+    static_assert(!XPOSE || !FIRST, "the transposed tile exists for the later rounds");
     static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
     const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
     const uint32_t blk = blockIdx.x / CL;
@@ -439,7 +439,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
     __shared__ __align__(16) float4 s_row[XPOSE ? kTileRows : 1];      // XPOSE: per-row operands (q_i, theta_i, kappa_i)
     __shared__ __align__(16) float2 s_rq[XPOSE ? kEpiWarps : 1][64];   // XPOSE: per warp and tile, (q_i, theta_i + kappa_i smax)
-    // carve: A tiles [2 accumulators][n_kblocks] x 16 KB | B ring | barriers
+    // carve: A tiles [n_kblocks][2 row halves] x 16 KB (the halves of a K-block adjacent: one N = 256 operand) | B ring | barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + 2 * kMaxKBlocks * kTileBytes;
@@ -459,7 +459,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
             const uint32_t row = row0 + t;
             const bool live = row < a.rows;
-            s_row[t] = make_float4(live ? a.psorted[a.rows_a ? a.rows_a[row] : row] : 0.0f,
+            s_row[t] = make_float4((live && STREAM) ? a.psorted[a.rows_a ? a.rows_a[row] : row] : 0.0f,
                                    live ? a.thr[row] : -__int_as_float(0x7f800000), live ? a.kap[row] : 0.0f, 0.0f);
         }
 
@@ -494,7 +494,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
                 for (uint32_t h = 0; h < 2; ++h)
                     for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
-                        tma_load_2d(a_base + (h * kMaxKBlocks + kb) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
+                        tma_load_2d(a_base + (kb * 2u + h) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
                                     (int32_t)(row0 + h * 128));
             }
             constexpr uint32_t n_stages = STREAM ? kStreamStages : kStages;
@@ -542,7 +542,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (uint32_t h = 0; h < 2; ++h)
 #pragma unroll
-                for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) adesc[h][kb] = umma_desc(a_base + (h * kMaxKBlocks + kb) * kTileBytes);
+                for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) adesc[h][kb] = umma_desc(a_base + (kb * 2u + h) * kTileBytes);
             const uint64_t bdesc0 = umma_desc(b_base), sdesc0 = umma_desc(a_base);
             for (uint32_t it = 0; it < steps; ++it) {
                 const bool have = it < n_tiles;
@@ -592,6 +592,14 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             mbar_wait(bar_b_full + 8 * st, ph);
                             tc_fence_after();
                             const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kTileBytes >> 4));
+                            if (XPOSE) {  // one M128 x N256 MMA per slab: B tile on the M axis, both row halves on the N axis
+                                const uint32_t d_tmem = tmem_base + as * kTileRows;
+#pragma unroll
+                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                                    if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                        tc_mma_f16(d_tmem, bdesc + 2u * kk, adesc[0][kb] + 2u * kk, kIdescX, (kb | kk) != 0u);
+                                }
+                            } else {
 #pragma unroll
                             for (uint32_t h = 0; h < 2; ++h) {
                                 const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
@@ -600,6 +608,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     if (kb * (kKBlock / 16) + kk < a.k_mmas)
                                         tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
                                 }
+                            }
                             }
                             tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
                             if (++st == n_stages) {
@@ -634,7 +643,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (uint32_t it = 0; it < n_tiles; ++it) {
                 const uint32_t tile = CNVB_TILE_AT(it);
                 const uint32_t j = tile * kTileCols + q * 32u + lane;
-                const float nj = __ldg(a.nprime + j), pj = __ldg(a.psorted + j);
+                const float nj = __ldg(a.nprime + j), pj = STREAM ? __ldg(a.psorted + j) : 0.0f;
                 const float smax = __ldg(a.tile_smax + tile);
                 s_rq[e][lane] = make_float2(ro0.x, fmaf(ro0.z, smax, ro0.y));
                 s_rq[e][32u + lane] = make_float2(ro1.x, fmaf(ro1.z, smax, ro1.y));
@@ -642,7 +651,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (it + 1 < n_tiles) {
                     const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + q * 32u;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
+                    if (STREAM) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
                 }
                 mbar_wait(bar_acc_full + 8 * as, aph);
                 tc_fence_after();
@@ -657,8 +666,9 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         // (q, rhs) of rows c and c + 1: same address for all lanes
                         const float4 two = *reinterpret_cast<const float4 *>(&s_rq[e][32 * h + c]);
                         const float d0 = __fsub_rz(pj, two.x), d1 = __fsub_rz(pj, two.z);
-                        const float v0 = __fmaf_rd(d0, d0, fmaf(-2.0f, __uint_as_float(r[c]), nj));
-                        const float v1 = __fmaf_rd(d1, d1, fmaf(-2.0f, __uint_as_float(r[c + 1]), nj));
+                        const float w0 = fmaf(-2.0f, __uint_as_float(r[c]), nj), w1 = fmaf(-2.0f, __uint_as_float(r[c + 1]), nj);
+                        const float v0 = STREAM ? __fmaf_rd(d0, d0, w0) : w0;  // (ortho mode only with streamed operands)
+                        const float v1 = STREAM ? __fmaf_rd(d1, d1, w1) : w1;
                         r[c] = __float_as_uint(v0);
                         r[c + 1] = __float_as_uint(v1);
                         gmask |= (v0 <= two.y || v1 <= two.w) ? (1u << (c >> 2)) : 0u;
@@ -1434,13 +1444,18 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         return e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }();
     const bool xp = stream_a && (xpose_env >= 0 ? xpose_env == 1 : T >= 1000000u);
+    // the same layout for S <= 128 (resident row operand): CNVB_WIS_XPOSE_SMALL = 1, off unless asked for
+    const bool xp_small = !stream_a && [] {
+        const char *e = getenv("CNVB_WIS_XPOSE_SMALL");
+        return e && atoi(e) == 1;
+    }();
     auto sweep_first = cl == 4 ? wis_sweep_kernel<true, true, 4, false>
                      : cl == 2 ? wis_sweep_kernel<true, true, 2, false>
                                : (stream_a ? wis_sweep_kernel<true, true, 1, false> : wis_sweep_kernel<true, false, 1, false>);
     auto sweep_next = cl == 4 ? (xp ? wis_sweep_kernel<false, true, 4, true> : wis_sweep_kernel<false, true, 4, false>)
                     : cl == 2 ? (xp ? wis_sweep_kernel<false, true, 2, true> : wis_sweep_kernel<false, true, 2, false>)
                     : stream_a ? (xp ? wis_sweep_kernel<false, true, 1, true> : wis_sweep_kernel<false, true, 1, false>)
-                               : wis_sweep_kernel<false, false, 1, false>;
+                               : (xp_small ? wis_sweep_kernel<false, false, 1, true> : wis_sweep_kernel<false, false, 1, false>);
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     BoundConsts bc{};
