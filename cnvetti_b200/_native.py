@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcnvetti_b200.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_REFERENCE_PANIC, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+OK, ERR_INVALID, ERR_CUDA, ERR_REFERENCE_PANIC, ERR_STATE, ERR_NOMEM, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_CLIPFAIL, FLAG_ISIZE_NONPOS = 0x1000, 0x2000
 FRAGMENTS_GENOME_WIDE, FRAGMENTS_TARGET_REGIONS, COVERAGE = 0, 1, 2
@@ -121,6 +121,22 @@ SYMBOLS = {
     "cnvb_wis_filters": (_int, [_vp, _vp, _vp, _u32, C.POINTER(WisOpts), _vp, _int]),
     "cnvb_wis_build": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _vp, _vp, _vp, _vp, _vp,
                               C.POINTER(C.c_float), _int]),
+    "cnvb_comm_unique_id": (_int, [_vp]),
+    "cnvb_comm_init_rank": (_int, [_vp, _vp, _int, _int, C.POINTER(_vp)]),
+    "cnvb_comm_from_nccl": (_int, [_vp, _vp, _int, _int, C.POINTER(_vp)]),
+    "cnvb_comm_destroy": (None, [_vp]),
+    "cnvb_comm_rank": (_int, [_vp]),
+    "cnvb_comm_world": (_int, [_vp]),
+    "cnvb_comm_nccl_version": (_int, [C.POINTER(_int)]),
+    "cnvb_comm_create_error": (C.c_char_p, []),
+    "cnvb_comm_all_gather_v": (_int, [_vp, _vp, _vp, _vp]),
+    "cnvb_comm_all_to_all_v": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "cnvb_comm_all_reduce_u32": (_int, [_vp, _vp, _u64]),
+    "cnvb_norm_total_sharded": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _int]),
+    "cnvb_norm_gc_median_sharded": (_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _int]),
+    "cnvb_wis_build_sharded": (_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(WisOpts), _vp, _vp, _vp, _vp, _vp,
+                                      C.POINTER(C.c_float), C.POINTER(_u32), C.POINTER(_u32), _int]),
+    "cnvb_merge_cov": (_int, [_vp, _vp, _vp, _u64, _u32, _u64, _vp]),
     "cnvb_hmm_segment": (_int, [_vp, _vp, _vp, _u32, _vp, C.POINTER(HmmOpts), _vp, _vp, _int]),
     "cnvb_modcov": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
     "cnvb_modcov_panel": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _int]),

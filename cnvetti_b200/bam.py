@@ -41,12 +41,24 @@ class BamReader:
 
     # -- the reference's sample-name rule: SM of the @RG lines, joined with ',' (lib.rs:36-64)
     def sample_names(self):
+        """Sample list of the header, as samples_from_header / parse_line_rg build it
+        (lib-shared/src/bam_utils.rs:43-87): per @RG line the LAST `ID:` and `SM:` fields, each the text
+        between the first and the second ':' of a tab-separated field; lines lacking either are skipped;
+        first occurrence order, no duplicates."""
         out = []
         for line in self.header_text.splitlines():
-            if line.startswith("@RG"):
-                for field in line.split("\t")[1:]:
-                    if field.startswith("SM:") and field[3:] not in out:
-                        out.append(field[3:])
+            if not line.startswith("@RG"):
+                continue
+            rg_id = sm = None
+            for field in line.split("\t"):
+                token = field.split(":")
+                if len(token) >= 2:
+                    if token[0] == "ID":
+                        rg_id = token[1]
+                    elif token[0] == "SM":
+                        sm = token[1]
+            if rg_id is not None and sm is not None and sm not in out:
+                out.append(sm)
         return out
 
     def decode(self, min_unclipped=0.6, pinned=True):

@@ -36,8 +36,15 @@ struct cnvb_ctx {
     size_t stage_bytes = 0;
     // caching device allocator: aggregators are created and destroyed once per region, and
     // cudaMalloc/cudaFree would serialise the device every time
-    std::map<size_t, std::vector<void *>> pool_free;
+    // (stream-aware: a free block remembers the stream it was released on; handing it to another
+    // stream first orders that stream behind the releasing one, see pool_alloc)
+    struct pool_block {
+        void *p;
+        cudaStream_t released_on;
+    };
+    std::map<size_t, std::vector<pool_block>> pool_free;
     std::unordered_map<void *, size_t> pool_live;
+    cudaEvent_t pool_event = nullptr;
     // pinned host slots for asynchronous read-back of per-aggregator tallies
     uint32_t *tally_slots = nullptr;  // kTallySlots x 4 u32
     uint32_t tally_next = 0;
@@ -62,7 +69,8 @@ namespace cnvb {
 int refstats_prepare(cnvb_ctx *ctx);  // refstats.cu: builds the classification table on ctx->stream if missing
 // refstats.cu: reference statistics of all regions in one launch; 1 = not applicable (go region by region)
 int refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const *seq, const uint64_t *len, const uint64_t *out_off,
-                          uint32_t window_length, float *gc, uint8_t *has_gap, bool shares_sms);
+                          uint32_t window_length, float *gc, uint8_t *has_gap, bool shares_sms,
+                          std::vector<void *> *defer_release);
 
 // error chain in the style of error-chain's "error: ... / caused by: ..." (cnvetti/src/main.rs)
 inline int fail(cnvb_ctx *ctx, int code, const char *fmt, ...) {
@@ -185,14 +193,34 @@ inline unsigned persistent_grid(cnvb_ctx *ctx, K kernel, int threads, size_t sme
 
 constexpr uint32_t kTallySlots = 4096;
 
-// pooled device allocation (size classes: next power of two, >= 512 B)
+// pooled device allocation (size classes: next power of two, >= 512 B).
+// Reuse is stream-ordered: a block is released while the work that uses it may still be in flight on
+// the stream current at release time (ctx->stream, which the region loop points at its side streams).
+// A block released on the stream that now asks is reused as is; a block released on ANOTHER stream is
+// handed out only after the asking stream has been ordered behind everything enqueued on the
+// releasing stream so far (event record + wait, no host synchronisation).
 inline cudaError_t pool_alloc(cnvb_ctx *ctx, size_t bytes, void **out) {
     size_t cls = 512;
     while (cls < bytes) cls <<= 1;
     auto it = ctx->pool_free.find(cls);
     if (it != ctx->pool_free.end() && !it->second.empty()) {
-        *out = it->second.back();
-        it->second.pop_back();
+        auto &v = it->second;
+        size_t pick = v.size() - 1;
+        for (size_t i = v.size(); i-- > 0;)
+            if (v[i].released_on == ctx->stream) {
+                pick = i;
+                break;
+            }
+        const cnvb_ctx::pool_block b = v[pick];
+        if (b.released_on != ctx->stream) {
+            cudaError_t e = cudaSuccess;
+            if (!ctx->pool_event) e = cudaEventCreateWithFlags(&ctx->pool_event, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->pool_event, b.released_on);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->pool_event, 0);
+            if (e != cudaSuccess) return e;
+        }
+        v.erase(v.begin() + (long)pick);
+        *out = b.p;
     } else {
         cudaError_t e = cudaMalloc(out, cls);
         if (e != cudaSuccess) return e;
@@ -207,20 +235,23 @@ inline cudaError_t pool_alloc_t(cnvb_ctx *ctx, size_t count, T **out) {
     *out = static_cast<T *>(p);
     return e;
 }
-// Returns the block to the pool.  Stream-ordered reuse is safe: everything runs on ctx->stream.
+// Returns the block to the pool, tagged with the stream its last use was enqueued on (= ctx->stream
+// at the time of the call: release a block BEFORE switching ctx->stream away from the stream that used it).
 inline void pool_release(cnvb_ctx *ctx, void *p) {
     if (!p) return;
     auto it = ctx->pool_live.find(p);
     if (it == ctx->pool_live.end()) return;
-    ctx->pool_free[it->second].push_back(p);
+    ctx->pool_free[it->second].push_back({p, ctx->stream});
     ctx->pool_live.erase(it);
 }
 inline void pool_destroy(cnvb_ctx *ctx) {
     for (auto &kv : ctx->pool_free)
-        for (void *p : kv.second) cudaFree(p);
+        for (auto &b : kv.second) cudaFree(b.p);
     for (auto &kv : ctx->pool_live) cudaFree(kv.first);
     ctx->pool_free.clear();
     ctx->pool_live.clear();
+    if (ctx->pool_event) cudaEventDestroy(ctx->pool_event);
+    ctx->pool_event = nullptr;
 }
 
 // Carves aligned sub-buffers out of one allocation.

@@ -7,7 +7,7 @@
 //       key = floor(GC*100) (f32), 101 bins; median = order statistic of rank ceil(n/2) of the
 //       bin's LCV values (what CKMS(1e-6).query(0.5) returns below 5e5 items per bin), found by a
 //       4-pass MSB radix select run for all 101 bins at once; CV = lcv/median, CV2 = log2(CV).
-#include "common.cuh"
+#include "comm.cuh"
 #include "dd.cuh"
 
 using namespace cnvb;
@@ -32,7 +32,18 @@ __global__ void __launch_bounds__(256) sum_dd_final_kernel(const double *__restr
     dd acc{0.0, 0.0};
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) acc = dd_add(acc, dd{partial[2 * i], partial[2 * i + 1]});
     acc = block_reduce_dd(acc);
-    if (threadIdx.x == 0) out[0] = __dadd_rn(acc.hi, acc.lo);
+    if (threadIdx.x == 0) {
+        out[0] = __dadd_rn(acc.hi, acc.lo);
+        out[1] = acc.hi;  // the unrounded pair: what a rank contributes when the records are sharded
+        out[2] = acc.lo;
+    }
+}
+
+// sharded records: the ranks' (hi, lo) pairs folded in rank order -- the same on every rank
+__global__ void sum_dd_ranks_kernel(const double *__restrict__ pairs, int world, double *__restrict__ out) {
+    dd acc{0.0, 0.0};
+    for (int r = 0; r < world; ++r) acc = dd_add(acc, dd{pairs[2 * r], pairs[2 * r + 1]});
+    out[0] = __dadd_rn(acc.hi, acc.lo);
 }
 
 __global__ void norm_total_map_kernel(const float *__restrict__ lcv, const float *__restrict__ lcvsd,
@@ -203,8 +214,9 @@ __global__ void norm_gc_map_kernel(const float *__restrict__ lcv, const float *_
 
 }  // namespace
 
-extern "C" int cnvb_norm_total(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, uint64_t n, float *cv,
-                               float *cvsd, double *lcv_sum, int mem) {
+namespace {
+int norm_total_impl(cnvb_ctx *ctx, cnvb_comm *comm, const float *lcv, const float *lcvsd, uint64_t n, float *cv,
+                    float *cvsd, double *lcv_sum, int mem) {
     if (!ctx) return CNVB_ERR_INVALID;
     if (n && (!lcv || !cv)) return fail(ctx, CNVB_ERR_INVALID, "cnvb_norm_total: null argument");
     CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
@@ -215,10 +227,12 @@ extern "C" int cnvb_norm_total(cnvb_ctx *ctx, const float *lcv, const float *lcv
     if (grid > maxg) grid = maxg;
     if (grid == 0) grid = 1;
     const size_t nn = n ? n : 1;
-    CNVB_TRY(ensure_scratch(ctx, Carver::need({(size_t)grid * 16, 16, nn * 4, nn * 4, nn * 4, nn * 4})));
+    const int world = comm_world(comm);
+    CNVB_TRY(ensure_scratch(ctx, Carver::need({(size_t)grid * 16, 32, (size_t)world * 16, nn * 4, nn * 4, nn * 4, nn * 4})));
     Carver c(ctx->scratch);
     double *partial = c.take<double>((size_t)grid * 2);
-    double *d_sum = c.take<double>(2);
+    double *d_sum = c.take<double>(4);
+    double *d_pairs = c.take<double>((size_t)world * 2);
     const float *d_lcv = lcv, *d_lcvsd = sd ? lcvsd : nullptr;
     float *d_cv = cv, *d_cvsd = sd ? cvsd : nullptr;
     if (host) {
@@ -234,6 +248,12 @@ extern "C" int cnvb_norm_total(cnvb_ctx *ctx, const float *lcv, const float *lcv
     CNVB_LAUNCHED(ctx, "sum_f32_dd_kernel");
     sum_dd_final_kernel<<<1, 256, 0, ctx->stream>>>(partial, grid, d_sum);
     CNVB_LAUNCHED(ctx, "sum_dd_final_kernel");
+    if (world > 1) {  // uncorrected.rs:20-49 runs over ALL records: one exchange of a (hi, lo) pair per rank
+        std::vector<uint64_t> bytes((size_t)world, 16);
+        CNVB_TRY(comm_all_gather_v(comm, d_sum + 1, d_pairs, bytes.data()));
+        sum_dd_ranks_kernel<<<1, 1, 0, ctx->stream>>>(d_pairs, world, d_sum);
+        CNVB_LAUNCHED(ctx, "sum_dd_ranks_kernel");
+    }
     if (n) {
         norm_total_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_lcv, d_lcvsd, n, d_sum, d_cv, d_cvsd);
         CNVB_LAUNCHED(ctx, "norm_total_map_kernel");
@@ -247,9 +267,8 @@ extern "C" int cnvb_norm_total(cnvb_ctx *ctx, const float *lcv, const float *lcv
     return CNVB_OK;
 }
 
-extern "C" int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, const float *gc,
-                                   uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
-                                   float *medians, int mem) {
+int norm_gc_median_impl(cnvb_ctx *ctx, cnvb_comm *comm, const float *lcv, const float *lcvsd, const float *gc,
+                        uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags, float *medians, int mem) {
     if (!ctx) return CNVB_ERR_INVALID;
     if (n && (!lcv || !gc || !cv || !cv2 || !flags))
         return fail(ctx, CNVB_ERR_INVALID, "cnvb_norm_gc_median: null argument");
@@ -296,6 +315,9 @@ extern "C" int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float 
         gc_radix_hist_kernel<P><<<grid, 512, smem, ctx->stream>>>(d_lcv, d_gc, n, st, hist);        \
     }                                                                                               \
     CNVB_LAUNCHED(ctx, "gc_radix_hist_kernel");                                                     \
+    /* sharded records: the medians run over ALL of them (correct_binned.rs:25-75) -- the histograms  \
+       of the ranks are summed, after which every rank picks the same digit */                       \
+    CNVB_TRY(comm_all_reduce_u32(comm, hist, kGcBins * 256));                                        \
     gc_radix_pick_kernel<P><<<kGcBins, 32, 0, ctx->stream>>>(hist, st, d_med);                      \
     CNVB_LAUNCHED(ctx, "gc_radix_pick_kernel");
     CNVB_RADIX_PASS(0)
@@ -317,4 +339,29 @@ extern "C" int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float 
     if (medians) CNVB_CUDA(ctx, cudaMemcpyAsync(medians, d_med, kGcBins * 4, cudaMemcpyDeviceToHost, ctx->stream), "download medians");
     if (host || medians) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "norm_gc_median");
     return CNVB_OK;
+}
+}  // namespace
+
+extern "C" int cnvb_norm_total(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, uint64_t n, float *cv,
+                               float *cvsd, double *lcv_sum, int mem) {
+    return norm_total_impl(ctx, nullptr, lcv, lcvsd, n, cv, cvsd, lcv_sum, mem);
+}
+
+extern "C" int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, const float *gc,
+                                   uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
+                                   float *medians, int mem) {
+    return norm_gc_median_impl(ctx, nullptr, lcv, lcvsd, gc, n, cv, cv2, cvsd, flags, medians, mem);
+}
+
+extern "C" int cnvb_norm_total_sharded(cnvb_comm *comm, const float *lcv, const float *lcvsd, uint64_t n, float *cv,
+                                       float *cvsd, double *lcv_sum, int mem) {
+    if (!comm) return CNVB_ERR_INVALID;
+    return norm_total_impl(comm->ctx, comm, lcv, lcvsd, n, cv, cvsd, lcv_sum, mem);
+}
+
+extern "C" int cnvb_norm_gc_median_sharded(cnvb_comm *comm, const float *lcv, const float *lcvsd, const float *gc,
+                                           uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
+                                           float *medians, int mem) {
+    if (!comm) return CNVB_ERR_INVALID;
+    return norm_gc_median_impl(comm->ctx, comm, lcv, lcvsd, gc, n, cv, cv2, cvsd, flags, medians, mem);
 }

@@ -412,7 +412,7 @@ extern "C" int cnvb_refstats(cnvb_ctx *ctx, const uint8_t *seq, uint64_t len, ui
 // not apply (the caller then goes region by region), 0 on success, a negative error otherwise.
 int cnvb::refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const *seq, const uint64_t *len,
                                 const uint64_t *out_off, uint32_t window_length, float *gc, uint8_t *has_gap,
-                                bool shares_sms) {
+                                bool shares_sms, std::vector<void *> *defer_release) {
     if (n == 0) return 0;
     if (window_length < 128 || n > kMaxBatchRegions) return 1;
     std::vector<RefRegion> regs(n);
@@ -472,7 +472,13 @@ int cnvb::refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const 
         }
 #undef CNVB_REF_BATCH
     }
-    pool_release(ctx, d_regs);  // stream-ordered reuse
+    // The region loop runs this launch on a side stream of its own: the table then stays with the caller
+    // until the streams have joined, so that no aggregator of another stream is handed the block (the
+    // pool would order that stream behind this whole launch).  Otherwise: stream-ordered reuse.
+    if (defer_release)
+        defer_release->push_back(d_regs);
+    else
+        pool_release(ctx, d_regs);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "smem opt-in");
     CNVB_LAUNCHED(ctx, "refstats_lut_kernel");
     return 0;

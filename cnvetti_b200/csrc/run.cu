@@ -166,7 +166,7 @@ extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int k
         if (all_dev && bs.size() > 1 && batch_on) {
             if (fan) ctx->stream = ctx->side[2];
             const int rc = refstats_batch_device(ctx, (uint32_t)bs.size(), bs.data(), bl.data(), bo.data(),
-                                                 opts->window_length, d.gc, d.gap, fan);
+                                                 opts->window_length, d.gc, d.gap, fan, &temps);
             ctx->stream = main_stream;
             if (rc < 0) return cleanup(rc);
             ref_batched = rc == 0;

@@ -15,7 +15,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "comm.cuh"
 #include "dd.cuh"
 
 using namespace cnvb;
@@ -89,7 +89,7 @@ __device__ void bitonic_sort_pairs(float *d, uint32_t *j, uint32_t n /* power of
 __global__ void __launch_bounds__(kRowThreads) wis_row_exact_kernel(
     const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S, uint32_t k,
     const uint32_t *__restrict__ row_list, uint32_t row_begin, float *__restrict__ out_dist,
-    uint32_t *__restrict__ out_idx) {
+    uint32_t *__restrict__ out_idx, uint32_t *__restrict__ nan_flag) {
     extern __shared__ float s_xi[];  // [S]
     __shared__ float s_d[kRowBuf];
     __shared__ uint32_t s_j[kRowBuf];
@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(kRowThreads) wis_row_exact_kernel(
             const uint32_t j = base + q * kRowThreads + threadIdx.x;
             if (j < T && tid[j] != ti) {  // same contig (and j == i): +inf in the reference
                 const float d = wis_ref_distance(s_xi, X + (size_t)j * S, S, vec4);
-                if (d <= thr) {
+                // a NaN distance: the reference's partial_cmp().unwrap() panics (lib.rs:168)
+                if (d != d && nan_flag) *nan_flag = 1u;
+                // (a computed +inf -- an infinite CV, or an overflowing sum -- ranks with the same-contig +inf
+                // entries by index: left to the fill-up below)
+                if (d <= thr && d < __int_as_float(0x7f800000)) {
                     const uint32_t slot = atomicAdd(&s_cnt, 1u);
                     s_d[slot] = d;  // slot < kRowBuf: the buffer is compacted below kRowChunk first
                     s_j[slot] = j;
@@ -119,8 +123,13 @@ __global__ void __launch_bounds__(kRowThreads) wis_row_exact_kernel(
             }
         }
         __syncthreads();
-        if (s_cnt > kRowBuf - kRowChunk) {  // next pass could overflow: keep the k smallest
-            const uint32_t n = s_cnt;
+        // Block-uniform decision: every thread takes its snapshot of the counter between two barriers, so no
+        // warp can start the next chunk's appends while another still evaluates the condition (the branch
+        // contains barriers of its own).
+        const uint32_t n_now = s_cnt;
+        __syncthreads();
+        if (n_now > kRowBuf - kRowChunk) {  // next pass could overflow: keep the k smallest
+            const uint32_t n = n_now;
             for (uint32_t t = n + threadIdx.x; t < kRowBuf; t += blockDim.x) {
                 s_d[t] = __int_as_float(0x7f800000);
                 s_j[t] = 0xffffffffu;
@@ -145,11 +154,12 @@ __global__ void __launch_bounds__(kRowThreads) wis_row_exact_kernel(
         out_dist[o + t] = s_d[t];
         out_idx[o + t] = s_j[t];
     }
-    // fewer than k other-contig targets: the reference's +inf entries fill up, in index order
+    // fewer than k finite distances: the reference's +inf entries (same contig, lib.rs:153-156, or a
+    // distance that is +inf) fill up, in index order
     if (threadIdx.x == 0 && m < k) {
         uint32_t w = m;
         for (uint32_t j = 0; j < T && w < k; ++j) {
-            if (tid[j] == ti) {
+            if (tid[j] == ti || wis_ref_distance(s_xi, X + (size_t)j * S, S, vec4) == __int_as_float(0x7f800000)) {
                 out_dist[o + w] = __int_as_float(0x7f800000);
                 out_idx[o + w] = j;
                 ++w;
@@ -580,7 +590,8 @@ int check_wis_opts(cnvb_ctx *ctx, const cnvb_wis_opts *o, uint32_t T) {
 }
 
 int run_rows_exact(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S, uint32_t k,
-                   const uint32_t *d_row_list, uint32_t n_rows, uint32_t row_begin, float *d_dist, uint32_t *d_idx) {
+                   const uint32_t *d_row_list, uint32_t n_rows, uint32_t row_begin, float *d_dist, uint32_t *d_idx,
+                   uint32_t *d_nan_flag) {
     if (n_rows == 0) return 0;
     const size_t smem = (size_t)S * sizeof(float);
     if (smem > 200 * 1024) return fail(ctx, CNVB_ERR_INVALID, "more than 51200 samples are not supported");
@@ -588,9 +599,39 @@ int run_rows_exact(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_
               "smem opt-in");
     KernelSpan span(ctx, "wis_row_exact_kernel");
     wis_row_exact_kernel<<<n_rows, kRowThreads, smem, ctx->stream>>>(dX, dtid, T, S, k, d_row_list, row_begin, d_dist,
-                                                                     d_idx);
+                                                                     d_idx, d_nan_flag);
     CNVB_LAUNCHED(ctx, "wis_row_exact_kernel");
     return 0;
+}
+
+// W1: the reference's ModelInput is NaN-free by assumption -- a NaN distance makes `partial_cmp().unwrap()`
+// panic (lib-model-wis/src/lib.rs:168).  One pass over the panel: the largest |x| by bit pattern (NaN patterns
+// order above +inf) and whether the targets lie on more than one contig (same-contig pairs are never
+// evaluated, lib.rs:153-156).
+__global__ void __launch_bounds__(256) wis_panel_check_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid,
+                                                              uint32_t T, uint64_t n, uint32_t *__restrict__ out) {
+    int mx = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(X) & 15u) == 0u) {
+        const int4 *X4 = reinterpret_cast<const int4 *>(X);
+        const uint64_t n4 = n >> 2;
+        for (uint64_t i = g; i < n4; i += stride) {
+            const int4 v = ld_stream(X4 + i);
+            mx = max(max(mx, v.x & 0x7fffffff), max(max(v.y & 0x7fffffff, v.z & 0x7fffffff), v.w & 0x7fffffff));
+        }
+        for (uint64_t i = (n4 << 2) + g; i < n; i += stride) mx = max(mx, __float_as_int(X[i]) & 0x7fffffff);
+    } else {
+        for (uint64_t i = g; i < n; i += stride) mx = max(mx, __float_as_int(X[i]) & 0x7fffffff);
+    }
+    bool other = false;
+    const uint32_t t0 = tid[0];
+    for (uint64_t i = g; i < T; i += stride) other |= tid[i] != t0;
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    other = __any_sync(0xffffffffu, other);
+    if (lane_id() == 0) {
+        if (mx) atomicMax(reinterpret_cast<int *>(out), mx);
+        if (other) out[1] = 1u;
+    }
 }
 
 int wis_distances_dev(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S,
@@ -602,9 +643,45 @@ int wis_distances_dev(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint
                                                                              : CNVB_WIS_ENGINE_EXACT;
     ctx->wis_stats[0] = row_end - row_begin;
     ctx->wis_stats[1] = ctx->wis_stats[2] = ctx->wis_stats[3] = 0;
+    if (row_end == row_begin) return 0;
+    uint32_t *d_chk = nullptr;  // [0] max |x| pattern | [1] more than one contig | [2] NaN distance seen
+    cudaError_t e = pool_alloc_t(ctx, 4, &d_chk);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "allocating the panel check");
+    struct Release {
+        cnvb_ctx *c;
+        void *p;
+        ~Release() { pool_release(c, p); }
+    } release{ctx, d_chk};
+    uint32_t chk[4] = {0, 0, 0, 0};
+    CNVB_CUDA(ctx, cudaMemsetAsync(d_chk, 0, 16, ctx->stream), "panel check");
+    {
+        const uint64_t n = (uint64_t)T * S;
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n / 4 + 255) / 256 + 1, (uint64_t)ctx->sm_count * 8);
+        wis_panel_check_kernel<<<blocks, 256, 0, ctx->stream>>>(dX, dtid, T, n, d_chk);
+        CNVB_LAUNCHED(ctx, "wis_panel_check_kernel");
+    }
+    CNVB_CUDA(ctx, cudaMemcpyAsync(chk, d_chk, 8, cudaMemcpyDeviceToHost, ctx->stream), "panel check");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "panel check");
+    const bool has_nan = chk[0] > 0x7f800000u, has_inf = chk[0] == 0x7f800000u;
+    if (has_nan && chk[1])
+        return fail(ctx, CNVB_ERR_REFERENCE_PANIC,
+                    "the panel holds a NaN (a missing FORMAT/CV): called `Option::unwrap()` on a `None` value, "
+                    "dist.partial_cmp() in compute_distances (lib-model-wis/src/lib.rs:168)");
+    // a non-finite panel has no fp16 image: every pair in the reference's own arithmetic (inf - inf = NaN panics there)
+    if (has_nan || has_inf) engine = CNVB_WIS_ENGINE_EXACT;
     if (engine == CNVB_WIS_ENGINE_TENSOR)
         return wis_distances_tensor(ctx, dX, dtid, T, S, k, row_begin, row_end, d_dist, d_idx);
-    return run_rows_exact(ctx, dX, dtid, T, S, k, nullptr, row_end - row_begin, row_begin, d_dist, d_idx);
+    CNVB_TRY(run_rows_exact(ctx, dX, dtid, T, S, k, nullptr, row_end - row_begin, row_begin, d_dist, d_idx,
+                            has_inf ? d_chk + 2 : nullptr));
+    if (has_inf) {
+        CNVB_CUDA(ctx, cudaMemcpyAsync(chk + 2, d_chk + 2, 4, cudaMemcpyDeviceToHost, ctx->stream), "panel check");
+        CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "panel check");
+        if (chk[2])
+            return fail(ctx, CNVB_ERR_REFERENCE_PANIC,
+                        "two targets hold the same infinity in one sample (inf - inf = NaN): called `Option::unwrap()` "
+                        "on a `None` value, dist.partial_cmp() in compute_distances (lib-model-wis/src/lib.rs:168)");
+    }
+    return 0;
 }
 
 }  // namespace
@@ -784,6 +861,104 @@ extern "C" int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid
     CNVB_TRY(oc.download());
     CNVB_TRY(of.download());
     if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis build");
+    return CNVB_OK;
+}
+
+// ---- build-model-wis with the targets sharded by row block over the ranks of a communicator ------------
+namespace {
+__global__ void wis_nearest_kernel(const float *__restrict__ dist, uint32_t rows, uint32_t k, float *__restrict__ nearest) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) nearest[r] = dist[(size_t)r * k];
+}
+}  // namespace
+
+extern "C" int cnvb_wis_build_sharded(cnvb_comm *comm, const float *X_rows, const uint32_t *tid_rows, uint32_t rows,
+                                      uint32_t S, const cnvb_wis_opts *opts, float *ref_dist, uint32_t *ref_idx,
+                                      uint32_t *ref_len, uint32_t *num_calls, uint8_t *filt, float *threshold,
+                                      uint32_t *row_begin_out, uint32_t *T_out, int mem) {
+    if (!comm) return CNVB_ERR_INVALID;
+    cnvb_ctx *ctx = comm->ctx;
+    if (!opts || !threshold || S == 0 || (rows && (!X_rows || !tid_rows || !ref_dist || !ref_idx || !ref_len || !num_calls || !filt)))
+        return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_build_sharded: bad argument");
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const int world = comm->world, me = comm->rank;
+    // row counts of all ranks (row blocks in rank order = target order)
+    uint32_t *d_counts = nullptr;
+    cudaError_t e = pool_alloc_t(ctx, (size_t)world, &d_counts);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "allocating the row counts");
+    PoolGuard guard{ctx};
+    guard.ptrs.push_back(d_counts);
+    std::vector<uint32_t> counts((size_t)world, 0);
+    {
+        std::vector<uint64_t> four((size_t)world, 4);
+        CNVB_CUDA(ctx, cudaMemcpyAsync(d_counts + me, &rows, 4, cudaMemcpyHostToDevice, ctx->stream), "row counts");
+        CNVB_TRY(comm_all_gather_v(comm, d_counts + me, d_counts, four.data()));
+        CNVB_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_counts, (size_t)world * 4, cudaMemcpyDeviceToHost, ctx->stream), "row counts");
+        CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "row counts");
+    }
+    uint64_t T64 = 0, lo64 = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == me) lo64 = T64;
+        T64 += counts[(size_t)r];
+    }
+    if (T64 == 0 || T64 > 0xFFFFFFF0ull) return fail(ctx, CNVB_ERR_INVALID, "cnvb_wis_build_sharded: %llu targets", (unsigned long long)T64);
+    const uint32_t T = (uint32_t)T64, lo = (uint32_t)lo64, hi = lo + rows;
+    if (row_begin_out) *row_begin_out = lo;
+    if (T_out) *T_out = T;
+    CNVB_TRY(check_wis_opts(ctx, opts, T));
+    const uint32_t k = T < opts->max_ref_targets ? T : opts->max_ref_targets;
+    // the ONE big exchange: every rank needs the whole panel (80 MB at config 3, 12 GB at config 5)
+    float *dX = nullptr;
+    uint32_t *dt = nullptr;
+    float *d_nearest = nullptr;
+    if ((e = pool_alloc_t(ctx, (size_t)T * S, &dX)) != cudaSuccess) return fail_cuda(ctx, e, "allocating the panel");
+    guard.ptrs.push_back(dX);
+    if ((e = pool_alloc_t(ctx, (size_t)T, &dt)) != cudaSuccess) return fail_cuda(ctx, e, "allocating contig ids");
+    guard.ptrs.push_back(dt);
+    if ((e = pool_alloc_t(ctx, (size_t)T, &d_nearest)) != cudaSuccess) return fail_cuda(ctx, e, "allocating nearest distances");
+    guard.ptrs.push_back(d_nearest);
+    std::vector<uint64_t> bx((size_t)world), bt((size_t)world);
+    for (int r = 0; r < world; ++r) {
+        bx[(size_t)r] = (uint64_t)counts[(size_t)r] * S * 4;
+        bt[(size_t)r] = (uint64_t)counts[(size_t)r] * 4;
+    }
+    const cudaMemcpyKind up = mem == CNVB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (rows) {
+        CNVB_CUDA(ctx, cudaMemcpyAsync(dX + (size_t)lo * S, X_rows, (size_t)rows * S * 4, up, ctx->stream), "placing the panel rows");
+        CNVB_CUDA(ctx, cudaMemcpyAsync(dt + lo, tid_rows, (size_t)rows * 4, up, ctx->stream), "placing contig ids");
+    }
+    CNVB_TRY(comm_all_gather_v(comm, dX + (size_t)lo * S, dX, bx.data()));
+    CNVB_TRY(comm_all_gather_v(comm, dt + lo, dt, bt.data()));
+    DevOut<float> od;
+    DevOut<uint32_t> oi, ol, oc;
+    DevOut<uint8_t> of;
+    CNVB_TRY(od.init(ctx, ref_dist, (size_t)rows * k, mem, "allocating distances"));
+    CNVB_TRY(oi.init(ctx, ref_idx, (size_t)rows * k, mem, "allocating indices"));
+    CNVB_TRY(ol.init(ctx, ref_len, rows, mem, "allocating lengths"));
+    CNVB_TRY(oc.init(ctx, num_calls, rows, mem, "allocating call counts"));
+    CNVB_TRY(of.init(ctx, filt, rows, mem, "allocating filters"));
+    CNVB_TRY(wis_distances_dev(ctx, dX, dt, T, S, opts, lo, hi, od.p, oi.p));                 // lib.rs:427, own rows
+    CNVB_TRY(od.download());
+    // prune threshold (lib.rs:207-216) runs over the nearest distance of ALL targets: one f32 per target
+    if (rows) {
+        wis_nearest_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(od.p, rows, k, d_nearest + lo);
+        CNVB_LAUNCHED(ctx, "wis_nearest_kernel");
+    }
+    CNVB_TRY(comm_all_gather_v(comm, d_nearest + lo, d_nearest, bt.data()));
+    CNVB_TRY(wis_threshold_dev(ctx, d_nearest, T, 1, opts->filter_z_score, threshold));        // same bits on every rank
+    if (rows) {
+        wis_prune_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(od.p, oi.p, rows, k, *threshold, ol.p);  // :221-228
+        CNVB_LAUNCHED(ctx, "wis_prune_kernel");
+        CNVB_TRY(wis_calls_dev(ctx, dX, S, oi.p, ol.p, k, opts, lo, rows, oc.p));               // lib.rs:429-436
+        wis_filters_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(ol.p, oc.p, rows, opts->min_ref_targets,
+                                                                        opts->max_samples_reliable, of.p);
+        CNVB_LAUNCHED(ctx, "wis_filters_kernel");
+    }
+    CNVB_TRY(oi.download());
+    CNVB_TRY(ol.download());
+    CNVB_TRY(oc.download());
+    CNVB_TRY(of.download());
+    if (mem != CNVB_MEM_DEVICE) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "wis build (sharded)");
     return CNVB_OK;
 }
 

@@ -1291,7 +1291,8 @@ inline int make_tmap(cnvb_ctx *ctx, void *H, uint64_t T, uint64_t Kp, CUtensorMa
 }
 
 int run_rows_exact(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, uint32_t T, uint32_t S, uint32_t k,
-                   const uint32_t *d_row_list, uint32_t n_rows, uint32_t row_begin, float *d_dist, uint32_t *d_idx);
+                   const uint32_t *d_row_list, uint32_t n_rows, uint32_t row_begin, float *d_dist, uint32_t *d_idx,
+                   uint32_t *d_nan_flag);
 
 struct PoolGuard {  // releases pooled blocks at scope exit
     cnvb_ctx *ctx;
@@ -1611,7 +1612,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ctx->wis_stats[1] = n_ovf;
     ctx->wis_stats[2] = h_cnt[1];
     ctx->wis_stats[3] = h_cnt[0];  // (includes the first window, swept twice)
-    if (n_ovf) CNVB_TRY(run_rows_exact(ctx, dX, dtid, T, S, k, ovf_list + 1, n_ovf, row_begin, d_dist, d_idx));
+    if (n_ovf) CNVB_TRY(run_rows_exact(ctx, dX, dtid, T, S, k, ovf_list + 1, n_ovf, row_begin, d_dist, d_idx, nullptr));
     CNVB_CUDA(ctx, cudaStreamSynchronize(st), "tensor engine");  // work space is released on return
     return 0;
 }

@@ -25,6 +25,13 @@ class BuildModelWisOptions:
     max_samples_reliable: int = 4
     engine: int = ENGINE_AUTO
 
+    @classmethod
+    def quick(cls, **kw):
+        """The preset `cnvetti quick wis-build-model` hard-codes (cnvetti/src/quick_wis_build_model.rs:
+        88-105): as the `cmd build-model-wis` defaults (cli.yaml:370-406) except max_samples_reliable = 8."""
+        kw.setdefault("max_samples_reliable", 8)
+        return cls(**kw)
+
     def c_opts(self):
         return N.WisOpts(self.filter_z_score, self.filter_rel, self.min_ref_targets, self.max_ref_targets,
                          self.max_samples_reliable, self.engine)
@@ -148,6 +155,33 @@ def run(X, tids, options=None, ctx=None):
     ctx.check(N.lib().cnvb_wis_build(ctx.handle, px, pt, T, S, C.byref(o), buf(dist)[0], buf(idx)[0],
                                      buf(ref_len)[0], buf(calls)[0], buf(filt)[0], C.byref(thr), mem))
     return WisModel(dist, idx, ref_len, calls, filt, thr.value)
+
+
+def run_sharded(X_rows, tid_rows, options, comm):
+    """lib_model_wis::run with the target rows sharded over the ranks of `comm` (cnvb_wis_build_sharded):
+    every rank passes its rows of the panel (row blocks in rank order) and gets the model of its rows,
+    ref_idx in global target indices.  Returns (WisModel, (row_begin, row_end), T).  Collective call."""
+    ctx = comm.ctx
+    options = options or BuildModelWisOptions()
+    px, pt, mem, rows, S, keep = _panel(X_rows, tid_rows)
+    # k = min(T, max_ref_targets) is known only after the row counts have been exchanged; panels with fewer
+    # targets than max_ref_targets are not what one shards
+    k = options.max_ref_targets
+    idt = np.int32 if mem == N.MEM_DEVICE else np.uint32
+    dist = _empty2(ctx, rows, k, np.float32, mem)
+    idx = _empty2(ctx, rows, k, idt, mem)
+    ref_len = ctx.empty(rows, idt, mem)
+    calls = ctx.empty(rows, idt, mem)
+    filt = ctx.empty(rows, np.uint8, mem)
+    thr = C.c_float(0.0)
+    lo, T = C.c_uint32(0), C.c_uint32(0)
+    o = options.c_opts()
+    ctx.check(N.lib().cnvb_wis_build_sharded(comm.handle, px, pt, rows, S, C.byref(o), buf(dist)[0], buf(idx)[0],
+                                             buf(ref_len)[0], buf(calls)[0], buf(filt)[0], C.byref(thr),
+                                             C.byref(lo), C.byref(T), mem))
+    if T.value < k:
+        raise N.CnvbError(N.ERR_INVALID, "run_sharded: fewer targets (%d) than max_ref_targets (%d)" % (T.value, k))
+    return WisModel(dist, idx, ref_len, calls, filt, thr.value), (lo.value, lo.value + rows), T.value
 
 
 def mod_coverage(cv, model_filt, ref_idx, ref_len, ctx=None):

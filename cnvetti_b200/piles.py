@@ -59,7 +59,7 @@ def compute_threshold(abs_freq, fdr_cutoff):
     return int(out.value)
 
 
-def gather_piles(regions, min_mapq=0, pile_max_gap=20, mask_piles_fdr=0.0001, ctx=None):
+def gather_piles(regions, min_mapq=0, pile_max_gap=20, mask_piles_fdr=0.001, ctx=None):
     """lib.rs:353-419: piles of every region, genome-wide size histogram, FDR threshold, and the
     black-listed intervals per region as (start, end) arrays usable as `Region.piles`.
     `regions`: pipeline.Region objects whose reads carry pos, end, mapq, flags."""

@@ -51,6 +51,7 @@ class CoverageTable:
     cv2: object = None
     cvsd: object = None
     norm_flags: object = None
+    medians: object = None
 
 
 def _num_regions(options, r):
@@ -143,38 +144,120 @@ def coverage_run(regions, options, ctx=None, device=True):
     return t
 
 
-def normalize_run(table, normalization="MedianGcBinned", ctx=None):
-    """`cnvetti cmd normalize` on the table (lib-normalize/src/lib.rs:57-60)."""
-    ctx = ctx or default_context()
+def normalize_run(table, normalization="MedianGcBinned", ctx=None, comm=None, want_medians=True):
+    """`cnvetti cmd normalize` on the table (lib-normalize/src/lib.rs:57-60).  comm: the table holds this
+    rank's regions of a sharded run (coverage_run_sharded); the statistics run over all ranks' records."""
+    ctx = (comm.ctx if comm is not None else ctx) or default_context()
     if normalization == "TotalCovSum":
-        table.cv, table.cvsd, _ = run_uncorrected_normalization(table.lcv, table.lcvsd, ctx=ctx)
+        table.cv, table.cvsd, _ = run_uncorrected_normalization(table.lcv, table.lcvsd, ctx=ctx, comm=comm,
+                                                                want_sum=want_medians)
     elif normalization == "MedianGcBinned":
         if table.gc is None:
             raise N.CnvbError(N.ERR_INVALID, "Could not access INFO/GC. Did you forget to pass in reference "
                               "when computing coverage so GC content was not computed?")
-        r = run_binned_correction(table.lcv, table.gc, table.lcvsd, ctx=ctx)
+        r = run_binned_correction(table.lcv, table.gc, table.lcvsd, ctx=ctx, comm=comm, want_medians=want_medians)
         table.cv, table.cv2, table.cvsd, table.norm_flags = r["cv"], r["cv2"], r["cvsd"], r["flags"]
+        table.medians = r["medians"]
     else:
         raise ValueError("Unknown normalization")
     return table
 
 
-def merge_cov(tables):
+def shard_regions(lengths, world):
+    """Which rank processes which region of `lib_coverage::run`'s loop (lib-coverage/src/lib.rs:768-781):
+    longest-processing-time assignment by region length (reads are ~proportional to it).  Returns
+    (owner[region], regions_of_rank[rank]); deterministic, the same on every rank."""
+    from . import parallel
+    per_rank = parallel.shard_by_weight([int(x) for x in lengths], world)
+    owner = [0] * len(lengths)
+    for r, lst in enumerate(per_rank):
+        for i in lst:
+            owner[i] = r
+    return owner, per_rank
+
+
+def coverage_run_sharded(local_regions, options, comm, device=True):
+    """The region loop with the regions (contigs) sharded over the ranks of `comm`: this rank processes
+    `local_regions` (its share under shard_regions, in genome order) exactly as the single-GPU loop would --
+    regions are independent (lib.rs:768-781), no data-path collective.  The table holds the rank's regions;
+    normalize_run(table, ..., comm=comm) then normalises against the statistics of ALL ranks' records and
+    gather_table() assembles the genome-order table where one is wanted."""
+    return coverage_run(local_regions, options, ctx=comm.ctx, device=device)
+
+
+def gather_table(table, owner, comm, columns=("start", "end", "rcv", "lcv", "gc", "gap", "ft", "cv", "cv2", "norm_flags")):
+    """Genome-order columns on every rank from the ranks' sharded tables (what the reference's single
+    output file holds).  `owner[i]` = rank of region i (shard_regions); the ranks' tables list their regions
+    in genome order.  One all-gather per column; collective."""
+    import torch
+    world = comm.world
+    # rows per region, from every rank (regions are in genome order within a rank)
+    mine = [hi - lo for lo, hi in zip(table.offsets[:-1], table.offsets[1:])]
+    n_regions = len(owner)
+    sizes = torch.zeros(n_regions, dtype=torch.int64, device="cuda:%d" % comm.ctx.device)
+    my_ids = [i for i, r in enumerate(owner) if r == comm.rank]
+    assert len(my_ids) == len(mine), "table does not hold this rank's regions"
+    counts_per_rank = [sum(1 for r in owner if r == q) for q in range(world)]
+    packed = torch.tensor(mine, dtype=torch.int64, device=sizes.device)
+    allsz = comm.all_gather_rows(packed, counts_per_rank).cpu().tolist()
+    pos = [0] * world
+    starts = np.concatenate([[0], np.cumsum(counts_per_rank)]).astype(np.int64)
+    region_rows = []
+    for i in range(n_regions):
+        q = owner[i]
+        region_rows.append(int(allsz[starts[q] + pos[q]]))
+        pos[q] += 1
+    rows_per_rank = [sum(region_rows[i] for i in range(n_regions) if owner[i] == q) for q in range(world)]
+    # rank-major concatenation -> genome order
+    rank_off = np.concatenate([[0], np.cumsum(rows_per_rank)]).astype(np.int64)
+    within = [0] * world
+    pieces = []
+    for i in range(n_regions):
+        q = owner[i]
+        pieces.append((int(rank_off[q] + within[q]), region_rows[i]))
+        within[q] += region_rows[i]
+    out = CoverageTable()
+    out.offsets = np.concatenate([[0], np.cumsum(region_rows)]).astype(np.int64).tolist()
+    for name in columns:
+        col = getattr(table, name, None)
+        if col is None:
+            continue
+        full = comm.all_gather_rows(col, rows_per_rank)
+        setattr(out, name, torch.cat([full[a:a + n] for a, n in pieces]) if pieces else full)
+    return out
+
+
+def merge_cov(tables, ctx=None):
     """`cnvetti cmd merge-cov` on in-memory tables (lib-merge-cov/src/lib.rs:102-232): the per-sample
     FORMAT/CV columns side by side -> panel X[T][S] (row-major f32) and the contig id of every record
     (ModelInput, lib-model-wis/src/lib.rs:49-62).  All samples must describe the same records."""
     import torch
+    ctx = ctx or default_context()
     if not tables:
         raise ValueError("merge_cov: no input")
     first = tables[0]
     for t in tables[1:]:
         if t.offsets != first.offsets or not torch.equal(t.start, first.start) or not torch.equal(t.end, first.end):
             raise N.CnvbError(N.ERR_INVALID, "merge-cov: the inputs do not describe the same regions")
-    X = torch.stack([t.cv for t in tables], dim=1).contiguous()
-    tids = torch.empty(first.offsets[-1], dtype=torch.int32, device=X.device)
+    T, S = int(first.offsets[-1]), len(tables)
+    cols = [t.cv.contiguous() for t in tables]
+    X = torch.empty((T, S), dtype=torch.float32, device=cols[0].device)
+    ptrs = (C.c_void_p * S)(*[c.data_ptr() for c in cols])
+    ctx.check(N.lib().cnvb_merge_cov(ctx.handle, ptrs, None, 0, S, T, X.data_ptr()))
+    tids = torch.empty(T, dtype=torch.int32, device=X.device)
     for i, (lo, hi) in enumerate(zip(first.offsets[:-1], first.offsets[1:])):
         tids[lo:hi] = i
     return X, tids
+
+
+def merge_cov_panel(cv_sample_major, ctx=None):
+    """The same for a cohort whose columns already sit in one block cv[S][T] (sample-major): -> X[T][S]."""
+    import torch
+    ctx = ctx or default_context()
+    S, T = int(cv_sample_major.shape[0]), int(cv_sample_major.shape[1])
+    X = torch.empty((T, S), dtype=torch.float32, device=cv_sample_major.device)
+    ctx.check(N.lib().cnvb_merge_cov(ctx.handle, None, cv_sample_major.data_ptr(), T, S, T, X.data_ptr()))
+    return X
 
 
 def quick_wis_build_model(samples, wis_options=None, ctx=None):
@@ -188,13 +271,14 @@ def quick_wis_build_model(samples, wis_options=None, ctx=None):
     opts = CoverageOptions(window_length=None, count_kind="Fragments", considered_regions="TargetRegions",
                            min_mapq=0, min_unclipped=0.6, min_window_remaining=0.5)
     tables = [normalize_run(coverage_run(regions, opts, ctx=ctx), "TotalCovSum", ctx=ctx) for regions in samples]
-    X, tids = merge_cov(tables)
-    model = model_wis.run(X, tids, wis_options or model_wis.BuildModelWisOptions(), ctx=ctx)
+    X, tids = merge_cov(tables, ctx=ctx)
+    # (the quick command's own preset: max_samples_reliable 8, not the 4 of `cmd build-model-wis`)
+    model = model_wis.run(X, tids, wis_options or model_wis.BuildModelWisOptions.quick(), ctx=ctx)
     return model, X, tids
 
 
 def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_options=None, sigma=0.08,
-                    segment=True, ctx=None, group=None, backend=None, timings=None):
+                    segment=True, ctx=None, group=None, backend=None, timings=None, comm=None):
     """BASELINE config 5, in memory: germline calling of a whole cohort against its own panel --
     per sample `cmd normalize --normalization TotalCovSum`, `merge-cov`, `build-model-wis`,
     per sample `mod-coverage` (the chain of cnvetti/src/quick_wis_build_model.rs:133-214 and
@@ -206,6 +290,9 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
     sample, then ONE all-gather of the normalised panel; distances / prune / calls / mod-coverage by
     target-row block (one all-gather of T nearest distances for the threshold); an all-to-all brings
     the relative coverage back to sample-major shards for the (sample, contig) HMM lanes.
+    `comm` (parallel.Communicator): the exchanges run inside the library (NCCL on the context's stream: the
+    samples' normalised columns are gathered straight into one [S][T] block and turned into X[T][S] by the
+    merge-cov kernel); without it they go through torch.distributed (`group`).
     `backend` (default: the CUDA library on this rank's GPU) is injectable so that the host logic can
     be exercised with gloo on a CPU-only box.
 
@@ -215,9 +302,11 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
     import time
     import torch
     from . import model_wis, parallel
+    if comm is not None:
+        ctx = comm.ctx
     backend = backend or parallel.CudaWisBackend(ctx or default_context())
-    wis_options = wis_options or model_wis.BuildModelWisOptions()
-    rank, world = parallel._world(group)
+    wis_options = wis_options or model_wis.BuildModelWisOptions.quick()  # quick_wis_build_model.rs:88-105
+    rank, world = (comm.rank, comm.world) if comm is not None else parallel._world(group)
     S_r, T = int(lcv.shape[0]), int(lcv.shape[1])
     if sample_ranges is None:
         sample_ranges = [(0, S_r)]
@@ -239,23 +328,37 @@ def wis_call_cohort(lcv, tids, sample_ranges=None, wis_options=None, discover_op
         return time.perf_counter()
 
     t0 = time.perf_counter()
-    # cmd normalize, one sample at a time (its sum runs over all targets of the sample)
-    cv = torch.empty_like(lcv)
+    # cmd normalize, one sample at a time (its sum runs over all targets of the sample); the normalised
+    # columns land in this rank's rows of the cohort block [S][T]
+    if hasattr(backend, "merge_cov_panel"):
+        full = torch.empty((S, T), dtype=lcv.dtype, device=dev)
+        cv = full[sample_ranges[rank][0]:sample_ranges[rank][1]]
+    else:
+        full, cv = None, torch.empty_like(lcv)
     for s in range(S_r):
         backend.normalize_total(lcv[s], cv[s])
     t0 = mark("normalize", t0)
     # merge-cov: the one big exchange, then the panel in ModelInput layout X[T][S]
-    X = parallel.all_gather_rows(cv, group).t().contiguous()  # (single process: just the transpose)
+    if full is not None:
+        if comm is not None:
+            comm.all_gather_into(full, [b - a for a, b in sample_ranges])
+        elif world > 1:
+            full = parallel.all_gather_rows(cv, group)
+        X = backend.merge_cov_panel(full)
+        del full
+    else:
+        X = parallel.all_gather_rows(cv, group).t().contiguous()  # (injected CPU backends)
     del cv
     t0 = mark("merge_cov", t0)
     lo, hi = parallel.shard_rows(T, rank, world)
-    m = parallel.wis_rows_distributed(X, tids, wis_options, lo, hi, backend=backend, group=group, with_modcov=True)
+    m = parallel.wis_rows_distributed(X, tids, wis_options, lo, hi, backend=backend, group=group, with_modcov=True,
+                                      comm=comm)
     t0 = mark("build_model_wis", t0)
     mc = m.pop("modcov")  # (the CUDA backend forms the per-probe calls and these values in one pass)
     if mc is None:
         mc = backend.modcov_panel(X, m["filt"], m["ref_idx"], m["ref_len"], lo, hi)
     t0 = mark("mod_coverage", t0)
-    rel = parallel.exchange_rows_to_samples(mc["cv_rel"], sample_ranges, group=group)  # [S_r][T]
+    rel = parallel.exchange_rows_to_samples(mc["cv_rel"], sample_ranges, group=group, comm=comm)  # [S_r][T]
     t0 = mark("exchange", t0)
     out = dict(model=m, rows=(lo, hi), cv_rel=rel, cvz_rows=mc["cvz"], panel=X, n_samples=S)
     if segment:
@@ -299,7 +402,7 @@ def read_fasta(path):
 
 
 def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(chr)?\d\d?$", targets=None, ctx=None,
-                 threads=0, command_line=None, mask_piles=False, mask_piles_fdr=0.0001, pile_max_gap=20):
+                 threads=0, command_line=None, mask_piles=False, mask_piles_fdr=0.001, pile_max_gap=20):
     """`cnvetti cmd coverage --input X.bam --output Y.vcf[.gz] [--reference R.fa] [--mask-piles] ...`
     (lib_coverage::run, lib-coverage/src/lib.rs:679-795): BAM decode on host threads, with --mask-piles the
     pile collection and its FDR threshold (gather_piles, :353-419), the region loop on the GPU, the coverage

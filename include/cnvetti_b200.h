@@ -18,7 +18,10 @@
  *    memory; the library stages through pinned buffers and copies asynchronously) or
  *    CNVB_MEM_DEVICE (device pointers on the ctx's device; zero-copy);
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
- *    CNVB_ERR_CUDA.
+ *    CNVB_ERR_CUDA;
+ *  - multi-GPU: one host process (or thread) per GPU, each with its own ctx and a cnvb_comm made
+ *    from it; the *_sharded entry points are collective -- every rank calls them, in the same
+ *    order, with its own share of the records / target rows.
  */
 #ifndef CNVETTI_B200_H
 #define CNVETTI_B200_H
@@ -36,6 +39,7 @@ extern "C" {
 #define CNVB_ERR_REFERENCE_PANIC (-3) /* input on which the reference itself panics          */
 #define CNVB_ERR_STATE (-4)           /* call order violated (e.g. get_stats before finish)  */
 #define CNVB_ERR_NOMEM (-5)
+#define CNVB_ERR_COMM (-6)            /* NCCL missing or a collective failed                 */
 
 #define CNVB_MEM_HOST 0
 #define CNVB_MEM_DEVICE 1
@@ -63,6 +67,39 @@ const char *cnvb_version(void);
 int cnvb_ctx_set_timing(cnvb_ctx *ctx, int on);
 int cnvb_ctx_timing_reset(cnvb_ctx *ctx);
 int cnvb_ctx_timing_query(cnvb_ctx *ctx, const char *kernel, double *total_ms, uint64_t *count);
+
+/* ---- communicator --------------------------------------------------
+ * The reference is one process with rayon threads (lib-model-wis/src/lib.rs:144-193,
+ * cnvetti/src/quick_wis_build_model.rs:148-184); here the host keeps that shape per GPU and the
+ * exchanges between GPUs happen inside the library: NCCL over NVLink / NVSwitch, resolved at run
+ * time (dlopen of libnccl.so.2, or the path in CNVB_NCCL_LIB; nothing is linked), enqueued on the
+ * ctx stream.  Either let the library make the NCCL communicator -- rank 0 calls
+ * cnvb_comm_unique_id and hands the 128 bytes to the other ranks by any means (a file, MPI, a
+ * socket, torch.distributed), then every rank calls cnvb_comm_init_rank -- or wrap an
+ * ncclComm_t the host already has (cnvb_comm_from_nccl; not destroyed with the handle).
+ * world == 1 needs no NCCL at all. */
+typedef struct cnvb_comm cnvb_comm;
+typedef struct {
+    char bytes[128]; /* an ncclUniqueId */
+} cnvb_comm_id;
+int cnvb_comm_unique_id(cnvb_comm_id *id);
+int cnvb_comm_init_rank(cnvb_ctx *ctx, const cnvb_comm_id *id, int rank, int world, cnvb_comm **out);
+int cnvb_comm_from_nccl(cnvb_ctx *ctx, void *nccl_comm, int rank, int world, cnvb_comm **out);
+void cnvb_comm_destroy(cnvb_comm *comm);
+int cnvb_comm_rank(const cnvb_comm *comm);
+int cnvb_comm_world(const cnvb_comm *comm);
+/* NCCL_VERSION_CODE of the library that was found; CNVB_ERR_COMM (text in
+ * cnvb_comm_create_error, thread-local) if there is none */
+int cnvb_comm_nccl_version(int *version);
+const char *cnvb_comm_create_error(void);
+/* Building blocks of the sharded drivers, for hosts that compose their own (device buffers):
+ * all-gather of blocks of different sizes (recv = the blocks back to back in rank order; send may
+ * be the rank's own slot of recv), all-to-all (block q of send, [send_off[q], send_off[q+1]), goes
+ * to rank q; offsets in bytes, world + 1 entries), in-place sum of u32. */
+int cnvb_comm_all_gather_v(cnvb_comm *comm, const void *send, void *recv, const uint64_t *bytes_per_rank);
+int cnvb_comm_all_to_all_v(cnvb_comm *comm, const void *send, const uint64_t *send_off, void *recv,
+                           const uint64_t *recv_off);
+int cnvb_comm_all_reduce_u32(cnvb_comm *comm, uint32_t *buf, uint64_t count);
 
 /* ---- read batches ------------------------------------------------------------------------ */
 /* Extra bits the host decoder ORs into the 16-bit FLAG word (BAM uses bits 0..11):          */
@@ -255,6 +292,18 @@ int cnvb_norm_gc_median(cnvb_ctx *ctx, const float *lcv, const float *lcvsd, con
                         uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
                         float *medians, int mem);
 
+/* The two normalisers with the RECORDS sharded over the ranks of `comm` (contigs on different
+ * GPUs, lib-coverage/src/lib.rs:768-781): arguments as above for the rank's own records, results
+ * for them.  The statistics run over all records of all ranks -- TotalCovSum exchanges one
+ * double-double partial sum per rank (uncorrected.rs:20-49), MedianGcBinned sums the 101 x 256
+ * radix histograms of the ranks in each of its four passes (correct_binned.rs:25-75) -- and are
+ * bit-identical to the single-GPU call on the concatenated records.  Collective. */
+int cnvb_norm_total_sharded(cnvb_comm *comm, const float *lcv, const float *lcvsd, uint64_t n, float *cv,
+                            float *cvsd, double *lcv_sum, int mem);
+int cnvb_norm_gc_median_sharded(cnvb_comm *comm, const float *lcv, const float *lcvsd, const float *gc,
+                                uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
+                                float *medians, int mem);
+
 /* ---- coverage VCF writer (text containers) ---------------------------
  * Replaces the htslib record assembly and output of process_region (lib-coverage/src/lib.rs:
  * 560-673) under the header of build_header (:67-166), plus what lib-normalize adds (FORMAT CV /
@@ -286,6 +335,16 @@ typedef struct {
 } cnvb_vcf_columns;
 int cnvb_vcf_write_coverage(const cnvb_vcf_opts *opts, const cnvb_vcf_columns *cols, uint64_t n_rows,
                             char *err, uint64_t err_len);
+
+/* ---- lib-merge-cov --------------------------------------------------------------------------
+ * = merge_files (lib-merge-cov/src/lib.rs:102-232) on in-memory columns: the FORMAT/CV columns of S
+ * single-sample tables that describe the same T records, side by side -> X[T][S] row-major, the
+ * record layout of the merged file and ModelInput's panel (lib-model-wis/src/lib.rs:49-62).
+ * Pass EITHER cv_cols (host array of S device pointers, one column of T floats each) OR
+ * cv_sample_major (one device block, column s at cv_sample_major + s * col_stride).  Device
+ * memory only; asynchronous on the ctx stream. */
+int cnvb_merge_cov(cnvb_ctx *ctx, const float *const *cv_cols, const float *cv_sample_major, uint64_t col_stride,
+                   uint32_t S, uint64_t T, float *X);
 
 /* ---- lib-model-wis ------------------------------------------------------------------------ */
 typedef struct {
@@ -341,6 +400,19 @@ int cnvb_wis_build(cnvb_ctx *ctx, const float *X, const uint32_t *tid, uint32_t 
                    const cnvb_wis_opts *opts, float *ref_dist, uint32_t *ref_idx, uint32_t *ref_len,
                    uint32_t *num_calls, uint8_t *filt, float *threshold, int mem);
 
+/* = lib_model_wis::run (lib.rs:422-447) with the target rows sharded over the ranks of `comm`
+ * ("cnvb_wis_build(..., n_gpus)").  Every rank passes ITS rows of the panel
+ * (X_rows[rows][S], tid_rows[rows]; row blocks in rank order = target order; sizes may differ, a
+ * rank may have none) and receives the model of its rows -- outputs as cnvb_wis_build, sized by
+ * `rows`, ref_idx holding GLOBAL target indices; *row_begin / *T (host, may be NULL) say where the
+ * block sits.  Inside: all-gather of the panel over NVLink, distances for the own rows, all-gather
+ * of one nearest distance per target, the same threshold on every rank (*threshold, host), local
+ * prune / per-probe calls / filters.  Bit-identical to the single-GPU model.  Collective. */
+int cnvb_wis_build_sharded(cnvb_comm *comm, const float *X_rows, const uint32_t *tid_rows, uint32_t rows,
+                           uint32_t S, const cnvb_wis_opts *opts, float *ref_dist, uint32_t *ref_idx,
+                           uint32_t *ref_len, uint32_t *num_calls, uint8_t *filt, float *threshold,
+                           uint32_t *row_begin, uint32_t *T, int mem);
+
 /* ---- lib-mod-cov ---------------------------------------------------------------------------- */
 /* = load_target_infos + the FORMAT/INFO values of write_mod_cov (lib-mod-cov/src/lib.rs:76-164,
  * 209-240) for one sample: cv[T] = FORMAT/CV of the sample, model_filt[T] != 0 marks model
@@ -385,9 +457,13 @@ typedef struct {
 /* Segmentation of `n_lanes` independent lanes (one per sample and contig).  cv holds the lanes'
  * FORMAT/CV values back to back, lane l = cv[lane_off[l] .. lane_off[l+1]); sigma_s[l] is the
  * lane's noise scale (1.4826 * MAD of CV).  Non-finite CV (missing) emits log-likelihood 0 in
- * every state.  state[i] = Viterbi copy-number state (log-space f64, strictly sequential
- * recurrence, ties -> lowest state); posterior (nullable) = [total bins][5] forward-backward
- * posteriors.  lane_off and sigma_s are host arrays; cv/state/posterior follow `mem`. */
+ * every state.  state[i] = Viterbi copy-number state on INTEGER scores in units of 2^-16 nat
+ * (transitions llrint(log p * 65536); emissions from four f32 operations, floored at -2^22 and
+ * rounded to nearest-even; recurrence max_r(delta[r] + t[r][s]) + e[s], ties -> lowest
+ * predecessor, trace-back from the first maximum: DESIGN.md section 6).  Integer (max,+) is
+ * associative, so the chunk-parallel evaluation on the GPU and a sequential walk give the same
+ * path, bit for bit.  posterior (nullable) = [total bins][5] forward-backward posteriors in f64
+ * log space (rel 1e-6).  lane_off and sigma_s are host arrays; cv/state/posterior follow `mem`. */
 int cnvb_hmm_segment(cnvb_ctx *ctx, const float *cv, const uint64_t *lane_off, uint32_t n_lanes,
                      const double *sigma_s, const cnvb_hmm_opts *opts, uint8_t *state, double *posterior,
                      int mem);
