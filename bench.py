@@ -1,22 +1,32 @@
 #!/usr/bin/env python3
-"""bench.py -- throughput of the read-depth hot path on B200 (BASELINE.json metric).
+"""bench.py -- throughput of the read-depth hot path on B200 (BASELINE.json metric: aligned reads/s
+binned; WIS bin-pairs/s; HMM bins/s at 1/2/4/8 B200 vs host CPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scale F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
 
-Workload (N=1 and every N): BASELINE.json configs[1] -- `cnvetti cmd coverage` (Fragments, 500 bp
-windows, --reference for GC) + `cmd normalize --normalization MedianGcBinned` on a synthetic 30x
-whole-genome sample (chr1-22 hg38 lengths, ~900 M reads).  One "step" = one pass of that path
-over the whole sample.  Multi-GPU: one process per GPU, each rank processes its own sample (the
-reference's only data parallelism is one coverage+normalize chain per input BAM,
-cnvetti/src/quick_wis_build_model.rs:148-184), no data-path collective => weak scaling.
-
-`value`  : reads/s, inputs already resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same through the public API with HOST (pinned) SoA buffers: H2D of all inputs and
-           D2H of the result table inside the timed region.
-`roofline`: dominant kernel frag_bin_gw_kernel, algorithmic 7 B/read (mid i32 + mapq u8 + flags
-           u16) over its CUDA-event time inside the timed steps.
-`cpu_baseline`: the oracle (restated reference CPU path) on a bounded sample, host cores stated.
-`--impl reference`: times that CPU path alone (the reference cannot be built here: no Rust).
+ONE JSON line.  Headline = BASELINE.json configs[1]: `cnvetti cmd coverage` (Fragments, 500 bp windows,
+--reference for GC) + `cmd normalize --normalization MedianGcBinned` on a synthetic 30x whole-genome
+sample (chr1-22 hg38 lengths, ~900 M reads); one "step" = one pass of that path over the whole sample.
+  N = 1   the sample on one GPU.
+  N > 1   the SAME sample sharded by contig over the ranks (longest-processing-time assignment,
+          lib-coverage/src/lib.rs:768-781: regions are independent), the normaliser's statistics
+          exchanged inside the library (4 all-reduces of the 101 x 256 radix histograms, NCCL on the
+          context's stream) => strong scaling; `replicas` (one sample per GPU, no collective: the
+          reference's own data parallelism, quick_wis_build_model.rs:148-184) is reported beside it.
+`value`   reads/s, inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`     the same through the public API with HOST (pinned) SoA buffers: H2D of all inputs and D2H
+          of the result table inside the timed region.
+`roofline` dominant kernel frag_bin_gw_kernel, algorithmic 7 B/read over its
+          CUDA-event time.
+`cpu_baseline` the oracle (restated reference CPU path) on a bounded sample, host cores stated.
+`checks`  chr19-22 of the workload through the GPU path against the oracle (counts, GC bits, medians,
+          CV bits): a mismatch fails the run.
+`workloads` the other BASELINE metrics in the same run, each a full line of its own (roofline,
+          cpu_baseline, e2e, clocks): cfg1 (chr22, three aggregator kinds), cfg3 (build-model-wis
+          200 000 x 100), cfg4 (HMM, 100 samples x 2.9 M bins), cfg5 (cohort 3 M x 1000, whole chain).
+          `--workload NAME` runs one of them alone (profiling).
+`--impl reference` times the restated reference CPU path alone (the Rust reference cannot be built
+          here: no cargo / rustc, un-vendored dependencies).
 """
 import argparse
 import json
@@ -36,37 +46,99 @@ MIN_MAPQ = 20
 READS_PER_BP = 900e6 / 2_875_001_522      # ~900 M reads over chr1-22
 BYTES_PER_READ_GW = 7                     # mid i32 + mapq u8 + flags u16
 
-
 HMM_KERNELS = ("hmm_viterbi_kernel", "hmm_chunk_matrix_kernel", "hmm_chunk_path_kernel", "hmm_boundary_kernel",
-               "hmm_backtrack_kernel", "hmm_states_kernel")
+               "hmm_backtrack_kernel", "hmm_states_kernel", "hmm_emit_kernel")
 HMM_BYTES_PER_BIN = 11  # SURVEY 8(d) cfg 4: 4 B CV + 5 B back-pointers + 1 B trace-back read + 1 B state
-
-
-def host_buffer(shape, dtype, torch):
-    """Pinned host memory where the box grants it (the e2e leg copies from it every step); pageable
-    otherwise -- eight ranks pinning ~9 GB each can exceed what a node allows."""
-    try:
-        return torch.empty(shape, dtype=dtype, pin_memory=True), True
-    except RuntimeError:
-        return torch.empty(shape, dtype=dtype), False
+WIS_KERNELS = ("wis_sweep_kernel", "wis_compact_kernel", "wis_rescore_kernel", "wis_calls_kernel",
+               "wis_row_exact_kernel", "wis_panel_check_kernel", "modcov_panel_kernel", "merge_cov_kernel")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full genome (tests)")
-    ap.add_argument("--quick", action="store_true", help="device-resident leg only (profiling runs)")
-    ap.add_argument("--workload", default="coverage", choices=["coverage", "wis", "hmm", "piles", "cfg1", "cfg5"],
-                    help="coverage = BASELINE configs[1] (default, the headline); wis = configs[2]")
+    ap.add_argument("--quick", action="store_true", help="device-resident legs only (profiling runs)")
+    ap.add_argument("--workload", default="all",
+                    choices=["all", "coverage", "wis", "hmm", "piles", "cfg1", "cfg5"],
+                    help="all = the headline (coverage, BASELINE configs[1]) with the other configs under "
+                         "`workloads`; a name = that workload alone")
     ap.add_argument("--targets", type=int, default=None, help="wis / cfg5: number of targets T (200 000 / 3 000 000)")
     ap.add_argument("--samples", type=int, default=None, help="wis / cfg5: number of samples S (100 / 1000)")
     ap.add_argument("--hmm-samples", type=int, default=100, help="hmm: number of samples (22 lanes each)")
     ap.add_argument("--cpu-rows", type=int, default=2000, help="wis: rows of the CPU baseline sample")
     ap.add_argument("--cpu-sample-contigs", type=int, default=4, help="last k contigs form the CPU sample")
+    ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the one-sample-per-GPU side measurement")
     return ap.parse_args()
+
+
+# ---- plumbing -------------------------------------------------------------------------------------------
+class Env:
+    """rank / device / context / communicator of this process"""
+
+    def __init__(self, args):
+        import torch
+        import cnvetti_b200 as cb
+        from cnvetti_b200 import parallel
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = "cuda:%d" % self.local
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+            self.dist = dist
+        self.ctx = cb.Context(self.local)
+        self.comm = parallel.Communicator(self.ctx, self.rank, self.world)
+        self.t0 = time.perf_counter()
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def log(self, msg):
+        if self.rank == 0:
+            sys.stderr.write("[bench %7.1f s] %s\n" % (time.perf_counter() - self.t0, msg))
+            sys.stderr.flush()
+
+    def free(self):
+        """between workloads: hand cached device memory back"""
+        import gc
+        gc.collect()
+        self.ctx.release_memory()
+        self.torch.cuda.empty_cache()
+
+    def close(self):
+        self.comm.close()
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def host_buffer(shape, dtype, torch):
+    """Pinned host memory where the box grants it (the e2e leg copies from it every step); pageable
+    otherwise."""
+    try:
+        return torch.empty(shape, dtype=dtype, pin_memory=True), True
+    except RuntimeError:
+        return torch.empty(shape, dtype=dtype), False
 
 
 def contigs(scale):
@@ -153,30 +225,86 @@ def measured_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def ncu_traffic(n_reads, launches_per_step):
-    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-    (profiles/roofline_traffic.json holds dram bytes per read of the captured launch)."""
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops_sustained", 1406.9)), "MEASURED_PEAKS.json bf16_tflops_sustained"
+    return 1406.9, "fallback 1406.9 TFLOP/s sustained bf16 (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, units_per_launch):
+    """DRAM bytes per launch of `kernel` from the COMMITTED ncu --set full capture (profiles/
+    roofline_traffic.json holds dram bytes per unit of the captured launch) -- not measured in this run."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p) and launches_per_step:
+    if os.path.exists(p) and units_per_launch:
         try:
-            per_read = float(json.load(open(p))["frag_bin_gw_kernel"]["dram_bytes_per_read"])
-            return per_read * n_reads / launches_per_step
+            ent = json.load(open(p))[kernel]
+            per = float(ent.get("dram_bytes_per_read", ent.get("dram_bytes_per_unit")))
+            return per * units_per_launch, "committed ncu capture (profiles/roofline_traffic.json: %.3f DRAM B/unit x units per launch)" % per
         except Exception:
-            return None
-    return None
+            return None, None
+    return None, None
 
 
-def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468):
+def timed_steps(env, step, steps, warmup, sampler=None):
+    """W untimed steps, then K steps between barrier + synchronize on both sides, CUDA events on the
+    context's stream (= torch's current stream), max over ranks.  Returns (ms per step, launches, clocks)."""
+    torch = env.torch
+    for _ in range(max(0, warmup)):
+        step()
+    env.barrier()
+    if sampler:
+        sampler.start()
+    l0 = env.ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    env.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = env.max_over_ranks(e0.elapsed_time(e1) / steps)
+    return ms, env.ctx.launch_count - l0, clocks
+
+
+def kernel_times(env, step, steps, names):
+    """per-kernel device time: a second, instrumented pass (events around every launch cost a few
+    microseconds each, so they stay out of the timed region; in timing mode the library keeps the
+    regions on one stream -- a kernel's duration means something only when it has the device to itself)"""
+    ctx, torch = env.ctx, env.torch
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(steps):
+        step()
+    i1.record()
+    torch.cuda.synchronize()
+    kern = {}
+    for kname in names:
+        kms, cnt = ctx.timing_query(kname)
+        if cnt:
+            kern[kname] = {"ms_per_step": kms / steps, "launches_per_step": cnt / steps}
+    ctx.set_timing(False)
+    ctx.timing_reset()
+    return kern, i0.elapsed_time(i1) / steps
+
+
+def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6):
     """Host BAM decode, timed on its own (north_star: reported separately from device time): a synthetic
-    coordinate-sorted BAM of the config-1 read mix is written, then decoded by the library's BGZF/BAM
-    decoder (zlib on all host threads) into pinned SoA columns."""
+    coordinate-sorted BAM of the config-1 read mix is written at zlib level `level` (htslib's default is 6),
+    then decoded by the library's BGZF/BAM decoder (zlib on all host threads) into pinned SoA columns."""
     import tempfile
     from cnvetti_b200 import bam, synth
     scale = n_pairs / 7_600_000.0
     L = max(100_000, int(contig_len * scale))
     d = synth.synth_bam_records(22, L, n_pairs)
     with tempfile.TemporaryDirectory() as tmp:
-        path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d])
+        try:
+            path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d], level=level)
+        except TypeError:
+            path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d])
+            level = 1
         size = os.path.getsize(path)
         best = None
         with bam.BamReader(path) as r:
@@ -185,11 +313,14 @@ def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468):
                 st = r.stats()
                 if best is None or st["decode_seconds"] < best["decode_seconds"]:
                     best = st
+    ncpu = os.cpu_count() or 1
     return {"reads": best["records"], "file_bytes": size, "uncompressed_bytes": best["uncompressed_bytes"],
-            "seconds": best["decode_seconds"], "inflate_seconds": best["inflate_seconds"],
+            "zlib_level": level, "seconds": best["decode_seconds"], "inflate_seconds": best["inflate_seconds"],
             "parse_seconds": best["parse_seconds"], "reads_per_s": best["records"] / best["decode_seconds"],
-            "threads": os.cpu_count(), "what": "BGZF inflate (zlib, level-1 file) + record walk + SoA derivation into "
-                                               "pinned columns; best of 3; not part of value / e2e"}
+            "compressed_mb_per_s": size / best["decode_seconds"] / 1e6,
+            "compressed_mb_per_s_per_thread": size / best["decode_seconds"] / 1e6 / ncpu,
+            "threads": ncpu, "what": "BGZF inflate (zlib) + record walk + SoA derivation into pinned columns; "
+                                     "best of 3; not part of value / e2e"}
 
 
 def file_level_leg(n_pairs=1_000_000, contig_len=50_818_468):
@@ -214,178 +345,199 @@ def file_level_leg(n_pairs=1_000_000, contig_len=50_818_468):
                         "VCF formatting + BGZF on host threads"}
 
 
-# ---------------------------------------------------------------------------------------------
+# ---- CPU legs (the only places that execute oracle/) -----------------------------------------------------
+def oracle_cfg2(sample):
+    """The oracle over the sample's contigs: coverage (Fragments, genome-wide) + refstats + record assembly
+    per contig, then MedianGcBinned over the sample's windows.  Returns every column (for the parity
+    check) -- single thread: `cmd coverage` / `cmd normalize` are single-threaded in the reference
+    (regions are processed sequentially, lib-coverage/src/lib.rs:768)."""
+    import oracle
+    oopts = oracle.cov_opts(window_length=WINDOW, min_mapq=MIN_MAPQ)
+    lcvs, gcs, gaps, rcvs, procs = [], [], [], [], []
+    for reads, L, seq in sample:
+        counts, proc, _ = oracle.frag_gw(reads, oopts, L)
+        cov, start, end, frm = oracle.frag_gw_stats(counts, oopts, L)
+        lcv, _, _ = oracle.cov_records(cov, None, start, end, frm, False, oopts)
+        gc, gap = oracle.refstats(seq, WINDOW)
+        lcvs.append(lcv), gcs.append(gc), gaps.append(gap), rcvs.append(cov), procs.append(proc)
+    lcv, gc = np.concatenate(lcvs), np.concatenate(gcs)
+    cv, cv2, _, flags, med = oracle.norm_gc_median(lcv, gc)
+    return dict(rcv=np.concatenate(rcvs), lcv=lcv, gc=gc, gap=np.concatenate(gaps), cv=cv, cv2=cv2, flags=flags,
+                medians=med, processed=procs)
+
+
 def cpu_reference_leg(sample, steps, warmup):
-    """Times the oracle (restated reference CPU path) on the sample: coverage (Fragments,
-    genome-wide) + refstats + record assembly per contig, then MedianGcBinned over the sample's
-    windows.  Single thread: `cmd coverage` / `cmd normalize` are single-threaded in the
-    reference (regions are processed sequentially, lib-coverage/src/lib.rs:768)."""
     import oracle
     oracle.build()
-    oopts = oracle.cov_opts(window_length=WINDOW, min_mapq=MIN_MAPQ)
     prepared = [(oracle.ReadBatch(d["pos"], d["isize"], d["flag"], d["mapq"], d["cigar_off"], d["cigar"]), L, seq)
                 for (d, L, seq) in sample]
     n_reads = sum(p[0].n for p in prepared)
-
-    def one():
-        lcvs, gcs = [], []
-        for reads, L, seq in prepared:
-            counts, _, _ = oracle.frag_gw(reads, oopts, L)
-            cov, start, end, frm = oracle.frag_gw_stats(counts, oopts, L)
-            lcv, _, _ = oracle.cov_records(cov, None, start, end, frm, False, oopts)
-            gc, _ = oracle.refstats(seq, WINDOW)
-            lcvs.append(lcv)
-            gcs.append(gc)
-        return oracle.norm_gc_median(np.concatenate(lcvs), np.concatenate(gcs))
-
+    out = None
     for _ in range(warmup):
-        one()
+        out = oracle_cfg2(prepared)
     t0 = time.perf_counter()
     for _ in range(steps):
-        one()
+        out = oracle_cfg2(prepared)
     dt = (time.perf_counter() - t0) / steps
-    return n_reads, dt
+    return n_reads, dt, out
 
 
-def bench_wis(args):
+def oracle_rows(X, tids, rows, k):
+    """compute_distances of single rows, one oracle call per row on a thread each (ctypes drops the GIL)"""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        return list(ex.map(lambda r: oracle.wis_distances(X, tids, k, int(r), int(r) + 1), rows))
+
+
+def check_rows_against_oracle(X_host, tids_host, rows, got_dist, got_idx, k=100):
+    """reference sets, their order and the distance bits of `rows` against the oracle -> (ok, n_rows)"""
+    ok = True
+    for q, (od, oi) in enumerate(oracle_rows(X_host, tids_host, rows, k)):
+        ok &= bool(np.array_equal(got_idx[q].astype(np.uint32), oi[0]))
+        ok &= bool(np.array_equal(np.ascontiguousarray(got_dist[q]).view(np.uint32), od[0].view(np.uint32)))
+    return ok, len(rows)
+
+
+# ---- workloads ------------------------------------------------------------------------------------------------
+def bench_wis(args, env, steps=None, warmup=None):
     """BASELINE configs[2]: build-model-wis on a synthetic panel (T targets x S samples, k=100).
-    One step = compute_distances + prune + per-probe calls + filters (lib_model_wis::run)."""
-    import torch
-    import cnvetti_b200 as cb
+    One step = compute_distances + prune + per-probe calls + filters (lib_model_wis::run).  N > 1: target
+    rows sharded over the ranks (cnvb_wis_build_sharded: panel all-gather, nearest-distance all-gather)."""
+    torch = env.torch
     from cnvetti_b200 import model_wis as mw
-    from cnvetti_b200 import synth
+    from cnvetti_b200 import parallel, synth
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
     T, S = args.targets or 200_000, args.samples or 100
-    dev = "cuda:0"
-    ctx = cb.Context(0)
+    dev, ctx, world, rank = env.dev, env.ctx, env.world, env.rank
     X, tids = synth.synth_panel(3, T, S)
-    dX = torch.from_numpy(X).to(dev)
-    dt = torch.from_numpy(tids.view(np.int32)).to(dev)
+    lo, hi = parallel.shard_rows(T, rank, world)
     opts = mw.BuildModelWisOptions(engine=mw.ENGINE_TENSOR)
     workload = "cfg3: build-model-wis, synthetic panel %d targets x %d samples, k=100 (tensor engine)" % (T, S)
+    if world == 1:
+        dX = torch.from_numpy(X).to(dev)
+        dt = torch.from_numpy(tids.view(np.int32)).to(dev)
 
-    def step():
-        return mw.run(dX, dt, opts, ctx=ctx)
+        def step():
+            return mw.run(dX, dt, opts, ctx=ctx)
+    else:
+        dX = torch.from_numpy(X[lo:hi]).to(dev)
+        dt = torch.from_numpy(tids[lo:hi].view(np.int32)).to(dev)
+
+        def step():
+            return mw.run_sharded(dX, dt, opts, env.comm)[0]
 
     m = step()
     torch.cuda.synchronize()
     stats = mw.last_stats(ctx)
-    sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
-    for _ in range(max(0, args.warmup - 1)):
-        step()
-    torch.cuda.synchronize()
-    sampler.start()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = ctx.launch_count - l0
-    # per-kernel times: a second, instrumented pass (timing mode serialises what the timed steps overlap)
-    ctx.set_timing(True)
-    ctx.timing_reset()
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    kern = {}
-    for kname in ("wis_sweep_kernel", "wis_compact_kernel", "wis_rescore_kernel", "wis_calls_kernel",
-                  "wis_row_exact_kernel"):
-        kms, cnt = ctx.timing_query(kname)
-        kern[kname] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps}
-    ctx.set_timing(False)
-    ctx.timing_reset()
+    # parity at full size: rows of this rank's block against the ORACLE (sets, order, distance bits)
+    checks = None
+    if not args.quick:
+        import oracle
+        oracle.build()
+        rows = sorted(set(np.linspace(lo, hi - 1, 24).astype(np.int64).tolist()))
+        gd = m.ref_dist[[r - lo for r in rows]].cpu().numpy()
+        gi = m.ref_idx[[r - lo for r in rows]].cpu().numpy()
+        ok, n = check_rows_against_oracle(X, tids, rows, gd, gi)
+        checks = {"rows_vs_oracle": n, "identical": ok}
+    sampler = ClockSampler(env.local)
+    ms, launches, clocks = timed_steps(env, step, steps, max(0, warmup - 1), sampler)
+    kern, _ = kernel_times(env, step, min(steps, 5), WIS_KERNELS)
     value = float(T) * T / (ms * 1e-3)
-    # e2e: host panel in, model out
-    hX = torch.from_numpy(X).pin_memory()
-    ht = torch.from_numpy(tids.view(np.int32)).pin_memory()
     k = min(T, opts.max_ref_targets)
+    e2e = None
+    if not args.quick and world == 1:
+        hX = torch.from_numpy(X).pin_memory()
+        ht = torch.from_numpy(tids.view(np.int32)).pin_memory()
+        h_idx = torch.empty((T, k), dtype=torch.int32, pin_memory=True)
+        h_len = torch.empty(T, dtype=torch.int32, pin_memory=True)
+        h_calls = torch.empty(T, dtype=torch.int32, pin_memory=True)
+        h_filt = torch.empty(T, dtype=torch.uint8, pin_memory=True)
 
-    h_idx = torch.empty((T, k), dtype=torch.int32, pin_memory=True)
-    h_len = torch.empty(T, dtype=torch.int32, pin_memory=True)
-    h_calls = torch.empty(T, dtype=torch.int32, pin_memory=True)
-    h_filt = torch.empty(T, dtype=torch.uint8, pin_memory=True)
+        def step_e2e():
+            mm = mw.run(hX.to(dev, non_blocking=True), ht.to(dev, non_blocking=True), opts, ctx=ctx)
+            h_idx.copy_(mm.ref_idx, non_blocking=True)
+            h_len.copy_(mm.ref_len, non_blocking=True)
+            h_calls.copy_(mm.num_calls, non_blocking=True)
+            h_filt.copy_(mm.filt, non_blocking=True)
+            torch.cuda.synchronize()
 
-    def step_e2e():
-        mm = mw.run(hX.to(dev, non_blocking=True), ht.to(dev, non_blocking=True), opts, ctx=ctx)
-        h_idx.copy_(mm.ref_idx, non_blocking=True)
-        h_len.copy_(mm.ref_len, non_blocking=True)
-        h_calls.copy_(mm.num_calls, non_blocking=True)
-        h_filt.copy_(mm.filt, non_blocking=True)
-        torch.cuda.synchronize()
-
-    step_e2e()
-    t0 = time.perf_counter()
-    esteps = max(1, min(args.steps, 3))
-    for _ in range(esteps):
         step_e2e()
-    e2e_s = (time.perf_counter() - t0) / esteps
-    peak_t = 1406.9
-    pfile = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pfile):
-        peak_t = float(json.load(open(pfile)).get("bf16_tflops_sustained", peak_t))
-    sweep = kern["wis_sweep_kernel"]["ms_per_step"]
-    achieved = 2.0 * T * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
+        t0 = time.perf_counter()
+        esteps = max(1, min(steps, 3))
+        for _ in range(esteps):
+            step_e2e()
+        e2e_s = (time.perf_counter() - t0) / esteps
+        e2e = {"value": float(T) * T / e2e_s, "unit": "bin-pairs/s", "h2d_bytes_per_step": int(X.nbytes + tids.nbytes),
+               "d2h_bytes_per_step": int(T * k * 4 + T * 9), "ms_per_step": e2e_s * 1e3}
+    peak_t, peak_src = measured_tensor_peak()
+    sweep = kern.get("wis_sweep_kernel", {}).get("ms_per_step", 0.0)
+    rows_n = hi - lo
+    algorithmic = 2.0 * rows_n * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
     # what the tensor cores executed: visited 256x128 tiles x padded K (projection windows skip the rest)
     tiles = float(stats["tiles"]) if stats else 0.0
     kp = ((S + 63) // 64) * 64
     executed = 2.0 * tiles * 256 * 128 * kp / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
-    tile_frac = tiles * 256 * 128 / (float(T) * T) if T else 0.0
+    tile_frac = tiles * 256 * 128 / (float(rows_n) * T) if T and rows_n else 0.0
     cpu = None
-    if not args.quick:
+    if not args.quick and world == 1:
         import oracle
-        oracle.build()
-        rows = min(args.cpu_rows, T)
+        rows_c = min(args.cpu_rows, T)
         ncpu = os.cpu_count() or 1
         t0 = time.perf_counter()
-        oracle.wis_distances(X, tids, 100, 0, rows, nthreads=ncpu)
+        oracle.wis_distances(X, tids, 100, 0, rows_c, nthreads=ncpu)
         dt_cpu = time.perf_counter() - t0
-        cpu = {"value": rows * float(T) / dt_cpu, "unit": "bin-pairs/s", "cores": ncpu, "kind": "port",
+        cpu = {"value": rows_c * float(T) / dt_cpu, "unit": "bin-pairs/s", "cores": ncpu, "kind": "port",
                "sample": "compute_distances for the first %d of %d target rows (all columns), %d threads as rayon "
-                         "does; linear in rows" % (rows, T, ncpu)}
-    line = {"metric": "WIS bin-pairs/s", "value": value, "unit": "bin-pairs/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (fp16 tensor filter + exact f32 re-score)", "data": "synthetic",
+                         "does; linear in rows" % (rows_c, T, ncpu)}
+    del dX, dt, m
+    env.free()
+    if rank != 0:
+        return None
+    return {"metric": "WIS bin-pairs/s", "value": value, "unit": "bin-pairs/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32 (fp16 tensor filter + exact f32 re-score)", "data": "synthetic",
             "config": {"workload": workload, "targets": T, "samples": S, "k": k,
+                       "parallelism": "single GPU" if world == 1 else "target rows / %d (cnvb_wis_build_sharded)" % world,
                        "l2": "panel %.0f MB + candidate buffers %.1f GB exceed L2" % (T * S * 4 / 1e6, T * 2048 * 8 / 1e9)},
-            "e2e": {"value": float(T) * T / e2e_s, "unit": "bin-pairs/s", "h2d_bytes_per_step": int(X.nbytes + tids.nbytes),
-                    "d2h_bytes_per_step": int(T * k * 4 + T * 9), "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": achieved, "peak": peak_t,
-                         "unit": "TFLOP/s", "frac": achieved / peak_t, "traffic": None,
-                         "algorithmic_flop_per_pair": 2 * S, "kernel_share_of_step": sweep / ms,
-                         "executed_tflops": executed, "tile_fraction_visited": tile_frac,
-                         "note": "achieved = 2*T*T*S / sweep time (SURVEY 8(d): the algorithmic count does not "
-                                 "change with the method); the sweep visits only tile_fraction_visited of the "
-                                 "pair matrix (projection windows), executed_tflops is what the tensor pipe did",
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
-            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern, "wis_stats": stats}
-    print(json.dumps(line))
-    return 0
+            "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": executed, "peak": peak_t,
+                         "unit": "TFLOP/s", "frac": executed / peak_t, "traffic": None,
+                         "what": "EXECUTED flops: visited 256x128 tiles x padded K (%d) x 2 / sweep time -- what the "
+                                 "tensor pipe did" % kp,
+                         "algorithmic_equiv": algorithmic, "algorithmic_flop_per_pair": 2 * S,
+                         "algorithmic_note": "2*rows*T*S / sweep time (SURVEY 8(d)'s count for the all-pairs "
+                                             "contraction); the projection windows skip most tiles, so this exceeds "
+                                             "what was executed and is NOT a roofline fraction",
+                         "tile_fraction_visited": tile_frac, "kernel_share_of_step": sweep / ms if ms else None,
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern, "wis_stats": stats, "checks": checks}
 
 
-def bench_hmm(args):
+def bench_hmm(args, env, steps=None, warmup=None):
     """BASELINE configs[3]: `cmd discover` on 100 samples x ~2.9 M bins (22 autosomes, 1 kbp windows):
-    one lane per (sample, contig).  One step = Viterbi segmentation of all lanes (state per bin)."""
-    import torch
-    import cnvetti_b200 as cb
-    from cnvetti_b200 import discover
+    one lane per (sample, contig).  One step = Viterbi segmentation of all lanes (state per bin).
+    N > 1: the samples are sharded over the ranks (lanes are independent, no collective)."""
+    torch = env.torch
+    from cnvetti_b200 import discover, parallel
     from cnvetti_b200.synth import HG38_AUTOSOMES
-    n_samples = args.hmm_samples
-    dev = "cuda:0"
-    ctx = cb.Context(0)
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    n_total = args.hmm_samples
+    dev, ctx, world, rank = env.dev, env.ctx, env.world, env.rank
+    s_lo, s_hi = parallel.shard_rows(n_total, rank, world)
+    n_samples = s_hi - s_lo
     lens = [(L + 999) // 1000 for L in HG38_AUTOSOMES]
+    bins_per_sample = int(sum(lens))
     lane_len = np.array(lens * n_samples, np.int64)
     lane_off = np.concatenate([[0], np.cumsum(lane_len)]).astype(np.uint64)
     n_bins = int(lane_off[-1])
     g = torch.Generator(device=dev)
-    g.manual_seed(4)
+    g.manual_seed(4 + 7919 * rank)
     cn = torch.full((n_bins,), 2.0, device=dev)
-    # planted segments: ~20 per lane, 5..500 bins, cn in {0,1,3,4}
-    nseg = 20 * len(lane_len)
-    seg_start = (torch.rand(nseg, generator=g, device=dev) * (n_bins - 600)).long()
+    nseg = 20 * len(lane_len)  # planted segments: ~20 per lane, 5..500 bins, cn in {0,1,3,4}
+    seg_start = (torch.rand(nseg, generator=g, device=dev) * max(1, n_bins - 600)).long()
     seg_len = (torch.rand(nseg, generator=g, device=dev) * 495).long() + 5
     seg_cn = torch.tensor([0.0, 1.0, 3.0, 4.0], device=dev)[(torch.rand(nseg, generator=g, device=dev) * 4).long().clamp_(0, 3)]
     delta = torch.zeros(n_bins + 1, device=dev)
@@ -397,8 +549,9 @@ def bench_hmm(args):
     del delta, cn, mu
     sigma = np.full(len(lane_len), 0.08)
     opts = discover.DiscoverOptions()
+    total_bins = bins_per_sample * n_total
     workload = "cfg4: cmd discover (5-state HMM Viterbi), %d samples x %d bins = %d lanes" % (
-        n_samples, n_bins // n_samples, len(lane_len))
+        n_total, bins_per_sample, 22 * n_total)
 
     def step():
         return discover.hmm_segment(cv, lane_off, sigma, opts, ctx=ctx)
@@ -406,59 +559,48 @@ def bench_hmm(args):
     st = step()
     torch.cuda.synchronize()
     frac_cn2 = float((st == 2).float().mean().item())
-    sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
-    for _ in range(max(0, args.warmup - 1)):
-        step()
-    torch.cuda.synchronize()
-    sampler.start()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = ctx.launch_count - l0
-    # per-kernel times: a second, instrumented pass (timing mode serialises what the timed steps overlap)
-    ctx.set_timing(True)
-    ctx.timing_reset()
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    kern = {}
-    for kname in HMM_KERNELS:
-        kms, cnt = ctx.timing_query(kname)
-        if cnt:
-            kern[kname] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps}
-    ctx.set_timing(False)
-    ctx.timing_reset()
-    # e2e: pinned host CV in, states out
-    hcv = torch.empty(n_bins, dtype=torch.float32, pin_memory=True)
-    hcv.copy_(cv)
-    hst = torch.empty(n_bins, dtype=torch.uint8, pin_memory=True)
+    # parity at full size: whole lanes of the first sample against the oracle's sequential Viterbi
+    checks = None
+    if not args.quick and rank == 0:
+        import oracle
+        oracle.build()
+        tab = oracle.hmm_tables(0.08, opts.sigma0, opts.eps_cn, opts.p_move)
+        ok, nl = True, 0
+        for li in (0, 10, 21):
+            a, b = int(lane_off[li]), int(lane_off[li + 1])
+            ok &= bool(np.array_equal(oracle.hmm_viterbi(cv[a:b].cpu().numpy(), tab), st[a:b].cpu().numpy()))
+            nl += 1
+        checks = {"lanes_vs_oracle": nl, "identical": ok}
+    sampler = ClockSampler(env.local)
+    ms, launches, clocks = timed_steps(env, step, steps, max(0, warmup - 1), sampler)
+    kern, _ = kernel_times(env, step, min(steps, 5), HMM_KERNELS)
+    e2e = None
+    if not args.quick and world == 1:
+        hcv = torch.empty(n_bins, dtype=torch.float32, pin_memory=True)
+        hcv.copy_(cv)
+        hst = torch.empty(n_bins, dtype=torch.uint8, pin_memory=True)
 
-    def step_e2e():
-        s_ = discover.hmm_segment(hcv.to(dev, non_blocking=True), lane_off, sigma, opts, ctx=ctx)
-        hst.copy_(s_, non_blocking=True)
-        torch.cuda.synchronize()
+        def step_e2e():
+            s_ = discover.hmm_segment(hcv.to(dev, non_blocking=True), lane_off, sigma, opts, ctx=ctx)
+            hst.copy_(s_, non_blocking=True)
+            torch.cuda.synchronize()
 
-    step_e2e()
-    esteps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(esteps):
         step_e2e()
-    e2e_s = (time.perf_counter() - t0) / esteps
+        esteps = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            step_e2e()
+        e2e_s = (time.perf_counter() - t0) / esteps
+        e2e = {"value": n_bins / e2e_s, "unit": "bins/s", "h2d_bytes_per_step": n_bins * 4,
+               "d2h_bytes_per_step": n_bins, "ms_per_step": e2e_s * 1e3}
     peak, peak_src = measured_peak()
     dom = max(kern, key=lambda k_: kern[k_]["ms_per_step"]) if kern else None
     dom_ms = kern[dom]["ms_per_step"] if dom else 0.0
-    achieved = HMM_BYTES_PER_BIN * n_bins / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    kernels_ms = sum(v["ms_per_step"] for v in kern.values())
     cpu = None
-    if not args.quick:
+    if not args.quick and world == 1:
         import oracle
         from concurrent.futures import ThreadPoolExecutor
-        oracle.build()
         ncpu = os.cpu_count() or 1
         nl = min(len(lens), 22)
         host = cv[:int(lane_off[nl])].cpu().numpy()
@@ -470,34 +612,40 @@ def bench_hmm(args):
         dt_cpu = time.perf_counter() - t0
         cpu = {"value": host.size / dt_cpu, "unit": "bins/s", "cores": min(ncpu, nl), "kind": "port",
                "sample": "one sample (22 lanes, %d bins), oracle Viterbi, one lane per thread" % host.size}
-    line = {"metric": "HMM bins/s", "value": n_bins / (ms * 1e-3), "unit": "bins/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fixed-point i32 scores from f64 emissions", "data": "synthetic",
-            "config": {"workload": workload, "samples": n_samples, "bins": n_bins, "lanes": len(lane_len),
-                       "frac_cn2": frac_cn2,
+    del cv, st
+    env.free()
+    if rank != 0:
+        return None
+    step_gbs = HMM_BYTES_PER_BIN * n_bins / (ms * 1e-3) / 1e9
+    return {"metric": "HMM bins/s", "value": total_bins / (ms * 1e-3), "unit": "bins/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "fixed-point i32 scores from f32 emissions", "data": "synthetic",
+            "config": {"workload": workload, "samples": n_total, "bins": total_bins, "lanes": 22 * n_total,
+                       "frac_cn2": frac_cn2, "parallelism": "single GPU" if world == 1 else "samples / %d, no collective" % world,
                        "l2": "CV %.1f GB/step exceeds L2" % (n_bins * 4 / 1e9)},
-            "e2e": {"value": n_bins / e2e_s, "unit": "bins/s", "h2d_bytes_per_step": n_bins * 4,
-                    "d2h_bytes_per_step": n_bins, "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+            "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "all HMM kernels of a step (%s dominant)" % dom,
+                         "achieved": step_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": step_gbs / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_bin": HMM_BYTES_PER_BIN,
-                         "kernel_share_of_step": dom_ms / ms if ms else None},
-            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
-    print(json.dumps(line))
-    return 0
+                         "what": "11 B/bin x bins of this rank / step time (the step IS the kernel chain; three "
+                                 "lane groups overlap on side streams)",
+                         "dominant_kernel_ms": dom_ms, "kernels_ms_serialised": kernels_ms,
+                         "kernel_share_of_step": dom_ms / kernels_ms if kernels_ms else None},
+            "cpu_baseline": cpu, "clocks": clocks, "kernels": kern, "checks": checks}
 
 
-def bench_piles(args):
+def bench_piles(args, env, steps=None, warmup=None):
     """`--mask-piles` pass of cmd coverage (lib-coverage/src/piles.rs) on BASELINE configs[0]'s input:
     chr22, ~15 M reads.  One step = collect_piles of the contig (pile list in HBM)."""
-    import torch
+    torch = env.torch
     import cnvetti_b200 as cb
     from cnvetti_b200 import piles as pl
     from cnvetti_b200 import synth_torch
     from cnvetti_b200.synth import CHR22_LEN
-    dev = "cuda:0"
-    ctx = cb.Context(0)
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    dev, ctx = env.dev, env.ctx
     L = int(CHR22_LEN * args.scale)
     n_pairs = int(7_600_000 * args.scale)
     soa = synth_torch.synth_soa_contig(22, L, n_pairs, dev)
@@ -507,25 +655,12 @@ def bench_piles(args):
     Lc = int(soa["end"].max().item()) + 1
     col = pl.PileCollector(20, MIN_MAPQ, ctx=ctx)
     got = col.collect_piles(batch, Lc)
-    sampler = ClockSampler(0)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
-    for _ in range(max(0, args.warmup - 1)):
-        col.collect_piles(batch, Lc)
-    torch.cuda.synchronize()
-    sampler.start()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        col.collect_piles(batch, Lc)
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = ctx.launch_count - l0
+    sampler = ClockSampler(env.local)
+    ms, launches, clocks = timed_steps(env, lambda: col.collect_piles(batch, Lc), steps, max(0, warmup - 1), sampler)
     hb = cb.ReadBatch(**{k: getattr(batch, k).cpu().pin_memory() for k in ("pos", "end", "mapq", "flags")})
     col.collect_piles(hb, Lc)
     t0 = time.perf_counter()
-    esteps = max(1, min(args.steps, 3))
+    esteps = max(1, min(steps, 3))
     for _ in range(esteps):
         col.collect_piles(hb, Lc)
     e2e_s = (time.perf_counter() - t0) / esteps
@@ -544,8 +679,12 @@ def bench_piles(args):
         cpu = {"value": nsub / dt_cpu, "unit": "reads/s", "cores": 1, "kind": "port",
                "sample": "first %d reads of the contig: per-base depth pass + base-by-base pile walk, single thread" % nsub}
     peak, peak_src = measured_peak()
-    line = {"metric": "aligned reads/s (pile collection)", "value": n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    del soa, batch
+    env.free()
+    if env.rank != 0:
+        return None
+    return {"metric": "aligned reads/s (pile collection)", "value": n_reads / (ms * 1e-3), "unit": "reads/s", "n_gpus": 1,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "cfg1 input (chr22, %d reads): cmd coverage --mask-piles, pile collection" % n_reads,
                        "piles": len(got), "max_pile_size": int(got.size.max()) if len(got) else 0,
@@ -558,55 +697,64 @@ def bench_piles(args):
                          "peak_source": peak_src, "algorithmic_bytes_per_read": 11,
                          "note": "whole call (two host syncs for the counts included), not a single kernel"},
             "cpu_baseline": cpu, "clocks": clocks}
-    print(json.dumps(line))
-    return 0
 
 
-def bench_cfg1(args):
+CFG1_KERNELS = ("frag_bin_gw_kernel", "frag_bin_tgt_kernel", "depth_tile_kernel", "depth_prepare_kernel",
+                "depth_ranges_kernel", "window_finalize_kernel", "next_covered_kernel", "depth_region_kernel")
+
+
+def bench_cfg1(args, env, steps=None, warmup=None):
     """BASELINE configs[0]: one contig (chr22, ~15 M reads), 1 kbp windows, MAPQ >= 20; the three
     aggregator kinds of lib-coverage/src/lib.rs:510-529.  `value` is count kind Coverage (per-base
-    depth mean/SD per window, the heaviest kind); the two Fragments kinds are reported beside it."""
-    import torch
+    depth mean/SD per window, the heaviest kind); the two Fragments kinds are reported beside it, each
+    with its own roofline fraction.  A single region does not shard: at N > 1 rank 0 alone runs it."""
+    torch = env.torch
     import cnvetti_b200 as cb
     from cnvetti_b200 import pipeline, synth, synth_torch
     from cnvetti_b200.synth import CHR22_LEN
-    dev = "cuda:0"
-    ctx = cb.Context(0)
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    if env.rank != 0:
+        return None
+    dev, ctx = env.dev, env.ctx
     L = int(CHR22_LEN * args.scale)
     soa = synth_torch.synth_soa_contig(22, L, int(7_600_000 * args.scale), dev)
     Lc = int(soa["end"].max().item()) + 1000
     batch = cb.ReadBatch(**{k: soa[k].contiguous() for k in ("pos", "end", "mid", "frag_end", "mapq", "flags")})
     n_reads = len(batch)
     ts, te = synth.synth_targets(22, L, int(4000 * args.scale) + 10)
+    n_windows = (Lc + 999) // 1000
     kinds = {
+        # SURVEY 8(d): Coverage 11 B/read + 8 B/base (difference array write + read; it lives in shared memory
+        # here, so only the 11 B/read + 8 B/window out reach HBM -- both figures are reported)
         "coverage": (cb.CoverageOptions(window_length=1000, min_mapq=MIN_MAPQ, count_kind="Coverage"), None, 11),
         "fragments_gw": (cb.CoverageOptions(window_length=1000, min_mapq=MIN_MAPQ), None, 7),
         "fragments_targets": (cb.CoverageOptions(window_length=None, min_mapq=MIN_MAPQ, considered_regions="TargetRegions"),
                               (ts, te), 11),
     }
+    peak, peak_src = measured_peak()
     res = {}
     clocks = None
     launches = 0
+    solo = Env.__new__(Env)  # this workload runs on rank 0 alone: no barrier / reduction over ranks
+    solo.__dict__.update(env.__dict__)
+    solo.dist = None
     for name, (opts, targets, bpr) in kinds.items():
         prep = pipeline.PreparedRegions([pipeline.Region("chr22", Lc, batch, None, targets=targets)], opts)
-        for _ in range(max(1, args.warmup)):
-            pipeline.coverage_run(prep, opts, ctx=ctx)
-        sampler = ClockSampler(0) if name == "coverage" else None
-        torch.cuda.synchronize()
+        sampler = ClockSampler(env.local) if name == "coverage" else None
+        step = lambda: pipeline.coverage_run(prep, opts, ctx=ctx)  # noqa: E731
+        ms, ln, ck = timed_steps(solo, step, steps, max(1, warmup), sampler)
         if sampler:
-            sampler.start()
-        l0 = ctx.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            pipeline.coverage_run(prep, opts, ctx=ctx)
-        e1.record()
-        torch.cuda.synchronize()
-        if sampler:
-            clocks = sampler.stop()
-            launches = ctx.launch_count - l0
-        ms = e0.elapsed_time(e1) / args.steps
-        res[name] = {"ms_per_step": ms, "reads_per_s": n_reads / (ms * 1e-3), "algorithmic_gbs": n_reads * bpr / (ms * 1e-3) / 1e9}
+            clocks, launches = ck, ln
+        kern, _ = kernel_times(solo, step, min(steps, 5), CFG1_KERNELS)
+        gbs = n_reads * bpr / (ms * 1e-3) / 1e9
+        res[name] = {"ms_per_step": ms, "reads_per_s": n_reads / (ms * 1e-3), "algorithmic_bytes_per_read": bpr,
+                     "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "launches_per_step": ln / steps,
+                     "kernels": kern}
+    cov = res["coverage"]
+    cov["survey_bytes_per_step"] = n_reads * 11 + 8 * Lc + 8 * n_windows
+    cov["survey_gbs"] = cov["survey_bytes_per_step"] / (cov["ms_per_step"] * 1e-3) / 1e9
+    cov["survey_frac_of_hbm_peak"] = cov["survey_gbs"] / peak
     # end to end (Coverage kind): pinned host columns in, table out
     opts = kinds["coverage"][0]
     hb = cb.ReadBatch(**{k: getattr(batch, k).cpu().pin_memory() for k in ("pos", "end", "mapq", "flags")})
@@ -619,165 +767,155 @@ def bench_cfg1(args):
         return out
 
     step_e2e()
-    esteps = max(1, min(args.steps, 5))
+    esteps = max(1, min(steps, 5))
     t0 = time.perf_counter()
     for _ in range(esteps):
         out = step_e2e()
     e2e_s = (time.perf_counter() - t0) / esteps
     cpu = None
+    checks = None
     if not args.quick:
+        # the whole contig through the oracle: CPU baseline AND parity at full size, all three kinds
         import oracle
         oracle.build()
-        nsub = min(n_reads, 4_000_000)
-        d = synth_torch.soa_to_oracle_records(soa, 0, nsub)
-        Ls = int(d["pos"].max()) + 2000
+        d = synth_torch.soa_to_oracle_records(soa)
         rb = oracle.ReadBatch(d["pos"], d["isize"], d["flag"], d["mapq"], d["cigar_off"], d["cigar"])
+        oopts = oracle.cov_opts(window_length=1000, min_mapq=MIN_MAPQ)
         t0 = time.perf_counter()
-        oracle.coverage(rb, oracle.cov_opts(window_length=1000, min_mapq=MIN_MAPQ), Ls)
-        dt_cpu = time.perf_counter() - t0
-        cpu = {"value": nsub / dt_cpu, "unit": "reads/s", "cores": 1, "kind": "port",
-               "sample": "first %d reads of the contig, CoverageAggregator restatement, single thread" % nsub}
-    peak, peak_src = measured_peak()
-    cov = res["coverage"]
+        omean, osd = oracle.coverage(rb, oopts, Lc)
+        dt_cov = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ocounts, oproc, oskip = oracle.frag_gw(rb, oopts, Lc)
+        dt_gw = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        otc, otp, ots = oracle.frag_targets(rb, oracle.cov_opts(window_length=0, min_mapq=MIN_MAPQ), ts, te)
+        dt_tg = time.perf_counter() - t0
+        cpu = {"value": n_reads / dt_cov, "unit": "reads/s", "cores": 1, "kind": "port",
+               "sample": "the whole contig (%d reads), CoverageAggregator restatement, single thread" % n_reads,
+               "fragments_gw_reads_per_s": n_reads / dt_gw, "fragments_targets_reads_per_s": n_reads / dt_tg}
+        tables = {}
+        for name, (o, targets, _) in kinds.items():
+            tables[name] = pipeline.coverage_run([pipeline.Region("chr22", Lc, batch, None, targets=targets)], o, ctx=ctx)
+        torch.cuda.synchronize()
+        bits = lambda x: np.ascontiguousarray(x.cpu().numpy() if hasattr(x, "cpu") else x, np.float32).view(np.uint32)  # noqa: E731
+        c = tables["coverage"]
+        sd_g, fin = c.rcvsd.cpu().numpy(), np.isfinite(osd)
+        ok_cov = bool(np.array_equal(bits(c.rcv), bits(omean))) and bool(
+            np.allclose(sd_g[fin], osd[fin], rtol=1e-6, atol=0) and np.array_equal(np.isfinite(sd_g), fin))
+        g = tables["fragments_gw"]
+        ok_gw = bool(np.array_equal(g.rcv.cpu().numpy().astype(np.int64), ocounts.astype(np.int64))) and \
+            g.num_processed == [oproc] and g.num_skipped == [oskip]
+        t = tables["fragments_targets"]
+        ok_tg = bool(np.array_equal(t.rcv.cpu().numpy().astype(np.int64), otc.astype(np.int64))) and \
+            t.num_processed == [otp] and t.num_skipped == [ots]
+        checks = {"what": "the whole contig against the oracle: window means bit-exact + SD rel 1e-6 (Coverage), "
+                          "counts and tallies (both Fragments kinds)",
+                  "coverage": ok_cov, "fragments_gw": ok_gw, "fragments_targets": ok_tg,
+                  "identical": ok_cov and ok_gw and ok_tg}
     line = {"metric": "aligned reads/s binned (count kind Coverage)", "value": cov["reads_per_s"], "unit": "reads/s",
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cov["ms_per_step"],
+            "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": cov["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 depths, f32 mean/sd", "data": "synthetic",
             "config": {"workload": "cfg1: chr22, %d reads, 1 kbp windows, MAPQ>=%d; Coverage / Fragments GW / Fragments targets"
                                    % (n_reads, MIN_MAPQ), "targets": int(ts.size),
+                       "parallelism": "one region: does not shard (rank 0 alone at N > 1)",
                        "l2": "read columns %.0f MB exceed L2" % (n_reads * 11 / 1e6)},
             "e2e": {"value": n_reads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n_reads * 11,
                     "d2h_bytes_per_step": int(sum(o.numel() * 4 for o in out)), "ms_per_step": e2e_s * 1e3},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "coverage_run (depth_prepare + depth_tile + finalize)",
+            "roofline": {"bound": "hbm", "kernel": "count kind Coverage: the whole region call",
                          "achieved": cov["algorithmic_gbs"], "peak": peak, "unit": "GB/s", "frac": cov["algorithmic_gbs"] / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_read": 11,
-                         "note": "whole region call, not a single kernel"},
-            "cpu_baseline": cpu, "clocks": clocks, "kinds": res,
+                         "survey_equiv": {"bytes_per_step": cov["survey_bytes_per_step"], "achieved": cov["survey_gbs"],
+                                          "frac": cov["survey_frac_of_hbm_peak"],
+                                          "what": "SURVEY 8(d)'s count incl. 8 B/base for the difference array, which "
+                                                  "never leaves the SM here"},
+                         "note": "whole region call, not a single kernel; `kinds` holds the same for both Fragments kinds"},
+            "cpu_baseline": cpu, "clocks": clocks, "kinds": res, "checks": checks,
             "host_bam_decode": host_bam_decode_leg() if not args.quick else None,
             "file_level": file_level_leg() if not args.quick else None}
-    print(json.dumps(line))
-    return 0
+    del soa, batch
+    env.free()
+    return line
 
 
-def bench_cfg5(args):
+def bench_cfg5(args, env, steps=None, warmup=None):
     """BASELINE configs[4]: end-to-end WIS germline calling of a synthetic cohort (T targets x S samples):
     TotalCovSum per sample -> merge-cov -> build-model-wis -> mod-coverage for every sample -> HMM.
     Strong scaling: the cohort is fixed; samples are sharded for normalise / segmentation, target rows for
-    the model and mod-coverage (one NCCL all-gather of the panel, one all-to-all of the relative coverage)."""
-    import torch
-    import torch.distributed as dist
-    import cnvetti_b200 as cb
+    the model and mod-coverage (one all-gather of the panel, one all-to-all of the relative coverage; NCCL
+    inside the library, on the context's stream)."""
+    torch = env.torch
     from cnvetti_b200 import model_wis as mw, parallel, pipeline, synth_torch
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = "cuda:%d" % local
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-    ctx = cb.Context(local)
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    rank, world, dev, ctx = env.rank, env.world, env.dev, env.ctx
     T, S = args.targets or 3_000_000, args.samples or 1000
     ranges = [parallel.shard_rows(S, r, world) for r in range(world)]
     a, b = ranges[rank]
-    t_gen = time.perf_counter()
     lcv, tids = synth_torch.synth_cohort_lcv(5, T, a, b, dev)
     torch.cuda.synchronize()
-
-    def log(msg):
-        if rank == 0:
-            sys.stderr.write("[cfg5 %7.1f s] %s\n" % (time.perf_counter() - t_gen, msg))
-            sys.stderr.flush()
-
-    log("cohort generated: %d targets x %d samples" % (T, b - a))
-    opts = mw.BuildModelWisOptions(engine=mw.ENGINE_TENSOR)
+    env.log("cfg5 cohort generated: %d targets x %d samples" % (T, b - a))
+    opts = mw.BuildModelWisOptions.quick(engine=mw.ENGINE_TENSOR)
     workload = ("cfg5: WIS germline calling, synthetic cohort %d targets x %d samples: TotalCovSum, merge-cov, "
                 "build-model-wis (k=100, tensor engine), mod-coverage, HMM segmentation" % (T, S))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step(timings=None):
-        r = pipeline.wis_call_cohort(lcv, tids, sample_ranges=ranges, wis_options=opts, sigma=0.08, ctx=ctx,
-                                     timings=timings)
+        r = pipeline.wis_call_cohort(lcv, tids, sample_ranges=ranges, wis_options=opts, sigma=0.08, timings=timings,
+                                     comm=env.comm)
         n_alt = int((r["states"] != 2).sum().item())  # the step's result, read back
         return r, n_alt
 
     first = {}
     r, n_alt = step(first)
     stats = mw.last_stats(ctx)
-    log("first step: stages %s; engine %s; alt bins %d" % ({k_: round(v, 3) for k_, v in first.items()}, stats, n_alt))
-    # spot check at full size: 64 rows of this rank's block against the exact f32 engine
+    env.log("cfg5 first step: stages %s; engine %s; alt bins %d" % ({k_: round(v, 3) for k_, v in first.items()}, stats, n_alt))
     lo, hi = r["rows"]
     m = r["model"]
-    pick = torch.linspace(0, hi - lo - 1, 64).long().tolist() if hi > lo else []
-    exact_opts = mw.BuildModelWisOptions(engine=mw.ENGINE_EXACT)
-    spot_ok = True
-    for q in pick:
-        d1, i1 = mw.compute_distances(r["panel"], tids, exact_opts, row_begin=lo + q, row_end=lo + q + 1, ctx=ctx)
-        spot_ok &= bool(torch.equal(d1[0].view(torch.int32), m["ref_dist"][q].view(torch.int32)))
+    # parity at full size: rows of rank 0's block against the ORACLE (reference sets, order, distance bits)
+    checks = {"alt_bins": n_alt}
+    if not args.quick and rank == 0:
+        import oracle
+        oracle.build()
+        n_rows = 32 if (os.cpu_count() or 1) >= 16 else 8
+        rows = sorted(set(np.linspace(lo, hi - 1, n_rows).astype(np.int64).tolist()))
+        gd = m["ref_dist"][[q - lo for q in rows]].cpu().numpy()
+        gi = m["ref_idx"][[q - lo for q in rows]].cpu().numpy()
+        try:
+            t0 = time.perf_counter()
+            Xh = r["panel"].cpu().numpy()
+            th = tids.cpu().numpy().astype(np.uint32)
+            ok, n = check_rows_against_oracle(Xh, th, rows, gd, gi)
+            checks.update({"rows_vs_oracle": n, "identical": ok, "oracle_seconds": round(time.perf_counter() - t0, 1)})
+            del Xh
+        except MemoryError:
+            checks.update({"rows_vs_oracle": 0, "identical": None, "note": "host memory too small for the panel"})
+        env.log("cfg5 oracle rows: %s" % checks)
     del r, m
-    log("spot check of %d rows against the exact engine: %s" % (len(pick), spot_ok))
-    sampler = ClockSampler(local)
-    for _ in range(max(0, args.warmup - 1)):
-        step()
-    barrier()
-    sampler.start()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    launches = ctx.launch_count - l0
-    # stage breakdown (host clock around each stage, one extra step) and the sweep's share
+    sampler = ClockSampler(env.local)
+    ms, launches, clocks = timed_steps(env, step, steps, max(0, warmup - 1), sampler)
     stages = {}
-    step(stages)
-    ctx.set_timing(True)
-    ctx.timing_reset()
-    step()
-    torch.cuda.synchronize()
-    kern = {}
-    for kname in ("wis_sweep_kernel", "wis_compact_kernel", "wis_rescore_kernel", "wis_calls_kernel",
-                  "modcov_panel_kernel") + tuple(HMM_KERNELS):
-        kms, cnt = ctx.timing_query(kname)
-        if cnt:
-            kern[kname] = {"ms_per_step": kms, "launches_per_step": cnt}
-    ctx.set_timing(False)
-    ctx.timing_reset()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-    peak_t = 1406.9
-    pfile = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pfile):
-        peak_t = float(json.load(open(pfile)).get("bf16_tflops_sustained", peak_t))
+    step(stages)  # stage breakdown (host clock around each stage, one extra step)
+    kern, _ = kernel_times(env, step, 1, WIS_KERNELS + HMM_KERNELS + ("sum_f32_dd_kernel", "norm_total_map_kernel"))
+    peak_t, peak_src = measured_tensor_peak()
     sweep = kern.get("wis_sweep_kernel", {}).get("ms_per_step", 0.0)
-    rows = hi - lo
+    rows_n = hi - lo
     kp = ((S + 63) // 64) * 64
     tiles = float(stats["tiles"]) if stats else 0.0
     executed = 2.0 * tiles * 256 * 128 * kp / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
-    achieved = 2.0 * rows * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
+    algorithmic = 2.0 * rows_n * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
     cpu = None
     e2e = None
     if not args.quick and world == 1:
         # end to end from pinned host memory: LCV columns in, state paths out
-        h_in = torch.empty(lcv.shape, dtype=torch.float32, pin_memory=True)
+        h_in, _ = host_buffer(lcv.shape, torch.float32, torch)
         h_in.copy_(lcv)
-        h_out = torch.empty((S, T), dtype=torch.uint8, pin_memory=True)
+        h_out, _ = host_buffer((S, T), torch.uint8, torch)
         del lcv
+        env.free()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         d_in = h_in.to(dev, non_blocking=True)
-        rr = pipeline.wis_call_cohort(d_in, tids, sample_ranges=ranges, wis_options=opts, sigma=0.08, ctx=ctx)
+        rr = pipeline.wis_call_cohort(d_in, tids, sample_ranges=ranges, wis_options=opts, sigma=0.08, comm=env.comm)
         h_out.copy_(rr["states"], non_blocking=True)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
@@ -785,21 +923,25 @@ def bench_cfg5(args):
                "d2h_bytes_per_step": int(h_out.numel()), "ms_per_step": e2e_s * 1e3, "steps": 1}
         # CPU baseline: a bounded sample of the stage that dominates the CPU run
         import oracle
-        oracle.build()
         ncpu = os.cpu_count() or 1
         nrows, cols = min(args.cpu_rows, 256), min(T, 200_000)
         pick_c = torch.arange(cols, device=dev) * (T // cols)  # spread over the genome (all contigs)
         Xs = np.ascontiguousarray(rr["panel"][pick_c].cpu().numpy())
         th = tids[pick_c].cpu().numpy().astype(np.uint32)
-        del rr, d_in
+        del rr, d_in, h_in, h_out
         t0 = time.perf_counter()
         oracle.wis_distances(Xs, th, 100, 0, nrows, nthreads=ncpu)
         dt_cpu = time.perf_counter() - t0
         cpu = {"value": nrows * float(cols) / dt_cpu, "unit": "bin-pairs/s", "cores": ncpu, "kind": "port",
                "sample": "compute_distances (the stage that dominates the CPU run) for %d target rows x %d columns x %d "
                          "samples, %d threads as rayon does; linear in rows and columns" % (nrows, cols, S, ncpu)}
-    line = {"metric": "WIS bin-pairs/s", "value": float(T) * T / (ms * 1e-3), "unit": "bin-pairs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+    else:
+        del lcv
+    env.free()
+    if rank != 0:
+        return None
+    return {"metric": "WIS bin-pairs/s", "value": float(T) * T / (ms * 1e-3), "unit": "bin-pairs/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (fp16 tensor filter + exact f32 re-score), f64 statistics, i32 HMM scores",
             "data": "synthetic",
             "config": {"workload": workload, "targets": T, "samples": S, "k": 100, "bins_segmented": T * S,
@@ -807,184 +949,153 @@ def bench_cfg5(args):
                                       "WIS+mod-coverage" % (world, world),
                        "l2": "panel %.1f GB exceeds L2" % (T * S * 4 / 1e9)},
             "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": achieved, "peak": peak_t,
-                         "unit": "TFLOP/s", "frac": achieved / peak_t, "traffic": None,
-                         "executed_tflops": executed, "executed_frac": executed / peak_t,
-                         "tile_fraction_visited": tiles * 256 * 128 / (float(rows) * T) if rows else None,
-                         "kernel_share_of_step": sweep / ms if ms else None,
-                         "note": "achieved = 2*rows*T*S / sweep time (rank 0's row block); executed_tflops = visited "
-                                 "256x128 tiles x padded K: what the tensor pipe did",
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": executed, "peak": peak_t,
+                         "unit": "TFLOP/s", "frac": executed / peak_t, "traffic": None,
+                         "what": "EXECUTED flops (rank 0): visited 256x128 tiles x padded K x 2 / sweep time",
+                         "algorithmic_equiv": algorithmic,
+                         "tile_fraction_visited": tiles * 256 * 128 / (float(rows_n) * T) if rows_n else None,
+                         "kernel_share_of_step": sweep / ms if ms else None, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks, "kernels": kern,
-            "stages_s": {k_: round(v, 4) for k_, v in stages.items()}, "wis_stats": stats,
-            "checks": {"alt_bins": n_alt, "spot_rows_vs_exact_engine": len(pick), "spot_identical": spot_ok}}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0 if spot_ok else 1
+            "stages_s": {k_: round(v, 4) for k_, v in stages.items()}, "wis_stats": stats, "checks": checks}
 
 
-def main():
-    args = parse_args()
-    if args.workload == "cfg5" and args.impl == "b200":
-        return bench_cfg5(args)
-    if args.workload == "cfg1" and args.impl == "b200":
-        return bench_cfg1(args)
-    if args.workload == "piles" and args.impl == "b200":
-        return bench_piles(args)
-    if args.workload == "hmm" and args.impl == "b200":
-        return bench_hmm(args)
-    if args.workload == "wis" and args.impl == "b200":
-        return bench_wis(args)
-    import torch
-    import torch.distributed as dist
-
+def reference_arm(args):
+    """--impl reference: the restated reference CPU path (oracle/) of the headline workload on a bounded
+    sample, plus bounded samples of the other BASELINE metrics under `workloads`.  Rank 0 alone runs."""
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    distributed = world > 1
-    if args.impl == "reference" and rank != 0:
-        return 0  # rank 0 alone runs the CPU arm
-
-    if not torch.cuda.is_available():
-        if args.impl == "reference":
-            dev = None
-        else:
-            print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
-            return 2
-    else:
-        torch.cuda.set_device(local_rank)
-        dev = "cuda:%d" % local_rank
-    if distributed and args.impl == "b200":
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-
-    import cnvetti_b200 as cb
-    from cnvetti_b200 import pipeline, synth, synth_torch
-
+    if rank != 0:
+        return 0
+    import torch
+    from cnvetti_b200 import synth, synth_torch
+    import oracle
+    oracle.build()
+    gdev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() else "cpu"
     regs = contigs(args.scale)
     n_pairs = [max(1000, int(round(L * READS_PER_BP / 2))) for _, L in regs]
-    workload = ("cfg2: cmd coverage (Fragments, %d bp windows, MAPQ>=%d, GC from reference) + normalize "
-                "MedianGcBinned, synthetic 30x WGS chr1-22" % (WINDOW, MIN_MAPQ))
-
-    # ---- reference arm: CPU only --------------------------------------------------------------
     k = max(1, min(args.cpu_sample_contigs, len(regs)))
     sample_ids = list(range(len(regs) - k, len(regs)))
-
-    def make_cpu_sample():
-        out = []
-        for ci in sample_ids:
-            L = regs[ci][1]
-            gdev = dev or "cpu"
-            soa = synth_torch.synth_soa_contig(2 * 1000 + ci + 7919 * rank, L, n_pairs[ci], gdev)
-            d = synth_torch.soa_to_oracle_records(soa)
-            seq = synth_torch.synth_reference_torch(2 * 1000 + ci, L, gdev).cpu().numpy()
-            out.append((d, L, seq))
-            del soa
-        return out
-
-    if args.impl == "reference":
-        sample = make_cpu_sample()
-        n_reads, dt = cpu_reference_leg(sample, max(1, args.steps), max(1, min(args.warmup, 1)))
-        val = n_reads / dt
-        desc = "%s (%.0f M reads) of the workload" % ("+".join(regs[i][0] for i in sample_ids), n_reads / 1e6)
-        line = {
-            "impl": "reference", "metric": "aligned reads/s binned", "value": val, "unit": "reads/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic", "config": {"workload": workload, "sample": desc},
-            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": 1, "kind": "port", "sample": desc,
-                             "host_cores_available": os.cpu_count()},
-            "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "restated reference CPU path (oracle/, plain C -O2); the Rust reference cannot be built "
-                    "here; cmd coverage/normalize are single-threaded in the reference",
-        }
-        print(json.dumps(line))
-        return 0
-
-    # ---- B200 arm ---------------------------------------------------------------------------------
-    ctx = cb.Context(local_rank)
-    opts = cb.CoverageOptions(window_length=WINDOW, min_mapq=MIN_MAPQ)
-    t_gen = time.perf_counter()
-    dev_regions, host_cols = [], []
-    n_reads = 0
-    for ci, (name, L) in enumerate(regs):
-        soa = synth_torch.synth_soa_contig(2 * 1000 + ci + 7919 * rank, L, n_pairs[ci], dev)
-        seq = synth_torch.synth_reference_torch(2 * 1000 + ci, L, dev)
-        batch = cb.ReadBatch(mid=soa["mid"].contiguous(), mapq=soa["mapq"].contiguous(), flags=soa["flags"].contiguous())
-        dev_regions.append(pipeline.Region(name, L, batch, seq))
-        n_reads += len(batch)
+    sample = []
+    for ci in sample_ids:
+        L = regs[ci][1]
+        soa = synth_torch.synth_soa_contig(2 * 1000 + ci, L, n_pairs[ci], gdev)
+        sample.append((synth_torch.soa_to_oracle_records(soa), L,
+                       synth_torch.synth_reference_torch(2 * 1000 + ci, L, gdev).cpu().numpy()))
         del soa
+    n_reads, dt, _ = cpu_reference_leg(sample, max(1, min(args.steps, 3)), 1)
+    del sample
+    val = n_reads / dt
+    desc = "%s (%.0f M reads) of the workload" % ("+".join(regs[i][0] for i in sample_ids), n_reads / 1e6)
+    ncpu = os.cpu_count() or 1
+    workloads = {}
+    if args.workload == "all" and args.scale >= 1.0:
+        # cfg3: compute_distances, bounded rows, all host threads (rayon's par_iter over rows)
+        T, S, rows = 200_000, 100, 1000
+        X, tids = synth.synth_panel(3, T, S)
+        t0 = time.perf_counter()
+        oracle.wis_distances(X, tids, 100, 0, rows, nthreads=ncpu)
+        d3 = time.perf_counter() - t0
+        workloads["cfg3"] = {"metric": "WIS bin-pairs/s", "value": rows * float(T) / d3, "unit": "bin-pairs/s",
+                             "cores": ncpu, "kind": "port",
+                             "sample": "compute_distances, first %d of %d rows x all columns x %d samples" % (rows, T, S)}
+        del X
+        # cfg4: the oracle's sequential Viterbi, one lane per thread
+        from concurrent.futures import ThreadPoolExecutor
+        from cnvetti_b200.synth import HG38_AUTOSOMES
+        lanes = [synth.synth_cv_lanes(400 + i, (L + 999) // 1000)[0] for i, L in enumerate(HG38_AUTOSOMES)]
+        tab = oracle.hmm_tables(0.08)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(ncpu) as ex:
+            list(ex.map(lambda x: oracle.hmm_viterbi(x, tab), lanes))
+        d4 = time.perf_counter() - t0
+        workloads["cfg4"] = {"metric": "HMM bins/s", "value": sum(x.size for x in lanes) / d4, "unit": "bins/s",
+                             "cores": min(ncpu, 22), "kind": "port", "sample": "one sample (22 lanes), one lane per thread"}
+        # cfg1: CoverageAggregator restatement on the first 4 M reads of chr22
+        d = synth.synth_bam_records(22, 13_000_000, 2_000_000)
+        rb = oracle.ReadBatch(d["pos"], d["isize"], d["flag"], d["mapq"], d["cigar_off"], d["cigar"])
+        t0 = time.perf_counter()
+        oracle.coverage(rb, oracle.cov_opts(window_length=1000, min_mapq=MIN_MAPQ), 13_001_000)
+        d1 = time.perf_counter() - t0
+        workloads["cfg1"] = {"metric": "aligned reads/s binned (count kind Coverage)", "value": rb.n / d1, "unit": "reads/s",
+                             "cores": 1, "kind": "port", "sample": "%d reads of a 13 Mbp contig, single thread" % rb.n}
+    workload = ("cfg2: cmd coverage (Fragments, %d bp windows, MAPQ>=%d, GC from reference) + normalize "
+                "MedianGcBinned, synthetic 30x WGS chr1-22" % (WINDOW, MIN_MAPQ))
+    line = {
+        "impl": "reference", "metric": "aligned reads/s binned", "value": val, "unit": "reads/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic", "config": {"workload": workload, "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "reads/s", "cores": 1, "kind": "port", "sample": desc,
+                         "host_cores_available": ncpu},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "workloads": workloads,
+        "note": "restated reference CPU path (oracle/, plain C -O2); the Rust reference cannot be built "
+                "here; cmd coverage/normalize are single-threaded in the reference",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def bench_coverage(args, env):
+    """The headline: BASELINE configs[1] (see the module docstring)."""
+    torch = env.torch
+    import cnvetti_b200 as cb
+    from cnvetti_b200 import pipeline, synth_torch
+    rank, world, dev, ctx, comm = env.rank, env.world, env.dev, env.ctx, env.comm
+    regs = contigs(args.scale)
+    n_pairs = [max(1000, int(round(L * READS_PER_BP / 2))) for _, L in regs]
+    total_reads = 2 * sum(n_pairs)
+    total_bp = sum(L for _, L in regs)
+    workload = ("cfg2: cmd coverage (Fragments, %d bp windows, MAPQ>=%d, GC from reference) + normalize "
+                "MedianGcBinned, synthetic 30x WGS chr1-22" % (WINDOW, MIN_MAPQ))
+    opts = cb.CoverageOptions(window_length=WINDOW, min_mapq=MIN_MAPQ)
+    owner, per_rank = pipeline.shard_regions([L for _, L in regs], world)
+    mine = per_rank[rank]
+
+    def make_regions(ids, seed_shift=0):
+        out, n = [], 0
+        for ci in ids:
+            name, L = regs[ci]
+            soa = synth_torch.synth_soa_contig(2 * 1000 + ci + seed_shift, L, n_pairs[ci], dev)
+            seq = synth_torch.synth_reference_torch(2 * 1000 + ci, L, dev)
+            batch = cb.ReadBatch(mid=soa["mid"].contiguous(), mapq=soa["mapq"].contiguous(), flags=soa["flags"].contiguous())
+            out.append(pipeline.Region(name, L, batch, seq))
+            n += len(batch)
+            del soa
+        return out, n
+
+    t_gen = time.perf_counter()
+    dev_regions, n_local = make_regions(mine)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t_gen
-
     prep_dev = pipeline.PreparedRegions(dev_regions, opts)
+    shard = comm if world > 1 else None
 
     def step_device():
         t = pipeline.coverage_run(prep_dev, opts, ctx=ctx)
-        return pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx)
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
+        return pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx, comm=shard, want_medians=False)
 
     # correctness guard on the full-size run: every counted fragment lands in exactly one window
     t = step_device()
     torch.cuda.synchronize()
     assert int(t.rcv.double().sum().item()) == sum(t.num_processed) - sum(t.num_skipped), "checksum"
-    n_windows = int(t.rcv.numel())
-    sampler = ClockSampler(local_rank)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
-    for _ in range(max(0, args.warmup - 1)):
-        step_device()
-    barrier()
-    sampler.start()
-    launches0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = ctx.launch_count - launches0
-    ms = e0.elapsed_time(e1) / args.steps
-    # per-kernel device time: a second, instrumented pass (events around every launch cost a few
-    # microseconds each, so they are kept out of the timed region above).  In timing mode the library
-    # keeps all regions on one stream: in the timed steps the regions' kernels overlap on side streams
-    # (memory-bound binning beside ALU-bound reference statistics), where a single kernel's duration
-    # says nothing about the kernel.
-    ctx.set_timing(True)
-    ctx.timing_reset()
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    i0.record()
-    for _ in range(args.steps):
-        step_device()
-    i1.record()
-    torch.cuda.synchronize()
-    ms_serial = i0.elapsed_time(i1) / args.steps
-    kern = {}
-    for kname in ("frag_bin_gw_kernel", "refstats_lut_kernel", "gc_radix_hist_kernel"):
-        kms, cnt = ctx.timing_query(kname)
-        kern[kname] = {"ms_per_step": kms / args.steps, "launches_per_step": cnt / args.steps}
-    ctx.set_timing(False)
-    ctx.timing_reset()
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max = float(tmax.item())
-    value = world * n_reads / (ms_max * 1e-3)
+    n_windows_local = int(t.rcv.numel())
+    n_windows = int(env.sum_over_ranks(n_windows_local))
+    sampler = ClockSampler(env.local)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
+    ms_max, launches, clocks = timed_steps(env, step_device, args.steps, max(0, args.warmup - 1), sampler)
+    kern, ms_serial = kernel_times(env, step_device, args.steps,
+                                   ("frag_bin_gw_kernel", "refstats_lut_kernel", "gc_radix_hist_kernel",
+                                    "gc_radix_pick_kernel", "norm_gc_map_kernel", "cov_records_kernel"))
+    value = total_reads / (ms_max * 1e-3)
+    loads = [sum(regs[i][1] for i in lst) for lst in per_rank]
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"metric": "aligned reads/s binned", "value": value, "unit": "reads/s",
-                              "n_gpus": world, "ms_per_step": ms_max, "gpu_launches": launches,
-                              "ms_per_step_serialised": ms_serial, "kernels": kern, "quick": True}))
-        if distributed:
-            dist.destroy_process_group()
-        return 0
+            return {"metric": "aligned reads/s binned", "value": value, "unit": "reads/s", "n_gpus": world,
+                    "ms_per_step": ms_max, "gpu_launches": launches, "ms_per_step_serialised": ms_serial, "kernels": kern,
+                    "quick": True, "scaling": "strong" if world > 1 else "weak"}, 0
+        return None, 0
 
-    # ---- end to end: pinned host SoA in, table out -----------------------------------------------------
+    # ---- end to end: pinned host SoA in, table out ---------------------------------------------------------
     host_regions = []
     h2d = 0
     all_pinned = True
@@ -1003,92 +1114,179 @@ def main():
         h2d += hseq.numel()
         host_regions.append(pipeline.Region(r.name, r.length, cb.ReadBatch(**cols), hseq))
     torch.cuda.synchronize()
-    out_host = {kcol: torch.empty(n_windows, dtype=dt, pin_memory=True)
-                for kcol, dt in (("cv", torch.float32), ("cv2", torch.float32), ("lcv", torch.float32),
-                                 ("rcv", torch.float32), ("gc", torch.float32), ("norm_flags", torch.uint8),
-                                 ("gap", torch.uint8))}
+    out_host = {kcol: torch.empty(n_windows_local, dtype=dt_, pin_memory=True)
+                for kcol, dt_ in (("cv", torch.float32), ("cv2", torch.float32), ("lcv", torch.float32),
+                                  ("rcv", torch.float32), ("gc", torch.float32), ("norm_flags", torch.uint8),
+                                  ("gap", torch.uint8))}
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
-
     prep_host = pipeline.PreparedRegions(host_regions, opts)
 
     def step_e2e():
         tt = pipeline.coverage_run(prep_host, opts, ctx=ctx)
-        pipeline.normalize_run(tt, "MedianGcBinned", ctx=ctx)
+        pipeline.normalize_run(tt, "MedianGcBinned", ctx=ctx, comm=shard, want_medians=False)
         for kcol, h in out_host.items():
             h.copy_(getattr(tt, kcol), non_blocking=True)
         torch.cuda.synchronize()
 
     e2e_steps = max(1, min(args.steps, 5))
     step_e2e()
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_reads / float(te.item())
+    env.barrier()
+    e2e_s = env.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = total_reads / e2e_s
+    h2d_total = int(env.sum_over_ranks(h2d))
+    d2h_total = int(env.sum_over_ranks(d2h))
+    del host_regions, prep_host, out_host
 
-    if rank != 0:
-        if distributed:
-            dist.destroy_process_group()
-        return 0
+    # ---- N > 1: the reference's own data parallelism beside it (one sample per GPU, no collective) ------------
+    replicas = None
+    if world > 1 and not args.no_replicas:
+        del dev_regions, prep_dev, t
+        env.free()
+        rep_regions, n_rep = make_regions(range(len(regs)), seed_shift=7919 * rank)
+        prep_rep = pipeline.PreparedRegions(rep_regions, opts)
 
-    # ---- roofline of the dominant kernel -----------------------------------------------------------------
-    peak, peak_src = measured_peak()
-    step_bytes = float(BYTES_PER_READ_GW * n_reads + sum(L for _, L in regs) + n_windows * (5 + 4 + 16 + 8))
-    gw = kern["frag_bin_gw_kernel"]
-    achieved = BYTES_PER_READ_GW * n_reads / (gw["ms_per_step"] * 1e-3) / 1e9 if gw["ms_per_step"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "frag_bin_gw_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(n_reads, gw["launches_per_step"]), "peak_source": peak_src,
-                "algorithmic_bytes_per_read": BYTES_PER_READ_GW,
-                "algorithmic_bytes_per_launch": BYTES_PER_READ_GW * n_reads / max(1.0, gw["launches_per_step"]),
-                "kernel_share_of_step": gw["ms_per_step"] / ms_serial,
-                "kernel_timing": "instrumented pass with the regions serialised on one stream (%.3f ms/step); the "
-                                 "timed steps overlap regions on three side streams" % ms_serial,
-                "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
-                         "frac": step_bytes / (ms * 1e-3) / 1e9 / peak,
-                         "what": "all kernels of one step together: 7 B/read + 1 B/base + 5 B/window refstats out "
-                                 "+ 4 B/window counts + normalise 8 B/window x 2 passes + 8 B/window out"}}
-    rs = kern["refstats_lut_kernel"]
-    total_bp = sum(L for _, L in regs)
-    roofline["step"]["algorithmic_bytes"] = step_bytes
-    kern["refstats_lut_kernel"]["achieved_gbs"] = total_bp / (rs["ms_per_step"] * 1e-3) / 1e9 if rs["ms_per_step"] > 0 else 0.0
+        def step_rep():
+            tt = pipeline.coverage_run(prep_rep, opts, ctx=ctx)
+            return pipeline.normalize_run(tt, "MedianGcBinned", ctx=ctx, want_medians=False)
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ------------------------------------------
-    cpu = None
-    if world == 1:
-        sample = make_cpu_sample()
-        cn, cdt = cpu_reference_leg(sample, 1, 1)
-        cpu = {"value": cn / cdt, "unit": "reads/s", "cores": 1, "kind": "port",
-               "sample": "%s (%.0f M reads) of the workload, oracle coverage+refstats+normalize, single thread "
-                         "(the reference's cmd coverage/normalize are single-threaded)" %
-                         ("+".join(regs[i][0] for i in sample_ids), cn / 1e6),
-               "host_cores_available": os.cpu_count()}
+        rsteps = max(3, min(args.steps, 10))
+        ms_rep, _, _ = timed_steps(env, step_rep, rsteps, 2)
+        replicas = {"value": world * n_rep / (ms_rep * 1e-3), "unit": "reads/s", "scaling": "weak", "ms_per_step": ms_rep,
+                    "steps": rsteps, "reads_per_gpu": n_rep,
+                    "what": "one whole-genome sample per GPU, no collective (quick_wis_build_model.rs:148-184)"}
+        del rep_regions, prep_rep
 
-    line = {
-        "metric": "aligned reads/s binned", "value": value, "unit": "reads/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload, "reads_per_gpu": n_reads, "windows_per_gpu": n_windows,
-                   "contigs": len(regs), "window_length": WINDOW, "scale": args.scale,
-                   "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" %
-                         ((BYTES_PER_READ_GW * n_reads + total_bp) / 1e9),
-                   "parallelism": "one sample per GPU, no collective" if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
-                "host_memory": "pinned" if all_pinned else "pageable (pinning refused)"},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "kernels": kern, "gen_seconds": gen_s,
-        "host_bam_decode": host_bam_decode_leg() if (rank == 0 and not args.quick) else None,
-    }
-    print(json.dumps(line))
-    if distributed:
-        dist.destroy_process_group()
-    return 0
+    # ---- rank 0: roofline, CPU baseline, parity of the sample contigs against the oracle ----------------------
+    rc = 0
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        step_bytes = float(BYTES_PER_READ_GW * total_reads + total_bp + n_windows * (5 + 4 + 16 + 8))
+        gw = kern["frag_bin_gw_kernel"]
+        achieved = BYTES_PER_READ_GW * n_local / (gw["ms_per_step"] * 1e-3) / 1e9 if gw["ms_per_step"] > 0 else 0.0
+        traffic, traffic_src = ncu_traffic("frag_bin_gw_kernel", n_local / max(1.0, gw["launches_per_step"]))
+        roofline = {"bound": "hbm", "kernel": "frag_bin_gw_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "algorithmic_bytes_per_read": BYTES_PER_READ_GW,
+                    "algorithmic_bytes_per_launch": BYTES_PER_READ_GW * n_local / max(1.0, gw["launches_per_step"]),
+                    "kernel_share_of_step": gw["ms_per_step"] / ms_serial,
+                    "kernel_timing": "instrumented pass with the regions serialised on one stream (%.3f ms/step); the "
+                                     "timed steps overlap regions on three side streams; rank 0's regions" % ms_serial,
+                    "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_max * 1e-3) / 1e9, "unit": "GB/s",
+                             "frac": step_bytes / (ms_max * 1e-3) / 1e9 / (peak * world), "peak": peak * world,
+                             "what": "all kernels of one step together, all ranks: 7 B/read + 1 B/base + 5 B/window "
+                                     "refstats out + 4 B/window counts + normalise 8 B/window x 2 passes + 8 B/window out"}}
+        rs = kern.get("refstats_lut_kernel")
+        if rs and rs["ms_per_step"] > 0:
+            rs["achieved_gbs"] = sum(regs[i][1] for i in mine) / (rs["ms_per_step"] * 1e-3) / 1e9
+        cpu, checks = None, None
+        if world == 1:
+            k = max(1, min(args.cpu_sample_contigs, len(regs)))
+            sample_ids = list(range(len(regs) - k, len(regs)))
+            sample = [(synth_torch.soa_to_oracle_records(synth_torch.synth_soa_contig(2 * 1000 + ci, regs[ci][1], n_pairs[ci], dev)),
+                       regs[ci][1], synth_torch.synth_reference_torch(2 * 1000 + ci, regs[ci][1], dev).cpu().numpy())
+                      for ci in sample_ids]
+            cn, cdt, o = cpu_reference_leg(sample, 1, 1)
+            del sample
+            cpu = {"value": cn / cdt, "unit": "reads/s", "cores": 1, "kind": "port",
+                   "sample": "%s (%.0f M reads) of the workload, oracle coverage+refstats+normalize, single thread "
+                             "(the reference's cmd coverage/normalize are single-threaded)" %
+                             ("+".join(regs[i][0] for i in sample_ids), cn / 1e6),
+                   "host_cores_available": os.cpu_count()}
+            # the same contigs through the GPU path (region loop + MedianGcBinned over these contigs) vs the oracle
+            sub = [dev_regions[i] for i in sample_ids]
+            g = pipeline.normalize_run(pipeline.coverage_run(sub, opts, ctx=ctx), "MedianGcBinned", ctx=ctx)
+            torch.cuda.synchronize()
+            bits = lambda x: np.ascontiguousarray(x.cpu().numpy() if hasattr(x, "cpu") else x, np.float32).view(np.uint32)  # noqa: E731
+            cv2_g, fin = g.cv2.cpu().numpy(), np.isfinite(o["cv2"])
+            parts = {
+                "counts": bool(np.array_equal(bits(g.rcv), bits(o["rcv"]))) and g.num_processed == o["processed"],
+                "lcv_bits": bool(np.array_equal(bits(g.lcv), bits(o["lcv"]))),
+                "gc_bits": bool(np.array_equal(bits(g.gc), bits(o["gc"]))),
+                "gap": bool(np.array_equal(g.gap.cpu().numpy(), o["gap"])),
+                "medians_bits": bool(np.array_equal(bits(g.medians), bits(o["medians"]))),
+                "cv_bits": bool(np.array_equal(bits(g.cv), bits(o["cv"]))),
+                "flags": bool(np.array_equal(g.norm_flags.cpu().numpy(), o["flags"])),
+                "cv2_rel_1e-6": bool(np.array_equal(np.isfinite(cv2_g), fin) and
+                                     np.allclose(cv2_g[fin], o["cv2"][fin], rtol=1e-6, atol=1e-7)),
+            }
+            checks = {"what": "%s (%d windows, %.0f M reads) through the region loop + MedianGcBinned against the oracle"
+                              % ("+".join(regs[i][0] for i in sample_ids), g.rcv.numel(), cn / 1e6),
+                      "identical": all(parts.values()), **parts}
+            if not checks["identical"]:
+                rc = 1
+        line = {
+            "metric": "aligned reads/s binned", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload, "reads": total_reads, "windows": n_windows,
+                       "contigs": len(regs), "window_length": WINDOW, "scale": args.scale,
+                       "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" %
+                             ((BYTES_PER_READ_GW * total_reads + total_bp) / 1e9),
+                       "parallelism": "single GPU" if world == 1 else
+                       "ONE sample, contigs sharded over %d GPUs (LPT by length; largest share %.1f %% of the genome, ideal "
+                       "%.1f %%); MedianGcBinned exchanges 4 x 103 KB radix histograms (NCCL all-reduce inside the "
+                       "library); result columns stay sharded" % (world, 100.0 * max(loads) / total_bp, 100.0 / world),
+                       "contigs_of_rank": [[regs[i][0] for i in lst] for lst in per_rank] if world > 1 else None},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "host_memory": "pinned" if all_pinned else "pageable (pinning refused)"},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "kernels": kern, "gen_seconds": gen_s, "checks": checks, "replicas": replicas,
+            "host_bam_decode": host_bam_decode_leg(),
+        }
+    return line, rc
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+        return 2
+    env = Env(args)
+    rc = 0
+    single = {"wis": bench_wis, "hmm": bench_hmm, "piles": bench_piles, "cfg1": bench_cfg1, "cfg5": bench_cfg5}
+    if args.workload in single:
+        line = single[args.workload](args, env)
+        if line and isinstance(line.get("checks"), dict) and line["checks"].get("identical") is False:
+            rc = 1
+    else:
+        line, rc = bench_coverage(args, env)
+        env.free()
+        if args.workload == "all" and not args.quick and args.scale >= 1.0:
+            # the other BASELINE metrics, each a full line of its own; bounded step counts keep the run short
+            subs = {}
+            plan = [("cfg1", bench_cfg1, min(args.steps, 20), min(args.warmup, 3)),
+                    ("cfg3", bench_wis, min(args.steps, 10), min(args.warmup, 3)),
+                    ("cfg4", bench_hmm, min(args.steps, 10), min(args.warmup, 3)),
+                    ("cfg5", bench_cfg5, 2, 1)]
+            for name, fn, k, w in plan:
+                env.log("workload %s" % name)
+                try:
+                    sub = fn(args, env, steps=k, warmup=w)
+                except Exception as ex:  # a failing side workload must not lose the headline
+                    sub = {"error": "%s: %s" % (type(ex).__name__, ex)}
+                    rc = rc or 1
+                    env.free()
+                if env.rank == 0:
+                    subs[name] = sub
+                    if sub and isinstance(sub.get("checks"), dict) and sub["checks"].get("identical") is False:
+                        rc = 1
+            if line is not None:
+                line["workloads"] = subs
+    if env.rank == 0 and line is not None:
+        if rc:
+            line["parity_failed"] = True
+        print(json.dumps(line))
+    env.close()
+    return rc
 
 
 if __name__ == "__main__":

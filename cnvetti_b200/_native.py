@@ -74,6 +74,7 @@ SYMBOLS = {
     "cnvb_create_error": (C.c_char_p, []),
     "cnvb_ctx_launch_count": (_u64, [_vp]),
     "cnvb_version": (C.c_char_p, []),
+    "cnvb_ctx_release_memory": (_int, [_vp]),
     "cnvb_ctx_set_timing": (_int, [_vp, _int]),
     "cnvb_ctx_timing_reset": (_int, [_vp]),
     "cnvb_ctx_timing_query": (_int, [_vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(_u64)]),

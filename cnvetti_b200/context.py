@@ -66,6 +66,10 @@ class Context:
     def synchronize(self):
         self.check(N.lib().cnvb_ctx_synchronize(self.handle))
 
+    def release_memory(self):
+        """hand the ctx's cached device memory (pool, scratch, staging) back to the driver"""
+        self.check(N.lib().cnvb_ctx_release_memory(self.handle))
+
     @property
     def launch_count(self):
         return int(N.lib().cnvb_ctx_launch_count(self.handle))

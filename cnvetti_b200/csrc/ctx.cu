@@ -82,6 +82,24 @@ extern "C" int cnvb_ctx_synchronize(cnvb_ctx *ctx) {
     return CNVB_OK;
 }
 
+extern "C" int cnvb_ctx_release_memory(cnvb_ctx *ctx) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "synchronising the context stream");
+    for (int q = 0; q < 3; ++q)
+        if (ctx->side[q]) CNVB_CUDA(ctx, cudaStreamSynchronize(ctx->side[q]), "synchronising the side streams");
+    for (auto &kv : ctx->pool_free)
+        for (auto &b : kv.second) cudaFree(b.p);
+    ctx->pool_free.clear();
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    return CNVB_OK;
+}
+
 extern "C" const char *cnvb_last_error(const cnvb_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
 
 extern "C" uint64_t cnvb_ctx_launch_count(const cnvb_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -61,6 +61,9 @@ const char *cnvb_create_error(void);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t cnvb_ctx_launch_count(const cnvb_ctx *ctx);
 const char *cnvb_version(void);
+/* Returns the cached device memory of the ctx (pooled blocks not in use, scratch and staging
+ * buffers) to the driver after synchronising the stream; the next calls allocate afresh. */
+int cnvb_ctx_release_memory(cnvb_ctx *ctx);
 /* Optional instrumentation: while on, every kernel launch is bracketed by CUDA events on the
  * ctx stream; cnvb_ctx_timing_query sums the device time of all launches of `kernel` (e.g.
  * "frag_bin_gw_kernel") since the last reset.  Query and reset synchronise the stream. */

@@ -1,9 +1,12 @@
 """The native region loop (cnvb_coverage_run = lib_coverage::run's loop, lib.rs:768-781) against the
 oracle run region by region, plus the chained normaliser; host and device inputs, all three kinds."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 import cnvetti_b200 as cb
 from cnvetti_b200 import _native as N
@@ -222,3 +225,82 @@ def test_region_loop_reference_statistics_batched_and_not(oracle, ctx, n_regions
         gc, gap = oracle.refstats(seq, wl)
         assert_f32_equal_bits(t.gc[lo:hi], gc, "gc")
         assert np.array_equal(to_np(t.gap[lo:hi]).astype(bool), gap.astype(bool))
+
+
+# ---- the communicator and the sharded entry points ---------------------------------------------------------
+def test_sharded_entry_points_world_1(ctx):
+    """cnvb_comm with one rank needs no NCCL: the sharded normalisers and the sharded model equal the plain
+    calls (the multi-rank runs are tools/check_sharded.py and tools/c_abi_sharded.c, below)."""
+    import torch
+    from cnvetti_b200 import model_wis as mw, parallel
+    from cnvetti_b200.normalize import run_binned_correction, run_uncorrected_normalization
+    comm = parallel.Communicator(ctx, 0, 1)
+    rng = np.random.default_rng(5)
+    lcv = torch.from_numpy((rng.poisson(120, 200_000) / 500.0).astype(np.float32)).cuda()
+    gc = torch.from_numpy(rng.uniform(0.3, 0.6, 200_000).astype(np.float32)).cuda()
+    a = run_binned_correction(lcv, gc, ctx=ctx)
+    b = run_binned_correction(lcv, gc, comm=comm)
+    assert torch.equal(a["cv"].view(torch.int32), b["cv"].view(torch.int32)) and np.array_equal(a["medians"], b["medians"])
+    assert torch.equal(run_uncorrected_normalization(lcv, ctx=ctx)[0].view(torch.int32),
+                       run_uncorrected_normalization(lcv, comm=comm)[0].view(torch.int32))
+    X, tids = synth.synth_panel(9, 5000, 32, n_contigs=5)
+    dX, dt = torch.from_numpy(X).cuda(), torch.from_numpy(tids.view(np.int32)).cuda()
+    o = mw.BuildModelWisOptions(max_ref_targets=30)
+    m, rows, T = mw.run_sharded(dX, dt, o, comm)
+    f = mw.run(dX, dt, o, ctx=ctx)
+    assert rows == (0, 5000) and T == 5000 and np.float32(m.threshold).tobytes() == np.float32(f.threshold).tobytes()
+    assert torch.equal(m.ref_dist.view(torch.int32), f.ref_dist.view(torch.int32)) and torch.equal(m.num_calls, f.num_calls)
+    assert torch.equal(m.filt, f.filt) and torch.equal(m.ref_len, f.ref_len)
+    comm.close()
+
+
+def test_merge_cov_kernel(ctx):
+    """cnvb_merge_cov: columns side by side -> X[T][S] (lib-merge-cov/src/lib.rs:102-232), both input forms,
+    ragged tile edges."""
+    import torch
+    from cnvetti_b200 import pipeline
+    for T, S in ((1000, 7), (4097, 33), (130, 100), (1, 1)):
+        cv = torch.randn(S, T, device="cuda")
+        X = pipeline.merge_cov_panel(cv, ctx=ctx)
+        assert torch.equal(X, cv.t().contiguous())
+        tables = []
+        for s in range(S):
+            t = pipeline.CoverageTable()
+            t.offsets, t.start, t.end = [0, T], torch.arange(T, device="cuda"), torch.arange(T, device="cuda") + 1
+            t.cv = cv[s].clone()
+            tables.append(t)
+        X2, tids = pipeline.merge_cov(tables, ctx=ctx)
+        assert torch.equal(X2, X) and int(tids.max()) == 0
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_c_abi_sharded_from_plain_c(tmp_path):
+    """The multi-GPU entry points driven by a C program with one host thread per GPU (no Python, no torch, no
+    CUDA calls of its own) -- what a Rust host binding the header does.  2 GPUs when the box has them
+    (NCCL inside the library), else the one-rank form."""
+    import subprocess
+    exe = str(tmp_path / "c_abi_sharded")
+    lib_dir = os.path.join(ROOT, "cnvetti_b200")
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "c_abi_sharded.c"),
+                           "-o", exe, "-L", lib_dir, "-lcnvetti_b200", "-Wl,-rpath," + lib_dir, "-lpthread", "-lm"])
+    world = 2 if _n_gpus() >= 2 else 1
+    r = subprocess.run([exe, str(world)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c_abi_sharded ok" in r.stdout
+
+
+def test_sharded_parity_under_torchrun():
+    """tools/check_sharded.py on 2 GPUs: one genome sharded by contig, the sharded model, the cohort chain --
+    all bit-identical to the single-GPU results."""
+    import subprocess
+    import sys
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs (run by gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "check_sharded.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ALL IDENTICAL" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
