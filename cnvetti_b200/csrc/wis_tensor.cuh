@@ -398,6 +398,8 @@ struct SweepArgs {
     float *cand_val;         // [rows][kCandCap]
     uint32_t *cand_idx;
     uint32_t *cand_cnt;      // [rows]
+    uint32_t dbg;            // CNVB_WIS_DBG (timing experiments only; results are wrong): 1 skip the epilogue's
+                             // TMEM reads and tests, 2 skip the MMAs
 };
 
 // STREAM: more than kMaxKBlocks K-blocks (S > 128): the A operand does not fit beside the B ring, so
@@ -605,7 +607,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
 #pragma unroll
                                 for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                                    if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                    if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
                                         tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
                                 }
                             }
@@ -767,6 +769,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                if (a.dbg & 1u) continue;
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
                 if (STREAM) {
@@ -889,6 +892,216 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #undef CNVB_TILE_AT
 #undef CNVB_TILE_G
 #undef CNVB_VAL
+
+// ---- sweep, S <= 128, rounds >= 1: M128 x N256 accumulators ------------------------------------------
+// The two M128 x N128 MMAs per K16 slab of the kernel above read 8 KB of shared-memory operands per
+// 64-cycle issue slot -- the whole 128 B/clk of the SM, with TMA writes and L1 traffic on top: measured
+// 164 cycles per MMA.  Here a step takes a DOUBLE tile of 256 columns: per row half (128 rows on the M
+// axis) one M128 x N256 x K16 MMA per slab, 12 KB of operands per 128-cycle slot (96 B/clk).  TMEM holds
+// the two halves' accumulators (2 x 256 columns = all 512); they alternate -- while the 16 epilogue warps
+// read half h (128 KB at TMEM's 64 B/clk = 2048 cycles, the bound of this kernel: twice the 1024 cycles
+// of the MMAs), the tensor core computes half 1 - h.
+// Work items are (row block, side of its window) pairs, handed out in order of decreasing size
+// (`order`, sorted after the window kernel): the hardware dispatches CTAs in index order as SMs free up,
+// which makes the launch a longest-processing-time schedule instead of 5.3 uneven waves.
+constexpr uint32_t kDStages = 2;  // double tiles in flight: 2 x (n_kblocks x 32 KB)
+constexpr uint32_t kIdesc256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__global__ void __launch_bounds__(kSweepThreads, 1)
+wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b2,
+                    const SweepArgs a, const uint32_t *__restrict__ order) {
+    const uint32_t item = order[blockIdx.x];
+    const uint32_t blk = item >> 1, side = item & 1u;
+    const uint4 rng = a.rng[blk];
+    const uint32_t t_begin = side ? rng.z : rng.x, t_end = side ? rng.w : rng.y;  // 128-column tiles [t_begin, t_end)
+    if (t_end <= t_begin) return;
+    const uint32_t n_dt = (t_end - t_begin + 1u) >> 1;  // double tiles (the last may hold one tile only)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;                                  // [n_kblocks][2 halves] x 16 KB
+    const uint32_t stage_bytes = a.n_kblocks * 2u * kTileBytes;         // n_kblocks boxes of 64 x 256
+    const uint32_t b_base = a_base + 2u * a.n_kblocks * kTileBytes;
+    const uint32_t bar_base = b_base + kDStages * stage_bytes;
+    const uint32_t bar_a_full = bar_base;
+    const uint32_t bar_b_full = bar_base + 8;                  // kDStages
+    const uint32_t bar_b_empty = bar_b_full + 8 * kDStages;    // kDStages
+    const uint32_t bar_acc_full = bar_b_empty + 8 * kDStages;  // 2 (row halves)
+    const uint32_t bar_acc_empty = bar_acc_full + 16;          // 2
+    const uint32_t tmem_slot = bar_acc_empty + 16;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t row0 = blk * kTileRows;
+    if (warp == 0 && lane == 0) {
+        mbar_init(bar_a_full, 1);
+        for (uint32_t s = 0; s < kDStages; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (uint32_t s = 0; s < 2; ++s) {
+            mbar_init(bar_acc_full + 8 * s, 1);
+            mbar_init(bar_acc_empty + 8 * s, kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
+            for (uint32_t h = 0; h < 2; ++h)
+                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
+                    tma_load_2d(a_base + (kb * 2u + h) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
+                                (int32_t)(row0 + h * 128));
+            uint32_t st = 0, ph = 0;
+            for (uint32_t it = 0; it < n_dt; ++it) {
+                const int32_t j0 = (int32_t)((t_begin + 2u * it) * kTileCols);
+                mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
+                mbar_expect_tx(bar_b_full + 8 * st, stage_bytes);
+                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)  // (rows beyond the panel arrive as zeros)
+                    tma_load_2d(b_base + st * stage_bytes + kb * 2u * kTileBytes, &tmap_b2, bar_b_full + 8 * st,
+                                (int32_t)(kb * kKBlock), j0);
+                if (++st == kDStages) {
+                    st = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            mbar_wait(bar_a_full, 0);
+            tc_fence_after();
+            uint32_t st = 0, ph = 0, aph = 0;
+            for (uint32_t it = 0; it < n_dt; ++it) {
+                mbar_wait(bar_b_full + 8 * st, ph);
+                tc_fence_after();
+#pragma unroll
+                for (uint32_t h = 0; h < 2; ++h) {
+                    mbar_wait(bar_acc_empty + 8 * h, aph ^ 1u);  // the epilogue has drained this half's last tile
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + h * 256u;
+                    for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
+                        const uint64_t ad = umma_desc(a_base + (kb * 2u + h) * kTileBytes);
+                        const uint64_t bd = umma_desc(b_base + st * stage_bytes + kb * 2u * kTileBytes);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < kKBlock / 16; ++kk)
+                            if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
+                                tc_mma_f16(d_tmem, ad + 2u * kk, bd + 2u * kk, kIdesc256, (kb | kk) != 0u);
+                    }
+                    tc_commit(bar_acc_full + 8 * h);
+                }
+                tc_commit(bar_b_empty + 8 * st);  // frees the stage when both halves' MMAs have retired
+                aph ^= 1u;
+                if (++st == kDStages) {
+                    st = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warp e reads TMEM lane quarter q = e & 3 (row h * 128 + 32 q + lane of the block) and
+        // the 64 columns [64 (e >> 2), +64) of the double tile, in two loads of 32 =====
+        const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
+        float thr[2], kap[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t row = row0 + h * 128 + q * 32 + lane;
+            const bool live = row < a.rows;
+            thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
+            kap[h] = live ? a.kap[row] : 0.0f;
+        }
+        uint32_t aph = 0;
+        for (uint32_t it = 0; it < n_dt; ++it) {
+            const uint32_t tile = t_begin + 2u * it + (cpart >> 1);  // the 128-column tile this warp's columns lie in
+            const bool wanted = tile < t_end;                        // (warp-uniform; false: the odd tile past the range)
+            const uint32_t j0 = tile * kTileCols + (cpart & 1u) * 64u;
+            const float smax = wanted ? __ldg(a.tile_smax + tile) : 0.0f;
+            if (it + 1 < n_dt) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + j0 + 2u * kTileCols));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(bar_acc_full + 8 * h, aph);
+                tc_fence_after();
+                if (wanted && !(a.dbg & 1u)) {
+                    const float rhs = fmaf(kap[h], smax, thr[h]);  // keep iff n'_j - 2 g <= theta_i + kappa_i smax
+                    const uint32_t row = row0 + h * 128 + q * 32 + lane;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float nj[32];
+                        const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0 + 32 * half);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {  // same addresses for all lanes: L1 broadcast
+                            const float4 v = __ldg(nj4 + g4);
+                            nj[4 * g4 + 0] = v.x;
+                            nj[4 * g4 + 1] = v.y;
+                            nj[4 * g4 + 2] = v.z;
+                            nj[4 * g4 + 3] = v.w;
+                        }
+                        uint32_t r[32];
+                        tc_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)h * 256u + cpart * 64u + 32u * half, r);
+                        uint32_t gmask = 0u;
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const bool p = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj[4 * g4 + 0]) <= rhs ||
+                                           fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj[4 * g4 + 1]) <= rhs ||
+                                           fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj[4 * g4 + 2]) <= rhs ||
+                                           fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj[4 * g4 + 3]) <= rhs;
+                            gmask |= p ? (1u << g4) : 0u;
+                        }
+                        const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+                        if (wmask) {  // survivors are rare: the append code runs only for groups in which some row passes
+#pragma unroll
+                            for (int g4 = 0; g4 < 8; ++g4) {
+                                if (wmask & (1u << g4)) {
+#pragma unroll
+                                    for (int e4 = 0; e4 < 4; ++e4) {
+                                        const int c = 4 * g4 + e4;
+                                        const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                                        const uint32_t j = j0 + 32 * half + c;
+                                        if (v <= rhs && j < a.T) {  // (rows beyond the end: theta = -inf)
+                                            const uint32_t slot = atomicAdd(&a.cand_cnt[row], 1u);
+                                            if (slot < kCandCap) {  // beyond: overflow, the row falls back
+                                                a.cand_val[(size_t)row * kCandCap + slot] = v;
+                                                a.cand_idx[(size_t)row * kCandCap + slot] = j;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * h);
+            }
+            aph ^= 1u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// work items of a round: (row block, side) with the number of tiles as sort key
+__global__ void wis_items_kernel(const uint4 *__restrict__ rng, uint32_t row_blocks, uint32_t *__restrict__ key,
+                                 uint32_t *__restrict__ item) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2u * row_blocks) return;
+    const uint4 r = rng[i >> 1];
+    key[i] = (i & 1u) ? r.w - r.z : r.y - r.x;
+    item[i] = i;
+}
 
 // ---- windows: which column tiles a block of rows still has to see --------------------------------
 struct WindowArgs {
@@ -1339,8 +1552,12 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     uint2 *done = nullptr;
     unsigned long long *counters = nullptr;  // [0] tiles swept | [1] pairs re-scored | [2] longest list
     void *cub_tmp = nullptr;
-    size_t sort_bytes = 0, sel_bytes = 0;
+    size_t sort_bytes = 0, sel_bytes = 0, item_bytes = 0;
+    uint32_t *item_key = nullptr, *item_key_sorted = nullptr, *item_id = nullptr, *item_order = nullptr;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, ctx->stream);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, item_bytes, item_key, item_key_sorted, item_id, item_order,
+                                              (int)(2 * row_blocks), 0, 32, ctx->stream);
+    sort_bytes = std::max(sort_bytes, item_bytes);
     if (subset)
         cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<uint32_t>(0), rflag, rows_a, n_sel, (int)T,
                                    ctx->stream);
@@ -1359,7 +1576,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(T, &perm)) != cudaSuccess || (e = g.alloc(Tpad, &tid_sorted)) != cudaSuccess ||
         (e = g.alloc(row_blocks, &rng)) != cudaSuccess || (e = g.alloc(row_blocks, &done)) != cudaSuccess ||
         (e = g.alloc(4, &counters)) != cudaSuccess || (e = g.alloc(S, &cmean)) != cudaSuccess ||
-        (e = g.alloc(Tpad, &meta)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &meta)) != cudaSuccess || (e = g.alloc(2 * row_blocks, &item_key)) != cudaSuccess ||
+        (e = g.alloc(2 * row_blocks, &item_key_sorted)) != cudaSuccess || (e = g.alloc(2 * row_blocks, &item_id)) != cudaSuccess ||
+        (e = g.alloc(2 * row_blocks, &item_order)) != cudaSuccess ||
         (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
@@ -1425,6 +1644,18 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b));
     if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
+    // S <= 128, rounds >= 1: double tiles of 256 columns on M128 x N256 accumulators (wis_sweep256_kernel);
+    // CNVB_WIS_N256 = 0 keeps the M128 x N128 form
+    const bool n256 = !stream_a && [] {
+        const char *e = getenv("CNVB_WIS_N256");
+        return !(e && atoi(e) == 0);
+    }();
+    CUtensorMap tmap_b2 = tmap_b;
+    if (n256) CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b2, 256));
+    const size_t smem256 = (size_t)(2 + 2 * kDStages) * (Kp / kKBlock) * kTileBytes + 512 + 1024;
+    if (n256)
+        CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem256),
+                  "smem opt-in");
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
     // streamed sweep: the CTAs of a cluster share their rows' operand through TMA multicast
     // (CNVB_WIS_CLUSTER = 1: one CTA per block, 2 or 4: CTAs per cluster)
@@ -1488,6 +1719,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.cand_val = cand_val;
     sa.cand_idx = cand_idx;
     sa.cand_cnt = cand_cnt;
+    {
+        const char *e = getenv("CNVB_WIS_DBG");
+        sa.dbg = e ? (uint32_t)atoi(e) : 0u;
+    }
     auto launch_sweep = [&](decltype(sweep_first) kern) -> cudaError_t {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)cl * row_blocks);
@@ -1570,11 +1805,25 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         CNVB_CUDA(ctx, cudaStreamSynchronize(st), "reading the round size");
         if (tiles_now == tiles_before && round > 1) break;
         tiles_before = tiles_now;
-        {
-            KernelSpan span(ctx, "wis_sweep_kernel");
-            CNVB_CUDA(ctx, launch_sweep(sweep_next), "launching the sweep");
+        if (n256) {
+            wis_items_kernel<<<(2 * row_blocks + 255) / 256, 256, 0, st>>>(rng, row_blocks, item_key, item_id);
+            CNVB_LAUNCHED(ctx, "wis_items_kernel");
+            CNVB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(cub_tmp, item_bytes, item_key, item_key_sorted, item_id,
+                                                                     item_order, (int)(2 * row_blocks), 0, 32, st),
+                      "ordering the work items");
+            ctx->launches += 1;
+            {
+                KernelSpan span(ctx, "wis_sweep_kernel");
+                wis_sweep256_kernel<<<2 * row_blocks, kSweepThreads, smem256, st>>>(tmap_a, tmap_b2, sa, item_order);
+            }
+            CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
+        } else {
+            {
+                KernelSpan span(ctx, "wis_sweep_kernel");
+                CNVB_CUDA(ctx, launch_sweep(sweep_next), "launching the sweep");
+            }
+            CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         }
-        CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         {
             KernelSpan span(ctx, "wis_compact_kernel");
             wis_compact_kernel<<<(rows + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, st>>>(ca);
