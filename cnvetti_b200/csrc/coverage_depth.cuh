@@ -126,14 +126,50 @@ __global__ void __launch_bounds__(256) depth_tile_kernel(DepthArgs a) {
     __syncthreads();
     // events of the alignments overlapping the tile
     uint32_t carry = 0u;
-    for (uint64_t i = r_lo + tid; i < r_hi; i += 256) {
-        const uint32_t f = a.flags[i];
-        const int64_t p = a.pos[i], e = a.end[i];
+    auto event = [&](uint32_t f, int64_t p, int64_t e, uint32_t mq) {
         if ((f & a.plp_mask) == 0u && p >= 0 && e > (int64_t)t0 && e > p) {
-            const uint32_t v = 0x10000u + depth_pass(f, a.mapq[i], a.min_mapq);
+            const uint32_t v = 0x10000u + depth_pass(f, mq, a.min_mapq);
             if (p < (int64_t)t0) carry += v; else atomicAdd(&d[p - t0], v);
             if (e < (int64_t)t1) atomicAdd(&d[e - t0], 0u - v);
         }
+    };
+    const bool vec = ((reinterpret_cast<uintptr_t>(a.pos) | reinterpret_cast<uintptr_t>(a.end)) & 15u) == 0u &&
+                     (reinterpret_cast<uintptr_t>(a.flags) & 7u) == 0u && (reinterpret_cast<uintptr_t>(a.mapq) & 3u) == 0u;
+    if (vec) {
+        // four alignments per thread and step (128-bit loads), two steps in flight: a tile's ~2500 alignments
+        // are three dependent trips to HBM instead of ten
+        const uint64_t nq_full = a.n >> 2;  // whole quads of the columns; the last n % 4 alignments go one by one
+        const uint64_t q_lo = r_lo >> 2, q_hi = min((r_hi + 3) >> 2, nq_full);
+        if (tid == 0)
+            for (uint64_t i = max(r_lo, nq_full << 2); i < r_hi; ++i) event(a.flags[i], a.pos[i], a.end[i], a.mapq[i]);
+        for (uint64_t q = q_lo + tid; q < q_hi; q += 512) {
+            const uint64_t q2 = q + 256;
+            const bool two = q2 < q_hi;
+            const int4 p0 = ld_stream(reinterpret_cast<const int4 *>(a.pos) + q);
+            const int4 e0 = ld_stream(reinterpret_cast<const int4 *>(a.end) + q);
+            const uint2 f0 = ld_stream(reinterpret_cast<const uint2 *>(a.flags) + q);
+            const uint32_t m0 = ld_stream(reinterpret_cast<const uint32_t *>(a.mapq) + q);
+            int4 p1 = make_int4(0, 0, 0, 0), e1 = make_int4(0, 0, 0, 0);
+            uint2 f1 = make_uint2(0u, 0u);
+            uint32_t m1 = 0u;
+            if (two) {
+                p1 = ld_stream(reinterpret_cast<const int4 *>(a.pos) + q2);
+                e1 = ld_stream(reinterpret_cast<const int4 *>(a.end) + q2);
+                f1 = ld_stream(reinterpret_cast<const uint2 *>(a.flags) + q2);
+                m1 = ld_stream(reinterpret_cast<const uint32_t *>(a.mapq) + q2);
+            }
+            auto quad = [&](uint64_t qq, const int4 &p, const int4 &e, const uint2 &f, uint32_t m) {
+                const uint64_t i0 = qq << 2;  // (the first and the last quad may reach outside [r_lo, r_hi))
+                if (i0 >= r_lo && i0 < r_hi) event(f.x & 0xffffu, p.x, e.x, m & 0xffu);
+                if (i0 + 1 >= r_lo && i0 + 1 < r_hi) event(f.x >> 16, p.y, e.y, (m >> 8) & 0xffu);
+                if (i0 + 2 >= r_lo && i0 + 2 < r_hi) event(f.y & 0xffffu, p.z, e.z, (m >> 16) & 0xffu);
+                if (i0 + 3 >= r_lo && i0 + 3 < r_hi) event(f.y >> 16, p.w, e.w, m >> 24);
+            };
+            quad(q, p0, e0, f0, m0);
+            if (two) quad(q2, p1, e1, f1, m1);
+        }
+    } else {
+        for (uint64_t i = r_lo + tid; i < r_hi; i += 256) event(a.flags[i], a.pos[i], a.end[i], a.mapq[i]);
     }
     carry = __reduce_add_sync(0xffffffffu, carry);
     if (lane == 0 && carry) atomicAdd(&s_carry, carry);

@@ -33,23 +33,31 @@ __device__ __forceinline__ uint32_t tgt_dist(uint32_t s, uint32_t e, uint32_t pt
     return 0u;
 }
 
+// target table loads: read-only global path, or plain loads when the table sits in shared memory
+template <bool SM>
+__device__ __forceinline__ uint32_t ldt(const uint32_t *p) {
+    if (SM) return *p;
+    return __ldg(p);
+}
+
 // returns target index or 0xffffffff
+template <bool SM = false>
 __device__ __forceinline__ uint32_t tgt_best(const TgtArgs &a, uint32_t begin, uint32_t end) {
     const uint32_t centre = (begin + end) >> 1;  // agg.rs:321 (u32)
     uint32_t lo = 0, hi = a.n_tgt;
     while (lo < hi) {  // first t with pmax[t] > begin
         const uint32_t m = (lo + hi) >> 1;
-        if (__ldg(a.pmax + m) > begin) hi = m; else lo = m + 1;
+        if (ldt<SM>(a.pmax + m) > begin) hi = m; else lo = m + 1;
     }
     uint32_t ub = lo;
     hi = a.n_tgt;
     while (ub < hi) {  // first t with ts[t] >= end
         const uint32_t m = (ub + hi) >> 1;
-        if (__ldg(a.ts + m) >= end) hi = m; else ub = m + 1;
+        if (ldt<SM>(a.ts + m) >= end) hi = m; else ub = m + 1;
     }
     uint32_t best = 0xffffffffu, best_d = 0xffffffffu;
     for (uint32_t t = lo; t < ub; ++t) {
-        const uint32_t s = __ldg(a.ts + t), e = __ldg(a.te + t);
+        const uint32_t s = ldt<SM>(a.ts + t), e = ldt<SM>(a.te + t);
         if (!(begin < e)) continue;  // (s < end holds for every t < ub)
         const uint32_t d = tgt_dist(s, e, centre);
         if (best == 0xffffffffu || d < best_d) {
@@ -63,7 +71,7 @@ __device__ __forceinline__ uint32_t tgt_best(const TgtArgs &a, uint32_t begin, u
 
 // First index of a sorted array with arr[i] > key (GT) or arr[i] >= key (!GT), found by the whole
 // warp: 32 probes per step, three steps cover 32768 targets.  `key` must be warp-uniform.
-template <bool GT>
+template <bool GT, bool SM = false>
 __device__ __forceinline__ uint32_t warp_first(const uint32_t *__restrict__ arr, uint32_t n, uint32_t key) {
     const uint32_t lane = lane_id();
     uint32_t lo = 0, hi = n;  // the answer lies in [lo, hi]
@@ -72,7 +80,7 @@ __device__ __forceinline__ uint32_t warp_first(const uint32_t *__restrict__ arr,
         const uint32_t idx = lo + (lane + 1u) * step - 1u;
         bool p = true;
         if (idx < hi) {
-            const uint32_t v = __ldg(arr + idx);
+            const uint32_t v = ldt<SM>(arr + idx);
             p = GT ? v > key : v >= key;
         }
         const unsigned b = __ballot_sync(0xffffffffu, p);
@@ -87,19 +95,38 @@ __device__ __forceinline__ uint32_t warp_first(const uint32_t *__restrict__ arr,
     const uint32_t idx = lo + lane;
     bool p = true;
     if (idx < hi) {
-        const uint32_t v = __ldg(arr + idx);
+        const uint32_t v = ldt<SM>(arr + idx);
         p = GT ? v > key : v >= key;
     }
     const unsigned b = __ballot_sync(0xffffffffu, p);
     return b ? lo + (uint32_t)__ffs(b) - 1u : hi;
 }
 
+// The same with a starting guess: coordinate-sorted reads handed to a warp in consecutive steps move the
+// answer by a few targets at most, so one probe round over [hint - 1, hint + 31) settles it (lane 0 checks
+// that the answer is not below the hint); anything else falls back to the full search.
+template <bool GT, bool SM>
+__device__ __forceinline__ uint32_t warp_first_hint(const uint32_t *__restrict__ arr, uint32_t n, uint32_t key, uint32_t hint) {
+    const uint32_t lane = lane_id();
+    if (hint > n) hint = n;
+    const uint32_t idx = hint + lane - 1u;  // lane 0: hint - 1
+    bool p = lane != 0u;                    // beyond the end counts as "true"; hint == 0: nothing below
+    if ((lane != 0u || hint != 0u) && idx < n) {
+        const uint32_t v = ldt<SM>(arr + idx);
+        p = GT ? v > key : v >= key;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    if ((b & 1u) == 0u && (b >> 1) != 0u) return hint + (uint32_t)__ffs(b >> 1) - 1u;
+    return warp_first<GT, SM>(arr, n, key);
+}
+
 // the scan of tgt_best over a candidate range that is a superset of the intersecting targets
+template <bool SM = false>
 __device__ __forceinline__ uint32_t tgt_best_in(const TgtArgs &a, uint32_t begin, uint32_t end, uint32_t lo, uint32_t ub) {
     const uint32_t centre = (begin + end) >> 1;  // agg.rs:321 (u32)
     uint32_t best = 0xffffffffu, best_d = 0xffffffffu;
     for (uint32_t t = lo; t < ub; ++t) {
-        const uint32_t s = __ldg(a.ts + t), e = __ldg(a.te + t);
+        const uint32_t s = ldt<SM>(a.ts + t), e = ldt<SM>(a.te + t);
         if (!(begin < e) || !(s < end)) continue;  // does not intersect [begin, end)
         const uint32_t d = tgt_dist(s, e, centre);
         if (best == 0xffffffffu || d < best_d) {
@@ -111,26 +138,59 @@ __device__ __forceinline__ uint32_t tgt_best_in(const TgtArgs &a, uint32_t begin
     return best;
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(256, 4) frag_bin_tgt_kernel(TgtArgs a) {
+// SM: the target table of the region (running max of ends | starts | ends, 12 B per target) is staged in
+// shared memory by every CTA -- the two cooperative searches and the candidate scans of a warp step are a
+// chain of ~8 dependent table reads, ~30 cycles each from shared memory against ~250 from L2.  The read
+// columns of the NEXT step are requested before the current one is processed (VEC), so the trip to HBM
+// overlaps the searches.
+template <bool VEC, bool SM>
+__global__ void __launch_bounds__(256, SM ? 3 : 4) frag_bin_tgt_kernel(TgtArgs a) {
     constexpr int E = VEC ? 4 : 1;
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    if (SM) {
+        const uint32_t n = a.n_tgt;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            s_tab[i] = __ldg(a.pmax + i);
+            s_tab[n + i] = __ldg(a.ts + i);
+            s_tab[2 * n + i] = __ldg(a.te + i);
+        }
+        __syncthreads();
+        a.pmax = s_tab;
+        a.ts = s_tab + n;
+        a.te = s_tab + 2 * n;
+    }
     const uint64_t nitems = VEC ? (a.n >> 2) : a.n;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t n_proc = 0, n_skip = 0;
-    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t qb = first - lane_id(); qb < nitems; qb += stride) {
+    // every warp takes a CONTIGUOUS run of steps (32 items each): the target range of one step is the
+    // starting guess of the next
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_steps = (nitems + 31) >> 5, per_warp = (n_steps + n_warps - 1) / n_warps;
+    const uint64_t warp_id = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t stride = 32;
+    const uint64_t first = warp_id * per_warp * 32 + lane_id();
+    const uint64_t w_end = min(nitems, (warp_id + 1) * per_warp * 32);
+    uint32_t n_proc = 0, n_skip = 0, hint_lo = 0, hint_ub = 0;
+    int4 np = make_int4(0, 0, 0, 0), nfe = make_int4(0, 0, 0, 0);
+    uint32_t nm = 0;
+    uint2 nf = make_uint2(0, 0);
+    if (VEC && first < w_end) {
+        np = ld_stream(reinterpret_cast<const int4 *>(a.pos) + first);
+        nfe = ld_stream(reinterpret_cast<const int4 *>(a.frag_end) + first);
+        nm = ld_stream(reinterpret_cast<const uint32_t *>(a.mapq) + first);
+        nf = ld_stream(reinterpret_cast<const uint2 *>(a.flags) + first);
+    }
+    for (uint64_t qb = first - lane_id(); qb < w_end; qb += stride) {
         const uint64_t q = qb + lane_id();
-        const bool valid = q < nitems;
+        const bool valid = q < w_end;
         uint32_t begin[E], fend[E], mq[E], fl[E];
         if (VEC) {
-            int4 p = make_int4(0, 0, 0, 0), fe = make_int4(0, 0, 0, 0);
-            uint32_t m = 0;
-            uint2 f = make_uint2(0, 0);
-            if (valid) {
-                p = ld_stream(reinterpret_cast<const int4 *>(a.pos) + q);
-                fe = ld_stream(reinterpret_cast<const int4 *>(a.frag_end) + q);
-                m = ld_stream(reinterpret_cast<const uint32_t *>(a.mapq) + q);
-                f = ld_stream(reinterpret_cast<const uint2 *>(a.flags) + q);
+            const int4 p = np, fe = nfe;
+            const uint32_t m = nm;
+            const uint2 f = nf;
+            if (q + stride < w_end) {  // the next step's columns
+                np = ld_stream(reinterpret_cast<const int4 *>(a.pos) + q + stride);
+                nfe = ld_stream(reinterpret_cast<const int4 *>(a.frag_end) + q + stride);
+                nm = ld_stream(reinterpret_cast<const uint32_t *>(a.mapq) + q + stride);
+                nf = ld_stream(reinterpret_cast<const uint2 *>(a.flags) + q + stride);
             }
             const uint32_t pp[4] = {(uint32_t)p.x, (uint32_t)p.y, (uint32_t)p.z, (uint32_t)p.w};
             const uint32_t ee[4] = {(uint32_t)fe.x, (uint32_t)fe.y, (uint32_t)fe.z, (uint32_t)fe.w};
@@ -165,15 +225,17 @@ __global__ void __launch_bounds__(256, 4) frag_bin_tgt_kernel(TgtArgs a) {
         bmin = __reduce_min_sync(0xffffffffu, bmin);
         emax = __reduce_max_sync(0xffffffffu, emax);
         if (emax == 0u && bmin == 0xffffffffu) continue;  // no fragment passes the filter (warp-uniform)
-        const uint32_t lo_w = warp_first<true>(a.pmax, a.n_tgt, bmin);    // first target whose running max end > begin
-        const uint32_t ub_w = warp_first<false>(a.ts, a.n_tgt, emax);     // first target starting at or after the end
+        const uint32_t lo_w = warp_first_hint<true, SM>(a.pmax, a.n_tgt, bmin, hint_lo);   // first target whose running max end > begin
+        const uint32_t ub_w = warp_first_hint<false, SM>(a.ts, a.n_tgt, emax, hint_ub);    // first target starting at or after the end
+        hint_lo = lo_w;
+        hint_ub = ub_w;
         const bool narrow = ub_w <= lo_w + 16u;  // otherwise (unsorted input, giant fragments): per-read search
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             uint32_t best = 0xffffffffu, cnt = 0;
             if (pass[e]) {
                 n_proc += 1;
-                best = narrow ? tgt_best_in(a, begin[e], fend[e], lo_w, ub_w) : tgt_best(a, begin[e], fend[e]);
+                best = narrow ? tgt_best_in<SM>(a, begin[e], fend[e], lo_w, ub_w) : tgt_best<SM>(a, begin[e], fend[e]);
                 if (best == 0xffffffffu) n_skip += 1; else cnt = 1;  // agg.rs:340-345
             }
             warp_bin_add(a.counters, best, cnt);
@@ -183,7 +245,7 @@ __global__ void __launch_bounds__(256, 4) frag_bin_tgt_kernel(TgtArgs a) {
         for (uint64_t i = (a.n >> 2) << 2; i < a.n; ++i) {
             if (frag_pass(a.flags[i], a.mapq[i], a.min_mapq)) {
                 n_proc += 1;
-                const uint32_t best = tgt_best(a, (uint32_t)a.pos[i], (uint32_t)a.frag_end[i]);
+                const uint32_t best = tgt_best<SM>(a, (uint32_t)a.pos[i], (uint32_t)a.frag_end[i]);
                 if (best == 0xffffffffu) n_skip += 1; else atomicAdd(&a.counters[best], 1u);
             }
         }
@@ -243,12 +305,28 @@ int put_targets(cnvb_ctx *ctx, const cnvb_read_soa *b, const uint32_t *d_ts, con
                              ((uintptr_t)g.mapq % 4 == 0) && ((uintptr_t)g.flags % 8 == 0);
         const uint64_t work = aligned ? (n + 3) / 4 : n;
         const uint64_t work_blocks = (work + 255) / 256;
+        // table in shared memory: up to 6144 targets (72 KB, three CTAs per SM)
+        // (off unless CNVB_TGT_SMEM=1: measured on config 1, 4010 targets -- 74 against 66 us; the 48 KB copy per
+        // CTA costs more than the shorter table latency returns once the searches start from a hint)
+        static const bool smem_on = [] {
+            const char *e = getenv("CNVB_TGT_SMEM");
+            return e && atoi(e) == 1;
+        }();
+        const bool in_smem = smem_on && n_tgt > 0 && n_tgt <= 6144 && n >= (1u << 16);
+        const size_t tab_bytes = in_smem ? (size_t)n_tgt * 12 : 0;
         {
             KernelSpan span(ctx, "frag_bin_tgt_kernel");
-            if (aligned)
-                frag_bin_tgt_kernel<true><<<persistent_grid(ctx, frag_bin_tgt_kernel<true>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);
-            else
-                frag_bin_tgt_kernel<false><<<persistent_grid(ctx, frag_bin_tgt_kernel<false>, 256, 0, work_blocks), 256, 0, ctx->stream>>>(g);
+#define CNVB_TGT_LAUNCH(V, M)                                                                                             \
+    do {                                                                                                                 \
+        auto kern = frag_bin_tgt_kernel<V, M>;                                                                           \
+        if (M) CNVB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 12), "smem opt-in"); \
+        kern<<<persistent_grid(ctx, kern, 256, M ? 6144 * 12 : 0, work_blocks), 256, tab_bytes, ctx->stream>>>(g);        \
+    } while (0)
+            if (aligned && in_smem) CNVB_TGT_LAUNCH(true, true);
+            else if (aligned) CNVB_TGT_LAUNCH(true, false);
+            else if (in_smem) CNVB_TGT_LAUNCH(false, true);
+            else CNVB_TGT_LAUNCH(false, false);
+#undef CNVB_TGT_LAUNCH
         }
         CNVB_LAUNCHED(ctx, "frag_bin_tgt_kernel");
     }

@@ -905,6 +905,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // (`order`, sorted after the window kernel): the hardware dispatches CTAs in index order as SMs free up,
 // which makes the launch a longest-processing-time schedule instead of 5.3 uneven waves.
 constexpr uint32_t kDStages = 2;  // double tiles in flight: 2 x (n_kblocks x 32 KB)
+constexpr uint32_t kQueueCap = 96;  // survivors a warp holds back before it goes for their slots
 constexpr uint32_t kIdesc256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __global__ void __launch_bounds__(kSweepThreads, 1)
@@ -928,6 +929,7 @@ wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t bar_acc_full = bar_b_empty + 8 * kDStages;  // 2 (row halves)
     const uint32_t bar_acc_empty = bar_acc_full + 16;          // 2
     const uint32_t tmem_slot = bar_acc_empty + 16;
+    const uint32_t queue_base = (tmem_slot + 16u + 15u) & ~15u;  // kEpiWarps x kQueueCap x 16 B
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blk * kTileRows;
     if (warp == 0 && lane == 0) {
@@ -1008,8 +1010,29 @@ wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp >= 4) {
         // ===== epilogue: warp e reads TMEM lane quarter q = e & 3 (row h * 128 + 32 q + lane of the block) and
-        // the 64 columns [64 (e >> 2), +64) of the double tile, in two loads of 32 =====
+        // the 64 columns [64 (e >> 2), +64) of the double tile, in two loads of 32.
+        // Survivors (a few per 1024 pairs, so nearly every load has some) do NOT go to their row's list at
+        // once: the slot comes from an atomic on the row's counter in HBM, and waiting for it inside the
+        // loop -- once per group of columns with a survivor -- cost more than everything else in this kernel
+        // (measured: 9700 of 11000 cycles per tile).  They are pushed to a queue of the warp in shared memory
+        // (positions from a ballot, no atomics) and the queue is emptied 32 entries at a time, one atomic per
+        // lane in flight together. =====
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
+        uint4 *queue = reinterpret_cast<uint4 *>(smem_raw + (queue_base - smem_u32(smem_raw))) + e * kQueueCap;
+        uint32_t qn = 0;  // entries in the queue (warp-uniform)
+        auto flush = [&]() {
+            __syncwarp();
+            for (uint32_t i = lane; i < qn; i += 32) {
+                const uint4 en = queue[i];  // (row, column, value)
+                const uint32_t slot = atomicAdd(&a.cand_cnt[en.x], 1u);
+                if (slot < kCandCap) {  // beyond: overflow, the row falls back
+                    a.cand_val[(size_t)en.x * kCandCap + slot] = __uint_as_float(en.z);
+                    a.cand_idx[(size_t)en.x * kCandCap + slot] = en.y;
+                }
+            }
+            qn = 0;
+            __syncwarp();
+        };
         float thr[2], kap[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -1056,7 +1079,7 @@ wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             gmask |= p ? (1u << g4) : 0u;
                         }
                         const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
-                        if (wmask) {  // survivors are rare: the append code runs only for groups in which some row passes
+                        if (wmask) {  // the push code runs (warp-uniformly) only for groups in which some row passes
 #pragma unroll
                             for (int g4 = 0; g4 < 8; ++g4) {
                                 if (wmask & (1u << g4)) {
@@ -1065,12 +1088,12 @@ wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                         const int c = 4 * g4 + e4;
                                         const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
                                         const uint32_t j = j0 + 32 * half + c;
-                                        if (v <= rhs && j < a.T) {  // (rows beyond the end: theta = -inf)
-                                            const uint32_t slot = atomicAdd(&a.cand_cnt[row], 1u);
-                                            if (slot < kCandCap) {  // beyond: overflow, the row falls back
-                                                a.cand_val[(size_t)row * kCandCap + slot] = v;
-                                                a.cand_idx[(size_t)row * kCandCap + slot] = j;
-                                            }
+                                        const bool keep = v <= rhs && j < a.T;  // (rows beyond the end: theta = -inf)
+                                        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                                        if (m) {
+                                            if (qn + 32u > kQueueCap) flush();
+                                            if (keep) queue[qn + __popc(m & ((1u << lane) - 1u))] = make_uint4(row, j, __float_as_uint(v), 0u);
+                                            qn += __popc(m);
                                         }
                                     }
                                 }
@@ -1081,9 +1104,11 @@ wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_acc_empty + 8 * h);
+                if (qn >= 32u) flush();  // after the accumulator has been handed back: the tensor core does not wait for it
             }
             aph ^= 1u;
         }
+        flush();
     }
     tc_fence_before();
     __syncthreads();
@@ -1652,7 +1677,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     }();
     CUtensorMap tmap_b2 = tmap_b;
     if (n256) CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b2, 256));
-    const size_t smem256 = (size_t)(2 + 2 * kDStages) * (Kp / kKBlock) * kTileBytes + 512 + 1024;
+    const size_t smem256 = (size_t)(2 + 2 * kDStages) * (Kp / kKBlock) * kTileBytes + 512 + 1024 +
+                           (size_t)kEpiWarps * kQueueCap * sizeof(uint4);
     if (n256)
         CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem256),
                   "smem opt-in");
