@@ -1669,11 +1669,13 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b));
     if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
-    // S <= 128, rounds >= 1: double tiles of 256 columns on M128 x N256 accumulators (wis_sweep256_kernel);
-    // CNVB_WIS_N256 = 0 keeps the M128 x N128 form
+    // S <= 128, rounds >= 1: double tiles of 256 columns on M128 x N256 accumulators (wis_sweep256_kernel) --
+    // only with CNVB_WIS_N256 = 1: measured at 200 000 x 100 the sweeps take 7.3 ms against 4.1 ms for the
+    // M128 x N128 form (gpurun_out/r2_wis_probe.txt: the longer per-item epilogue outweighs the halved
+    // operand traffic), so the N128 form stays the default
     const bool n256 = !stream_a && [] {
         const char *e = getenv("CNVB_WIS_N256");
-        return !(e && atoi(e) == 0);
+        return e && atoi(e) == 1;
     }();
     CUtensorMap tmap_b2 = tmap_b;
     if (n256) CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b2, 256));

@@ -262,6 +262,21 @@ def test_wis_streamed_sweep_variants(oracle, ctx, monkeypatch, cluster, xpose):
     assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
 
 
+def test_wis_resident_sweep_n256_variant(oracle, ctx, monkeypatch):
+    """S <= 128: the M128 x N256 double-tile form of the later rounds (CNVB_WIS_N256 = 1; off by default,
+    it measured slower than the N128 form at config 3) still selects the oracle's sets, bit for bit."""
+    monkeypatch.setenv("CNVB_WIS_N256", "1")
+    T, S, k = 6100, 100, 40
+    X, tids = synth.synth_panel(911, T, S, n_contigs=6)
+    X[40] = X[41]
+    odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
+    opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)
+    dist, idx = mw.compute_distances(_dev(X), _dev(tids), opts, ctx=ctx)
+    assert np.array_equal(to_np(idx).astype(np.uint32), oidx)
+    assert_f32_equal_bits(to_np(dist).ravel(), odist.ravel(), "distances")
+    assert mw.last_stats(ctx)["fallback_rows"] == 0
+
+
 def test_wis_tensor_single_contig_and_tiny_other_contig(oracle, ctx):
     T, S, k = 4500, 20, 50
     X, _ = synth.synth_panel(77, T, S, n_contigs=1)
