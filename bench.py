@@ -94,6 +94,7 @@ class Env:
             dist.init_process_group("nccl", device_id=torch.device(self.dev))
             self.dist = dist
         self.ctx = cb.Context(self.local)
+        ClockSampler.enabled = self.rank == 0
         self.comm = parallel.Communicator(self.ctx, self.rank, self.world)
         self.t0 = time.perf_counter()
 
@@ -147,75 +148,98 @@ def contigs(scale):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  One
-    long-running `nvidia-smi -lms 20` is started early (`arm`, before the warm-up: the tool needs
-    ~100 ms to come up); `start`/`stop` bracket the timed region by wall clock and only the samples
-    stamped inside it are reported.  A timed region shorter than the sampling period falls back to
-    the samples taken under the same load since `arm`, and says so."""
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), sampled
+    in-process through NVML every 5 ms: two light queries per sample (SM clock, clocks-event reasons).
+    A background `nvidia-smi -lms 20` -- the first version of this sampler -- stalls NCCL collectives on the
+    sampled GPU: at 8 ranks the sharded normaliser went from 0.18 to 0.79 ms per step with it
+    (gpurun_out/r2_scale_probe_n8.json), so only rank 0 samples, and only these two counters.  `start`/`stop`
+    bracket the timed region by wall clock; a region shorter than the period falls back to the samples
+    taken under the same load since `arm` (the warm-up), and says so.  Falls back to one `nvidia-smi`
+    query after the region when NVML is not importable."""
+    enabled = True   # Env switches it off on ranks other than 0
+    PERIOD = 0.005
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
-        self.arm()
+        self.index, self.rows, self.t0, self.t1 = index, [], None, None
+        self.nvml, self.handle, self.max_mhz, self.thread, self.stop_flag = None, None, None, None, False
+        if ClockSampler.enabled:
+            self.arm()
 
     def arm(self):
-        if self.proc:
+        if self.thread:
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.time(), float(mhz), int(why)))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD)
 
     def start(self):
         t_wait = time.time()
-        while self.proc and not self.rows and time.time() - t_wait < 0.5:  # the tool is up once it has printed a line
-            time.sleep(0.005)
+        while self.thread and not self.rows and time.time() - t_wait < 0.2:
+            time.sleep(0.001)
         self.t0 = time.time()
-
-    def _read(self):
-        import datetime
-        for line in self.proc.stdout:
-            r = [x.strip() for x in line.split(",")]
-            try:
-                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-            except Exception:
-                ts = time.time()
-            self.rows.append((ts, r))
 
     def stop(self):
         self.t1 = time.time()
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)  # let the sample that covers the end of the region arrive
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 - 0.01 <= ts <= self.t1 + 0.01]
+        if not ClockSampler.enabled:
+            return None
+        if not self.thread:
+            return self._smi_once()
+        time.sleep(2 * self.PERIOD)  # let the sample that covers the end of the region arrive
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nvml
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 - 0.002 <= r[0] <= self.t1 + 0.002]
         window = "timed region"
         if not inside:
-            inside = [r for ts, r in self.rows if ts <= self.t1 + 0.01][-10:]
-            window = "timed region shorter than the 20 ms sampling period: last samples under the same load (warm-up)"
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in inside:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for n, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
+            inside = [r for r in self.rows if r[0] <= self.t1 + 0.002][-10:]
+            window = "timed region shorter than the 5 ms sampling period: last samples under the same load (warm-up)"
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, b in bits.items() if any(r[2] & b for r in inside))
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "window": window, "reasons": reasons, "source": "NVML in-process, rank 0, 5 ms period"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(r[0]), "sm_max_mhz": float(r[1]), "samples": 1,
+                    "window": "one nvidia-smi query right after the timed region (NVML not importable)",
+                    "reasons": sorted(n for n, v in zip(names, r[2:6]) if v.strip().lower().startswith("active"))}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
 def measured_peak():

@@ -42,16 +42,22 @@ class CovColumns(C.Structure):
                                           "mean_mapq", "gap", "ft")]
 
 
-class VcfOpts(C.Structure):
-    _fields_ = [("path", C.c_char_p), ("sample", C.c_char_p), ("n_contigs", C.c_uint32),
-                ("contig_names", C.POINTER(C.c_char_p)), ("contig_lens", C.c_void_p),
-                ("command_line", C.c_char_p), ("file_date", C.c_char_p), ("is_targets", C.c_int),
+class VfileFmt(C.Structure):
+    _fields_ = [("key", C.c_char_p), ("values", C.c_void_p), ("present", C.c_void_p)]
+
+
+class VfileWriteArgs(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("header_text", C.c_char_p), ("n_samples", C.c_uint32),
+                ("samples", C.POINTER(C.c_char_p)), ("n_rows", C.c_uint64), ("rid", C.c_void_p), ("pos", C.c_void_p),
+                ("end", C.c_void_p), ("is_targets", C.c_int), ("filters", C.c_void_p), ("gap", C.c_void_p),
+                ("gc", C.c_void_p), ("mean_mapq", C.c_void_p), ("few_gc", C.c_void_p), ("ref_mean", C.c_void_p),
+                ("ref_sd", C.c_void_p), ("ref_present", C.c_void_p), ("num_calls", C.c_void_p),
+                ("ref_off", C.c_void_p), ("ref_idx", C.c_void_p), ("n_fmt", C.c_uint32),
+                ("fmt", C.POINTER(VfileFmt)), ("ft", C.c_void_p), ("ft_pos", C.c_uint32), ("write_index", C.c_int),
                 ("n_threads", C.c_int)]
 
 
-class VcfColumns(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("contig", "start", "end", "rcv", "rcvsd", "lcv", "lcvsd", "frm", "gc",
-                                          "gap", "mean_mapq", "ft", "cv", "cv2", "cvsd", "norm_flags")]
+VF_PASS, VF_PILE, VF_LOWCOV, VF_NO_REF, VF_FEW_REF, VF_UNRELIABLE, VF_OTHER = 1, 2, 4, 8, 16, 32, 128
 
 
 class WisOpts(C.Structure):
@@ -89,7 +95,26 @@ SYMBOLS = {
     "cnvb_bam_ref_reads": (_int, [_vp, _u32, C.POINTER(ReadSoa)]),
     "cnvb_bam_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
     "cnvb_bam_close": (None, [_vp]),
-    "cnvb_vcf_write_coverage": (_int, [_vp, _vp, _u64, C.c_char_p, _u64]),
+    "cnvb_vfile_write": (_int, [C.POINTER(VfileWriteArgs), C.c_char_p, _u64]),
+    "cnvb_vfile_open": (_int, [C.c_char_p, _int, C.POINTER(_vp), C.c_char_p, _u64]),
+    "cnvb_vfile_close": (None, [_vp]),
+    "cnvb_vfile_last_error": (C.c_char_p, [_vp]),
+    "cnvb_vfile_num_records": (_u64, [_vp]),
+    "cnvb_vfile_num_samples": (_u32, [_vp]),
+    "cnvb_vfile_sample": (C.c_char_p, [_vp, _u32]),
+    "cnvb_vfile_num_contigs": (_u32, [_vp]),
+    "cnvb_vfile_contig_name": (C.c_char_p, [_vp, _u32]),
+    "cnvb_vfile_contig_length": (_u32, [_vp, _u32]),
+    "cnvb_vfile_header_text": (C.c_char_p, [_vp]),
+    "cnvb_vfile_is_bcf": (_int, [_vp]),
+    "cnvb_vfile_fixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_int)]),
+    "cnvb_vfile_info_float": (_int, [_vp, C.c_char_p, _vp, _vp]),
+    "cnvb_vfile_info_int": (_int, [_vp, C.c_char_p, _vp, _vp]),
+    "cnvb_vfile_info_flag": (_int, [_vp, C.c_char_p, _vp]),
+    "cnvb_vfile_format_float": (_int, [_vp, C.c_char_p, _vp, _vp]),
+    "cnvb_vfile_format_ft": (_int, [_vp, _vp, _vp]),
+    "cnvb_vfile_match_ids": (_int, [_vp, _vp, _vp]),
+    "cnvb_vfile_ref_targets": (_int, [_vp, _vp, _vp, _vp, _u64]),
     "cnvb_cov_create": (_int, [_vp, C.POINTER(CovOpts), _int, _u32, _vp, _vp, _u32, _vp, _vp,
                                _u32, C.POINTER(_vp)]),
     "cnvb_cov_put_records": (_int, [_vp, C.POINTER(ReadSoa)]),

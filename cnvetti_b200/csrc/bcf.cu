@@ -1,0 +1,1573 @@
+// bcf.cu -- host reader / writer of the VCF / BCF files that chain the commands of the path, with their index.
+//
+// The reference moves every intermediate result through htslib files: `cmd coverage` writes one record per
+// window (lib-coverage/src/lib.rs:560-673) under the header of :67-166; `cmd normalize` reads them back, pushes
+// FORMAT/CV (CV2, CVSD) and writes again (lib-normalize/src/shared.rs:16-75); `cmd merge-cov` joins N files
+// into a multi-sample one (lib-merge-cov/src/lib.rs:102-232); `cmd build-model-wis` reads the panel from it
+// (lib-model-wis/src/lib.rs:65-125) and writes the model records with INFO/REF_TARGETS (:340-419);
+// `cmd mod-coverage` reads both (lib-mod-cov/src/lib.rs:33-164) and writes the coverage records with
+// REF_MEAN / REF_STD_DEV / CV / CVZ / CV2 (:167-248); each ends with build_index
+// (lib-shared/src/bcf_utils.rs:47-82: `.bcf` -> CSI with min_shift 14, `.vcf.gz` -> TBI).  This file is the
+// htslib-free equivalent for exactly those files: binary BCF2.2 and VCF text, raw and BGZF, CSI and TBI.
+//
+// Records are COLUMNS here (one array per tag, see include/cnvetti_b200.h): the writer formats rows on host
+// threads into BGZF blocks deflated on host threads; the reader inflates the blocks on threads, walks the
+// record boundaries once and extracts a tag as a column on request.  Encoding follows the BCF2.2 / CSI / tabix
+// specifications (typed values with the smallest integer type, `rlen` = END - POS, dictionary indices in
+// header order with PASS = 0, virtual offsets = block address << 16 | offset in block).
+//
+// Pure host code.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr size_t kBlock = 0xff00;  // uncompressed bytes per BGZF block
+constexpr uint32_t kFloatMissing = CNVB_F32_MISSING_BITS;
+enum { BT_NULL = 0, BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5, BT_CHAR = 7 };
+enum { HT_FLAG = 0, HT_INT = 1, HT_REAL = 2, HT_STR = 3 };
+
+int hw_threads(int want) {
+    if (want > 0) return want;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw ? (int)hw : 1;
+}
+
+void parallel_for(int n_threads, uint64_t n, const std::function<void(uint64_t, uint64_t, int)> &fn) {
+    if (n_threads <= 1 || n < 2) {
+        if (n) fn(0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    const uint64_t per = (n + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const uint64_t a = std::min<uint64_t>(n, per * t), b = std::min<uint64_t>(n, a + per);
+        if (a < b) th.emplace_back(fn, a, b, t);
+    }
+    for (auto &x : th) x.join();
+}
+
+int vfail(char *err, uint64_t err_len, int code, const std::string &msg) {
+    if (err && err_len) snprintf(err, (size_t)err_len, "%s", msg.c_str());
+    return code;
+}
+
+bool ends_with(const std::string &s, const char *suffix) {
+    const size_t n = strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+
+// ---- BGZF ---------------------------------------------------------------------------------------------
+std::string bgzf_block(const uint8_t *data, size_t n, int level) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    std::string out(18 + compressBound((uLong)n) + 8, '\0');
+    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = const_cast<Bytef *>(data);
+    zs.avail_in = (uInt)n;
+    zs.next_out = reinterpret_cast<Bytef *>(&out[18]);
+    zs.avail_out = (uInt)(out.size() - 18);
+    deflate(&zs, Z_FINISH);
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(&out[0], head, 16);
+    const uint16_t bsize = (uint16_t)(clen + 25);
+    memcpy(&out[16], &bsize, 2);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data, (uInt)n), isize = (uint32_t)n;
+    memcpy(&out[18 + clen], &crc, 4);
+    memcpy(&out[18 + clen + 4], &isize, 4);
+    out.resize(18 + clen + 8);
+    return out;
+}
+
+// Output stream: raw bytes or BGZF blocks of exactly kBlock uncompressed bytes (the last one shorter), so
+// that the block of an uncompressed offset is offset / kBlock and virtual offsets follow from the table
+// of block addresses.
+struct Sink {
+    FILE *f = nullptr;
+    bool bgzf = false;
+    int n_threads = 1;
+    std::string pending;
+    uint64_t utotal = 0;               // uncompressed bytes accepted so far
+    uint64_t cpos = 0;                 // compressed bytes written so far
+    std::vector<uint64_t> block_addr;  // file offset of block i (+ one entry for the EOF block)
+    bool write_all(const std::string &s) {
+        cpos += s.size();
+        return fwrite(s.data(), 1, s.size(), f) == s.size();
+    }
+    bool put(const char *p, size_t n, bool final) {
+        utotal += n;
+        if (!bgzf) {
+            cpos += n;
+            return fwrite(p, 1, n, f) == n;
+        }
+        pending.append(p, n);
+        const size_t n_full = pending.size() / kBlock;
+        const size_t n_blocks = n_full + ((final && pending.size() % kBlock) ? 1 : 0);
+        std::vector<std::string> out(n_blocks);
+        parallel_for(n_threads, n_blocks, [&](uint64_t a, uint64_t b, int) {
+            for (uint64_t i = a; i < b; ++i) {
+                const size_t off = i * kBlock, len = std::min(kBlock, pending.size() - off);
+                out[i] = bgzf_block(reinterpret_cast<const uint8_t *>(pending.data()) + off, len, 6);
+            }
+        });
+        for (auto &o : out) {
+            block_addr.push_back(cpos);
+            if (!write_all(o)) return false;
+        }
+        pending.erase(0, std::min(pending.size(), n_blocks * kBlock));
+        if (final) {
+            block_addr.push_back(cpos);
+            return write_all(bgzf_block(nullptr, 0, 6));  // the 28-byte EOF marker
+        }
+        return true;
+    }
+    uint64_t voffset(uint64_t uoff) const {
+        const uint64_t b = uoff / kBlock;
+        return (block_addr[(size_t)std::min<uint64_t>(b, block_addr.size() - 1)] << 16) | (uoff % kBlock);
+    }
+};
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+// whole-file inflate: BGZF members on threads; a plain gzip stream (no BC subfield) sequentially
+bool inflate_all(const uint8_t *p, uint64_t n, int n_threads, std::string &out, std::string &err) {
+    struct Blk { uint64_t off; uint32_t clen, isize; uint64_t uoff; };
+    std::vector<Blk> blocks;
+    uint64_t at = 0, utot = 0;
+    bool is_bgzf = true;
+    while (at < n) {
+        if (n - at < 18 || p[at] != 0x1f || p[at + 1] != 0x8b) { err = "truncated or corrupt gzip member"; return false; }
+        const uint16_t xlen = (p[at + 3] & 4) ? rd16(p + at + 10) : 0;
+        uint32_t bsize = 0;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t *sf = p + at + 12 + x;
+            const uint16_t slen = rd16(sf + 2);
+            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2) bsize = rd16(sf + 4) + 1u;
+            x += 4u + slen;
+        }
+        if (!bsize) { is_bgzf = false; break; }
+        if (at + bsize > n || bsize < 12u + xlen + 8u) { err = "truncated BGZF block"; return false; }
+        Blk b;
+        b.off = at + 12 + xlen;
+        b.clen = bsize - 12 - xlen - 8;
+        b.isize = rd32(p + at + bsize - 4);
+        b.uoff = utot;
+        utot += b.isize;
+        blocks.push_back(b);
+        at += bsize;
+    }
+    if (!is_bgzf) {  // ordinary (multi-member) gzip
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, 15 + 32) != Z_OK) { err = "zlib init failed"; return false; }
+        zs.next_in = const_cast<Bytef *>(p);
+        zs.avail_in = (uInt)std::min<uint64_t>(n, UINT_MAX);
+        out.clear();
+        std::vector<char> buf(1 << 20);
+        for (;;) {
+            zs.next_out = reinterpret_cast<Bytef *>(buf.data());
+            zs.avail_out = (uInt)buf.size();
+            const int rc = inflate(&zs, Z_NO_FLUSH);
+            out.append(buf.data(), buf.size() - zs.avail_out);
+            if (rc == Z_STREAM_END) {
+                if (zs.avail_in == 0) break;
+                inflateReset(&zs);
+            } else if (rc != Z_OK) {
+                inflateEnd(&zs);
+                err = "gzip stream is corrupt";
+                return false;
+            }
+        }
+        inflateEnd(&zs);
+        return true;
+    }
+    out.resize(utot);
+    std::atomic<bool> bad{false};
+    parallel_for(n_threads, blocks.size(), [&](uint64_t a, uint64_t b, int) {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+        for (uint64_t i = a; i < b && !bad; ++i) {
+            const Blk &k = blocks[i];
+            if (!k.isize) continue;
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef *>(p + k.off);
+            zs.avail_in = k.clen;
+            zs.next_out = reinterpret_cast<Bytef *>(&out[k.uoff]);
+            zs.avail_out = k.isize;
+            if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.avail_out != 0) bad = true;
+        }
+        inflateEnd(&zs);
+    });
+    if (bad) { err = "BGZF block does not inflate"; return false; }
+    return true;
+}
+
+// ---- header -------------------------------------------------------------------------------------------
+struct DictEntry {
+    std::string id;
+    int info_type = -1, fmt_type = -1;
+    bool is_filter = false;
+};
+
+struct Header {
+    std::vector<std::string> lines;  // the ## lines, IDX keys removed
+    std::vector<std::string> samples;
+    std::vector<std::string> contig_names;
+    std::vector<uint32_t> contig_lens;
+    std::vector<DictEntry> dict;
+    std::unordered_map<std::string, int> dict_idx, contig_idx;
+    std::vector<int> line_idx;  // dictionary index of FILTER / INFO / FORMAT / contig lines (else -1)
+
+    int find(const char *id) const {
+        auto it = dict_idx.find(id);
+        return it == dict_idx.end() ? -1 : it->second;
+    }
+};
+
+// "KEY=<a=b,c="d,e">" -> pairs; returns false for a line without the <...> structure
+bool parse_structured(const std::string &line, std::string &kind, std::vector<std::pair<std::string, std::string>> &kv) {
+    if (line.size() < 4 || line[0] != '#' || line[1] != '#') return false;
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos || eq + 1 >= line.size() || line[eq + 1] != '<') return false;
+    kind = line.substr(2, eq - 2);
+    size_t i = eq + 2;
+    const size_t n = line.size();
+    while (i < n && line[i] != '>') {
+        size_t k0 = i;
+        while (i < n && line[i] != '=' && line[i] != ',' && line[i] != '>') ++i;
+        std::string key = line.substr(k0, i - k0), val;
+        if (i < n && line[i] == '=') {
+            ++i;
+            if (i < n && line[i] == '"') {
+                size_t v0 = ++i;
+                while (i < n && !(line[i] == '"' && line[i - 1] != '\\')) ++i;
+                val = line.substr(v0, i - v0);
+                if (i < n) ++i;
+            } else {
+                size_t v0 = i;
+                while (i < n && line[i] != ',' && line[i] != '>') ++i;
+                val = line.substr(v0, i - v0);
+            }
+        }
+        kv.emplace_back(key, val);
+        if (i < n && line[i] == ',') ++i;
+    }
+    return true;
+}
+
+std::string strip_idx(const std::string &line) {
+    const size_t p = line.rfind(",IDX=");
+    if (p == std::string::npos) return line;
+    size_t q = p + 5;
+    while (q < line.size() && isdigit((unsigned char)line[q])) ++q;
+    return line.substr(0, p) + line.substr(q);
+}
+
+int type_code(const std::string &t) {
+    if (t == "Flag") return HT_FLAG;
+    if (t == "Integer") return HT_INT;
+    if (t == "Float") return HT_REAL;
+    return HT_STR;
+}
+
+// builds the dictionaries from the ## lines (in order; explicit IDX wins; PASS is entry 0)
+bool header_build(Header &h, const std::vector<std::string> &raw_lines, std::string &err) {
+    h.dict.clear();
+    h.dict_idx.clear();
+    h.dict.push_back(DictEntry{"PASS", -1, -1, true});
+    h.dict_idx["PASS"] = 0;
+    for (const std::string &raw : raw_lines) {
+        std::string kind;
+        std::vector<std::pair<std::string, std::string>> kv;
+        int idx_of_line = -1;
+        if (parse_structured(raw, kind, kv)) {
+            std::string id, type;
+            int idx = -1;
+            uint32_t length = 0;
+            for (auto &p : kv) {
+                if (p.first == "ID") id = p.second;
+                else if (p.first == "IDX") idx = atoi(p.second.c_str());
+                else if (p.first == "Type") type = p.second;
+                else if (p.first == "length") length = (uint32_t)strtoul(p.second.c_str(), nullptr, 10);
+            }
+            if (kind == "contig") {
+                if (id.empty()) { err = "##contig line without ID"; return false; }
+                if (!h.contig_idx.count(id)) {
+                    if (idx < 0) idx = (int)h.contig_names.size();
+                    if ((size_t)idx >= h.contig_names.size()) { h.contig_names.resize(idx + 1); h.contig_lens.resize(idx + 1, 0); }
+                    h.contig_names[idx] = id;
+                    h.contig_lens[idx] = length;
+                    h.contig_idx[id] = idx;
+                }
+                idx_of_line = h.contig_idx[id];
+            } else if (kind == "FILTER" || kind == "INFO" || kind == "FORMAT") {
+                if (id.empty()) { err = "##" + kind + " line without ID"; return false; }
+                auto it = h.dict_idx.find(id);
+                int at;
+                if (it != h.dict_idx.end()) {
+                    at = it->second;
+                } else {
+                    at = idx >= 0 ? idx : (int)h.dict.size();
+                    if ((size_t)at >= h.dict.size()) h.dict.resize(at + 1);
+                    h.dict[at].id = id;
+                    h.dict_idx[id] = at;
+                }
+                DictEntry &e = h.dict[at];
+                if (kind == "FILTER") e.is_filter = true;
+                else if (kind == "INFO") { if (e.info_type < 0) e.info_type = type_code(type); }  // (a repeated line is ignored)
+                else if (e.fmt_type < 0) e.fmt_type = type_code(type);
+                idx_of_line = at;
+            }
+        }
+        h.lines.push_back(strip_idx(raw));
+        h.line_idx.push_back(idx_of_line);
+    }
+    return true;
+}
+
+// the header as text: VCF (no IDX) or BCF (IDX on every dictionary line, as htslib writes it)
+std::string header_text(const Header &h, bool with_idx) {
+    std::string s;
+    for (size_t i = 0; i < h.lines.size(); ++i) {
+        const std::string &l = h.lines[i];
+        if (with_idx && h.line_idx[i] >= 0 && !l.empty() && l.back() == '>') {
+            s.append(l, 0, l.size() - 1);
+            s += ",IDX=" + std::to_string(h.line_idx[i]) + ">";
+        } else {
+            s += l;
+        }
+        s += '\n';
+    }
+    s += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO";
+    if (!h.samples.empty()) {
+        s += "\tFORMAT";
+        for (auto &x : h.samples) { s += '\t'; s += x; }
+    }
+    s += '\n';
+    return s;
+}
+
+std::vector<std::string> split_lines(const char *text) {
+    std::vector<std::string> out;
+    if (!text) return out;
+    const char *p = text;
+    while (*p) {
+        const char *e = strchr(p, '\n');
+        const size_t n = e ? (size_t)(e - p) : strlen(p);
+        if (n) out.emplace_back(p, n);
+        p += n + (e ? 1 : 0);
+    }
+    return out;
+}
+
+// ---- typed values -------------------------------------------------------------------------------------
+inline void put32(std::string &s, uint32_t v) { s.append(reinterpret_cast<const char *>(&v), 4); }
+inline void enc_int(std::string &s, int32_t x);
+inline void enc_size(std::string &s, int size, int type) {
+    if (size < 15) {
+        s.push_back((char)(size << 4 | type));
+    } else {
+        s.push_back((char)(15 << 4 | type));
+        enc_int(s, size);
+    }
+}
+inline void enc_int(std::string &s, int32_t x) {  // one typed integer in the smallest type that holds it
+    if (x <= 127 && x >= -120) {
+        enc_size(s, 1, BT_INT8);
+        s.push_back((char)(int8_t)x);
+    } else if (x <= 32767 && x >= -32760) {
+        enc_size(s, 1, BT_INT16);
+        const int16_t v = (int16_t)x;
+        s.append(reinterpret_cast<const char *>(&v), 2);
+    } else {
+        enc_size(s, 1, BT_INT32);
+        put32(s, (uint32_t)x);
+    }
+}
+inline void enc_str(std::string &s, const char *p, size_t n) {
+    enc_size(s, (int)n, BT_CHAR);
+    s.append(p, n);
+}
+inline void enc_float(std::string &s, float v) {
+    enc_size(s, 1, BT_FLOAT);
+    s.append(reinterpret_cast<const char *>(&v), 4);
+}
+
+inline int bt_size(int type) { return type == BT_INT8 || type == BT_CHAR ? 1 : type == BT_INT16 ? 2 : (type == BT_INT32 || type == BT_FLOAT) ? 4 : 0; }
+inline int32_t read_int(const uint8_t *p, int type, bool *missing = nullptr) {
+    if (type == BT_INT8) { const int8_t v = (int8_t)*p; if (missing) *missing = v == INT8_MIN; return v; }
+    if (type == BT_INT16) { int16_t v; memcpy(&v, p, 2); if (missing) *missing = v == INT16_MIN; return v; }
+    int32_t v; memcpy(&v, p, 4); if (missing) *missing = v == INT32_MIN; return v;
+}
+// descriptor byte (+ overflow length) -> type, element count; returns the first byte after it
+inline const uint8_t *read_desc(const uint8_t *p, int &type, int &len) {
+    const uint8_t b = *p++;
+    type = b & 0xf;
+    len = b >> 4;
+    if (len == 15) {
+        const uint8_t b2 = *p++;
+        const int t2 = b2 & 0xf;
+        len = read_int(p, t2);
+        p += bt_size(t2);
+    }
+    return p;
+}
+inline const uint8_t *skip_typed(const uint8_t *p) {
+    int t, l;
+    p = read_desc(p, t, l);
+    return p + (size_t)l * bt_size(t);
+}
+inline const uint8_t *read_typed_int(const uint8_t *p, int32_t &v) {
+    int t, l;
+    p = read_desc(p, t, l);
+    v = l ? read_int(p, t) : 0;
+    return p + (size_t)l * bt_size(t);
+}
+
+void put_float_text(std::string &s, float v) {
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    if (bits == kFloatMissing) { s += '.'; return; }
+    char buf[32];
+    const int n = snprintf(buf, sizeof buf, "%g", (double)v);
+    s.append(buf, (size_t)n);
+}
+void put_int_text(std::string &s, long long v) {
+    char buf[24];
+    const int n = snprintf(buf, sizeof buf, "%lld", v);
+    s.append(buf, (size_t)n);
+}
+
+const char *const kFilterNames[6] = {"PASS", "PILE", "LOWCOV", "NO_REF", "FEW_REF", "UNRELIABLE"};
+
+// ---- index (CSI for BCF, TBI for bgzipped VCF) ------------------------------------------------------------
+inline int reg2bin(int64_t beg, int64_t end, int min_shift, int depth) {
+    int l, s = min_shift, t = ((1 << depth * 3) - 1) / 7;
+    for (--end, l = depth; l > 0; --l, s += 3, t -= 1 << l * 3)
+        if (beg >> s == end >> s) return t + (int)(beg >> s);
+    return 0;
+}
+inline int bin_first(int l) { return ((1 << 3 * l) - 1) / 7; }
+inline int bin_bot(int bin, int depth) {  // first window (at min_shift granularity) a bin covers
+    int l = 0;
+    for (int b = bin; b; ++l, b = (b - 1) >> 3) {}
+    return (bin - bin_first(l)) << (depth - l) * 3;
+}
+
+struct IndexRef {
+    std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+    std::vector<uint64_t> lidx;
+    uint64_t off_beg = ~0ull, off_end = 0, n = 0;
+};
+
+struct IndexBuilder {
+    int min_shift = 14, depth = 5;
+    std::vector<IndexRef> refs;
+    void add(uint32_t ref, int64_t beg, int64_t end, uint64_t vbeg, uint64_t vend) {
+        if (ref >= refs.size()) refs.resize(ref + 1);
+        IndexRef &r = refs[ref];
+        if (end <= beg) end = beg + 1;
+        const int64_t max_pos = (int64_t)1 << (min_shift + 3 * depth);
+        if (end > max_pos) end = max_pos;
+        if (beg >= max_pos) beg = max_pos - 1;
+        auto &chunks = r.bins[(uint32_t)reg2bin(beg, end, min_shift, depth)];
+        if (!chunks.empty() && chunks.back().second == vbeg) chunks.back().second = vend;  // consecutive records of a bin
+        else chunks.emplace_back(vbeg, vend);
+        const size_t w0 = (size_t)(beg >> min_shift), w1 = (size_t)((end - 1) >> min_shift);
+        if (r.lidx.size() <= w1) r.lidx.resize(w1 + 1, ~0ull);
+        for (size_t w = w0; w <= w1; ++w)
+            if (r.lidx[w] == ~0ull) r.lidx[w] = vbeg;
+        r.off_beg = std::min(r.off_beg, vbeg);
+        r.off_end = std::max(r.off_end, vend);
+        r.n += 1;
+    }
+    void finish() {  // windows nothing starts in inherit the next offset
+        for (IndexRef &r : refs)
+            for (size_t i = r.lidx.size(); i-- > 1;)
+                if (r.lidx[i - 1] == ~0ull) r.lidx[i - 1] = r.lidx[i];
+    }
+    uint32_t meta_bin() const { return (uint32_t)(((1 << (3 * depth + 3)) - 1) / 7 + 1); }
+};
+
+template <typename T>
+inline void putv(std::string &s, T v) { s.append(reinterpret_cast<const char *>(&v), sizeof(T)); }
+
+bool write_bgzf_file(const std::string &path, const std::string &body) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = true;
+    for (size_t off = 0; off < body.size() && ok; off += kBlock) {
+        const std::string b = bgzf_block(reinterpret_cast<const uint8_t *>(body.data()) + off, std::min(kBlock, body.size() - off), 6);
+        ok = fwrite(b.data(), 1, b.size(), f) == b.size();
+    }
+    const std::string eof = bgzf_block(nullptr, 0, 6);
+    ok = ok && fwrite(eof.data(), 1, eof.size(), f) == eof.size();
+    return fclose(f) == 0 && ok;
+}
+
+void put_bins(std::string &s, const IndexBuilder &ib, const IndexRef &r, bool csi) {
+    const int32_t n_bin = r.n ? (int32_t)r.bins.size() + 1 : 0;
+    putv<int32_t>(s, n_bin);
+    for (auto &kv : r.bins) {
+        putv<uint32_t>(s, kv.first);
+        if (csi) {
+            const size_t w = (size_t)bin_bot((int)kv.first, ib.depth);
+            putv<uint64_t>(s, w < r.lidx.size() ? r.lidx[w] : 0);
+        }
+        putv<int32_t>(s, (int32_t)kv.second.size());
+        for (auto &c : kv.second) { putv<uint64_t>(s, c.first); putv<uint64_t>(s, c.second); }
+    }
+    if (r.n) {  // the pseudo-bin: file span and record counts of the reference
+        putv<uint32_t>(s, ib.meta_bin());
+        if (csi) putv<uint64_t>(s, 0);
+        putv<int32_t>(s, 2);
+        putv<uint64_t>(s, r.off_beg); putv<uint64_t>(s, r.off_end);
+        putv<uint64_t>(s, r.n); putv<uint64_t>(s, 0);
+    }
+}
+
+bool write_csi(const std::string &path, IndexBuilder &ib, uint32_t n_ref) {
+    ib.finish();
+    std::string s("CSI\1", 4);
+    putv<int32_t>(s, ib.min_shift);
+    putv<int32_t>(s, ib.depth);
+    putv<int32_t>(s, 0);  // l_aux
+    putv<int32_t>(s, (int32_t)n_ref);
+    const IndexRef empty;
+    for (uint32_t i = 0; i < n_ref; ++i) put_bins(s, ib, i < ib.refs.size() ? ib.refs[i] : empty, true);
+    putv<uint64_t>(s, 0);  // records without coordinates
+    return write_bgzf_file(path, s);
+}
+
+bool write_tbi(const std::string &path, IndexBuilder &ib, const std::vector<std::string> &names) {
+    ib.finish();
+    std::string s("TBI\1", 4);
+    putv<int32_t>(s, (int32_t)names.size());
+    putv<int32_t>(s, 2);    // format: VCF
+    putv<int32_t>(s, 1);    // column of the sequence name
+    putv<int32_t>(s, 2);    // column of the start
+    putv<int32_t>(s, 0);    // column of the end (VCF: from the record)
+    putv<int32_t>(s, '#');  // comment character
+    putv<int32_t>(s, 0);    // lines to skip
+    std::string nm;
+    for (auto &x : names) { nm += x; nm.push_back('\0'); }
+    putv<int32_t>(s, (int32_t)nm.size());
+    s += nm;
+    const IndexRef empty;
+    for (size_t i = 0; i < names.size(); ++i) {
+        const IndexRef &r = i < ib.refs.size() ? ib.refs[i] : empty;
+        put_bins(s, ib, r, false);
+        putv<int32_t>(s, (int32_t)r.lidx.size());
+        for (uint64_t v : r.lidx) putv<uint64_t>(s, v == ~0ull ? 0 : v);
+    }
+    putv<uint64_t>(s, 0);
+    return write_bgzf_file(path, s);
+}
+
+}  // namespace
+
+// ======================================================================================================
+// writer
+// ======================================================================================================
+extern "C" int cnvb_vfile_write(const cnvb_vfile_write_args *a, char *err, uint64_t err_len) {
+    if (!a || !a->path || !a->header_text) return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: null argument");
+    const uint64_t n_rows = a->n_rows;
+    if (n_rows && (!a->rid || !a->pos || !a->end))
+        return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: rid, pos and end columns are required");
+    if (a->n_samples && !a->samples) return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: sample names missing");
+    if ((a->ref_off == nullptr) != (a->ref_idx == nullptr) && n_rows && a->ref_off && a->ref_off[n_rows])
+        return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: REF_TARGETS needs both ref_off and ref_idx");
+    const std::string path = a->path;
+    // lib-coverage/src/lib.rs:174-175 (the same two lines in every writer of the reference)
+    const bool is_vcf = ends_with(path, ".vcf") || ends_with(path, ".vcf.gz");
+    const bool compressed = ends_with(path, ".bcf") || ends_with(path, ".vcf.gz");
+
+    // ---- header
+    Header h;
+    {
+        std::vector<std::string> lines = split_lines(a->header_text);
+        if (lines.empty() || lines[0].compare(0, 13, "##fileformat=") != 0) lines.insert(lines.begin(), "##fileformat=VCFv4.2");
+        bool has_pass = false;
+        for (auto &l : lines) has_pass = has_pass || l.compare(0, 17, "##FILTER=<ID=PASS") == 0;
+        if (!has_pass) lines.insert(lines.begin() + 1, "##FILTER=<ID=PASS,Description=\"All filters passed\">");
+        std::string e;
+        if (!header_build(h, lines, e)) return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: " + e);
+        for (uint32_t i = 0; i < a->n_samples; ++i) h.samples.emplace_back(a->samples[i]);
+    }
+    const uint32_t S = a->n_samples;
+    struct Keys { int end, gap, gc, mean_mapq, few_gc, ref_mean, ref_sd, num_calls, ref_targets, gt, ft, filt[6]; } k;
+    auto need = [&](const char *id, bool wanted, bool info, int &slot) -> bool {
+        slot = -1;
+        if (!wanted) return true;
+        slot = h.find(id);
+        const bool ok = slot >= 0 && (info ? h.dict[slot].info_type >= 0 : h.dict[slot].fmt_type >= 0);
+        if (!ok) vfail(err, err_len, CNVB_ERR_INVALID, std::string(info ? "INFO/" : "FORMAT/") + id + " is not defined in the header");
+        return ok;
+    };
+    if (!need("END", true, true, k.end) || !need("GAP", a->gc && a->gap, true, k.gap) || !need("GC", a->gc, true, k.gc) ||
+        !need("MEAN_MAPQ", a->mean_mapq, true, k.mean_mapq) || !need("FEW_GCWINDOWS", a->few_gc, true, k.few_gc) ||
+        !need("REF_MEAN", a->ref_mean, true, k.ref_mean) || !need("REF_STD_DEV", a->ref_sd, true, k.ref_sd) ||
+        !need("NUM_CALLS", a->num_calls, true, k.num_calls) || !need("REF_TARGETS", a->ref_off, true, k.ref_targets) ||
+        !need("GT", S > 0, false, k.gt) || !need("FT", S > 0 && a->ft, false, k.ft))
+        return CNVB_ERR_INVALID;
+    std::vector<int> fmt_key(a->n_fmt, -1);
+    for (uint32_t i = 0; i < a->n_fmt && S; ++i) {
+        if (!a->fmt[i].key || !a->fmt[i].values) return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: FORMAT column without key or values");
+        if (!need(a->fmt[i].key, true, false, fmt_key[i])) return CNVB_ERR_INVALID;
+    }
+    for (int i = 0; i < 6; ++i) {
+        k.filt[i] = h.find(kFilterNames[i]);
+        if (k.filt[i] >= 0 && !h.dict[k.filt[i]].is_filter) k.filt[i] = -1;
+    }
+    if ((a->ref_mean == nullptr) != (a->ref_sd == nullptr))
+        return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_write: REF_MEAN and REF_STD_DEV come together");
+
+    Sink sink;
+    sink.f = fopen(path.c_str(), "wb");
+    if (!sink.f) return vfail(err, err_len, CNVB_ERR_INVALID, "Could not open " + path + " for writing");
+    sink.bgzf = compressed;
+    sink.n_threads = hw_threads(a->n_threads);
+    bool ok;
+    {
+        std::string head;
+        if (is_vcf) {
+            head = header_text(h, false);
+        } else {
+            const std::string text = header_text(h, true);
+            head.assign("BCF\2\2", 5);
+            put32(head, (uint32_t)text.size() + 1);
+            head += text;
+            head.push_back('\0');
+        }
+        ok = sink.put(head.data(), head.size(), n_rows == 0);
+    }
+    const bool want_index = a->write_index && compressed;
+    std::vector<uint64_t> rec_uoff(want_index ? n_rows + 1 : 0);
+
+    const char *alt = a->is_targets ? "<TARGET>" : "<WINDOW>";
+    const size_t alt_len = strlen(alt);
+    std::atomic<int> bad{0};  // 1 contig index, 2 filter not in header, 3 REF_TARGETS row out of range
+    auto id_of = [&](std::string &s, uint64_t r) {  // chrom:pos+1-end (lib.rs:586-588)
+        s += h.contig_names[(size_t)a->rid[r]];
+        s += ':';
+        put_int_text(s, (long long)a->pos[r] + 1);
+        s += '-';
+        put_int_text(s, a->end[r]);
+    };
+    auto row_ok = [&](uint64_t r) {
+        if (a->rid[r] < 0 || (size_t)a->rid[r] >= h.contig_names.size() || h.contig_names[(size_t)a->rid[r]].empty()) { bad = 1; return false; }
+        if (a->filters)
+            for (int b = 0; b < 6; ++b)
+                if ((a->filters[r] >> b & 1) && k.filt[b] < 0) { bad = 2; return false; }
+        if (a->ref_off)
+            for (uint64_t j = a->ref_off[r]; j < a->ref_off[r + 1]; ++j)
+                if (a->ref_idx[j] >= n_rows || a->rid[a->ref_idx[j]] < 0 || (size_t)a->rid[a->ref_idx[j]] >= h.contig_names.size()) { bad = 3; return false; }
+        return true;
+    };
+    auto fmt_present = [&](uint32_t i, uint64_t r) { return !a->fmt[i].present || a->fmt[i].present[r]; };
+    auto ft_present = [&](uint64_t r) {
+        if (!a->ft || !S) return false;
+        for (uint32_t s = 0; s < S; ++s)
+            if (a->ft[r * S + s]) return true;
+        return false;
+    };
+    auto ft_text = [](std::string &s, uint8_t ft) {  // joined with ';' (lib.rs:659-664)
+        if (ft & CNVB_FT_LOWCOV) s += "LOWCOV";
+        if ((ft & CNVB_FT_LOWCOV) && (ft & CNVB_FT_PILE)) s += ';';
+        if (ft & CNVB_FT_PILE) s += "PILE";
+    };
+    auto has_ref_stats = [&](uint64_t r) { return a->ref_mean && (!a->ref_present || a->ref_present[r]); };
+    auto has_ref_targets = [&](uint64_t r) { return a->ref_off && a->ref_off[r + 1] > a->ref_off[r]; };
+
+    auto bcf_row = [&](std::string &s, uint64_t r) {
+        const size_t start = s.size();
+        s.append(8, '\0');
+        put32(s, (uint32_t)a->rid[r]);
+        put32(s, (uint32_t)a->pos[r]);
+        put32(s, (uint32_t)(a->end[r] - a->pos[r]));
+        put32(s, kFloatMissing);
+        const uint32_t n_info = 1u + (a->gc ? 1u + ((a->gap && a->gap[r]) ? 1u : 0u) : 0u) + (a->mean_mapq ? 1u : 0u) +
+                                ((a->few_gc && a->few_gc[r]) ? 1u : 0u) + (has_ref_stats(r) ? 2u : 0u) + (a->num_calls ? 1u : 0u) +
+                                (has_ref_targets(r) ? 1u : 0u);
+        uint32_t n_fmt = 0;
+        const bool ftp = ft_present(r);
+        if (S) {
+            n_fmt = 1u + (ftp ? 1u : 0u);
+            for (uint32_t i = 0; i < a->n_fmt; ++i) n_fmt += fmt_present(i, r) ? 1u : 0u;
+        }
+        put32(s, 2u << 16 | n_info);
+        put32(s, n_fmt << 24 | S);
+        {
+            std::string id;
+            id_of(id, r);
+            enc_str(s, id.data(), id.size());
+        }
+        enc_str(s, "N", 1);
+        enc_str(s, alt, alt_len);
+        {  // FILTER
+            int ids[6], n = 0;
+            if (a->filters)
+                for (int b = 0; b < 6; ++b)
+                    if (a->filters[r] >> b & 1) ids[n++] = k.filt[b];
+            if (!n) {
+                enc_size(s, 0, BT_NULL);
+            } else {
+                int mx = 0;
+                for (int i = 0; i < n; ++i) mx = std::max(mx, ids[i]);
+                if (mx <= 127) { enc_size(s, n, BT_INT8); for (int i = 0; i < n; ++i) s.push_back((char)ids[i]); }
+                else if (mx <= 32767) { enc_size(s, n, BT_INT16); for (int i = 0; i < n; ++i) putv<int16_t>(s, (int16_t)ids[i]); }
+                else { enc_size(s, n, BT_INT32); for (int i = 0; i < n; ++i) putv<int32_t>(s, ids[i]); }
+            }
+        }
+        enc_int(s, k.end); enc_int(s, a->end[r]);
+        if (a->gc) {  // lib.rs:597-606: GAP flag, then GC
+            if (a->gap && a->gap[r]) { enc_int(s, k.gap); enc_size(s, 0, BT_NULL); }
+            enc_int(s, k.gc); enc_float(s, a->gc[r]);
+        }
+        if (a->mean_mapq) { enc_int(s, k.mean_mapq); enc_float(s, a->mean_mapq[r]); }
+        if (a->few_gc && a->few_gc[r]) { enc_int(s, k.few_gc); enc_size(s, 0, BT_NULL); }
+        if (has_ref_stats(r)) {
+            enc_int(s, k.ref_mean); enc_float(s, a->ref_mean[r]);
+            enc_int(s, k.ref_sd); enc_float(s, a->ref_sd[r]);
+        }
+        if (a->num_calls) { enc_int(s, k.num_calls); enc_int(s, a->num_calls[r]); }
+        if (has_ref_targets(r)) {  // Number=., Type=String: one comma-joined character vector
+            std::string v;
+            for (uint64_t j = a->ref_off[r]; j < a->ref_off[r + 1]; ++j) {
+                if (j > a->ref_off[r]) v += ',';
+                id_of(v, a->ref_idx[j]);
+            }
+            enc_int(s, k.ref_targets);
+            enc_str(s, v.data(), v.size());
+        }
+        const uint32_t l_shared = (uint32_t)(s.size() - start - 8);
+        if (S) {
+            enc_int(s, k.gt);  // push_format_integer(b"GT", &[GT_MISSING]): one int8 0 per sample (lib.rs:613-615)
+            enc_size(s, 1, BT_INT8);
+            s.append(S, '\0');
+            for (uint32_t i = 0; i <= a->n_fmt; ++i) {
+                if (ftp && i == std::min(a->ft_pos, a->n_fmt)) {
+                    size_t w = 0;
+                    std::vector<std::string> vals(S);
+                    for (uint32_t q = 0; q < S; ++q) { ft_text(vals[q], a->ft[r * S + q]); w = std::max(w, vals[q].size()); }
+                    enc_int(s, k.ft);
+                    enc_size(s, (int)w, BT_CHAR);
+                    for (uint32_t q = 0; q < S; ++q) { s += vals[q]; s.append(w - vals[q].size(), '\0'); }
+                }
+                if (i < a->n_fmt && fmt_present(i, r)) {
+                    enc_int(s, fmt_key[i]);
+                    enc_size(s, 1, BT_FLOAT);
+                    s.append(reinterpret_cast<const char *>(a->fmt[i].values + r * S), 4 * (size_t)S);
+                }
+            }
+        }
+        const uint32_t l_indiv = (uint32_t)(s.size() - start - 8 - l_shared);
+        memcpy(&s[start], &l_shared, 4);
+        memcpy(&s[start + 4], &l_indiv, 4);
+    };
+
+    auto vcf_row = [&](std::string &s, uint64_t r) {
+        const std::string &chrom = h.contig_names[(size_t)a->rid[r]];
+        s += chrom;
+        s += '\t';
+        put_int_text(s, (long long)a->pos[r] + 1);
+        s += '\t';
+        id_of(s, r);
+        s += "\tN\t";
+        s += alt;
+        s += "\t.\t";
+        {
+            bool any = false;
+            if (a->filters)
+                for (int b = 0; b < 6; ++b)
+                    if (a->filters[r] >> b & 1) { if (any) s += ';'; s += kFilterNames[b]; any = true; }
+            if (!any) s += '.';
+        }
+        s += "\tEND=";
+        put_int_text(s, a->end[r]);
+        if (a->gc) {
+            if (a->gap && a->gap[r]) s += ";GAP";
+            s += ";GC=";
+            put_float_text(s, a->gc[r]);
+        }
+        if (a->mean_mapq) { s += ";MEAN_MAPQ="; put_float_text(s, a->mean_mapq[r]); }
+        if (a->few_gc && a->few_gc[r]) s += ";FEW_GCWINDOWS";
+        if (has_ref_stats(r)) {
+            s += ";REF_MEAN="; put_float_text(s, a->ref_mean[r]);
+            s += ";REF_STD_DEV="; put_float_text(s, a->ref_sd[r]);
+        }
+        if (a->num_calls) { s += ";NUM_CALLS="; put_int_text(s, a->num_calls[r]); }
+        if (has_ref_targets(r)) {
+            s += ";REF_TARGETS=";
+            for (uint64_t j = a->ref_off[r]; j < a->ref_off[r + 1]; ++j) {
+                if (j > a->ref_off[r]) s += ',';
+                id_of(s, a->ref_idx[j]);
+            }
+        }
+        if (S) {
+            const bool ftp = ft_present(r);
+            s += "\tGT";
+            for (uint32_t i = 0; i <= a->n_fmt; ++i) {
+                if (ftp && i == std::min(a->ft_pos, a->n_fmt)) s += ":FT";
+                if (i < a->n_fmt && fmt_present(i, r)) { s += ':'; s += a->fmt[i].key; }
+            }
+            for (uint32_t q = 0; q < S; ++q) {
+                s += "\t.";
+                for (uint32_t i = 0; i <= a->n_fmt; ++i) {
+                    if (ftp && i == std::min(a->ft_pos, a->n_fmt)) {
+                        s += ':';
+                        if (a->ft[r * S + q]) ft_text(s, a->ft[r * S + q]); else s += '.';
+                    }
+                    if (i < a->n_fmt && fmt_present(i, r)) { s += ':'; put_float_text(s, a->fmt[i].values[r * S + q]); }
+                }
+            }
+        }
+        s += '\n';
+    };
+
+    // ---- records, in batches (bounded memory), formatted on threads
+    constexpr uint64_t kBatch = 1u << 19;
+    const int nt = sink.n_threads;
+    for (uint64_t b0 = 0; ok && b0 < n_rows && !bad; b0 += kBatch) {
+        const uint64_t nb = std::min<uint64_t>(kBatch, n_rows - b0);
+        std::vector<std::string> parts((size_t)nt);
+        std::vector<std::vector<uint32_t>> lens((size_t)nt);
+        const uint64_t per = (nb + nt - 1) / nt;
+        parallel_for(nt, (uint64_t)nt, [&](uint64_t ta, uint64_t tb, int) {
+            for (uint64_t t = ta; t < tb; ++t) {
+                const uint64_t lo = std::min<uint64_t>(nb, per * t), hi = std::min<uint64_t>(nb, lo + per);
+                std::string &s = parts[(size_t)t];
+                s.reserve((hi - lo) * (96 + 12 * (size_t)S));
+                if (want_index) lens[(size_t)t].reserve(hi - lo);
+                for (uint64_t r = b0 + lo; r < b0 + hi && !bad; ++r) {
+                    if (!row_ok(r)) return;
+                    const size_t before = s.size();
+                    if (is_vcf) vcf_row(s, r); else bcf_row(s, r);
+                    if (want_index) lens[(size_t)t].push_back((uint32_t)(s.size() - before));
+                }
+            }
+        });
+        if (bad) break;
+        std::string batch;
+        size_t tot = 0;
+        for (auto &p : parts) tot += p.size();
+        batch.reserve(tot);
+        uint64_t u = sink.utotal, r = b0;
+        for (size_t t = 0; t < parts.size(); ++t) {
+            batch += parts[t];
+            if (want_index)
+                for (uint32_t l : lens[t]) { rec_uoff[r++] = u; u += l; }
+        }
+        ok = sink.put(batch.data(), batch.size(), b0 + nb == n_rows);
+    }
+    if (want_index && n_rows) rec_uoff[n_rows] = sink.utotal;
+    if (fclose(sink.f) != 0) ok = false;
+    if (bad == 1) return vfail(err, err_len, CNVB_ERR_INVALID, "a row names a contig index the header does not define");
+    if (bad == 2) return vfail(err, err_len, CNVB_ERR_INVALID, "a row carries a FILTER the header does not define");
+    if (bad == 3) return vfail(err, err_len, CNVB_ERR_INVALID, "REF_TARGETS names a row beyond the table");
+    if (!ok) return vfail(err, err_len, CNVB_ERR_INVALID, "Could not write " + path);
+
+    // ---- build_index (lib-shared/src/bcf_utils.rs:47-82)
+    if (want_index) {
+        IndexBuilder ib;
+        ib.min_shift = 14;
+        if (is_vcf) {
+            ib.depth = 5;
+        } else {  // bcf_index_build: as many levels as the longest contig needs
+            int64_t max_len = 0;
+            for (uint32_t l : h.contig_lens) max_len = std::max<int64_t>(max_len, l);
+            if (!max_len) max_len = ((int64_t)1 << 31) - 1;
+            max_len += 256;
+            int64_t s = (int64_t)1 << ib.min_shift;
+            for (ib.depth = 0; max_len > s; ++ib.depth, s <<= 3) {}
+        }
+        std::vector<std::string> names;        // TBI: sequence names in order of appearance
+        std::vector<int> tbx_id(h.contig_names.size(), -1);
+        for (uint64_t r = 0; r < n_rows; ++r) {
+            uint32_t ref = (uint32_t)a->rid[r];
+            if (is_vcf) {
+                if (tbx_id[ref] < 0) { tbx_id[ref] = (int)names.size(); names.push_back(h.contig_names[ref]); }
+                ref = (uint32_t)tbx_id[ref];
+            }
+            ib.add(ref, a->pos[r], a->end[r], sink.voffset(rec_uoff[r]), sink.voffset(rec_uoff[r + 1]));
+        }
+        const bool iok = is_vcf ? write_tbi(path + ".tbi", ib, names) : write_csi(path + ".csi", ib, (uint32_t)h.contig_names.size());
+        if (!iok) return vfail(err, err_len, CNVB_ERR_INVALID, is_vcf ? "Could not create .tbi index" : "Could not create .csi index");
+    }
+    return CNVB_OK;
+}
+
+// ======================================================================================================
+// reader
+// ======================================================================================================
+struct cnvb_vfile {
+    Header h;
+    std::string data;       // the whole file, uncompressed
+    std::string head_text;  // the ## lines without IDX
+    bool bcf = false;
+    int n_threads = 1;
+    std::vector<uint64_t> rec_off;  // n + 1: records (BCF) or lines (VCF)
+    std::string err;
+    // per record, from the pass at open time
+    std::vector<int32_t> rid, pos, end;
+    std::vector<uint8_t> alt, filters;
+    std::vector<uint32_t> id_off, id_len;       // the ID inside `data`, relative to the record start
+    std::vector<uint32_t> info_off, fmt_off;    // start of the INFO section / FORMAT section, relative
+    bool canonical = true;
+    std::mutex mu;
+    std::unordered_map<std::string_view, uint32_t> id_map;
+    bool id_map_ready = false;
+
+    uint64_t n() const { return rec_off.empty() ? 0 : rec_off.size() - 1; }
+    const uint8_t *rec(uint64_t r) const { return reinterpret_cast<const uint8_t *>(data.data()) + rec_off[r]; }
+    std::string_view id(uint64_t r) const { return std::string_view(data.data() + rec_off[r] + id_off[r], id_len[r]); }
+    const std::unordered_map<std::string_view, uint32_t> &ids() {
+        std::lock_guard<std::mutex> g(mu);
+        if (!id_map_ready) {
+            id_map.reserve(n() * 2);
+            for (uint64_t r = 0; r < n(); ++r) id_map.emplace(id(r), (uint32_t)r);  // (first record of a name wins)
+            id_map_ready = true;
+        }
+        return id_map;
+    }
+};
+
+namespace {
+
+struct Field {  // one INFO / FORMAT value as found in a record
+    bool found = false;
+    // BCF
+    int type = 0, len = 0;
+    const uint8_t *p = nullptr;
+    // VCF
+    const char *v = nullptr;
+    size_t vlen = 0;
+    bool has_value = false;
+};
+
+// VCF: the k-th tab-separated column of a line [b, e)
+inline const char *next_tab(const char *b, const char *e) {
+    const char *t = static_cast<const char *>(memchr(b, '\t', (size_t)(e - b)));
+    return t ? t : e;
+}
+
+// VCF: end of line r without its line break
+inline const char *line_end(const cnvb_vfile *f, uint64_t r) {
+    const char *b = reinterpret_cast<const char *>(f->rec(r));
+    const char *e = reinterpret_cast<const char *>(f->rec(r + 1));
+    while (e > b && (e[-1] == '\n' || e[-1] == '\r')) --e;
+    return e;
+}
+
+Field info_find(const cnvb_vfile *f, uint64_t r, int key, const char *name, size_t name_len) {
+    Field out;
+    const uint8_t *rec = f->rec(r);
+    if (f->bcf) {
+        const uint32_t n_info = rd32(rec + 24) & 0xffff;
+        const uint8_t *p = rec + f->info_off[r];
+        for (uint32_t i = 0; i < n_info; ++i) {
+            int32_t kk;
+            p = read_typed_int(p, kk);
+            int t, l;
+            const uint8_t *q = read_desc(p, t, l);
+            if (kk == key) {
+                out.found = true;
+                out.type = t;
+                out.len = l;
+                out.p = q;
+                return out;
+            }
+            p = q + (size_t)l * bt_size(t);
+        }
+        return out;
+    }
+    const char *b = reinterpret_cast<const char *>(rec) + f->info_off[r];
+    const char *e = next_tab(b, line_end(f, r));
+    while (b < e) {
+        const char *semi = static_cast<const char *>(memchr(b, ';', (size_t)(e - b)));
+        const char *fe = semi ? semi : e;
+        if ((size_t)(fe - b) >= name_len && memcmp(b, name, name_len) == 0 && (b + name_len == fe || b[name_len] == '=')) {
+            out.found = true;
+            out.has_value = b + name_len < fe;
+            out.v = out.has_value ? b + name_len + 1 : fe;
+            out.vlen = (size_t)(fe - out.v);
+            return out;
+        }
+        b = fe + 1;
+    }
+    return out;
+}
+
+inline float parse_float_text(const char *v, size_t n, bool &missing) {
+    missing = n == 0 || (n == 1 && v[0] == '.');
+    if (missing) { float m; memcpy(&m, &kFloatMissing, 4); return m; }
+    char buf[64];
+    const size_t k = std::min(n, sizeof buf - 1);
+    memcpy(buf, v, k);
+    buf[k] = '\0';
+    return strtof(buf, nullptr);
+}
+
+inline float bcf_float(const Field &fd, size_t at = 0) {  // first value of a numeric vector as f32
+    float out;
+    if (fd.type == BT_FLOAT) { memcpy(&out, fd.p + 4 * at, 4); return out; }
+    bool miss = false;
+    const int32_t v = read_int(fd.p + (size_t)bt_size(fd.type) * at, fd.type, &miss);
+    if (miss) { memcpy(&out, &kFloatMissing, 4); return out; }
+    return (float)v;
+}
+
+int vset(cnvb_vfile *f, int code, const std::string &msg) {
+    f->err = msg;
+    return code;
+}
+
+// the pass at open time: fixed columns and section offsets of every record
+bool index_records(cnvb_vfile *f, std::string &err) {
+    const uint64_t n = f->n();
+    f->rid.resize(n); f->pos.resize(n); f->end.resize(n); f->alt.resize(n); f->filters.resize(n);
+    f->id_off.resize(n); f->id_len.resize(n); f->info_off.resize(n); f->fmt_off.resize(n);
+    const int k_end = f->h.find("END");
+    int filt_bit[6];
+    for (int b = 0; b < 6; ++b) filt_bit[b] = f->h.find(kFilterNames[b]);
+    std::atomic<bool> bad{false}, canonical{true};
+    std::mutex mu;
+    auto fail_at = [&](uint64_t r, const char *what) {
+        std::lock_guard<std::mutex> g(mu);
+        if (!bad.exchange(true)) err = std::string(what) + " (record " + std::to_string(r + 1) + ")";
+    };
+    parallel_for(f->n_threads, n, [&](uint64_t a, uint64_t b, int) {
+        std::string canon;
+        for (uint64_t r = a; r < b && !bad; ++r) {
+            const uint8_t *rec = f->rec(r);
+            const uint64_t rec_len = f->rec_off[r + 1] - f->rec_off[r];
+            std::string_view alt_s, ref_s;
+            if (f->bcf) {
+                const uint32_t l_shared = rd32(rec);
+                if (rec_len < 32 || l_shared + 8ull > rec_len) { fail_at(r, "truncated BCF record"); return; }
+                f->rid[r] = (int32_t)rd32(rec + 8);
+                f->pos[r] = (int32_t)rd32(rec + 12);
+                const int32_t rlen = (int32_t)rd32(rec + 16);
+                const uint32_t n_allele = rd32(rec + 24) >> 16;
+                const uint8_t *p = rec + 32;
+                int t, l;
+                p = read_desc(p, t, l);
+                f->id_off[r] = (uint32_t)(p - rec);
+                f->id_len[r] = (uint32_t)l;
+                p += l;
+                for (uint32_t i = 0; i < n_allele; ++i) {
+                    p = read_desc(p, t, l);
+                    if (i == 0) ref_s = std::string_view(reinterpret_cast<const char *>(p), (size_t)l);
+                    if (i == 1) alt_s = std::string_view(reinterpret_cast<const char *>(p), (size_t)l);
+                    p += l;
+                }
+                p = read_desc(p, t, l);
+                uint8_t bits = 0;
+                for (int i = 0; i < l; ++i) {
+                    const int32_t id = read_int(p + (size_t)i * bt_size(t), t);
+                    int b2 = 0;
+                    for (; b2 < 6; ++b2)
+                        if (filt_bit[b2] == id) break;
+                    bits |= b2 < 6 ? (uint8_t)(1u << b2) : (uint8_t)CNVB_VF_OTHER;
+                }
+                f->filters[r] = bits;
+                p += (size_t)l * bt_size(t);
+                f->info_off[r] = (uint32_t)(p - rec);
+                f->fmt_off[r] = 8 + l_shared;
+                f->end[r] = f->pos[r] + rlen;
+                if (f->rid[r] < 0 || (size_t)f->rid[r] >= f->h.contig_names.size()) { fail_at(r, "record names a contig the header does not define"); return; }
+            } else {
+                const char *b0 = reinterpret_cast<const char *>(rec);
+                const char *e = b0 + rec_len;
+                while (e > b0 && (e[-1] == '\n' || e[-1] == '\r')) --e;
+                const char *col[9];
+                const char *p = b0;
+                int nc = 0;
+                for (; nc < 9 && p <= e; ++nc) {
+                    col[nc] = p;
+                    const char *t = next_tab(p, e);
+                    p = t + 1;
+                    if (t == e) { ++nc; break; }
+                }
+                if (nc < 8) { fail_at(r, "VCF line with fewer than 8 columns"); return; }
+                auto len_of = [&](int c) { return (size_t)((c + 1 < nc ? col[c + 1] - 1 : e) - col[c]); };
+                auto it = f->h.contig_idx.find(std::string(col[0], len_of(0)));
+                if (it == f->h.contig_idx.end()) { fail_at(r, "record names a contig the header does not define"); return; }
+                f->rid[r] = it->second;
+                f->pos[r] = (int32_t)strtol(col[1], nullptr, 10) - 1;
+                f->id_off[r] = (uint32_t)(col[2] - b0);
+                f->id_len[r] = (uint32_t)len_of(2);
+                ref_s = std::string_view(col[3], len_of(3));
+                alt_s = std::string_view(col[4], len_of(4));
+                uint8_t bits = 0;
+                {
+                    const char *q = col[6], *qe = col[6] + len_of(6);
+                    if (!(qe - q == 1 && *q == '.'))
+                        while (q < qe) {
+                            const char *semi = static_cast<const char *>(memchr(q, ';', (size_t)(qe - q)));
+                            const char *fe = semi ? semi : qe;
+                            int b2 = 0;
+                            for (; b2 < 6; ++b2)
+                                if (strlen(kFilterNames[b2]) == (size_t)(fe - q) && memcmp(kFilterNames[b2], q, (size_t)(fe - q)) == 0) break;
+                            bits |= b2 < 6 ? (uint8_t)(1u << b2) : (uint8_t)CNVB_VF_OTHER;
+                            q = fe + 1;
+                        }
+                }
+                f->filters[r] = bits;
+                f->info_off[r] = (uint32_t)(col[7] - b0);
+                f->fmt_off[r] = nc > 8 ? (uint32_t)(col[8] - b0) : (uint32_t)(e - b0);
+                f->end[r] = f->pos[r] + (int32_t)ref_s.size();
+            }
+            if (k_end >= 0) {
+                const Field fd = info_find(f, r, k_end, "END", 3);
+                if (fd.found) {
+                    if (f->bcf) { if (fd.len) f->end[r] = read_int(fd.p, fd.type); }
+                    else if (fd.has_value) f->end[r] = (int32_t)strtol(fd.v, nullptr, 10);
+                }
+            }
+            f->alt[r] = alt_s == "<WINDOW>" ? 0 : alt_s == "<TARGET>" ? 1 : 2;
+            canon.clear();
+            canon += f->h.contig_names[(size_t)f->rid[r]];
+            canon += ':';
+            put_int_text(canon, (long long)f->pos[r] + 1);
+            canon += '-';
+            put_int_text(canon, f->end[r]);
+            if (f->id(r) != canon) canonical = false;
+        }
+    });
+    f->canonical = canonical;
+    return !bad;
+}
+
+}  // namespace
+
+extern "C" int cnvb_vfile_open(const char *path, int n_threads, cnvb_vfile **out, char *err, uint64_t err_len) {
+    if (!path || !out) return vfail(err, err_len, CNVB_ERR_INVALID, "cnvb_vfile_open: null argument");
+    *out = nullptr;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return vfail(err, err_len, CNVB_ERR_INVALID, std::string("Could not open BCF file: ") + path);
+    std::string raw;
+    {
+        fseek(fp, 0, SEEK_END);
+        const long sz = ftell(fp);
+        fseek(fp, 0, SEEK_SET);
+        raw.resize(sz > 0 ? (size_t)sz : 0);
+        const size_t got = raw.empty() ? 0 : fread(&raw[0], 1, raw.size(), fp);
+        fclose(fp);
+        if (got != raw.size()) return vfail(err, err_len, CNVB_ERR_INVALID, std::string("Could not read ") + path);
+    }
+    auto *f = new (std::nothrow) cnvb_vfile();
+    if (!f) return vfail(err, err_len, CNVB_ERR_NOMEM, "out of memory");
+    f->n_threads = hw_threads(n_threads);
+    std::string e;
+    if (raw.size() >= 2 && (uint8_t)raw[0] == 0x1f && (uint8_t)raw[1] == 0x8b) {
+        if (!inflate_all(reinterpret_cast<const uint8_t *>(raw.data()), raw.size(), f->n_threads, f->data, e)) {
+            delete f;
+            return vfail(err, err_len, CNVB_ERR_INVALID, std::string(path) + ": " + e);
+        }
+        raw.clear();
+        raw.shrink_to_fit();
+    } else {
+        f->data.swap(raw);
+    }
+    const std::string &d = f->data;
+    std::vector<std::string> lines;
+    uint64_t body = 0;
+    f->bcf = d.size() >= 9 && memcmp(d.data(), "BCF\2\2", 5) == 0;
+    std::string text;
+    if (f->bcf) {
+        const uint32_t l_text = rd32(reinterpret_cast<const uint8_t *>(d.data()) + 5);
+        if (9ull + l_text > d.size()) { delete f; return vfail(err, err_len, CNVB_ERR_INVALID, std::string(path) + ": truncated BCF header"); }
+        text.assign(d.data() + 9, strnlen(d.data() + 9, l_text));
+        body = 9ull + l_text;
+    } else {
+        uint64_t at = 0;
+        while (at < d.size() && d[at] == '#') {
+            const char *nl = static_cast<const char *>(memchr(d.data() + at, '\n', d.size() - at));
+            at = nl ? (uint64_t)(nl - d.data()) + 1 : d.size();
+        }
+        text.assign(d.data(), at);
+        body = at;
+    }
+    for (std::string &l : split_lines(text.c_str())) {
+        while (!l.empty() && l.back() == '\r') l.pop_back();
+        if (l.compare(0, 2, "##") == 0) {
+            lines.push_back(l);
+        } else if (l.compare(0, 6, "#CHROM") == 0) {
+            size_t p = 0;
+            int c = 0;
+            while (p <= l.size()) {
+                size_t t = l.find('\t', p);
+                if (t == std::string::npos) t = l.size();
+                if (c >= 9) f->h.samples.push_back(l.substr(p, t - p));
+                ++c;
+                p = t + 1;
+            }
+        }
+    }
+    if (lines.empty()) { delete f; return vfail(err, err_len, CNVB_ERR_INVALID, std::string(path) + ": neither a VCF nor a BCF file"); }
+    if (!header_build(f->h, lines, e)) { delete f; return vfail(err, err_len, CNVB_ERR_INVALID, std::string(path) + ": " + e); }
+    for (auto &l : f->h.lines) { f->head_text += l; f->head_text += '\n'; }
+    // record boundaries
+    if (f->bcf) {
+        uint64_t at = body;
+        while (at + 8 <= d.size()) {
+            const uint64_t len = 8ull + rd32(reinterpret_cast<const uint8_t *>(d.data()) + at) + rd32(reinterpret_cast<const uint8_t *>(d.data()) + at + 4);
+            if (at + len > d.size()) { delete f; return vfail(err, err_len, CNVB_ERR_INVALID, std::string(path) + ": truncated BCF record"); }
+            f->rec_off.push_back(at);
+            at += len;
+        }
+        f->rec_off.push_back(at);
+    } else {
+        uint64_t at = body;
+        while (at < d.size()) {
+            const char *nl = static_cast<const char *>(memchr(d.data() + at, '\n', d.size() - at));
+            const uint64_t next = nl ? (uint64_t)(nl - d.data()) + 1 : d.size();
+            if (next - at > 1) f->rec_off.push_back(at);  // (skips empty lines)
+            at = next;
+        }
+        // lines are contiguous except for empty ones; the end of record r is taken as the start of r + 1, and
+        // trailing newlines are trimmed where a line is parsed
+        f->rec_off.push_back(d.size());
+    }
+    if (!index_records(f, e)) { delete f; return vfail(err, err_len, CNVB_ERR_INVALID, std::string(path) + ": " + e); }
+    *out = f;
+    return CNVB_OK;
+}
+
+extern "C" void cnvb_vfile_close(cnvb_vfile *f) { delete f; }
+extern "C" const char *cnvb_vfile_last_error(const cnvb_vfile *f) { return f ? f->err.c_str() : "null handle"; }
+extern "C" uint64_t cnvb_vfile_num_records(const cnvb_vfile *f) { return f ? f->n() : 0; }
+extern "C" uint32_t cnvb_vfile_num_samples(const cnvb_vfile *f) { return f ? (uint32_t)f->h.samples.size() : 0; }
+extern "C" const char *cnvb_vfile_sample(const cnvb_vfile *f, uint32_t i) { return f && i < f->h.samples.size() ? f->h.samples[i].c_str() : nullptr; }
+extern "C" uint32_t cnvb_vfile_num_contigs(const cnvb_vfile *f) { return f ? (uint32_t)f->h.contig_names.size() : 0; }
+extern "C" const char *cnvb_vfile_contig_name(const cnvb_vfile *f, uint32_t i) { return f && i < f->h.contig_names.size() ? f->h.contig_names[i].c_str() : nullptr; }
+extern "C" uint32_t cnvb_vfile_contig_length(const cnvb_vfile *f, uint32_t i) { return f && i < f->h.contig_lens.size() ? f->h.contig_lens[i] : 0; }
+extern "C" const char *cnvb_vfile_header_text(const cnvb_vfile *f) { return f ? f->head_text.c_str() : nullptr; }
+extern "C" int cnvb_vfile_is_bcf(const cnvb_vfile *f) { return f && f->bcf ? 1 : 0; }
+
+extern "C" int cnvb_vfile_fixed(cnvb_vfile *f, int32_t *rid, int32_t *pos, int32_t *end, uint8_t *alt, uint8_t *filters, int *canonical_ids) {
+    if (!f) return CNVB_ERR_INVALID;
+    const uint64_t n = f->n();
+    if (rid && n) memcpy(rid, f->rid.data(), n * 4);
+    if (pos && n) memcpy(pos, f->pos.data(), n * 4);
+    if (end && n) memcpy(end, f->end.data(), n * 4);
+    if (alt && n) memcpy(alt, f->alt.data(), n);
+    if (filters && n) memcpy(filters, f->filters.data(), n);
+    if (canonical_ids) *canonical_ids = f->canonical ? 1 : 0;
+    return CNVB_OK;
+}
+
+namespace {
+int info_key(cnvb_vfile *f, const char *key, int &idx) {
+    if (!f || !key) return CNVB_ERR_INVALID;
+    idx = f->h.find(key);
+    if (idx < 0 || f->h.dict[idx].info_type < 0) return vset(f, CNVB_ERR_INVALID, std::string("INFO/") + key + " is not defined in the header");
+    return CNVB_OK;
+}
+int fmt_key(cnvb_vfile *f, const char *key, int &idx) {
+    if (!f || !key) return CNVB_ERR_INVALID;
+    idx = f->h.find(key);
+    if (idx < 0 || f->h.dict[idx].fmt_type < 0) return vset(f, CNVB_ERR_INVALID, std::string("FORMAT/") + key + " is not defined in the header");
+    return CNVB_OK;
+}
+}  // namespace
+
+extern "C" int cnvb_vfile_info_float(cnvb_vfile *f, const char *key, float *out, uint8_t *present) {
+    int idx;
+    CNVB_TRY(info_key(f, key, idx));
+    if (!out) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_info_float: null output");
+    const size_t kl = strlen(key);
+    parallel_for(f->n_threads, f->n(), [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) {
+            const Field fd = info_find(f, r, idx, key, kl);
+            bool has = fd.found;
+            float v;
+            memcpy(&v, &kFloatMissing, 4);
+            if (has) {
+                if (f->bcf) { if (fd.len && fd.type != BT_CHAR && fd.type != BT_NULL) v = bcf_float(fd); }
+                else { bool miss; v = parse_float_text(fd.v, std::min(fd.vlen, (size_t)((const char *)memchr(fd.v, ',', fd.vlen) ? (const char *)memchr(fd.v, ',', fd.vlen) - fd.v : (ptrdiff_t)fd.vlen)), miss); }
+            }
+            out[r] = v;
+            if (present) present[r] = has ? 1 : 0;
+        }
+    });
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_vfile_info_int(cnvb_vfile *f, const char *key, int32_t *out, uint8_t *present) {
+    int idx;
+    CNVB_TRY(info_key(f, key, idx));
+    if (!out) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_info_int: null output");
+    const size_t kl = strlen(key);
+    parallel_for(f->n_threads, f->n(), [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) {
+            const Field fd = info_find(f, r, idx, key, kl);
+            int32_t v = INT32_MIN;
+            if (fd.found) {
+                if (f->bcf) {
+                    if (fd.len && (fd.type == BT_INT8 || fd.type == BT_INT16 || fd.type == BT_INT32)) {
+                        bool miss = false;
+                        v = read_int(fd.p, fd.type, &miss);
+                        if (miss) v = INT32_MIN;
+                    }
+                } else if (fd.has_value && !(fd.vlen == 1 && fd.v[0] == '.')) {
+                    v = (int32_t)strtol(fd.v, nullptr, 10);
+                }
+            }
+            out[r] = v;
+            if (present) present[r] = fd.found ? 1 : 0;
+        }
+    });
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_vfile_info_flag(cnvb_vfile *f, const char *key, uint8_t *out) {
+    int idx;
+    CNVB_TRY(info_key(f, key, idx));
+    if (!out) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_info_flag: null output");
+    const size_t kl = strlen(key);
+    parallel_for(f->n_threads, f->n(), [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) out[r] = info_find(f, r, idx, key, kl).found ? 1 : 0;
+    });
+    return CNVB_OK;
+}
+
+namespace {
+
+// FORMAT key of record r: BCF -> the typed vector; VCF -> position of the key in the FORMAT column (len) and
+// the start of the first sample column (v)
+Field format_find(const cnvb_vfile *f, uint64_t r, int key, const char *name, size_t name_len) {
+    Field out;
+    const uint8_t *rec = f->rec(r);
+    const uint32_t S = (uint32_t)f->h.samples.size();
+    if (f->bcf) {
+        const uint32_t n_fmt = rd32(rec + 28) >> 24;
+        const uint8_t *p = rec + f->fmt_off[r];
+        for (uint32_t i = 0; i < n_fmt; ++i) {
+            int32_t kk;
+            p = read_typed_int(p, kk);
+            int t, l;
+            const uint8_t *q = read_desc(p, t, l);
+            if (kk == key) {
+                out.found = true;
+                out.type = t;
+                out.len = l;
+                out.p = q;
+                return out;
+            }
+            p = q + (size_t)l * bt_size(t) * S;
+        }
+        return out;
+    }
+    const char *b = reinterpret_cast<const char *>(rec) + f->fmt_off[r];
+    const char *lend = line_end(f, r);
+    const char *e = next_tab(b, lend);
+    int k = 0;
+    const char *q = b;
+    while (q < e) {
+        const char *colon = static_cast<const char *>(memchr(q, ':', (size_t)(e - q)));
+        const char *fe = colon ? colon : e;
+        if ((size_t)(fe - q) == name_len && memcmp(q, name, name_len) == 0) {
+            out.found = true;
+            out.len = k;
+            out.v = e < lend ? e + 1 : lend;
+            out.vlen = (size_t)(lend - out.v);
+            return out;
+        }
+        ++k;
+        q = fe + 1;
+    }
+    return out;
+}
+
+// VCF: field `k` of sample column `s` (columns start at v, vlen bytes to the end of the line)
+inline bool sample_field(const Field &fd, uint32_t s, const char *&v, size_t &n) {
+    const char *p = fd.v, *e = fd.v + fd.vlen;
+    for (uint32_t i = 0; i < s && p < e; ++i) p = next_tab(p, e) + 1;
+    if (p > e) return false;
+    const char *ce = next_tab(p, e);
+    for (int i = 0; i < fd.len; ++i) {
+        const char *colon = static_cast<const char *>(memchr(p, ':', (size_t)(ce - p)));
+        if (!colon) return false;
+        p = colon + 1;
+    }
+    const char *colon = static_cast<const char *>(memchr(p, ':', (size_t)(ce - p)));
+    v = p;
+    n = (size_t)((colon ? colon : ce) - p);
+    return true;
+}
+
+}  // namespace
+
+extern "C" int cnvb_vfile_format_float(cnvb_vfile *f, const char *key, float *out, uint8_t *present) {
+    int idx;
+    CNVB_TRY(fmt_key(f, key, idx));
+    if (!out) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_format_float: null output");
+    const size_t kl = strlen(key);
+    const uint32_t S = (uint32_t)f->h.samples.size();
+    parallel_for(f->n_threads, f->n(), [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) {
+            const Field fd = format_find(f, r, idx, key, kl);
+            const bool numeric = !f->bcf || (fd.len && fd.type != BT_CHAR && fd.type != BT_NULL);
+            for (uint32_t s = 0; s < S; ++s) {
+                float v;
+                memcpy(&v, &kFloatMissing, 4);
+                if (fd.found && numeric) {
+                    if (f->bcf) {
+                        v = bcf_float(fd, (size_t)s * fd.len);
+                    } else {
+                        const char *p;
+                        size_t n;
+                        if (sample_field(fd, s, p, n)) {
+                            const char *comma = static_cast<const char *>(memchr(p, ',', n));
+                            bool miss;
+                            v = parse_float_text(p, comma ? (size_t)(comma - p) : n, miss);
+                        }
+                    }
+                }
+                out[r * S + s] = v;
+            }
+            if (present) present[r] = fd.found ? 1 : 0;
+        }
+    });
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_vfile_format_ft(cnvb_vfile *f, uint8_t *out, uint8_t *present) {
+    int idx;
+    CNVB_TRY(fmt_key(f, "FT", idx));
+    if (!out) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_format_ft: null output");
+    const uint32_t S = (uint32_t)f->h.samples.size();
+    auto bits_of = [](const char *p, size_t n) {
+        uint8_t bits = 0;
+        const char *e = p + n;
+        while (p < e && *p) {
+            const char *q = p;
+            while (q < e && *q && *q != ';') ++q;
+            if (q - p == 6 && memcmp(p, "LOWCOV", 6) == 0) bits |= CNVB_FT_LOWCOV;
+            else if (q - p == 4 && memcmp(p, "PILE", 4) == 0) bits |= CNVB_FT_PILE;
+            p = q + 1;
+        }
+        return bits;
+    };
+    parallel_for(f->n_threads, f->n(), [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) {
+            const Field fd = format_find(f, r, idx, "FT", 2);
+            for (uint32_t s = 0; s < S; ++s) {
+                uint8_t bits = 0;
+                if (fd.found) {
+                    if (f->bcf) {
+                        if (fd.type == BT_CHAR) bits = bits_of(reinterpret_cast<const char *>(fd.p) + (size_t)s * fd.len, (size_t)fd.len);
+                    } else {
+                        const char *p;
+                        size_t n;
+                        if (sample_field(fd, s, p, n)) bits = bits_of(p, n);
+                    }
+                }
+                out[r * S + s] = bits;
+            }
+            if (present) present[r] = fd.found ? 1 : 0;
+        }
+    });
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_vfile_match_ids(cnvb_vfile *f, cnvb_vfile *other, uint32_t *row) {
+    if (!f || !other || !row) return CNVB_ERR_INVALID;
+    const auto &m = other->ids();
+    parallel_for(f->n_threads, f->n(), [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) {
+            auto it = m.find(f->id(r));
+            row[r] = it == m.end() ? UINT32_MAX : it->second;
+        }
+    });
+    return CNVB_OK;
+}
+
+extern "C" int cnvb_vfile_ref_targets(cnvb_vfile *f, cnvb_vfile *against, uint64_t *off, uint32_t *idx, uint64_t idx_cap) {
+    int key;
+    CNVB_TRY(info_key(f, "REF_TARGETS", key));
+    if (!off) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_ref_targets: null output");
+    if (!against) against = f;
+    const uint64_t n = f->n();
+    auto value_of = [&](uint64_t r, const char *&v, size_t &len) {
+        const Field fd = info_find(f, r, key, "REF_TARGETS", 11);
+        v = nullptr;
+        len = 0;
+        if (!fd.found) return;
+        if (f->bcf) {
+            if (fd.type != BT_CHAR) return;
+            v = reinterpret_cast<const char *>(fd.p);
+            len = strnlen(v, (size_t)fd.len);
+        } else if (fd.has_value && !(fd.vlen == 1 && fd.v[0] == '.')) {
+            v = fd.v;
+            len = fd.vlen;
+        }
+    };
+    std::vector<uint64_t> cnt(n + 1, 0);
+    parallel_for(f->n_threads, n, [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b; ++r) {
+            const char *v;
+            size_t len;
+            value_of(r, v, len);
+            uint64_t c = 0;
+            if (len) {
+                c = 1;
+                for (size_t i = 0; i < len; ++i) c += v[i] == ',';
+            }
+            cnt[r + 1] = c;
+        }
+    });
+    off[0] = 0;
+    for (uint64_t r = 0; r < n; ++r) off[r + 1] = off[r] + cnt[r + 1];
+    if (!idx) return CNVB_OK;
+    if (idx_cap < off[n]) return vset(f, CNVB_ERR_INVALID, "cnvb_vfile_ref_targets: index buffer too small");
+    const auto &m = against->ids();
+    std::atomic<bool> bad{false};
+    std::mutex mu;
+    parallel_for(f->n_threads, n, [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t r = a; r < b && !bad; ++r) {
+            const char *v;
+            size_t len;
+            value_of(r, v, len);
+            uint64_t at = off[r];
+            const char *p = v, *e = v + len;
+            while (p < e) {
+                const char *comma = static_cast<const char *>(memchr(p, ',', (size_t)(e - p)));
+                const char *fe = comma ? comma : e;
+                auto it = m.find(std::string_view(p, (size_t)(fe - p)));
+                if (it == m.end()) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (!bad.exchange(true)) f->err = "Could not find: " + std::string(p, (size_t)(fe - p));  // lib-mod-cov/src/lib.rs:149
+                    return;
+                }
+                idx[at++] = it->second;
+                p = fe + 1;
+            }
+        }
+    });
+    return bad ? CNVB_ERR_REFERENCE_PANIC : CNVB_OK;
+}

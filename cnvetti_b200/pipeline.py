@@ -401,89 +401,13 @@ def read_fasta(path):
     return out
 
 
-def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(chr)?\d\d?$", targets=None, ctx=None,
-                 threads=0, command_line=None, mask_piles=False, mask_piles_fdr=0.001, pile_max_gap=20):
-    """`cnvetti cmd coverage --input X.bam --output Y.vcf[.gz] [--reference R.fa] [--mask-piles] ...`
-    (lib_coverage::run, lib-coverage/src/lib.rs:679-795): BAM decode on host threads, with --mask-piles the
-    pile collection and its FDR threshold (gather_piles, :353-419), the region loop on the GPU, the coverage
-    VCF written on host threads.  Returns (table, timings) with the host decode / device / write times
-    apart."""
-    import time
-    import torch
-    from . import bam as bam_mod
-    from . import vcf
-    ctx = ctx or default_context()
-    timings = {}
-    t0 = time.perf_counter()
-    with bam_mod.BamReader(input_bam, threads=threads) as reader:
-        samples = reader.sample_names()
-        reader.decode(min_unclipped=options.min_unclipped, pinned=True)
-        timings["bam_decode"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        seqs = read_fasta(reference) if reference else None
-        timings["fasta"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        regions = reader.regions(contig_regex=contig_regex, sequences=seqs, targets=targets)
-        if seqs is not None:
-            missing = [r.name for r in regions if r.sequence is None]
-            if missing:
-                raise N.CnvbError(N.ERR_INVALID, "Could not load reference sequence for %s" % missing[0])
-        if mask_piles:  # (lib.rs:755-764: whatever the count kind; only the genome-wide fragment counter uses them)
-            from . import piles as piles_mod
-            masks, _ = piles_mod.gather_piles(regions, min_mapq=options.min_mapq, pile_max_gap=pile_max_gap,
-                                              mask_piles_fdr=mask_piles_fdr, ctx=ctx)
-            for r, m in zip(regions, masks):
-                r.piles = m
-        table = coverage_run(regions, options, ctx=ctx)
-        torch.cuda.synchronize()
-        timings["device"] = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        contigs = list(zip(reader.references, reader.lengths))
-        vcf.write_coverage_vcf(output, table, ",".join(samples) if samples else "sample", contigs,
-                               is_targets=options.considered_regions == "TargetRegions", command_line=command_line,
-                               threads=threads)
-        timings["write"] = time.perf_counter() - t0
-    return table, timings
+def cmd_coverage(*args, **kwargs):
+    """`cnvetti cmd coverage` at file level: see commands.cmd_coverage."""
+    from .commands import cmd_coverage as f
+    return f(*args, **kwargs)
 
 
-def cmd_normalize(input_vcf, output, normalization="MedianGcBinned", ctx=None, threads=0, command_line=None):
-    """`cnvetti cmd normalize --input X.vcf[.gz] --output Y.vcf[.gz] --normalization ...`
-    (lib_normalize::run, lib-normalize/src/lib.rs:43-66): FORMAT/LCV (LCVSD) and INFO/GC in, the same
-    records plus FORMAT/CV (CV2, CVSD) and INFO/FEW_GCWINDOWS out."""
-    from . import vcf
-    ctx = ctx or default_context()
-    r = vcf.read_coverage_vcf(input_vcf)
-    t = CoverageTable()
-    n = len(r["chrom"])
-    names, offsets = [], [0]
-    for i, c in enumerate(r["chrom"]):
-        if not names or names[-1] != c:
-            if names:
-                offsets.append(i)
-            names.append(c)
-    offsets.append(n)
-    t.names, t.offsets = names, offsets
-    t.start = r["pos"].astype(np.int32)
-    t.end = np.array([int(x) for x in r["info"]["END"]], np.int32)
-    f = r["format"]
-    t.rcv, t.lcv = f["RCV"], f["LCV"]
-    t.rcvsd, t.lcvsd, t.frm = f.get("RCVSD"), f.get("LCVSD"), f.get("FRM")
-    ft = f.get("FT")
-    if ft is not None:
-        t.ft = np.array([(N.FT_LOWCOV if x and "LOWCOV" in x else 0) | (N.FT_PILE if x and "PILE" in x else 0)
-                         for x in ft], np.uint8)
-    if "GC" in r["info"]:
-        miss = np.frombuffer(np.uint32(N.F32_MISSING_BITS).tobytes(), np.float32)[0]
-        t.gc = np.array([miss if (x is None or x == ".") else np.float32(x) for x in r["info"]["GC"]], np.float32)
-        t.gap = np.array([1 if x else 0 for x in r["info"].get("GAP", [None] * n)], np.uint8)
-    normalize_run(t, normalization, ctx=ctx)
-    contigs = []
-    for line in r["header"]:
-        if line.startswith("##contig=<ID="):
-            body = line[len("##contig=<"):-1]
-            kv = dict(x.split("=", 1) for x in body.split(","))
-            contigs.append((kv["ID"], int(kv.get("length", 0))))
-    vcf.write_coverage_vcf(output, t, r["samples"][0] if r["samples"] else "sample", contigs,
-                           is_targets=bool(r["alt"]) and r["alt"][0] == "<TARGET>", command_line=command_line,
-                           threads=threads)
-    return t
+def cmd_normalize(*args, **kwargs):
+    """`cnvetti cmd normalize` at file level: see commands.cmd_normalize."""
+    from .commands import cmd_normalize as f
+    return f(*args, **kwargs)

@@ -307,37 +307,102 @@ int cnvb_norm_gc_median_sharded(cnvb_comm *comm, const float *lcv, const float *
                                 uint64_t n, float *cv, float *cv2, float *cvsd, uint8_t *flags,
                                 float *medians, int mem);
 
-/* ---- coverage VCF writer (text containers) ---------------------------
- * Replaces the htslib record assembly and output of process_region (lib-coverage/src/lib.rs:
- * 560-673) under the header of build_header (:67-166), plus what lib-normalize adds (FORMAT CV /
- * CV2 / CVSD, INFO FEW_GCWINDOWS; uncorrected.rs:51-96, correct_binned.rs:77-146), for the
- * containers the extension selects in lib-shared/src/bcf_utils.rs:47-82: `.vcf` and `.vcf.gz`
- * (BGZF).  Binary `.bcf` and the CSI / TBI index are not implemented (a `.bcf` path is an error).
- * All columns are HOST arrays of n_rows entries; optional ones may be NULL.  Pure host code. */
+/* ---- variant files: VCF / BCF reader and writer + index ----------------
+ * Replaces what the commands of the path get from rust-htslib's bcf module: the record assembly
+ * and output of process_region (lib-coverage/src/lib.rs:560-673) under build_header (:67-166), the
+ * read / translate / push / write loops of lib-normalize (src/shared.rs:16-75, uncorrected.rs:
+ * 51-96, correct_binned.rs:77-146), lib-merge-cov (src/lib.rs:102-232), lib-model-wis (read_coverage_bcf
+ * src/lib.rs:65-125, write_output :340-419) and lib-mod-cov (src/lib.rs:33-60, 89-164, 167-248), and
+ * build_index (lib-shared/src/bcf_utils.rs:47-82).  The container follows the file name exactly as
+ * there: `.bcf` = BGZF-compressed binary BCF2.2 (+ `.csi`, min_shift 14), `.vcf.gz` = BGZF text
+ * (+ `.tbi`), `.vcf` = plain text, any other name = uncompressed BCF; neither of the last two gets an
+ * index.  The reader takes all four, telling them apart by content.
+ *
+ * The schema is the closed tag set of the two headers of the path (coverage: lib-coverage/src/lib.rs:
+ * 99-160; model: lib-model-wis/src/lib.rs:308-322): records are columns -- one host array per tag --
+ * so that they move to and from the kernels without a per-record object.  Every record of these
+ * files has REF N, one symbolic ALT (<WINDOW> | <TARGET>), no QUAL and the ID `chrom:pos+1-end`
+ * (lib.rs:586-588, lib-model-wis/src/lib.rs:359-361).  Tags outside the schema are skipped on
+ * reading.  Floats are stored exactly in BCF and printed with six significant digits in VCF (as
+ * htslib does): only BCF chains the commands bit for bit.  Pure host code (threads for record
+ * formatting / parsing and for BGZF blocks). */
+#define CNVB_VF_PASS 1        /* FILTER bits of a record (written in this order)                */
+#define CNVB_VF_PILE 2
+#define CNVB_VF_LOWCOV 4
+#define CNVB_VF_NO_REF 8
+#define CNVB_VF_FEW_REF 16
+#define CNVB_VF_UNRELIABLE 32
+#define CNVB_VF_OTHER 128     /* reading: a filter outside the schema                           */
 typedef struct {
-    const char *path;                 /* *.vcf or *.vcf.gz                                       */
-    const char *sample;               /* sample column (get_sample_name, lib.rs:36-64)           */
-    uint32_t n_contigs;
-    const char *const *contig_names;  /* ##contig lines, in this order                           */
-    const uint32_t *contig_lens;
-    const char *command_line;         /* ##cnvetti_cmdCoverageCommand (NULL: a placeholder)      */
-    const char *file_date;            /* YYYYMMDD (NULL: today, UTC)                             */
-    int is_targets;                   /* ALT <TARGET> instead of <WINDOW>                        */
-    int n_threads;                    /* <= 0: all cores                                         */
-} cnvb_vcf_opts;
+    const char *key;          /* FORMAT key of a Float tag (RCV, LCV, CV, ...)                  */
+    const float *values;      /* [n_rows][n_samples]                                            */
+    const uint8_t *present;   /* [n_rows] or NULL (every record carries the key)                */
+} cnvb_vfile_fmt;
 typedef struct {
-    const uint32_t *contig;   /* index into contig_names per row                                */
-    const int32_t *start, *end;
-    const float *rcv, *rcvsd, *lcv, *lcvsd, *frm;   /* rcvsd / lcvsd / frm optional             */
-    const float *gc;          /* optional: INFO GC (+ GAP from `gap`)                           */
-    const uint8_t *gap;
-    const float *mean_mapq;   /* optional: 60 when NULL (agg.rs:241)                            */
-    const uint8_t *ft;        /* optional: CNVB_FT_* bits -> FORMAT/FT "LOWCOV;PILE"            */
-    const float *cv, *cv2, *cvsd;  /* optional: normalised values                               */
-    const uint8_t *norm_flags;     /* optional: CNVB_N2_* bits say which of them a row carries  */
-} cnvb_vcf_columns;
-int cnvb_vcf_write_coverage(const cnvb_vcf_opts *opts, const cnvb_vcf_columns *cols, uint64_t n_rows,
-                            char *err, uint64_t err_len);
+    const char *path;
+    const char *header_text;  /* the `##` meta lines, '\n'-separated: ##fileformat and the PASS
+                                 filter are added when missing; the dictionary (IDX) follows the
+                                 order of the lines                                             */
+    uint32_t n_samples;
+    const char *const *samples;
+    uint64_t n_rows;
+    const int32_t *rid;       /* index into the header's ##contig lines                         */
+    const int32_t *pos;       /* 0-based start                                                  */
+    const int32_t *end;       /* INFO/END; also the record length (rlen = end - pos)            */
+    int is_targets;           /* ALT <TARGET> instead of <WINDOW>                               */
+    const uint8_t *filters;   /* CNVB_VF_* bits per row, or NULL                                */
+    /* INFO, in this order; NULL = the tag is not written */
+    const uint8_t *gap;       /* flag GAP (only with gc)                                        */
+    const float *gc;
+    const float *mean_mapq;
+    const uint8_t *few_gc;    /* flag FEW_GCWINDOWS                                             */
+    const float *ref_mean, *ref_sd;
+    const uint8_t *ref_present; /* rows that carry REF_MEAN / REF_STD_DEV (NULL: all)           */
+    const int32_t *num_calls;
+    const uint64_t *ref_off;  /* REF_TARGETS: CSR over the rows of this table, written as their IDs */
+    const uint32_t *ref_idx;
+    /* FORMAT: GT (always the no-call) first, then the keys of `fmt` in order, FT before fmt[ft_pos] */
+    uint32_t n_fmt;
+    const cnvb_vfile_fmt *fmt;
+    const uint8_t *ft;        /* [n_rows][n_samples] CNVB_FT_* bits or NULL; a record carries FT
+                                 when any sample has a bit set (lib.rs:659-664)                 */
+    uint32_t ft_pos;
+    int write_index;          /* build_index: .csi beside .bcf, .tbi beside .vcf.gz             */
+    int n_threads;            /* <= 0: all cores                                                */
+} cnvb_vfile_write_args;
+int cnvb_vfile_write(const cnvb_vfile_write_args *args, char *err, uint64_t err_len);
+
+typedef struct cnvb_vfile cnvb_vfile;
+int cnvb_vfile_open(const char *path, int n_threads, cnvb_vfile **out, char *err, uint64_t err_len);
+void cnvb_vfile_close(cnvb_vfile *f);
+const char *cnvb_vfile_last_error(const cnvb_vfile *f);
+uint64_t cnvb_vfile_num_records(const cnvb_vfile *f);
+uint32_t cnvb_vfile_num_samples(const cnvb_vfile *f);
+const char *cnvb_vfile_sample(const cnvb_vfile *f, uint32_t i);
+uint32_t cnvb_vfile_num_contigs(const cnvb_vfile *f);
+const char *cnvb_vfile_contig_name(const cnvb_vfile *f, uint32_t i);
+uint32_t cnvb_vfile_contig_length(const cnvb_vfile *f, uint32_t i);
+const char *cnvb_vfile_header_text(const cnvb_vfile *f); /* the ## lines as read (without IDX keys) */
+int cnvb_vfile_is_bcf(const cnvb_vfile *f);
+/* the fixed columns of every record; any pointer may be NULL.  alt: 0 <WINDOW>, 1 <TARGET>, 2 other;
+ * end = INFO/END (pos + length of REF without it); canonical_ids: 1 if every ID is chrom:pos+1-end */
+int cnvb_vfile_fixed(cnvb_vfile *f, int32_t *rid, int32_t *pos, int32_t *end, uint8_t *alt, uint8_t *filters,
+                     int *canonical_ids);
+/* one tag as a column; `present` (nullable) says which records carry it.  Absent values are left as the
+ * BCF missing pattern (floats 0x7F800001, ints INT32_MIN); a key the header does not define is
+ * CNVB_ERR_INVALID.  Numeric INFO tags yield their first value; FORMAT tags the first value per sample */
+int cnvb_vfile_info_float(cnvb_vfile *f, const char *key, float *out, uint8_t *present);
+int cnvb_vfile_info_int(cnvb_vfile *f, const char *key, int32_t *out, uint8_t *present);
+int cnvb_vfile_info_flag(cnvb_vfile *f, const char *key, uint8_t *out);
+int cnvb_vfile_format_float(cnvb_vfile *f, const char *key, float *out, uint8_t *present);
+int cnvb_vfile_format_ft(cnvb_vfile *f, uint8_t *out, uint8_t *present);
+/* for every record of `f` the row of `other` with the same ID (UINT32_MAX: none) -- the by-name lookups
+ * of lib-mod-cov (src/lib.rs:121-123, 146-152) */
+int cnvb_vfile_match_ids(cnvb_vfile *f, cnvb_vfile *other, uint32_t *row);
+/* INFO/REF_TARGETS of a model file, the names resolved to rows of `against` (the file itself when NULL):
+ * off[n + 1], idx[off[n]].  Call with idx = NULL to size: only `off` is filled.  A name `against` does not
+ * hold is CNVB_ERR_REFERENCE_PANIC ("Could not find: ...", lib-mod-cov/src/lib.rs:149) */
+int cnvb_vfile_ref_targets(cnvb_vfile *f, cnvb_vfile *against, uint64_t *off, uint32_t *idx, uint64_t idx_cap);
 
 /* ---- lib-merge-cov --------------------------------------------------------------------------
  * = merge_files (lib-merge-cov/src/lib.rs:102-232) on in-memory columns: the FORMAT/CV columns of S

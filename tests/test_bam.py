@@ -146,7 +146,7 @@ def test_coverage_from_bam_equals_arrays(tmp_path):
 def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
     """The two commands of the path at file level: BAM (+ FASTA) in, coverage VCF out, normalised VCF out;
     the values in the files are the oracle's (text precision of %g for the floats)."""
-    from cnvetti_b200 import pipeline, vcf
+    from cnvetti_b200 import files, pipeline
     from util import oracle_reads, to_np as to_np3
     ctx = cb.Context(0)
     lens = (300_000, 200_000)
@@ -164,8 +164,10 @@ def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
     out1 = str(tmp_path / "cov.vcf.gz")
     table, timings = pipeline.cmd_coverage(bam_path, out1, opts, reference=str(fa), ctx=ctx)
     assert set(timings) == {"bam_decode", "fasta", "device", "write"} and table.names == ["chr1", "chr2"]
-    r = vcf.read_coverage_vcf(out1)
-    assert r["samples"] == ["S1"] and "##contig=<ID=chrUn,length=1000>" in r["header"]
+    r = files.VariantFile(out1)
+    # only the contigs matching --contig-regex are listed (build_chroms_bam, lib.rs:734-741)
+    assert r.samples == ["S1"] and r.contigs == [("chr1", lens[0]), ("chr2", lens[1])]
+    assert os.path.exists(out1 + ".tbi")
     oopts = oracle.cov_opts(window_length=500, min_mapq=20)
     lcv_all, gc_all = [], []
     for d, s, L in zip(recs, seqs, lens):
@@ -174,19 +176,36 @@ def test_cmd_coverage_and_normalize_files(tmp_path, oracle):
         lcv_all.append(oracle.cov_records(cov, None, start, end, frm, False, oopts)[0])
         gc_all.append(oracle.refstats(s, 500)[0])
     lcv, gc = np.concatenate(lcv_all), np.concatenate(gc_all)
-    np.testing.assert_allclose(r["format"]["LCV"], lcv, rtol=1e-5)
-    got_gc = np.array([np.nan if x == "." else float(x) for x in r["info"]["GC"]])
-    np.testing.assert_allclose(got_gc[np.isfinite(gc)], gc[np.isfinite(gc)], rtol=1e-5)
+    file_lcv = r.format_float("LCV")[0][:, 0]
+    np.testing.assert_allclose(file_lcv, lcv, rtol=1e-5)      # text container: six significant digits
+    file_gc, _ = r.info_float("GC")
+    np.testing.assert_allclose(file_gc[np.isfinite(gc)], gc[np.isfinite(gc)], rtol=1e-5)
+    assert not np.isfinite(file_gc[~np.isfinite(gc)]).any()
     out2 = str(tmp_path / "norm.vcf")
     pipeline.cmd_normalize(out1, out2, "MedianGcBinned", ctx=ctx)
-    r2 = vcf.read_coverage_vcf(out2)
+    r2 = files.VariantFile(out2)
     # the oracle on the values as they stand in the first file (what lib-normalize reads)
-    cv, _, _, flags, _ = oracle.norm_gc_median(r["format"]["LCV"], np.array(
-        [np.frombuffer(np.uint32(0x7F800001).tobytes(), np.float32)[0] if x == "." else np.float32(x) for x in r["info"]["GC"]], np.float32))
+    cv, _, _, flags, _ = oracle.norm_gc_median(file_lcv, file_gc)
     has = (flags & 1).astype(bool)
     assert has.sum() > 100
-    np.testing.assert_allclose(r2["format"]["CV"][has], cv[has], rtol=1e-5)
-    assert np.array_equal(r2["pos"], r["pos"]) and r2["id"] == r["id"]
+    cv2, pcv = r2.format_float("CV")
+    assert np.array_equal(pcv != 0, has)
+    np.testing.assert_allclose(cv2[has, 0], cv[has], rtol=1e-5)
+    assert np.array_equal(r2.fixed()["pos"], r.fixed()["pos"]) and r2.fixed()["canonical_ids"]
+    # binary container: the same chain is bit-exact (BCF stores the f32 values as they are)
+    out1b, out2b = str(tmp_path / "cov.bcf"), str(tmp_path / "norm.bcf")
+    tb, _ = pipeline.cmd_coverage(bam_path, out1b, opts, reference=str(fa), ctx=ctx)
+    assert os.path.exists(out1b + ".csi")
+    rb = files.VariantFile(out1b)
+    assert rb.is_bcf and np.array_equal(rb.format_float("LCV")[0][:, 0].view(np.uint32), lcv.view(np.uint32))
+    assert np.array_equal(rb.info_float("GC")[0].view(np.uint32), gc.view(np.uint32))
+    pipeline.cmd_normalize(out1b, out2b, "MedianGcBinned", ctx=ctx)
+    ocv, ocv2, _, oflags, _ = oracle.norm_gc_median(lcv, gc)
+    rb2 = files.VariantFile(out2b)
+    gcv, gp = rb2.format_float("CV")
+    assert np.array_equal(gp != 0, (oflags & 1) != 0)
+    assert np.array_equal(gcv[gp != 0, 0].view(np.uint32), ocv[gp != 0].view(np.uint32))
+    assert np.array_equal(rb2.info_flag("FEW_GCWINDOWS") != 0, (oflags & 8) != 0)
     # --mask-piles: the file-level driver == pile collection + region loop on the decoded regions
     from cnvetti_b200 import piles as piles_mod
     # (a sparse BAM: isolated piles of depth 1 and 2 are what the Poisson fit of compute_threshold needs)
