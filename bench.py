@@ -284,6 +284,8 @@ def timed_steps(env, step, steps, warmup, sampler=None):
     e0.record()
     for _ in range(steps):
         step()
+    if hasattr(step, "flush"):
+        step.flush()   # (deferred steps: the last tallies are collected inside the timed region)
     e1.record()
     env.barrier()
     clocks = sampler.stop() if sampler else None
@@ -302,6 +304,8 @@ def kernel_times(env, step, steps, names):
     i0.record()
     for _ in range(steps):
         step()
+    if hasattr(step, "flush"):
+        step.flush()
     i1.record()
     torch.cuda.synchronize()
     kern = {}
@@ -1100,12 +1104,27 @@ def bench_coverage(args, env):
     prep_dev = pipeline.PreparedRegions(dev_regions, opts)
     shard = comm if world > 1 else None
 
+    # Steps are enqueued without a host wait in between (cnvb_coverage_run_async): the tallies and the
+    # reference-panic checks of step i are collected while step i + 1 runs, so at most two steps are in flight
+    # and every step still delivers everything the synchronous call does.
+    in_flight = []
+
     def step_device():
-        t = pipeline.coverage_run(prep_dev, opts, ctx=ctx)
-        return pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx, comm=shard, want_medians=False)
+        t = pipeline.coverage_run(prep_dev, opts, ctx=ctx, defer=True)
+        pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx, comm=shard, want_medians=False)
+        in_flight.append(t)
+        if len(in_flight) > 1:
+            in_flight.pop(0).wait()
+        return t
+
+    def flush():
+        while in_flight:
+            in_flight.pop(0).wait()
+    step_device.flush = flush
 
     # correctness guard on the full-size run: every counted fragment lands in exactly one window
     t = step_device()
+    flush()
     torch.cuda.synchronize()
     assert int(t.rcv.double().sum().item()) == sum(t.num_processed) - sum(t.num_skipped), "checksum"
     n_windows_local = int(t.rcv.numel())

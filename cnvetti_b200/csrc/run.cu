@@ -39,10 +39,33 @@ extern "C" uint64_t cnvb_coverage_rows(const cnvb_cov_opts *opts, int kind, cons
     return total;
 }
 
-extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind,
-                                 const cnvb_region *regions, uint32_t n_regions,
-                                 const cnvb_cov_columns *out, uint64_t *num_processed,
-                                 uint64_t *num_skipped, int mem) {
+// What a deferred run leaves behind: the aggregators (their tallies arrive in pinned slots, in stream order)
+// and the pooled temporaries, handed back by cnvb_coverage_wait.
+struct cnvb_cov_pending {
+    cnvb_ctx *ctx = nullptr;
+    std::vector<cnvb_cov *> aggs;
+    std::vector<void *> temps;
+};
+
+namespace {
+
+int coverage_complete(cnvb_ctx *ctx, std::vector<cnvb_cov *> &aggs, uint64_t *num_processed, uint64_t *num_skipped) {
+    // the single synchronisation point: tallies + reference-panic checks of every region, in order
+    for (uint32_t i = 0; i < aggs.size(); ++i) {
+        const int rc = cnvb_cov_finish(aggs[i]);
+        if (rc) {
+            const std::string inner = ctx->err;
+            return fail(ctx, rc, "region %u\ncaused by: %s", i, inner.c_str());
+        }
+        if (num_processed) num_processed[i] = cnvb_cov_num_processed(aggs[i]);
+        if (num_skipped) num_skipped[i] = cnvb_cov_num_skipped(aggs[i]);
+    }
+    return CNVB_OK;
+}
+
+int coverage_run_impl(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions, uint32_t n_regions,
+                      const cnvb_cov_columns *out, uint64_t *num_processed, uint64_t *num_skipped, int mem,
+                      cnvb_cov_pending **deferred) {
     if (!ctx) return CNVB_ERR_INVALID;
     if (!opts || !out || (n_regions && !regions))
         return fail(ctx, CNVB_ERR_INVALID, "cnvb_coverage_run: null argument");
@@ -241,18 +264,52 @@ extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int k
             (e = back(out->ft, d.ft, total)) != cudaSuccess)
             return cleanup(fail_cuda(ctx, e, "copying the coverage table to the host"));
     }
-    // the single synchronisation point: tallies + reference-panic checks of every region, in order
-    for (uint32_t i = 0; i < n_regions; ++i) {
-        const int rc = cnvb_cov_finish(aggs[i]);
-        if (rc) {
-            const std::string inner = ctx->err;
-            return cleanup(fail(ctx, rc, "region %u\ncaused by: %s", i, inner.c_str()));
-        }
-        if (num_processed) num_processed[i] = cnvb_cov_num_processed(aggs[i]);
-        if (num_skipped) num_skipped[i] = cnvb_cov_num_skipped(aggs[i]);
+    if (deferred) {  // the caller collects tallies and checks later (cnvb_coverage_wait); nothing waits here
+        cnvb_cov_pending *p = new (std::nothrow) cnvb_cov_pending();
+        if (!p) return cleanup(fail(ctx, CNVB_ERR_NOMEM, "out of host memory"));
+        p->ctx = ctx;
+        p->aggs.swap(aggs);
+        p->temps.swap(temps);
+        *deferred = p;
+        return CNVB_OK;
+    }
+    {
+        const int rc = coverage_complete(ctx, aggs, num_processed, num_skipped);
+        if (rc) return cleanup(rc);
     }
     if (mem != CNVB_MEM_DEVICE)
         if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
             return cleanup(fail_cuda(ctx, e, "copying the coverage table to the host"));
     return cleanup(CNVB_OK);
+}
+
+}  // namespace
+
+extern "C" int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind,
+                                 const cnvb_region *regions, uint32_t n_regions,
+                                 const cnvb_cov_columns *out, uint64_t *num_processed,
+                                 uint64_t *num_skipped, int mem) {
+    return coverage_run_impl(ctx, opts, kind, regions, n_regions, out, num_processed, num_skipped, mem, nullptr);
+}
+
+extern "C" int cnvb_coverage_run_async(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind,
+                                       const cnvb_region *regions, uint32_t n_regions,
+                                       const cnvb_cov_columns *out, cnvb_cov_pending **pending) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (!pending) return fail(ctx, CNVB_ERR_INVALID, "cnvb_coverage_run_async: null argument");
+    *pending = nullptr;
+    for (uint32_t i = 0; i < n_regions && regions; ++i)
+        if (regions[i].reads.mem != CNVB_MEM_DEVICE || (regions[i].seq && regions[i].seq_mem != CNVB_MEM_DEVICE))
+            return fail(ctx, CNVB_ERR_INVALID, "cnvb_coverage_run_async: inputs must be device-resident (region %u)", i);
+    return coverage_run_impl(ctx, opts, kind, regions, n_regions, out, nullptr, nullptr, CNVB_MEM_DEVICE, pending);
+}
+
+extern "C" int cnvb_coverage_wait(cnvb_cov_pending *p, uint64_t *num_processed, uint64_t *num_skipped) {
+    if (!p) return CNVB_ERR_INVALID;
+    cnvb_ctx *ctx = p->ctx;
+    const int rc = coverage_complete(ctx, p->aggs, num_processed, num_skipped);
+    for (cnvb_cov *a : p->aggs) cnvb_cov_destroy(a);
+    for (void *t : p->temps) pool_release(ctx, t);
+    delete p;
+    return rc;
 }

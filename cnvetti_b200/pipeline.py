@@ -52,6 +52,20 @@ class CoverageTable:
     cvsd: object = None
     norm_flags: object = None
     medians: object = None
+    _pending: object = None          # (handle, ctx, n_regions) of a deferred run
+
+    def wait(self):
+        """After coverage_run(..., defer=True): block until the regions' tallies have arrived, fill
+        num_processed / num_skipped and raise what the synchronous call would have raised."""
+        if self._pending is not None:
+            handle, ctx, n = self._pending
+            self._pending = None
+            nproc = np.zeros(max(1, n), np.uint64)
+            nskip = np.zeros(max(1, n), np.uint64)
+            ctx.check(N.lib().cnvb_coverage_wait(handle, nproc.ctypes.data, nskip.ctypes.data))
+            self.num_processed = [int(x) for x in nproc[:n]]
+            self.num_skipped = [int(x) for x in nskip[:n]]
+        return self
 
 
 def _num_regions(options, r):
@@ -109,9 +123,11 @@ class PreparedRegions:
         self.names = [r.name for r in self.regions]
 
 
-def coverage_run(regions, options, ctx=None, device=True):
+def coverage_run(regions, options, ctx=None, device=True, defer=False):
     """`cnvetti cmd coverage` on in-memory inputs: the region loop of lib_coverage::run
-    (lib.rs:768-781) as one native call (cnvb_coverage_run); columns stay in HBM."""
+    (lib.rs:768-781) as one native call (cnvb_coverage_run); columns stay in HBM.
+    defer=True (device-resident inputs): nothing waits -- the columns are valid in stream order, the
+    tallies and the reference-panic checks arrive with table.wait() (cnvb_coverage_run_async)."""
     import torch
     ctx = ctx or default_context()
     prep = regions if isinstance(regions, PreparedRegions) else PreparedRegions(regions, options)
@@ -135,6 +151,12 @@ def coverage_run(regions, options, ctx=None, device=True):
     ptr = lambda x: x.data_ptr() if x is not None else None
     cols = N.CovColumns(ptr(t.start), ptr(t.end), ptr(t.rcv), ptr(t.rcvsd), ptr(t.lcv), ptr(t.lcvsd),
                         ptr(t.frm), ptr(t.gc), None, ptr(t.gap), ptr(t.ft))
+    if defer:
+        handle = C.c_void_p()
+        ctx.check(N.lib().cnvb_coverage_run_async(ctx.handle, C.byref(prep.c_opts), prep.kind, prep.array, prep.n,
+                                                  C.byref(cols), C.byref(handle)))
+        t._pending = (handle, ctx, prep.n)
+        return t
     nproc = np.zeros(max(1, prep.n), np.uint64)
     nskip = np.zeros(max(1, prep.n), np.uint64)
     ctx.check(N.lib().cnvb_coverage_run(ctx.handle, C.byref(prep.c_opts), prep.kind, prep.array, prep.n,

@@ -230,6 +230,17 @@ uint64_t cnvb_coverage_rows(const cnvb_cov_opts *opts, int kind, const cnvb_regi
 int cnvb_coverage_run(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
                       uint32_t n_regions, const cnvb_cov_columns *out, uint64_t *num_processed,
                       uint64_t *num_skipped, int mem);
+/* The same without the host wait, for device-resident inputs and columns: every stage is enqueued and
+ * the call returns; the columns are valid in stream order (a following cnvb_norm_* call on the same
+ * context may consume them at once).  cnvb_coverage_wait blocks until the regions' tallies have
+ * arrived, fills num_processed / num_skipped (n_regions entries each, may be NULL), reports the first
+ * region on which the reference would have panicked exactly as cnvb_coverage_run does, and frees the
+ * pending state -- it must be called once per successful cnvb_coverage_run_async.  At most 4096
+ * regions may be pending per context (the tallies travel through a ring of pinned slots). */
+typedef struct cnvb_cov_pending cnvb_cov_pending;
+int cnvb_coverage_run_async(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
+                            uint32_t n_regions, const cnvb_cov_columns *out, cnvb_cov_pending **pending);
+int cnvb_coverage_wait(cnvb_cov_pending *pending, uint64_t *num_processed, uint64_t *num_skipped);
 
 /* ---- lib-coverage: pile collection for --mask-piles --------------------------------------- */
 typedef struct cnvb_piles cnvb_piles;

@@ -85,6 +85,44 @@ def test_region_loop_targets_and_coverage(oracle, ctx):
         np.testing.assert_allclose(to_np(t.rcvsd[lo:hi]), sd, rtol=1e-6)
 
 
+def test_region_loop_deferred_equals_synchronous(oracle, ctx):
+    """cnvb_coverage_run_async + cnvb_coverage_wait: several runs enqueued without a host wait (normaliser chained
+    in stream order) deliver the columns and tallies of the synchronous call; a reference panic surfaces at wait()."""
+    import torch
+    regions, raw = _regions("cuda")
+    for kind_opts in (cb.CoverageOptions(window_length=500, min_mapq=10),
+                      cb.CoverageOptions(window_length=1000, count_kind="Coverage")):
+        ref = pipeline.coverage_run(regions, kind_opts, ctx=ctx)
+        if kind_opts.count_kind == "Fragments":
+            pipeline.normalize_run(ref, "MedianGcBinned", ctx=ctx)
+        prep = pipeline.PreparedRegions(regions, kind_opts)
+        tables = []
+        for _ in range(4):
+            t = pipeline.coverage_run(prep, kind_opts, ctx=ctx, defer=True)
+            assert t.num_processed == [] and t._pending is not None
+            if kind_opts.count_kind == "Fragments":
+                pipeline.normalize_run(t, "MedianGcBinned", ctx=ctx, want_medians=False)
+            tables.append(t)
+        for t in tables:
+            t.wait()
+            assert t.num_processed == ref.num_processed and t.num_skipped == ref.num_skipped
+            for col in ("start", "end", "rcv", "rcvsd", "lcv", "ft", "gc", "gap", "cv", "cv2", "norm_flags"):
+                a, b = getattr(t, col), getattr(ref, col)
+                assert (a is None) == (b is None), col
+                if a is not None:
+                    assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), col
+            assert t.wait() is t       # idempotent
+    # an unpaired read whose centre pos + end_pos lands outside the windows: the reference panics (agg.rs:144)
+    d2 = simple_reads([45], [60])
+    bad = [pipeline.Region("chrP", 50, soa_batch(d2, device="cuda"), None)]
+    t = pipeline.coverage_run(bad, cb.CoverageOptions(window_length=100), ctx=ctx, defer=True)
+    with pytest.raises(cb.ReferencePanic, match="region 0"):
+        t.wait()
+    with pytest.raises(cb.CnvbError, match="device-resident"):
+        pipeline.coverage_run([pipeline.Region("chrH", 50, soa_batch(d2), None)], cb.CoverageOptions(window_length=100),
+                              ctx=ctx, defer=True)
+
+
 def test_region_loop_host_columns_and_panic(oracle, ctx):
     """C ABI called directly with HOST columns; a region that makes the reference panic fails the run."""
     wl = 100

@@ -41,11 +41,25 @@ def main():
     def cov():
         pipeline.coverage_run(prep, opts, ctx=env.ctx)
 
+    flight = []
+
+    def both_deferred():
+        t = pipeline.coverage_run(prep, opts, ctx=env.ctx, defer=True)
+        pipeline.normalize_run(t, "MedianGcBinned", ctx=env.ctx, comm=shard, want_medians=False)
+        flight.append(t)
+        if len(flight) > 1:
+            flight.pop(0).wait()
+
+    def flush():
+        while flight:
+            flight.pop(0).wait()
+    both_deferred.flush = flush
+
     def norm():
         pipeline.normalize_run(table, "MedianGcBinned", ctx=env.ctx, comm=shard, want_medians=False)
 
     res = {"world": env.world}
-    for name, fn in (("both", both), ("cov", cov), ("norm", norm)):
+    for name, fn in (("both", both), ("both_deferred", both_deferred), ("cov", cov), ("norm", norm)):
         for with_sampler in (False, True):
             s = bench.ClockSampler(env.local) if with_sampler else None
             ms, _, _ = bench.timed_steps(env, fn, 50, 5, s)
@@ -56,6 +70,8 @@ def main():
         t0 = time.perf_counter()
         for _ in range(20):
             fn()
+        if hasattr(fn, "flush"):
+            fn.flush()
         host = (time.perf_counter() - t0) / 20
         torch.cuda.synchronize()
         res[name + "_host_ms"] = round(host * 1e3, 4)
