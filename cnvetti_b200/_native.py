@@ -92,6 +92,7 @@ SYMBOLS = {
     "cnvb_bam_ref_len": (_u32, [_vp, _u32]),
     "cnvb_bam_header_text": (_vp, [_vp, C.POINTER(_u64)]),
     "cnvb_bam_decode": (_int, [_vp, C.c_float, _int]),
+    "cnvb_bam_fetch": (_int, [_vp, _u32, _u32, _u32, C.c_float, _int]),
     "cnvb_bam_ref_reads": (_int, [_vp, _u32, C.POINTER(ReadSoa)]),
     "cnvb_bam_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
     "cnvb_bam_close": (None, [_vp]),

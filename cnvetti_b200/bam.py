@@ -25,6 +25,7 @@ class BamError(N.CnvbError):
 class BamReader:
     def __init__(self, path, threads=0):
         self._h = C.c_void_p()
+        self.path = str(path)
         rc = N.lib().cnvb_bam_open(str(path).encode(), int(threads), C.byref(self._h))
         if rc != N.OK:
             msg = N.lib().cnvb_bam_error(self._h).decode() if self._h else "could not open %s" % path
@@ -115,6 +116,24 @@ class BamReader:
             b = ReadBatch(**{k: np.ascontiguousarray(getattr(b, k)[keep])
                              for k in ("pos", "end", "mid", "frag_end", "mapq", "flags")})
         return b
+
+    def has_index(self):
+        import os
+        return os.path.exists(self.path + ".bai") or (self.path.endswith(".bam") and os.path.exists(self.path[:-4] + ".bai"))
+
+    def fetch_indexed(self, tid, start, end, min_unclipped=0.6, pinned=False):
+        """bam::IndexedReader::fetch(tid, start, end) + the record loop (lib-coverage/src/lib.rs:533-547) through
+        the .bai index: only the blocks of the interval are read and inflated (cnvb_bam_fetch).  Returns the
+        ReadBatch of the records overlapping [start, end) -- views of the decoder's columns of `tid`, valid until
+        the next fetch / decode."""
+        if isinstance(tid, str):
+            tid = self.references.index(tid)
+        rc = N.lib().cnvb_bam_fetch(self._h, int(tid), int(start), int(end), C.c_float(float(np.float32(min_unclipped))),
+                                    1 if pinned else 0)
+        if rc != N.OK:
+            raise BamError(rc, N.lib().cnvb_bam_error(self._h).decode())
+        self.decoded = True
+        return self.fetch(tid)
 
     def regions(self, contig_regex=r"^(chr)?\d\d?$", sequences=None, targets=None):
         """The region loop's inputs (GenomeRegions::from_name_and_length over the contigs matching

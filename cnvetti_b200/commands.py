@@ -68,9 +68,22 @@ def load_model_targets(path, threads=0):
         return out
 
 
+def parse_genome_region(text):
+    """`--genome-region chr:a-b` -> (chr, a - 1, b) (GenomeRegions::from_string_list, lib-shared/src/regions.rs:56-90:
+    exactly one ':' and one '-', thousands separators ',' and '_' allowed)."""
+    parts = text.split(":")
+    if len(parts) != 2:
+        raise N.CnvbError(N.ERR_INVALID, "Problem parsing region\ncaused by: Could not parse genome region (not exactly one ':')")
+    nums = parts[1].split("-")
+    if len(nums) != 2:
+        raise N.CnvbError(N.ERR_INVALID, "Problem parsing region\ncaused by: Could not parse genome region (not exatly one '-')")
+    a, b = (int(x.replace(",", "").replace("_", "")) for x in nums)
+    return parts[0], a - 1, b
+
+
 def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(chr)?\d\d?$", targets_bed=None,
                  wis_model_bcf=None, targets=None, ctx=None, threads=0, command_line=None, mask_piles=False,
-                 mask_piles_fdr=0.001, pile_max_gap=20, file_date=None):
+                 mask_piles_fdr=0.001, pile_max_gap=20, file_date=None, genome_region=None):
     """`cnvetti cmd coverage --input X.bam --output Y.{bcf,vcf.gz,vcf} [--reference R.fa] [--targets-bed T.bed |
     --wis-model-bcf M.bcf] [--mask-piles] ...`: BAM decode on host threads, with --mask-piles the pile collection
     and its FDR threshold (gather_piles, lib.rs:353-419), the region loop on the GPU, the file written on host
@@ -85,7 +98,22 @@ def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(ch
     t0 = time.perf_counter()
     with bam_mod.BamReader(input_bam, threads=threads) as reader:
         samples = reader.sample_names()
-        reader.decode(min_unclipped=options.min_unclipped, pinned=True)
+        region = parse_genome_region(genome_region) if genome_region else None
+        region_reads = None
+        if region is not None:
+            # lib.rs:707-711, 533-543: ONE region (chr, a - 1, b); fetch(tid, a - 1, b) through the .bai -- only the
+            # blocks of the interval are inflated.  (Without an index the whole file is decoded and filtered.)
+            if region[0] not in reader.references:
+                raise N.ReferencePanic(N.ERR_REFERENCE_PANIC, "contig %s is not in the BAM header (the reference unwraps "
+                                       "header.tid(), lib-coverage/src/lib.rs:540)" % region[0])
+            if reader.has_index():
+                region_reads = reader.fetch_indexed(region[0], region[1], region[2], min_unclipped=options.min_unclipped,
+                                                    pinned=True)
+            else:
+                reader.decode(min_unclipped=options.min_unclipped, pinned=False)
+                region_reads = reader.fetch(region[0], region[1], region[2])
+        else:
+            reader.decode(min_unclipped=options.min_unclipped, pinned=True)
         timings["bam_decode"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         seqs = read_fasta(reference) if reference else None
@@ -95,7 +123,16 @@ def cmd_coverage(input_bam, output, options, reference=None, contig_regex=r"^(ch
             targets = load_model_targets(wis_model_bcf, threads=threads)
         timings["fasta"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        regions = reader.regions(contig_regex=contig_regex, sequences=seqs, targets=targets)
+        if region is not None:
+            from .pipeline import Region
+            name, _, r_end = region
+            seq = None if seqs is None else seqs.get(name)
+            wl = options.window_length
+            if seq is not None and wl:   # statistics of the contig's windows, as many as the region has (lib.rs:440-454, 560)
+                seq = seq[:((r_end + wl - 1) // wl) * wl]
+            regions = [Region(name, r_end, region_reads, seq, None if targets is None else targets.get(name))]
+        else:
+            regions = reader.regions(contig_regex=contig_regex, sequences=seqs, targets=targets)
         if options.considered_regions == "TargetRegions":
             empty = (np.zeros(0, np.uint32), np.zeros(0, np.uint32))
             for r in regions:   # a contig without targets yields an empty GenomeRegions (lib.rs:193-199)

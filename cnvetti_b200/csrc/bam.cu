@@ -158,7 +158,20 @@ void run_parallel(int n_threads, uint64_t n_items, const std::function<void(uint
 
 }  // namespace
 
+struct BaiRef {  // one reference of a .bai index
+    std::unordered_map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+    std::vector<uint64_t> linear;
+};
+
+struct FetchRange {  // an indexed fetch: start reading at a virtual offset, keep what overlaps [beg, end) on tid
+    uint64_t coff;   // file offset of the first BGZF block
+    uint32_t uoff;   // offset of the first record inside it
+    int32_t tid, beg, end;
+};
+
 struct cnvb_bam {
+    std::vector<BaiRef> bai;
+    bool bai_loaded = false;
     std::string path, error, text;
     std::vector<std::string> ref_names;
     std::vector<uint32_t> ref_lens;
@@ -196,12 +209,14 @@ struct Run {  // consecutive records of one refID inside a chunk
 // stage B of chunk k runs on a helper thread while stage A of chunk k+1 proceeds (two uncompressed
 // buffers).  Stage B is sequential from chunk to chunk (it hands the partial record at the end of a chunk
 // to the next one); its serial part, the record walk, is what the overlap hides.
-int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
+int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only, const FetchRange *range = nullptr) {
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
     FILE *f = fopen(b->path.c_str(), "rb");
     if (!f) return fail_to(b->error, CNVB_ERR_INVALID, "Could not open BAM file %s", b->path.c_str());
-    uint64_t kChunkBytes = header_only ? (1ull << 20) : (8ull << 20);  // compressed bytes per chunk
+    // compressed bytes per chunk (an indexed fetch starts small and doubles: short intervals stay short reads)
+    uint64_t kChunkBytes = header_only ? (1ull << 20) : range ? (256ull << 10) : (8ull << 20);
+    const bool grow_chunks = range != nullptr && !getenv("CNVB_BAM_CHUNK");
     if (const char *e = getenv("CNVB_BAM_CHUNK")) {  // (tests: small chunks exercise the chunk seams)
         const long v = atol(e);
         if (v >= 64) kChunkBytes = (uint64_t)v;
@@ -214,12 +229,20 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
     uint64_t file_pos = 0;
     bool eof = false;
     int rc = CNVB_OK;
+    if (range) {
+        if (fseeko(f, (off_t)range->coff, SEEK_SET) != 0) {
+            fclose(f);
+            return fail_to(b->error, CNVB_ERR_INVALID, "Could not seek to region in %s", b->path.c_str());
+        }
+        file_pos = range->coff;
+    }
 
     // ---- stage B state (touched by the helper thread only while it runs)
     std::vector<uint8_t> carry, joined;
     std::vector<uint64_t> rec_off;
     std::vector<Run> runs;
-    bool header_done = false, stop_after_header = false;
+    bool header_done = range != nullptr, stop_after_header = false;  // (an indexed fetch starts at a record)
+    bool first_parse = true;
     std::string werr;
     int wrc = CNVB_OK;
     double t_parse = 0.0;
@@ -238,6 +261,8 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             un = joined.size();
         }
         uint64_t q = 0;
+        if (range && first_parse) q = range->uoff;
+        first_parse = false;
         if (!header_done) {
             bool complete = false;
             do {
@@ -301,6 +326,28 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             __builtin_prefetch(u + q + 12 * (4 + bs));
             __builtin_prefetch(u + q + 12 * (4 + bs) + 64);
             const int32_t tid = (int32_t)rd32(u + q + 4);
+            if (range) {
+                // htslib's iterator: the records from the start offset on until one lies on another reference or
+                // starts at / after the end; of those, the ones whose [pos, bam_endpos) overlaps the interval
+                const int32_t pos = (int32_t)rd32(u + q + 8);
+                if (tid != range->tid || pos >= range->end) {
+                    stop_after_header = true;  // (ends the read loop)
+                    break;
+                }
+                const uint32_t l_name = u[q + 12], n_cigar = rd16(u + q + 16);
+                const uint16_t flag = rd16(u + q + 18);
+                uint32_t ref_len = 0;
+                if (36ull + l_name + 4ull * n_cigar <= 4ull + bs)
+                    for (uint32_t c = 0; c < n_cigar; ++c) {
+                        const uint32_t w = rd32(u + q + 36 + l_name + 4 * c), op = w & 0xFu;
+                        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += w >> 4;
+                    }
+                const int32_t endpos = pos + (int32_t)((!(flag & 0x4) && n_cigar > 0 && ref_len) ? ref_len : 1);
+                if (endpos <= range->beg) {
+                    q += 4 + bs;
+                    continue;
+                }
+            }
             if (runs.empty() || tid != run_tid) {
                 runs.push_back(Run{rec_off.size(), tid, 0});
                 run_tid = tid;
@@ -363,7 +410,8 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
             return;
         }
         b->n_records += nr;
-        carry.assign(u + q, u + un);  // (may alias `joined`: assign from a range of another vector is fine)
+        if (stop_after_header) carry.clear();
+        else carry.assign(u + q, u + un);  // (may alias `joined`: assign from a range of another vector is fine)
         t_parse += std::chrono::duration<double>(clk::now() - t1).count();
     };
 
@@ -380,6 +428,7 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only) {
         }
         if (have) memcpy(cbuf.data(), left.data(), have);
         const size_t got = fread(cbuf.data() + have, 1, kChunkBytes, f);
+        if (grow_chunks && kChunkBytes < (8ull << 20)) kChunkBytes *= 2;
         cbuf.n = have + got;
         file_pos += got;
         if (got == 0) eof = true;
@@ -524,6 +573,99 @@ extern "C" int cnvb_bam_decode(cnvb_bam *b, float min_unclipped, int pinned) {
     const int rc = decode(b, min_unclipped, pinned != 0, false);
     b->decoded = rc == CNVB_OK;
     return rc;
+}
+
+namespace {
+
+// the .bai beside the file: <path>.bai, else <path without .bam>.bai
+int load_bai(cnvb_bam *b) {
+    if (b->bai_loaded) return CNVB_OK;
+    std::string p1 = b->path + ".bai", p2;
+    if (b->path.size() > 4 && b->path.compare(b->path.size() - 4, 4, ".bam") == 0) p2 = b->path.substr(0, b->path.size() - 4) + ".bai";
+    FILE *f = fopen(p1.c_str(), "rb");
+    if (!f && !p2.empty()) f = fopen(p2.c_str(), "rb");
+    if (!f) return fail_to(b->error, CNVB_ERR_INVALID, "Could not open BAI-indexed BAM file %s: no index", b->path.c_str());
+    std::vector<uint8_t> d;
+    {
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        d.resize(sz > 0 ? (size_t)sz : 0);
+        const size_t got = d.empty() ? 0 : fread(d.data(), 1, d.size(), f);
+        fclose(f);
+        if (got != d.size()) return fail_to(b->error, CNVB_ERR_INVALID, "Could not read the index of %s", b->path.c_str());
+    }
+    auto bad = [&]() { return fail_to(b->error, CNVB_ERR_INVALID, "%s: corrupt .bai index", b->path.c_str()); };
+    if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return bad();
+    const uint32_t n_ref = rd32(d.data() + 4);
+    uint64_t at = 8;
+    std::vector<BaiRef> refs(n_ref);
+    auto rd64 = [&](uint64_t o) { uint64_t v; memcpy(&v, d.data() + o, 8); return v; };
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (at + 4 > d.size()) return bad();
+        const uint32_t n_bin = rd32(d.data() + at);
+        at += 4;
+        for (uint32_t k = 0; k < n_bin; ++k) {
+            if (at + 8 > d.size()) return bad();
+            const uint32_t bin = rd32(d.data() + at), n_chunk = rd32(d.data() + at + 4);
+            at += 8;
+            if (at + 16ull * n_chunk > d.size()) return bad();
+            auto &v = refs[r].bins[bin];
+            for (uint32_t c = 0; c < n_chunk; ++c) v.emplace_back(rd64(at + 16ull * c), rd64(at + 16ull * c + 8));
+            at += 16ull * n_chunk;
+        }
+        if (at + 4 > d.size()) return bad();
+        const uint32_t n_intv = rd32(d.data() + at);
+        at += 4;
+        if (at + 8ull * n_intv > d.size()) return bad();
+        refs[r].linear.resize(n_intv);
+        for (uint32_t i = 0; i < n_intv; ++i) refs[r].linear[i] = rd64(at + 8ull * i);
+        at += 8ull * n_intv;
+    }
+    b->bai.swap(refs);
+    b->bai_loaded = true;
+    return CNVB_OK;
+}
+
+}  // namespace
+
+// `fetch(tid, start, end)` of bam::IndexedReader (lib-coverage/src/lib.rs:533-543) through the .bai index: the bins
+// overlapping the interval give the candidate chunks, the linear index bounds them from below, the decoder seeks to
+// the first of them and reads until a record lies past the interval; of the records met, those whose alignment
+// overlaps [start, end) -- what htslib's iterator yields, in file order.  The records replace the columns of `tid`.
+extern "C" int cnvb_bam_fetch(cnvb_bam *b, uint32_t tid, uint32_t start, uint32_t end, float min_unclipped, int pinned) {
+    if (!b) return CNVB_ERR_INVALID;
+    if (tid >= b->refs.size()) return fail_to(b->error, CNVB_ERR_INVALID, "no such reference: %u", tid);
+    CNVB_TRY(load_bai(b));
+    RefReads &rr = b->refs[tid];
+    rr.n = 0;
+    rr.pos.n = rr.end.n = rr.mid.n = rr.frag_end.n = rr.mapq.n = rr.flags.n = 0;
+    b->decoded = true;  // (the columns of this reference are valid after the call; others keep what they had)
+    if (end <= start || tid >= b->bai.size()) return CNVB_OK;
+    const BaiRef &ix = b->bai[tid];
+    const uint64_t w = (uint64_t)start >> 14;
+    uint64_t min_off = 0;
+    if (!ix.linear.empty()) min_off = w < ix.linear.size() ? ix.linear[w] : ix.linear.back();
+    uint64_t first = ~0ull;
+    {   // reg2bins(start, end) of the BAM specification (min_shift 14, depth 5)
+        const uint32_t e = end - 1;
+        uint32_t t = 0;
+        for (int l = 0, s = 29; l <= 5; ++l, s -= 3) {
+            const uint32_t lo = t + (start >> s), hi = t + (e >> s);
+            for (uint32_t bin = lo; bin <= hi; ++bin) {
+                auto it = ix.bins.find(bin);
+                if (it == ix.bins.end()) continue;
+                for (auto &c : it->second)
+                    if (c.second > min_off) first = std::min(first, c.first);
+            }
+            t += 1u << (3 * l);
+        }
+    }
+    if (first == ~0ull) return CNVB_OK;
+    FetchRange range{first >> 16, (uint32_t)(first & 0xffff), (int32_t)tid, (int32_t)start, (int32_t)end};
+    b->n_records = b->n_unplaced = b->bytes_compressed = b->bytes_uncompressed = 0;
+    b->t_inflate = b->t_parse = b->t_total = 0.0;
+    return decode(b, min_unclipped, pinned != 0, false, &range);
 }
 
 extern "C" int cnvb_bam_ref_reads(const cnvb_bam *b, uint32_t tid, cnvb_read_soa *out) {

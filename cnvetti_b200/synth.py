@@ -214,7 +214,51 @@ def _bgzf_block(payload, level):
     return head + data + struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload))
 
 
-def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, block_payload=0xff00):
+def _write_bai(path, n_ref, tids, beg, end, vbeg, vend):
+    """The .bai of a BAM file from its records (SAM specification 5.2: bins of reg2bin(beg, end) with their chunks,
+    16 kbp linear index, virtual offsets).  Test / bench infrastructure: the product READS such an index."""
+    import struct
+    out = [b"BAI\x01", struct.pack("<i", n_ref)]
+    b, e = beg.astype(np.int64), np.maximum(end.astype(np.int64), beg.astype(np.int64) + 1) - 1
+    bins = np.zeros(b.size, np.int64)
+    done = np.zeros(b.size, bool)
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        m = ~done & ((b >> shift) == (e >> shift))
+        bins[m] = base + (b[m] >> shift)
+        done |= m
+    for r in range(n_ref):
+        sel = np.flatnonzero(tids == r)
+        if sel.size == 0:
+            out.append(struct.pack("<ii", 0, 0))
+            continue
+        ub = np.unique(bins[sel])
+        parts = [struct.pack("<i", ub.size + 1)]
+        for bn in ub:
+            idx = sel[bins[sel] == bn]
+            cut = np.flatnonzero(np.diff(idx) != 1) + 1       # records consecutive in the file share a chunk
+            starts = np.concatenate([[0], cut])
+            stops = np.concatenate([cut, [idx.size]]) - 1
+            parts.append(struct.pack("<Ii", int(bn), starts.size))
+            for a, z in zip(starts, stops):
+                parts.append(struct.pack("<QQ", int(vbeg[idx[a]]), int(vend[idx[z]])))
+        parts.append(struct.pack("<IiQQQQ", 37450, 2, int(vbeg[sel[0]]), int(vend[sel[-1]]), int(sel.size), 0))
+        n_intv = int(e[sel].max() >> 14) + 1
+        lin = np.full(n_intv, -1, np.int64)
+        for i in sel:                                          # first record overlapping each 16 kbp window
+            w0, w1 = int(b[i] >> 14), int(e[i] >> 14)
+            seg = lin[w0:w1 + 1]
+            seg[seg < 0] = int(vbeg[i])
+        for w in range(n_intv - 2, -1, -1):
+            if lin[w] < 0:
+                lin[w] = lin[w + 1]
+        parts.append(struct.pack("<i", n_intv))
+        parts.append(lin.astype("<u8").tobytes())
+        out += parts
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
+def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, block_payload=0xff00, index=False):
     """Write a coordinate-sorted BAM file.  `contigs`: [(name, length)]; `records`: one dict per contig (or
     None) with the BAM-level arrays of `synth_bam_records` (pos, isize, flag, mapq, cigar_off, cigar);
     an optional entry with key -1 in a dict `records` holds reads without a reference.  Read names,
@@ -232,6 +276,8 @@ def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, blo
     for name, length in contigs:
         head += struct.pack("<I", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<I", length)
     chunks = [np.frombuffer(head, np.uint8)]
+    ix = dict(tid=[], beg=[], end=[], uoff=[], ulen=[])
+    stream_at = len(head)
     l_name = 8  # "r" + 6 characters + NUL
     for tid, d in list(enumerate(records)) + [(-1, extra)]:
         if d is None or len(d["pos"]) == 0:
@@ -288,9 +334,30 @@ def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, blo
             for i in range(n):
                 buf[qbase[i]:qbase[i] + l_seq[i]] = 0xFF
         chunks.append(buf)
+        if index and tid >= 0:
+            rl = np.where(np.isin(ops, (0, 2, 3, 7, 8)), lens, 0)
+            rcs = np.concatenate([[0], np.cumsum(rl)])
+            ref_len = (rcs[coff[1:]] - rcs[coff[:-1]]).astype(np.int64)
+            unmapped = (np.asarray(d["flag"], np.int64) & 4) != 0
+            ref_len = np.where(unmapped | (ncig == 0) | (ref_len == 0), 1, ref_len)   # bam_endpos
+            ix["tid"].append(np.full(n, tid, np.int64))
+            ix["beg"].append(pos)
+            ix["end"].append(pos + ref_len)
+            ix["uoff"].append(stream_at + off[:-1])
+            ix["ulen"].append(size + 4)
+        stream_at += int(off[-1])
     stream = np.concatenate(chunks)
+    block_addr = []
     with open(path, "wb") as f:
         for a in range(0, stream.size, block_payload):
+            block_addr.append(f.tell())
             f.write(_bgzf_block(stream[a:a + block_payload].tobytes(), level))
+        block_addr.append(f.tell())
         f.write(_bgzf_block(b"", level))  # EOF marker
+    if index:
+        cat = {k: (np.concatenate(v) if v else np.zeros(0, np.int64)) for k, v in ix.items()}
+        addr = np.asarray(block_addr, np.int64)
+        voff = lambda u: (addr[u // block_payload] << 16) | (u % block_payload)  # noqa: E731
+        _write_bai(path + ".bai", len(contigs), cat["tid"], cat["beg"], cat["end"], voff(cat["uoff"]),
+                   voff(cat["uoff"] + cat["ulen"]))
     return path

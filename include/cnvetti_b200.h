@@ -284,6 +284,13 @@ const char *cnvb_bam_header_text(const cnvb_bam *b, uint64_t *len);
  * CUDA runtime is usable).  min_unclipped as in cnvb_pack_reads. */
 int cnvb_bam_decode(cnvb_bam *b, float min_unclipped, int pinned);
 /* The decoded columns of one contig (pointers stay valid until the next decode / close). */
+/* = bam::IndexedReader::fetch(tid, start, end) + the record loop (lib-coverage/src/lib.rs:533-547)
+ * through the `.bai` beside the file (<path>.bai or <path minus .bam>.bai): only the blocks from the
+ * first candidate chunk of the overlapping bins on are read and inflated, reading stops at the first
+ * record past the interval; the records whose alignment [pos, bam_endpos) overlaps [start, end)
+ * (0-based, half-open) replace the columns of `tid`.  Without an index: CNVB_ERR_INVALID ("Could not
+ * open BAI-indexed BAM file", lib.rs:531-532). */
+int cnvb_bam_fetch(cnvb_bam *bam, uint32_t tid, uint32_t start, uint32_t end, float min_unclipped, int pinned);
 int cnvb_bam_ref_reads(const cnvb_bam *b, uint32_t tid, cnvb_read_soa *out);
 /* counts: records decoded | records without reference | compressed bytes | uncompressed bytes;
  * seconds: whole decode | inflate phases | record walk + SoA derivation (wall clock). */

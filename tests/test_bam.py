@@ -264,3 +264,38 @@ def test_bam_decode_property_random_records(tmp_path):
                     assert len(r.fetch(tid)) == 0
 
     run()
+
+
+@pytest.mark.parametrize("block_payload,threads", [(0xff00, 4), (1500, 2)])
+def test_bam_indexed_fetch_equals_full_decode(tmp_path, block_payload, threads, monkeypatch):
+    """cnvb_bam_fetch (bam::IndexedReader::fetch through the .bai, lib-coverage/src/lib.rs:533-543): for random
+    intervals the records are exactly those the whole-file decode selects by overlap, in file order; only a part of
+    the file is inflated.  Small BGZF blocks and small read chunks put records across every kind of seam."""
+    if block_payload < 0xff00:
+        monkeypatch.setenv("CNVB_BAM_CHUNK", "4096")
+    rng = np.random.default_rng(7)
+    contigs = [("chr1", 400_000), ("chr2", 250_000), ("chrE", 90_000), ("chr3", 120_000)]
+    recs = {0: synth.synth_bam_records(11, 400_000, 20_000), 1: synth.synth_bam_records(12, 250_000, 9_000),
+            3: synth.synth_bam_records(13, 120_000, 3_000), -1: synth.synth_bam_records(14, 1000, 50)}
+    path = synth.write_bam(str(tmp_path / "x.bam"), contigs, recs, block_payload=block_payload, index=True, read_len=20)
+    with bam.BamReader(path, threads=threads) as full, bam.BamReader(path, threads=threads) as ix:
+        assert ix.has_index()
+        full.decode(min_unclipped=0.6, pinned=False)
+        whole = full.stats()["compressed_bytes"]
+        for tid, L in ((0, 400_000), (1, 250_000), (3, 120_000), (2, 90_000)):
+            cases = [(0, L), (0, 1), (L - 1, L), (16384, 16385), (16383, 16384), (5, 5)]
+            cases += [tuple(sorted(rng.integers(0, L, 2).tolist())) for _ in range(12)]
+            for a, b in cases:
+                want = full.fetch(tid, a, b)
+                got = ix.fetch_indexed(tid, a, b, min_unclipped=0.6)
+                assert len(got) == len(want), (tid, a, b, len(got), len(want))
+                for k in ("pos", "end", "mid", "frag_end", "mapq", "flags"):
+                    assert np.array_equal(np.asarray(getattr(got, k)), np.asarray(getattr(want, k))), (tid, a, b, k)
+                if b - a < L // 20 and len(want) and block_payload < 0xff00:
+                    assert ix.stats()["compressed_bytes"] < whole // 3, (tid, a, b)   # a seek, not a scan
+    # no index: the reference cannot open the file either (lib.rs:531-532)
+    plain = synth.write_bam(str(tmp_path / "noidx.bam"), contigs, recs)
+    with bam.BamReader(plain) as r:
+        assert not r.has_index()
+        with pytest.raises(bam.BamError, match="BAI-indexed"):
+            r.fetch_indexed(0, 0, 100)

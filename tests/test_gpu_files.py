@@ -154,3 +154,32 @@ def test_merge_cov_pairs_records_by_position(tmp_path):
     os.remove(pb + ".csi")
     with pytest.raises(N.CnvbError, match="index missing"):
         commands.cmd_merge_cov([pa, pb], out, ctx=ctx)
+
+
+def test_cmd_coverage_genome_region_through_the_index(tmp_path, oracle):
+    """`--genome-region chr:a-b` (lib-coverage/src/lib.rs:707-711): one region (chr, a - 1, b), the reads fetched
+    through the .bai, windows counted from 0 to b -- against the oracle on the records htslib's fetch yields."""
+    ctx = cb.Context(0)
+    L = 400_000
+    d = synth.synth_bam_records(77, L, 30_000)
+    path = synth.write_bam(str(tmp_path / "r.bam"), [("chr1", L), ("chr2", 1000)], [d, None], sample="R", index=True)
+    a, b = 100_000, 200_300
+    end, _, _, _ = cb.pack_reads(d["pos"], d["isize"], d["flag"], d["cigar_off"], d["cigar"], 0.6)
+    keep = np.flatnonzero((d["pos"] < b) & (end > a))
+    coff = np.asarray(d["cigar_off"], np.int64)
+    ncig = (coff[1:] - coff[:-1])[keep]
+    sub = dict(pos=d["pos"][keep], isize=d["isize"][keep], flag=d["flag"][keep], mapq=d["mapq"][keep],
+               cigar_off=np.concatenate([[0], np.cumsum(ncig)]).astype(np.uint64),
+               cigar=np.concatenate([d["cigar"][coff[i]:coff[i + 1]] for i in keep]))
+    opts = cb.CoverageOptions(window_length=1000, count_kind="Coverage", min_mapq=10)
+    out = str(tmp_path / "region.bcf")
+    table, timings = commands.cmd_coverage(path, out, opts, genome_region="chr1:100,001-200_300", ctx=ctx)
+    mean, sd = oracle.coverage(oracle_reads(oracle, sub), oracle.cov_opts(window_length=1000, min_mapq=10), b)[:2]
+    with files.VariantFile(out) as vf:
+        assert vf.n == 201 and vf.contigs == [("chr1", L)]
+        assert_f32_equal_bits(vf.format_float("RCV")[0][:, 0], mean, "window means")
+        np.testing.assert_allclose(vf.format_float("RCVSD")[0][:, 0], sd, rtol=1e-6)
+        assert vf.fixed()["end"][-1] == b                      # the last window ends at the region end
+    assert mean[:99].sum() == 0 and mean[101:200].min() > 0    # nothing before the interval was fetched
+    with pytest.raises(N.CnvbError, match="not exactly one ':'"):
+        commands.cmd_coverage(path, out, opts, genome_region="chr1", ctx=ctx)
