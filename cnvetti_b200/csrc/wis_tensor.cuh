@@ -400,6 +400,11 @@ struct SweepArgs {
     uint32_t *cand_cnt;      // [rows]
     uint32_t dbg;            // CNVB_WIS_DBG (timing experiments only; results are wrong): 1 skip the epilogue's
                              // TMEM reads and tests, 2 skip the MMAs
+    // S <= 128, rounds >= 1: the round's work cut into items of at most `piece` tiles (wis_split_kernel) -- a CTA
+    // takes item blockIdx.x = (row block, tiles [g0, g1) of its concatenated ranges) instead of a whole block;
+    // several CTAs may then append to the same rows, so the slots come from the global per-row counters
+    const uint4 *items;      // nullptr: one CTA per row block
+    const uint32_t *n_items;
 };
 
 // STREAM: more than kMaxKBlocks K-blocks (S > 128): the A operand does not fit beside the B ring, so
@@ -424,10 +429,20 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     static_assert(!XPOSE || !FIRST, "the transposed tile exists for the later rounds");
     static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
     const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
-    const uint32_t blk = blockIdx.x / CL;
+    constexpr bool ITEMS_OK = !FIRST && !STREAM && CL == 1 && !XPOSE;
+    const bool split = ITEMS_OK && a.items != nullptr;
+    uint32_t blk = blockIdx.x / CL, g_off = 0u, g_end = 0xffffffffu;
+    if (split) {
+        if (blockIdx.x >= *a.n_items) return;
+        const uint4 item = a.items[blockIdx.x];
+        blk = item.x;
+        g_off = item.y;
+        g_end = item.z;
+    }
     // this block's share of the round: two tile ranges either side of what it has swept before
     const uint4 rng = a.rng[blk];
-    const uint32_t n_lo = rng.y - rng.x, n_all = n_lo + (rng.w - rng.z);
+    const uint32_t n_lo = rng.y - rng.x, n_blk = n_lo + (rng.w - rng.z);
+    const uint32_t n_all = split ? min(g_end, n_blk) - min(g_off, n_blk) : n_blk;
     if (n_all == 0) return;  // (both CTAs of a cluster)
     // CLUSTER: tile i of this CTA is tile 2 i + rank of the block; both CTAs make `steps` passes through the
     // operand ring (the second one without a tile of its own in the last pass when the count is odd)
@@ -435,7 +450,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t steps = (n_all + CL - 1u) / CL;
     const uint32_t rng_x = rng.x, rng_z = rng.z;
 #define CNVB_TILE_G(g) ((g) < n_lo ? rng_x + (g) : rng_z + ((g) - n_lo))
-#define CNVB_TILE_AT(it) CNVB_TILE_G((uint32_t)CL * (it) + crank)
+#define CNVB_TILE_AT(it) CNVB_TILE_G(g_off + (uint32_t)CL * (it) + crank)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
@@ -454,7 +469,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blk * kTileRows;  // position in the sorted row list
-    if (!CLUSTER && !XPOSE)
+    if (!CLUSTER && !XPOSE && !split)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
     if (XPOSE)  // row operands (projection, theta, kappa): constant for the whole launch, read back as broadcasts
@@ -855,8 +870,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const float v = CNVB_VAL(c);
                                 const uint32_t j = j0 + c;
                                 if (v <= rhs && j < a.T) {  // (same-contig pairs are dropped by the compaction)
-                                    const uint32_t slot =  // 4 warps (CLUSTER: of two CTAs) share a row
-                                        CLUSTER ? atomicAdd(&a.cand_cnt[row], 1u) : atomicAdd(&s_cnt[rloc[h]], 1u);
+                                    const uint32_t slot =  // 4 warps (CLUSTER / split items: of several CTAs) share a row
+                                        (CLUSTER || split) ? atomicAdd(&a.cand_cnt[row], 1u) : atomicAdd(&s_cnt[rloc[h]], 1u);
                                     if (slot < kCandCap) {  // beyond: overflow, the row falls back
                                         cv[slot] = v;
                                         ci[slot] = j;
@@ -879,7 +894,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (!CLUSTER && !XPOSE)
+    if (!CLUSTER && !XPOSE && !split)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
     if (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still send to it
@@ -1126,6 +1141,23 @@ __global__ void wis_items_kernel(const uint4 *__restrict__ rng, uint32_t row_blo
     const uint4 r = rng[i >> 1];
     key[i] = (i & 1u) ? r.w - r.z : r.y - r.x;
     item[i] = i;
+}
+
+// work items of a round for the resident sweep: every row block's tiles [0, n) in pieces of at most `piece`;
+// item = (row block, first tile, end tile, -) in the block's concatenated tile list.  Slots are reserved with
+// one atomic per block, so the order of the items is arbitrary -- the pieces are (nearly) equal, and the
+// hardware hands CTAs to SMs as they free up.
+__global__ void wis_split_kernel(const uint4 *__restrict__ rng, uint32_t row_blocks, uint32_t piece, uint32_t cap,
+                                 uint4 *__restrict__ items, uint32_t *__restrict__ n_items) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= row_blocks) return;
+    const uint4 r = rng[b];
+    const uint32_t n = (r.y - r.x) + (r.w - r.z);
+    if (n == 0) return;
+    const uint32_t pieces = (n + piece - 1u) / piece;
+    const uint32_t at = atomicAdd(n_items, pieces);
+    for (uint32_t p = 0; p < pieces && at + p < cap; ++p)
+        items[at + p] = make_uint4(b, p * piece, min(n, (p + 1u) * piece), 0u);
 }
 
 // ---- windows: which column tiles a block of rows still has to see --------------------------------
@@ -1579,6 +1611,11 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     void *cub_tmp = nullptr;
     size_t sort_bytes = 0, sel_bytes = 0, item_bytes = 0;
     uint32_t *item_key = nullptr, *item_key_sorted = nullptr, *item_id = nullptr, *item_order = nullptr;
+    // split work items of the resident sweep: at most one piece per block beyond total / piece
+    const uint32_t kItemTarget = 8u * (uint32_t)ctx->sm_count;   // pieces per round aimed at (8 per SM)
+    const uint32_t items_cap = row_blocks + kItemTarget + 64u;
+    uint4 *items = nullptr;
+    uint32_t *n_items = nullptr;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, ctx->stream);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, item_bytes, item_key, item_key_sorted, item_id, item_order,
                                               (int)(2 * row_blocks), 0, 32, ctx->stream);
@@ -1603,7 +1640,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(4, &counters)) != cudaSuccess || (e = g.alloc(S, &cmean)) != cudaSuccess ||
         (e = g.alloc(Tpad, &meta)) != cudaSuccess || (e = g.alloc(2 * row_blocks, &item_key)) != cudaSuccess ||
         (e = g.alloc(2 * row_blocks, &item_key_sorted)) != cudaSuccess || (e = g.alloc(2 * row_blocks, &item_id)) != cudaSuccess ||
-        (e = g.alloc(2 * row_blocks, &item_order)) != cudaSuccess ||
+        (e = g.alloc(2 * row_blocks, &item_order)) != cudaSuccess || (e = g.alloc(items_cap, &items)) != cudaSuccess ||
+        (e = g.alloc(4, &n_items)) != cudaSuccess ||
         (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
@@ -1751,9 +1789,17 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         const char *e = getenv("CNVB_WIS_DBG");
         sa.dbg = e ? (uint32_t)atoi(e) : 0u;
     }
+    // resident sweep, rounds >= 1: split work items behind CNVB_WIS_SPLIT = 1 (default: one CTA per row block, as
+    // the first round).  Measured at config 3: sweep 7.2 ms against 4.0 ms -- every piece reloads the resident row
+    // operand and its appends go through the global per-row counters; kept under test, off by default
+    const bool split_items = !stream_a && !xp_small && !n256 && [] {
+        const char *e = getenv("CNVB_WIS_SPLIT");
+        return e && atoi(e) == 1;
+    }();
+    uint32_t grid_items = 0;  // > 0: the next launch takes this many items
     auto launch_sweep = [&](decltype(sweep_first) kern) -> cudaError_t {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)cl * row_blocks);
+        cfg.gridDim = dim3(grid_items ? grid_items : (unsigned)cl * row_blocks);
         cfg.blockDim = dim3(kSweepThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
@@ -1832,6 +1878,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         CNVB_CUDA(ctx, cudaMemcpyAsync(&tiles_now, counters, 8, cudaMemcpyDeviceToHost, st), "reading the round size");
         CNVB_CUDA(ctx, cudaStreamSynchronize(st), "reading the round size");
         if (tiles_now == tiles_before && round > 1) break;
+        const unsigned long long tiles_prev_round = tiles_before;
         tiles_before = tiles_now;
         if (n256) {
             wis_items_kernel<<<(2 * row_blocks + 255) / 256, 256, 0, st>>>(rng, row_blocks, item_key, item_id);
@@ -1846,11 +1893,26 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
             }
             CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         } else {
+            if (split_items) {
+                // pieces of (nearly) equal size, about eight per SM: the launch is then balanced by the hardware's
+                // own dispatch instead of 5.3 waves of row blocks whose windows differ by a factor of several
+                const unsigned long long round_tiles = tiles_now - tiles_prev_round;
+                const uint32_t piece = (uint32_t)std::max<unsigned long long>(8, (round_tiles + kItemTarget - 1) / kItemTarget);
+                CNVB_CUDA(ctx, cudaMemsetAsync(n_items, 0, 4, st), "clearing the item counter");
+                wis_split_kernel<<<(row_blocks + 255) / 256, 256, 0, st>>>(rng, row_blocks, piece, items_cap, items, n_items);
+                CNVB_LAUNCHED(ctx, "wis_split_kernel");
+                sa.items = items;
+                sa.n_items = n_items;
+                grid_items = (uint32_t)std::min<unsigned long long>(items_cap, row_blocks + round_tiles / piece + 1);
+            }
             {
                 KernelSpan span(ctx, "wis_sweep_kernel");
                 CNVB_CUDA(ctx, launch_sweep(sweep_next), "launching the sweep");
             }
             CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
+            sa.items = nullptr;
+            sa.n_items = nullptr;
+            grid_items = 0;
         }
         {
             KernelSpan span(ctx, "wis_compact_kernel");

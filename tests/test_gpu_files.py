@@ -176,7 +176,7 @@ def test_cmd_coverage_genome_region_through_the_index(tmp_path, oracle):
     table, timings = commands.cmd_coverage(path, out, opts, genome_region="chr1:100,001-200_300", ctx=ctx)
     mean, sd = oracle.coverage(oracle_reads(oracle, sub), oracle.cov_opts(window_length=1000, min_mapq=10), b)[:2]
     with files.VariantFile(out) as vf:
-        assert vf.n == 201 and vf.contigs == [("chr1", L)]
+        assert vf.n == 201 and vf.contigs == [("chr1", L), ("chr2", 1000)]
         assert_f32_equal_bits(vf.format_float("RCV")[0][:, 0], mean, "window means")
         np.testing.assert_allclose(vf.format_float("RCVSD")[0][:, 0], sd, rtol=1e-6)
         assert vf.fixed()["end"][-1] == b                      # the last window ends at the region end

@@ -262,10 +262,12 @@ def test_wis_streamed_sweep_variants(oracle, ctx, monkeypatch, cluster, xpose):
     assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
 
 
-def test_wis_resident_sweep_n256_variant(oracle, ctx, monkeypatch):
-    """S <= 128: the M128 x N256 double-tile form of the later rounds (CNVB_WIS_N256 = 1; off by default,
-    it measured slower than the N128 form at config 3) still selects the oracle's sets, bit for bit."""
-    monkeypatch.setenv("CNVB_WIS_N256", "1")
+@pytest.mark.parametrize("env", [("CNVB_WIS_N256", "1"), ("CNVB_WIS_SPLIT", "1")])
+def test_wis_resident_sweep_variants(oracle, ctx, monkeypatch, env):
+    """S <= 128, the forms of the later rounds the defaults do not pick: the M128 x N256 double-tile kernel
+    (CNVB_WIS_N256 = 1; it measured slower than the N128 form at config 3) and split work items instead of one CTA per row
+    block (CNVB_WIS_SPLIT = 1; slower too: 7.2 against 4.0 ms) -- both select the oracle's sets, bit for bit."""
+    monkeypatch.setenv(*env)
     T, S, k = 6100, 100, 40
     X, tids = synth.synth_panel(911, T, S, n_contigs=6)
     X[40] = X[41]
