@@ -57,7 +57,7 @@ constexpr uint32_t kStages = 8;       // B ring: 8 x 16 KB
 constexpr uint32_t kTileBytes = 128 * kKBlock * 2;  // 16 KB: 128 rows x 64 fp16
 constexpr uint32_t kCandCap = 2048;   // candidate buffer entries per row
 constexpr uint32_t kMaxTensorS = 4096;  // samples (K dimension) the tensor engine takes
-constexpr uint32_t kMaxTensorK = 384;  // 32 x 16 first-window candidates must hold k after same-contig drops
+constexpr uint32_t kMaxTensorK = 384;  // 32 x 24 first-window candidates must hold k after same-contig drops
 constexpr uint32_t kEpiWarps = 16;     // 4 per TMEM lane quarter, each a quarter of the tile's columns
 constexpr uint32_t kSweepThreads = (4 + kEpiWarps) * 32;
 
@@ -242,7 +242,7 @@ __global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__r
                                 const uint32_t *__restrict__ perm, const uint32_t *__restrict__ pkey_sorted,
                                 __half *__restrict__ H, float *__restrict__ nrm, float *__restrict__ delta,
                                 uint32_t *__restrict__ tid_sorted, float *__restrict__ psorted,
-                                float *__restrict__ maxes, int ortho) {
+                                float *__restrict__ maxes, int ortho, __half *__restrict__ HR) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (warp >= T) return;
     const uint32_t src = perm[warp];
@@ -264,6 +264,8 @@ __global__ void wis_pack_kernel(const float *__restrict__ X, const uint32_t *__r
             e += r * r;
         }
         H[(size_t)warp * Kp + s] = h;
+        // resident sweep: the rows' operand, -2 h (exact: |h| < 2^11) and the three fold entries behind the samples
+        if (HR) HR[(size_t)warp * Kp + s] = s < S ? __float2half_rn(-2.0f * __half2float(h)) : __float2half_rn(s < S + 3u ? 32768.0f : 0.0f);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -398,13 +400,14 @@ struct SweepArgs {
     float *cand_val;         // [rows][kCandCap]
     uint32_t *cand_idx;
     uint32_t *cand_cnt;      // [rows]
-    uint32_t dbg;            // CNVB_WIS_DBG (timing experiments only; results are wrong): 1 skip the epilogue's
-                             // TMEM reads and tests, 2 skip the MMAs
+    uint32_t dbg;            // CNVB_WIS_DBG (timing experiments only; results are wrong), bits: 1 skip the epilogue's
+                             // TMEM reads and tests, 2 skip the MMAs, 4 skip the append's stores, 8 skip the appends
     // S <= 128, rounds >= 1: the round's work cut into items of at most `piece` tiles (wis_split_kernel) -- a CTA
     // takes item blockIdx.x = (row block, tiles [g0, g1) of its concatenated ranges) instead of a whole block;
     // several CTAs may then append to the same rows, so the slots come from the global per-row counters
     const uint4 *items;      // nullptr: one CTA per row block
     const uint32_t *n_items;
+    const __half *HA;        // resident sweep (wis_resident.cuh): the rows' operand (-2 h | C, C, C), [Tpad][128], sorted order
 };
 
 // STREAM: more than kMaxKBlocks K-blocks (S > 128): the A operand does not fit beside the B ring, so
@@ -430,6 +433,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
     const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
     constexpr bool ITEMS_OK = !FIRST && !STREAM && CL == 1 && !XPOSE;
+    constexpr bool XP_OWN = XPOSE && CL == 1;  // transposed tiles, one CTA per row block: the rows' counters live in shared memory
     const bool split = ITEMS_OK && a.items != nullptr;
     uint32_t blk = blockIdx.x / CL, g_off = 0u, g_end = 0xffffffffu;
     if (split) {
@@ -469,7 +473,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blk * kTileRows;  // position in the sorted row list
-    if (!CLUSTER && !XPOSE && !split)
+    if ((!CLUSTER && !XPOSE && !split) || XP_OWN)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
     if (XPOSE)  // row operands (projection, theta, kappa): constant for the whole launch, read back as broadcasts
@@ -613,8 +617,19 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const uint32_t d_tmem = tmem_base + as * kTileRows;
 #pragma unroll
                                 for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                                    if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                    if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
                                         tc_mma_f16(d_tmem, bdesc + 2u * kk, adesc[0][kb] + 2u * kk, kIdescX, (kb | kk) != 0u);
+                                }
+                            } else {
+                            if (a.dbg & 16u) {  // (experiment: the two accumulators alternate MMA by MMA)
+#pragma unroll
+                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+#pragma unroll
+                                    for (uint32_t h = 0; h < 2; ++h) {
+                                        const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
+                                        if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
+                                            tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
+                                    }
                                 }
                             } else {
 #pragma unroll
@@ -625,6 +640,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
                                         tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
                                 }
+                            }
                             }
                             }
                             tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
@@ -675,6 +691,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t r0 = cpart * 64u + (uint32_t)h * 32u;  // first row of this batch within the block
+                    if (a.dbg & 1u) continue;
                     uint32_t r[32];
                     tc_ld32(tmem_base + ((q * 32u) << 16) + as * kTileRows + r0, r);
                     uint32_t gmask = 0u;
@@ -690,19 +707,28 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         r[c + 1] = __float_as_uint(v1);
                         gmask |= (v0 <= two.y || v1 <= two.w) ? (1u << (c >> 2)) : 0u;
                     }
-                    const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+                    const uint32_t wmask = (a.dbg & 8u) ? 0u : __reduce_or_sync(0xffffffffu, gmask);
                     if (wmask) {  // survivors are rare: the append code runs only for row groups in which some column passes
 #pragma unroll
                         for (int g4 = 0; g4 < 8; ++g4) {
                             if (wmask & (1u << g4)) {
 #pragma unroll
                                 for (int e4 = 0; e4 < 4; ++e4) {
+                                    // one row, this warp's 32 columns: the lanes that pass take consecutive slots
+                                    // (ONE counter update per warp and row, the stores of a row coalesce)
                                     const int c = 4 * g4 + e4;
                                     const float v = __uint_as_float(r[c]);
-                                    if (v <= s_rq[e][32 * h + c].y && j < a.T) {  // (rows beyond the end: theta = -inf)
+                                    const bool pass = v <= s_rq[e][32 * h + c].y && j < a.T;  // (rows beyond the end: theta = -inf)
+                                    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                                    if (bal) {
                                         const uint32_t row = row0 + r0 + c;
-                                        const uint32_t slot = atomicAdd(&a.cand_cnt[row], 1u);
-                                        if (slot < kCandCap) {  // beyond: overflow, the row falls back
+                                        uint32_t base = 0u;
+                                        if (lane == 0)
+                                            base = XP_OWN ? atomicAdd(&s_cnt[r0 + c], (uint32_t)__popc(bal))
+                                                          : atomicAdd(&a.cand_cnt[row], (uint32_t)__popc(bal));
+                                        base = __shfl_sync(0xffffffffu, base, 0);
+                                        const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                                        if (pass && slot < kCandCap && !(a.dbg & 4u)) {  // beyond: overflow, the row falls back
                                             a.cand_val[(size_t)row * kCandCap + slot] = v;
                                             a.cand_idx[(size_t)row * kCandCap + slot] = j;
                                         }
@@ -787,6 +813,13 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (a.dbg & 1u) continue;
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((q * 32u) << 16) + (as * 2 + h) * kTileCols + cpart * 32u, r);
+                if (h == 1) {
+                    // the tile's values are in registers: the accumulator stage goes back to the MMA issuer now,
+                    // not after the tests and appends of this half
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+                }
                 if (STREAM) {
                     // ortho mode: r[c] <- n'_j - 2 g + (q_j - q_i)^2.  The difference is rounded towards zero
                     // and the FMA down, so the value never exceeds the exact one: a column that passes the
@@ -804,87 +837,103 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         r[4 * g4 + 3] = __float_as_uint(__fmaf_rd(d3, d3, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nv.w)));
                     }
                 }
-                // the value of column c under test: already formed in ortho mode
-#define CNVB_VAL(c) (STREAM ? __uint_as_float(r[c]) : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]))
+                // the values under test, v_c = n'_j - 2 g (already formed in ortho mode)
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    v[c] = STREAM ? __uint_as_float(r[c]) : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                const uint32_t row = row0 + rloc[h];
+                float *cv = a.cand_val + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
+                uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
+                const float inf = __int_as_float(0x7f800000);
+                if (FIRST) {  // (same-contig columns are no candidates)
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = tj[c] == trow[h] ? inf : v[c];
+                }
+                // minima of every four columns (FMNMX3 + FMNMX each) and of the row's 32 values
+                float gm[8];
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4)
+                    gm[g4] = fminf(fminf(v[4 * g4], v[4 * g4 + 1]), fminf(v[4 * g4 + 2], v[4 * g4 + 3]));
+                const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
                 if (FIRST) {
-                    // First window, no bound yet: store only the 8 smallest values of this row's 32
-                    // columns (same-contig columns excluded).  The k-th smallest upper bound among the
-                    // stored ones is a valid -- and nearly exact -- first bound; the lists are thrown
-                    // away after it has been derived and the window is swept again with the bound.
-                    const float inf = __int_as_float(0x7f800000);
-                    float top[8];
+                    // First window, no bound yet: of every four columns the nearest one is stored -- 8 per row and
+                    // warp, 32 per row and tile.  ANY k distinct columns give a valid bound (the k-th smallest
+                    // upper bound among them); the lists are thrown away after it has been derived and the window
+                    // is swept again with the bound.  (Minima of larger groups over a wider window were tried --
+                    // one of 32 over 0.4 k tiles: the stored minima then come from tiles far away in projection,
+                    // where even the nearest column is far, and the bound is useless.)
+                    if (row < a.rows && m < inf) {
+                        uint32_t pick = 0u, have = 0u;
 #pragma unroll
-                    for (int t8 = 0; t8 < 8; ++t8) top[t8] = inf;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        float v = tj[c] == trow[h] ? inf : CNVB_VAL(c);
-#pragma unroll
-                        for (int t8 = 0; t8 < 8; ++t8) {  // sorted insertion
-                            const float lo = fminf(top[t8], v);
-                            v = fmaxf(top[t8], v);
-                            top[t8] = lo;
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const uint32_t w = v[4 * g4] == gm[g4] ? 0u : (v[4 * g4 + 1] == gm[g4] ? 1u : (v[4 * g4 + 2] == gm[g4] ? 2u : 3u));
+                            pick |= w << (2 * g4);
+                            have |= (gm[g4] < inf ? 1u : 0u) << g4;
                         }
-                    }
-                    const uint32_t row = row0 + rloc[h];
-                    float *cv = a.cand_val + (size_t)row * kCandCap;
-                    uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
-                    if (top[0] < inf && row < a.rows) {
+                        const uint32_t cnt = (uint32_t)__popc(have);
+                        uint32_t slot = CLUSTER ? atomicAdd(&a.cand_cnt[row], cnt) : atomicAdd(&s_cnt[rloc[h]], cnt);
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float v = CNVB_VAL(c);
-                            if (v <= top[7] && tj[c] != trow[h]) {
-                                const uint32_t slot = CLUSTER ? atomicAdd(&a.cand_cnt[row], 1u) : atomicAdd(&s_cnt[rloc[h]], 1u);
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            if (have & (1u << g4)) {
                                 if (slot < kCandCap) {
-                                    cv[slot] = v;
-                                    ci[slot] = j0 + c;
+                                    cv[slot] = gm[g4];
+                                    ci[slot] = j0 + 4u * g4 + ((pick >> (2 * g4)) & 3u);
                                 }
+                                ++slot;
                             }
                         }
                     }
                     continue;
                 }
-                // keep iff  n'_j - 2 g - kappa_i s_j <= theta_i;  sufficient: n'_j - 2 g <= theta_i + kappa_i smax
+                // keep iff  n'_j - 2 g - kappa_i s_j <= theta_i;  sufficient: n'_j - 2 g <= theta_i + kappa_i smax.
+                // Survivors are rare in the later rounds: the row's minimum decides, one vote per warp; the append
+                // code runs only where some row of the warp has a column that passes, and there only for the groups
+                // of four columns in which one does.
                 const float rhs = fmaf(kap[h], smax, thr[h]);
-                const uint32_t row = row0 + rloc[h];
-                float *cv = a.cand_val + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
-                uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
-                // Survivors are rare (a few per 1024 pairs).  All 32 compares are independent; groups of
-                // four columns fold into one predicate each, the eight group bits of all lanes are
-                // OR-reduced with one REDUX, and the append code runs (warp-uniformly) only for groups in
-                // which some row passes.
-                uint32_t gmask = 0u;
+                if (__any_sync(0xffffffffu, m <= rhs) && !(a.dbg & 8u)) {
+                    uint32_t gmask = 0u;
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    const bool p = CNVB_VAL(4 * g4 + 0) <= rhs || CNVB_VAL(4 * g4 + 1) <= rhs ||
-                                   CNVB_VAL(4 * g4 + 2) <= rhs || CNVB_VAL(4 * g4 + 3) <= rhs;
-                    gmask |= p ? (1u << g4) : 0u;
-                }
-                const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
-                if (wmask) {
+                    for (int g4 = 0; g4 < 8; ++g4) gmask |= gm[g4] <= rhs ? (1u << g4) : 0u;
+                    const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
+                    // (rows without a bound yet have rhs = +inf: the padding columns, n'_j = +inf, must not pass)
+                    const uint32_t valid = j0 + 32u <= a.T ? 0xFFFFFFFFu : (j0 < a.T ? (1u << (a.T - j0)) - 1u : 0u);
+                    uint32_t mask = 0u;
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        if (wmask & (1u << g4)) {  // (warp-uniform)
+#pragma unroll
+                            for (int e4 = 0; e4 < 4; ++e4) mask |= v[4 * g4 + e4] <= rhs ? (1u << (4 * g4 + e4)) : 0u;
+                        }
+                    }
+                    mask &= valid;
+                    // one counter update per row, warp and tile: the row's passing columns take consecutive slots
+                    const uint32_t cnt = (uint32_t)__popc(mask);
+                    uint32_t slot = 0u;
+                    if (cnt) slot = (CLUSTER || split) ? atomicAdd(&a.cand_cnt[row], cnt) : atomicAdd(&s_cnt[rloc[h]], cnt);
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4) {
                         if (wmask & (1u << g4)) {
 #pragma unroll
                             for (int e4 = 0; e4 < 4; ++e4) {
                                 const int c = 4 * g4 + e4;
-                                const float v = CNVB_VAL(c);
-                                const uint32_t j = j0 + c;
-                                if (v <= rhs && j < a.T) {  // (same-contig pairs are dropped by the compaction)
-                                    const uint32_t slot =  // 4 warps (CLUSTER / split items: of several CTAs) share a row
-                                        (CLUSTER || split) ? atomicAdd(&a.cand_cnt[row], 1u) : atomicAdd(&s_cnt[rloc[h]], 1u);
-                                    if (slot < kCandCap) {  // beyond: overflow, the row falls back
-                                        cv[slot] = v;
-                                        ci[slot] = j;
+                                if (mask & (1u << c)) {
+                                    if (slot < kCandCap && !(a.dbg & 4u)) {  // beyond: overflow, the row falls back
+                                        cv[slot] = v[c];
+                                        ci[slot] = j0 + (uint32_t)c;
                                     }
+                                    ++slot;
                                 }
                             }
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+            if (a.dbg & 1u) {  // (the halves were skipped: release the stage here)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+            }
             if (++as == 2) {
                 as = 0;
                 aph ^= 1u;
@@ -894,7 +943,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (!CLUSTER && !XPOSE && !split)
+    if ((!CLUSTER && !XPOSE && !split) || XP_OWN)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
     if (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still send to it
@@ -906,7 +955,6 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 #undef CNVB_TILE_AT
 #undef CNVB_TILE_G
-#undef CNVB_VAL
 
 // ---- sweep, S <= 128, rounds >= 1: M128 x N256 accumulators ------------------------------------------
 // The two M128 x N128 MMAs per K16 slab of the kernel above read 8 KB of shared-memory operands per
@@ -1536,6 +1584,10 @@ __global__ void wis_overflow_list_kernel(const uint32_t *__restrict__ overflow, 
     if (lane_id() == 0 && c) atomicAdd(n_rescored, (unsigned long long)c);
 }
 
+}  // namespace
+#include "wis_resident.cuh"
+namespace {
+
 // ---- host orchestration ------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1583,7 +1635,13 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
                          uint32_t row_begin, uint32_t row_end, float *d_dist, uint32_t *d_idx) {
     const uint32_t rows = row_end - row_begin;
     if (rows == 0) return 0;
-    const uint32_t Kp = ((S + kKBlock - 1) / kKBlock) * kKBlock;
+    // up to 125 samples: the resident sweep (rows in tensor memory, column norms folded into the contraction;
+    // wis_resident.cuh).  CNVB_WIS_RES = 0 selects the shared-memory form it replaced.
+    const bool res = S + 3u <= kResK && [] {
+        const char *e = getenv("CNVB_WIS_RES");
+        return !(e && atoi(e) == 0);
+    }();
+    const uint32_t Kp = res ? kResK : ((S + kKBlock - 1) / kKBlock) * kKBlock;
     if (Kp > kMaxTensorS)
         return fail(ctx, CNVB_ERR_INVALID, "tensor engine: more than %u samples; use the exact engine", kMaxTensorS);
     const bool stream_a = Kp > kMaxKBlocks * kKBlock;  // A no longer fits beside the B ring: stream both operands
@@ -1596,7 +1654,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     PoolGuard g(ctx);
     double *colsum = nullptr;
     float *scal = nullptr;  // [0] absmax | [1] rho | [2] max |p|
-    __half *H = nullptr, *HA = nullptr;
+    __half *H = nullptr, *HA = nullptr, *HR = nullptr;
     float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *vg = nullptr, *cand_val = nullptr,
           *nprime = nullptr, *snorm = nullptr, *tile_smax = nullptr, *psorted = nullptr;
     uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *seen = nullptr, *ovf_list = nullptr,
@@ -1645,7 +1703,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
-                   (e = g.alloc(1, &n_sel)) != cudaSuccess || (e = g.alloc((size_t)rows_pad * Kp, &HA)) != cudaSuccess))
+                   (e = g.alloc(1, &n_sel)) != cudaSuccess ||
+                   (!res && (e = g.alloc((size_t)rows_pad * Kp, &HA)) != cudaSuccess)))
+        return fail_cuda(ctx, e, "allocating the tensor engine's work space");
+    if (res && (e = g.alloc((size_t)Tpad * Kp, &HR)) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     cudaStream_t st = ctx->stream;
     cudaMemsetAsync(colsum, 0, S * sizeof(double), st);
@@ -1664,7 +1725,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     // |x - c| <= 2 absmax; map that to about 2^13 so that fp16 keeps 11 significant bits
     int ex = 0;
     frexpf(absmax > 0.0f ? 2.0f * absmax : 1.0f, &ex);
-    const float scale = ldexpf(1.0f, 13 - ex);
+    // (resident sweep: 2^11, so that the norms n'_j / 2^15 and the rows' -2 h stay inside the fp16 range)
+    const float scale = ldexpf(1.0f, (res ? 11 : 13) - ex);
     wis_cmean_kernel<<<(S + 127) / 128, 128, 0, st>>>(colsum, T, S, cmean);
     CNVB_LAUNCHED(ctx, "wis_cmean_kernel");
     // sort the targets by their projection on the all-ones direction
@@ -1675,16 +1737,23 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     ctx->launches += 1;
     if (Tpad > T) cudaMemsetAsync(H + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
     wis_pack_kernel<<<(T + 7) / 8, 256, 0, st>>>(dX, dtid, T, S, Kp, cmean, scale, perm, pkey_sorted, H, nrm, delta,
-                                                 tid_sorted, psorted, scal + 1, stream_a ? 1 : 0);
+                                                 tid_sorted, psorted, scal + 1, stream_a ? 1 : 0, HR);
     CNVB_LAUNCHED(ctx, "wis_pack_kernel");
     const double c_acc = (double)Kp / 8388608.0;  // fp32 accumulation of Kp exact products, truncating adds
-    const double c_rnd = 8.0 / 16777216.0;        // f32 rounding of norms and of the epilogue FFMAs
+    // f32 rounding of norms and of the epilogue FFMAs; resident sweep: the norm is an addend of the tensor
+    // accumulation (error up to c_acc n_j), carried by the same terms of the bounds
+    const double c_rnd = 8.0 / 16777216.0 + (res ? c_acc : 0.0);
     if (Tpad > T) cudaMemsetAsync(tid_sorted + T, 0xFF, (size_t)(Tpad - T) * 4, st);
     if (Tpad > T) cudaMemsetAsync(psorted + T, 0, (size_t)(Tpad - T) * 4, st);  // (n'_j = +inf there)
     wis_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nrm, delta, tid_sorted, T, Tpad, scal + 1, c_rnd, nprime, snorm, meta);
     CNVB_LAUNCHED(ctx, "wis_cols_kernel");
     wis_tile_smax_kernel<<<(n_tiles + 7) / 8, 256, 0, st>>>(snorm, n_tiles, tile_smax);
     CNVB_LAUNCHED(ctx, "wis_tile_smax_kernel");
+    if (res) {
+        if (Tpad > T) cudaMemsetAsync(HR + (size_t)T * Kp, 0, (size_t)(Tpad - T) * Kp * 2, st);
+        wis_fold_cols_kernel<<<(Tpad + 255) / 256, 256, 0, st>>>(nprime, T, Tpad, S, H);
+        CNVB_LAUNCHED(ctx, "wis_fold_cols_kernel");
+    }
     wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(thr, 0, rows, __builtin_inff());
     CNVB_LAUNCHED(ctx, "wis_fill_kernel");
     wis_fill_kernel<<<(rows + 255) / 256, 256, 0, st>>>(vg, 0, rows, __builtin_inff());
@@ -1696,8 +1765,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         CNVB_CUDA(ctx, cub::DeviceSelect::Flagged(cub_tmp, sel_bytes, cub::CountingInputIterator<uint32_t>(0), rflag, rows_a,
                                                   n_sel, (int)T, st), "selecting the rows");
         ctx->launches += 1;
-        wis_gather_rows_kernel<<<rows_pad, 64, 0, st>>>(H, Kp, rows_a, rows, rows_pad, HA);
-        CNVB_LAUNCHED(ctx, "wis_gather_rows_kernel");
+        if (!res) {
+            wis_gather_rows_kernel<<<rows_pad, 64, 0, st>>>(H, Kp, rows_a, rows, rows_pad, HA);
+            CNVB_LAUNCHED(ctx, "wis_gather_rows_kernel");
+        }
     }
     float pabs = 0.0f;
     CNVB_CUDA(ctx, cudaMemcpyAsync(&pabs, scal + 2, 4, cudaMemcpyDeviceToHost, st), "reading the projection range");
@@ -1705,13 +1776,13 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
 
     CUtensorMap tmap_b, tmap_a;
     CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b));
-    if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
+    if (subset && !res) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
     // S <= 128, rounds >= 1: double tiles of 256 columns on M128 x N256 accumulators (wis_sweep256_kernel) --
     // only with CNVB_WIS_N256 = 1: measured at 200 000 x 100 the sweeps take 7.3 ms against 4.1 ms for the
     // M128 x N128 form (gpurun_out/r2_wis_probe.txt: the longer per-item epilogue outweighs the halved
     // operand traffic), so the N128 form stays the default
-    const bool n256 = !stream_a && [] {
+    const bool n256 = !stream_a && !res && [] {
         const char *e = getenv("CNVB_WIS_N256");
         return e && atoi(e) == 1;
     }();
@@ -1743,7 +1814,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     }();
     const bool xp = stream_a && (xpose_env >= 0 ? xpose_env == 1 : T >= 1000000u);
     // the same layout for S <= 128 (resident row operand): CNVB_WIS_XPOSE_SMALL = 1, off unless asked for
-    const bool xp_small = !stream_a && [] {
+    const bool xp_small = !stream_a && !res && [] {
         const char *e = getenv("CNVB_WIS_XPOSE_SMALL");
         return e && atoi(e) == 1;
     }();
@@ -1780,7 +1851,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.rows = rows;
     sa.tid_sorted = tid_sorted;
     sa.rows_a = rows_a;
-    sa.k_mmas = (S + 15) / 16;
+    sa.k_mmas = ((res ? S + 3u : S) + 15) / 16;
+    sa.HA = HR;
     sa.n_kblocks = Kp / kKBlock;
     sa.cand_val = cand_val;
     sa.cand_idx = cand_idx;
@@ -1792,12 +1864,26 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     // resident sweep, rounds >= 1: split work items behind CNVB_WIS_SPLIT = 1 (default: one CTA per row block, as
     // the first round).  Measured at config 3: sweep 7.2 ms against 4.0 ms -- every piece reloads the resident row
     // operand and its appends go through the global per-row counters; kept under test, off by default
-    const bool split_items = !stream_a && !xp_small && !n256 && [] {
+    const bool split_items = !stream_a && !res && !xp_small && !n256 && [] {
         const char *e = getenv("CNVB_WIS_SPLIT");
         return e && atoi(e) == 1;
     }();
     uint32_t grid_items = 0;  // > 0: the next launch takes this many items
+    const size_t smem_res = (size_t)kResStages * kTileBytes + 512 + 1024;
+    if (res) {
+        CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_res_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res),
+                  "smem opt-in");
+        CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_res_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res),
+                  "smem opt-in");
+    }
     auto launch_sweep = [&](decltype(sweep_first) kern) -> cudaError_t {
+        if (res) {
+            if (kern == sweep_first)
+                wis_sweep_res_kernel<true><<<row_blocks, kSweepThreads, smem_res, st>>>(tmap_b, sa);
+            else
+                wis_sweep_res_kernel<false><<<row_blocks, kSweepThreads, smem_res, st>>>(tmap_b, sa);
+            return cudaGetLastError();
+        }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid_items ? grid_items : (unsigned)cl * row_blocks);
         cfg.blockDim = dim3(kSweepThreads);
@@ -1811,6 +1897,52 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, sa);
+    };
+    // CNVB_WIS_TRACE = 1 (diagnostics, stderr): per round the tiles swept, the candidates the sweep left in the
+    // buffers (before the compaction) and the time of the launch, each bracketed by a host synchronisation
+    const bool trace = [] {
+        const char *e = getenv("CNVB_WIS_TRACE");
+        return e && atoi(e) != 0;
+    }();
+    std::vector<uint32_t> trace_cnt;
+    cudaEvent_t tr_a = nullptr, tr_b = nullptr;
+    if (trace) {
+        cudaEventCreate(&tr_a);
+        cudaEventCreate(&tr_b);
+    }
+    auto trace_begin = [&]() {
+        if (trace) cudaEventRecord(tr_a, st);
+    };
+    auto trace_end = [&](const char *what, uint32_t round, unsigned long long tiles) {
+        if (!trace) return;
+        cudaEventRecord(tr_b, st);
+        cudaEventSynchronize(tr_b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, tr_a, tr_b);
+        trace_cnt.resize(rows);
+        cudaMemcpy(trace_cnt.data(), cand_cnt, (size_t)rows * 4, cudaMemcpyDeviceToHost);
+        unsigned long long sum = 0, mx = 0;
+        for (uint32_t c : trace_cnt) {
+            sum += c;
+            mx = std::max<unsigned long long>(mx, c);
+        }
+        fprintf(stderr, "[wis trace] round %u %-8s %8.3f ms  tiles %9llu  candidates in buffers %11llu (%.1f per row, max %llu)\n",
+                round, what, ms, tiles, sum, (double)sum / rows, mx);
+        if (tiles) {  // how the blocks' tile counts spread over the SMs when CTAs are dispatched in index order
+            std::vector<uint4> h_rng(row_blocks);
+            cudaMemcpy(h_rng.data(), rng, (size_t)row_blocks * sizeof(uint4), cudaMemcpyDeviceToHost);
+            std::vector<unsigned long long> sm((size_t)ctx->sm_count, 0ull);
+            unsigned long long big = 0, total = 0;
+            for (const uint4 &r4 : h_rng) {
+                const unsigned long long n = (r4.y - r4.x) + (r4.w - r4.z);
+                big = std::max(big, n);
+                total += n;
+                *std::min_element(sm.begin(), sm.end()) += n;
+            }
+            const unsigned long long span = *std::max_element(sm.begin(), sm.end());
+            fprintf(stderr, "[wis trace]          blocks %u, largest %llu tiles, in-order makespan %llu tiles = %.2f x the mean per SM\n",
+                    row_blocks, big, span, (double)span * ctx->sm_count / std::max<unsigned long long>(total, 1));
+        }
     };
     CompactArgs ca{};
     ca.cand_val = cand_val;
@@ -1835,9 +1967,11 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     wa.T = T;
     wa.n_tiles = n_tiles;
     wa.rows = rows;
-    // first window: 2 (1 + w0) tiles; every (tile, column quarter) group stores its 8 smallest values,
-    // so 32 x tiles candidates per row, of which at least k must remain after the same-contig ones
-    wa.w0 = std::min<uint32_t>(7, std::max<uint32_t>(2, (5 * k / 4 + 63) / 64 - 1));
+    // first window: 2 (1 + w0) tiles; every (tile, column quarter) group stores the nearest of each four columns,
+    // so 32 x tiles candidates per row, of which at least k must remain after the same-contig ones.  The window
+    // is sized for 3.2 k candidates: the k-th smallest of them is then about the 9 % quantile of the window's
+    // distances
+    wa.w0 = std::min<uint32_t>(11, std::max<uint32_t>(2, (16 * k / 5 + 63) / 64 - 1));
     const uint32_t tiles0 = std::min<uint32_t>(n_tiles, 2 * (1 + wa.w0));
     // f32 rounding of the projections (2 x half an ulp of the largest) plus their f64 summation error
     wa.slack = pabs * (1.0f / 4194304.0f) + 1e-30f;
@@ -1854,13 +1988,17 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     if (32 * tiles0 >= 5 * k / 4) {
         {
             KernelSpan span(ctx, "wis_sweep_kernel");
+            trace_begin();
             CNVB_CUDA(ctx, launch_sweep(sweep_first), "launching the first sweep");
+            trace_end("sweep", 0, (unsigned long long)tiles0 * row_blocks);
         }
         CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
         ca.discard = 1;
         {
             KernelSpan span(ctx, "wis_compact_kernel");
+            trace_begin();
             wis_compact_kernel<<<(rows + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, st>>>(ca);
+            trace_end("compact", 0, 0);
         }
         CNVB_LAUNCHED(ctx, "wis_compact_kernel");
         ca.discard = 0;
@@ -1907,7 +2045,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
             }
             {
                 KernelSpan span(ctx, "wis_sweep_kernel");
+                trace_begin();
                 CNVB_CUDA(ctx, launch_sweep(sweep_next), "launching the sweep");
+                trace_end("sweep", round, tiles_now - tiles_prev_round);
             }
             CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
             sa.items = nullptr;
@@ -1916,7 +2056,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         }
         {
             KernelSpan span(ctx, "wis_compact_kernel");
+            trace_begin();
             wis_compact_kernel<<<(rows + kCompactWarps - 1) / kCompactWarps, kCompactWarps * 32, 0, st>>>(ca);
+            trace_end("compact", round, 0);
         }
         CNVB_LAUNCHED(ctx, "wis_compact_kernel");
         if (half_prev >= n_tiles) break;  // the last round was allowed to reach every tile

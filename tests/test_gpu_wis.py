@@ -262,7 +262,8 @@ def test_wis_streamed_sweep_variants(oracle, ctx, monkeypatch, cluster, xpose):
     assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
 
 
-@pytest.mark.parametrize("env", [("CNVB_WIS_N256", "1"), ("CNVB_WIS_SPLIT", "1")])
+@pytest.mark.parametrize("env", [("CNVB_WIS_N256", "1"), ("CNVB_WIS_SPLIT", "1"), ("CNVB_WIS_XPOSE_SMALL", "1"),
+                                 ("CNVB_WIS_XPOSE_SMALL", "0")])
 def test_wis_resident_sweep_variants(oracle, ctx, monkeypatch, env):
     """S <= 128, the forms of the later rounds the defaults do not pick: the M128 x N256 double-tile kernel
     (CNVB_WIS_N256 = 1; it measured slower than the N128 form at config 3) and split work items instead of one CTA per row
