@@ -268,8 +268,7 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
                 for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(r[c]);
                 const uint32_t rloc = (uint32_t)h * 128u + q * 32u + lane;
                 const uint32_t row = row0 + rloc;
-                float *cv = a.cand_val + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
-                uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
+                uint2 *cand = a.cand + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
                 if (FIRST) {  // (same-contig columns are no candidates)
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] = tj[c] == trow[h] ? inf : v[c];
@@ -301,8 +300,7 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
                         for (int g4 = 0; g4 < 8; ++g4) {
                             if (have & (1u << g4)) {
                                 if (slot < kCandCap) {
-                                    cv[slot] = gm[g4];
-                                    ci[slot] = j0 + 4u * g4 + ((pick >> (2 * g4)) & 3u);
+                                    cand[slot] = make_uint2(__float_as_uint(gm[g4]), j0 + 4u * g4 + ((pick >> (2 * g4)) & 3u));
                                 }
                                 ++slot;
                             }
@@ -341,8 +339,7 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
                                 const int c = 4 * g4 + e4;
                                 if (mask & (1u << c)) {
                                     if (slot < kCandCap && !(a.dbg & 4u)) {  // beyond: overflow, the row falls back
-                                        cv[slot] = v[c];
-                                        ci[slot] = j0 + (uint32_t)c;
+                                        cand[slot] = make_uint2(__float_as_uint(v[c]), j0 + (uint32_t)c);
                                     }
                                     ++slot;
                                 }

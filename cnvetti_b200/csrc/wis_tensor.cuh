@@ -397,16 +397,10 @@ struct SweepArgs {
     const uint32_t *rows_a;  // [rows] sorted position of every row (nullptr: identity)
     uint32_t k_mmas;         // K16 slabs per tile that hold data: ceil(S / 16)
     uint32_t n_kblocks;      // ceil(Kp / 64)
-    float *cand_val;         // [rows][kCandCap]
-    uint32_t *cand_idx;
+    uint2 *cand;             // [rows][kCandCap] (bits of v = n'_j - 2 g, sorted column position): one 8-byte store per candidate
     uint32_t *cand_cnt;      // [rows]
     uint32_t dbg;            // CNVB_WIS_DBG (timing experiments only; results are wrong), bits: 1 skip the epilogue's
                              // TMEM reads and tests, 2 skip the MMAs, 4 skip the append's stores, 8 skip the appends
-    // S <= 128, rounds >= 1: the round's work cut into items of at most `piece` tiles (wis_split_kernel) -- a CTA
-    // takes item blockIdx.x = (row block, tiles [g0, g1) of its concatenated ranges) instead of a whole block;
-    // several CTAs may then append to the same rows, so the slots come from the global per-row counters
-    const uint4 *items;      // nullptr: one CTA per row block
-    const uint32_t *n_items;
     const __half *HA;        // resident sweep (wis_resident.cuh): the rows' operand (-2 h | C, C, C), [Tpad][128], sorted order
 };
 
@@ -423,30 +417,20 @@ constexpr int kDefaultCluster = 2;      // CTAs per cluster of the streamed swee
 // refilled when BOTH consumers are done with it: the MMA issuers commit to the stage's empty barrier in
 // both CTAs (multicast commit), which therefore counts two arrivals.  Candidate slots come from the
 // global per-row counter (two CTAs append to the same rows).
-template <bool FIRST, bool STREAM, int CL, bool XPOSE>
+template <bool FIRST, int CL, bool XPOSE>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
+    constexpr bool STREAM = true;  // (the form with the rows' operand resident in shared memory gave way to wis_resident.cuh)
     constexpr bool CLUSTER = CL > 1;
     static_assert(CL == 1 || CL == 2 || CL == 4, "clusters of 2 or 4 CTAs");
     static_assert(!XPOSE || !FIRST, "the transposed tile exists for the later rounds");
-    static_assert(!CLUSTER || STREAM, "the cluster variant exists for the streamed sweep only");
     const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
-    constexpr bool ITEMS_OK = !FIRST && !STREAM && CL == 1 && !XPOSE;
     constexpr bool XP_OWN = XPOSE && CL == 1;  // transposed tiles, one CTA per row block: the rows' counters live in shared memory
-    const bool split = ITEMS_OK && a.items != nullptr;
-    uint32_t blk = blockIdx.x / CL, g_off = 0u, g_end = 0xffffffffu;
-    if (split) {
-        if (blockIdx.x >= *a.n_items) return;
-        const uint4 item = a.items[blockIdx.x];
-        blk = item.x;
-        g_off = item.y;
-        g_end = item.z;
-    }
+    const uint32_t blk = blockIdx.x / CL;
     // this block's share of the round: two tile ranges either side of what it has swept before
     const uint4 rng = a.rng[blk];
-    const uint32_t n_lo = rng.y - rng.x, n_blk = n_lo + (rng.w - rng.z);
-    const uint32_t n_all = split ? min(g_end, n_blk) - min(g_off, n_blk) : n_blk;
+    const uint32_t n_lo = rng.y - rng.x, n_all = n_lo + (rng.w - rng.z);
     if (n_all == 0) return;  // (both CTAs of a cluster)
     // CLUSTER: tile i of this CTA is tile 2 i + rank of the block; both CTAs make `steps` passes through the
     // operand ring (the second one without a tile of its own in the last pass when the count is odd)
@@ -454,7 +438,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t steps = (n_all + CL - 1u) / CL;
     const uint32_t rng_x = rng.x, rng_z = rng.z;
 #define CNVB_TILE_G(g) ((g) < n_lo ? rng_x + (g) : rng_z + ((g) - n_lo))
-#define CNVB_TILE_AT(it) CNVB_TILE_G(g_off + (uint32_t)CL * (it) + crank)
+#define CNVB_TILE_AT(it) CNVB_TILE_G((uint32_t)CL * (it) + crank)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
@@ -473,7 +457,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blk * kTileRows;  // position in the sorted row list
-    if ((!CLUSTER && !XPOSE && !split) || XP_OWN)
+    if ((!CLUSTER && !XPOSE) || XP_OWN)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
     if (XPOSE)  // row operands (projection, theta, kappa): constant for the whole launch, read back as broadcasts
@@ -729,8 +713,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                         base = __shfl_sync(0xffffffffu, base, 0);
                                         const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
                                         if (pass && slot < kCandCap && !(a.dbg & 4u)) {  // beyond: overflow, the row falls back
-                                            a.cand_val[(size_t)row * kCandCap + slot] = v;
-                                            a.cand_idx[(size_t)row * kCandCap + slot] = j;
+                                            a.cand[(size_t)row * kCandCap + slot] = make_uint2(__float_as_uint(v), j);
                                         }
                                     }
                                 }
@@ -843,8 +826,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int c = 0; c < 32; ++c)
                     v[c] = STREAM ? __uint_as_float(r[c]) : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
                 const uint32_t row = row0 + rloc[h];
-                float *cv = a.cand_val + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
-                uint32_t *ci = a.cand_idx + (size_t)row * kCandCap;
+                uint2 *cand = a.cand + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
                 const float inf = __int_as_float(0x7f800000);
                 if (FIRST) {  // (same-contig columns are no candidates)
 #pragma unroll
@@ -877,8 +859,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int g4 = 0; g4 < 8; ++g4) {
                             if (have & (1u << g4)) {
                                 if (slot < kCandCap) {
-                                    cv[slot] = gm[g4];
-                                    ci[slot] = j0 + 4u * g4 + ((pick >> (2 * g4)) & 3u);
+                                    cand[slot] = make_uint2(__float_as_uint(gm[g4]), j0 + 4u * g4 + ((pick >> (2 * g4)) & 3u));
                                 }
                                 ++slot;
                             }
@@ -910,7 +891,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     // one counter update per row, warp and tile: the row's passing columns take consecutive slots
                     const uint32_t cnt = (uint32_t)__popc(mask);
                     uint32_t slot = 0u;
-                    if (cnt) slot = (CLUSTER || split) ? atomicAdd(&a.cand_cnt[row], cnt) : atomicAdd(&s_cnt[rloc[h]], cnt);
+                    if (cnt) slot = CLUSTER ? atomicAdd(&a.cand_cnt[row], cnt) : atomicAdd(&s_cnt[rloc[h]], cnt);
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4) {
                         if (wmask & (1u << g4)) {
@@ -919,8 +900,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const int c = 4 * g4 + e4;
                                 if (mask & (1u << c)) {
                                     if (slot < kCandCap && !(a.dbg & 4u)) {  // beyond: overflow, the row falls back
-                                        cv[slot] = v[c];
-                                        ci[slot] = j0 + (uint32_t)c;
+                                        cand[slot] = make_uint2(__float_as_uint(v[c]), j0 + (uint32_t)c);
                                     }
                                     ++slot;
                                 }
@@ -943,7 +923,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if ((!CLUSTER && !XPOSE && !split) || XP_OWN)
+    if ((!CLUSTER && !XPOSE) || XP_OWN)
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
             if (row0 + t < a.rows) a.cand_cnt[row0 + t] = s_cnt[t];
     if (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still send to it
@@ -955,258 +935,6 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 #undef CNVB_TILE_AT
 #undef CNVB_TILE_G
-
-// ---- sweep, S <= 128, rounds >= 1: M128 x N256 accumulators ------------------------------------------
-// The two M128 x N128 MMAs per K16 slab of the kernel above read 8 KB of shared-memory operands per
-// 64-cycle issue slot -- the whole 128 B/clk of the SM, with TMA writes and L1 traffic on top: measured
-// 164 cycles per MMA.  Here a step takes a DOUBLE tile of 256 columns: per row half (128 rows on the M
-// axis) one M128 x N256 x K16 MMA per slab, 12 KB of operands per 128-cycle slot (96 B/clk).  TMEM holds
-// the two halves' accumulators (2 x 256 columns = all 512); they alternate -- while the 16 epilogue warps
-// read half h (128 KB at TMEM's 64 B/clk = 2048 cycles, the bound of this kernel: twice the 1024 cycles
-// of the MMAs), the tensor core computes half 1 - h.
-// Work items are (row block, side of its window) pairs, handed out in order of decreasing size
-// (`order`, sorted after the window kernel): the hardware dispatches CTAs in index order as SMs free up,
-// which makes the launch a longest-processing-time schedule instead of 5.3 uneven waves.
-constexpr uint32_t kDStages = 2;  // double tiles in flight: 2 x (n_kblocks x 32 KB)
-constexpr uint32_t kQueueCap = 96;  // survivors a warp holds back before it goes for their slots
-constexpr uint32_t kIdesc256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-
-__global__ void __launch_bounds__(kSweepThreads, 1)
-wis_sweep256_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b2,
-                    const SweepArgs a, const uint32_t *__restrict__ order) {
-    const uint32_t item = order[blockIdx.x];
-    const uint32_t blk = item >> 1, side = item & 1u;
-    const uint4 rng = a.rng[blk];
-    const uint32_t t_begin = side ? rng.z : rng.x, t_end = side ? rng.w : rng.y;  // 128-column tiles [t_begin, t_end)
-    if (t_end <= t_begin) return;
-    const uint32_t n_dt = (t_end - t_begin + 1u) >> 1;  // double tiles (the last may hold one tile only)
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_base = smem_base;                                  // [n_kblocks][2 halves] x 16 KB
-    const uint32_t stage_bytes = a.n_kblocks * 2u * kTileBytes;         // n_kblocks boxes of 64 x 256
-    const uint32_t b_base = a_base + 2u * a.n_kblocks * kTileBytes;
-    const uint32_t bar_base = b_base + kDStages * stage_bytes;
-    const uint32_t bar_a_full = bar_base;
-    const uint32_t bar_b_full = bar_base + 8;                  // kDStages
-    const uint32_t bar_b_empty = bar_b_full + 8 * kDStages;    // kDStages
-    const uint32_t bar_acc_full = bar_b_empty + 8 * kDStages;  // 2 (row halves)
-    const uint32_t bar_acc_empty = bar_acc_full + 16;          // 2
-    const uint32_t tmem_slot = bar_acc_empty + 16;
-    const uint32_t queue_base = (tmem_slot + 16u + 15u) & ~15u;  // kEpiWarps x kQueueCap x 16 B
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t row0 = blk * kTileRows;
-    if (warp == 0 && lane == 0) {
-        mbar_init(bar_a_full, 1);
-        for (uint32_t s = 0; s < kDStages; ++s) {
-            mbar_init(bar_b_full + 8 * s, 1);
-            mbar_init(bar_b_empty + 8 * s, 1);
-        }
-        for (uint32_t s = 0; s < 2; ++s) {
-            mbar_init(bar_acc_full + 8 * s, 1);
-            mbar_init(bar_acc_empty + 8 * s, kEpiWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
-            for (uint32_t h = 0; h < 2; ++h)
-                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
-                    tma_load_2d(a_base + (kb * 2u + h) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
-                                (int32_t)(row0 + h * 128));
-            uint32_t st = 0, ph = 0;
-            for (uint32_t it = 0; it < n_dt; ++it) {
-                const int32_t j0 = (int32_t)((t_begin + 2u * it) * kTileCols);
-                mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
-                mbar_expect_tx(bar_b_full + 8 * st, stage_bytes);
-                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)  // (rows beyond the panel arrive as zeros)
-                    tma_load_2d(b_base + st * stage_bytes + kb * 2u * kTileBytes, &tmap_b2, bar_b_full + 8 * st,
-                                (int32_t)(kb * kKBlock), j0);
-                if (++st == kDStages) {
-                    st = 0;
-                    ph ^= 1u;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            mbar_wait(bar_a_full, 0);
-            tc_fence_after();
-            uint32_t st = 0, ph = 0, aph = 0;
-            for (uint32_t it = 0; it < n_dt; ++it) {
-                mbar_wait(bar_b_full + 8 * st, ph);
-                tc_fence_after();
-#pragma unroll
-                for (uint32_t h = 0; h < 2; ++h) {
-                    mbar_wait(bar_acc_empty + 8 * h, aph ^ 1u);  // the epilogue has drained this half's last tile
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + h * 256u;
-                    for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
-                        const uint64_t ad = umma_desc(a_base + (kb * 2u + h) * kTileBytes);
-                        const uint64_t bd = umma_desc(b_base + st * stage_bytes + kb * 2u * kTileBytes);
-#pragma unroll
-                        for (uint32_t kk = 0; kk < kKBlock / 16; ++kk)
-                            if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
-                                tc_mma_f16(d_tmem, ad + 2u * kk, bd + 2u * kk, kIdesc256, (kb | kk) != 0u);
-                    }
-                    tc_commit(bar_acc_full + 8 * h);
-                }
-                tc_commit(bar_b_empty + 8 * st);  // frees the stage when both halves' MMAs have retired
-                aph ^= 1u;
-                if (++st == kDStages) {
-                    st = 0;
-                    ph ^= 1u;
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ===== epilogue: warp e reads TMEM lane quarter q = e & 3 (row h * 128 + 32 q + lane of the block) and
-        // the 64 columns [64 (e >> 2), +64) of the double tile, in two loads of 32.
-        // Survivors (a few per 1024 pairs, so nearly every load has some) do NOT go to their row's list at
-        // once: the slot comes from an atomic on the row's counter in HBM, and waiting for it inside the
-        // loop -- once per group of columns with a survivor -- cost more than everything else in this kernel
-        // (measured: 9700 of 11000 cycles per tile).  They are pushed to a queue of the warp in shared memory
-        // (positions from a ballot, no atomics) and the queue is emptied 32 entries at a time, one atomic per
-        // lane in flight together. =====
-        const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
-        uint4 *queue = reinterpret_cast<uint4 *>(smem_raw + (queue_base - smem_u32(smem_raw))) + e * kQueueCap;
-        uint32_t qn = 0;  // entries in the queue (warp-uniform)
-        auto flush = [&]() {
-            __syncwarp();
-            for (uint32_t i = lane; i < qn; i += 32) {
-                const uint4 en = queue[i];  // (row, column, value)
-                const uint32_t slot = atomicAdd(&a.cand_cnt[en.x], 1u);
-                if (slot < kCandCap) {  // beyond: overflow, the row falls back
-                    a.cand_val[(size_t)en.x * kCandCap + slot] = __uint_as_float(en.z);
-                    a.cand_idx[(size_t)en.x * kCandCap + slot] = en.y;
-                }
-            }
-            qn = 0;
-            __syncwarp();
-        };
-        float thr[2], kap[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint32_t row = row0 + h * 128 + q * 32 + lane;
-            const bool live = row < a.rows;
-            thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
-            kap[h] = live ? a.kap[row] : 0.0f;
-        }
-        uint32_t aph = 0;
-        for (uint32_t it = 0; it < n_dt; ++it) {
-            const uint32_t tile = t_begin + 2u * it + (cpart >> 1);  // the 128-column tile this warp's columns lie in
-            const bool wanted = tile < t_end;                        // (warp-uniform; false: the odd tile past the range)
-            const uint32_t j0 = tile * kTileCols + (cpart & 1u) * 64u;
-            const float smax = wanted ? __ldg(a.tile_smax + tile) : 0.0f;
-            if (it + 1 < n_dt) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + j0 + 2u * kTileCols));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                mbar_wait(bar_acc_full + 8 * h, aph);
-                tc_fence_after();
-                if (wanted && !(a.dbg & 1u)) {
-                    const float rhs = fmaf(kap[h], smax, thr[h]);  // keep iff n'_j - 2 g <= theta_i + kappa_i smax
-                    const uint32_t row = row0 + h * 128 + q * 32 + lane;
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float nj[32];
-                        const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0 + 32 * half);
-#pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4) {  // same addresses for all lanes: L1 broadcast
-                            const float4 v = __ldg(nj4 + g4);
-                            nj[4 * g4 + 0] = v.x;
-                            nj[4 * g4 + 1] = v.y;
-                            nj[4 * g4 + 2] = v.z;
-                            nj[4 * g4 + 3] = v.w;
-                        }
-                        uint32_t r[32];
-                        tc_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)h * 256u + cpart * 64u + 32u * half, r);
-                        uint32_t gmask = 0u;
-#pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4) {
-                            const bool p = fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nj[4 * g4 + 0]) <= rhs ||
-                                           fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nj[4 * g4 + 1]) <= rhs ||
-                                           fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nj[4 * g4 + 2]) <= rhs ||
-                                           fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nj[4 * g4 + 3]) <= rhs;
-                            gmask |= p ? (1u << g4) : 0u;
-                        }
-                        const uint32_t wmask = __reduce_or_sync(0xffffffffu, gmask);
-                        if (wmask) {  // the push code runs (warp-uniformly) only for groups in which some row passes
-#pragma unroll
-                            for (int g4 = 0; g4 < 8; ++g4) {
-                                if (wmask & (1u << g4)) {
-#pragma unroll
-                                    for (int e4 = 0; e4 < 4; ++e4) {
-                                        const int c = 4 * g4 + e4;
-                                        const float v = fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
-                                        const uint32_t j = j0 + 32 * half + c;
-                                        const bool keep = v <= rhs && j < a.T;  // (rows beyond the end: theta = -inf)
-                                        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-                                        if (m) {
-                                            if (qn + 32u > kQueueCap) flush();
-                                            if (keep) queue[qn + __popc(m & ((1u << lane) - 1u))] = make_uint4(row, j, __float_as_uint(v), 0u);
-                                            qn += __popc(m);
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * h);
-                if (qn >= 32u) flush();  // after the accumulator has been handed back: the tensor core does not wait for it
-            }
-            aph ^= 1u;
-        }
-        flush();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// work items of a round: (row block, side) with the number of tiles as sort key
-__global__ void wis_items_kernel(const uint4 *__restrict__ rng, uint32_t row_blocks, uint32_t *__restrict__ key,
-                                 uint32_t *__restrict__ item) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2u * row_blocks) return;
-    const uint4 r = rng[i >> 1];
-    key[i] = (i & 1u) ? r.w - r.z : r.y - r.x;
-    item[i] = i;
-}
-
-// work items of a round for the resident sweep: every row block's tiles [0, n) in pieces of at most `piece`;
-// item = (row block, first tile, end tile, -) in the block's concatenated tile list.  Slots are reserved with
-// one atomic per block, so the order of the items is arbitrary -- the pieces are (nearly) equal, and the
-// hardware hands CTAs to SMs as they free up.
-__global__ void wis_split_kernel(const uint4 *__restrict__ rng, uint32_t row_blocks, uint32_t piece, uint32_t cap,
-                                 uint4 *__restrict__ items, uint32_t *__restrict__ n_items) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= row_blocks) return;
-    const uint4 r = rng[b];
-    const uint32_t n = (r.y - r.x) + (r.w - r.z);
-    if (n == 0) return;
-    const uint32_t pieces = (n + piece - 1u) / piece;
-    const uint32_t at = atomicAdd(n_items, pieces);
-    for (uint32_t p = 0; p < pieces && at + p < cap; ++p)
-        items[at + p] = make_uint4(b, p * piece, min(n, (p + 1u) * piece), 0u);
-}
 
 // ---- windows: which column tiles a block of rows still has to see --------------------------------
 struct WindowArgs {
@@ -1299,8 +1027,7 @@ __global__ void __launch_bounds__(kTileRows) wis_window_kernel(WindowArgs a) {
 
 // ---- compaction: k-th smallest candidate value per row, new threshold -----------------------------
 struct CompactArgs {
-    float *cand_val;         // stored v = n'_j - 2 g
-    uint32_t *cand_idx;      // sorted column position
+    uint2 *cand;             // (bits of the stored v = n'_j - 2 g, sorted column position)
     uint32_t *cand_cnt;
     float *thr, *kap;
     uint32_t *overflow;      // [rows] sticky flag
@@ -1372,16 +1099,16 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
     }
     if (a.overflow[r] || n == a.seen[r]) return;  // nothing new since the last compaction
     uint32_t *hist = s_hist[threadIdx.x >> 5];
-    float *cv = a.cand_val + (size_t)r * kCandCap;
-    uint32_t *ci = a.cand_idx + (size_t)r * kCandCap;
+    uint2 *cand = a.cand + (size_t)r * kCandCap;
     const ColMeta mi = a.meta[a.rows_a ? a.rows_a[r] : r];
     const float rho = a.bc.maxes[0];
     const float rho2c = __fadd_ru(__fmul_ru(rho, rho), a.bc.c_rnd), rho2c_rd = __fadd_rd(__fmul_rd(rho, rho), a.bc.c_rnd);
     // key of candidate c: ordered bits of U_ij, all ones for same-contig pairs (never candidates)
     auto key_of = [&](uint32_t c) -> uint32_t {
-        const ColMeta mj = a.meta[ci[c]];
+        const uint2 en = cand[c];
+        const ColMeta mj = a.meta[en.y];
         if (mj.tid == mi.tid) return 0xFFFFFFFFu;
-        return __float_as_uint(pair_upper(cv[c], mi, mj, rho2c, a.bc)) | 0x80000000u;  // U >= 0
+        return __float_as_uint(pair_upper(__uint_as_float(en.x), mi, mj, rho2c, a.bc)) | 0x80000000u;  // U >= 0
     };
     uint32_t key[kKeyRegs];
     uint32_t kmin = 0xFFFFFFFFu, kmax = 0u, n_valid = 0;
@@ -1451,8 +1178,9 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
         uint32_t j = 0;
         bool keep = false;
         if (c < n) {
-            v = cv[c];
-            j = ci[c];
+            const uint2 en = cand[c];
+            v = __uint_as_float(en.x);
+            j = en.y;
             const ColMeta mj = a.meta[j];
             keep = mj.tid != mi.tid && (!have_bound || pair_alive(v, mi, mj, rho2c_rd, vg, a.bc));
         }
@@ -1460,8 +1188,7 @@ __global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(Compact
         const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
         __syncwarp();
         if (keep) {
-            cv[pos] = v;  // pos <= c: compaction in place, front to back
-            ci[pos] = j;
+            cand[pos] = make_uint2(__float_as_uint(v), j);  // pos <= c: compaction in place, front to back
         }
         kept += __popc(m);
         __syncwarp();
@@ -1490,7 +1217,7 @@ template <bool STAGED>
 __global__ void __launch_bounds__(kRescoreWarps * 32)
 wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid, uint32_t T, uint32_t S, uint32_t k,
                    uint32_t row_begin, uint32_t rows, const uint32_t *__restrict__ perm,
-                   const uint32_t *__restrict__ rows_a, const uint32_t *__restrict__ cand_idx,
+                   const uint32_t *__restrict__ rows_a, const uint2 *__restrict__ cand,
                    const uint32_t *__restrict__ cand_cnt, const uint32_t *__restrict__ overflow, uint32_t key_cap,
                    float *__restrict__ out_dist, uint32_t *__restrict__ out_idx) {
     extern __shared__ __align__(16) uint8_t s_raw[];
@@ -1511,7 +1238,7 @@ wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid
         const uint32_t row_f4 = S >> 2;
         for (uint32_t c0 = warp * 32; c0 < n; c0 += kRescoreWarps * 32) {
             const uint32_t c = c0 + lane;
-            const uint32_t j = c < n ? perm[cand_idx[(size_t)r * kCandCap + c]] : i;  // (padding lanes: any valid row)
+            const uint32_t j = c < n ? perm[cand[(size_t)r * kCandCap + c].y] : i;  // (padding lanes: any valid row)
             float y = 0.0f;
             for (uint32_t f0 = 0; f0 < row_f4; f0 += kStageF4) {
                 const uint32_t nf = min(kStageF4, row_f4 - f0);
@@ -1541,7 +1268,7 @@ wis_rescore_kernel(const float *__restrict__ X, const uint32_t *__restrict__ tid
         }
     } else {
         for (uint32_t c = threadIdx.x; c < n; c += blockDim.x) {
-            const uint32_t j = perm[cand_idx[(size_t)r * kCandCap + c]];
+            const uint32_t j = perm[cand[(size_t)r * kCandCap + c].y];
             s_key[c] = ((unsigned long long)__float_as_uint(wis_ref_distance(s_xi, X + (size_t)j * S, S, false)) << 32) | j;
         }
     }
@@ -1644,7 +1371,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     const uint32_t Kp = res ? kResK : ((S + kKBlock - 1) / kKBlock) * kKBlock;
     if (Kp > kMaxTensorS)
         return fail(ctx, CNVB_ERR_INVALID, "tensor engine: more than %u samples; use the exact engine", kMaxTensorS);
-    const bool stream_a = Kp > kMaxKBlocks * kKBlock;  // A no longer fits beside the B ring: stream both operands
+    const bool stream_a = !res;  // more than 125 samples: both operands stream through the K-block ring
     if (k > kMaxTensorK) return fail(ctx, CNVB_ERR_INVALID, "tensor engine: max_ref_targets > %u", kMaxTensorK);
     const uint32_t n_tiles = (T + kTileCols - 1) / kTileCols;
     const uint32_t Tpad = n_tiles * kTileCols;
@@ -1655,9 +1382,10 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     double *colsum = nullptr;
     float *scal = nullptr;  // [0] absmax | [1] rho | [2] max |p|
     __half *H = nullptr, *HA = nullptr, *HR = nullptr;
-    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *vg = nullptr, *cand_val = nullptr,
+    float *nrm = nullptr, *delta = nullptr, *thr = nullptr, *kap = nullptr, *vg = nullptr,
           *nprime = nullptr, *snorm = nullptr, *tile_smax = nullptr, *psorted = nullptr;
-    uint32_t *cand_idx = nullptr, *cand_cnt = nullptr, *overflow = nullptr, *seen = nullptr, *ovf_list = nullptr,
+    uint2 *cand = nullptr;
+    uint32_t *cand_cnt = nullptr, *overflow = nullptr, *seen = nullptr, *ovf_list = nullptr,
              *pkey = nullptr, *pkey_sorted = nullptr, *ident = nullptr, *perm = nullptr, *tid_sorted = nullptr,
              *rows_a = nullptr, *n_sel = nullptr;
     uint8_t *rflag = nullptr;
@@ -1667,17 +1395,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     uint2 *done = nullptr;
     unsigned long long *counters = nullptr;  // [0] tiles swept | [1] pairs re-scored | [2] longest list
     void *cub_tmp = nullptr;
-    size_t sort_bytes = 0, sel_bytes = 0, item_bytes = 0;
-    uint32_t *item_key = nullptr, *item_key_sorted = nullptr, *item_id = nullptr, *item_order = nullptr;
-    // split work items of the resident sweep: at most one piece per block beyond total / piece
-    const uint32_t kItemTarget = 8u * (uint32_t)ctx->sm_count;   // pieces per round aimed at (8 per SM)
-    const uint32_t items_cap = row_blocks + kItemTarget + 64u;
-    uint4 *items = nullptr;
-    uint32_t *n_items = nullptr;
+    size_t sort_bytes = 0, sel_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, pkey, pkey_sorted, ident, perm, (int)T, 0, 32, ctx->stream);
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, item_bytes, item_key, item_key_sorted, item_id, item_order,
-                                              (int)(2 * row_blocks), 0, 32, ctx->stream);
-    sort_bytes = std::max(sort_bytes, item_bytes);
     if (subset)
         cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<uint32_t>(0), rflag, rows_a, n_sel, (int)T,
                                    ctx->stream);
@@ -1688,18 +1407,14 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         (e = g.alloc(rows, &kap)) != cudaSuccess || (e = g.alloc(rows, &vg)) != cudaSuccess ||
         (e = g.alloc(Tpad, &nprime)) != cudaSuccess || (e = g.alloc(Tpad, &snorm)) != cudaSuccess ||
         (e = g.alloc(n_tiles, &tile_smax)) != cudaSuccess || (e = g.alloc(Tpad, &psorted)) != cudaSuccess ||
-        (e = g.alloc((size_t)rows * kCandCap, &cand_val)) != cudaSuccess ||
-        (e = g.alloc((size_t)rows * kCandCap, &cand_idx)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
+        (e = g.alloc((size_t)rows * kCandCap, &cand)) != cudaSuccess || (e = g.alloc(rows, &cand_cnt)) != cudaSuccess ||
         (e = g.alloc(rows, &overflow)) != cudaSuccess || (e = g.alloc(rows, &seen)) != cudaSuccess ||
         (e = g.alloc(rows + 1, &ovf_list)) != cudaSuccess || (e = g.alloc(T, &pkey)) != cudaSuccess ||
         (e = g.alloc(T, &pkey_sorted)) != cudaSuccess || (e = g.alloc(T, &ident)) != cudaSuccess ||
         (e = g.alloc(T, &perm)) != cudaSuccess || (e = g.alloc(Tpad, &tid_sorted)) != cudaSuccess ||
         (e = g.alloc(row_blocks, &rng)) != cudaSuccess || (e = g.alloc(row_blocks, &done)) != cudaSuccess ||
         (e = g.alloc(4, &counters)) != cudaSuccess || (e = g.alloc(S, &cmean)) != cudaSuccess ||
-        (e = g.alloc(Tpad, &meta)) != cudaSuccess || (e = g.alloc(2 * row_blocks, &item_key)) != cudaSuccess ||
-        (e = g.alloc(2 * row_blocks, &item_key_sorted)) != cudaSuccess || (e = g.alloc(2 * row_blocks, &item_id)) != cudaSuccess ||
-        (e = g.alloc(2 * row_blocks, &item_order)) != cudaSuccess || (e = g.alloc(items_cap, &items)) != cudaSuccess ||
-        (e = g.alloc(4, &n_items)) != cudaSuccess ||
+        (e = g.alloc(Tpad, &meta)) != cudaSuccess ||
         (e = g.alloc(std::max(sort_bytes, sel_bytes) + 16, reinterpret_cast<uint8_t **>(&cub_tmp))) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
@@ -1778,21 +1493,6 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b));
     if (subset && !res) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
 
-    // S <= 128, rounds >= 1: double tiles of 256 columns on M128 x N256 accumulators (wis_sweep256_kernel) --
-    // only with CNVB_WIS_N256 = 1: measured at 200 000 x 100 the sweeps take 7.3 ms against 4.1 ms for the
-    // M128 x N128 form (gpurun_out/r2_wis_probe.txt: the longer per-item epilogue outweighs the halved
-    // operand traffic), so the N128 form stays the default
-    const bool n256 = !stream_a && !res && [] {
-        const char *e = getenv("CNVB_WIS_N256");
-        return e && atoi(e) == 1;
-    }();
-    CUtensorMap tmap_b2 = tmap_b;
-    if (n256) CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b2, 256));
-    const size_t smem256 = (size_t)(2 + 2 * kDStages) * (Kp / kKBlock) * kTileBytes + 512 + 1024 +
-                           (size_t)kEpiWarps * kQueueCap * sizeof(uint4);
-    if (n256)
-        CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem256),
-                  "smem opt-in");
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
     // streamed sweep: the CTAs of a cluster share their rows' operand through TMA multicast
     // (CNVB_WIS_CLUSTER = 1: one CTA per block, 2 or 4: CTAs per cluster)
@@ -1813,18 +1513,12 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         return e ? (atoi(e) != 0 ? 1 : 0) : -1;
     }();
     const bool xp = stream_a && (xpose_env >= 0 ? xpose_env == 1 : T >= 1000000u);
-    // the same layout for S <= 128 (resident row operand): CNVB_WIS_XPOSE_SMALL = 1, off unless asked for
-    const bool xp_small = !stream_a && !res && [] {
-        const char *e = getenv("CNVB_WIS_XPOSE_SMALL");
-        return e && atoi(e) == 1;
-    }();
-    auto sweep_first = cl == 4 ? wis_sweep_kernel<true, true, 4, false>
-                     : cl == 2 ? wis_sweep_kernel<true, true, 2, false>
-                               : (stream_a ? wis_sweep_kernel<true, true, 1, false> : wis_sweep_kernel<true, false, 1, false>);
-    auto sweep_next = cl == 4 ? (xp ? wis_sweep_kernel<false, true, 4, true> : wis_sweep_kernel<false, true, 4, false>)
-                    : cl == 2 ? (xp ? wis_sweep_kernel<false, true, 2, true> : wis_sweep_kernel<false, true, 2, false>)
-                    : stream_a ? (xp ? wis_sweep_kernel<false, true, 1, true> : wis_sweep_kernel<false, true, 1, false>)
-                               : (xp_small ? wis_sweep_kernel<false, false, 1, true> : wis_sweep_kernel<false, false, 1, false>);
+    auto sweep_first = cl == 4 ? wis_sweep_kernel<true, 4, false>
+                     : cl == 2 ? wis_sweep_kernel<true, 2, false>
+                               : wis_sweep_kernel<true, 1, false>;
+    auto sweep_next = cl == 4 ? (xp ? wis_sweep_kernel<false, 4, true> : wis_sweep_kernel<false, 4, false>)
+                    : cl == 2 ? (xp ? wis_sweep_kernel<false, 2, true> : wis_sweep_kernel<false, 2, false>)
+                               : (xp ? wis_sweep_kernel<false, 1, true> : wis_sweep_kernel<false, 1, false>);
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     CNVB_CUDA(ctx, cudaFuncSetAttribute(sweep_next, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in");
     BoundConsts bc{};
@@ -1854,21 +1548,12 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.k_mmas = ((res ? S + 3u : S) + 15) / 16;
     sa.HA = HR;
     sa.n_kblocks = Kp / kKBlock;
-    sa.cand_val = cand_val;
-    sa.cand_idx = cand_idx;
+    sa.cand = cand;
     sa.cand_cnt = cand_cnt;
     {
         const char *e = getenv("CNVB_WIS_DBG");
         sa.dbg = e ? (uint32_t)atoi(e) : 0u;
     }
-    // resident sweep, rounds >= 1: split work items behind CNVB_WIS_SPLIT = 1 (default: one CTA per row block, as
-    // the first round).  Measured at config 3: sweep 7.2 ms against 4.0 ms -- every piece reloads the resident row
-    // operand and its appends go through the global per-row counters; kept under test, off by default
-    const bool split_items = !stream_a && !res && !xp_small && !n256 && [] {
-        const char *e = getenv("CNVB_WIS_SPLIT");
-        return e && atoi(e) == 1;
-    }();
-    uint32_t grid_items = 0;  // > 0: the next launch takes this many items
     const size_t smem_res = (size_t)kResStages * kTileBytes + 512 + 1024;
     if (res) {
         CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_res_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res),
@@ -1885,7 +1570,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
             return cudaGetLastError();
         }
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid_items ? grid_items : (unsigned)cl * row_blocks);
+        cfg.gridDim = dim3((unsigned)cl * row_blocks);
         cfg.blockDim = dim3(kSweepThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
@@ -1945,8 +1630,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         }
     };
     CompactArgs ca{};
-    ca.cand_val = cand_val;
-    ca.cand_idx = cand_idx;
+    ca.cand = cand;
     ca.cand_cnt = cand_cnt;
     ca.thr = thr;
     ca.kap = kap;
@@ -2018,31 +1702,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         if (tiles_now == tiles_before && round > 1) break;
         const unsigned long long tiles_prev_round = tiles_before;
         tiles_before = tiles_now;
-        if (n256) {
-            wis_items_kernel<<<(2 * row_blocks + 255) / 256, 256, 0, st>>>(rng, row_blocks, item_key, item_id);
-            CNVB_LAUNCHED(ctx, "wis_items_kernel");
-            CNVB_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(cub_tmp, item_bytes, item_key, item_key_sorted, item_id,
-                                                                     item_order, (int)(2 * row_blocks), 0, 32, st),
-                      "ordering the work items");
-            ctx->launches += 1;
-            {
-                KernelSpan span(ctx, "wis_sweep_kernel");
-                wis_sweep256_kernel<<<2 * row_blocks, kSweepThreads, smem256, st>>>(tmap_a, tmap_b2, sa, item_order);
-            }
-            CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
-        } else {
-            if (split_items) {
-                // pieces of (nearly) equal size, about eight per SM: the launch is then balanced by the hardware's
-                // own dispatch instead of 5.3 waves of row blocks whose windows differ by a factor of several
-                const unsigned long long round_tiles = tiles_now - tiles_prev_round;
-                const uint32_t piece = (uint32_t)std::max<unsigned long long>(8, (round_tiles + kItemTarget - 1) / kItemTarget);
-                CNVB_CUDA(ctx, cudaMemsetAsync(n_items, 0, 4, st), "clearing the item counter");
-                wis_split_kernel<<<(row_blocks + 255) / 256, 256, 0, st>>>(rng, row_blocks, piece, items_cap, items, n_items);
-                CNVB_LAUNCHED(ctx, "wis_split_kernel");
-                sa.items = items;
-                sa.n_items = n_items;
-                grid_items = (uint32_t)std::min<unsigned long long>(items_cap, row_blocks + round_tiles / piece + 1);
-            }
+        {
             {
                 KernelSpan span(ctx, "wis_sweep_kernel");
                 trace_begin();
@@ -2050,9 +1710,6 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
                 trace_end("sweep", round, tiles_now - tiles_prev_round);
             }
             CNVB_LAUNCHED(ctx, "wis_sweep_kernel");
-            sa.items = nullptr;
-            sa.n_items = nullptr;
-            grid_items = 0;
         }
         {
             KernelSpan span(ctx, "wis_compact_kernel");
@@ -2077,7 +1734,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         auto kern = staged ? wis_rescore_kernel<true> : wis_rescore_kernel<false>;
         CNVB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem), "smem opt-in");
         KernelSpan span(ctx, "wis_rescore_kernel");
-        kern<<<rows, kRescoreWarps * 32, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, perm, rows_a, cand_idx, cand_cnt,
+        kern<<<rows, kRescoreWarps * 32, rsmem, st>>>(dX, dtid, T, S, k, row_begin, rows, perm, rows_a, cand, cand_cnt,
                                                       overflow, key_cap, d_dist, d_idx);
     }
     CNVB_LAUNCHED(ctx, "wis_rescore_kernel");

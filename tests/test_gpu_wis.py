@@ -262,15 +262,13 @@ def test_wis_streamed_sweep_variants(oracle, ctx, monkeypatch, cluster, xpose):
     assert np.array_equal(i2, oidx[lo:hi]) and np.array_equal(d2.view(np.uint32), odist[lo:hi].view(np.uint32))
 
 
-@pytest.mark.parametrize("env", [("CNVB_WIS_N256", "1"), ("CNVB_WIS_SPLIT", "1"), ("CNVB_WIS_XPOSE_SMALL", "1"),
-                                 ("CNVB_WIS_XPOSE_SMALL", "0")])
-def test_wis_resident_sweep_variants(oracle, ctx, monkeypatch, env):
-    """S <= 128, the forms of the later rounds the defaults do not pick: the M128 x N256 double-tile kernel
-    (CNVB_WIS_N256 = 1; it measured slower than the N128 form at config 3) and split work items instead of one CTA per row
-    block (CNVB_WIS_SPLIT = 1; slower too: 7.2 against 4.0 ms) -- both select the oracle's sets, bit for bit."""
-    monkeypatch.setenv(*env)
-    T, S, k = 6100, 100, 40
-    X, tids = synth.synth_panel(911, T, S, n_contigs=6)
+@pytest.mark.parametrize("S", [100, 125, 126, 128])
+def test_wis_sweep_forms_by_sample_count(oracle, ctx, S):
+    """Up to 125 samples the rows' operand lives in tensor memory and the column norms are three extra K entries
+    (S + 3 <= 128, wis_resident.cuh); 126 - 128 samples take the streamed sweep with two K blocks -- both select
+    the oracle's sets, bit for bit, including the boundary cases either side."""
+    T, k = 6100, 40
+    X, tids = synth.synth_panel(911 + S, T, S, n_contigs=6)
     X[40] = X[41]
     odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=16)
     opts = mw.BuildModelWisOptions(max_ref_targets=k, engine=mw.ENGINE_TENSOR)

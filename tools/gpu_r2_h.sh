@@ -1,5 +1,10 @@
 #!/bin/bash
-for dbg in 1 17; do
-echo "== RES=0 CNVB_WIS_DBG=$dbg"
-env CNVB_WIS_RES=0 CNVB_WIS_TRACE=1 CNVB_WIS_DBG=$dbg timeout 40 python bench.py --workload wis --steps 1 --warmup 1 --quick 2>&1 >/dev/null | grep "wis trace" | grep sweep | tail -5 | awk '{if ($9>0) printf "%s  -> %.0f clk/tile\n", $0, $6*1e-3*1.965e9*148/$9; else print $0}'
+timeout 150 python -m pytest tests/test_gpu_wis.py -x -q 2>&1 | tail -15
+for dbg in 0; do
+echo "== CNVB_WIS_DBG=$dbg"
+env CNVB_WIS_TRACE=1 CNVB_WIS_DBG=$dbg timeout 40 python bench.py --workload wis --steps 1 --warmup 1 --quick 2>&1 >/dev/null | grep "wis trace" | grep -v blocks | tail -8 | awk '{if ($9>0) printf "%s  -> %.0f clk/tile\n", $0, $6*1e-3*1.965e9*148/$9; else print $0}'
 done
+timeout 40 python bench.py --workload wis --steps 5 --warmup 2 --quick 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+k=d['kernels']; print('step %.2f ms' % d['ms_per_step'], {n: round(v['ms_per_step'],3) for n,v in k.items()}, d['roofline']['frac'], d['wis_stats'], d['checks'])"
