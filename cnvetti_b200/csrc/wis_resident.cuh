@@ -1,59 +1,45 @@
-// wis_resident.cuh -- the sweep for panels of up to 125 samples (S + 3 <= 128): the block's 256 rows are
-// the A operand of the MMAs and live in TENSOR MEMORY for the whole launch.  Included by wis_tensor.cuh.
+// wis_resident.cuh -- the sweep for panels of up to 125 samples (S + 3 <= 128): the block's 256 rows stay in
+// shared memory for the whole launch, the column tiles stream past.  Included by wis_tensor.cuh.
 //
-// What the measurements of the shared-memory form (wis_sweep_kernel<.., STREAM = false, ..>, removed) said:
-//   * an SS-mode M128 x N128 x K16 tcgen05.mma reads 8 KB of operands from shared memory per 64-cycle slot --
-//     the SM's whole 128 B/clk, with the TMA writes of the next tile on top: 135 cycles per MMA measured,
-//     1890 per 256 x 128 tile (14 MMAs) with the epilogue switched off;
-//   * the epilogue (tcgen05.ld, one FFMA with n'_j and one compare per pair, group predicates) was 5160 warp
-//     instructions per tile = 1290 issue cycles per scheduler at best, 2100 measured alone;
-//   * both share two accumulator stages of a whole tile each, so every stall of one side reaches the other:
-//     2660 cycles per tile in rounds that append nothing, 4000 - 17 000 in the rounds that append.
+// What the measurements of the first form of this kernel said (per-round trace, CNVB_WIS_TRACE / CNVB_WIS_DBG;
+// 200 000 targets x 100 samples):
+//   * its epilogue (tcgen05.ld, one FFMA with n'_j and one compare per pair, group predicates) was 5160 warp
+//     instructions per 256 x 128 tile = 1290 issue cycles per scheduler at best, 2100 measured alone, against
+//     1890 for the 14 MMAs alone (135 cycles per M128 x N128 x K16 instruction, SS mode);
+//   * MMA issuer and epilogue shared two accumulator stages of a whole tile each, so every stall of one side
+//     reached the other: 2660 cycles per tile in rounds that append nothing;
+//   * the rounds that append were bound by the stores: every candidate cost two scattered 4-byte stores (value,
+//     index), and an SM retires ONE lane store to a distinct line per clock: 1.4 ms for 88 M candidates.
 // Here:
-//   * TS-mode MMAs: A = the rows, from TMEM (written once per CTA with tcgen05.st: lane = row, 32-bit column c =
-//     K elements 2 c, 2 c + 1), B = the column tile from shared memory, 4 KB per 64-cycle slot -- half the
-//     shared-memory bandwidth, and all 192 KB of it is B ring (12 stages = 6 tiles in flight);
 //   * the column norms are FOLDED into the contraction: rows hold (-2 h_i | C, C, C), columns
 //     (h_j | hi, mid, lo) with hi + mid + lo = n'_j / C exactly (three fp16 hold the 24 bits of an f32; C = 2^15
 //     keeps them in range), so the accumulator IS the value under test, v_ij = n'_j - 2 g_ij.  No column operands
-//     in the epilogue: a tree of three-input minima over the 32 values of a row (16 FMNMX3 / FMNMX), ONE compare
+//     in the epilogue: a tree of three-input minima over the 32 values of a row (FMNMX3 / FMNMX), ONE compare
 //     with the row's threshold, one vote per warp.  The products C x part are exact; the fp32 accumulation sees
 //     addends of total magnitude 2 s_i s_j + n_j instead of 2 s_i s_j, which the bounds carry as c_acc n_j
 //     (BoundConsts::c_rnd is raised by c_acc on this path);
-//   * the unit of the accumulator ring is a HALF tile (128 rows x 128 columns, 128 TMEM columns), three of them
-//     beside the 128 columns of the operand: while the epilogue warps hold one, the tensor core fills the next
-//     and has a third to go on to.  An epilogue warp gives its stage back as soon as tcgen05.ld has delivered the
-//     values to its registers -- before the tests and appends.
+//   * the unit of the accumulator ring is a HALF tile (128 rows x 128 columns, 128 TMEM columns), four of them:
+//     while the epilogue warps hold one, the tensor core fills the next and has two more to go on to.  An
+//     epilogue warp gives its stage back as soon as tcgen05.ld has delivered the values to its registers --
+//     before the tests and appends;
+//   * candidates are (value, index) pairs, one 8-byte store each; the first window stores two per 16-byte store.
+// An MMA of this kind costs about 64 + N / 2 cycles whatever feeds it: 133 per M128 x N128 x K16 from shared or
+// tensor memory once consecutive MMAs go to different accumulators, 192 per M128 x N256 x K16.  The transposed
+// M128 x N256 tile (1460 cycles per tile for the MMAs alone against 1890) was built on this kernel too and is
+// SLOWER in the sweep: a thread then owns a column and meets 32 rows with 32 different thresholds per tcgen05.ld,
+// and its tcgen05.ld traffic does not overlap the N = 256 MMAs -- 2700 - 2950 cycles per tile with both, the sum
+// of the two alone (1460 + 1490 - 1640), against 2150 - 2500 here.
+// Tried and measured slower: the rows' operand in TENSOR MEMORY (TS-mode tcgen05.mma, written once per CTA with
+// tcgen05.st; bit-exact): 2240 - 2400 cycles per tile for the MMAs alone against 1890 - 2020 from shared memory --
+// the operand reads compete with the accumulators' read-modify-write for the TMEM ports.
 #pragma once
 
 namespace {
 
-constexpr uint32_t kResStages = 12;   // B ring: 12 x 16 KB (one 128-column x 64-K block each)
-constexpr uint32_t kResAcc = 3;       // accumulator ring: half tiles of 128 TMEM columns
-constexpr uint32_t kResACols = 64;    // TMEM columns of one row half's operand: 128 K elements, two per column
+constexpr uint32_t kResStages = 8;    // B ring: 8 x 16 KB (one 128-column x 64-K block each)
+constexpr uint32_t kResAcc = 4;       // accumulator ring: half tiles of 128 TMEM columns
 constexpr uint32_t kResK = 128;       // padded K of this path
 constexpr float kFoldC = 32768.0f;    // the rows' three fold entries; the columns' are n'_j / C in three parts
-
-__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 
 // the fold entries of the column operand: n'_j / C in three fp16 parts whose sum never exceeds it
 // (+inf beyond T: such a column never passes a test)
@@ -80,7 +66,7 @@ __global__ void wis_fold_cols_kernel(const float *__restrict__ nprime, uint32_t 
 
 template <bool FIRST>
 __global__ void __launch_bounds__(kSweepThreads, 1)
-wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs a) {
+wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const SweepArgs a) {
     const uint32_t blk = blockIdx.x;
     // this block's share of the round: two tile ranges either side of what it has swept before
     const uint4 rng = a.rng[blk];
@@ -91,8 +77,10 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_base = smem_base;
+    const uint32_t a_base = smem_base;  // the rows' operand: [K block][row half] x 16 KB
+    const uint32_t b_base = a_base + 4u * kTileBytes;
     const uint32_t bar_base = b_base + kResStages * kTileBytes;
+    const uint32_t bar_a_full = bar_base + 8 * (2 * kResStages + 2 * kResAcc) + 8;
     const uint32_t bar_b_full = bar_base;                          // kResStages
     const uint32_t bar_b_empty = bar_b_full + 8 * kResStages;      // kResStages
     const uint32_t bar_acc_full = bar_b_empty + 8 * kResStages;    // kResAcc
@@ -100,9 +88,11 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
     const uint32_t tmem_slot = bar_acc_empty + 8 * kResAcc;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t row0 = blk * kTileRows;  // position in the sorted row list
+    const uint32_t n_kb = (a.k_mmas + 3u) / 4u;  // K blocks of 64 that hold data (S + 3 <= 64: one)
     for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x)
         s_cnt[t] = row0 + t < a.rows ? a.cand_cnt[row0 + t] : 0u;
     if (warp == 0 && lane == 0) {
+        mbar_init(bar_a_full, 1);
         for (uint32_t s = 0; s < kResStages; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
             mbar_init(bar_b_empty + 8 * s, 1);
@@ -113,7 +103,7 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: 2 x 64 operand columns | 3 x 128 accumulator columns
+    if (warp == 1) {  // TMEM: 4 x 128 accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -123,92 +113,70 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    const uint32_t acc_base = tmem_base + 2u * kResACols;
+    const uint32_t acc_base = tmem_base;
 
-    // TMA producer (one thread), first part: as many tiles as the empty ring takes are on their way while the
-    // operand is written (no waits here: this thread has to reach the barrier below)
-    uint32_t p_st = 0, p_ph = 0, p_it = 0;
-    auto produce = [&](uint32_t it_end) {
-        for (; p_it < it_end; ++p_it) {
-            const int32_t j0 = (int32_t)(CNVB_RTILE(p_it) * kTileCols);
-            for (uint32_t kb = 0; kb < 2; ++kb) {
-                mbar_wait(bar_b_empty + 8 * p_st, p_ph ^ 1u);
-                mbar_expect_tx(bar_b_full + 8 * p_st, kTileBytes);
-                tma_load_2d(b_base + p_st * kTileBytes, &tmap_b, bar_b_full + 8 * p_st, (int32_t)(kb * kKBlock), j0);
-                if (++p_st == kResStages) {
-                    p_st = 0;
-                    p_ph ^= 1u;
+    if (warp == 0) {
+        // ===== TMA producer (one thread): the rows' operand once, then the column tiles =====
+        if (lane == 0) {
+            mbar_expect_tx(bar_a_full, 2u * n_kb * kTileBytes);
+            for (uint32_t kb = 0; kb < n_kb; ++kb)
+                for (uint32_t h = 0; h < 2; ++h)
+                    tma_load_2d(a_base + (kb * 2u + h) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock), (int32_t)(row0 + h * 128));
+            uint32_t st = 0, ph = 0;
+            for (uint32_t it = 0; it < n_tiles; ++it) {
+                const int32_t j0 = (int32_t)(CNVB_RTILE(it) * kTileCols);
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
+                    mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
+                    tma_load_2d(b_base + st * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                    if (++st == kResStages) {
+                        st = 0;
+                        ph ^= 1u;
+                    }
                 }
             }
         }
-    };
-    if (warp == 0 && lane == 0) produce(min(n_tiles, kResStages / 2u));
-    if (warp >= 4) {
-        // the rows' operand: epilogue warp e writes TMEM lane quarter e & 3 of row half (e >> 2) & 1, the 32
-        // columns (64 K elements) e >> 3 -- every thread its own row, 128 bytes of it
-        const uint32_t e = warp - 4, q = e & 3u, h = (e >> 2) & 1u, kh = e >> 3;
-        const uint32_t row = row0 + h * 128u + q * 32u + lane;
-        uint32_t w[32];
-        if (row < a.rows) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.HA + (size_t)(a.rows_a ? a.rows_a[row] : row) * kResK + kh * 64u);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint4 x = __ldg(src + i);
-                w[4 * i + 0] = x.x;
-                w[4 * i + 1] = x.y;
-                w[4 * i + 2] = x.z;
-                w[4 * i + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = 0u;
-        }
-        tc_st32(tmem_base + ((q * 32u) << 16) + h * kResACols + kh * 32u, w);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    if (warp == 0) {
-        if (lane == 0) produce(n_tiles);  // ===== TMA producer, the rest =====
     } else if (warp == 1) {
         // ===== MMA issuer (one thread): per tile and row half seven (ceil((S + 3) / 16)) M128 x N128 x K16 MMAs =====
         if (lane == 0) {
-            uint32_t st = 0, ph = 0, as = 0, aph = 0;
-            const uint64_t bdesc0 = umma_desc(b_base);
+            // The two halves of a tile alternate MMA by MMA: an MMA into the accumulator the previous one wrote
+            // waits for it (seven in a row: 160 cycles each; alternating: 133), so a tile takes two stages of
+            // the ring at a time and both complete together.
+            uint32_t st = 0, ph = 0, u = 0;
+            const uint64_t bdesc0 = umma_desc(b_base), adesc0 = umma_desc(a_base);
+            mbar_wait(bar_a_full, 0);
+            tc_fence_after();
             for (uint32_t it = 0; it < n_tiles; ++it) {
+                const uint32_t as0 = u % kResAcc, as1 = (u + 1u) % kResAcc, aph = (u / kResAcc) & 1u;  // (kResAcc is even: same lap)
+                u += 2u;
+                mbar_wait(bar_acc_empty + 8 * as0, aph ^ 1u);
+                mbar_wait(bar_acc_empty + 8 * as1, aph ^ 1u);
+                tc_fence_after();
 #pragma unroll
-                for (uint32_t h = 0; h < 2; ++h) {
-                    mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = acc_base + as * kTileCols;
-#pragma unroll
-                    for (uint32_t kb = 0; kb < 2; ++kb) {
-                        const uint32_t sb = st + kb;  // (kResStages is even: a tile's two stages never wrap apart)
-                        if (h == 0) {
-                            mbar_wait(bar_b_full + 8 * sb, ph);
-                            tc_fence_after();
-                        }
-                        const uint64_t bdesc = bdesc0 + (uint64_t)(sb * (kTileBytes >> 4));
+                for (uint32_t kb = 0; kb < 2; ++kb) {
+                    if (kb < n_kb) {
+                        mbar_wait(bar_b_full + 8 * st, ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kTileBytes >> 4));
 #pragma unroll
                         for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                            if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
-                                tc_mma_f16_ts(d_tmem, tmem_base + h * kResACols + (kb * (kKBlock / 16) + kk) * 8u, bdesc + 2u * kk,
-                                              kIdesc, (kb | kk) != 0u);
+#pragma unroll
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
+                                    tc_mma_f16(acc_base + (h ? as1 : as0) * kTileCols,
+                                               adesc0 + (uint64_t)((kb * 2u + h) * (kTileBytes >> 4)) + 2u * kk, bdesc + 2u * kk, kIdesc,
+                                               (kb | kk) != 0u);
+                            }
                         }
-                        if (h == 1) tc_commit(bar_b_empty + 8 * sb);  // frees the B stage when these MMAs retire
-                    }
-                    tc_commit(bar_acc_full + 8 * as);  // this half tile's accumulators complete
-                    if (++as == kResAcc) {
-                        as = 0;
-                        aph ^= 1u;
+                        tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
+                        if (++st == kResStages) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
-                st += 2;
-                if (st == kResStages) {
-                    st = 0;
-                    ph ^= 1u;
-                }
+                tc_commit(bar_acc_full + 8 * as0);  // both half tiles' accumulators complete
+                tc_commit(bar_acc_full + 8 * as1);
             }
         }
     } else if (warp >= 4) {
@@ -217,6 +185,7 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
         const uint32_t e = warp - 4, q = e & 3u, cpart = e >> 2;
         float thr[2], kap[2];
         uint32_t trow[2];  // FIRST: contig of the row (a value no column has for rows beyond the end)
+        uint32_t own[2];   // the row's own column (sorted position): a same-contig index for padding entries
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint32_t row = row0 + h * 128 + q * 32 + lane;
@@ -224,7 +193,8 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
             thr[h] = live ? a.thr[row] : -__int_as_float(0x7f800000);
             kap[h] = live ? a.kap[row] : 0.0f;
             trow[h] = 0xFFFFFFFEu;
-            if (FIRST && live) trow[h] = a.tid_sorted[a.rows_a ? a.rows_a[row] : row];
+            own[h] = live ? (a.rows_a ? a.rows_a[row] : row) : 0u;
+            if (FIRST && live) trow[h] = a.tid_sorted[own[h]];
         }
         const float inf = __int_as_float(0x7f800000);
         uint32_t as = 0, aph = 0;
@@ -286,23 +256,25 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
                     // is swept again with the bound.  (Minima of larger groups over a wider window were tried --
                     // one of 32 over 0.4 k tiles: the stored minima then come from tiles far away in projection,
                     // where even the nearest column is far, and the bound is useless.)
-                    if (row < a.rows && m < inf) {
-                        uint32_t pick = 0u, have = 0u;
+                    // Every (row, warp, half tile) stores exactly eight entries -- groups without a finite minimum as
+                    // padding (the row's own column: same contig, dropped by the compaction) -- so the slots are
+                    // multiples of eight and two entries go out per 16-byte store.
+                    if (row < a.rows) {
+                        uint32_t pick = 0u;
 #pragma unroll
                         for (int g4 = 0; g4 < 8; ++g4) {
                             const uint32_t w = v[4 * g4] == gm[g4] ? 0u : (v[4 * g4 + 1] == gm[g4] ? 1u : (v[4 * g4 + 2] == gm[g4] ? 2u : 3u));
                             pick |= w << (2 * g4);
-                            have |= (gm[g4] < inf ? 1u : 0u) << g4;
                         }
-                        // (v = +inf beyond T: padding columns are never a group's minimum)
-                        uint32_t slot = atomicAdd(&s_cnt[rloc], (uint32_t)__popc(have));
+                        const uint32_t slot = atomicAdd(&s_cnt[rloc], 8u);
+                        if (slot + 8u <= kCandCap) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(cand + slot);
 #pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4) {
-                            if (have & (1u << g4)) {
-                                if (slot < kCandCap) {
-                                    cand[slot] = make_uint2(__float_as_uint(gm[g4]), j0 + 4u * g4 + ((pick >> (2 * g4)) & 3u));
-                                }
-                                ++slot;
+                            for (int g2 = 0; g2 < 4; ++g2) {
+                                const int ga = 2 * g2, gb = 2 * g2 + 1;
+                                const uint32_t ja = gm[ga] < inf ? j0 + 4u * ga + ((pick >> (2 * ga)) & 3u) : own[h];
+                                const uint32_t jb = gm[gb] < inf ? j0 + 4u * gb + ((pick >> (2 * gb)) & 3u) : own[h];
+                                dst[g2] = make_uint4(__float_as_uint(gm[ga]), ja, __float_as_uint(gm[gb]), jb);
                             }
                         }
                     }
@@ -361,5 +333,6 @@ wis_sweep_res_kernel(const __grid_constant__ CUtensorMap tmap_b, const SweepArgs
 }
 
 #undef CNVB_RTILE
+
 
 }  // namespace

@@ -401,7 +401,6 @@ struct SweepArgs {
     uint32_t *cand_cnt;      // [rows]
     uint32_t dbg;            // CNVB_WIS_DBG (timing experiments only; results are wrong), bits: 1 skip the epilogue's
                              // TMEM reads and tests, 2 skip the MMAs, 4 skip the append's stores, 8 skip the appends
-    const __half *HA;        // resident sweep (wis_resident.cuh): the rows' operand (-2 h | C, C, C), [Tpad][128], sorted order
 };
 
 // STREAM: more than kMaxKBlocks K-blocks (S > 128): the A operand does not fit beside the B ring, so
@@ -1419,7 +1418,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (subset && ((e = g.alloc(rows, &rows_a)) != cudaSuccess || (e = g.alloc(T, &rflag)) != cudaSuccess ||
                    (e = g.alloc(1, &n_sel)) != cudaSuccess ||
-                   (!res && (e = g.alloc((size_t)rows_pad * Kp, &HA)) != cudaSuccess)))
+                   (e = g.alloc((size_t)rows_pad * Kp, &HA)) != cudaSuccess))
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
     if (res && (e = g.alloc((size_t)Tpad * Kp, &HR)) != cudaSuccess)
         return fail_cuda(ctx, e, "allocating the tensor engine's work space");
@@ -1480,10 +1479,8 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         CNVB_CUDA(ctx, cub::DeviceSelect::Flagged(cub_tmp, sel_bytes, cub::CountingInputIterator<uint32_t>(0), rflag, rows_a,
                                                   n_sel, (int)T, st), "selecting the rows");
         ctx->launches += 1;
-        if (!res) {
-            wis_gather_rows_kernel<<<rows_pad, 64, 0, st>>>(H, Kp, rows_a, rows, rows_pad, HA);
-            CNVB_LAUNCHED(ctx, "wis_gather_rows_kernel");
-        }
+        wis_gather_rows_kernel<<<rows_pad, 64, 0, st>>>(res ? HR : H, Kp, rows_a, rows, rows_pad, HA);
+        CNVB_LAUNCHED(ctx, "wis_gather_rows_kernel");
     }
     float pabs = 0.0f;
     CNVB_CUDA(ctx, cudaMemcpyAsync(&pabs, scal + 2, 4, cudaMemcpyDeviceToHost, st), "reading the projection range");
@@ -1491,7 +1488,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
 
     CUtensorMap tmap_b, tmap_a;
     CNVB_TRY(make_tmap(ctx, H, Tpad, Kp, &tmap_b));
-    if (subset && !res) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a)); else tmap_a = tmap_b;
+    if (subset) CNVB_TRY(make_tmap(ctx, HA, rows_pad, Kp, &tmap_a));
+    else if (res) CNVB_TRY(make_tmap(ctx, HR, Tpad, Kp, &tmap_a));  // (resident sweep: the rows' operand is its own matrix)
+    else tmap_a = tmap_b;
 
     const size_t smem = 2 * kMaxKBlocks * kTileBytes + kStages * kTileBytes + 512 + 1024;
     // streamed sweep: the CTAs of a cluster share their rows' operand through TMA multicast
@@ -1546,7 +1545,6 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     sa.tid_sorted = tid_sorted;
     sa.rows_a = rows_a;
     sa.k_mmas = ((res ? S + 3u : S) + 15) / 16;
-    sa.HA = HR;
     sa.n_kblocks = Kp / kKBlock;
     sa.cand = cand;
     sa.cand_cnt = cand_cnt;
@@ -1554,7 +1552,7 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
         const char *e = getenv("CNVB_WIS_DBG");
         sa.dbg = e ? (uint32_t)atoi(e) : 0u;
     }
-    const size_t smem_res = (size_t)kResStages * kTileBytes + 512 + 1024;
+    const size_t smem_res = (size_t)(4 + kResStages) * kTileBytes + 512 + 1024;
     if (res) {
         CNVB_CUDA(ctx, cudaFuncSetAttribute(wis_sweep_res_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res),
                   "smem opt-in");
@@ -1564,9 +1562,9 @@ int wis_distances_tensor(cnvb_ctx *ctx, const float *dX, const uint32_t *dtid, u
     auto launch_sweep = [&](decltype(sweep_first) kern) -> cudaError_t {
         if (res) {
             if (kern == sweep_first)
-                wis_sweep_res_kernel<true><<<row_blocks, kSweepThreads, smem_res, st>>>(tmap_b, sa);
+                wis_sweep_res_kernel<true><<<row_blocks, kSweepThreads, smem_res, st>>>(tmap_a, tmap_b, sa);
             else
-                wis_sweep_res_kernel<false><<<row_blocks, kSweepThreads, smem_res, st>>>(tmap_b, sa);
+                wis_sweep_res_kernel<false><<<row_blocks, kSweepThreads, smem_res, st>>>(tmap_a, tmap_b, sa);
             return cudaGetLastError();
         }
         cudaLaunchConfig_t cfg{};

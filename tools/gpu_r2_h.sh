@@ -1,6 +1,6 @@
 #!/bin/bash
 timeout 150 python -m pytest tests/test_gpu_wis.py -x -q 2>&1 | tail -15
-for dbg in 0; do
+for dbg in 0 1; do
 echo "== CNVB_WIS_DBG=$dbg"
 env CNVB_WIS_TRACE=1 CNVB_WIS_DBG=$dbg timeout 40 python bench.py --workload wis --steps 1 --warmup 1 --quick 2>&1 >/dev/null | grep "wis trace" | grep -v blocks | tail -8 | awk '{if ($9>0) printf "%s  -> %.0f clk/tile\n", $0, $6*1e-3*1.965e9*148/$9; else print $0}'
 done
