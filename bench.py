@@ -593,12 +593,18 @@ def bench_hmm(args, env, steps=None, warmup=None):
         import oracle
         oracle.build()
         tab = oracle.hmm_tables(0.08, opts.sigma0, opts.eps_cn, opts.p_move)
-        ok, nl = True, 0
+        ok, nl, differ, total = True, 0, 0, 0
         for li in (0, 10, 21):
             a, b = int(lane_off[li]), int(lane_off[li + 1])
-            ok &= bool(np.array_equal(oracle.hmm_viterbi(cv[a:b].cpu().numpy(), tab), st[a:b].cpu().numpy()))
+            lane_cv, lane_st = cv[a:b].cpu().numpy(), st[a:b].cpu().numpy()
+            ok &= bool(np.array_equal(oracle.hmm_viterbi(lane_cv, tab), lane_st))
+            # quality number: the integer-score spec against the same recurrence in log-space FP64 (north_star's wording)
+            differ += int(np.count_nonzero(oracle.hmm_viterbi_f64(lane_cv, tab) != lane_st))
+            total += b - a
             nl += 1
-        checks = {"lanes_vs_oracle": nl, "identical": ok}
+        checks = {"lanes_vs_oracle": nl, "identical": ok,
+                  "fp64_path_disagreement": {"bins": differ, "of": total, "rate": differ / max(total, 1),
+                                             "what": "state calls that differ from a sequential log-space FP64 Viterbi"}}
     sampler = ClockSampler(env.local)
     ms, launches, clocks = timed_steps(env, step, steps, max(0, warmup - 1), sampler)
     kern, _ = kernel_times(env, step, min(steps, 5), HMM_KERNELS)

@@ -113,6 +113,8 @@ def _declare(L):
     L.orc_hmm_make_tables.argtypes = [d, d, d, d, C.POINTER(HmmTables)]
     L.orc_hmm_viterbi.restype = None
     L.orc_hmm_viterbi.argtypes = [vp, C.c_uint64, C.POINTER(HmmTables), vp]
+    L.orc_hmm_viterbi_f64.restype = None
+    L.orc_hmm_viterbi_f64.argtypes = [vp, C.c_uint64, C.POINTER(HmmTables), vp]
     L.orc_hmm_emit_scores.restype = None
     L.orc_hmm_emit_scores.argtypes = [C.c_float, C.POINTER(HmmTables), vp]
     L.orc_hmm_posterior.restype = None
@@ -357,6 +359,15 @@ def hmm_viterbi(cv, tables):
     cv = _arr(cv, np.float32)
     state = np.zeros(cv.size, np.uint8)
     lib().orc_hmm_viterbi(_p(cv), cv.size, C.byref(tables), _p(state))
+    return state
+
+
+def hmm_viterbi_f64(cv, tables):
+    """The recurrence in log-space FP64 (north_star's wording); the product runs on integer scores -- this is for
+    the disagreement rate between the two specs."""
+    cv = _arr(cv, np.float32)
+    state = np.zeros(cv.size, np.uint8)
+    lib().orc_hmm_viterbi_f64(_p(cv), cv.size, C.byref(tables), _p(state))
     return state
 
 

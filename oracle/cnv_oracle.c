@@ -980,6 +980,45 @@ void orc_hmm_viterbi(const float *cv, uint64_t n, const orc_hmm_tables *t, uint8
     free(bp);
 }
 
+/* The same recurrence in log-space FP64, strictly sequential -- what BASELINE.json's north_star words for the
+ * segmentation ("log-space FP64 with the reference's tie-breaking").  The product runs on the integer scores
+ * above (exactly associative, hence chunk-parallel); this function exists so that the rate at which the two
+ * specs disagree can be reported (bench.py, cfg4: `fp64_path_disagreement`).  Emissions as in hmm_emit, no floor;
+ * ties keep the lowest predecessor / the first maximum, as above. */
+void orc_hmm_viterbi_f64(const float *cv, uint64_t n, const orc_hmm_tables *t, uint8_t *state) {
+    const int K = ORC_HMM_STATES;
+    if (n == 0) return;
+    uint8_t *bp = (uint8_t *)malloc(n * K);
+    double d[ORC_HMM_STATES], nd[ORC_HMM_STATES], e[ORC_HMM_STATES];
+    hmm_emit((double)cv[0], !isfinite(cv[0]), t, e);
+    for (int s = 0; s < K; ++s) d[s] = t->log_start[s] + e[s];
+    for (uint64_t b = 1; b < n; ++b) {
+        hmm_emit((double)cv[b], !isfinite(cv[b]), t, e);
+        for (int s = 0; s < K; ++s) {
+            double best = d[0] + t->log_trans[0][s];
+            int arg = 0;
+            for (int r = 1; r < K; ++r) {
+                double c = d[r] + t->log_trans[r][s];
+                if (c > best) {
+                    best = c;
+                    arg = r;
+                }
+            }
+            nd[s] = best + e[s];
+            bp[b * K + s] = (uint8_t)arg;
+        }
+        for (int s = 0; s < K; ++s) d[s] = nd[s];
+    }
+    int arg = 0;
+    for (int s = 1; s < K; ++s)
+        if (d[s] > d[arg]) arg = s;
+    for (uint64_t b = n; b-- > 0;) {
+        state[b] = (uint8_t)arg;
+        if (b > 0) arg = bp[b * K + arg];
+    }
+    free(bp);
+}
+
 static inline double lse5(const double *v) {
     double m = v[0];
     for (int s = 1; s < ORC_HMM_STATES; ++s)

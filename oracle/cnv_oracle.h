@@ -171,6 +171,7 @@ void orc_hmm_emit_scores(float cv, const orc_hmm_tables *t, int32_t *e);
 void orc_hmm_make_tables(double sigma_s, double sigma0, double eps_cn, double p_move,
                          orc_hmm_tables *t);
 void orc_hmm_viterbi(const float *cv, uint64_t n, const orc_hmm_tables *t, uint8_t *state);
+void orc_hmm_viterbi_f64(const float *cv, uint64_t n, const orc_hmm_tables *t, uint8_t *state);
 void orc_hmm_posterior(const float *cv, uint64_t n, const orc_hmm_tables *t, double *post);
 
 #ifdef __cplusplus
