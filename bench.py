@@ -428,6 +428,12 @@ def check_rows_against_oracle(X_host, tids_host, rows, got_dist, got_idx, k=100)
 
 
 # ---- workloads ------------------------------------------------------------------------------------------------
+def wis_k_issued(S):
+    """K extent of the tcgen05.mma instructions one tile takes: 16 per K16 slab that holds data -- up to 125 samples the
+    three fold entries ride along (wis_resident.cuh), beyond that the samples alone (streamed sweep)."""
+    return 16 * ((S + 3 + 15) // 16) if S + 3 <= 128 else 16 * ((S + 15) // 16)
+
+
 def bench_wis(args, env, steps=None, warmup=None):
     """BASELINE configs[2]: build-model-wis on a synthetic panel (T targets x S samples, k=100).
     One step = compute_distances + prune + per-probe calls + filters (lib_model_wis::run).  N > 1: target
@@ -505,7 +511,7 @@ def bench_wis(args, env, steps=None, warmup=None):
     algorithmic = 2.0 * rows_n * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
     # what the tensor cores executed: visited 256x128 tiles x padded K (projection windows skip the rest)
     tiles = float(stats["tiles"]) if stats else 0.0
-    kp = ((S + 63) // 64) * 64
+    kp = wis_k_issued(S)
     executed = 2.0 * tiles * 256 * 128 * kp / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
     tile_frac = tiles * 256 * 128 / (float(rows_n) * T) if T and rows_n else 0.0
     cpu = None
@@ -532,8 +538,9 @@ def bench_wis(args, env, steps=None, warmup=None):
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": executed, "peak": peak_t,
                          "unit": "TFLOP/s", "frac": executed / peak_t, "traffic": None,
-                         "what": "EXECUTED flops: visited 256x128 tiles x padded K (%d) x 2 / sweep time -- what the "
-                                 "tensor pipe did" % kp,
+                         "what": "EXECUTED flops: visited 256x128 tiles x K of the MMAs issued (%d: 16 per K16 slab that "
+                                 "holds data; round 1 quoted 128, the padded K) x 2 / sweep time -- what the tensor pipe did" % kp,
+                         "padded_k_equiv": executed * (((S + 63) // 64) * 64) / kp if kp else None,
                          "algorithmic_equiv": algorithmic, "algorithmic_flop_per_pair": 2 * S,
                          "algorithmic_note": "2*rows*T*S / sweep time (SURVEY 8(d)'s count for the all-pairs "
                                              "contraction); the projection windows skip most tiles, so this exceeds "
@@ -939,7 +946,7 @@ def bench_cfg5(args, env, steps=None, warmup=None):
     peak_t, peak_src = measured_tensor_peak()
     sweep = kern.get("wis_sweep_kernel", {}).get("ms_per_step", 0.0)
     rows_n = hi - lo
-    kp = ((S + 63) // 64) * 64
+    kp = wis_k_issued(S)
     tiles = float(stats["tiles"]) if stats else 0.0
     executed = 2.0 * tiles * 256 * 128 * kp / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
     algorithmic = 2.0 * rows_n * T * S / (sweep * 1e-3) / 1e12 if sweep > 0 else 0.0
@@ -991,7 +998,7 @@ def bench_cfg5(args, env, steps=None, warmup=None):
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "wis_sweep_kernel", "achieved": executed, "peak": peak_t,
                          "unit": "TFLOP/s", "frac": executed / peak_t, "traffic": None,
-                         "what": "EXECUTED flops (rank 0): visited 256x128 tiles x padded K x 2 / sweep time",
+                         "what": "EXECUTED flops (rank 0): visited 256x128 tiles x K of the MMAs issued (%d) x 2 / sweep time" % kp,
                          "algorithmic_equiv": algorithmic,
                          "tile_fraction_visited": tiles * 256 * 128 / (float(rows_n) * T) if rows_n else None,
                          "kernel_share_of_step": sweep / ms if ms else None, "peak_source": peak_src},
