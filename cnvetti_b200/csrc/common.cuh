@@ -68,6 +68,9 @@ namespace cnvb {
 
 int refstats_prepare(cnvb_ctx *ctx);  // refstats.cu: builds the classification table on ctx->stream if missing
 // refstats.cu: reference statistics of all regions in one launch; 1 = not applicable (go region by region)
+// FragmentsGenomeWide records of all regions of a run in one launch (coverage.cu); 1 = does not apply
+int gw_batch_put(cnvb_ctx *ctx, cnvb_cov *const *aggs, const cnvb_read_soa *batches, size_t batch_stride, uint32_t n,
+                 int ctas_per_sm);
 int refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const *seq, const uint64_t *len, const uint64_t *out_off,
                           uint32_t window_length, float *gc, uint8_t *has_gap, bool shares_sms,
                           std::vector<void *> *defer_release);

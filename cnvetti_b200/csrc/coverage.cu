@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t frag_pass4(uint32_t mq, uint2 fl, uint32_t m
 }
 
 template <bool PILES, bool WL_SMALL, int Q>
-__global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
+__device__ __forceinline__ void gw_region(const GwArgs &a) {
     // A warp step covers Q consecutive groups of 32 quads (Q x 128 reads): lane l owns quad
     // qb + 32 u + l of group u, so every load instruction of the warp is one contiguous
     // 512 / 128 / 256-byte run.  The per-step warp work (anchor, division, REDUX, counter REDs)
@@ -298,6 +298,26 @@ __global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
         if (n_skip) atomicAdd(&a.stats[1], n_skip);
         if (n_oob) atomicAdd(&a.stats[2], n_oob);
     }
+}
+
+template <bool PILES, bool WL_SMALL, int Q>
+__global__ void __launch_bounds__(256, 4) frag_bin_gw_kernel(GwArgs a) {
+    gw_region<PILES, WL_SMALL, Q>(a);
+}
+
+// All regions of a run in ONE launch (the loop of lib_coverage::run, lib-coverage/src/lib.rs:768-781, over
+// device-resident read columns): every CTA takes its grid-stride share of region 0, then of region 1, ... --
+// no barrier in between, so the warps flow from one region into the next and the launch pays ONE fill and one
+// tail instead of one per region (fit over the 22 contigs of config 2: ~5 us each, a tenth of the binning
+// time).  The regions' arguments travel in the kernel parameters (constant bank, indexed by the region).
+constexpr uint32_t kGwBatchMax = 40;  // x 88 bytes of arguments: inside the 4 KB of kernel parameters
+struct GwBatch {
+    uint32_t n;
+    GwArgs r[kGwBatchMax];
+};
+template <bool PILES, bool WL_SMALL, int Q>
+__global__ void __launch_bounds__(256, 4) frag_bin_gw_batch_kernel(const __grid_constant__ GwBatch b) {
+    for (uint32_t i = 0; i < b.n; ++i) gw_region<PILES, WL_SMALL, Q>(b.r[i]);
 }
 
 // Same operator for SoA pointers that are not 16/4/8-byte aligned: scalar coalesced loads.
@@ -534,6 +554,24 @@ int stage_column(cnvb_ctx *ctx, const T *src, uint64_t n, int mem, T *dst_stage,
 
 constexpr uint64_t kChunkReads = 32ull << 20;  // host batches are streamed in 32 Mi-read chunks
 
+// everything of the kernel arguments that comes from the aggregator (the read columns are the caller's)
+void gw_fill_args(const cnvb_cov *a, GwArgs *g) {
+    g->counters = a->d_counters;
+    g->num_bins = (uint32_t)a->num_regions;
+    g->div = make_fastdiv(a->opts.window_length);
+    g->magic_up = (uint32_t)(((1ull << 32) + a->opts.window_length - 1) / a->opts.window_length);
+    g->wl_small = a->opts.window_length >= 16 && a->opts.window_length <= 32768;
+    g->min_mapq = a->opts.min_mapq;
+    g->pile_start = a->d_pile_start;
+    g->pile_end = a->d_pile_end;
+    g->n_pile = a->n_pile;
+    g->stats = a->d_stats;
+}
+bool gw_aligned(const GwArgs &g) {
+    return ((uintptr_t)g.mid % 16 == 0) && ((uintptr_t)g.mapq % 4 == 0) && ((uintptr_t)g.flags % 8 == 0) &&
+           g.min_mapq <= 255u;  // (packed byte compare)
+}
+
 int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
     cnvb_ctx *ctx = a->ctx;
     if (!b->mid || !b->mapq || !b->flags)
@@ -558,18 +596,8 @@ int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
         CNVB_TRY(stage_column(ctx, b->mapq + off, n, b->mem, s_mq, &g.mapq));
         CNVB_TRY(stage_column(ctx, b->flags + off, n, b->mem, s_fl, &g.flags));
         g.n = n;
-        g.counters = a->d_counters;
-        g.num_bins = (uint32_t)a->num_regions;
-        g.div = make_fastdiv(a->opts.window_length);
-        g.magic_up = (uint32_t)(((1ull << 32) + a->opts.window_length - 1) / a->opts.window_length);
-        g.wl_small = a->opts.window_length >= 16 && a->opts.window_length <= 32768;
-        g.min_mapq = a->opts.min_mapq;
-        g.pile_start = a->d_pile_start;
-        g.pile_end = a->d_pile_end;
-        g.n_pile = a->n_pile;
-        g.stats = a->d_stats;
-        const bool aligned = ((uintptr_t)g.mid % 16 == 0) && ((uintptr_t)g.mapq % 4 == 0) &&
-                             ((uintptr_t)g.flags % 8 == 0) && g.min_mapq <= 255u;  // (packed byte compare)
+        gw_fill_args(a, &g);
+        const bool aligned = gw_aligned(g);
         const uint64_t work = aligned ? (n + 3) / 4 : n;
         const uint64_t work_blocks = (work + 255) / 256;
         static const int gw_quads = [] {  // quads per lane and step (tuning knob; 2 measured best)
@@ -603,6 +631,60 @@ int put_gw(cnvb_cov *a, const cnvb_read_soa *b) {
 }
 
 }  // namespace
+
+// FragmentsGenomeWide, all regions of a run at once: aggs[i] takes batches[i] (device-resident columns).
+// Returns 0 when the records are on their way (ONE launch per kGwBatchMax regions on the context's stream),
+// 1 when the batch form does not apply -- the caller then feeds the aggregators one by one -- or an error.
+int cnvb::gw_batch_put(cnvb_ctx *ctx, cnvb_cov *const *aggs, const cnvb_read_soa *batches, size_t batch_stride,
+                       uint32_t n, int ctas_per_sm) {
+    if (n < 2) return 1;
+    std::vector<GwArgs> args(n);
+    bool piles = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const cnvb_cov *a = aggs[i];
+        const cnvb_read_soa *b = reinterpret_cast<const cnvb_read_soa *>(reinterpret_cast<const char *>(batches) + i * batch_stride);
+        if (!a || a->kind != CNVB_FRAGMENTS_GENOME_WIDE || a->state != 0 || b->mem != CNVB_MEM_DEVICE) return 1;
+        if (b->n >= (1ull << 31) || (b->n && (!b->mid || !b->mapq || !b->flags))) return 1;
+        if (a->opts.window_length != aggs[0]->opts.window_length || a->opts.min_mapq != aggs[0]->opts.min_mapq) return 1;
+        GwArgs &g = args[i];
+        g = GwArgs{};
+        g.mid = b->mid;
+        g.mapq = b->mapq;
+        g.flags = b->flags;
+        g.n = b->n;
+        gw_fill_args(a, &g);
+        if (b->n && !gw_aligned(g)) return 1;
+        piles = piles || a->n_pile != 0;
+    }
+    CNVB_CUDA(ctx, cudaSetDevice(ctx->device), "selecting device");
+    const bool wl_small = args[0].wl_small != 0;
+    for (uint32_t first = 0; first < n; first += kGwBatchMax) {
+        GwBatch batch{};
+        batch.n = std::min<uint32_t>(kGwBatchMax, n - first);
+        uint64_t quads = 0;
+        for (uint32_t i = 0; i < batch.n; ++i) {
+            batch.r[i] = args[first + i];
+            quads = std::max<uint64_t>(quads, (batch.r[i].n + 3) / 4);
+        }
+        const uint64_t work_blocks = (((quads + 255) / 256) + 1) / 2;  // (two quads per lane and step)
+        {
+            KernelSpan span(ctx, "frag_bin_gw_kernel");
+            // (a persistent grid must be RESIDENT as a whole: beside another persistent kernel -- the reference
+            // statistics on their side stream -- the caller asks for fewer CTAs per SM than the kernel could have alone)
+            const uint64_t cap = ctas_per_sm > 0 ? (uint64_t)ctas_per_sm * (uint64_t)ctx->sm_count : ~0ull;
+#define CNVB_GW_BATCH_LAUNCH(P, S) \
+    frag_bin_gw_batch_kernel<P, S, 2><<<(unsigned)std::min<uint64_t>(cap, persistent_grid(ctx, frag_bin_gw_batch_kernel<P, S, 2>, 256, 0, work_blocks)), 256, 0, ctx->stream>>>(batch)
+            if (piles) {
+                if (wl_small) CNVB_GW_BATCH_LAUNCH(true, true); else CNVB_GW_BATCH_LAUNCH(true, false);
+            } else {
+                if (wl_small) CNVB_GW_BATCH_LAUNCH(false, true); else CNVB_GW_BATCH_LAUNCH(false, false);
+            }
+#undef CNVB_GW_BATCH_LAUNCH
+        }
+        CNVB_LAUNCHED(ctx, "frag_bin_gw_kernel");
+    }
+    return 0;
+}
 
 extern "C" int cnvb_cov_put_records(cnvb_cov *a, const cnvb_read_soa *b) {
     if (!a) return CNVB_ERR_INVALID;

@@ -195,11 +195,69 @@ int coverage_run_impl(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const 
             ref_batched = rc == 0;
         }
     }
+    // FragmentsGenomeWide over device-resident regions: the regions are taken in a few GROUPS of consecutive
+    // regions with about the same number of records.  Per group: the aggregators are constructed, ONE launch bins
+    // the records of all its regions (coverage.cu: frag_bin_gw_batch_kernel -- one fill and one tail per group
+    // instead of one per region), then the per-region statistics follow; consecutive groups alternate between two
+    // side streams, so the small operations of one group run beside the binning of the next.
+    // OFF unless CNVB_GW_BATCH = 1.  Measured on config 2 (22 regions): the binning alone drops from 1.10 to 0.93 ms
+    // (one group; 0.96 with four) -- 6.8 TB/s, above the copy-measured HBM peak -- but the STEP grows from 1.65 to
+    // 1.73 - 2.0 ms: the per-region form hides every region's small operations (two allocations, three memsets,
+    // the tally copy, the window statistics: ~13 us per region) behind the binning of its neighbours on the other
+    // stream, and a long persistent launch beside the persistent reference-statistics kernel leaves half of its
+    // CTAs waiting for a free slot.  The batch form pays off only once those small operations are batched too.
+    bool gw_try = kind == CNVB_FRAGMENTS_GENOME_WIDE && n_regions > 1 && [] {
+        const char *e = getenv("CNVB_GW_BATCH");
+        return e && atoi(e) == 1;
+    }();
+    for (uint32_t i = 0; i < n_regions && gw_try; ++i) gw_try = regions[i].reads.mem == CNVB_MEM_DEVICE;
+    std::vector<uint32_t> gstart;  // first region of every group, then n_regions
+    if (gw_try) {
+        const uint32_t want_groups = [] {
+            const char *e = getenv("CNVB_GW_GROUPS");
+            const int v = e ? atoi(e) : 0;
+            return (uint32_t)(v > 0 ? v : 4);
+        }();
+        const uint32_t G = std::max<uint32_t>(1, std::min<uint32_t>(want_groups, n_regions / 2));
+        uint64_t total_reads = 0, seen = 0;
+        for (uint32_t i = 0; i < n_regions; ++i) total_reads += regions[i].reads.n;
+        gstart.push_back(0);
+        for (uint32_t i = 0; i < n_regions; ++i) {
+            // a group ends where the running share of the records passes the next multiple of 1 / G
+            if (i > 0 && gstart.size() < G && seen * G >= (uint64_t)gstart.size() * total_reads) gstart.push_back(i);
+            seen += regions[i].reads.n;
+        }
+        gstart.push_back(n_regions);
+        aggs.resize(n_regions, nullptr);
+    }
+    std::vector<uint8_t> batched(n_regions, 0);
+    uint32_t g_cur = 0;
     uint64_t off = 0;
     for (uint32_t i = 0; i < n_regions; ++i) {
         const cnvb_region *r = &regions[i];
         const uint64_t rows = rows_of(opts, kind, r);
         if (fan) ctx->stream = ctx->side[ref_batched ? i % 2 : i % 3];
+        if (gw_try) {
+            while (i >= gstart[g_cur + 1]) ++g_cur;
+            if (fan) ctx->stream = ctx->side[g_cur % 2];
+            if (i == gstart[g_cur]) {  // the group's aggregators, then its records in one launch
+                const uint32_t g0 = gstart[g_cur], g1 = gstart[g_cur + 1];
+                for (uint32_t q = g0; q < g1; ++q) {
+                    const cnvb_region *rq = &regions[q];
+                    const int rc = cnvb_cov_create(ctx, opts, kind, rq->region_end, rq->tgt_start, rq->tgt_end, rq->n_tgt,
+                                                   rq->pile_start, rq->pile_end, rq->n_pile, &aggs[q]);
+                    if (rc) return cleanup(rc);
+                }
+                static const int beside = [] {
+                    const char *e = getenv("CNVB_GW_BESIDE");
+                    return e ? atoi(e) : 2;
+                }();
+                const int rc = gw_batch_put(ctx, aggs.data() + g0, &regions[g0].reads, sizeof(cnvb_region), g1 - g0,
+                                            fan && ref_batched ? beside : 0);
+                if (rc < 0) return cleanup(rc);
+                for (uint32_t q = g0; q < g1; ++q) batched[q] = rc == 0;
+            }
+        }
         // lib.rs:440-454: GC content and gap flag per window from the contig bytes
         if (r->seq && (d.gc || d.gap) && !ref_batched) {
             if (!d.gc || !d.gap)
@@ -226,12 +284,15 @@ int coverage_run_impl(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const 
             if (rc) return cleanup(rc);
         }
         // lib.rs:510-529, :547, :560-561
-        cnvb_cov *agg = nullptr;
-        int rc = cnvb_cov_create(ctx, opts, kind, r->region_end, r->tgt_start, r->tgt_end, r->n_tgt,
+        cnvb_cov *agg = gw_try ? aggs[i] : nullptr;
+        int rc = 0;
+        if (!gw_try) {
+            rc = cnvb_cov_create(ctx, opts, kind, r->region_end, r->tgt_start, r->tgt_end, r->n_tgt,
                                  r->pile_start, r->pile_end, r->n_pile, &agg);
-        if (rc) return cleanup(rc);
-        aggs.push_back(agg);
-        if ((rc = cnvb_cov_put_records(agg, &r->reads)) != 0 || (rc = cnvb_cov_finish_async(agg)) != 0 ||
+            if (rc) return cleanup(rc);
+            aggs.push_back(agg);
+        }
+        if ((!batched[i] && (rc = cnvb_cov_put_records(agg, &r->reads)) != 0) || (rc = cnvb_cov_finish_async(agg)) != 0 ||
             (rc = cnvb_cov_get_stats(agg, d.rcv + off, d.rcvsd ? d.rcvsd + off : nullptr, d.start + off,
                                      d.end + off, d.frm ? d.frm + off : nullptr, d.mq ? d.mq + off : nullptr,
                                      CNVB_MEM_DEVICE)) != 0)

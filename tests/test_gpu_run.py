@@ -34,8 +34,11 @@ def _regions(device, with_targets=False):
     return out, raw
 
 
-@pytest.mark.parametrize("device", [None, "cuda"])
-def test_region_loop_fragments_gw(oracle, ctx, device):
+@pytest.mark.parametrize("device,batch", [(None, "0"), ("cuda", "0"), ("cuda", "1")])
+def test_region_loop_fragments_gw(oracle, ctx, device, batch, monkeypatch):
+    """(batch = 1: the records of all regions of a group in one launch, CNVB_GW_BATCH -- off by default, run.cu.)"""
+    monkeypatch.setenv("CNVB_GW_BATCH", batch)
+    monkeypatch.setenv("CNVB_GW_GROUPS", "2")
     wl = 500
     regions, raw = _regions(device)
     opts = cb.CoverageOptions(window_length=wl, min_mapq=10)
