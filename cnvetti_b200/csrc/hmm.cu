@@ -181,13 +181,30 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_matrix_kernel(VitArgs
 #pragma unroll
             for (int c = 0; c < K; ++c) d[r][c] = (r == c ? stay : move) + e[c];
     }
+    // Once the best paths from all five entry states have merged -- with data that speaks for one state a move
+    // is paid once and staying wrong is paid per bin, so after two or three bins -- the matrix has rank one in
+    // (max,+): d[r][c] = a[r] + d[0][c].  A product of a rank-one matrix with anything stays rank one, so from
+    // there on only row 0 is carried (13 instead of 65 instructions per bin beside the 35 of the emissions) and
+    // the rows are put back at the end: the same integers, (max,+) being exactly associative.  The test costs 35
+    // instructions and runs after bins 3, 7, 15 and 31; a warp switches when all its chunks have merged (either
+    // form gives the same matrix, so the vote is about speed only).
+    bool merged = false;
+    int arow[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) arow[r] = 0;
     for (uint32_t i = 1; i < p.len; ++i) {
         emit_scores(x[i], em, e);
+        if (merged) {
+            const int m = __vimax3_s32(__vimax3_s32(d[0][0], d[0][1], d[0][2]), d[0][3], d[0][4]) + move;
 #pragma unroll
-        for (int r = 0; r < K; ++r) {  // DPX: three-way max and fused add-max
-            const int m = __vimax3_s32(__vimax3_s32(d[r][0], d[r][1], d[r][2]), d[r][3], d[r][4]) + move;
+            for (int c = 0; c < K; ++c) d[0][c] = __viaddmax_s32(d[0][c], stay, m) + e[c];
+        } else {
 #pragma unroll
-            for (int c = 0; c < K; ++c) d[r][c] = __viaddmax_s32(d[r][c], stay, m) + e[c];
+            for (int r = 0; r < K; ++r) {  // DPX: three-way max and fused add-max
+                const int m = __vimax3_s32(__vimax3_s32(d[r][0], d[r][1], d[r][2]), d[r][3], d[r][4]) + move;
+#pragma unroll
+                for (int c = 0; c < K; ++c) d[r][c] = __viaddmax_s32(d[r][c], stay, m) + e[c];
+            }
         }
         if ((i & 15u) == 0u) {  // keep the scores small: a common constant changes no decision
             int g = d[0][0];
@@ -196,8 +213,26 @@ __global__ void __launch_bounds__(kChunkThreads) hmm_chunk_matrix_kernel(VitArgs
 #pragma unroll
             for (int r = 0; r < K; ++r)
 #pragma unroll
-                for (int c = 0; c < K; ++c) d[r][c] -= g;
+                for (int c = 0; c < K; ++c) d[r][c] -= g;  // (merged: rows 1.. are dead, the compiler drops them)
         }
+        if (!merged && (i == 3u || i == 7u || i == 15u || i == 31u)) {
+            bool one = true;
+#pragma unroll
+            for (int r = 1; r < K; ++r)
+#pragma unroll
+                for (int c = 1; c < K; ++c) one = one && (d[r][c] - d[0][c]) == (d[r][0] - d[0][0]);
+            if (__all_sync(__activemask(), one)) {
+                merged = true;
+#pragma unroll
+                for (int r = 1; r < K; ++r) arow[r] = d[r][0] - d[0][0];
+            }
+        }
+    }
+    if (merged) {
+#pragma unroll
+        for (int r = 1; r < K; ++r)
+#pragma unroll
+            for (int c = 0; c < K; ++c) d[r][c] = arow[r] + d[0][c];
     }
     {
         int g = d[0][0];
