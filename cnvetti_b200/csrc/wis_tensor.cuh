@@ -9,12 +9,13 @@
 //            round to fp16: H[T][Kp].  Per row keep n_t = |h_t|^2 and delta_t = |u_t - h_t|
 //            (the actual rounding error norm), so that for the real distance D and the fp16
 //            distance d_h:  | D_ij - d_h,ij | <= delta_i + delta_j   (triangle inequality).
-//   sweep    wis_sweep_kernel: one CTA per 256 target rows, A operand resident in shared memory
-//            (TMA, 128B swizzle), B tiles of 128 columns streamed by TMA through an mbarrier
-//            ring, tcgen05.mma (cta_group::1, M128 N128 K16, fp16 x fp16 -> fp32) into
-//            double-buffered TMEM accumulators; 4 epilogue warps read them back with tcgen05.ld
-//            and test  n_j - 2 g_ij <= theta'_i  (one FFMA + one compare per pair), appending the
-//            rare survivors to the row's candidate buffer in HBM.
+//   sweep    one CTA per 256 target rows, column tiles of 128 streamed by TMA through an mbarrier ring,
+//            tcgen05.mma (cta_group::1, K16, fp16 x fp16 -> fp32) into TMEM accumulators, 16 epilogue warps
+//            read them back with tcgen05.ld and test  n'_j - 2 g_ij <= theta_i + kappa_i smax, appending the
+//            survivors to the row's candidate buffer in HBM.  Two kernels: up to 125 samples the rows' operand
+//            stays in shared memory and the column norms ride in the contraction (wis_resident.cuh); beyond
+//            that both operands stream K block by K block (wis_sweep_kernel below: CTA pairs with TMA
+//            multicast, transposed M128 x N256 tiles for large panels).
 //   order    rows are sorted by their projection p_t on the all-ones direction (the panel's first
 //            principal direction: targets differ mostly by capture efficiency).  A projection is
 //            1-Lipschitz, |p_i - p_j| <= D_ij, so a column can only be among the k nearest of row
@@ -420,7 +421,6 @@ template <bool FIRST, int CL, bool XPOSE>
 __global__ void __launch_bounds__(kSweepThreads, 1)
 wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const SweepArgs a) {
-    constexpr bool STREAM = true;  // (the form with the rows' operand resident in shared memory gave way to wis_resident.cuh)
     constexpr bool CLUSTER = CL > 1;
     static_assert(CL == 1 || CL == 2 || CL == 4, "clusters of 2 or 4 CTAs");
     static_assert(!XPOSE || !FIRST, "the transposed tile exists for the later rounds");
@@ -440,7 +440,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #define CNVB_TILE_AT(it) CNVB_TILE_G((uint32_t)CL * (it) + crank)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t s_cnt[kTileRows];  // candidates collected so far per row of this CTA
-    __shared__ __align__(16) float s_col[STREAM ? kEpiWarps : 1][64];  // STREAM: per-warp column operands (n'_j | q_j)
+    __shared__ __align__(16) float s_col[kEpiWarps][64];  // per-warp column operands (n'_j | q_j)
     __shared__ __align__(16) float4 s_row[XPOSE ? kTileRows : 1];      // XPOSE: per-row operands (q_i, theta_i, kappa_i)
     __shared__ __align__(16) float2 s_rq[XPOSE ? kEpiWarps : 1][64];   // XPOSE: per warp and tile, (q_i, theta_i + kappa_i smax)
     // carve: A tiles [n_kblocks][2 row halves] x 16 KB (the halves of a K-block adjacent: one N = 256 operand) | B ring | barriers
@@ -463,7 +463,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (uint32_t t = threadIdx.x; t < kTileRows; t += blockDim.x) {
             const uint32_t row = row0 + t;
             const bool live = row < a.rows;
-            s_row[t] = make_float4((live && STREAM) ? a.psorted[a.rows_a ? a.rows_a[row] : row] : 0.0f,
+            s_row[t] = make_float4(live ? a.psorted[a.rows_a ? a.rows_a[row] : row] : 0.0f,
                                    live ? a.thr[row] : -__int_as_float(0x7f800000), live ? a.kap[row] : 0.0f, 0.0f);
         }
 
@@ -494,36 +494,25 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            if (!STREAM) {
-                mbar_expect_tx(bar_a_full, 2 * a.n_kblocks * kTileBytes);
-                for (uint32_t h = 0; h < 2; ++h)
-                    for (uint32_t kb = 0; kb < a.n_kblocks; ++kb)
-                        tma_load_2d(a_base + (kb * 2u + h) * kTileBytes, &tmap_a, bar_a_full, (int32_t)(kb * kKBlock),
-                                    (int32_t)(row0 + h * 128));
-            }
-            constexpr uint32_t n_stages = STREAM ? kStreamStages : kStages;
+            constexpr uint32_t n_stages = kStreamStages;
             uint32_t st = 0, ph = 0;
             for (uint32_t it = 0; it < steps; ++it) {
                 const bool have = it < n_tiles;  // (CLUSTER: the last pass may only serve the peer)
                 const int32_t j0 = have ? (int32_t)(CNVB_TILE_AT(it) * kTileCols) : 0;
                 for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
                     mbar_wait(bar_b_empty + 8 * st, ph ^ 1u);
-                    if (STREAM) {
-                        const uint32_t sb = a_base + st * 3u * kTileBytes;
-                        mbar_expect_tx(bar_b_full + 8 * st, (have ? 3u : 2u) * kTileBytes);
-                        if (CLUSTER) {  // this CTA's share of the rows (256 / CL of them), into all CTAs of the cluster
-                            tma_load_2d_mc(sb + crank * (2u * kTileBytes / CL), &tmap_a, bar_b_full + 8 * st,
-                                           (int32_t)(kb * kKBlock), (int32_t)(row0 + crank * (256u / CL)),
-                                           (uint16_t)((1u << CL) - 1u));
-                        } else {
-                            tma_load_2d(sb, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)row0);
-                            tma_load_2d(sb + kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)(row0 + 128));
-                        }
-                        if (have) tma_load_2d(sb + 2u * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                    const uint32_t sb = a_base + st * 3u * kTileBytes;
+                    mbar_expect_tx(bar_b_full + 8 * st, (have ? 3u : 2u) * kTileBytes);
+                    if (CLUSTER) {  // this CTA's share of the rows (256 / CL of them), into all CTAs of the cluster
+                        tma_load_2d_mc(sb + crank * (2u * kTileBytes / CL), &tmap_a, bar_b_full + 8 * st,
+                                       (int32_t)(kb * kKBlock), (int32_t)(row0 + crank * (256u / CL)),
+                                       (uint16_t)((1u << CL) - 1u));
                     } else {
-                        mbar_expect_tx(bar_b_full + 8 * st, kTileBytes);
-                        tma_load_2d(b_base + st * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                        tma_load_2d(sb, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)row0);
+                        tma_load_2d(sb + kTileBytes, &tmap_a, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), (int32_t)(row0 + 128));
                     }
+                    if (have) tma_load_2d(sb + 2u * kTileBytes, &tmap_b, bar_b_full + 8 * st, (int32_t)(kb * kKBlock), j0);
+                
                     if (++st == n_stages) {
                         st = 0;
                         ph ^= 1u;
@@ -534,106 +523,52 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            if (!STREAM) {
-                mbar_wait(bar_a_full, 0);
-                tc_fence_after();
-            }
-            constexpr uint32_t n_stages = STREAM ? kStreamStages : kStages;
+            constexpr uint32_t n_stages = kStreamStages;
             uint32_t st = 0, ph = 0, as = 0, aph = 0;
-            // descriptors differ from these bases only in the start-address field (16-byte units):
+            // descriptors differ from this base only in the start-address field (16-byte units):
             // +2 per K16 slab inside a 128-byte swizzle row, + bytes / 16 per tile or stage
-            uint64_t adesc[2][kMaxKBlocks];
-#pragma unroll
-            for (uint32_t h = 0; h < 2; ++h)
-#pragma unroll
-                for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) adesc[h][kb] = umma_desc(a_base + (kb * 2u + h) * kTileBytes);
-            const uint64_t bdesc0 = umma_desc(b_base), sdesc0 = umma_desc(a_base);
+            const uint64_t sdesc0 = umma_desc(a_base);
             for (uint32_t it = 0; it < steps; ++it) {
                 const bool have = it < n_tiles;
                 if (have) {
                     mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
                     tc_fence_after();
                 }
-                if (STREAM) {
-                    for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
-                        mbar_wait(bar_b_full + 8 * st, ph);
-                        tc_fence_after();
-                        const uint64_t sd = sdesc0 + (uint64_t)(st * (3u * kTileBytes >> 4));
-                        if (have && XPOSE) {
-                            // one M128 x N256 MMA per K16 slab: the B tile's 128 columns on the M axis, the block's
-                            // 256 rows (two adjacent 16 KB tiles) on the N axis -- 12 KB of operands per 128-cycle
-                            // slot instead of 8 KB per 64-cycle slot
-                            const uint32_t d_tmem = tmem_base + as * kTileRows;
+                for (uint32_t kb = 0; kb < a.n_kblocks; ++kb) {
+                    mbar_wait(bar_b_full + 8 * st, ph);
+                    tc_fence_after();
+                    const uint64_t sd = sdesc0 + (uint64_t)(st * (3u * kTileBytes >> 4));
+                    if (have && XPOSE) {
+                        // one M128 x N256 MMA per K16 slab: the B tile's 128 columns on the M axis, the block's
+                        // 256 rows (two adjacent 16 KB tiles) on the N axis -- 12 KB of operands per 128-cycle
+                        // slot instead of 8 KB per 64-cycle slot
+                        const uint32_t d_tmem = tmem_base + as * kTileRows;
+#pragma unroll
+                        for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
+                            if (kb * (kKBlock / 16) + kk < a.k_mmas)
+                                tc_mma_f16(d_tmem, sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, sd + 2u * kk, kIdescX,
+                                           (kb | kk) != 0u);
+                        }
+                    } else if (have) {
+#pragma unroll
+                        for (uint32_t h = 0; h < 2; ++h) {
+                            const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
 #pragma unroll
                             for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
                                 if (kb * (kKBlock / 16) + kk < a.k_mmas)
-                                    tc_mma_f16(d_tmem, sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, sd + 2u * kk, kIdescX,
-                                               (kb | kk) != 0u);
+                                    tc_mma_f16(d_tmem, sd + (uint64_t)(h * (kTileBytes >> 4)) + 2u * kk,
+                                               sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, kIdesc, (kb | kk) != 0u);
                             }
-                        } else if (have) {
-#pragma unroll
-                            for (uint32_t h = 0; h < 2; ++h) {
-                                const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
-#pragma unroll
-                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                                    if (kb * (kKBlock / 16) + kk < a.k_mmas)
-                                        tc_mma_f16(d_tmem, sd + (uint64_t)(h * (kTileBytes >> 4)) + 2u * kk,
-                                                   sd + (uint64_t)(2u * (kTileBytes >> 4)) + 2u * kk, kIdesc, (kb | kk) != 0u);
-                                }
-                            }
-                        }
-                        // frees the stage (in both CTAs: the peer's producer writes into this one's too)
-                        if (CLUSTER) tc_commit_mc(bar_b_empty + 8 * st, (uint16_t)((1u << CL) - 1u)); else tc_commit(bar_b_empty + 8 * st);
-                        if (++st == n_stages) {
-                            st = 0;
-                            ph ^= 1u;
                         }
                     }
-                } else {
-#pragma unroll
-                    for (uint32_t kb = 0; kb < kMaxKBlocks; ++kb) {
-                        if (kb < a.n_kblocks) {
-                            mbar_wait(bar_b_full + 8 * st, ph);
-                            tc_fence_after();
-                            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kTileBytes >> 4));
-                            if (XPOSE) {  // one M128 x N256 MMA per slab: B tile on the M axis, both row halves on the N axis
-                                const uint32_t d_tmem = tmem_base + as * kTileRows;
-#pragma unroll
-                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                                    if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
-                                        tc_mma_f16(d_tmem, bdesc + 2u * kk, adesc[0][kb] + 2u * kk, kIdescX, (kb | kk) != 0u);
-                                }
-                            } else {
-                            if (a.dbg & 16u) {  // (experiment: the two accumulators alternate MMA by MMA)
-#pragma unroll
-                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-#pragma unroll
-                                    for (uint32_t h = 0; h < 2; ++h) {
-                                        const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
-                                        if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
-                                            tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                            for (uint32_t h = 0; h < 2; ++h) {
-                                const uint32_t d_tmem = tmem_base + (as * 2 + h) * kTileCols;
-#pragma unroll
-                                for (uint32_t kk = 0; kk < kKBlock / 16; ++kk) {
-                                    if (kb * (kKBlock / 16) + kk < a.k_mmas && !(a.dbg & 2u))
-                                        tc_mma_f16(d_tmem, adesc[h][kb] + 2u * kk, bdesc + 2u * kk, kIdesc, (kb | kk) != 0u);
-                                }
-                            }
-                            }
-                            }
-                            tc_commit(bar_b_empty + 8 * st);  // frees the B stage when these MMAs retire
-                            if (++st == n_stages) {
-                                st = 0;
-                                ph ^= 1u;
-                            }
-                        }
+                    // frees the stage (in both CTAs: the peer's producer writes into this one's too)
+                    if (CLUSTER) tc_commit_mc(bar_b_empty + 8 * st, (uint16_t)((1u << CL) - 1u)); else tc_commit(bar_b_empty + 8 * st);
+                    if (++st == n_stages) {
+                        st = 0;
+                        ph ^= 1u;
                     }
                 }
+            
                 if (have) {
                     tc_commit(bar_acc_full + 8 * as);  // accumulators of this tile complete
                     if (++as == 2) {
@@ -659,7 +594,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (uint32_t it = 0; it < n_tiles; ++it) {
                 const uint32_t tile = CNVB_TILE_AT(it);
                 const uint32_t j = tile * kTileCols + q * 32u + lane;
-                const float nj = __ldg(a.nprime + j), pj = STREAM ? __ldg(a.psorted + j) : 0.0f;
+                const float nj = __ldg(a.nprime + j), pj = __ldg(a.psorted + j);
                 const float smax = __ldg(a.tile_smax + tile);
                 s_rq[e][lane] = make_float2(ro0.x, fmaf(ro0.z, smax, ro0.y));
                 s_rq[e][32u + lane] = make_float2(ro1.x, fmaf(ro1.z, smax, ro1.y));
@@ -667,7 +602,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (it + 1 < n_tiles) {
                     const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + q * 32u;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
-                    if (STREAM) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
                 }
                 mbar_wait(bar_acc_full + 8 * as, aph);
                 tc_fence_after();
@@ -684,8 +619,8 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const float4 two = *reinterpret_cast<const float4 *>(&s_rq[e][32 * h + c]);
                         const float d0 = __fsub_rz(pj, two.x), d1 = __fsub_rz(pj, two.z);
                         const float w0 = fmaf(-2.0f, __uint_as_float(r[c]), nj), w1 = fmaf(-2.0f, __uint_as_float(r[c + 1]), nj);
-                        const float v0 = STREAM ? __fmaf_rd(d0, d0, w0) : w0;  // (ortho mode only with streamed operands)
-                        const float v1 = STREAM ? __fmaf_rd(d1, d1, w1) : w1;
+                        const float v0 = __fmaf_rd(d0, d0, w0);
+                        const float v1 = __fmaf_rd(d1, d1, w1);
                         r[c] = __float_as_uint(v0);
                         r[c + 1] = __float_as_uint(v1);
                         gmask |= (v0 <= two.y || v1 <= two.w) ? (1u << (c >> 2)) : 0u;
@@ -742,7 +677,7 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             trow[h] = 0xFFFFFFFEu;
             qrow[h] = 0.0f;
             if (FIRST && live) trow[h] = a.tid_sorted[a.rows_a ? a.rows_a[row] : row];
-            if (STREAM && live) qrow[h] = a.psorted[a.rows_a ? a.rows_a[row] : row];
+            if (live) qrow[h] = a.psorted[a.rows_a ? a.rows_a[row] : row];
         }
         uint32_t as = 0, aph = 0;
         for (uint32_t it = 0; it < n_tiles; ++it) {
@@ -750,31 +685,20 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t j0 = tile * kTileCols + cpart * 32u;
             // column operands of this warp's 32 columns (same addresses for all lanes: L1 broadcast)
             float nj[32];
-            if (!STREAM) {
-                const float4 *nj4 = reinterpret_cast<const float4 *>(a.nprime + j0);
-#pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    const float4 v = __ldg(nj4 + g4);
-                    nj[4 * g4 + 0] = v.x;
-                    nj[4 * g4 + 1] = v.y;
-                    nj[4 * g4 + 2] = v.z;
-                    nj[4 * g4 + 3] = v.w;
-                }
-            } else {
-                // ortho mode needs two operands per column; 64 registers for them beside the 32 accumulator
-                // values would spill.  Each lane fetches one column's pair (two coalesced 128-byte loads, before
-                // the accumulator wait) into the warp's own shared-memory strip, and the values come back four
-                // at a time as broadcast LDS.128 while the accumulators are consumed.
-                s_col[e][lane] = __ldg(a.nprime + j0 + lane);
-                s_col[e][32 + lane] = __ldg(a.psorted + j0 + lane);
-                __syncwarp();
-            }
+            // ortho mode needs two operands per column; 64 registers for them beside the 32 accumulator
+            // values would spill.  Each lane fetches one column's pair (two coalesced 128-byte loads, before
+            // the accumulator wait) into the warp's own shared-memory strip, and the values come back four
+            // at a time as broadcast LDS.128 while the accumulators are consumed.
+            s_col[e][lane] = __ldg(a.nprime + j0 + lane);
+            s_col[e][32 + lane] = __ldg(a.psorted + j0 + lane);
+            __syncwarp();
+        
             const float smax = __ldg(a.tile_smax + tile);
             if (it + 1 < n_tiles) {  // the next tile's column operands: in L1 by the time they are needed
                 const uint32_t jn = CNVB_TILE_AT(it + 1) * kTileCols + cpart * 32u;
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(a.nprime + jn));
                 if (FIRST) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.tid_sorted + jn));
-                if (STREAM) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.psorted + jn));
             }
             uint32_t tj[FIRST ? 32 : 1];
             if (FIRST) {
@@ -802,28 +726,27 @@ wis_sweep_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
                 }
-                if (STREAM) {
-                    // ortho mode: r[c] <- n'_j - 2 g + (q_j - q_i)^2.  The difference is rounded towards zero
-                    // and the FMA down, so the value never exceeds the exact one: a column that passes the
-                    // exact test passes this one, and the stored value is a lower bound (the compaction
-                    // inflates it for the upper bound).
+                // ortho mode: r[c] <- n'_j - 2 g + (q_j - q_i)^2.  The difference is rounded towards zero
+                // and the FMA down, so the value never exceeds the exact one: a column that passes the
+                // exact test passes this one, and the stored value is a lower bound (the compaction
+                // inflates it for the upper bound).
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 nv = *reinterpret_cast<const float4 *>(&s_col[e][4 * g4]);
-                        const float4 pv = *reinterpret_cast<const float4 *>(&s_col[e][32 + 4 * g4]);
-                        const float d0 = __fsub_rz(pv.x, qrow[h]), d1 = __fsub_rz(pv.y, qrow[h]);
-                        const float d2 = __fsub_rz(pv.z, qrow[h]), d3 = __fsub_rz(pv.w, qrow[h]);
-                        r[4 * g4 + 0] = __float_as_uint(__fmaf_rd(d0, d0, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nv.x)));
-                        r[4 * g4 + 1] = __float_as_uint(__fmaf_rd(d1, d1, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nv.y)));
-                        r[4 * g4 + 2] = __float_as_uint(__fmaf_rd(d2, d2, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nv.z)));
-                        r[4 * g4 + 3] = __float_as_uint(__fmaf_rd(d3, d3, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nv.w)));
-                    }
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    const float4 nv = *reinterpret_cast<const float4 *>(&s_col[e][4 * g4]);
+                    const float4 pv = *reinterpret_cast<const float4 *>(&s_col[e][32 + 4 * g4]);
+                    const float d0 = __fsub_rz(pv.x, qrow[h]), d1 = __fsub_rz(pv.y, qrow[h]);
+                    const float d2 = __fsub_rz(pv.z, qrow[h]), d3 = __fsub_rz(pv.w, qrow[h]);
+                    r[4 * g4 + 0] = __float_as_uint(__fmaf_rd(d0, d0, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 0]), nv.x)));
+                    r[4 * g4 + 1] = __float_as_uint(__fmaf_rd(d1, d1, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 1]), nv.y)));
+                    r[4 * g4 + 2] = __float_as_uint(__fmaf_rd(d2, d2, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 2]), nv.z)));
+                    r[4 * g4 + 3] = __float_as_uint(__fmaf_rd(d3, d3, fmaf(-2.0f, __uint_as_float(r[4 * g4 + 3]), nv.w)));
                 }
+            
                 // the values under test, v_c = n'_j - 2 g (already formed in ortho mode)
                 float v[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    v[c] = STREAM ? __uint_as_float(r[c]) : fmaf(-2.0f, __uint_as_float(r[c]), nj[c]);
+                    v[c] = __uint_as_float(r[c]);
                 const uint32_t row = row0 + rloc[h];
                 uint2 *cand = a.cand + (size_t)row * kCandCap;  // (rows beyond a.rows never pass: thr = -inf)
                 const float inf = __int_as_float(0x7f800000);
