@@ -71,6 +71,8 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=2000, help="wis: rows of the CPU baseline sample")
     ap.add_argument("--cpu-sample-contigs", type=int, default=4, help="last k contigs form the CPU sample")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the one-sample-per-GPU side measurement")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="default workload: eager region loop in the timed steps instead of the CUDA-graph plan")
     return ap.parse_args()
 
 
@@ -1135,6 +1137,38 @@ def bench_coverage(args, env):
             in_flight.pop(0).wait()
     step_device.flush = flush
 
+    # The timed steps replay the region loop as a CUDA graph (cnvb_coverage_plan_*: one launch instead of ~10 API
+    # calls per region -- on 8 GPUs, with 2 - 3 small regions per rank, the eager loop is bound by the host's
+    # enqueueing); two plans alternate so that the tallies and reference-panic checks of step i are still collected
+    # while step i + 1 runs.  The normaliser (with its all-reduces) follows eagerly on the same stream.
+    # --no-graph: the eager loop above; the per-kernel timing pass always uses the eager loop.
+    plans = []
+    if not args.no_graph:
+        try:
+            plans = [pipeline.CoveragePlan(prep_dev, opts, ctx=ctx) for _ in range(2)]
+        except Exception as exc:  # (reported in the line: `graph` false)
+            env.log("coverage plan unavailable, eager steps: %s" % exc)
+            plans = []
+    plan_turn = [0]
+    plan_busy = []
+
+    def step_graph():
+        p = plans[plan_turn[0] % 2]
+        plan_turn[0] += 1
+        if p in plan_busy:      # (its previous launch: two steps back)
+            plan_busy.remove(p)
+            p.wait()
+        tt = p.launch()
+        pipeline.normalize_run(tt, "MedianGcBinned", ctx=ctx, comm=shard, want_medians=False)
+        plan_busy.append(p)
+        return tt
+
+    def flush_graph():
+        while plan_busy:
+            plan_busy.pop(0).wait()
+    step_graph.flush = flush_graph
+    step_timed = step_graph if plans else step_device
+
     # correctness guard on the full-size run: every counted fragment lands in exactly one window
     t = step_device()
     flush()
@@ -1143,7 +1177,14 @@ def bench_coverage(args, env):
     n_windows_local = int(t.rcv.numel())
     n_windows = int(env.sum_over_ranks(n_windows_local))
     sampler = ClockSampler(env.local)  # armed before the warm-up (nvidia-smi needs ~100 ms to come up)
-    ms_max, launches, clocks = timed_steps(env, step_device, args.steps, max(0, args.warmup - 1), sampler)
+    if plans:  # the planned loop must deliver what the eager loop delivered above
+        tg = step_graph()
+        flush_graph()
+        torch.cuda.synchronize()
+        assert tg.num_processed == t.num_processed and tg.num_skipped == t.num_skipped, "planned loop: tallies"
+        same = lambda a, b: torch.equal(a.view(torch.int32), b.view(torch.int32))  # noqa: E731  (bits: missing values are NaNs)
+        assert same(tg.rcv, t.rcv) and same(tg.cv, t.cv) and torch.equal(tg.norm_flags, t.norm_flags), "planned loop: columns"
+    ms_max, launches, clocks = timed_steps(env, step_timed, args.steps, max(0, args.warmup - 1), sampler)
     kern, ms_serial = kernel_times(env, step_device, args.steps,
                                    ("frag_bin_gw_kernel", "refstats_lut_kernel", "gc_radix_hist_kernel",
                                     "gc_radix_pick_kernel", "norm_gc_map_kernel", "cov_records_kernel"))
@@ -1154,7 +1195,7 @@ def bench_coverage(args, env):
         if rank == 0:
             return {"metric": "aligned reads/s binned", "value": value, "unit": "reads/s", "n_gpus": world,
                     "ms_per_step": ms_max, "gpu_launches": launches, "ms_per_step_serialised": ms_serial, "kernels": kern,
-                    "quick": True, "scaling": "strong" if world > 1 else "weak"}, 0
+                    "quick": True, "scaling": "strong" if world > 1 else "weak", "graph": bool(plans)}, 0
         return None, 0
 
     # ---- end to end: pinned host SoA in, table out ---------------------------------------------------------
@@ -1297,7 +1338,11 @@ def bench_coverage(args, env):
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "host_memory": "pinned" if all_pinned else "pageable (pinning refused)"},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches,
+            "graph": {"used": bool(plans), "what": "the timed steps replay the region loop as a CUDA graph (cnvb_coverage_plan_*), "
+                      "two plans alternating; the normaliser follows eagerly; gpu_launches counts the kernels inside the "
+                      "replays; --no-graph runs the eager loop"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "kernels": kern, "gen_seconds": gen_s, "checks": checks, "replicas": replicas,
             "host_bam_decode": host_bam_decode_leg(),
         }

@@ -136,6 +136,11 @@ SYMBOLS = {
     "cnvb_coverage_run_async": (_int, [_vp, C.POINTER(CovOpts), _int, C.POINTER(Region), _u32,
                                        C.POINTER(CovColumns), C.POINTER(_vp)]),
     "cnvb_coverage_wait": (_int, [_vp, _vp, _vp]),
+    "cnvb_coverage_plan_create": (_int, [_vp, C.POINTER(CovOpts), _int, C.POINTER(Region), _u32,
+                                         C.POINTER(CovColumns), C.POINTER(_vp)]),
+    "cnvb_coverage_plan_launch": (_int, [_vp]),
+    "cnvb_coverage_plan_wait": (_int, [_vp, _vp, _vp]),
+    "cnvb_coverage_plan_destroy": (None, [_vp]),
     "cnvb_piles_collect": (_int, [_vp, C.POINTER(ReadSoa), C.POINTER(CovOpts), _u32, _u32, C.POINTER(_vp)]),
     "cnvb_piles_count": (_u64, [_vp]),
     "cnvb_piles_get": (_int, [_vp, _vp, _vp, _vp, _int]),

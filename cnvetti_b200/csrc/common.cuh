@@ -62,6 +62,12 @@ struct cnvb_ctx {
     std::vector<std::string> span_names;
     std::vector<cnvb_span> spans;
     std::vector<cudaEvent_t> event_pool;
+    // a coverage plan is being captured into a CUDA graph (run.cu: cnvb_coverage_plan_create): blocks released
+    // meanwhile are HELD (the graph's nodes keep using them at every replay), host tables the graph reads and
+    // the tally slots live in pinned memory the plan owns
+    bool capturing = false;
+    std::vector<void *> capture_hold;     // device blocks released during the capture
+    std::vector<void *> capture_pinned;   // cudaMallocHost blocks
 };
 
 namespace cnvb {
@@ -69,6 +75,9 @@ namespace cnvb {
 int refstats_prepare(cnvb_ctx *ctx);  // refstats.cu: builds the classification table on ctx->stream if missing
 // refstats.cu: reference statistics of all regions in one launch; 1 = not applicable (go region by region)
 // FragmentsGenomeWide records of all regions of a run in one launch (coverage.cu); 1 = does not apply
+// coverage.cu: the tallies and reference-panic checks of an aggregator whose stream work is known to be complete
+// (cnvb_cov_finish without the event wait: a plan synchronises once for all its aggregators)
+int cov_collect(cnvb_cov *a);
 int gw_batch_put(cnvb_ctx *ctx, cnvb_cov *const *aggs, const cnvb_read_soa *batches, size_t batch_stride, uint32_t n,
                  int ctas_per_sm);
 int refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const *seq, const uint64_t *len, const uint64_t *out_off,
@@ -202,6 +211,8 @@ constexpr uint32_t kTallySlots = 4096;
 // A block released on the stream that now asks is reused as is; a block released on ANOTHER stream is
 // handed out only after the asking stream has been ordered behind everything enqueued on the
 // releasing stream so far (event record + wait, no host synchronisation).
+// (a block tagged kPoolQuiescent was released before the last device-wide synchronisation: no ordering needed)
+static const cudaStream_t kPoolQuiescent = reinterpret_cast<cudaStream_t>(~(uintptr_t)0);
 inline cudaError_t pool_alloc(cnvb_ctx *ctx, size_t bytes, void **out) {
     size_t cls = 512;
     while (cls < bytes) cls <<= 1;
@@ -215,7 +226,7 @@ inline cudaError_t pool_alloc(cnvb_ctx *ctx, size_t bytes, void **out) {
                 break;
             }
         const cnvb_ctx::pool_block b = v[pick];
-        if (b.released_on != ctx->stream) {
+        if (b.released_on != ctx->stream && b.released_on != kPoolQuiescent) {
             cudaError_t e = cudaSuccess;
             if (!ctx->pool_event) e = cudaEventCreateWithFlags(&ctx->pool_event, cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventRecord(ctx->pool_event, b.released_on);
@@ -244,8 +255,26 @@ inline void pool_release(cnvb_ctx *ctx, void *p) {
     if (!p) return;
     auto it = ctx->pool_live.find(p);
     if (it == ctx->pool_live.end()) return;
+    if (ctx->capturing) {  // the captured work uses the block at every replay: it stays out of circulation
+        ctx->capture_hold.push_back(p);
+        return;
+    }
     ctx->pool_free[it->second].push_back({p, ctx->stream});
     ctx->pool_live.erase(it);
+}
+// after a device-wide synchronisation: every free block may go to any stream without an ordering event
+inline void pool_quiesce(cnvb_ctx *ctx) {
+    for (auto &kv : ctx->pool_free)
+        for (auto &b : kv.second) b.released_on = kPoolQuiescent;
+}
+// pinned host memory that lives as long as the plan under capture (nullptr when none is being captured)
+inline void *capture_pin(cnvb_ctx *ctx, const void *src, size_t bytes) {
+    if (!ctx->capturing) return nullptr;
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    if (src) memcpy(p, src, bytes); else memset(p, 0, bytes);
+    ctx->capture_pinned.push_back(p);
+    return p;
 }
 inline void pool_destroy(cnvb_ctx *ctx) {
     for (auto &kv : ctx->pool_free)

@@ -463,6 +463,13 @@ extern "C" int cnvb_cov_create(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kin
     a->kind = kind;
     a->region_end = region_end;
     a->h_tally = ctx->tally_slots + 4 * (ctx->tally_next++ % kTallySlots);
+    if (ctx->capturing) {  // (a plan's aggregators outlive any number of other calls: their own slot)
+        a->h_tally = static_cast<uint32_t *>(capture_pin(ctx, nullptr, 16));
+        if (!a->h_tally) {
+            delete a;
+            return fail(ctx, CNVB_ERR_NOMEM, "pinned tally slot");
+        }
+    }
     if (kind == CNVB_FRAGMENTS_TARGET_REGIONS) {
         a->num_regions = n_tgt;
         a->n_tgt = n_tgt;
@@ -524,6 +531,8 @@ extern "C" int cnvb_cov_create(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kin
         a->n_pile = n_pile;
     }
     // caller-owned host arrays may be freed after we return
+    if (uploaded && ctx->capturing)
+        return bail(fail(ctx, CNVB_ERR_INVALID, "a coverage plan takes regions without per-region host tables (targets, piles)"));
     if (uploaded && (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
         return bail(fail_cuda(ctx, e, "initialising aggregator"));
     *out = a;
@@ -726,6 +735,12 @@ extern "C" int cnvb_cov_finish(cnvb_cov *a) {
     if (a->state == 2) return a->finish_rc;
     CNVB_TRY(cnvb_cov_finish_async(a));
     CNVB_CUDA(ctx, cudaEventSynchronize(a->done), "finishing aggregator");
+    return cov_collect(a);
+}
+
+int cnvb::cov_collect(cnvb_cov *a) {
+    if (!a) return CNVB_ERR_INVALID;
+    cnvb_ctx *ctx = a->ctx;
     memcpy(a->h_stats, a->h_tally, 16);
     a->state = 2;
     a->finish_rc = CNVB_OK;

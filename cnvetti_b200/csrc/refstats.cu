@@ -431,8 +431,17 @@ int cnvb::refstats_batch_device(cnvb_ctx *ctx, uint32_t n, const uint8_t *const 
     RefRegion *d_regs = nullptr;
     cudaError_t e = pool_alloc_t(ctx, (size_t)n, &d_regs);
     if (e != cudaSuccess) return fail_cuda(ctx, e, "allocating the region table");
-    // (pageable source: the copy is staged by the runtime before the call returns, so `regs` may go)
-    e = cudaMemcpyAsync(d_regs, regs.data(), n * sizeof(RefRegion), cudaMemcpyHostToDevice, ctx->stream);
+    // (pageable source: the copy is staged by the runtime before the call returns, so `regs` may go; under a
+    // plan's capture the copy is a graph node that reads its source at every replay: pinned, owned by the plan)
+    const void *src = regs.data();
+    if (ctx->capturing) {
+        src = capture_pin(ctx, regs.data(), n * sizeof(RefRegion));
+        if (!src) {
+            pool_release(ctx, d_regs);
+            return fail(ctx, CNVB_ERR_NOMEM, "pinned region table");
+        }
+    }
+    e = cudaMemcpyAsync(d_regs, src, n * sizeof(RefRegion), cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) {
         pool_release(ctx, d_regs);
         return fail_cuda(ctx, e, "uploading the region table");

@@ -374,3 +374,125 @@ extern "C" int cnvb_coverage_wait(cnvb_cov_pending *p, uint64_t *num_processed, 
     delete p;
     return rc;
 }
+
+// ---- the region loop as a CUDA graph --------------------------------------------------------------------
+// Repeated runs over the same device buffers (a pipeline that copies every sample into fixed device columns, the
+// strong-scaling step of bench.py) are bound by the HOST once the regions are small: enqueueing the ~25 operations
+// of a three-region run takes 0.25 ms of CPU, the GPU needs 0.15 ms for them (tools/scale_probe.py on 8 GPUs).  A
+// plan runs the loop once under stream capture -- side streams, memsets, kernels, tally copies and all -- and
+// replays the instantiated graph with ONE launch.  Everything the graph touches is owned by the plan: the
+// aggregators, the pooled temporaries, the blocks released during the capture, the pinned tables and tally slots.
+struct cnvb_cov_plan {
+    cnvb_ctx *ctx = nullptr;
+    cnvb_cov_pending *pending = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t done = nullptr;  // recorded behind every launch: plan_wait waits for the plan's own work only
+    uint64_t kernels = 0;        // kernel launches one replay stands for (cnvb_ctx_launch_count counts those)
+    std::vector<void *> hold, pinned;
+};
+
+extern "C" void cnvb_coverage_plan_destroy(cnvb_cov_plan *p) {
+    if (!p) return;
+    cnvb_ctx *ctx = p->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    if (p->done) cudaEventDestroy(p->done);
+    if (p->pending) {
+        for (cnvb_cov *a : p->pending->aggs) cnvb_cov_destroy(a);
+        for (void *t : p->pending->temps) pool_release(ctx, t);
+        delete p->pending;
+    }
+    for (void *b : p->hold) pool_release(ctx, b);
+    for (void *h : p->pinned) cudaFreeHost(h);
+    delete p;
+}
+
+extern "C" int cnvb_coverage_plan_create(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
+                                         uint32_t n_regions, const cnvb_cov_columns *out, cnvb_cov_plan **plan) {
+    if (!ctx) return CNVB_ERR_INVALID;
+    if (!plan) return fail(ctx, CNVB_ERR_INVALID, "cnvb_coverage_plan_create: null argument");
+    *plan = nullptr;
+    if (ctx->timing) return fail(ctx, CNVB_ERR_STATE, "a plan cannot be built in per-kernel timing mode");
+    if (ctx->capturing) return fail(ctx, CNVB_ERR_STATE, "a plan is already being captured on this context");
+    // one eager run first: pooled blocks of every size the loop asks for, function attributes, the classification
+    // table, the side streams -- nothing is created while the capture is open
+    {
+        cnvb_cov_pending *warm = nullptr;
+        CNVB_TRY(cnvb_coverage_run_async(ctx, opts, kind, regions, n_regions, out, &warm));
+        CNVB_TRY(cnvb_coverage_wait(warm, nullptr, nullptr));
+    }
+    CNVB_CUDA(ctx, cudaDeviceSynchronize(), "before the capture");
+    pool_quiesce(ctx);
+    cnvb_cov_plan *p = new (std::nothrow) cnvb_cov_plan();
+    if (!p) return fail(ctx, CNVB_ERR_NOMEM, "out of host memory");
+    p->ctx = ctx;
+    // the capture runs on a stream of its own (the context's may be the legacy default stream, which cannot be
+    // captured); the graph is launched on the context's stream afterwards
+    cudaStream_t cap = nullptr, user = ctx->stream;
+    cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) {
+        if (cap) cudaStreamDestroy(cap);
+        delete p;
+        return fail_cuda(ctx, e, "opening the capture");
+    }
+    ctx->capturing = true;
+    ctx->stream = cap;
+    const uint64_t launches_before = ctx->launches;
+    const int rc = coverage_run_impl(ctx, opts, kind, regions, n_regions, out, nullptr, nullptr, CNVB_MEM_DEVICE, &p->pending);
+    ctx->stream = user;
+    ctx->capturing = false;
+    p->kernels = ctx->launches - launches_before;
+    ctx->launches = launches_before;  // (captured, not launched)
+    p->hold.swap(ctx->capture_hold);
+    p->pinned.swap(ctx->capture_pinned);
+    e = cudaStreamEndCapture(cap, &p->graph);
+    cudaStreamDestroy(cap);
+    if (rc != CNVB_OK || e != cudaSuccess || !p->graph) {
+        const std::string inner = ctx->err;
+        // (the blocks named in pool_live stay valid; an unfinished capture leaves no work behind)
+        cnvb_coverage_plan_destroy(p);
+        if (rc != CNVB_OK) return fail(ctx, rc, "capturing the region loop\ncaused by: %s", inner.c_str());
+        return fail_cuda(ctx, e != cudaSuccess ? e : cudaErrorUnknown, "closing the capture");
+    }
+    e = cudaGraphInstantiate(&p->exec, p->graph, 0);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cnvb_coverage_plan_destroy(p);
+        return fail_cuda(ctx, e, "instantiating the graph");
+    }
+    *plan = p;
+    return CNVB_OK;
+}
+
+// one run of the planned loop, enqueued on the context's stream; returns at once
+extern "C" int cnvb_coverage_plan_launch(cnvb_cov_plan *p) {
+    if (!p || !p->exec) return CNVB_ERR_INVALID;
+    cnvb_ctx *ctx = p->ctx;
+    CNVB_CUDA(ctx, cudaGraphLaunch(p->exec, ctx->stream), "launching the planned region loop");
+    CNVB_CUDA(ctx, cudaEventRecord(p->done, ctx->stream), "marking the end of the planned region loop");
+    ctx->launches += p->kernels;
+    return CNVB_OK;
+}
+
+// waits for the plan's launches so far (not for later work on the stream); tallies and reference-panic checks of
+// the last one (nullable outputs)
+extern "C" int cnvb_coverage_plan_wait(cnvb_cov_plan *p, uint64_t *num_processed, uint64_t *num_skipped) {
+    if (!p || !p->pending) return CNVB_ERR_INVALID;
+    cnvb_ctx *ctx = p->ctx;
+    CNVB_CUDA(ctx, cudaEventSynchronize(p->done), "waiting for the planned region loop");
+    std::vector<cnvb_cov *> &aggs = p->pending->aggs;
+    for (uint32_t i = 0; i < aggs.size(); ++i) {
+        const int rc = cov_collect(aggs[i]);
+        if (rc) {
+            const std::string inner = ctx->err;
+            return fail(ctx, rc, "region %u\ncaused by: %s", i, inner.c_str());
+        }
+        if (num_processed) num_processed[i] = cnvb_cov_num_processed(aggs[i]);
+        if (num_skipped) num_skipped[i] = cnvb_cov_num_skipped(aggs[i]);
+    }
+    return CNVB_OK;
+}

@@ -166,6 +166,62 @@ def coverage_run(regions, options, ctx=None, device=True, defer=False):
     return t
 
 
+class CoveragePlan:
+    """The region loop over the SAME device buffers again and again, as a CUDA graph (cnvb_coverage_plan_*): for
+    pipelines that copy every sample into fixed device columns, where the host's enqueueing -- not the GPU -- bounds
+    a run over a few small regions.  `table` holds the output columns (allocated once); launch() enqueues one run
+    and returns the table (columns valid in stream order), wait() blocks and fills num_processed / num_skipped.
+    Device-resident regions without targets or piles."""
+
+    def __init__(self, regions, options, ctx=None):
+        import torch
+        self.ctx = ctx or default_context()
+        self.prep = regions if isinstance(regions, PreparedRegions) else PreparedRegions(regions, options)
+        prep, dev = self.prep, "cuda:%d" % self.ctx.device
+        total = prep.offsets[-1]
+        t = CoverageTable()
+        t.offsets, t.names = prep.offsets, prep.names
+        f32 = lambda: torch.empty(total, dtype=torch.float32, device=dev)  # noqa: E731
+        t.start, t.end = (torch.empty(total, dtype=torch.int32, device=dev) for _ in range(2))
+        t.rcv, t.lcv, t.ft = f32(), f32(), torch.empty(total, dtype=torch.uint8, device=dev)
+        if prep.kind == N.COVERAGE:
+            t.rcvsd, t.lcvsd = f32(), f32()
+        if prep.kind == N.FRAGMENTS_GENOME_WIDE:
+            t.frm = f32()
+        if prep.have_ref:
+            t.gc, t.gap = f32(), torch.empty(total, dtype=torch.uint8, device=dev)
+        ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
+        self._cols = N.CovColumns(ptr(t.start), ptr(t.end), ptr(t.rcv), ptr(t.rcvsd), ptr(t.lcv), ptr(t.lcvsd),
+                                  ptr(t.frm), ptr(t.gc), None, ptr(t.gap), ptr(t.ft))
+        self.table = t
+        self._h = C.c_void_p()
+        self.ctx.check(N.lib().cnvb_coverage_plan_create(self.ctx.handle, C.byref(prep.c_opts), prep.kind, prep.array,
+                                                         prep.n, C.byref(self._cols), C.byref(self._h)))
+        self._nproc = np.zeros(max(1, prep.n), np.uint64)
+        self._nskip = np.zeros(max(1, prep.n), np.uint64)
+
+    def launch(self):
+        self.ctx.check(N.lib().cnvb_coverage_plan_launch(self._h))
+        return self.table
+
+    def wait(self):
+        self.ctx.check(N.lib().cnvb_coverage_plan_wait(self._h, self._nproc.ctypes.data, self._nskip.ctypes.data))
+        self.table.num_processed = [int(x) for x in self._nproc[:self.prep.n]]
+        self.table.num_skipped = [int(x) for x in self._nskip[:self.prep.n]]
+        return self.table
+
+    def close(self):
+        if self._h:
+            N.lib().cnvb_coverage_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def normalize_run(table, normalization="MedianGcBinned", ctx=None, comm=None, want_medians=True):
     """`cnvetti cmd normalize` on the table (lib-normalize/src/lib.rs:57-60).  comm: the table holds this
     rank's regions of a sharded run (coverage_run_sharded); the statistics run over all ranks' records."""

@@ -241,6 +241,21 @@ typedef struct cnvb_cov_pending cnvb_cov_pending;
 int cnvb_coverage_run_async(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
                             uint32_t n_regions, const cnvb_cov_columns *out, cnvb_cov_pending **pending);
 int cnvb_coverage_wait(cnvb_cov_pending *pending, uint64_t *num_processed, uint64_t *num_skipped);
+/* The loop of lib_coverage::run (lib.rs:768-781) over the SAME device buffers again and again -- a pipeline that copies
+ * every sample into fixed device columns; the strong-scaling step of bench.py -- as a CUDA graph.  plan_create runs
+ * the loop once eagerly and once under stream capture (device-resident inputs and columns; regions without
+ * per-region host tables, i.e. no targets and no piles) and instantiates the graph; plan_launch enqueues one run on
+ * the context's stream with a single launch and returns; plan_wait blocks until the plan's launches so far are done
+ * (not for work enqueued behind them: two plans can alternate, one waited for while the other runs) and reports the
+ * tallies and reference-panic checks of the last one as cnvb_coverage_run does.  The plan owns everything
+ * the graph touches; the regions' read columns, sequences and the output columns are the caller's and must stay
+ * where they are (their CONTENTS may change between launches, their addresses and lengths may not). */
+typedef struct cnvb_cov_plan cnvb_cov_plan;
+int cnvb_coverage_plan_create(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, const cnvb_region *regions,
+                              uint32_t n_regions, const cnvb_cov_columns *out, cnvb_cov_plan **plan);
+int cnvb_coverage_plan_launch(cnvb_cov_plan *plan);
+int cnvb_coverage_plan_wait(cnvb_cov_plan *plan, uint64_t *num_processed, uint64_t *num_skipped);
+void cnvb_coverage_plan_destroy(cnvb_cov_plan *plan);
 
 /* ---- lib-coverage: pile collection for --mask-piles --------------------------------------- */
 typedef struct cnvb_piles cnvb_piles;

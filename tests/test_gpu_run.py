@@ -126,6 +126,33 @@ def test_region_loop_deferred_equals_synchronous(oracle, ctx):
                               ctx=ctx, defer=True)
 
 
+def test_region_loop_as_a_graph_equals_the_eager_loop(oracle, ctx):
+    """cnvb_coverage_plan_*: the loop captured into a CUDA graph and replayed -- the same columns and tallies as the
+    eager loop, also after the CONTENTS of the inputs changed between launches (addresses and lengths stay)."""
+    import torch
+    regions, raw = _regions("cuda")
+    opts = cb.CoverageOptions(window_length=500, min_mapq=10)
+    eager = pipeline.coverage_run(regions, opts, ctx=ctx)
+    plan = pipeline.CoveragePlan(regions, opts, ctx=ctx)
+    for _ in range(3):
+        plan.launch()
+    t = plan.wait()
+    assert t.num_processed == eager.num_processed and t.num_skipped == eager.num_skipped
+    bits = lambda x: x.view(torch.int32) if x.dtype == torch.float32 else x  # noqa: E731  (missing values are NaNs)
+    for name in ("start", "end", "rcv", "lcv", "frm", "gc", "gap", "ft"):
+        assert torch.equal(bits(getattr(t, name)), bits(getattr(eager, name))), name
+    # other contents in the same buffers: every read of the first region fails the MAPQ filter now
+    regions[0].reads.mapq.zero_()
+    eager2 = pipeline.coverage_run(regions, opts, ctx=ctx)
+    t2 = plan.launch() and plan.wait()
+    assert t2.num_processed == eager2.num_processed and t2.num_processed[0] == 0
+    assert torch.equal(bits(t2.rcv), bits(eager2.rcv)) and torch.equal(bits(t2.lcv), bits(eager2.lcv))
+    plan.close()
+    # eager calls keep working on the context after the plan is gone
+    again = pipeline.coverage_run(regions, opts, ctx=ctx)
+    assert torch.equal(bits(again.rcv), bits(eager2.rcv))
+
+
 def test_region_loop_host_columns_and_panic(oracle, ctx):
     """C ABI called directly with HOST columns; a region that makes the reference panic fails the run."""
     wl = 100
