@@ -1185,6 +1185,10 @@ def bench_coverage(args, env):
         same = lambda a, b: torch.equal(a.view(torch.int32), b.view(torch.int32))  # noqa: E731  (bits: missing values are NaNs)
         assert same(tg.rcv, t.rcv) and same(tg.cv, t.cv) and torch.equal(tg.norm_flags, t.norm_flags), "planned loop: columns"
     ms_max, launches, clocks = timed_steps(env, step_timed, args.steps, max(0, args.warmup - 1), sampler)
+    used_graph = bool(plans)
+    for p_ in plans:  # (their aggregators, tables and pinned slots go back before the other legs allocate)
+        p_.close()
+    plans = []
     kern, ms_serial = kernel_times(env, step_device, args.steps,
                                    ("frag_bin_gw_kernel", "refstats_lut_kernel", "gc_radix_hist_kernel",
                                     "gc_radix_pick_kernel", "norm_gc_map_kernel", "cov_records_kernel"))
@@ -1195,7 +1199,7 @@ def bench_coverage(args, env):
         if rank == 0:
             return {"metric": "aligned reads/s binned", "value": value, "unit": "reads/s", "n_gpus": world,
                     "ms_per_step": ms_max, "gpu_launches": launches, "ms_per_step_serialised": ms_serial, "kernels": kern,
-                    "quick": True, "scaling": "strong" if world > 1 else "weak", "graph": bool(plans)}, 0
+                    "quick": True, "scaling": "strong" if world > 1 else "weak", "graph": used_graph}, 0
         return None, 0
 
     # ---- end to end: pinned host SoA in, table out ---------------------------------------------------------
@@ -1339,7 +1343,7 @@ def bench_coverage(args, env):
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "host_memory": "pinned" if all_pinned else "pageable (pinning refused)"},
             "gpu_launches": launches,
-            "graph": {"used": bool(plans), "what": "the timed steps replay the region loop as a CUDA graph (cnvb_coverage_plan_*), "
+            "graph": {"used": used_graph, "what": "the timed steps replay the region loop as a CUDA graph (cnvb_coverage_plan_*), "
                       "two plans alternating; the normaliser follows eagerly; gpu_launches counts the kernels inside the "
                       "replays; --no-graph runs the eager loop"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
