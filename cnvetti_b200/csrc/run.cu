@@ -415,6 +415,9 @@ extern "C" int cnvb_coverage_plan_create(cnvb_ctx *ctx, const cnvb_cov_opts *opt
     if (!ctx) return CNVB_ERR_INVALID;
     if (!plan) return fail(ctx, CNVB_ERR_INVALID, "cnvb_coverage_plan_create: null argument");
     *plan = nullptr;
+    if (kind != CNVB_FRAGMENTS_GENOME_WIDE)
+        return fail(ctx, CNVB_ERR_INVALID, "a coverage plan exists for genome-wide fragment counts: the other kinds size "
+                                          "their launches from the records (targets tables, the longest alignment)");
     if (ctx->timing) return fail(ctx, CNVB_ERR_STATE, "a plan cannot be built in per-kernel timing mode");
     if (ctx->capturing) return fail(ctx, CNVB_ERR_STATE, "a plan is already being captured on this context");
     // one eager run first: pooled blocks of every size the loop asks for, function attributes, the classification

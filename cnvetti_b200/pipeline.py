@@ -171,7 +171,7 @@ class CoveragePlan:
     pipelines that copy every sample into fixed device columns, where the host's enqueueing -- not the GPU -- bounds
     a run over a few small regions.  `table` holds the output columns (allocated once); launch() enqueues one run
     and returns the table (columns valid in stream order), wait() blocks and fills num_processed / num_skipped.
-    Device-resident regions without targets or piles."""
+    Count kind FragmentsGenomeWide, device-resident regions without piles (the library refuses the rest)."""
 
     def __init__(self, regions, options, ctx=None):
         import torch

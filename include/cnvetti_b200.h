@@ -243,8 +243,8 @@ int cnvb_coverage_run_async(cnvb_ctx *ctx, const cnvb_cov_opts *opts, int kind, 
 int cnvb_coverage_wait(cnvb_cov_pending *pending, uint64_t *num_processed, uint64_t *num_skipped);
 /* The loop of lib_coverage::run (lib.rs:768-781) over the SAME device buffers again and again -- a pipeline that copies
  * every sample into fixed device columns; the strong-scaling step of bench.py -- as a CUDA graph.  plan_create runs
- * the loop once eagerly and once under stream capture (device-resident inputs and columns; regions without
- * per-region host tables, i.e. no targets and no piles) and instantiates the graph; plan_launch enqueues one run on
+ * the loop once eagerly and once under stream capture (count kind FragmentsGenomeWide, device-resident inputs and
+ * columns, no piles: the other kinds size their launches from the records) and instantiates the graph; plan_launch enqueues one run on
  * the context's stream with a single launch and returns; plan_wait blocks until the plan's launches so far are done
  * (not for work enqueued behind them: two plans can alternate, one waited for while the other runs) and reports the
  * tallies and reference-panic checks of the last one as cnvb_coverage_run does.  The plan owns everything

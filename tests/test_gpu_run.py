@@ -153,6 +153,28 @@ def test_region_loop_as_a_graph_equals_the_eager_loop(oracle, ctx):
     assert torch.equal(bits(again.rcv), bits(eager2.rcv))
 
 
+def test_region_loop_plan_refuses_what_it_cannot_capture(oracle, ctx):
+    """A plan exists for genome-wide fragment counts without piles: the other kinds size their launches from the
+    records, per-region host tables cannot be part of a captured loop.  The plan says so instead of building a graph
+    that would go stale, and the context goes on working eagerly."""
+    import torch
+    regions, raw = _regions("cuda", with_targets=True)
+    for opts in (cb.CoverageOptions(window_length=None, considered_regions="TargetRegions", min_raw_coverage=3),
+                 cb.CoverageOptions(window_length=1000, count_kind="Coverage")):
+        eager = pipeline.coverage_run(regions, opts, ctx=ctx)
+        with pytest.raises(N.CnvbError, match="plan"):
+            pipeline.CoveragePlan(regions, opts, ctx=ctx)
+        again = pipeline.coverage_run(regions, opts, ctx=ctx)
+        assert torch.equal(again.rcv.view(torch.int32), eager.rcv.view(torch.int32))
+    # piles: host tables per region
+    gw = cb.CoverageOptions(window_length=500, min_mapq=10)
+    piled = [pipeline.Region(r.name, r.length, r.reads, r.sequence, piles=(np.array([100], np.uint32), np.array([200], np.uint32)))
+             for r in regions]
+    with pytest.raises(N.CnvbError, match="plan"):
+        pipeline.CoveragePlan(piled, gw, ctx=ctx)
+    assert pipeline.coverage_run(piled, gw, ctx=ctx).rcv.numel() > 0
+
+
 def test_region_loop_host_columns_and_panic(oracle, ctx):
     """C ABI called directly with HOST columns; a region that makes the reference panic fails the run."""
     wl = 100
