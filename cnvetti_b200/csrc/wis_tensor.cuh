@@ -1004,7 +1004,9 @@ __device__ __forceinline__ uint32_t hist_find(const uint32_t *hist, uint32_t &wa
 
 // One warp per row: upper bounds U_ij of all stored pairs, V = (an upper bound of) the k-th smallest of
 // them by a two-level 256-bin histogram over the key range, then only the pairs with L_ij <= V stay.
-__global__ void __launch_bounds__(kCompactWarps * 32) wis_compact_kernel(CompactArgs a) {
+// (six CTAs per SM: the kernel waits on its gathers -- ncu: 11 - 13 long-scoreboard stalls per issue at 44 % occupancy
+// with the 64 registers ptxas takes unasked; at 40 registers and 52 bytes of spills: 2.29 -> 1.93 ms at config 3)
+__global__ void __launch_bounds__(kCompactWarps * 32, 6) wis_compact_kernel(CompactArgs a) {
     __shared__ uint32_t s_hist[kCompactWarps][256];
     const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
     if (r >= a.rows) return;
