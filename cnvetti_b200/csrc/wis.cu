@@ -375,13 +375,43 @@ __global__ void modcov_kernel(const float *__restrict__ cv, uint32_t T, const ui
 }
 
 
+// (double)x of a NORMAL x (exponent field 1 .. 254) with integer instructions: |x| >> 3 puts exponent and mantissa
+// in place in the high word (as the high half of |x| * 2^29, with the addend moving the exponent bias from 127 to
+// 1023 in the same multiply-add), the low word is x << 29, the sign is OR-ed back.
+__device__ __forceinline__ double widen_normal_f32(uint32_t b) {
+    uint32_t hi;
+    asm("mad.hi.u32 %0, %1, 0x20000000, 0x38000000;" : "=r"(hi) : "r"(b & 0x7FFFFFFFu));
+    return __hiloint2double((int)(hi | (b & 0x80000000u)), (int)(b << 29));
+}
+
 // M1 for a batch of samples at once: X[T][S] holds FORMAT/CV of S samples side by side (the merge-cov
 // layout); outputs are sample-major [S][T], i.e. one contiguous per-sample column each, as the per-sample
-// call writes them (and as the segmentation reads them).  A CTA takes 32 targets; warp w handles targets
-// w, w+8, .. for the 32 samples of a chunk (neighbouring lanes read neighbouring samples of the same
-// reference row: whole 128-byte lines), results are transposed through shared memory so that the stores
-// run along the target axis.  Arithmetic and its order are those of modcov_kernel.
-constexpr uint32_t kPanelGroup = 32, kPanelThreads = 256;
+// call writes them (and as the segmentation reads them).  A CTA takes 32 targets and walks the samples in chunks
+// of 32 x SPL; warp w handles targets w, w+8, .. of a chunk, a lane the samples lane, lane + 32, .. of it
+// (neighbouring lanes read neighbouring samples of the same reference row: whole 128-byte lines), results are
+// transposed through shared memory so that the stores run along the target axis.  Arithmetic and its order
+// are those of modcov_kernel.
+//
+// Staged forms: the values of a chunk's samples in the target's reference targets are copied into shared memory
+// ONCE and the passes (sum, the double-double fallback, variance) read them from there.  At config 5 the unstaged
+// kernel was bound by HBM (ncu: 3.2 TB read in 0.64 s = 5.1 TB/s, 13 % L2 hits): every pass fetched the 100 rows'
+// segments again, 2.7 x the 1.2 TB that have to move once.  A warp owns k x 32 x SPL floats.
+//   kPanelAsync16  cp.async of 16 bytes per lane: a warp instruction moves two (SPL = 1: four) rows' segments.  Needs
+//                  16-byte aligned segments: S % 4 == 0.  The default where it applies.
+//   kPanelAsync    cp.async of 4 bytes per lane, sample and row (any S).
+//   kPanelBulk     one bulk copy (cp.async.bulk) per reference row and warp, counted by the warp's mbarrier.  The
+//                  copy takes uniform operands, so the lanes' copies are issued one at a time behind R2UR (ncu: 61
+//                  cycles per copy, 28 % of the warps' time) -- measured slower than the 16-byte cp.async, kept
+//                  under test (CNVB_PANEL_STAGE=2).
+// A chunk is 64 samples wide at the reference's default k: two independent f64 chains per lane.  The eight warps an
+// SM holds (shared memory: 205 KB of values at k = 100) leave the loops bound by latency and by the conversion
+// pipe: F2F.F64.F32 issues once per 8 cycles and SM quarter (ncu: the loops advance one reference target per 36 - 46
+// cycles, two warps x two conversions x 8).  The odd columns of a lane are therefore widened f32 -> f64 with integer
+// instructions (same bits for normal numbers: sign, exponent + 896, mantissa << 29; a column in which the first
+// pass sees a zero, a subnormal, an infinity or a NaN is redone with F2F), the even ones on the conversion pipe.
+enum PanelMode { kPanelPlain = 0, kPanelAsync = 1, kPanelBulk = 2, kPanelAsync16 = 3 };
+constexpr uint32_t kPanelGroup = 32, kPanelThreads = 256, kPanelWarps = kPanelThreads / 32;
+constexpr size_t panel_out_bytes(uint32_t spl) { return (size_t)5 * 32 * spl * (kPanelGroup + 1) * sizeof(float); }
 
 struct PanelOut {
     float *ref_mean, *ref_sd, *cv_rel, *cvz, *cv2;
@@ -399,17 +429,23 @@ struct PanelCalls {
     uint32_t *num_calls;
 };
 
-template <bool CALLS>
-__global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float *__restrict__ X, uint32_t S,
-                                                                     uint32_t row_begin, uint32_t rows,
-                                                                     const uint8_t *__restrict__ model_filt,
-                                                                     const uint32_t *__restrict__ ref_idx,
-                                                                     const uint32_t *__restrict__ ref_len, uint32_t k,
-                                                                     PanelOut o, PanelCalls pc) {
-    extern __shared__ uint32_t s_ref[];  // [kPanelGroup][k]
+template <bool CALLS, int MODE, int SPL>
+__global__ void __launch_bounds__(kPanelThreads)
+    modcov_panel_kernel(const float *__restrict__ X, uint32_t S, uint32_t row_begin, uint32_t rows,
+                        const uint8_t *__restrict__ model_filt, const uint32_t *__restrict__ ref_idx,
+                        const uint32_t *__restrict__ ref_len, uint32_t k, PanelOut o, PanelCalls pc) {
+    constexpr bool STAGED = MODE != kPanelPlain;
+    constexpr uint32_t CH = 32 * SPL;                         // samples of a chunk
+    constexpr uint32_t NIT = kPanelGroup / kPanelWarps;       // targets of a warp per chunk
+    extern __shared__ __align__(128) uint32_t s_ref[];        // [kPanelGroup][k], then (staged) the values [warp][k][CH]
     __shared__ uint32_t s_len[kPanelGroup], s_calls[kPanelGroup];
-    __shared__ float s_out[5][32][kPanelGroup + 1];  // [value][sample in chunk][target]
-    __shared__ uint8_t s_st[32][kPanelGroup + 4];
+    __shared__ float s_out_own[STAGED ? 1 : 5 * CH * (kPanelGroup + 1)];
+    __shared__ uint8_t s_st[CH][kPanelGroup + 4];
+    __shared__ __align__(8) uint64_t s_bar[kPanelWarps];
+    float *const stage = reinterpret_cast<float *>(s_ref + kPanelGroup * k);
+    // [value][sample in chunk][target]; staged: over the staged values, which are dead once the chunk's targets are done
+    float(*const s_out)[CH][kPanelGroup + 1] =
+        reinterpret_cast<float(*)[CH][kPanelGroup + 1]>(STAGED ? stage : s_out_own);
     const uint32_t r0 = blockIdx.x * kPanelGroup;  // relative to row_begin, like every per-row argument
     const uint32_t groups = min(kPanelGroup, rows - r0);
     for (uint32_t g = threadIdx.x; g < kPanelGroup; g += blockDim.x) {
@@ -421,6 +457,11 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
             s_len[g] = (g < groups && model_filt[r0 + g] == 0) ? ref_len[r0 + g] : 0u;  // lib.rs:104-113, :146
         }
     }
+    if (MODE == kPanelBulk && threadIdx.x == 0) {
+        for (uint32_t w = 0; w < kPanelWarps; ++w)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[w])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < groups * k; e += blockDim.x) {
         const uint32_t g = e / k, q = e - g * k;
@@ -428,71 +469,194 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
     }
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    for (uint32_t s0 = 0; s0 < S; s0 += 32) {
-        const uint32_t sm = s0 + lane;
-        for (uint32_t g = warp; g < groups; g += kPanelThreads / 32) {
-            uint8_t st = 0;
-            float o_mean = f32_missing(), o_sd = f32_missing(), o_rel = f32_missing(), o_z = f32_missing(),
-                  o_cv2 = f32_missing();
-            double o_zd = 0.0, o_reld = 1.0;  // CALLS: the f64 values behind cvz / cv_rel
+    const float *const mine = stage + (size_t)warp * k * CH + lane;  // this lane's first column of the warp's values
+    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(mine);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]);
+    uint32_t phase = 0;
+    for (uint32_t s0 = 0; s0 < S; s0 += CH) {
+        // a warp's targets of this chunk; the results wait in registers because the transposition buffer lies
+        // over the staged values of the other warps
+        float res[NIT][SPL][5];
+        uint8_t res_st[NIT][SPL];
+        uint32_t sm[SPL];  // the lane's samples; past the end of the panel (last chunk): computed on whatever the
+                           // staging area holds (unstaged: on the last sample) and discarded
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) sm[j] = s0 + 32 * j + lane;
+#pragma unroll
+        for (uint32_t it = 0; it < NIT; ++it) {
+            const uint32_t g = warp + it * kPanelWarps;
+            if (g >= groups) continue;
             const uint32_t m = s_len[g];
-            if (m > 0 && sm < S) {
-                const uint32_t *ref = s_ref + g * k;
+            const uint32_t *ref = s_ref + g * k;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+#pragma unroll
+                for (int v = 0; v < 5; ++v) res[it][j][v] = f32_missing();
+                res_st[it][j] = 0;
+            }
+            double o_zd[SPL], o_reld[SPL];  // CALLS: the f64 values behind cvz / cv_rel
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) o_zd[j] = 0.0, o_reld[j] = 1.0;
+            if (m > 0) {
+                if (MODE == kPanelBulk) {
+                    const uint32_t bytes = min(CH, S - s0) * 4u;
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(m * bytes) : "memory");
+                    __syncwarp();  // every lane is done with the previous target's values
+                    for (uint32_t q = lane; q < m; q += 32)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         mine_s - lane * 4u + q * (CH * 4u)),
+                                     "l"(X + (size_t)ref[q] * S + s0), "r"(bytes), "r"(bar)
+                                     : "memory");
+                    uint32_t ok;
+                    do {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                            "selp.u32 %0, 1, 0, p;\n\t}"
+                            : "=r"(ok)
+                            : "r"(bar), "r"(phase)
+                            : "memory");
+                    } while (!ok);
+                    phase ^= 1u;
+                } else if (MODE == kPanelAsync16) {
+                    constexpr uint32_t LPR = CH / 4, RPI = 32 / LPR;  // lanes per row segment, rows per instruction
+                    const uint32_t col = (lane % LPR) * 4u;
+                    __syncwarp();  // every lane is done with the previous target's values
+                    if (col < min(CH, S - s0))
+                        for (uint32_t q = lane / LPR; q < m; q += RPI)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mine_s - lane * 4u + (q * CH + col) * 4u),
+                                         "l"(X + (size_t)ref[q] * S + s0 + col)
+                                         : "memory");
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp();  // the lanes read one another's copies
+                } else if (MODE == kPanelAsync) {
+                    for (uint32_t q = 0; q < m; ++q) {
+#pragma unroll
+                        for (int j = 0; j < SPL; ++j)
+                            if (sm[j] < S)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(mine_s + (q * CH + 32 * j) * 4u),
+                                             "l"(X + (size_t)ref[q] * S + sm[j])
+                                             : "memory");
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");  // a lane reads back its own copies only
+                }
+                auto xat = [&](uint32_t q, int j) -> float {
+                    return STAGED ? mine[q * CH + 32 * j] : __ldg(X + (size_t)ref[q] * S + min(sm[j], S - 1));
+                };
                 // exact sum (Stats::sum): a plain f64 sum of m f32 values is exact when their exponents lie
                 // close together (see wis_calls_kernel); double-double otherwise
-                double sum = 0.0;
-                uint32_t amax = 0u, amin = 0x7FFFFFFFu;
+                double sum[SPL];
+                uint32_t amax[SPL], amin[SPL];  // of |x| as integers; amin over ALL values here, zeros included
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) sum[j] = 0.0, amax[j] = 0u, amin[j] = 0x7FFFFFFFu;
+#pragma unroll 4
                 for (uint32_t q = 0; q < m; ++q) {
-                    const float xf = __ldg(X + (size_t)ref[q] * S + sm);
-                    const uint32_t bits = __float_as_uint(xf) & 0x7FFFFFFFu;
-                    amax = max(amax, bits);
-                    amin = min(amin, bits ? bits : 0x7FFFFFFFu);
-                    sum = __dadd_rn(sum, (double)xf);
+#pragma unroll
+                    for (int j = 0; j < SPL; ++j) {
+                        const float xf = xat(q, j);
+                        const uint32_t bits = __float_as_uint(xf) & 0x7FFFFFFFu;
+                        amax[j] = max(amax[j], bits);
+                        amin[j] = min(amin[j], bits);
+                        // odd columns widen on the integer pipes, even ones on the conversion pipe (redone below
+                        // if the column turns out to hold a zero, a subnormal, an infinity or a NaN)
+                        sum[j] = __dadd_rn(sum[j], (STAGED && (j & 1)) ? widen_normal_f32(__float_as_uint(xf)) : (double)xf);
+                    }
                 }
-                const int span = (int)(amax >> 23) - (int)max(amin >> 23, 1u);
                 const int room = 29 - (32 - __clz((int)m - 1));  // 29 - ceil(log2 m)
-                if (amax != 0u && span > room) {
-                    dd acc{0.0, 0.0};
-                    for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)__ldg(X + (size_t)ref[q] * S + sm));
-                    sum = __dadd_rn(acc.hi, acc.lo);
+                double mean[SPL], v[SPL];
+                bool normal = true;  // only normal numbers in the lane's odd columns: exponent fields 1 .. 254
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    const bool normal_j = !(j & 1) || (amin[j] >= 0x00800000u && amax[j] < 0x7F800000u);
+                    normal = normal && normal_j;
+                    if (STAGED && !normal_j) {
+                        sum[j] = 0.0;
+                        for (uint32_t q = 0; q < m; ++q) sum[j] = __dadd_rn(sum[j], (double)xat(q, j));
+                    }
+                    if (amin[j] == 0u) {  // the span is taken over the non-zero values
+                        amin[j] = 0x7FFFFFFFu;
+                        for (uint32_t q = 0; q < m; ++q) {
+                            const uint32_t bits = __float_as_uint(xat(q, j)) & 0x7FFFFFFFu;
+                            amin[j] = min(amin[j], bits ? bits : 0x7FFFFFFFu);
+                        }
+                    }
+                    const int span = (int)(amax[j] >> 23) - (int)max(amin[j] >> 23, 1u);
+                    if (amax[j] != 0u && span > room) {
+                        dd acc{0.0, 0.0};
+                        for (uint32_t q = 0; q < m; ++q) acc = dd_add_d(acc, (double)xat(q, j));
+                        sum[j] = __dadd_rn(acc.hi, acc.lo);
+                    }
+                    mean[j] = __ddiv_rn(sum[j], (double)m);  // lib.rs:147
+                    v[j] = 0.0;
                 }
-                const double mean = __ddiv_rn(sum, (double)m);  // lib.rs:147
-                double v = 0.0;
-                for (uint32_t q = 0; q < m; ++q) {
-                    const double d = __dsub_rn((double)__ldg(X + (size_t)ref[q] * S + sm), mean);
-                    v = __dadd_rn(v, __dmul_rn(d, d));
+                if (STAGED && normal) {
+#pragma unroll 4
+                    for (uint32_t q = 0; q < m; ++q) {
+#pragma unroll
+                        for (int j = 0; j < SPL; ++j) {
+                            const float xf = xat(q, j);
+                            const double d = __dsub_rn((j & 1) ? widen_normal_f32(__float_as_uint(xf)) : (double)xf, mean[j]);
+                            v[j] = __dadd_rn(v[j], __dmul_rn(d, d));
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (uint32_t q = 0; q < m; ++q) {
+#pragma unroll
+                        for (int j = 0; j < SPL; ++j) {
+                            const double d = __dsub_rn((double)xat(q, j), mean[j]);
+                            v[j] = __dadd_rn(v[j], __dmul_rn(d, d));
+                        }
+                    }
                 }
-                const double sd = __dsqrt_rn(m < 2 ? 0.0 : __ddiv_rn(v, (double)(m - 1)));  // lib.rs:148
-                const double x = (double)X[(size_t)(row_begin + r0 + g) * S + sm];
-                const double rel = __ddiv_rn(x, mean);                // lib.rs:78-80
-                const double zs = __ddiv_rn(__dsub_rn(x, mean), sd);  // lib.rs:83-85
-                o_mean = (float)mean;
-                o_sd = (float)sd;
-                o_rel = (float)rel;
-                o_z = (float)zs;
-                o_zd = zs;
-                o_reld = rel;
-                st = CNVB_MODCOV_HAS_INFO;
-                if (isfinite(rel)) {  // lib.rs:223-232
-                    o_cv2 = rel == 0.0 ? f32_missing() : (float)log2(rel);
-                    st |= CNVB_MODCOV_CV2;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    if (sm[j] >= S) continue;
+                    const double sd = __dsqrt_rn(m < 2 ? 0.0 : __ddiv_rn(v[j], (double)(m - 1)));  // lib.rs:148
+                    const double x = (double)X[(size_t)(row_begin + r0 + g) * S + sm[j]];
+                    const double rel = __ddiv_rn(x, mean[j]);                // lib.rs:78-80
+                    const double zs = __ddiv_rn(__dsub_rn(x, mean[j]), sd);  // lib.rs:83-85
+                    res[it][j][0] = (float)mean[j];
+                    res[it][j][1] = (float)sd;
+                    res[it][j][2] = (float)rel;
+                    res[it][j][3] = (float)zs;
+                    o_zd[j] = zs;
+                    o_reld[j] = rel;
+                    uint8_t st = CNVB_MODCOV_HAS_INFO;
+                    if (isfinite(rel)) {  // lib.rs:223-232
+                        res[it][j][4] = rel == 0.0 ? f32_missing() : (float)log2(rel);
+                        st |= CNVB_MODCOV_CV2;
+                    }
+                    res_st[it][j] = st;
                 }
             }
             if (CALLS) {  // lib.rs:260-266 (|x - mean| / sd = |(x - mean) / sd| bit for bit)
-                const bool hit = (st & CNVB_MODCOV_HAS_INFO) && fabs((double)o_zd) > pc.zthr && fabs(__dsub_rn(o_reld, 1.0)) > pc.rel_thr;
-                const uint32_t n_hit = __popc(__ballot_sync(0xffffffffu, hit));
+                uint32_t n_hit = 0;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    const bool hit = (res_st[it][j] & CNVB_MODCOV_HAS_INFO) && fabs(o_zd[j]) > pc.zthr &&
+                                     fabs(__dsub_rn(o_reld[j], 1.0)) > pc.rel_thr;
+                    n_hit += __popc(__ballot_sync(0xffffffffu, hit));
+                }
                 if (lane == 0 && n_hit) atomicAdd(&s_calls[g], n_hit);
             }
-            s_out[0][lane][g] = o_mean;
-            s_out[1][lane][g] = o_sd;
-            s_out[2][lane][g] = o_rel;
-            s_out[3][lane][g] = o_z;
-            s_out[4][lane][g] = o_cv2;
-            s_st[lane][g] = st;
+        }
+        if (STAGED) __syncthreads();
+#pragma unroll
+        for (uint32_t it = 0; it < NIT; ++it) {
+            const uint32_t g = warp + it * kPanelWarps;
+            if (g >= groups) continue;
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) {
+#pragma unroll
+                for (int v = 0; v < 5; ++v) s_out[v][32 * j + lane][g] = res[it][j][v];
+                s_st[32 * j + lane][g] = res_st[it][j];
+            }
         }
         __syncthreads();
         float *const outs[5] = {o.ref_mean, o.ref_sd, o.cv_rel, o.cvz, o.cv2};
-        for (uint32_t e = threadIdx.x; e < 32 * kPanelGroup; e += blockDim.x) {
+        for (uint32_t e = threadIdx.x; e < CH * kPanelGroup; e += blockDim.x) {
             const uint32_t sl = e / kPanelGroup, g = e % kPanelGroup;
             if (s0 + sl < S && g < groups) {
                 const size_t at = (size_t)(s0 + sl) * rows + r0 + g;
@@ -502,6 +666,8 @@ __global__ void __launch_bounds__(kPanelThreads) modcov_panel_kernel(const float
                 if (o.status) o.status[at] = s_st[sl][g];
             }
         }
+        // the next chunk's bulk copies (async proxy) overwrite what was written and read here (generic proxy)
+        if (MODE == kPanelBulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
     }
     if (CALLS)
@@ -962,6 +1128,43 @@ extern "C" int cnvb_wis_build_sharded(cnvb_comm *comm, const float *X_rows, cons
     return CNVB_OK;
 }
 
+namespace {
+// launch shape of modcov_panel_kernel: staged with 64-sample chunks, staged with 32-sample chunks, or unstaged;
+// 16-byte copies where the segments are 16-byte aligned.  CNVB_PANEL_STAGE=0 / 1 / 2 force the unstaged / the 4-byte
+// cp.async / the bulk-copy form, CNVB_PANEL_SPL=1 the 32-sample chunks (A/B measurements and the tests of the fallbacks).
+struct PanelLaunch {
+    size_t smem;
+    int mode, spl;
+};
+PanelLaunch panel_launch(uint32_t k, const float *X, uint32_t S) {
+    const size_t ref = (size_t)kPanelGroup * k * sizeof(uint32_t);
+    const size_t limit = 227 * 1024 - 3072;  // less the kernel's static arrays
+    const char *e = getenv("CNVB_PANEL_STAGE");
+    const int want = e ? atoi(e) : (int)kPanelAsync16;
+    e = getenv("CNVB_PANEL_SPL");
+    const int max_spl = e ? atoi(e) : 2;
+    if (want != kPanelPlain)
+        for (int spl = 2; spl >= 1; --spl) {
+            const size_t stage = std::max((size_t)k * 32 * spl * kPanelWarps * sizeof(float), panel_out_bytes(spl));
+            if (spl > max_spl || ref + stage > limit) continue;
+            const bool aligned = S % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0;
+            return {ref + stage, (want == kPanelAsync || !aligned) ? (int)kPanelAsync : want == kPanelBulk ? (int)kPanelBulk : (int)kPanelAsync16, spl};
+        }
+    return {ref, kPanelPlain, 1};
+}
+template <bool CALLS, int SPL>
+auto panel_kernel_spl(int mode) {
+    return mode == kPanelAsync16 ? modcov_panel_kernel<CALLS, kPanelAsync16, SPL>
+           : mode == kPanelBulk  ? modcov_panel_kernel<CALLS, kPanelBulk, SPL>
+                                 : modcov_panel_kernel<CALLS, kPanelAsync, SPL>;
+}
+template <bool CALLS>
+auto panel_kernel(const PanelLaunch &pl) {
+    if (pl.mode == kPanelPlain) return modcov_panel_kernel<CALLS, kPanelPlain, 1>;
+    return pl.spl == 2 ? panel_kernel_spl<CALLS, 2>(pl.mode) : panel_kernel_spl<CALLS, 1>(pl.mode);
+}
+}  // namespace
+
 extern "C" int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint32_t S, uint32_t row_begin,
                                  uint32_t row_end, const uint8_t *model_filt, const uint32_t *ref_idx,
                                  const uint32_t *ref_len, uint32_t k, float *ref_mean, float *ref_sd, float *cv_rel,
@@ -993,11 +1196,11 @@ extern "C" int cnvb_modcov_panel(cnvb_ctx *ctx, const float *X, uint32_t T, uint
     {
         KernelSpan span(ctx, "modcov_panel_kernel");
         const PanelOut po{o1.p, o2.p, o3.p, o4.p, o5.p, os.p};
-        const size_t smem = (size_t)kPanelGroup * k * sizeof(uint32_t);
-        if (smem > 24 * 1024)
-            CNVB_CUDA(ctx, cudaFuncSetAttribute(modcov_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                      "smem opt-in");
-        modcov_panel_kernel<false><<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, smem, ctx->stream>>>(
+        const PanelLaunch pl = panel_launch(k, dx.p, S);
+        auto kern = panel_kernel<false>(pl);
+        if (pl.smem > 24 * 1024)
+            CNVB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem), "smem opt-in");
+        kern<<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, pl.smem, ctx->stream>>>(
             dx.p, S, row_begin, rows, dmf.p, di.p, dl.p, k, po, PanelCalls{});
     }
     CNVB_LAUNCHED(ctx, "modcov_panel_kernel");
@@ -1046,12 +1249,12 @@ extern "C" int cnvb_wis_calls_modcov_panel(cnvb_ctx *ctx, const float *X, uint32
         CNVB_CUDA(ctx, cudaMemsetAsync(oc.p, 0, rows * sizeof(uint32_t), ctx->stream), "clearing the call counts");
     } else {
         KernelSpan span(ctx, "modcov_panel_kernel");
-        const size_t smem = (size_t)kPanelGroup * k * sizeof(uint32_t);
-        if (smem > 24 * 1024)
-            CNVB_CUDA(ctx, cudaFuncSetAttribute(modcov_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                      "smem opt-in");
+        const PanelLaunch pl = panel_launch(k, dx.p, S);
+        auto kern = panel_kernel<true>(pl);
+        if (pl.smem > 24 * 1024)
+            CNVB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem), "smem opt-in");
         const PanelCalls pc{opts->min_ref_targets, opts->filter_z_score, opts->filter_rel, oc.p};
-        modcov_panel_kernel<true><<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, smem, ctx->stream>>>(
+        kern<<<(rows + kPanelGroup - 1) / kPanelGroup, kPanelThreads, pl.smem, ctx->stream>>>(
             dx.p, S, row_begin, rows, nullptr, di.p, dl.p, k, po, pc);
     }
     CNVB_LAUNCHED(ctx, "modcov_panel_kernel");

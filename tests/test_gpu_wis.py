@@ -116,12 +116,21 @@ def test_modcov_parity(oracle, ctx, device):
     assert (o["status"] == 0).any() and (o["status"] == 3).any()
 
 
-@pytest.mark.parametrize("T,S,device", [(3000, 12, True), (1037, 70, False), (40, 33, True)])
-def test_modcov_panel_matches_per_sample_oracle(oracle, ctx, T, S, device):
+@pytest.mark.parametrize("T,S,device,k,env", [
+    (3000, 12, True, 50, {}), (1037, 70, False, 50, {}), (40, 33, True, 40, {}),    # 16-byte / 4-byte (S % 4 != 0) cp.async, 64-sample chunks
+    (1200, 136, True, 100, {}), (1200, 136, True, 100, {"CNVB_PANEL_STAGE": "1"}),   # three chunks, the last one partial
+    (1200, 136, True, 100, {"CNVB_PANEL_STAGE": "2"}), (1037, 72, True, 50, {"CNVB_PANEL_STAGE": "2", "CNVB_PANEL_SPL": "1"}),
+    (1500, 40, True, 150, {}), (900, 45, True, 150, {}),                             # 32-sample chunks (105 < k <= 210)
+    (1037, 72, True, 50, {"CNVB_PANEL_SPL": "1"}),
+    (1200, 45, True, 230, {}), (1037, 70, True, 50, {"CNVB_PANEL_STAGE": "0"})])     # the unstaged kernel
+def test_modcov_panel_matches_per_sample_oracle(oracle, ctx, monkeypatch, T, S, device, k, env):
     """cnvb_modcov_panel: every column of the sample-major outputs equals the oracle's per-sample
-    mod-coverage of that sample (bit-exact; CV2 = log2 within the north_star tolerance)."""
+    mod-coverage of that sample (bit-exact; CV2 = log2 within the north_star tolerance), in every form of the
+    kernel (reference values staged in shared memory by 16-byte cp.async, 4-byte cp.async or bulk copies, or
+    read from global memory)."""
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
     X, tids = synth.synth_panel(31 + T, T, S, n_contigs=6)
-    k = min(T, 50)
     odist, oidx = oracle.wis_distances(X, tids, max_ref_targets=k, nthreads=4)
     _, ridx, rlen = oracle.wis_prune(odist, oidx, z=2.0)
     rng = np.random.default_rng(2)
@@ -129,6 +138,10 @@ def test_modcov_panel_matches_per_sample_oracle(oracle, ctx, T, S, device):
     rlen[rng.integers(0, T, 5)] = 0
     Y = (X * rng.normal(1, 0.1, X.shape)).astype(np.float32)  # the samples being called
     Y[17 % T, 3] = 0.0
+    if S > 42:   # a zero, a subnormal and a negative value in columns the kernel widens with integer instructions
+        Y[5, 40] = 0.0   # (samples 32 .. 63 of a chunk)
+        Y[9, 41] = np.float32(1e-42)
+        Y[11, 42] = -Y[11, 42]
     Y[::7] *= np.float32(1e-15)   # reference sets mixing magnitudes: the plain f64 sum is not exact there
     names = ("ref_mean", "ref_sd", "cv_rel", "cvz", "cv2", "status")
     if device:
