@@ -23,10 +23,10 @@ for line in out.splitlines():
         kern = base + ("<%s>" % targs.group(1) if targs and not base.startswith("cub::") else "")
         hist.setdefault(kern, collections.Counter())
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Za-z0-9_.]*)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Za-z0-9_.]*)", line)
     if m and kern:
         hist[kern][m.group(1)] += 1
-interesting = re.compile(r"^(UTC|UTMA|LDTM|STTM|UBLKCP|SYNCS|RED|ATOM|ATOMS|ATOMG|VIMNMX|VIADDMNMX|FMNMX|LDG\.E\.128|LDG\.E\.64|STG\.E\.128|LDS\.128|STS\.128|SHFL|MATCH|VOTE|REDUX|HMMA|IMMA|DADD|DFMA|DMUL|POPC|LOP3|PRMT|BAR|ELECT|CCTL|FENCE|MEMBAR|UCGABAR)")
+interesting = re.compile(r"^(LDGSTS|F2F|UTC|UTMA|LDTM|STTM|UBLKCP|SYNCS|RED|ATOM|ATOMS|ATOMG|VIMNMX|VIADDMNMX|FMNMX|LDG\.E\.128|LDG\.E\.64|STG\.E\.128|LDS\.128|STS\.128|SHFL|MATCH|VOTE|REDUX|HMMA|IMMA|DADD|DFMA|DMUL|POPC|LOP3|PRMT|BAR|ELECT|CCTL|FENCE|MEMBAR|UCGABAR)")
 with open(os.path.join(ROOT, "profiles", "r2_sass_opcodes.txt"), "w") as f:
     f.write("# cuobjdump -sass cnvetti_b200/libcnvetti_b200.so (sm_100a), opcode counts per kernel; tools/sass_histogram.py\n")
     for k, c in hist.items():
