@@ -323,7 +323,8 @@ def kernel_times(env, step, steps, names):
 def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6):
     """Host BAM decode, timed on its own (north_star: reported separately from device time): a synthetic
     coordinate-sorted BAM of the config-1 read mix is written at zlib level `level` (htslib's default is 6),
-    then decoded by the library's BGZF/BAM decoder (zlib on all host threads) into pinned SoA columns."""
+    then decoded by the library's BGZF/BAM decoder (csrc/hostz.cpp's DEFLATE decoder and CRC-32 on all host threads, zlib
+    behind them) into pinned SoA columns."""
     import tempfile
     from cnvetti_b200 import bam, synth
     scale = n_pairs / 7_600_000.0
@@ -349,7 +350,8 @@ def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6):
             "parse_seconds": best["parse_seconds"], "reads_per_s": best["records"] / best["decode_seconds"],
             "compressed_mb_per_s": size / best["decode_seconds"] / 1e6,
             "compressed_mb_per_s_per_thread": size / best["decode_seconds"] / 1e6 / ncpu,
-            "threads": ncpu, "what": "BGZF inflate (zlib) + record walk + SoA derivation into pinned columns; "
+            "threads": ncpu, "what": "BGZF inflate (own DEFLATE decoder + CLMUL CRC-32, zlib as fallback) + record walk on all threads + SoA "
+                                     "derivation into pinned columns; "
                                      "best of 3; not part of value / e2e"}
 
 

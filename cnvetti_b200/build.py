@@ -35,14 +35,14 @@ def nvcc():
 
 
 def sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))  # (.cpp: host-only, nvcc hands it to g++)
 
 
 def _deps_mtime():
     m = 0.0
     for root in (CSRC, INCLUDE):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".cpp")):
                 m = max(m, os.path.getmtime(os.path.join(root, f)))
     return max(m, os.path.getmtime(__file__))
 
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
     exe = nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src[:-3] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         cmd = [exe] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
             ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)

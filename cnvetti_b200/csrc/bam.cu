@@ -5,7 +5,8 @@
 // agg.rs:224-228) and the per-record derivations of the aggregators (agg.rs:124-133, 174-198,
 // 312-320).  `cmd coverage` visits every contig of the file in turn, so the decoder makes ONE
 // pass over the file instead of one index seek per region: BGZF blocks are inflated on host
-// threads (zlib raw inflate, one block per task), record boundaries are walked once, and the
+// threads (hostz.cpp's DEFLATE decoder and carry-less-multiplication CRC-32, zlib behind them; one block per task),
+// record boundaries are walked once, and the
 // threads derive the SoA columns of disjoint record ranges.  The columns of a contig are what
 // `fetch` on that contig yields, in file (= coordinate) order: every record whose refID is the
 // contig, including unmapped reads placed at their mate's position; records without a
@@ -28,6 +29,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostz.h"
 
 using namespace cnvb;
 
@@ -204,6 +206,111 @@ struct Run {  // consecutive records of one refID inside a chunk
     uint64_t dst;    // row in the contig's columns where the run starts
 };
 
+// One stretch of the record walk: the records that start in [q, limit) and lie completely inside the n bytes at u.
+// Appends their offsets and the runs of equal refID (first = index into offs); returns where the walk stopped (the
+// first record at / past the limit, or the incomplete one at the end of the data).  bad: a block_size below 32.
+struct WalkOut {
+    std::vector<uint64_t> offs;
+    std::vector<Run> runs;
+    uint64_t end = 0, bad_size = 0;
+    bool bad = false;
+};
+void walk_records(const uint8_t *u, uint64_t n, uint64_t q, uint64_t limit, WalkOut &o) {
+    int32_t run_tid = 0;
+    while (q < limit && q + 4 <= n) {
+        const uint64_t bs = rd32(u + q);
+        if (bs < 32) {
+            o.bad = true;
+            o.bad_size = bs;
+            break;
+        }
+        if (q + 4 + bs > n) break;
+        // the walk is a chain of dependent loads, one cache line per record (~55 ns each when cold): records
+        // of a file have similar sizes, so the line some records ahead can be requested now
+        __builtin_prefetch(u + q + 12 * (4 + bs));
+        __builtin_prefetch(u + q + 12 * (4 + bs) + 64);
+        const int32_t tid = (int32_t)rd32(u + q + 4);
+        if (o.runs.empty() || tid != run_tid) {
+            o.runs.push_back(Run{o.offs.size(), tid, 0});
+            run_tid = tid;
+        }
+        o.offs.push_back(q);
+        q += 4 + bs;
+    }
+    o.end = q;
+}
+
+// Does a chain of records start at q?  The fixed fields of up to four consecutive records must be consistent with
+// one another and with the header (a guess: walk_parallel keeps a stretch only if the walk before it arrives at
+// exactly this offset).
+bool plausible_record_chain(const uint8_t *u, uint64_t n, uint64_t q, int64_t n_ref) {
+    for (int k = 0; k < 4; ++k) {
+        if (q + 36 > n) return k > 0;
+        const uint64_t bs = rd32(u + q);
+        const int64_t tid = (int32_t)rd32(u + q + 4), pos = (int32_t)rd32(u + q + 8);
+        const uint64_t l_name = u[q + 12], n_cigar = rd16(u + q + 16), l_seq = rd32(u + q + 20);
+        const int64_t mtid = (int32_t)rd32(u + q + 24), mpos = (int32_t)rd32(u + q + 28);
+        if (bs < 32 || bs > (1u << 28) || tid < -1 || tid >= n_ref || pos < -1 || mtid < -1 || mtid >= n_ref || mpos < -1 ||
+            l_name == 0 || l_seq > (1u << 28))
+            return false;
+        if (32 + l_name + 4 * n_cigar + (l_seq + 1) / 2 + l_seq > bs) return false;
+        if (q + 36 + l_name <= n && u[q + 36 + l_name - 1] != 0) return false;  // read_name is NUL-terminated
+        q += 4 + bs;
+    }
+    return true;
+}
+
+// The record walk of a chunk on all threads.  The chain of block_size fields is serial, so every thread but the
+// first GUESSES where a record starts in its share of the bytes (the first offset from which four records in a row
+// look like records) and walks from there; the stretches are then joined front to back, and a stretch is kept only
+// if the walk before it ends exactly where the stretch began -- otherwise that share is walked again from the true
+// offset.  The result is the serial walk's, whatever the guesses were.
+void walk_parallel(const uint8_t *u, uint64_t n, uint64_t q, int64_t n_ref, int n_threads, WalkOut &out) {
+    const uint64_t span = n - q;
+    uint64_t share = 1ull << 20;  // at least 1 MiB each (tests: CNVB_BAM_WALK_SHARE makes the shares small)
+    if (const char *e = getenv("CNVB_BAM_WALK_SHARE")) share = std::max<uint64_t>(64, (uint64_t)atoll(e));
+    const int parts = (int)std::min<uint64_t>((uint64_t)std::max(1, n_threads), span / share);
+    if (parts <= 1) {
+        walk_records(u, n, q, n, out);
+        return;
+    }
+    std::vector<WalkOut> seg(parts);
+    std::vector<uint64_t> lo(parts + 1), guess(parts, UINT64_MAX);
+    for (int i = 0; i <= parts; ++i) lo[i] = i == parts ? n : q + span * (uint64_t)i / parts;
+    run_parallel(parts, (uint64_t)parts, [&](uint64_t a, uint64_t b, int) {
+        for (uint64_t i = a; i < b; ++i) {
+            uint64_t start = lo[i];
+            if (i > 0) {
+                const uint64_t stop = std::min<uint64_t>(lo[i + 1], lo[i] + (4ull << 20));  // (records longer than this: walked serially)
+                while (start < stop && !plausible_record_chain(u, n, start, n_ref)) ++start;
+                if (start >= stop) continue;  // (no record starts in this share, or none that looks like one)
+            }
+            guess[i] = start;
+            walk_records(u, n, start, lo[i + 1], seg[i]);
+        }
+    });
+    uint64_t cur = q;
+    for (int i = 0; i < parts && !out.bad; ++i) {
+        if (cur >= lo[i + 1]) continue;  // a record spans the whole share
+        WalkOut redo;
+        WalkOut *w = &seg[i];
+        if (guess[i] != cur) {
+            walk_records(u, n, cur, lo[i + 1], redo);
+            w = &redo;
+        }
+        const uint64_t base = out.offs.size();
+        for (const Run &r : w->runs)
+            if (out.runs.empty() || out.runs.back().tid != r.tid) out.runs.push_back(Run{base + r.first, r.tid, 0});
+        out.offs.insert(out.offs.end(), w->offs.begin(), w->offs.end());
+        out.bad = w->bad;
+        out.bad_size = w->bad_size;
+        const bool stopped_short = w->end < lo[i + 1];  // incomplete record at the end of the data (or a bad one)
+        cur = w->end;
+        if (stopped_short) break;
+    }
+    out.end = cur;
+}
+
 // The whole decode: one pass over the file in chunks of compressed bytes.  Two stages per chunk --
 // (A) read, cut into BGZF blocks, inflate on all threads; (B) header / record walk / SoA derivation -- and
 // stage B of chunk k runs on a helper thread while stage A of chunk k+1 proceeds (two uncompressed
@@ -221,6 +328,7 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only, cons
         const long v = atol(e);
         if (v >= 64) kChunkBytes = (uint64_t)v;
     }
+    const bool zlib_only = getenv("CNVB_BAM_ZLIB") != nullptr;  // (A/B measurements, tests of the fallback)
     constexpr uint64_t kHead = 1ull << 16;  // room in front of a chunk's bytes for the carried-over partial record
     RawBuf &cbuf = b->cbuf;
     RawBuf *ubufs[2] = {&b->ubuf, &b->ubuf2};
@@ -312,8 +420,21 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only, cons
         // record boundaries, and the runs of equal refID among them (the refID sits next to block_size)
         rec_off.clear();
         runs.clear();
+        if (!range) {
+            WalkOut w;
+            if (getenv("CNVB_BAM_SERIAL_WALK")) walk_records(u, un, q, un, w);  // (A/B measurements, tests)
+            else walk_parallel(u, un, q, (int64_t)b->refs.size(), b->n_threads, w);
+            if (w.bad) {
+                wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: corrupt BAM record (block_size %llu)", b->path.c_str(),
+                              (unsigned long long)w.bad_size);
+                return;
+            }
+            rec_off.swap(w.offs);
+            runs.swap(w.runs);
+            q = w.end;
+        }
         int32_t run_tid = 0;
-        while (q + 4 <= un) {
+        while (range && q + 4 <= un) {
             const uint64_t bs = rd32(u + q);
             if (bs < 32) {
                 wrc = fail_to(werr, CNVB_ERR_INVALID, "%s: corrupt BAM record (block_size %llu)", b->path.c_str(),
@@ -422,7 +543,7 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only, cons
     for (uint64_t k = 0; !eof && rc == CNVB_OK; ++k) {
         // ---- stage A: read compressed bytes, cut into whole blocks
         const uint64_t have = left.size();
-        if (!cbuf.resize(have + kChunkBytes, false)) {
+        if (!cbuf.resize(have + kChunkBytes + kInflateSlack, false)) {  // (the decoder's loads may run past a block's end)
             rc = fail_to(b->error, CNVB_ERR_NOMEM, "out of host memory while decoding %s", b->path.c_str());
             break;
         }
@@ -482,26 +603,35 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only, cons
         }
         std::atomic<int> bad{0};
         run_parallel(b->n_threads, blocks.size(), [&](uint64_t lo, uint64_t hi, int) {
+            // hostz.cpp's decoder first (a BGZF block is one buffer of known size); zlib for whatever it refuses
+            // or gets wrong by the block's CRC-32 -- zlib's verdict is the one that stands
             z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) {
-                bad = 1;
-                return;
-            }
+            bool zs_init = false;
             for (uint64_t i = lo; i < hi; ++i) {
                 const Block &bl = blocks[i];
                 if (bl.isize == 0) continue;
-                inflateReset(&zs);
+                uint8_t *dst = ub->data() + kHead + bl.uoff;
+                if (!zlib_only && inflate_raw_fast(cbuf.data() + bl.off, bl.clen, dst, bl.isize) &&
+                    crc32_fast(dst, bl.isize) == bl.crc)
+                    continue;
+                if (!zs_init) {
+                    memset(&zs, 0, sizeof zs);
+                    if (inflateInit2(&zs, -15) != Z_OK) {
+                        bad = 1;
+                        return;
+                    }
+                    zs_init = true;
+                } else {
+                    inflateReset(&zs);
+                }
                 zs.next_in = cbuf.data() + bl.off;
                 zs.avail_in = bl.clen;
-                zs.next_out = ub->data() + kHead + bl.uoff;
+                zs.next_out = dst;
                 zs.avail_out = bl.isize;
                 const int r = inflate(&zs, Z_FINISH);
-                if (r != Z_STREAM_END || zs.avail_out != 0 ||
-                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), ub->data() + kHead + bl.uoff, bl.isize) != bl.crc)
-                    bad = 1;
+                if (r != Z_STREAM_END || zs.avail_out != 0 || crc32_fast(dst, bl.isize) != bl.crc) bad = 1;
             }
-            inflateEnd(&zs);
+            if (zs_init) inflateEnd(&zs);
         });
         b->t_inflate += std::chrono::duration<double>(clk::now() - t0).count();
         if (bad) {

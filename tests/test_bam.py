@@ -98,6 +98,28 @@ def test_bam_chunk_seams(tmp_path, monkeypatch):
     monkeypatch.delenv("CNVB_BAM_CHUNK")
 
 
+@pytest.mark.parametrize("env", [{}, {"CNVB_BAM_ZLIB": "1"}, {"CNVB_BAM_SERIAL_WALK": "1"}, {"CNVB_BAM_WALK_SHARE": "64"},
+                                 {"CNVB_BAM_WALK_SHARE": "200"}, {"CNVB_BAM_WALK_SHARE": "5000", "CNVB_BAM_CHUNK": "70001"}])
+@pytest.mark.parametrize("level,block_payload", [(6, None), (1, 3000), (9, 65280), (0, 20000)])
+def test_bam_decoder_paths_agree(tmp_path, monkeypatch, env, level, block_payload):
+    """The decoder's own DEFLATE / CRC-32 (hostz.cpp) against zlib behind the same file, and the record walk on all
+    threads (guessed record starts, kept only where the walk before them arrives) against the serial walk: the same
+    columns whatever the compression level, the block size and the size of the threads' shares (shares smaller
+    than a record, records spanning shares)."""
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    contigs = [("chr1", 200_000), ("chr2", 150_000), ("chr3", 90_000)]
+    recs = {0: synth.synth_bam_records(21, 200_000, 6000), 1: synth.synth_bam_records(22, 150_000, 3500),
+            2: synth.synth_bam_records(23, 90_000, 11), -1: synth.synth_bam_records(24, 1000, 5)}
+    kw = {} if block_payload is None else {"block_payload": block_payload}
+    path = synth.write_bam(str(tmp_path / "p.bam"), contigs, recs, level=level, **kw)
+    with bam.BamReader(path, threads=4) as r:
+        r.decode(min_unclipped=0.6, pinned=False)
+        assert r.stats()["records"] == sum(len(d["pos"]) for d in recs.values()) and r.stats()["unplaced"] == 10
+        for t in (0, 1, 2):
+            _check(r.fetch(t), _expected(recs[t], 0.6))
+
+
 def test_bam_errors_are_loud(tmp_path):
     with pytest.raises(bam.BamError, match="Could not open"):
         bam.BamReader(str(tmp_path / "missing.bam"))
