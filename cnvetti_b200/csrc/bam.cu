@@ -14,6 +14,7 @@
 //
 // Pure host code.  The columns are page-locked on request (cudaHostRegister, once the decode is complete) so
 // that they can be handed to cnvb_cov_put_records / cnvb_coverage_run and copied by DMA.
+#include <sys/mman.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -35,6 +36,21 @@ using namespace cnvb;
 
 namespace {
 
+// Fresh anonymous memory costs a page fault per 4 KiB the first time it is touched -- for a cold decode (one reader
+// per file: the real case) that was more than the decode itself (2 M reads, 8 threads: 154 ms cold against 66 ms
+// with buffers reused).  Transparent huge pages are opt-in on these boxes (madvise): ask for them on every large
+// buffer, one fault per 2 MiB then.
+inline void advise_huge(void *p, uint64_t bytes) {
+#ifdef MADV_HUGEPAGE
+    static const bool off = getenv("CNVB_BAM_NO_THP") != nullptr;  // (A/B measurements)
+    if (off || bytes < (4ull << 20)) return;
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 4095u) & ~uintptr_t(4095), e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~uintptr_t(4095);
+    if (e > a) madvise(reinterpret_cast<void *>(a), e - a, MADV_HUGEPAGE);
+#else
+    (void)p, (void)bytes;
+#endif
+}
+
 template <typename T>
 struct HostColumn {  // growing array; page-locked in place once the decode is complete
     T *p = nullptr;
@@ -46,6 +62,7 @@ struct HostColumn {  // growing array; page-locked in place once the decode is c
         const uint64_t ncap = std::max<uint64_t>(want, cap ? cap * 2 : 1 << 16);
         T *q = static_cast<T *>(realloc(p, ncap * sizeof(T)));  // (grows in place or by remapping: no pinned copies)
         if (!q) return false;
+        advise_huge(q, ncap * sizeof(T));
         p = q;
         cap = ncap;
         return true;
@@ -90,9 +107,12 @@ struct RawBuf {  // byte buffer without value-initialisation (std::vector::resiz
     uint64_t n = 0, cap = 0;
     bool resize(uint64_t want, bool keep) {
         if (want > cap) {
-            const uint64_t ncap = std::max<uint64_t>(want, cap + cap / 2);
-            uint8_t *q = static_cast<uint8_t *>(keep ? realloc(p, ncap) : malloc(ncap));
+            uint64_t ncap = std::max<uint64_t>(want, cap + cap / 2);
+            const bool huge = !keep && ncap >= (4ull << 20);  // (2 MiB aligned, so that every part of it can be a huge page)
+            if (huge) ncap = (ncap + (2ull << 20) - 1) & ~((2ull << 20) - 1);
+            uint8_t *q = static_cast<uint8_t *>(keep ? realloc(p, ncap) : huge ? aligned_alloc(2ull << 20, ncap) : malloc(ncap));
             if (!q) return false;
+            advise_huge(q, ncap);
             if (!keep) free(p);
             p = q;
             cap = ncap;
