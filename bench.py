@@ -320,11 +320,13 @@ def kernel_times(env, step, steps, names):
     return kern, i0.elapsed_time(i1) / steps
 
 
-def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6):
+def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6, payload="filler"):
     """Host BAM decode, timed on its own (north_star: reported separately from device time): a synthetic
     coordinate-sorted BAM of the config-1 read mix is written at zlib level `level` (htslib's default is 6),
     then decoded by the library's BGZF/BAM decoder (csrc/hostz.cpp's DEFLATE decoder and CRC-32 on all host threads, zlib
-    behind them) into pinned SoA columns."""
+    behind them) into pinned SoA columns.  payload="filler": sequences and qualities are zeros / 0xFF and deflate 15 : 1
+    (the decoder's best case: long matches); payload="random": random bases and qualities from eight bins, 2.2 : 1 --
+    what a sequencer's file looks like to the inflater (short matches and literals), the number to plan with."""
     import tempfile
     from cnvetti_b200 import bam, synth
     scale = n_pairs / 7_600_000.0
@@ -332,7 +334,7 @@ def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6):
     d = synth.synth_bam_records(22, L, n_pairs)
     with tempfile.TemporaryDirectory() as tmp:
         try:
-            path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d], level=level)
+            path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d], level=level, payload=payload)
         except TypeError:
             path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("chr22", L)], [d])
             level = 1
@@ -346,7 +348,7 @@ def host_bam_decode_leg(n_pairs=1_000_000, contig_len=50_818_468, level=6):
                     best = st
     ncpu = os.cpu_count() or 1
     return {"reads": best["records"], "file_bytes": size, "uncompressed_bytes": best["uncompressed_bytes"],
-            "zlib_level": level, "seconds": best["decode_seconds"], "inflate_seconds": best["inflate_seconds"],
+            "zlib_level": level, "payload": payload, "seconds": best["decode_seconds"], "inflate_seconds": best["inflate_seconds"],
             "parse_seconds": best["parse_seconds"], "reads_per_s": best["records"] / best["decode_seconds"],
             "compressed_mb_per_s": size / best["decode_seconds"] / 1e6,
             "compressed_mb_per_s_per_thread": size / best["decode_seconds"] / 1e6 / ncpu,
@@ -1351,6 +1353,7 @@ def bench_coverage(args, env):
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "kernels": kern, "gen_seconds": gen_s, "checks": checks, "replicas": replicas,
             "host_bam_decode": host_bam_decode_leg(),
+            "host_bam_decode_realistic": host_bam_decode_leg(n_pairs=200_000, payload="random"),
         }
     return line, rc
 

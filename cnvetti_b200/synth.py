@@ -258,11 +258,14 @@ def _write_bai(path, n_ref, tids, beg, end, vbeg, vend):
         f.write(b"".join(out))
 
 
-def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, block_payload=0xff00, index=False):
+def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, block_payload=0xff00, index=False,
+              payload="filler"):
     """Write a coordinate-sorted BAM file.  `contigs`: [(name, length)]; `records`: one dict per contig (or
     None) with the BAM-level arrays of `synth_bam_records` (pos, isize, flag, mapq, cigar_off, cigar);
     an optional entry with key -1 in a dict `records` holds reads without a reference.  Read names,
-    sequences and qualities are fillers (the coverage path never looks at them).  The records are laid
+    sequences and qualities are fillers (the coverage path never looks at them): zeros and 0xFF, which deflate
+    15 : 1 -- payload="random" writes random bases and qualities drawn from eight bins instead (about 3 : 1, what
+    a sequencer's BAM file compresses to), the honest input for timing the decoder.  The records are laid
     out with numpy, so tens of millions of reads are practical."""
     import struct
     if isinstance(records, dict):
@@ -295,7 +298,13 @@ def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, blo
             l_seq = np.full(n, int(read_len), np.int64)
         size = 32 + l_name + 4 * ncig + (l_seq + 1) // 2 + l_seq          # block_size
         off = np.concatenate([[0], np.cumsum(size + 4)]).astype(np.int64)
-        buf = np.zeros(int(off[-1]), np.uint8)
+        if payload == "random":   # (sequence bytes; every fixed field, name, CIGAR and quality is written over it)
+            # (a random tile of 1 MiB + 13 bytes repeated: deflate's window is 32 KiB, it cannot see the repeats)
+            nib = np.array([1, 2, 4, 8], np.uint8)   # A C G T in the 4-bit code
+            two = np.random.default_rng(1000 + tid).integers(0, 16, (1 << 20) + 13, dtype=np.uint8)
+            buf = np.resize((nib[two >> 2] << 4) | nib[two & 3], int(off[-1]))
+        else:
+            buf = np.zeros(int(off[-1]), np.uint8)
         o = off[:-1]
 
         def put(at, val, nbytes):
@@ -317,6 +326,7 @@ def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, blo
         put(28, (pos + np.asarray(d["isize"], np.int64)) & 0xFFFFFFFF, 4)  # (filler)
         put(32, np.asarray(d["isize"], np.int64) & 0xFFFFFFFF, 4)
         idx = np.arange(n)
+        buf[o + 36 + l_name - 1] = 0
         buf[o + 36] = ord("r")
         for k in range(6):
             buf[o + 37 + k] = 48 + (idx // 10 ** (5 - k)) % 10
@@ -328,11 +338,15 @@ def write_bam(path, contigs, records, sample="SYN1", level=1, read_len=None, blo
             buf[base + k] = (cig >> (8 * k)) & 0xFF
         # qualities 0xFF (missing)
         qbase = o + 36 + l_name + 4 * ncig + (l_seq + 1) // 2
+        qrng = np.random.default_rng(2000 + tid)
+        qbins = np.array([2, 12, 18, 24, 28, 32, 36, 40], np.uint8)
+        qprob = [0.02, 0.02, 0.03, 0.05, 0.08, 0.15, 0.25, 0.40]
         if (l_seq == l_seq[0]).all():
-            buf[(qbase[:, None] + np.arange(int(l_seq[0]))[None, :]).ravel()] = 0xFF
+            qv = 0xFF if payload != "random" else np.resize(qbins[qrng.choice(8, size=(1 << 20) + 29, p=qprob)], n * int(l_seq[0]))
+            buf[(qbase[:, None] + np.arange(int(l_seq[0]))[None, :]).ravel()] = qv
         else:
             for i in range(n):
-                buf[qbase[i]:qbase[i] + l_seq[i]] = 0xFF
+                buf[qbase[i]:qbase[i] + l_seq[i]] = 0xFF if payload != "random" else qbins[qrng.choice(8, size=int(l_seq[i]), p=qprob)]
         chunks.append(buf)
         if index and tid >= 0:
             rl = np.where(np.isin(ops, (0, 2, 3, 7, 8)), lens, 0)
