@@ -465,6 +465,16 @@ def test_multi_sample_file_and_many_blocks(tmp_path):
             assert (g[present == 0].view(np.uint32) == MISS).all() and g.view(np.uint32)[17, 2] == MISS
             f2, fp = vf.format_ft()
             assert np.array_equal(f2, ft) and fp.sum() == 1
+    # every BGZF block is checked against its CRC-32 (the library's own inflater first, zlib behind it): a flipped
+    # payload bit that still inflates to the right length, and one in the stored checksum, are both refused
+    raw = bytearray(open(str(tmp_path / "merged.bcf"), "rb").read())
+    bsize = struct.unpack_from("<H", raw, 16)[0] + 1
+    for at in (bsize - 8, bsize + 18 + 4000):   # the first block's CRC field; deflate data of the second block
+        bad = bytearray(raw)
+        bad[at] ^= 0x10
+        open(str(tmp_path / "bad.bcf"), "wb").write(bytes(bad))
+        with pytest.raises(N.CnvbError, match="inflate|CRC"):
+            files.VariantFile(str(tmp_path / "bad.bcf"), threads=2)
     with gzip.open(str(tmp_path / "merged.vcf.gz"), "rt") as f:
         rows = [l for l in f if not l.startswith("#")]
     assert len(rows) == n and rows[5].split("\t")[8] == "GT:LCV:FT:CV"
