@@ -94,7 +94,8 @@ __attribute__((target("pclmul,sse4.1"))) uint32_t crc32_clmul(const uint8_t *buf
 }
 
 // ---- DEFLATE ----------------------------------------------------------------------------------------
-// table entry: value << 16 | kind << 12 | extra bits << 8 | code length
+// table entry: value << 16 | kind << 12 | extra bits << 8 | bits to drop (the code; for a length / distance entry the
+// code and its extra bits together)
 //   literal: value = the byte;  length / distance: value = base;  subtable: value = its offset, extra = its index bits
 // (Entries holding TWO literals where both codes fit the primary index were built and measured: no gain on BAM-like
 // data -- a sequencer's bases and binned qualities come out of zlib as short matches, not as runs of literals -- and a
@@ -180,7 +181,8 @@ bool build_table(const uint8_t *lens, uint32_t n, uint32_t bits, uint32_t *table
         const uint32_t l = lens[s];
         if (!l) continue;
         const uint32_t rev = reverse_bits(next[l]++, l);
-        const uint32_t e = sym_entry(s) | l;
+        const uint32_t se = sym_entry(s);
+        const uint32_t e = se | (l + ((se & kIsBase) ? ((se >> 8) & 15u) : 0u));  // base entries: code + extra bits
         if (l <= bits) {
             for (uint32_t i = rev; i < primary; i += 1u << l) table[i] = e;
         } else {
@@ -226,6 +228,12 @@ struct Bits {
     }
     inline size_t bits_used() const { return (size_t)(ip - in) * 8 - bc; }
 };
+
+// the extra bits of a length / distance entry: they follow its code in the bit buffer
+inline uint32_t extra_bits(uint64_t bb, uint32_t e) {
+    const uint32_t x = (e >> 8) & 15u;
+    return (uint32_t)(bb >> ((e & 255u) - x)) & ((1u << x) - 1u);
+}
 
 inline uint32_t lookup(const uint32_t *table, uint32_t bits, uint64_t bb) {
     uint32_t e = table[(uint32_t)bb & ((1u << bits) - 1u)];
@@ -364,12 +372,14 @@ __attribute__((always_inline)) inline bool inflate_impl(const uint8_t *in, size_
                     }
                     return false;
                 }
+                // (an entry's low byte counts the code AND its extra bits: one shift on the bit buffer's dependency
+                // chain; the extra bits are cut out of a copy beside it)
+                const uint32_t len = (e >> 16) + extra_bits(b.bb, e);
                 b.drop(e & 255u);
-                const uint32_t len = (e >> 16) + b.take((e >> 8) & 15u);
                 const uint32_t d = lookup(dist, kDistBits, b.bb);
                 if (__builtin_expect(!(d & kIsBase), 0)) return false;
+                const uint32_t back = (d >> 16) + extra_bits(b.bb, d);
                 b.drop(d & 255u);
-                const uint32_t back = (d >> 16) + b.take((d >> 8) & 15u);
                 if (__builtin_expect(back > (size_t)(op - out), 0)) return false;
                 const uint8_t *src = op - back;
                 uint8_t *dst = op;
@@ -408,12 +418,12 @@ __attribute__((always_inline)) inline bool inflate_impl(const uint8_t *in, size_
                 break;
             }
             if (!(e & kIsBase)) return false;
+            const uint32_t len = (e >> 16) + extra_bits(b.bb, e);
             b.drop(e & 255u);
-            const uint32_t len = (e >> 16) + b.take((e >> 8) & 15u);
             const uint32_t d = lookup(dist, kDistBits, b.bb);
             if (!(d & kIsBase)) return false;
+            const uint32_t back = (d >> 16) + extra_bits(b.bb, d);
             b.drop(d & 255u);
-            const uint32_t back = (d >> 16) + b.take((d >> 8) & 15u);
             if (back > (size_t)(op - out) || len > (size_t)(out_end - op)) return false;
             const uint8_t *src = op - back;
             for (uint32_t i = 0; i < len; ++i) op[i] = src[i];
