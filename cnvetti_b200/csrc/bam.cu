@@ -71,7 +71,9 @@ struct HostColumn {  // growing array; page-locked in place once the decode is c
     // front and copying on every growth step cost 80 ms per 2 M reads
     void pin() {
         if (pinned || !p || !n) return;
-        if (cudaHostRegister(p, cap * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) pinned = true; else cudaGetLastError();
+        // (the rows in use, not the capacity the doubling left behind: page-locking costs by the page)
+        const uint64_t bytes = std::min<uint64_t>(cap * sizeof(T), (n * sizeof(T) + 4095u) & ~uint64_t(4095));
+        if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) pinned = true; else cudaGetLastError();
     }
     void unpin() {
         if (pinned) cudaHostUnregister(p);
