@@ -993,6 +993,17 @@ def bench_cfg5(args, env, steps=None, warmup=None):
     env.free()
     if rank != 0:
         return None
+    try:  # the calls + mod-coverage pass: k reference rows' values per (target, sample) once, five f32 + one u8 out
+        pk = kern.get("modcov_panel_kernel")
+        if pk and pk.get("ms_per_step") and rows_n:
+            hbm, _ = measured_peak()
+            pbytes = float(rows_n) * S * (100 * 4 + 4 + 21)
+            pk["hbm"] = {"algorithmic_bytes": pbytes, "achieved": pbytes / (pk["ms_per_step"] * 1e-3) / 1e9, "unit": "GB/s",
+                         "frac": pbytes / (pk["ms_per_step"] * 1e-3) / 1e9 / hbm, "peak": hbm,
+                         "what": "rank 0's rows x samples x (100 reference values + the target's own, 4 B each, + 21 B out); "
+                                 "bound by latency at 8 warps per SM and the f32 -> f64 conversions, not by HBM (DESIGN 4.9)"}
+    except Exception as exc:  # (a side figure must not cost the line)
+        env.log("panel kernel figure skipped: %r" % (exc,))
     return {"metric": "WIS bin-pairs/s", "value": float(T) * T / (ms * 1e-3), "unit": "bin-pairs/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (fp16 tensor filter + exact f32 re-score), f64 statistics, i32 HMM scores",
