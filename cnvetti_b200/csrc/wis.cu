@@ -409,6 +409,8 @@ __device__ __forceinline__ double widen_normal_f32(uint32_t b) {
 // cycles, two warps x two conversions x 8).  The odd columns of a lane are therefore widened f32 -> f64 with integer
 // instructions (same bits for normal numbers: sign, exponent + 896, mantissa << 29; a column in which the first
 // pass sees a zero, a subnormal, an infinity or a NaN is redone with F2F), the even ones on the conversion pipe.
+// SPL = 2 up to k = 105 (205 KB at k = 100), SPL = 1 up to k = 199, the unstaged form beyond.  The staging area is
+// reused for the transposed outputs of the chunk.  Arithmetic and its order are unchanged: identical bits.
 enum PanelMode { kPanelPlain = 0, kPanelAsync = 1, kPanelBulk = 2, kPanelAsync16 = 3 };
 constexpr uint32_t kPanelGroup = 32, kPanelThreads = 256, kPanelWarps = kPanelThreads / 32;
 constexpr size_t panel_out_bytes(uint32_t spl) { return (size_t)5 * 32 * spl * (kPanelGroup + 1) * sizeof(float); }

@@ -120,7 +120,7 @@ def test_modcov_parity(oracle, ctx, device):
     (3000, 12, True, 50, {}), (1037, 70, False, 50, {}), (40, 33, True, 40, {}),    # 16-byte / 4-byte (S % 4 != 0) cp.async, 64-sample chunks
     (1200, 136, True, 100, {}), (1200, 136, True, 100, {"CNVB_PANEL_STAGE": "1"}),   # three chunks, the last one partial
     (1200, 136, True, 100, {"CNVB_PANEL_STAGE": "2"}), (1037, 72, True, 50, {"CNVB_PANEL_STAGE": "2", "CNVB_PANEL_SPL": "1"}),
-    (1500, 40, True, 150, {}), (900, 45, True, 150, {}),                             # 32-sample chunks (105 < k <= 210)
+    (1500, 40, True, 150, {}), (900, 45, True, 150, {}),                             # 32-sample chunks (105 < k <= 199)
     (1037, 72, True, 50, {"CNVB_PANEL_SPL": "1"}),
     (1200, 45, True, 230, {}), (1037, 70, True, 50, {"CNVB_PANEL_STAGE": "0"})])     # the unstaged kernel
 def test_modcov_panel_matches_per_sample_oracle(oracle, ctx, monkeypatch, T, S, device, k, env):
