@@ -624,12 +624,17 @@ int decode(cnvb_bam *b, float min_unclipped, bool pinned, bool header_only, cons
             break;
         }
         std::atomic<int> bad{0};
-        run_parallel(b->n_threads, blocks.size(), [&](uint64_t lo, uint64_t hi, int) {
+        // (blocks are handed out four at a time from a shared cursor: their decode times differ, and the helper
+        // thread's parse of the previous chunk takes cores away unevenly)
+        std::atomic<uint64_t> cursor{0};
+        const uint64_t n_blocks = blocks.size();
+        run_parallel(b->n_threads, (uint64_t)std::max(1, b->n_threads), [&](uint64_t, uint64_t, int) {
             // hostz.cpp's decoder first (a BGZF block is one buffer of known size); zlib for whatever it refuses
             // or gets wrong by the block's CRC-32 -- zlib's verdict is the one that stands
             z_stream zs;
             bool zs_init = false;
-            for (uint64_t i = lo; i < hi; ++i) {
+            for (uint64_t i0 = cursor.fetch_add(4); i0 < n_blocks; i0 = cursor.fetch_add(4))
+            for (uint64_t i = i0; i < std::min(n_blocks, i0 + 4); ++i) {
                 const Block &bl = blocks[i];
                 if (bl.isize == 0) continue;
                 uint8_t *dst = ub->data() + kHead + bl.uoff;
