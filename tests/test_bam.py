@@ -120,6 +120,50 @@ def test_bam_decoder_paths_agree(tmp_path, monkeypatch, env, level, block_payloa
             _check(r.fetch(t), _expected(recs[t], 0.6))
 
 
+def test_bam_walk_rejects_a_wrong_guess(tmp_path, monkeypatch):
+    """The threaded record walk guesses record starts; here the guess MUST be wrong: one record's quality string is
+    made of byte patterns that look like a chain of small records, and it is long enough for every share boundary
+    to fall inside it.  The share in which that record ends begins its walk at a fake record, the join sees that the
+    walk before it ends elsewhere and walks the share again: the columns are those of the serial walk."""
+    import struct
+    from cnvetti_b200.synth import _bgzf_block
+
+    def record(pos, l_seq, qual=None, mapq=30, flag=0, tlen=0):
+        name = b"q\0"
+        cigar = struct.pack("<I", (l_seq << 4) | 0)
+        body = struct.pack("<iiBBHHHiiii", 0, pos, len(name), mapq, 4680, 1, flag, l_seq, -1, -1, tlen) + name + cigar + \
+            bytes((l_seq + 1) // 2) + (qual if qual is not None else b"\xff" * l_seq)
+        return struct.pack("<I", len(body)) + body
+
+    fake = struct.pack("<IiiBBHHHiiii", 40, 0, 7, 4, 0, 0, 0, 0, 0, -1, -1, 0) + b"abc\0" + bytes(4)   # 44 bytes, chains on
+    assert len(fake) == 44
+    L = 44 * 1500
+    recs = [record(10 + i, 50) for i in range(20)] + [record(40, L, qual=fake * 1500)] + [record(100 + 3 * i, 60) for i in range(400)]
+    text = b"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chr1\tLN:100000\n"
+    stream = b"BAM\x01" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1) + struct.pack("<I", 5) + b"chr1\0" + \
+        struct.pack("<I", 100000) + b"".join(recs)
+    path = str(tmp_path / "fake.bam")
+    with open(path, "wb") as f:
+        for a in range(0, len(stream), 0xff00):
+            f.write(_bgzf_block(stream[a:a + 0xff00], 6))
+        f.write(_bgzf_block(b"", 6))
+    out = {}
+    for mode, env in (("serial", {"CNVB_BAM_SERIAL_WALK": "1"}), ("threads", {"CNVB_BAM_WALK_SHARE": "64"})):
+        for key in ("CNVB_BAM_SERIAL_WALK", "CNVB_BAM_WALK_SHARE"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        with bam.BamReader(path, threads=4) as r:
+            r.decode(min_unclipped=0.6, pinned=False)
+            assert r.stats()["records"] == len(recs)
+            got = r.fetch(0)
+            out[mode] = {k: np.asarray(getattr(got, k)).copy() for k in ("pos", "end", "mid", "frag_end", "mapq", "flags")}
+    assert out["serial"]["pos"].tolist() == [10 + i for i in range(20)] + [40] + [100 + 3 * i for i in range(400)]
+    assert out["serial"]["end"][20] == 40 + L
+    for k, v in out["serial"].items():
+        assert np.array_equal(out["threads"][k], v), k
+
+
 def test_bam_errors_are_loud(tmp_path):
     with pytest.raises(bam.BamError, match="Could not open"):
         bam.BamReader(str(tmp_path / "missing.bam"))
