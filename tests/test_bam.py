@@ -120,6 +120,22 @@ def test_bam_decoder_paths_agree(tmp_path, monkeypatch, env, level, block_payloa
             _check(r.fetch(t), _expected(recs[t], 0.6))
 
 
+def test_bam_realistic_payload_decodes_to_the_same_columns(tmp_path):
+    """synth.write_bam(payload="random") -- random bases and binned qualities, the file the bench times the decoder
+    on beside the filler one -- holds the same records: same columns, a compression ratio a sequencer's file has."""
+    d = synth.synth_bam_records(31, 400_000, 20_000)
+    a = synth.write_bam(str(tmp_path / "filler.bam"), [("chr1", 400_000)], [d], level=6)
+    b = synth.write_bam(str(tmp_path / "random.bam"), [("chr1", 400_000)], [d], level=6, payload="random")
+    ratio = []
+    for path in (a, b):
+        with bam.BamReader(path, threads=2) as r:
+            r.decode(min_unclipped=0.6, pinned=False)
+            st = r.stats()
+            ratio.append(st["uncompressed_bytes"] / st["compressed_bytes"])
+            _check(r.fetch(0), _expected(d, 0.6))   # (the columns belong to the reader: compared while it is open)
+    assert ratio[0] > 8 and 1.5 < ratio[1] < 4
+
+
 def test_bam_walk_rejects_a_wrong_guess(tmp_path, monkeypatch):
     """The threaded record walk guesses record starts; here the guess MUST be wrong: one record's quality string is
     made of byte patterns that look like a chain of small records, and it is long enough for every share boundary
