@@ -368,7 +368,7 @@ def file_level_leg(n_pairs=1_000_000, contig_len=50_818_468):
     d = synth.synth_bam_records(22, L, n_pairs)
     opts = cb.CoverageOptions(window_length=1000, min_mapq=MIN_MAPQ)
     with tempfile.TemporaryDirectory() as tmp:
-        path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("22", L)], [d])
+        path = synth.write_bam(os.path.join(tmp, "synth.bam"), [("22", L)], [d], level=6)  # (htslib's default level)
         out = os.path.join(tmp, "cov.vcf.gz")
         timings = None
         for _ in range(2):
